@@ -1,0 +1,213 @@
+/*
+ * b200reg.h -- C ABI of libb200reg.so: the B200-native (sm_100a) Demons registration, resampling and
+ * label-fusion engine that replaces the SimpleITK/ITK filters on platipy's hot path.
+ *
+ * The reference has no C/FFI boundary on this path: its boundary is the Python call signature
+ * (platipy/imaging/registration/deformable.py:190, utils.py:148,195; platipy/imaging/label/fusion.py:205,239).
+ * Each entry point below replaces the ITK filter(s) behind one reference call site, cited as
+ * file:line relative to the reference repository root.  `platipy_b200/_abi.py` is the ctypes binding;
+ * INTEGRATION.md shows the stub a platipy maintainer would add.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer named d_* is DEVICE memory, h_* is HOST memory.
+ *  - scalar volumes are C-order [z][y][x] (x fastest) == numpy view of a SimpleITK image.
+ *  - displacement fields on the device are SoA: three contiguous f64 planes [3][z][y][x] holding
+ *    (dx, dy, dz) in physical mm.  b200reg_aos_to_soa / b200reg_soa_to_aos convert from/to the AoS
+ *    [z][y][x][3] layout of a sitkVectorFloat64 image.
+ *  - all work is enqueued on the context's CUDA stream; calls return without synchronising unless
+ *    stated.  Every call returns a b200reg_status; b200reg_last_error() gives the thread-local text.
+ *  - no exceptions cross the ABI; the caller owns every buffer it passes.
+ */
+#ifndef B200REG_H
+#define B200REG_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200REG_ABI_VERSION 1
+#define B200REG_MAX_TRANSFORMS 4
+#define B200REG_MAX_LEVELS 8
+#define B200REG_MAX_BATCH 64
+
+typedef struct b200reg_ctx b200reg_ctx;
+
+typedef enum {
+    B200REG_OK = 0,
+    B200REG_ERR_CUDA = 1,        /* CUDA runtime error (text in b200reg_last_error) */
+    B200REG_ERR_ARG = 2,         /* invalid argument                              -> ValueError   */
+    B200REG_ERR_UNSUPPORTED = 3, /* e.g. B-spline interpolation                   -> NotImplementedError */
+    B200REG_ERR_RUNTIME = 4      /* ITK-style runtime failure (e.g. line < 4 px)  -> RuntimeError */
+} b200reg_status;
+
+/* SimpleITK pixel IDs (Linux builds) */
+typedef enum {
+    B200REG_I8 = 0, B200REG_U8 = 1, B200REG_I16 = 2, B200REG_U16 = 3, B200REG_I32 = 4, B200REG_U32 = 5,
+    B200REG_I64 = 6, B200REG_U64 = 7, B200REG_F32 = 8, B200REG_F64 = 9
+} b200reg_dtype;
+
+/* sitkNearestNeighbor / sitkLinear (deformable.py:221-224) */
+typedef enum { B200REG_INTERP_NN = 1, B200REG_INTERP_LINEAR = 2 } b200reg_interp;
+
+/* itk::ImageBase geometry: size (x,y,z), spacing, origin, direction cosines (row-major 3x3) */
+typedef struct {
+    int32_t size[3];
+    double spacing[3];
+    double origin[3];
+    double direction[9];
+} b200reg_geom;
+
+typedef enum { B200REG_TFM_AFFINE = 0, B200REG_TFM_DVF = 1 } b200reg_tfm_kind;
+
+/* One element of a transform chain, in APPLICATION order (first applied first; the reverse of
+ * sitk.CompositeTransform's add order).  AFFINE: p' = matrix * p + offset
+ * (itk::MatrixOffsetTransformBase).  DVF: p' = p + D(p), identity outside the field buffer
+ * (itk::DisplacementFieldTransform; deformable.py:139,296). */
+typedef struct {
+    int32_t kind;
+    int32_t pad;
+    double matrix[9];
+    double offset[3];
+    const double* d_dvf;      /* device, SoA [3][z][y][x] f64 */
+    b200reg_geom dvf_geom;
+} b200reg_transform;
+
+/* sitk.FastSymmetricForcesDemonsRegistrationFilter parameters as platipy leaves them
+ * (deformable.py:244-257; everything it does not set keeps the SimpleITK default). */
+typedef struct {
+    double std_dev[3];            /* SetStandardDeviations, voxel units (deformable.py:253-257) */
+    double update_std_dev[3];     /* UpdateFieldStandardDeviations, default 1.0 */
+    int32_t smooth_displacement_field; /* deformable.py:250 */
+    int32_t smooth_update_field;       /* deformable.py:249 */
+    double max_error;             /* 0.1 */
+    int32_t max_kernel_width;     /* 30 */
+    int32_t number_of_iterations; /* deformable.py:143-144 */
+    double max_rms_error;         /* 0.02 */
+    double max_update_step_length;        /* 0.5 */
+    double intensity_difference_threshold; /* 0.001 */
+    double denominator_threshold;          /* 1e-9 */
+} b200reg_demons_params;
+
+typedef struct {
+    int32_t elapsed_iterations;   /* GetElapsedIterations() (utils.py:41) */
+    int32_t voxels_lo;            /* voxels of the level grid (low 31 bits are enough for one GPU) */
+    double metric;                /* GetMetric(): SSD / N of the last iteration */
+    double rms_change;            /* GetRMSChange() */
+    double gpu_ms;                /* device time of the level's Demons loop (CUDA events) */
+} b200reg_demons_stats;
+
+/* multiscale_demons configuration (deformable.py:31-42) */
+typedef struct {
+    int32_t n_levels;
+    int32_t isotropic_resample;               /* resolution = voxel size in mm instead of shrink factor */
+    double resolution_staging[B200REG_MAX_LEVELS];
+    double smoothing_sigmas[B200REG_MAX_LEVELS];   /* mm; 0 = no smoothing (utils.py:216) */
+    int32_t iteration_staging[B200REG_MAX_LEVELS];
+    int32_t interp_order;                     /* b200reg_interp */
+    b200reg_demons_params demons;             /* number_of_iterations is overwritten per level */
+} b200reg_multires_config;
+
+/* ---- context ------------------------------------------------------------------------------------ */
+int b200reg_abi_version(void);
+const char* b200reg_last_error(void);
+/* device: CUDA ordinal; stream: a cudaStream_t (NULL = a new non-blocking stream owned by the ctx) */
+int b200reg_create(int device, void* stream, b200reg_ctx** out);
+int b200reg_destroy(b200reg_ctx* ctx);
+int b200reg_set_stream(b200reg_ctx* ctx, void* stream);
+int b200reg_synchronize(b200reg_ctx* ctx);
+/* number of kernels this context has launched since creation (bench.py's gpu_launches) */
+int64_t b200reg_launch_count(b200reg_ctx* ctx);
+
+/* ---- memory helpers (hosts without their own CUDA allocator) --------------------------------------- */
+int b200reg_malloc(b200reg_ctx* ctx, size_t bytes, void** d_ptr);
+int b200reg_free(b200reg_ctx* ctx, void* d_ptr);
+int b200reg_malloc_host(size_t bytes, void** h_ptr);   /* pinned */
+int b200reg_free_host(void* h_ptr);
+int b200reg_memcpy_h2d(b200reg_ctx* ctx, void* d_dst, const void* h_src, size_t bytes);
+int b200reg_memcpy_d2h(b200reg_ctx* ctx, void* h_dst, const void* d_src, size_t bytes);
+int b200reg_memset(b200reg_ctx* ctx, void* d_ptr, int value, size_t bytes);
+
+/* ---- layout / dtype helpers ------------------------------------------------------------------------- */
+int b200reg_aos_to_soa(b200reg_ctx* ctx, const double* d_aos, double* d_soa, size_t nvox);
+int b200reg_soa_to_aos(b200reg_ctx* ctx, const double* d_soa, double* d_aos, size_t nvox);
+/* sitk.Cast (deformable.py:239,241,304; utils.py:190): C static_cast, float->int truncates toward zero */
+int b200reg_cast(b200reg_ctx* ctx, const void* d_in, int in_dtype, void* d_out, int out_dtype, size_t n);
+/* min / max of a scalar volume as double (deformable.py:290 CT-like test; RescaleIntensity). Synchronises. */
+int b200reg_minmax(b200reg_ctx* ctx, const void* d_in, int dtype, size_t n, double* h_min, double* h_max);
+
+/* ---- N1: itk::DiscreteGaussianImageFilter (utils.py:226; fusion.py:168,279) ------------------------- */
+int b200reg_discrete_gaussian_f32(b200reg_ctx* ctx, const float* d_in, float* d_out, const b200reg_geom* geom,
+                                  const double variance[3], int max_kernel_width, double max_error, int use_image_spacing);
+/* GaussianOperator coefficients (host-side; used by tests): returns radius, fills kernel[0..2r] */
+int b200reg_gaussian_operator(double variance, double max_error, int max_kernel_width, double* h_kernel, int capacity);
+
+/* ---- N2/N5/N9: itk::ResampleImageFilter, scalar (utils.py:176-190,257-267; deformable.py:140,281-301) */
+int b200reg_resample(b200reg_ctx* ctx, const void* d_in, int dtype, const b200reg_geom* in_geom, void* d_out,
+                     const b200reg_geom* out_geom, const b200reg_transform* chain, int n_chain, int interp,
+                     double default_value);
+/* Batched form: n images on the same input grid through the same chain onto the same output grid
+ * (multiatlas/run.py:331-345: one CT + S label masks).  The chain (and the DVF behind it) is evaluated
+ * once per output voxel. */
+int b200reg_resample_batch(b200reg_ctx* ctx, int n, const void* const* d_in, const int* dtypes, const b200reg_geom* in_geom,
+                           void* const* d_out, const b200reg_geom* out_geom, const b200reg_transform* chain, int n_chain,
+                           const int* interps, const double* default_values);
+/* ---- N3/N7: itk::ResampleImageFilter on a VectorFloat64 image (deformable.py:130,137,154,185) -------- */
+int b200reg_resample_vec3(b200reg_ctx* ctx, const double* d_in_soa, const b200reg_geom* in_geom, double* d_out_soa,
+                          const b200reg_geom* out_geom, const b200reg_transform* chain, int n_chain, double default_value);
+/* dvf_total + sitk.Resample(dvf_iter, tfm_total) (deformable.py:154), d_total updated in place.
+ * d_scratch_soa: 3 planes on the same grid. */
+int b200reg_compose_dvf(b200reg_ctx* ctx, double* d_total_soa, const double* d_iter_soa, const b200reg_geom* geom,
+                        double* d_scratch_soa);
+
+/* ---- N6: sitk.FastSymmetricForcesDemonsRegistrationFilter.Execute (deformable.py:149) ---------------- */
+/* Starts from a zero field on the fixed grid; d_out_soa receives the field.  h_stats is filled after an
+ * internal stream synchronisation. */
+int b200reg_demons_execute(b200reg_ctx* ctx, const float* d_fixed, const b200reg_geom* fixed_geom, const float* d_moving,
+                           const b200reg_geom* moving_geom, const b200reg_demons_params* params, double* d_out_soa,
+                           b200reg_demons_stats* h_stats);
+/* One InitializeIteration + CalculateChange (warp + ESM force), for unit parity tests: d_w (f32 warped
+ * moving, FLT_MAX outside), d_u_soa (raw update); h_metric / h_rms after synchronisation. */
+int b200reg_demons_force(b200reg_ctx* ctx, const float* d_fixed, const b200reg_geom* fixed_geom, const float* d_moving,
+                         const b200reg_geom* moving_geom, const double* d_field_soa, const b200reg_demons_params* params,
+                         float* d_w, double* d_u_soa, double* h_metric, double* h_rms);
+/* PDEDeformableRegistrationFilter::SmoothDisplacementField on its own (x -> y -> z, voxel-unit sigmas) */
+int b200reg_pde_smooth_field(b200reg_ctx* ctx, double* d_field_soa, const b200reg_geom* geom, const double std_dev[3],
+                             double max_error, int max_kernel_width);
+
+/* ---- N8: sitk.SmoothingRecursiveGaussian on a VectorFloat64 image (deformable.py:158) ----------------- */
+int b200reg_recursive_gaussian_vec3(b200reg_ctx* ctx, double* d_field_soa, const b200reg_geom* geom, const double sigma[3]);
+
+/* ---- a2: multiscale_demons (deformable.py:31-187), device resident ------------------------------------ */
+/* d_initial_soa may be NULL (zero field).  d_out_soa: field on the fixed grid.  h_level_stats[n_levels]
+ * filled after an internal synchronisation. */
+int b200reg_multiscale_demons(b200reg_ctx* ctx, const float* d_fixed, const b200reg_geom* fixed_geom, const float* d_moving,
+                              const b200reg_geom* moving_geom, const b200reg_multires_config* cfg,
+                              const double* d_initial_soa, const b200reg_geom* initial_geom, double* d_out_soa,
+                              b200reg_demons_stats* h_level_stats);
+/* utils.py:195-267 smooth_and_resample output grid: size = int(sz/f + 0.5), align-corners spacing */
+int b200reg_pyramid_geom(const b200reg_geom* in_geom, int isotropic, double resolution, b200reg_geom* out_geom);
+
+/* ---- N12/N13: label fusion (fusion.py:56-202, 239-292) -------------------------------------------------- */
+/* compute_weight_map: vote_type 0 = unweighted, 1 = global (factor / sum SSD), 2 = local (1/(G*SD + eps)) */
+int b200reg_weight_map(b200reg_ctx* ctx, const float* d_target, const float* d_moving, const b200reg_geom* geom, int vote_type,
+                       double factor, double sigma, double epsilon, float* d_weight);
+/* acc_num += w * label ; acc_den += w  (fusion.py:263,269-276), f32 arithmetic in atlas order */
+int b200reg_vote_accumulate(b200reg_ctx* ctx, const uint8_t* d_label, const float* d_weight, float* d_acc_num,
+                            float* d_acc_den, size_t n, int first);
+/* num / guarded den -> DiscreteGaussian(var) -> RescaleIntensity(0,1) -> Threshold (fusion.py:264-288).
+ * d_num is overwritten; d_out may alias d_num.  Synchronises (global min/max). */
+int b200reg_vote_finalize(b200reg_ctx* ctx, float* d_num, const float* d_den, const b200reg_geom* geom,
+                          double smooth_variance, double threshold, float* d_out);
+/* ---- N14: sitk.STAPLE + RescaleIntensity + Threshold (fusion.py:217-232) --------------------------------- */
+/* d_decisions: n_raters pointers (host array of device pointers) to u8 volumes already binarised
+ * (>= 0.5).  d_out: f64.  h_pq (optional): 2*n_raters doubles (p then q).  Synchronises. */
+int b200reg_staple(b200reg_ctx* ctx, const uint8_t* const* d_decisions, int n_raters, size_t n, double confidence_weight,
+                   uint32_t max_iterations, double threshold, int rescale, double* d_out, double* h_pq, int32_t* h_elapsed);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200REG_H */

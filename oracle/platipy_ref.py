@@ -1,0 +1,268 @@
+"""
+CPU restatement of the reference's Python glue on the hot path -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+PARITY UNPINNED (see ``itk_oracle.c``).  Function names and argument meaning follow the reference
+(paths relative to /root/reference):
+
+  smooth_and_resample                          platipy/imaging/registration/utils.py:195-267
+  apply_transform                              platipy/imaging/registration/utils.py:148-192
+  multiscale_demons                            platipy/imaging/registration/deformable.py:31-187
+  fast_symmetric_forces_demons_registration    platipy/imaging/registration/deformable.py:190-306
+  compute_weight_map / combine_labels / combine_labels_staple   platipy/imaging/label/fusion.py:56-292
+
+Every ITK filter call in those functions is replaced by the corresponding routine of ``itk_oracle``.
+Images are ``platipy_b200.sitk_compat.Image`` containers (data holders only; no product compute).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from platipy_b200 import sitk_compat as sk
+from platipy_b200.sitk_compat import Image
+
+from . import itk_oracle as orc
+
+
+def _like(arr, ref, is_vector=False):
+    return Image(arr, ref.GetSpacing(), ref.GetOrigin(), ref.GetDirection(), is_vector)
+
+
+def _chain_of(transform):
+    """sitk transform object -> oracle chain in application order."""
+    chain = []
+    if transform is None:
+        return chain
+    for t in transform.flatten():
+        if isinstance(t, sk.DisplacementFieldTransform):
+            f = t.GetDisplacementField()
+            chain.append(("dvf", f.array, orc.geom_of(f)))
+        else:
+            chain.append(("affine", t.matrix, t.offset))
+    return chain
+
+
+def resample(image, reference_geom_image=None, transform=None, interpolator=sk.sitkLinear, default_value=0.0,
+             size=None, spacing=None, origin=None, direction=None):
+    """sitk.Resample in the three call forms the reference uses."""
+    if reference_geom_image is None:
+        reference_geom_image = image
+    if size is None:
+        gout = orc.geom_of(reference_geom_image)
+        sp, og, dr = reference_geom_image.GetSpacing(), reference_geom_image.GetOrigin(), reference_geom_image.GetDirection()
+    else:
+        gout = orc.make_geom(size, spacing, origin, direction)
+        sp, og, dr = spacing, origin, direction
+    gin = orc.geom_of(image)
+    chain = _chain_of(transform)
+    if image.is_vector:
+        out = orc.resample_vec3(image.array, gin, gout, chain, default_value)
+        return Image(out, sp, og, dr, True)
+    if interpolator not in (sk.sitkNearestNeighbor, sk.sitkLinear):
+        raise NotImplementedError("oracle: only nearest-neighbour and linear interpolation")
+    out = orc.resample_scalar(image.array, gin, gout, chain, interpolator, default_value)
+    return Image(out, sp, og, dr, False)
+
+
+def smooth_and_resample(image, isotropic_voxel_size_mm=None, shrink_factor=None, smoothing_sigma=None,
+                        interpolator=sk.sitkLinear):
+    # utils.py:216-226: variance = sigma^2 (mm^2); max kernel width = int(max(8 * var_i * spacing_i))
+    if smoothing_sigma:
+        if hasattr(smoothing_sigma, "__iter__"):
+            variance = [s * s for s in smoothing_sigma]
+        else:
+            variance = (smoothing_sigma ** 2,) * 3
+        max_width = int(max(8 * v * sp for sp, v in zip(image.GetSpacing(), variance)))
+        if image.array.dtype != np.float32:
+            raise NotImplementedError("oracle: DiscreteGaussian restated for Float32 images")
+        image = _like(orc.discrete_gaussian_f32(image.array, orc.geom_of(image), variance, max_width), image)
+
+    size_o, spacing_o = image.GetSize(), image.GetSpacing()
+    # utils.py:231-250
+    if shrink_factor and isotropic_voxel_size_mm:
+        raise AttributeError("Function must be called with either isotropic_voxel_size_mm or shrink_factor, not both.")
+    elif isotropic_voxel_size_mm:
+        scale = isotropic_voxel_size_mm * np.ones_like(size_o) / np.array(spacing_o)
+        size_n = [int(sz / float(sf) + 0.5) for sz, sf in zip(size_o, scale)]
+    elif shrink_factor:
+        if isinstance(shrink_factor, list):
+            size_n = [int(sz / float(sf) + 0.5) for sz, sf in zip(size_o, shrink_factor)]
+        else:
+            size_n = [int(sz / float(shrink_factor) + 0.5) for sz in size_o]
+    else:
+        return image
+    # utils.py:252-255: align-corners spacing
+    spacing_n = [((so - 1) * sp) / (sn - 1) for so, sp, sn in zip(size_o, spacing_o, size_n)]
+    # utils.py:257-267: identity transform, default pixel 0.0, same pixel type
+    return resample(image, transform=None, interpolator=interpolator, default_value=0.0, size=size_n,
+                    spacing=spacing_n, origin=image.GetOrigin(), direction=image.GetDirection())
+
+
+def apply_transform(input_image, reference_image=None, transform=None, default_value=0, interpolator=sk.sitkNearestNeighbor):
+    # utils.py:174-190; output pixel type = input pixel type (Resample), Cast back is then a no-op
+    ref = reference_image if reference_image else input_image
+    return resample(input_image, ref, transform, interpolator, default_value)
+
+
+class DemonsFilter:
+    """The method set of sitk.FastSymmetricForcesDemonsRegistrationFilter that the reference uses
+    (deformable.py:244-257,143-149,157; utils.py:41), on the oracle's Demons loop."""
+
+    def __init__(self):
+        self.std_dev = [1.0, 1.0, 1.0]
+        self.iterations = 10
+        self.smooth_update = False
+        self.smooth_field = True
+        self.stats = None
+
+    def SetNumberOfThreads(self, n):
+        pass
+
+    def SetSmoothUpdateField(self, flag):
+        self.smooth_update = bool(flag)
+
+    def SetSmoothDisplacementField(self, flag):
+        self.smooth_field = bool(flag)
+
+    def SetStandardDeviations(self, sd):
+        self.std_dev = [float(sd)] * 3 if np.isscalar(sd) else [float(s) for s in sd]
+
+    def GetStandardDeviations(self):
+        return tuple(self.std_dev)
+
+    def SetNumberOfIterations(self, n):
+        self.iterations = int(n)
+
+    def GetElapsedIterations(self):
+        return self.stats["elapsed_iterations"]
+
+    def GetMetric(self):
+        return self.stats["metric"]
+
+    def GetRMSChange(self):
+        return self.stats["rms_change"]
+
+    def Execute(self, fixed, moving):
+        params = orc.demons_params(self.std_dev, self.iterations, smooth_displacement_field=self.smooth_field,
+                                   smooth_update_field=self.smooth_update)
+        D, self.stats = orc.demons_execute(fixed.array, orc.geom_of(fixed), moving.array, orc.geom_of(moving), params)
+        return _like(D, fixed, True)
+
+
+def multiscale_demons(registration_algorithm, fixed_image, moving_image, initial_transform=None,
+                      initial_displacement_field=None, isotropic_resample=None, resolution_staging=None,
+                      smoothing_sigmas=None, iteration_staging=None, interp_order=sk.sitkLinear, level_stats=None):
+    # deformable.py:67-94: pyramid from the original images for every level
+    fixed_images, moving_images = [], []
+    for resolution, sigma in zip(resolution_staging, smoothing_sigmas):
+        kw = {"isotropic_voxel_size_mm": resolution} if isotropic_resample else {"shrink_factor": resolution}
+        fixed_images.append(smooth_and_resample(fixed_image, smoothing_sigma=sigma, interpolator=interp_order, **kw))
+        moving_images.append(smooth_and_resample(moving_image, smoothing_sigma=sigma, interpolator=interp_order, **kw))
+
+    # deformable.py:99-125
+    if not initial_displacement_field:
+        if initial_transform:
+            raise NotImplementedError("oracle: TransformToDisplacementField (no in-repo caller passes initial_transform)")
+        zeros = np.zeros(fixed_image.array.shape + (3,), dtype=np.float64)
+        initial_displacement_field = _like(zeros, fixed_image, True)
+    else:
+        initial_displacement_field = resample(initial_displacement_field, fixed_image)
+
+    dvf_total = resample(initial_displacement_field, fixed_image)  # :130
+    for f_image, m_image, iters in zip(fixed_images, moving_images, iteration_staging):
+        dvf_total = resample(dvf_total, f_image)  # :137
+        tfm_total = sk.DisplacementFieldTransform(sk.Cast(dvf_total, sk.sitkVectorFloat64))  # :139
+        m_image = resample(m_image, m_image, tfm_total, interp_order, 0.0)  # :140
+        registration_algorithm.SetNumberOfIterations(iters)  # :143-144
+        dvf_iter = registration_algorithm.Execute(f_image, m_image)  # :149
+        if level_stats is not None:
+            level_stats.append(dict(registration_algorithm.stats, voxels=f_image.GetNumberOfPixels()))
+        warped_iter = resample(dvf_iter, dvf_iter, tfm_total)  # :154  Resample(dvf_iter, tfm_total)
+        dvf_total = _like(dvf_total.array + warped_iter.array, dvf_total, True)
+        sigma = registration_algorithm.GetStandardDeviations()  # :157
+        dvf_total = _like(orc.recursive_gaussian_vec3(dvf_total.array, orc.geom_of(dvf_total), sigma), dvf_total, True)  # :158
+    return resample(dvf_total, fixed_image)  # :185
+
+
+def fast_symmetric_forces_demons_registration(fixed_image, moving_image, resolution_staging=[8, 4, 1],
+                                              iteration_staging=[10, 10, 10], isotropic_resample=False,
+                                              initial_displacement_field=None, regularisation_kernel_mm=1.5,
+                                              smoothing_sigma_factor=1, smoothing_sigmas=False, default_value=None,
+                                              ncores=1, interp_order=sk.sitkLinear, verbose=False, level_stats=None):
+    moving_type = moving_image.GetPixelID()
+    # deformable.py:238-241 (pixel id 6 is Int64: the quirk is kept)
+    if fixed_image.GetPixelID() != 6:
+        fixed_image = sk.Cast(fixed_image, sk.sitkFloat32)
+    if moving_image.GetPixelID() != 6:
+        moving_image = sk.Cast(moving_image, sk.sitkFloat32)
+    reg = DemonsFilter()
+    reg.SetNumberOfThreads(ncores)
+    reg.SetSmoothUpdateField(True)
+    reg.SetSmoothDisplacementField(True)
+    # deformable.py:253-257: voxel-unit sigmas from the FULL-resolution spacing
+    reg.SetStandardDeviations((np.array(regularisation_kernel_mm) / np.array(fixed_image.GetSpacing())).tolist())
+    if not smoothing_sigmas:
+        smoothing_sigmas = [i * smoothing_sigma_factor for i in resolution_staging]
+    dvf = multiscale_demons(reg, fixed_image, moving_image, resolution_staging=resolution_staging,
+                            smoothing_sigmas=smoothing_sigmas, iteration_staging=iteration_staging,
+                            isotropic_resample=isotropic_resample, initial_displacement_field=initial_displacement_field,
+                            interp_order=interp_order, level_stats=level_stats)
+    # deformable.py:286-293
+    if default_value is None:
+        default_value = 0
+        if moving_image.array.min() <= -1000:
+            default_value = -1000
+    tfm = sk.DisplacementFieldTransform(sk.Cast(dvf, sk.sitkVectorFloat64))
+    registered = resample(moving_image, fixed_image, tfm, interp_order, default_value)  # :281-301
+    registered = sk.Cast(registered, moving_type)  # :303-304
+    return registered, tfm, dvf
+
+
+def compute_weight_map(target_image, moving_image, vote_type="unweighted", vote_params=None):
+    # fusion.py:76-80,148-177,202 (unweighted / global / local)
+    if target_image.GetPixelID() != 6:
+        target_image = sk.Cast(target_image, sk.sitkFloat32)
+    if moving_image.GetPixelID() != 6:
+        moving_image = sk.Cast(moving_image, sk.sitkFloat32)
+    t, m = target_image.array, moving_image.array
+    sq = ((t.astype(np.float64) - m.astype(np.float64)) ** 2).astype(np.float32)
+    vt = vote_type.lower()
+    if vt == "unweighted":
+        w = (t * np.float32(0.0) + np.float32(1.0)).astype(np.float32)
+    elif vt == "global":
+        gw = vote_params["factor"] / sq.sum(dtype=np.float64)
+        w = (t * np.float32(0.0) + np.float32(gw)).astype(np.float32)
+    elif vt == "local":
+        sigma, eps = vote_params["sigma"], vote_params["epsilon"]
+        raw = orc.discrete_gaussian_f32(sq, orc.geom_of(target_image), sigma * sigma)
+        w = np.power((raw + np.float32(eps)).astype(np.float64), -1.0).astype(np.float32)
+        if isinstance(vote_params.get("normalise", False), bool) and vote_params.get("normalise", False):
+            w = (w / w.max()).astype(np.float32)
+    else:
+        raise NotImplementedError(vote_type)
+    return _like(w, target_image)
+
+
+def combine_labels(atlas_set, structure_name, label="DIR", threshold=1e-4, smooth_sigma=1.0):
+    # fusion.py:239-292
+    names = [structure_name] if isinstance(structure_name, str) else list(structure_name)
+    out = {}
+    for s in names:
+        cases = [c for c in atlas_set if s in atlas_set[c][label]]
+        ws = [atlas_set[c][label]["Weight Map"].array for c in cases]
+        ls = [atlas_set[c][label][s].array for c in cases]
+        ref = atlas_set[cases[0]][label][s]
+        out[s] = _like(orc.combine_labels_f32(ls, ws, orc.geom_of(ref), smooth_sigma * smooth_sigma, threshold), ref)
+    return out
+
+
+def combine_labels_staple(label_list_dict, threshold=1e-4):
+    # fusion.py:205-236
+    names = np.unique([n for d in label_list_dict.values() for n in d.keys()])
+    out = {}
+    for s in names:
+        imgs = [label_list_dict[i][s] for i in label_list_dict]
+        binary = [((im.array >= 0.5) & (im.array <= 255)).astype(np.uint8) for im in imgs]  # BinaryThreshold(lower=0.5, upper=255)
+        W, _, _, _ = orc.staple(binary)
+        W = orc.rescale_threshold_f64(W, threshold)
+        out[str(s)] = _like(W, imgs[0])
+    return out

@@ -1,0 +1,600 @@
+// b200reg.cu -- C ABI of libb200reg.so (see include/b200reg.h).  sm_100a only, -fmad=false.
+#include "common.cuh"
+#include "demons.cuh"
+#include "deriche.cuh"
+#include "fusion.cuh"
+#include "gauss.cuh"
+#include "resample.cuh"
+
+using namespace b200;
+
+#define API extern "C" __attribute__((visibility("default")))
+#define REQUIRE(cond, ...)                                             \
+    do {                                                               \
+        if (!(cond)) return set_error(B200REG_ERR_ARG, __VA_ARGS__);   \
+    } while (0)
+
+namespace {
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+        else prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+}  // namespace
+#define ENTER(ctx)                                      \
+    REQUIRE((ctx) != nullptr, "null context");          \
+    DeviceGuard _guard((ctx)->device)
+
+// ---- context ------------------------------------------------------------------------------------------
+API int b200reg_abi_version(void) { return B200REG_ABI_VERSION; }
+API const char* b200reg_last_error(void) { return last_error_ref().c_str(); }
+
+API int b200reg_create(int device, void* stream, b200reg_ctx** out)
+{
+    REQUIRE(out != nullptr, "null output pointer");
+    int count = 0;
+    B200_CUDA(cudaGetDeviceCount(&count));
+    REQUIRE(device >= 0 && device < count, "CUDA device %d not present (%d visible)", device, count);
+    B200_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    B200_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return set_error(B200REG_ERR_UNSUPPORTED, "libb200reg is built for sm_100a only; device %d is sm_%d%d", device, prop.major, prop.minor);
+    auto* ctx = new b200reg_ctx();
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    if (stream) {
+        ctx->stream = (cudaStream_t)stream;
+    } else {
+        B200_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->owns_stream = true;
+    }
+    // keep freed stream-ordered allocations cached in the pool
+    cudaMemPool_t pool;
+    B200_CUDA(cudaDeviceGetDefaultMemPool(&pool, device));
+    uint64_t thr = UINT64_MAX;
+    B200_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
+    B200_CUDA(cudaMallocHost(&ctx->h_scratch, 64 * sizeof(double)));
+    *out = ctx;
+    return B200REG_OK;
+}
+API int b200reg_destroy(b200reg_ctx* ctx)
+{
+    if (!ctx) return B200REG_OK;
+    DeviceGuard g(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
+    if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
+    delete ctx;
+    return B200REG_OK;
+}
+API int b200reg_set_stream(b200reg_ctx* ctx, void* stream)
+{
+    ENTER(ctx);
+    if (ctx->owns_stream) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaStreamDestroy(ctx->stream);
+        ctx->owns_stream = false;
+    }
+    ctx->stream = (cudaStream_t)stream;
+    return B200REG_OK;
+}
+API int b200reg_synchronize(b200reg_ctx* ctx)
+{
+    ENTER(ctx);
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    return B200REG_OK;
+}
+API int64_t b200reg_launch_count(b200reg_ctx* ctx) { return ctx ? ctx->launches : -1; }
+
+// ---- memory helpers ---------------------------------------------------------------------------------------
+API int b200reg_malloc(b200reg_ctx* ctx, size_t bytes, void** d_ptr)
+{
+    ENTER(ctx);
+    REQUIRE(d_ptr != nullptr, "null output pointer");
+    B200_CUDA(cudaMalloc(d_ptr, bytes ? bytes : 16));
+    return B200REG_OK;
+}
+API int b200reg_free(b200reg_ctx* ctx, void* d_ptr)
+{
+    ENTER(ctx);
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    B200_CUDA(cudaFree(d_ptr));
+    return B200REG_OK;
+}
+API int b200reg_malloc_host(size_t bytes, void** h_ptr)
+{
+    REQUIRE(h_ptr != nullptr, "null output pointer");
+    B200_CUDA(cudaMallocHost(h_ptr, bytes ? bytes : 16));
+    return B200REG_OK;
+}
+API int b200reg_free_host(void* h_ptr)
+{
+    B200_CUDA(cudaFreeHost(h_ptr));
+    return B200REG_OK;
+}
+API int b200reg_memcpy_h2d(b200reg_ctx* ctx, void* d_dst, const void* h_src, size_t bytes)
+{
+    ENTER(ctx);
+    B200_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return B200REG_OK;
+}
+API int b200reg_memcpy_d2h(b200reg_ctx* ctx, void* h_dst, const void* d_src, size_t bytes)
+{
+    ENTER(ctx);
+    B200_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return B200REG_OK;
+}
+API int b200reg_memset(b200reg_ctx* ctx, void* d_ptr, int value, size_t bytes)
+{
+    ENTER(ctx);
+    B200_CUDA(cudaMemsetAsync(d_ptr, value, bytes, ctx->stream));
+    return B200REG_OK;
+}
+
+// ---- layout / dtype helpers ---------------------------------------------------------------------------------
+API int b200reg_aos_to_soa(b200reg_ctx* ctx, const double* d_aos, double* d_soa, size_t n)
+{
+    ENTER(ctx);
+    REQUIRE(d_aos && d_soa, "null pointer");
+    aos_to_soa_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_aos, d_soa, n);
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+API int b200reg_soa_to_aos(b200reg_ctx* ctx, const double* d_soa, double* d_aos, size_t n)
+{
+    ENTER(ctx);
+    REQUIRE(d_aos && d_soa, "null pointer");
+    soa_to_aos_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_soa, d_aos, n);
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+API int b200reg_cast(b200reg_ctx* ctx, const void* d_in, int in_dtype, void* d_out, int out_dtype, size_t n)
+{
+    ENTER(ctx);
+    REQUIRE(d_in && d_out, "null pointer");
+    const int nb = ctx->sm_count * 8;
+    B200_DISPATCH_DTYPE(in_dtype, TI, {
+        B200_DISPATCH_DTYPE(out_dtype, TO, { cast_kernel<TI, TO><<<nb, 256, 0, ctx->stream>>>((const TI*)d_in, (TO*)d_out, n); });
+    });
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+API int b200reg_minmax(b200reg_ctx* ctx, const void* d_in, int dtype, size_t n, double* h_min, double* h_max)
+{
+    ENTER(ctx);
+    REQUIRE(d_in && n > 0, "empty input");
+    TempBuf part, mm;
+    B200_TRY(mm.alloc(ctx, 2 * sizeof(double)));
+    B200_DISPATCH_DTYPE(dtype, T, { B200_TRY(minmax_device<T>(ctx, (const T*)d_in, n, mm.as<double>(), &part)); });
+    B200_CUDA(cudaMemcpyAsync(ctx->h_scratch, mm.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (h_min) *h_min = ctx->h_scratch[0];
+    if (h_max) *h_max = ctx->h_scratch[1];
+    return B200REG_OK;
+}
+
+// ---- N1 -------------------------------------------------------------------------------------------------------
+API int b200reg_discrete_gaussian_f32(b200reg_ctx* ctx, const float* d_in, float* d_out, const b200reg_geom* geom, const double variance[3],
+                                      int max_kernel_width, double max_error, int use_image_spacing)
+{
+    ENTER(ctx);
+    REQUIRE(d_in && d_out && variance && valid_geom(geom), "invalid argument");
+    return discrete_gaussian_f32(ctx, d_in, d_out, *geom, variance, max_kernel_width, max_error, use_image_spacing);
+}
+API int b200reg_gaussian_operator(double variance, double max_error, int max_kernel_width, double* h_kernel, int capacity)
+{
+    const std::vector<double> k = gaussian_operator(variance, max_error, max_kernel_width);
+    if ((int)k.size() > capacity) return -1;
+    for (size_t i = 0; i < k.size(); ++i) h_kernel[i] = k[i];
+    return ((int)k.size() - 1) / 2;
+}
+
+// ---- N2/N5/N9 ---------------------------------------------------------------------------------------------------
+API int b200reg_resample_batch(b200reg_ctx* ctx, int n, const void* const* d_in, const int* dtypes, const b200reg_geom* in_geom,
+                               void* const* d_out, const b200reg_geom* out_geom, const b200reg_transform* chain, int n_chain,
+                               const int* interps, const double* default_values)
+{
+    ENTER(ctx);
+    REQUIRE(n > 0 && n <= B200REG_MAX_BATCH, "batch size %d not in [1, %d]", n, B200REG_MAX_BATCH);
+    REQUIRE(d_in && d_out && dtypes && interps && default_values, "null argument");
+    REQUIRE(valid_geom(in_geom) && valid_geom(out_geom), "invalid geometry");
+    return resample_batch(ctx, n, d_in, dtypes, *in_geom, d_out, *out_geom, chain, n_chain, interps, default_values);
+}
+API int b200reg_resample(b200reg_ctx* ctx, const void* d_in, int dtype, const b200reg_geom* in_geom, void* d_out, const b200reg_geom* out_geom,
+                         const b200reg_transform* chain, int n_chain, int interp, double default_value)
+{
+    return b200reg_resample_batch(ctx, 1, &d_in, &dtype, in_geom, &d_out, out_geom, chain, n_chain, &interp, &default_value);
+}
+API int b200reg_resample_vec3(b200reg_ctx* ctx, const double* d_in_soa, const b200reg_geom* in_geom, double* d_out_soa,
+                              const b200reg_geom* out_geom, const b200reg_transform* chain, int n_chain, double default_value)
+{
+    ENTER(ctx);
+    REQUIRE(d_in_soa && d_out_soa && valid_geom(in_geom) && valid_geom(out_geom), "invalid argument");
+    return resample_vec3(ctx, d_in_soa, *in_geom, d_out_soa, *out_geom, chain, n_chain, default_value);
+}
+
+static b200reg_transform dvf_transform(const double* d_soa, const b200reg_geom& g)
+{
+    b200reg_transform t;
+    memset(&t, 0, sizeof(t));
+    t.kind = B200REG_TFM_DVF;
+    t.d_dvf = d_soa;
+    t.dvf_geom = g;
+    return t;
+}
+
+API int b200reg_compose_dvf(b200reg_ctx* ctx, double* d_total_soa, const double* d_iter_soa, const b200reg_geom* geom, double* d_scratch_soa)
+{
+    ENTER(ctx);
+    REQUIRE(d_total_soa && d_iter_soa && d_scratch_soa && valid_geom(geom), "invalid argument");
+    const b200reg_transform t = dvf_transform(d_total_soa, *geom);
+    B200_TRY(resample_vec3(ctx, d_iter_soa, *geom, d_scratch_soa, *geom, &t, 1, 0.0, d_total_soa));
+    B200_CUDA(cudaMemcpyAsync(d_total_soa, d_scratch_soa, 3 * nvox(*geom) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return B200REG_OK;
+}
+
+// ---- N6 -----------------------------------------------------------------------------------------------------------
+static int check_demons_params(const b200reg_demons_params* p)
+{
+    REQUIRE(p != nullptr, "null Demons parameters");
+    REQUIRE(p->number_of_iterations >= 0, "negative iteration count");
+    for (int a = 0; a < 3; ++a) REQUIRE(p->std_dev[a] >= 0 && p->update_std_dev[a] >= 0, "negative standard deviation");
+    REQUIRE(p->max_error > 0 && p->max_error < 1, "maximum error must be in (0, 1)");
+    return B200REG_OK;
+}
+
+static int read_stats(b200reg_ctx* ctx, const DemonsWorkspace& ws, const b200reg_geom& g, b200reg_demons_stats* st, float ms)
+{
+    DemonsCtrl h;
+    B200_CUDA(cudaMemcpyAsync(ctx->h_scratch, ws.ctrl.p, sizeof(DemonsCtrl), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    memcpy(&h, ctx->h_scratch, sizeof(h));
+    st->elapsed_iterations = h.elapsed;
+    st->voxels_lo = (int32_t)(nvox(g) & 0x7fffffff);
+    st->metric = h.metric;
+    st->rms_change = h.rms;
+    st->gpu_ms = ms;
+    return B200REG_OK;
+}
+
+API int b200reg_demons_execute(b200reg_ctx* ctx, const float* d_fixed, const b200reg_geom* fixed_geom, const float* d_moving,
+                               const b200reg_geom* moving_geom, const b200reg_demons_params* params, double* d_out_soa,
+                               b200reg_demons_stats* h_stats)
+{
+    ENTER(ctx);
+    REQUIRE(d_fixed && d_moving && d_out_soa && valid_geom(fixed_geom) && valid_geom(moving_geom), "invalid argument");
+    B200_TRY(check_demons_params(params));
+    DemonsWorkspace ws;
+    B200_TRY(demons_prepare(ctx, *fixed_geom, params->number_of_iterations, &ws, false));
+    cudaEvent_t e0, e1;
+    B200_CUDA(cudaEventCreate(&e0));
+    B200_CUDA(cudaEventCreate(&e1));
+    B200_CUDA(cudaEventRecord(e0, ctx->stream));
+    int rc = demons_enqueue(ctx, d_fixed, *fixed_geom, d_moving, *moving_geom, *params, d_out_soa, &ws);
+    cudaEventRecord(e1, ctx->stream);
+    float ms = 0.f;
+    if (rc == B200REG_OK) {
+        cudaEventSynchronize(e1);
+        cudaEventElapsedTime(&ms, e0, e1);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    B200_TRY(rc);
+    if (h_stats) B200_TRY(read_stats(ctx, ws, *fixed_geom, h_stats, ms));
+    return B200REG_OK;
+}
+
+API int b200reg_demons_force(b200reg_ctx* ctx, const float* d_fixed, const b200reg_geom* fixed_geom, const float* d_moving,
+                             const b200reg_geom* moving_geom, const double* d_field_soa, const b200reg_demons_params* params, float* d_w,
+                             double* d_u_soa, double* h_metric, double* h_rms)
+{
+    ENTER(ctx);
+    REQUIRE(d_fixed && d_moving && d_field_soa && d_w && d_u_soa && valid_geom(fixed_geom) && valid_geom(moving_geom), "invalid argument");
+    B200_TRY(check_demons_params(params));
+    DemonsWorkspace ws;
+    B200_TRY(demons_prepare(ctx, *fixed_geom, 1, &ws, false));
+    demons_ctrl_init_kernel<<<1, 1, 0, ctx->stream>>>(ws.ctrl.as<DemonsCtrl>(), 1);
+    ctx->launches++;
+    const GeomD gf = make_geomd(*fixed_geom), gm = make_geomd(*moving_geom);
+    B200_TRY(demons_calculate_change(ctx, d_fixed, gf, d_moving, gm, d_field_soa, make_force_params(*fixed_geom, *params), &ws, 0, 1));
+    const size_t n = nvox(*fixed_geom);
+    B200_CUDA(cudaMemcpyAsync(d_w, ws.W.p, n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+    B200_CUDA(cudaMemcpyAsync(d_u_soa, ws.U.p, 3 * n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    b200reg_demons_stats st;
+    B200_TRY(read_stats(ctx, ws, *fixed_geom, &st, 0.f));
+    if (h_metric) *h_metric = st.metric;
+    if (h_rms) *h_rms = st.rms_change;
+    return B200REG_OK;
+}
+
+API int b200reg_pde_smooth_field(b200reg_ctx* ctx, double* d_field_soa, const b200reg_geom* geom, const double std_dev[3], double max_error,
+                                 int max_kernel_width)
+{
+    ENTER(ctx);
+    REQUIRE(d_field_soa && valid_geom(geom) && std_dev, "invalid argument");
+    const size_t n = nvox(*geom);
+    TempBuf t1, t2;
+    B200_TRY(t1.alloc(ctx, 3 * n * sizeof(double)));
+    B200_TRY(t2.alloc(ctx, 3 * n * sizeof(double)));
+    KernelCoeffs kc[3];
+    B200_TRY(make_pde_coeffs(std_dev, max_error, max_kernel_width, kc));
+    return pde_smooth(ctx, d_field_soa, nullptr, t1.as<double>(), t2.as<double>(), geom->size[0], geom->size[1], geom->size[2], kc, nullptr, 0);
+}
+
+// ---- N8 --------------------------------------------------------------------------------------------------------------
+API int b200reg_recursive_gaussian_vec3(b200reg_ctx* ctx, double* d_field_soa, const b200reg_geom* geom, const double sigma[3])
+{
+    ENTER(ctx);
+    REQUIRE(d_field_soa && valid_geom(geom) && sigma, "invalid argument");
+    for (int a = 0; a < 3; ++a) REQUIRE(sigma[a] > 0, "sigma must be positive");
+    return recursive_gaussian_vec3(ctx, d_field_soa, *geom, sigma);
+}
+
+// ---- a2/a3: pyramid + multiscale_demons --------------------------------------------------------------------------------
+API int b200reg_pyramid_geom(const b200reg_geom* in, int isotropic, double resolution, b200reg_geom* out)
+{
+    REQUIRE(valid_geom(in) && out, "invalid argument");
+    REQUIRE(resolution > 0, "resolution must be positive");
+    *out = *in;
+    for (int a = 0; a < 3; ++a) {
+        // utils.py:237-247: scale factor = voxel size / spacing (isotropic) or the shrink factor
+        const double sf = isotropic ? (resolution * 1.0 / in->spacing[a]) : resolution;
+        const int sz = (int)((double)in->size[a] / sf + 0.5);
+        REQUIRE(sz >= 1, "pyramid level collapses to an empty grid along axis %d", a);
+        out->size[a] = sz;
+        // utils.py:252-255 (align corners); a size of 1 divides by zero in the reference as well
+        REQUIRE(sz > 1, "pyramid level has a single voxel along axis %d (the reference divides by zero here)", a);
+        out->spacing[a] = ((double)(in->size[a] - 1) * in->spacing[a]) / (double)(sz - 1);
+    }
+    return B200REG_OK;
+}
+
+// smooth_and_resample (utils.py:195-267) for one Float32 image onto a precomputed level grid
+static int smooth_and_resample_f32(b200reg_ctx* ctx, const float* d_in, const b200reg_geom& gin, double sigma, const b200reg_geom& gout, int interp,
+                                   float* d_out)
+{
+    const size_t n = nvox(gin);
+    TempBuf sm;
+    const float* src = d_in;
+    if (sigma != 0.0) {
+        const double var[3] = { sigma * sigma, sigma * sigma, sigma * sigma };
+        double mw = 0.0;
+        for (int a = 0; a < 3; ++a) mw = fmax(mw, 8 * var[a] * gin.spacing[a]);
+        B200_TRY(sm.alloc(ctx, n * sizeof(float)));
+        B200_TRY(discrete_gaussian_f32(ctx, d_in, sm.as<float>(), gin, var, (int)mw, 0.01, 1));
+        src = sm.as<float>();
+    }
+    const void* ins[1] = { src };
+    void* outs[1] = { d_out };
+    const int dt = B200REG_F32;
+    const double dv = 0.0;
+    return resample_batch(ctx, 1, ins, &dt, gin, outs, gout, nullptr, 0, &interp, &dv);
+}
+
+API int b200reg_multiscale_demons(b200reg_ctx* ctx, const float* d_fixed, const b200reg_geom* fixed_geom, const float* d_moving,
+                                  const b200reg_geom* moving_geom, const b200reg_multires_config* cfg, const double* d_initial_soa,
+                                  const b200reg_geom* initial_geom, double* d_out_soa, b200reg_demons_stats* h_level_stats)
+{
+    ENTER(ctx);
+    REQUIRE(d_fixed && d_moving && d_out_soa && cfg && valid_geom(fixed_geom) && valid_geom(moving_geom), "invalid argument");
+    REQUIRE(cfg->n_levels >= 0 && cfg->n_levels <= B200REG_MAX_LEVELS, "number of levels %d not in [0, %d]", cfg->n_levels, B200REG_MAX_LEVELS);
+    REQUIRE(cfg->interp_order == B200REG_INTERP_NN || cfg->interp_order == B200REG_INTERP_LINEAR ? true : false,
+            "interpolator %d is not supported (nearest neighbour = 1, linear = 2)", cfg->interp_order);
+    B200_TRY(check_demons_params(&cfg->demons));
+    const int L = cfg->n_levels;
+    const b200reg_geom gF = *fixed_geom, gM = *moving_geom;
+
+    // deformable.py:67-94: both pyramids, all levels, from the ORIGINAL images
+    std::vector<b200reg_geom> gfl(L), gml(L);
+    std::vector<TempBuf> Fl(L), Ml(L);
+    for (int l = 0; l < L; ++l) {
+        const double res = cfg->resolution_staging[l];
+        // utils.py:249-250: neither factor given -> image returned unchanged
+        if (res == 0.0) {
+            gfl[l] = gF;
+            gml[l] = gM;
+        } else {
+            B200_TRY(b200reg_pyramid_geom(&gF, cfg->isotropic_resample, res, &gfl[l]));
+            B200_TRY(b200reg_pyramid_geom(&gM, cfg->isotropic_resample, res, &gml[l]));
+        }
+        B200_TRY(Fl[l].alloc(ctx, nvox(gfl[l]) * sizeof(float)));
+        B200_TRY(Ml[l].alloc(ctx, nvox(gml[l]) * sizeof(float)));
+        if (res == 0.0) {
+            // smoothed if a sigma was given (utils.py:216-226 precede the early return), never resampled
+            const float* srcs[2] = { d_fixed, d_moving };
+            float* dsts[2] = { Fl[l].as<float>(), Ml[l].as<float>() };
+            const b200reg_geom* gs[2] = { &gF, &gM };
+            for (int q = 0; q < 2; ++q) {
+                const double sg = cfg->smoothing_sigmas[l];
+                if (sg != 0.0) {
+                    const double var[3] = { sg * sg, sg * sg, sg * sg };
+                    double mw = 0.0;
+                    for (int a = 0; a < 3; ++a) mw = fmax(mw, 8 * var[a] * gs[q]->spacing[a]);
+                    B200_TRY(discrete_gaussian_f32(ctx, srcs[q], dsts[q], *gs[q], var, (int)mw, 0.01, 1));
+                } else {
+                    B200_CUDA(cudaMemcpyAsync(dsts[q], srcs[q], nvox(*gs[q]) * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+                }
+            }
+        } else {
+            B200_TRY(smooth_and_resample_f32(ctx, d_fixed, gF, cfg->smoothing_sigmas[l], gfl[l], cfg->interp_order, Fl[l].as<float>()));
+            B200_TRY(smooth_and_resample_f32(ctx, d_moving, gM, cfg->smoothing_sigmas[l], gml[l], cfg->interp_order, Ml[l].as<float>()));
+        }
+    }
+
+    // deformable.py:99-130: initial field on the fixed grid (zeros, or the given field re-gridded twice)
+    const size_t nF = nvox(gF);
+    TempBuf total, next;
+    b200reg_geom g_total = gF;
+    B200_TRY(total.alloc(ctx, 3 * nF * sizeof(double)));
+    if (d_initial_soa) {
+        REQUIRE(valid_geom(initial_geom), "invalid initial field geometry");
+        TempBuf tmp;
+        B200_TRY(tmp.alloc(ctx, 3 * nF * sizeof(double)));
+        B200_TRY(resample_vec3(ctx, d_initial_soa, *initial_geom, tmp.as<double>(), gF, nullptr, 0, 0.0));
+        B200_TRY(resample_vec3(ctx, tmp.as<double>(), gF, total.as<double>(), gF, nullptr, 0, 0.0));
+    } else {
+        B200_CUDA(cudaMemsetAsync(total.p, 0, 3 * nF * sizeof(double), ctx->stream));
+    }
+
+    std::vector<cudaEvent_t> ev(2 * (size_t)L);
+    for (auto& e : ev) B200_CUDA(cudaEventCreate(&e));
+    std::vector<DemonsWorkspace> wss(L);
+    int rc = B200REG_OK;
+    for (int l = 0; l < L && rc == B200REG_OK; ++l) {
+        const b200reg_geom& gl = gfl[l];
+        const size_t nl = nvox(gl);
+        auto step = [&]() -> int {
+            // :137 dvf_total -> level grid
+            B200_TRY(next.alloc(ctx, 3 * nl * sizeof(double)));
+            B200_TRY(resample_vec3(ctx, total.as<double>(), g_total, next.as<double>(), gl, nullptr, 0, 0.0));
+            std::swap(total.p, next.p);
+            g_total = gl;
+            // :139-140 warp the level's moving image by the running total (default pixel 0)
+            const b200reg_transform tfm = dvf_transform(total.as<double>(), gl);
+            TempBuf mw;
+            B200_TRY(mw.alloc(ctx, nvox(gml[l]) * sizeof(float)));
+            {
+                const void* ins[1] = { Ml[l].p };
+                void* outs[1] = { mw.p };
+                const int dt = B200REG_F32, ip = cfg->interp_order;
+                const double dv = 0.0;
+                B200_TRY(resample_batch(ctx, 1, ins, &dt, gml[l], outs, gml[l], &tfm, 1, &ip, &dv));
+            }
+            // :143-149 Demons from a zero field
+            b200reg_demons_params p = cfg->demons;
+            p.number_of_iterations = cfg->iteration_staging[l];
+            TempBuf iter;
+            B200_TRY(iter.alloc(ctx, 3 * nl * sizeof(double)));
+            B200_TRY(demons_prepare(ctx, gl, p.number_of_iterations, &wss[l], false));
+            B200_CUDA(cudaEventRecord(ev[2 * l], ctx->stream));
+            B200_TRY(demons_enqueue(ctx, Fl[l].as<float>(), gl, mw.as<float>(), gml[l], p, iter.as<double>(), &wss[l]));
+            B200_CUDA(cudaEventRecord(ev[2 * l + 1], ctx->stream));
+            // :154 dvf_total + Resample(dvf_iter, tfm_total)
+            B200_TRY(next.alloc(ctx, 3 * nl * sizeof(double)));
+            B200_TRY(resample_vec3(ctx, iter.as<double>(), gl, next.as<double>(), gl, &tfm, 1, 0.0, total.as<double>()));
+            std::swap(total.p, next.p);
+            // :157-159 recursive Gaussian with the filter's (voxel-unit) sigmas passed as physical
+            B200_TRY(recursive_gaussian_vec3(ctx, total.as<double>(), gl, p.std_dev));
+            return B200REG_OK;
+        };
+        rc = step();
+    }
+    // :185 back onto the fixed grid
+    if (rc == B200REG_OK) rc = resample_vec3(ctx, total.as<double>(), g_total, d_out_soa, gF, nullptr, 0, 0.0);
+    if (rc == B200REG_OK && h_level_stats) {
+        for (int l = 0; l < L && rc == B200REG_OK; ++l) {
+            float ms = 0.f;
+            if (cudaEventSynchronize(ev[2 * l + 1]) == cudaSuccess) cudaEventElapsedTime(&ms, ev[2 * l], ev[2 * l + 1]);
+            rc = read_stats(ctx, wss[l], gfl[l], &h_level_stats[l], ms);
+        }
+    }
+    if (rc != B200REG_OK) cudaStreamSynchronize(ctx->stream);
+    for (auto& e : ev) cudaEventDestroy(e);
+    return rc;
+}
+
+// ---- fusion ----------------------------------------------------------------------------------------------------------------
+API int b200reg_weight_map(b200reg_ctx* ctx, const float* d_target, const float* d_moving, const b200reg_geom* geom, int vote_type, double factor,
+                           double sigma, double epsilon, float* d_weight)
+{
+    ENTER(ctx);
+    REQUIRE(d_target && d_moving && d_weight && valid_geom(geom), "invalid argument");
+    return weight_map(ctx, d_target, d_moving, *geom, vote_type, factor, sigma, epsilon, d_weight);
+}
+API int b200reg_vote_accumulate(b200reg_ctx* ctx, const uint8_t* d_label, const float* d_weight, float* d_acc_num, float* d_acc_den, size_t n,
+                                int first)
+{
+    ENTER(ctx);
+    REQUIRE(d_label && d_weight && d_acc_num, "invalid argument");
+    vote_accumulate_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_label, d_weight, d_acc_num, d_acc_den, n, first);
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+API int b200reg_vote_finalize(b200reg_ctx* ctx, float* d_num, const float* d_den, const b200reg_geom* geom, double smooth_variance,
+                              double threshold, float* d_out)
+{
+    ENTER(ctx);
+    REQUIRE(d_num && d_out && valid_geom(geom), "invalid argument");
+    return vote_finalize(ctx, d_num, d_den, *geom, smooth_variance, threshold, d_out);
+}
+
+API int b200reg_staple(b200reg_ctx* ctx, const uint8_t* const* d_decisions, int n_raters, size_t n, double confidence_weight,
+                       uint32_t max_iterations, double threshold, int rescale, double* d_out, double* h_pq, int32_t* h_elapsed)
+{
+    ENTER(ctx);
+    REQUIRE(d_decisions && d_out && n > 0, "invalid argument");
+    REQUIRE(n_raters >= 1 && n_raters <= STAPLE_MAX_RATERS, "number of raters %d not in [1, %d]", n_raters, STAPLE_MAX_RATERS);
+    StaplePtrs ptrs;
+    ptrs.n = n_raters;
+    for (int j = 0; j < n_raters; ++j) {
+        REQUIRE(d_decisions[j] != nullptr, "null decision volume");
+        ptrs.d[j] = d_decisions[j];
+    }
+    const int nb = ctx->sm_count * 4;
+    const int stride = 2 * n_raters + 2;
+    TempBuf partial, state;
+    B200_TRY(partial.alloc(ctx, sizeof(double) * (size_t)nb * stride));
+    B200_TRY(state.alloc(ctx, sizeof(StapleState)));
+    StapleState* st = state.as<StapleState>();
+    staple_init_kernel<<<nb, 256, 0, ctx->stream>>>(ptrs, d_out, n, partial.as<double>());
+    staple_g_kernel<<<1, 32, 0, ctx->stream>>>(partial.as<double>(), nb, n, confidence_weight, st);
+    ctx->launches += 2;
+    StapleState* h_state = nullptr;
+    B200_CUDA(cudaMallocHost(&h_state, sizeof(StapleState)));
+    uint32_t iter = 0;
+    int rc = B200REG_OK;
+    bool done = false;
+    while (!done && iter < max_iterations) {
+        // enqueue a burst of EM iterations, then look at the convergence flag once
+        const uint32_t burst = 8;
+        for (uint32_t b = 0; b < burst && iter < max_iterations; ++b, ++iter) {
+            staple_mstep_kernel<<<nb, 256, 0, ctx->stream>>>(ptrs, d_out, n, partial.as<double>(), st);
+            staple_pq_kernel<<<1, 256, 0, ctx->stream>>>(partial.as<double>(), nb, n_raters, st);
+            staple_estep_kernel<<<nb, 256, 0, ctx->stream>>>(ptrs, d_out, n, st);
+            staple_converge_kernel<<<1, 1, 0, ctx->stream>>>(st, n_raters, iter);
+            ctx->launches += 4;
+        }
+        if (cudaGetLastError() != cudaSuccess || cudaMemcpyAsync(h_state, st, sizeof(StapleState), cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess ||
+            cudaStreamSynchronize(ctx->stream) != cudaSuccess) {
+            rc = set_error(B200REG_ERR_CUDA, "STAPLE iteration failed: %s", cudaGetErrorString(cudaGetLastError()));
+            break;
+        }
+        done = h_state->converged != 0;
+    }
+    if (rc == B200REG_OK) {
+        if (iter == 0) {
+            cudaMemcpyAsync(h_state, st, sizeof(StapleState), cudaMemcpyDeviceToHost, ctx->stream);
+            cudaStreamSynchronize(ctx->stream);
+        }
+        if (h_pq)
+            for (int j = 0; j < n_raters; ++j) {
+                h_pq[j] = h_state->p[j];
+                h_pq[n_raters + j] = h_state->q[j];
+            }
+        if (h_elapsed) *h_elapsed = done ? h_state->elapsed : (int32_t)iter;
+    }
+    cudaFreeHost(h_state);
+    B200_TRY(rc);
+    if (rescale || threshold != 0.0) {
+        TempBuf part, mm;
+        B200_TRY(mm.alloc(ctx, 2 * sizeof(double)));
+        B200_TRY(minmax_device<double>(ctx, d_out, n, mm.as<double>(), &part));
+        rescale_threshold_kernel<double><<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_out, d_out, n, mm.as<double>(), threshold, DBL_EPSILON, rescale);
+        ctx->launches++;
+        B200_CHECK_LAUNCH();
+        B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return B200REG_OK;
+}

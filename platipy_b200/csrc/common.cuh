@@ -1,0 +1,292 @@
+// common.cuh -- context, error plumbing, device geometry and pixel traits shared by all kernels.
+// Compiled with -fmad=false: no FMA contraction anywhere, so f64 arithmetic is reproducible against the
+// CPU oracle wherever the operation order is the same.
+#pragma once
+#include <cuda_runtime.h>
+#include <cfloat>
+#include <cmath>
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/b200reg.h"
+
+namespace b200 {
+
+// ---- error plumbing --------------------------------------------------------------------------------
+inline std::string& last_error_ref()
+{
+    static thread_local std::string s;
+    return s;
+}
+inline int set_error(int code, const char* fmt, ...)
+{
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    last_error_ref() = buf;
+    return code;
+}
+#define B200_CUDA(expr)                                                                                          \
+    do {                                                                                                         \
+        cudaError_t _e = (expr);                                                                                 \
+        if (_e != cudaSuccess)                                                                                   \
+            return ::b200::set_error(B200REG_ERR_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,      \
+                                     cudaGetErrorString(_e));                                                    \
+    } while (0)
+#define B200_CHECK_LAUNCH() B200_CUDA(cudaGetLastError())
+#define B200_TRY(expr)                       \
+    do {                                     \
+        int _s = (expr);                     \
+        if (_s != B200REG_OK) return _s;     \
+    } while (0)
+
+}  // namespace b200
+
+struct b200reg_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool owns_stream = false;
+    int64_t launches = 0;
+    int sm_count = 148;
+    // pinned scratch for small read-backs
+    double* h_scratch = nullptr;  // 64 doubles
+};
+
+namespace b200 {
+
+// Stream-ordered temporary buffer (cudaMallocAsync pool; release threshold is raised at ctx creation so
+// freed blocks stay cached in the pool).
+struct TempBuf {
+    void* p = nullptr;
+    cudaStream_t s = nullptr;
+    TempBuf() = default;
+    TempBuf(const TempBuf&) = delete;
+    TempBuf& operator=(const TempBuf&) = delete;
+    int alloc(b200reg_ctx* ctx, size_t bytes)
+    {
+        release();
+        s = ctx->stream;
+        B200_CUDA(cudaMallocAsync(&p, bytes ? bytes : 16, s));
+        return B200REG_OK;
+    }
+    void release()
+    {
+        if (p) cudaFreeAsync(p, s);
+        p = nullptr;
+    }
+    ~TempBuf() { release(); }
+    template <typename T>
+    T* as() const
+    {
+        return reinterpret_cast<T*>(p);
+    }
+};
+
+// ---- geometry --------------------------------------------------------------------------------------
+struct GeomD {
+    int nx, ny, nz;
+    double origin[3];
+    double i2p[9];  // Direction * diag(Spacing)
+    double p2i[9];  // inverse
+    double spacing[3];
+    double direction[9];
+};
+
+inline void inv3(const double* m, double* o)
+{
+    // diagonal (identity direction): exact reciprocals
+    if (m[1] == 0 && m[2] == 0 && m[3] == 0 && m[5] == 0 && m[6] == 0 && m[7] == 0) {
+        for (int i = 0; i < 9; ++i) o[i] = 0.0;
+        o[0] = 1.0 / m[0];
+        o[4] = 1.0 / m[4];
+        o[8] = 1.0 / m[8];
+        return;
+    }
+    double c00 = m[4] * m[8] - m[5] * m[7], c01 = m[5] * m[6] - m[3] * m[8], c02 = m[3] * m[7] - m[4] * m[6];
+    double det = m[0] * c00 + m[1] * c01 + m[2] * c02;
+    o[0] = c00 / det;
+    o[1] = (m[2] * m[7] - m[1] * m[8]) / det;
+    o[2] = (m[1] * m[5] - m[2] * m[4]) / det;
+    o[3] = c01 / det;
+    o[4] = (m[0] * m[8] - m[2] * m[6]) / det;
+    o[5] = (m[2] * m[3] - m[0] * m[5]) / det;
+    o[6] = c02 / det;
+    o[7] = (m[1] * m[6] - m[0] * m[7]) / det;
+    o[8] = (m[0] * m[4] - m[1] * m[3]) / det;
+}
+
+inline GeomD make_geomd(const b200reg_geom& s)
+{
+    GeomD g;
+    g.nx = s.size[0];
+    g.ny = s.size[1];
+    g.nz = s.size[2];
+    for (int r = 0; r < 3; ++r) {
+        g.origin[r] = s.origin[r];
+        g.spacing[r] = s.spacing[r];
+        for (int c = 0; c < 3; ++c) {
+            g.i2p[r * 3 + c] = s.direction[r * 3 + c] * s.spacing[c];
+            g.direction[r * 3 + c] = s.direction[r * 3 + c];
+        }
+    }
+    inv3(g.i2p, g.p2i);
+    return g;
+}
+inline size_t nvox(const b200reg_geom& g) { return (size_t)g.size[0] * g.size[1] * g.size[2]; }
+inline bool valid_geom(const b200reg_geom* g)
+{
+    if (!g) return false;
+    for (int i = 0; i < 3; ++i)
+        if (g->size[i] <= 0 || !(g->spacing[i] > 0.0)) return false;
+    return true;
+}
+
+// ImageBase::TransformIndexToPhysicalPoint: sum over columns, then + origin
+__device__ __forceinline__ void idx2pt(const GeomD& g, double i0, double i1, double i2, double* p)
+{
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        double sum = 0.0;
+        sum += g.i2p[r * 3 + 0] * i0;
+        sum += g.i2p[r * 3 + 1] * i1;
+        sum += g.i2p[r * 3 + 2] * i2;
+        p[r] = sum + g.origin[r];
+    }
+}
+// ImageBase::TransformPhysicalPointToContinuousIndex
+__device__ __forceinline__ void pt2cidx(const GeomD& g, const double* p, double* c)
+{
+    double v0 = p[0] - g.origin[0], v1 = p[1] - g.origin[1], v2 = p[2] - g.origin[2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        double sum = 0.0;
+        sum += g.p2i[r * 3 + 0] * v0;
+        sum += g.p2i[r * 3 + 1] * v1;
+        sum += g.p2i[r * 3 + 2] * v2;
+        c[r] = sum;
+    }
+}
+// ImageFunction::IsInsideBuffer(ContinuousIndex): [-0.5, size - 0.5), NaN -> outside
+__device__ __forceinline__ bool inside_buffer(const GeomD& g, const double* c)
+{
+    return (c[0] >= -0.5 && c[0] < g.nx - 0.5 && c[1] >= -0.5 && c[1] < g.ny - 0.5 && c[2] >= -0.5 && c[2] < g.nz - 0.5);
+}
+
+// ---- pixel traits: load as double; store with CastPixelWithBoundsChecking ------------------------------
+template <typename T>
+struct Px;
+#define B200_INT_PX(T, LO, HI)                                                      \
+    template <>                                                                     \
+    struct Px<T> {                                                                  \
+        __device__ static __forceinline__ double ld(const T* p, size_t i) { return (double)p[i]; } \
+        __device__ static __forceinline__ T cast(double v)                          \
+        {                                                                           \
+            double w = v;                                                           \
+            if (w < (double)(LO)) w = (double)(LO);                                 \
+            if (w > (double)(HI)) w = (double)(HI);                                 \
+            return (T)w;                                                            \
+        }                                                                           \
+    };
+B200_INT_PX(int8_t, INT8_MIN, INT8_MAX)
+B200_INT_PX(uint8_t, 0, UINT8_MAX)
+B200_INT_PX(int16_t, INT16_MIN, INT16_MAX)
+B200_INT_PX(uint16_t, 0, UINT16_MAX)
+B200_INT_PX(int32_t, INT32_MIN, INT32_MAX)
+B200_INT_PX(uint32_t, 0, UINT32_MAX)
+#undef B200_INT_PX
+template <>
+struct Px<int64_t> {
+    __device__ static __forceinline__ double ld(const int64_t* p, size_t i) { return (double)p[i]; }
+    __device__ static __forceinline__ int64_t cast(double v)
+    {
+        if (v <= -9223372036854775808.0) return INT64_MIN;
+        if (v >= 9223372036854775808.0) return INT64_MAX;
+        return (int64_t)v;
+    }
+};
+template <>
+struct Px<uint64_t> {
+    __device__ static __forceinline__ double ld(const uint64_t* p, size_t i) { return (double)p[i]; }
+    __device__ static __forceinline__ uint64_t cast(double v)
+    {
+        if (v <= 0.0) return 0;
+        if (v >= 18446744073709551616.0) return UINT64_MAX;
+        return (uint64_t)v;
+    }
+};
+template <>
+struct Px<float> {
+    __device__ static __forceinline__ double ld(const float* p, size_t i) { return (double)p[i]; }
+    __device__ static __forceinline__ float cast(double v)
+    {
+        double w = v;
+        if (w < -(double)FLT_MAX) w = -(double)FLT_MAX;
+        if (w > (double)FLT_MAX) w = (double)FLT_MAX;
+        return (float)w;
+    }
+};
+template <>
+struct Px<double> {
+    __device__ static __forceinline__ double ld(const double* p, size_t i) { return p[i]; }
+    __device__ static __forceinline__ double cast(double v) { return v; }
+};
+
+inline size_t dtype_size(int dt)
+{
+    switch (dt) {
+    case B200REG_I8: case B200REG_U8: return 1;
+    case B200REG_I16: case B200REG_U16: return 2;
+    case B200REG_I32: case B200REG_U32: case B200REG_F32: return 4;
+    case B200REG_I64: case B200REG_U64: case B200REG_F64: return 8;
+    default: return 0;
+    }
+}
+
+// dispatch a generic lambda on the pixel type: f(T{}) with T the C type
+#define B200_DISPATCH_DTYPE(dt, NAME, ...)                                       \
+    switch (dt) {                                                                \
+    case B200REG_I8: { using NAME = int8_t; __VA_ARGS__; } break;                \
+    case B200REG_U8: { using NAME = uint8_t; __VA_ARGS__; } break;               \
+    case B200REG_I16: { using NAME = int16_t; __VA_ARGS__; } break;              \
+    case B200REG_U16: { using NAME = uint16_t; __VA_ARGS__; } break;             \
+    case B200REG_I32: { using NAME = int32_t; __VA_ARGS__; } break;              \
+    case B200REG_U32: { using NAME = uint32_t; __VA_ARGS__; } break;             \
+    case B200REG_I64: { using NAME = int64_t; __VA_ARGS__; } break;              \
+    case B200REG_U64: { using NAME = uint64_t; __VA_ARGS__; } break;             \
+    case B200REG_F32: { using NAME = float; __VA_ARGS__; } break;                \
+    case B200REG_F64: { using NAME = double; __VA_ARGS__; } break;               \
+    default: return ::b200::set_error(B200REG_ERR_ARG, "unsupported pixel type %d", (int)(dt)); \
+    }
+
+// 3-D launch shape used by the per-voxel kernels: x fastest, 64x4 threads per block
+constexpr int BX = 64, BY = 4;
+inline dim3 grid3(int nx, int ny, int nz) { return dim3((nx + BX - 1) / BX, (ny + BY - 1) / BY, nz); }
+inline dim3 block3() { return dim3(BX, BY, 1); }
+
+// warp / block reductions (fixed order -> deterministic)
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    return v;
+}
+
+}  // namespace b200

@@ -1,0 +1,396 @@
+// fusion.cuh -- label fusion (reference platipy/imaging/label/fusion.py:56-292) and small utility kernels.
+#pragma once
+#include "common.cuh"
+#include "gauss.cuh"
+
+namespace b200 {
+
+// ---- layout / cast / reductions ---------------------------------------------------------------------
+__global__ void aos_to_soa_kernel(const double* __restrict__ aos, double* __restrict__ soa, size_t n)
+{
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) {
+        soa[q] = aos[3 * q];
+        soa[q + n] = aos[3 * q + 1];
+        soa[q + 2 * n] = aos[3 * q + 2];
+    }
+}
+__global__ void soa_to_aos_kernel(const double* __restrict__ soa, double* __restrict__ aos, size_t n)
+{
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) {
+        aos[3 * q] = soa[q];
+        aos[3 * q + 1] = soa[q + n];
+        aos[3 * q + 2] = soa[q + 2 * n];
+    }
+}
+
+// sitk.Cast: static_cast (no clamping; float -> int truncates toward zero)
+template <typename TI, typename TO>
+__global__ void cast_kernel(const TI* __restrict__ in, TO* __restrict__ out, size_t n)
+{
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) out[q] = (TO)in[q];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) minmax_partial_kernel(const T* __restrict__ in, size_t n, double* __restrict__ partial)
+{
+    double mn = DBL_MAX, mx = -DBL_MAX;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) {
+        const double v = (double)in[q];
+        mn = fmin(mn, v);
+        mx = fmax(mx, v);
+    }
+    __shared__ double sh[2][8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    if (lane == 0) {
+        sh[0][wid] = mn;
+        sh[1][wid] = mx;
+    }
+    __syncthreads();
+    if (wid == 0) {
+        mn = lane < 8 ? sh[0][lane] : DBL_MAX;
+        mx = lane < 8 ? sh[1][lane] : -DBL_MAX;
+        mn = warp_min(mn);
+        mx = warp_max(mx);
+        if (lane == 0) {
+            partial[2 * blockIdx.x] = mn;
+            partial[2 * blockIdx.x + 1] = mx;
+        }
+    }
+}
+__global__ void minmax_final_kernel(const double* __restrict__ partial, int nb, double* __restrict__ out)
+{
+    double mn = DBL_MAX, mx = -DBL_MAX;
+    for (int q = threadIdx.x; q < nb; q += 32) {
+        mn = fmin(mn, partial[2 * q]);
+        mx = fmax(mx, partial[2 * q + 1]);
+    }
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    if (threadIdx.x == 0) {
+        out[0] = mn;
+        out[1] = mx;
+    }
+}
+
+// device-resident min/max into d_out[0..1]
+template <typename T>
+inline int minmax_device(b200reg_ctx* ctx, const T* d_in, size_t n, double* d_out, TempBuf* partial)
+{
+    const int nb = ctx->sm_count * 4;
+    B200_TRY(partial->alloc(ctx, sizeof(double) * 2 * (size_t)nb));
+    minmax_partial_kernel<T><<<nb, 256, 0, ctx->stream>>>(d_in, n, partial->as<double>());
+    minmax_final_kernel<<<1, 32, 0, ctx->stream>>>(partial->as<double>(), nb, d_out);
+    ctx->launches += 2;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+
+// fixed-order sum of doubles: per-block partials then one block
+template <typename T, typename F>
+__global__ void __launch_bounds__(256) sum_partial_kernel(const T* __restrict__ in, size_t n, double* __restrict__ partial, F f)
+{
+    double s = 0.0;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) s += f(in[q]);
+    __shared__ double sh[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    s = warp_sum(s);
+    if (lane == 0) sh[wid] = s;
+    __syncthreads();
+    if (wid == 0) {
+        s = lane < 8 ? sh[lane] : 0.0;
+        s = warp_sum(s);
+        if (lane == 0) partial[blockIdx.x] = s;
+    }
+}
+
+// ---- compute_weight_map (fusion.py:148-177) -----------------------------------------------------------
+// SquaredDifferenceImageFilter: (double(a) - double(b))^2 cast to float
+__global__ void sqdiff_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, size_t n)
+{
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) {
+        const double d = (double)a[q] - (double)b[q];
+        out[q] = (float)(d * d);
+    }
+}
+// target * 0.0 + w  (keeps NaN/Inf propagation of the reference expression)
+__global__ void const_weight_kernel(const float* __restrict__ target, float* __restrict__ out, size_t n, const double* __restrict__ d_sum,
+                                    double factor, int use_sum)
+{
+    const float w = use_sum ? (float)(factor / d_sum[0]) : 1.0f;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) out[q] = target[q] * 0.0f + w;
+}
+// sitk.Pow(raw + eps, -1.0): std::pow in double, stored as float
+__global__ void local_weight_kernel(float* __restrict__ io, size_t n, double eps)
+{
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) {
+        const float r = (float)((double)io[q] + eps);
+        io[q] = (float)pow((double)r, -1.0);
+    }
+}
+__global__ void sum_final_kernel(const double* __restrict__ partial, int nb, double* __restrict__ out)
+{
+    double s = 0.0;
+    for (int q = threadIdx.x; q < nb; q += 32) s += partial[q];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) out[0] = s;
+}
+
+struct IdentF {
+    __device__ double operator()(float v) const { return (double)v; }
+};
+
+inline int weight_map(b200reg_ctx* ctx, const float* d_target, const float* d_moving, const b200reg_geom& g, int vote_type, double factor,
+                      double sigma, double epsilon, float* d_weight)
+{
+    const size_t n = nvox(g);
+    const int nb = ctx->sm_count * 8;
+    if (vote_type == 0) {
+        const_weight_kernel<<<nb, 256, 0, ctx->stream>>>(d_target, d_weight, n, nullptr, 0.0, 0);
+        ctx->launches++;
+    } else if (vote_type == 1) {
+        TempBuf sq, part, sum;
+        B200_TRY(sq.alloc(ctx, n * sizeof(float)));
+        B200_TRY(part.alloc(ctx, sizeof(double) * (size_t)nb));
+        B200_TRY(sum.alloc(ctx, sizeof(double)));
+        sqdiff_kernel<<<nb, 256, 0, ctx->stream>>>(d_target, d_moving, sq.as<float>(), n);
+        sum_partial_kernel<float, IdentF><<<nb, 256, 0, ctx->stream>>>(sq.as<float>(), n, part.as<double>(), IdentF());
+        sum_final_kernel<<<1, 32, 0, ctx->stream>>>(part.as<double>(), nb, sum.as<double>());
+        const_weight_kernel<<<nb, 256, 0, ctx->stream>>>(d_target, d_weight, n, sum.as<double>(), factor, 1);
+        ctx->launches += 4;
+    } else if (vote_type == 2) {
+        TempBuf sq;
+        B200_TRY(sq.alloc(ctx, n * sizeof(float)));
+        sqdiff_kernel<<<nb, 256, 0, ctx->stream>>>(d_target, d_moving, sq.as<float>(), n);
+        ctx->launches++;
+        const double var[3] = { sigma * sigma, sigma * sigma, sigma * sigma };
+        B200_TRY(discrete_gaussian_f32(ctx, sq.as<float>(), d_weight, g, var, 32, 0.01, 1));
+        local_weight_kernel<<<nb, 256, 0, ctx->stream>>>(d_weight, n, epsilon);
+        ctx->launches++;
+    } else {
+        return set_error(B200REG_ERR_UNSUPPORTED, "vote type %d is not supported (0 unweighted, 1 global, 2 local)", vote_type);
+    }
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+
+// ---- combine_labels (fusion.py:253-288) ---------------------------------------------------------------
+// float32 arithmetic in atlas order: num = sum_a w_a * float(L_a), den = sum_a w_a
+__global__ void vote_accumulate_kernel(const uint8_t* __restrict__ label, const float* __restrict__ w, float* __restrict__ num,
+                                       float* __restrict__ den, size_t n, int first)
+{
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) {
+        const float wv = w[q];
+        const float t = wv * (float)label[q];
+        if (first) {
+            num[q] = t;
+            if (den) den[q] = wv;
+        } else {
+            num[q] = num[q] + t;
+            if (den) den[q] = den[q] + wv;
+        }
+    }
+}
+// sitk.Mask(den, den == 0, maskingValue=1, outsideValue=1) then num / den
+__global__ void vote_divide_kernel(float* __restrict__ num, const float* __restrict__ den, size_t n)
+{
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) {
+        float d = den[q];
+        if (d == 0.0f) d = 1.0f;
+        num[q] = num[q] / d;
+    }
+}
+// RescaleIntensityImageFilter(0, 1) + ThresholdImageFilter(lower, 1, outside 0) with min/max on device
+template <typename T>
+__global__ void rescale_threshold_kernel(const T* in, T* out, size_t n, const double* __restrict__ mm, double threshold,
+                                         double type_eps, int rescale)
+{
+    const double mn = mm[0], mx = mm[1];
+    double scale, shift;
+    if (fabs((double)((T)mx - (T)mn)) > type_eps) scale = 1.0 / (mx - mn);
+    else if (mx != 0.0) scale = 1.0 / mx;
+    else scale = 0.0;
+    shift = 0.0 - mn * scale;
+    const T lower = (T)threshold;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) {
+        T r = in[q];
+        if (rescale) {
+            const double v = (double)r * scale + shift;
+            r = (T)v;
+            r = (r > (T)1) ? (T)1 : r;
+            r = (r < (T)0) ? (T)0 : r;
+        }
+        if (threshold != 0.0) {
+            if (!(r >= lower && r <= (T)1)) r = (T)0;
+        }
+        out[q] = r;
+    }
+}
+
+inline int vote_finalize(b200reg_ctx* ctx, float* d_num, const float* d_den, const b200reg_geom& g, double smooth_variance, double threshold,
+                         float* d_out)
+{
+    const size_t n = nvox(g);
+    const int nb = ctx->sm_count * 8;
+    if (d_den) {
+        vote_divide_kernel<<<nb, 256, 0, ctx->stream>>>(d_num, d_den, n);
+        ctx->launches++;
+    }
+    TempBuf sm, part, mm;
+    B200_TRY(sm.alloc(ctx, n * sizeof(float)));
+    const double var[3] = { smooth_variance, smooth_variance, smooth_variance };
+    B200_TRY(discrete_gaussian_f32(ctx, d_num, sm.as<float>(), g, var, 32, 0.01, 1));
+    B200_TRY(mm.alloc(ctx, 2 * sizeof(double)));
+    B200_TRY(minmax_device<float>(ctx, sm.as<float>(), n, mm.as<double>(), &part));
+    rescale_threshold_kernel<float><<<nb, 256, 0, ctx->stream>>>(sm.as<float>(), d_out, n, mm.as<double>(), threshold, (double)FLT_EPSILON, 1);
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+
+// ---- sitk.STAPLE (itk::STAPLEImageFilter), binary EM ---------------------------------------------------
+constexpr int STAPLE_MAX_RATERS = 32;
+struct StaplePtrs {
+    const uint8_t* d[STAPLE_MAX_RATERS];
+    int n;
+};
+struct StapleState {
+    double p[STAPLE_MAX_RATERS], q[STAPLE_MAX_RATERS], last_p[STAPLE_MAX_RATERS], last_q[STAPLE_MAX_RATERS];
+    double g;
+    int converged;
+    int elapsed;
+};
+
+// W = mean_j D_j ; partial sums of W for g
+__global__ void __launch_bounds__(256) staple_init_kernel(const __grid_constant__ StaplePtrs ptrs, double* __restrict__ W, size_t n,
+                                                           double* __restrict__ partial)
+{
+    double s = 0.0;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (size_t)gridDim.x * blockDim.x) {
+        double w = 0.0;
+        for (int j = 0; j < ptrs.n; ++j)
+            if (ptrs.d[j][v] == 1) w = w + 1.0;
+        w = w / (double)ptrs.n;
+        W[v] = w;
+        s += w;
+    }
+    __shared__ double sh[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    s = warp_sum(s);
+    if (lane == 0) sh[wid] = s;
+    __syncthreads();
+    if (wid == 0) {
+        s = lane < 8 ? sh[lane] : 0.0;
+        s = warp_sum(s);
+        if (lane == 0) partial[blockIdx.x] = s;
+    }
+}
+__global__ void staple_g_kernel(const double* __restrict__ partial, int nb, size_t n, double confidence, StapleState* st)
+{
+    double s = 0.0;
+    for (int q = threadIdx.x; q < nb; q += 32) s += partial[q];
+    s = warp_sum(s);
+    if (threadIdx.x == 0) {
+        st->g = (s / (double)n) * confidence;
+        st->converged = 0;
+        st->elapsed = 0;
+        for (int j = 0; j < STAPLE_MAX_RATERS; ++j) {
+            st->last_p[j] = -10.0;
+            st->last_q[j] = -10.0;
+        }
+    }
+}
+// M-step partial sums: for every rater sum_{D=1} W and sum_{D=0} (1 - W); plus sum W and sum (1 - W)
+__global__ void __launch_bounds__(256) staple_mstep_kernel(const __grid_constant__ StaplePtrs ptrs, const double* __restrict__ W, size_t n,
+                                                            double* __restrict__ partial, const StapleState* st)
+{
+    if (st->converged) return;
+    double pn[STAPLE_MAX_RATERS], qn[STAPLE_MAX_RATERS];
+    for (int j = 0; j < ptrs.n; ++j) pn[j] = qn[j] = 0.0;
+    double sw = 0.0, s1w = 0.0;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (size_t)gridDim.x * blockDim.x) {
+        const double w = W[v], w1 = 1.0 - w;
+        sw += w;
+        s1w += w1;
+        for (int j = 0; j < ptrs.n; ++j) {
+            if (ptrs.d[j][v] == 1) pn[j] += w;
+            else qn[j] += w1;
+        }
+    }
+    __shared__ double sh[8];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const int stride = 2 * ptrs.n + 2;
+    for (int t = 0; t < stride; ++t) {
+        double val = t < ptrs.n ? pn[t] : (t < 2 * ptrs.n ? qn[t - ptrs.n] : (t == 2 * ptrs.n ? sw : s1w));
+        val = warp_sum(val);
+        if (lane == 0) sh[wid] = val;
+        __syncthreads();
+        if (wid == 0) {
+            double x = lane < 8 ? sh[lane] : 0.0;
+            x = warp_sum(x);
+            if (lane == 0) partial[(size_t)blockIdx.x * stride + t] = x;
+        }
+        __syncthreads();
+    }
+}
+__global__ void staple_pq_kernel(const double* __restrict__ partial, int nb, int n_raters, StapleState* st)
+{
+    if (st->converged) return;
+    const int stride = 2 * n_raters + 2;
+    __shared__ double tot[2 * STAPLE_MAX_RATERS + 2];
+    for (int t = threadIdx.x >> 5; t < stride; t += blockDim.x >> 5) {
+        double s = 0.0;
+        for (int q = threadIdx.x & 31; q < nb; q += 32) s += partial[(size_t)q * stride + t];
+        s = warp_sum(s);
+        if ((threadIdx.x & 31) == 0) tot[t] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int j = 0; j < n_raters; ++j) {
+            st->p[j] = tot[j] / tot[2 * n_raters];
+            st->q[j] = tot[n_raters + j] / tot[2 * n_raters + 1];
+        }
+    }
+}
+// E-step
+__global__ void __launch_bounds__(256) staple_estep_kernel(const __grid_constant__ StaplePtrs ptrs, double* __restrict__ W, size_t n,
+                                                            const StapleState* st)
+{
+    if (st->converged) return;
+    const double g = st->g;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (size_t)gridDim.x * blockDim.x) {
+        double alpha1 = 1.0, beta1 = 1.0;
+        for (int j = 0; j < ptrs.n; ++j) {
+            if (ptrs.d[j][v] == 1) {
+                alpha1 = alpha1 * st->p[j];
+                beta1 = beta1 * (1.0 - st->q[j]);
+            } else {
+                alpha1 = alpha1 * (1.0 - st->p[j]);
+                beta1 = beta1 * st->q[j];
+            }
+        }
+        W[v] = g * alpha1 / (g * alpha1 + (1.0 - g) * beta1);
+    }
+}
+// convergence test after the E-step of iteration `iter`
+__global__ void staple_converge_kernel(StapleState* st, int n_raters, unsigned iter)
+{
+    if (st->converged) return;
+    bool flag = false;
+    if (iter != 0) {
+        flag = true;
+        for (int j = 0; j < n_raters; ++j) {
+            if (((st->p[j] - st->last_p[j]) * (st->p[j] - st->last_p[j])) > 1.0e-14) { flag = false; break; }
+            if (((st->q[j] - st->last_q[j]) * (st->q[j] - st->last_q[j])) > 1.0e-14) { flag = false; break; }
+        }
+    }
+    for (int j = 0; j < n_raters; ++j) {
+        st->last_p[j] = st->p[j];
+        st->last_q[j] = st->q[j];
+    }
+    st->elapsed = (int)iter;
+    if (flag) st->converged = 1;
+}
+
+}  // namespace b200

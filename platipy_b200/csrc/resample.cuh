@@ -1,0 +1,323 @@
+// resample.cuh -- itk::ResampleImageFilter for scalar volumes and 3-component f64 fields, with
+// identity / affine / displacement-field transform chains, nearest-neighbour and linear interpolation.
+//   N2 utils.py:257-267   N3 deformable.py:130,137,185   N5 deformable.py:140   N7 deformable.py:154
+//   N9 utils.py:176-190, deformable.py:281-301
+#pragma once
+#include "common.cuh"
+
+namespace b200 {
+
+struct TfmD {
+    int kind;
+    double matrix[9];
+    double offset[3];
+    const double* dvf;  // SoA planes
+    GeomD g;
+};
+struct ChainD {
+    int n;
+    int linear;  // every element affine -> ITK's scan-line path
+    TfmD t[B200REG_MAX_TRANSFORMS];
+};
+
+inline int make_chain(const b200reg_transform* chain, int n_chain, ChainD* out)
+{
+    if (n_chain < 0 || n_chain > B200REG_MAX_TRANSFORMS)
+        return set_error(B200REG_ERR_ARG, "transform chain length %d not in [0, %d]", n_chain, B200REG_MAX_TRANSFORMS);
+    if (n_chain > 0 && !chain) return set_error(B200REG_ERR_ARG, "null transform chain");
+    out->n = n_chain;
+    out->linear = 1;
+    for (int i = 0; i < n_chain; ++i) {
+        TfmD& t = out->t[i];
+        t.kind = chain[i].kind;
+        for (int k = 0; k < 9; ++k) t.matrix[k] = chain[i].matrix[k];
+        for (int k = 0; k < 3; ++k) t.offset[k] = chain[i].offset[k];
+        t.dvf = chain[i].d_dvf;
+        if (t.kind == B200REG_TFM_DVF) {
+            if (!t.dvf || !valid_geom(&chain[i].dvf_geom)) return set_error(B200REG_ERR_ARG, "invalid displacement-field transform");
+            t.g = make_geomd(chain[i].dvf_geom);
+            out->linear = 0;
+        } else if (t.kind != B200REG_TFM_AFFINE) {
+            return set_error(B200REG_ERR_ARG, "unknown transform kind %d", t.kind);
+        }
+    }
+    return B200REG_OK;
+}
+
+// VectorLinearInterpolateImageFunction (inside DisplacementFieldTransform): weighted sum over the 8
+// neighbours, bit k of the counter selects the upper neighbour in dim k, indices clamped into the
+// buffer, zero-overlap neighbours skipped, early exit when the accumulated overlap is exactly 1.
+__device__ __forceinline__ void interp_wsum_vec3(const double* __restrict__ f, const GeomD& g, const double* c, double* out)
+{
+    const int b[3] = { (int)floor(c[0]), (int)floor(c[1]), (int)floor(c[2]) };
+    const double d[3] = { c[0] - (double)b[0], c[1] - (double)b[1], c[2] - (double)b[2] };
+    const int n[3] = { g.nx, g.ny, g.nz };
+    const size_t plane = (size_t)g.nx * g.ny * g.nz;
+    out[0] = out[1] = out[2] = 0.0;
+    double total = 0.0;
+#pragma unroll
+    for (unsigned counter = 0; counter < 8; ++counter) {
+        double overlap = 1.0;
+        int ni[3];
+#pragma unroll
+        for (int dim = 0; dim < 3; ++dim) {
+            if ((counter >> dim) & 1u) {
+                ni[dim] = b[dim] + 1;
+                if (ni[dim] > n[dim] - 1) ni[dim] = n[dim] - 1;
+                overlap *= d[dim];
+            } else {
+                ni[dim] = b[dim];
+                if (ni[dim] < 0) ni[dim] = 0;
+                overlap *= 1.0 - d[dim];
+            }
+        }
+        if (overlap != 0.0) {
+            const size_t o = ((size_t)ni[2] * n[1] + ni[1]) * n[0] + ni[0];
+            out[0] += overlap * __ldg(f + o);
+            out[1] += overlap * __ldg(f + plane + o);
+            out[2] += overlap * __ldg(f + 2 * plane + o);
+            total += overlap;
+        }
+        if (total == 1.0) break;
+    }
+}
+
+__device__ __forceinline__ void apply_chain(const ChainD& ch, double* p)
+{
+    for (int i = 0; i < ch.n; ++i) {
+        const TfmD& t = ch.t[i];
+        if (t.kind == B200REG_TFM_AFFINE) {
+            double q[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                double sum = 0.0;
+                sum += t.matrix[r * 3 + 0] * p[0];
+                sum += t.matrix[r * 3 + 1] * p[1];
+                sum += t.matrix[r * 3 + 2] * p[2];
+                q[r] = sum + t.offset[r];
+            }
+            p[0] = q[0];
+            p[1] = q[1];
+            p[2] = q[2];
+        } else {
+            double c[3], dd[3];
+            pt2cidx(t.g, p, c);
+            if (inside_buffer(t.g, c)) {
+                interp_wsum_vec3(t.dvf, t.g, c, dd);
+                p[0] += dd[0];
+                p[1] += dd[1];
+                p[2] += dd[2];
+            }
+        }
+    }
+}
+
+// continuous input index of output voxel (i, j, k).  Linear chains follow
+// ResampleImageFilter::LinearThreadedGenerateData: continuous index at the first index of the row and at
+// one-past-the-last, interpolated with alpha = i / size_x.
+__device__ __forceinline__ void out_to_in_cidx(const GeomD& go, const GeomD& gi, const ChainD& ch, int i, int j, int k, double* c)
+{
+    double p[3];
+    if (!ch.linear) {
+        idx2pt(go, (double)i, (double)j, (double)k, p);
+        apply_chain(ch, p);
+        pt2cidx(gi, p, c);
+    } else {
+        double cs[3], ce[3];
+        idx2pt(go, 0.0, (double)j, (double)k, p);
+        apply_chain(ch, p);
+        pt2cidx(gi, p, cs);
+        idx2pt(go, (double)go.nx, (double)j, (double)k, p);
+        apply_chain(ch, p);
+        pt2cidx(gi, p, ce);
+        const double alpha = (double)i / (double)go.nx;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) c[r] = cs[r] + alpha * (ce[r] - cs[r]);
+    }
+}
+
+// LinearInterpolateImageFunction::EvaluateOptimized(Dispatch<3>): nested lerps x, y, z as
+// a + (b - a) * d in double.  Base index clamped up to 0 with non-positive distances treated as 0,
+// upper neighbours clamped to the last index: bit-identical to ITK's branchy form.
+struct LinW {
+    int b0, b1, b2, u0, u1, u2;
+    double d0, d1, d2;
+};
+__device__ __forceinline__ LinW lin_setup(const GeomD& g, const double* c)
+{
+    LinW w;
+    w.b0 = (int)floor(c[0]);
+    w.b1 = (int)floor(c[1]);
+    w.b2 = (int)floor(c[2]);
+    if (w.b0 < 0) w.b0 = 0;
+    if (w.b1 < 0) w.b1 = 0;
+    if (w.b2 < 0) w.b2 = 0;
+    w.d0 = c[0] - (double)w.b0;
+    w.d1 = c[1] - (double)w.b1;
+    w.d2 = c[2] - (double)w.b2;
+    if (w.d0 <= 0.) w.d0 = 0.;
+    if (w.d1 <= 0.) w.d1 = 0.;
+    if (w.d2 <= 0.) w.d2 = 0.;
+    w.u0 = w.b0 + 1 > g.nx - 1 ? g.nx - 1 : w.b0 + 1;
+    w.u1 = w.b1 + 1 > g.ny - 1 ? g.ny - 1 : w.b1 + 1;
+    w.u2 = w.b2 + 1 > g.nz - 1 ? g.nz - 1 : w.b2 + 1;
+    return w;
+}
+template <typename T>
+__device__ __forceinline__ double lin_eval(const T* __restrict__ img, const GeomD& g, const LinW& w)
+{
+    const size_t sy = (size_t)g.nx, sz = (size_t)g.nx * g.ny;
+    const size_t r00 = (size_t)w.b2 * sz + (size_t)w.b1 * sy, r10 = (size_t)w.b2 * sz + (size_t)w.u1 * sy;
+    const size_t r01 = (size_t)w.u2 * sz + (size_t)w.b1 * sy, r11 = (size_t)w.u2 * sz + (size_t)w.u1 * sy;
+    const double v000 = (double)__ldg(img + r00 + w.b0), v100 = (double)__ldg(img + r00 + w.u0);
+    const double v010 = (double)__ldg(img + r10 + w.b0), v110 = (double)__ldg(img + r10 + w.u0);
+    const double v001 = (double)__ldg(img + r01 + w.b0), v101 = (double)__ldg(img + r01 + w.u0);
+    const double v011 = (double)__ldg(img + r11 + w.b0), v111 = (double)__ldg(img + r11 + w.u0);
+    const double vx00 = v000 + (v100 - v000) * w.d0;
+    const double vx10 = v010 + (v110 - v010) * w.d0;
+    const double vxx0 = vx00 + (vx10 - vx00) * w.d1;
+    const double vx01 = v001 + (v101 - v001) * w.d0;
+    const double vx11 = v011 + (v111 - v011) * w.d0;
+    const double vxx1 = vx01 + (vx11 - vx01) * w.d1;
+    return vxx0 + (vxx1 - vxx0) * w.d2;
+}
+
+// One image of a batch
+struct BatchItem {
+    const void* in;
+    void* out;
+    int dtype;
+    int interp;
+    double default_value;
+};
+constexpr int RESAMPLE_BATCH = 8;
+struct BatchD {
+    int n;
+    BatchItem item[RESAMPLE_BATCH];
+};
+
+template <typename T>
+__device__ __forceinline__ void resample_one(const BatchItem& it, const GeomD& gi, const double* c, bool inside, size_t o)
+{
+    const T* in = reinterpret_cast<const T*>(it.in);
+    T* out = reinterpret_cast<T*>(it.out);
+    if (inside) {
+        double v;
+        if (it.interp == B200REG_INTERP_NN) {
+            // NearestNeighborInterpolateImageFunction: RoundHalfIntegerUp = floor(x + 0.5)
+            const int i0 = (int)floor(c[0] + 0.5), i1 = (int)floor(c[1] + 0.5), i2 = (int)floor(c[2] + 0.5);
+            v = Px<T>::ld(in, ((size_t)i2 * gi.ny + i1) * gi.nx + i0);
+        } else {
+            const LinW w = lin_setup(gi, c);
+            v = lin_eval<T>(in, gi, w);
+        }
+        out[o] = Px<T>::cast(v);
+    } else {
+        out[o] = Px<T>::cast(it.default_value);
+    }
+}
+
+__global__ void __launch_bounds__(BX* BY) resample_batch_kernel(const __grid_constant__ BatchD batch, const __grid_constant__ GeomD gi,
+                                                                 const __grid_constant__ GeomD go, const __grid_constant__ ChainD ch)
+{
+    const int i = blockIdx.x * BX + threadIdx.x;
+    const int j = blockIdx.y * BY + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= go.nx || j >= go.ny) return;
+    double c[3];
+    out_to_in_cidx(go, gi, ch, i, j, k, c);
+    const bool inside = inside_buffer(gi, c);
+    const size_t o = ((size_t)k * go.ny + j) * go.nx + i;
+    for (int b = 0; b < batch.n; ++b) {
+        const BatchItem& it = batch.item[b];
+        switch (it.dtype) {
+        case B200REG_I8: resample_one<int8_t>(it, gi, c, inside, o); break;
+        case B200REG_U8: resample_one<uint8_t>(it, gi, c, inside, o); break;
+        case B200REG_I16: resample_one<int16_t>(it, gi, c, inside, o); break;
+        case B200REG_U16: resample_one<uint16_t>(it, gi, c, inside, o); break;
+        case B200REG_I32: resample_one<int32_t>(it, gi, c, inside, o); break;
+        case B200REG_U32: resample_one<uint32_t>(it, gi, c, inside, o); break;
+        case B200REG_I64: resample_one<int64_t>(it, gi, c, inside, o); break;
+        case B200REG_U64: resample_one<uint64_t>(it, gi, c, inside, o); break;
+        case B200REG_F32: resample_one<float>(it, gi, c, inside, o); break;
+        default: resample_one<double>(it, gi, c, inside, o); break;
+        }
+    }
+}
+
+inline int resample_batch(b200reg_ctx* ctx, int n, const void* const* d_in, const int* dtypes, const b200reg_geom& gin,
+                          void* const* d_out, const b200reg_geom& gout, const b200reg_transform* chain, int n_chain,
+                          const int* interps, const double* defaults)
+{
+    ChainD ch;
+    B200_TRY(make_chain(chain, n_chain, &ch));
+    const GeomD gi = make_geomd(gin), go = make_geomd(gout);
+    for (int i = 0; i < n; ++i) {
+        if (!d_in[i] || !d_out[i]) return set_error(B200REG_ERR_ARG, "null image pointer in resample batch");
+        if (dtype_size(dtypes[i]) == 0) return set_error(B200REG_ERR_ARG, "unsupported pixel type %d", dtypes[i]);
+        if (interps[i] != B200REG_INTERP_NN && interps[i] != B200REG_INTERP_LINEAR)
+            return set_error(B200REG_ERR_UNSUPPORTED, "interpolator %d is not supported (nearest neighbour = 1, linear = 2)", interps[i]);
+    }
+    for (int start = 0; start < n; start += RESAMPLE_BATCH) {
+        BatchD b;
+        b.n = (n - start) < RESAMPLE_BATCH ? (n - start) : RESAMPLE_BATCH;
+        for (int q = 0; q < b.n; ++q) b.item[q] = BatchItem{ d_in[start + q], d_out[start + q], dtypes[start + q], interps[start + q], defaults[start + q] };
+        resample_batch_kernel<<<grid3(go.nx, go.ny, go.nz), block3(), 0, ctx->stream>>>(b, gi, go, ch);
+        ctx->launches++;
+        B200_CHECK_LAUNCH();
+    }
+    return B200REG_OK;
+}
+
+// ---- vector (f64 x 3, SoA) --------------------------------------------------------------------------
+// LinearInterpolateImageFunction on a VectorImage: the same nested-lerp form, per component.
+// ACCUM: out = acc + value (dvf_total + Resample(dvf_iter, tfm_total), deformable.py:154).
+template <bool ACCUM>
+__global__ void __launch_bounds__(BX* BY) resample_vec3_kernel(const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ acc,
+                                                                const __grid_constant__ GeomD gi, const __grid_constant__ GeomD go,
+                                                                const __grid_constant__ ChainD ch, double default_value)
+{
+    const int i = blockIdx.x * BX + threadIdx.x;
+    const int j = blockIdx.y * BY + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= go.nx || j >= go.ny) return;
+    double c[3];
+    out_to_in_cidx(go, gi, ch, i, j, k, c);
+    const size_t o = ((size_t)k * go.ny + j) * go.nx + i;
+    const size_t po = (size_t)go.nx * go.ny * go.nz, pi = (size_t)gi.nx * gi.ny * gi.nz;
+    double v[3];
+    if (inside_buffer(gi, c)) {
+        const LinW w = lin_setup(gi, c);
+        v[0] = lin_eval<double>(in, gi, w);
+        v[1] = lin_eval<double>(in + pi, gi, w);
+        v[2] = lin_eval<double>(in + 2 * pi, gi, w);
+    } else {
+        v[0] = v[1] = v[2] = default_value;
+    }
+    if (ACCUM) {
+        out[o] = acc[o] + v[0];
+        out[o + po] = acc[o + po] + v[1];
+        out[o + 2 * po] = acc[o + 2 * po] + v[2];
+    } else {
+        out[o] = v[0];
+        out[o + po] = v[1];
+        out[o + 2 * po] = v[2];
+    }
+}
+
+inline int resample_vec3(b200reg_ctx* ctx, const double* d_in, const b200reg_geom& gin, double* d_out, const b200reg_geom& gout,
+                         const b200reg_transform* chain, int n_chain, double default_value, const double* d_acc = nullptr)
+{
+    ChainD ch;
+    B200_TRY(make_chain(chain, n_chain, &ch));
+    const GeomD gi = make_geomd(gin), go = make_geomd(gout);
+    if (d_acc)
+        resample_vec3_kernel<true><<<grid3(go.nx, go.ny, go.nz), block3(), 0, ctx->stream>>>(d_in, d_out, d_acc, gi, go, ch, default_value);
+    else
+        resample_vec3_kernel<false><<<grid3(go.nx, go.ny, go.nz), block3(), 0, ctx->stream>>>(d_in, d_out, nullptr, gi, go, ch, default_value);
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+
+}  // namespace b200

@@ -1,0 +1,369 @@
+"""
+Device plumbing: one ``Engine`` per GPU owns a CUDA stream (a ``torch.cuda.Stream``), the ``b200reg`` context
+bound to it, and wraps every C-ABI entry point on ``DeviceImage`` handles.
+
+PyTorch is used only for device/pinned memory, the stream and (in ``platipy_b200.multiatlas``) the NCCL
+process group; all arithmetic is done by the CUDA kernels of ``libb200reg.so``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import threading
+
+import numpy as np
+import torch
+
+from . import _abi
+from . import sitk_compat as sk
+from .sitk_compat import Image
+
+# numpy dtype -> (b200reg dtype id, torch container dtype of the same width)
+_DT = {
+    np.dtype(np.int8): (0, torch.int8), np.dtype(np.uint8): (1, torch.uint8),
+    np.dtype(np.int16): (2, torch.int16), np.dtype(np.uint16): (3, torch.int16),
+    np.dtype(np.int32): (4, torch.int32), np.dtype(np.uint32): (5, torch.int32),
+    np.dtype(np.int64): (6, torch.int64), np.dtype(np.uint64): (7, torch.int64),
+    np.dtype(np.float32): (8, torch.float32), np.dtype(np.float64): (9, torch.float64),
+}
+_SIGNED_VIEW = {np.dtype(np.uint16): np.int16, np.dtype(np.uint32): np.int32, np.dtype(np.uint64): np.int64}
+
+
+def _as_torch_host(arr):
+    """numpy array -> torch CPU tensor sharing memory (unsigned types travel in a signed container)."""
+    arr = np.ascontiguousarray(arr)
+    if arr.dtype in _SIGNED_VIEW:
+        arr = arr.view(_SIGNED_VIEW[arr.dtype])
+    return torch.from_numpy(arr)
+
+
+class DeviceImage:
+    """A volume resident in HBM.  Scalar: tensor ``[z, y, x]``.  Vector (f64 x 3): SoA tensor ``[3, z, y, x]``."""
+
+    __slots__ = ("tensor", "np_dtype", "spacing", "origin", "direction", "is_vector")
+
+    def __init__(self, tensor, np_dtype, spacing, origin, direction, is_vector=False):
+        self.tensor = tensor
+        self.np_dtype = np.dtype(np_dtype)
+        self.spacing = tuple(float(s) for s in spacing)
+        self.origin = tuple(float(s) for s in origin)
+        self.direction = tuple(float(s) for s in direction)
+        self.is_vector = bool(is_vector)
+
+    def GetSize(self):
+        z, y, x = self.tensor.shape[-3:]
+        return (int(x), int(y), int(z))
+
+    def GetSpacing(self):
+        return self.spacing
+
+    def GetOrigin(self):
+        return self.origin
+
+    def GetDirection(self):
+        return self.direction
+
+    def GetPixelID(self):
+        return sk.dtype_to_pixel_id(self.np_dtype, self.is_vector)
+
+    def GetNumberOfPixels(self):
+        x, y, z = self.GetSize()
+        return x * y * z
+
+    @property
+    def ptr(self):
+        return C.c_void_p(self.tensor.data_ptr())
+
+    @property
+    def geom(self):
+        return _abi.make_geom(self.GetSize(), self.spacing, self.origin, self.direction)
+
+    @property
+    def dtype_id(self):
+        return _DT[self.np_dtype][0]
+
+    def like(self, tensor, np_dtype=None, is_vector=None):
+        return DeviceImage(tensor, self.np_dtype if np_dtype is None else np_dtype, self.spacing, self.origin, self.direction,
+                           self.is_vector if is_vector is None else is_vector)
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by pinned host memory (keeps the owning tensor alive through ``.base``)."""
+    dtype = np.dtype(dtype)
+    container = _DT[dtype][1]
+    t = torch.empty(tuple(int(s) for s in shape), dtype=container, pin_memory=True)
+    a = t.numpy()
+    if dtype in _SIGNED_VIEW:
+        a = a.view(dtype)
+    return a
+
+
+def pinned_image(image):
+    """Copy of ``image`` whose pixel buffer lives in pinned host memory (fast H2D)."""
+    image = sk.to_native(image)
+    buf = pinned_empty(image.array.shape, image.array.dtype)
+    np.copyto(buf, image.array)
+    out = Image.__new__(Image)
+    out._arr = buf
+    out._spacing, out._origin, out._direction, out._is_vector = image._spacing, image._origin, image._direction, image._is_vector
+    return out
+
+
+class Engine:
+    """Per-GPU engine; ``Engine.get()`` returns the singleton of the current (or given) CUDA device."""
+
+    _instances = {}
+    _lock = threading.Lock()
+
+    @classmethod
+    def get(cls, device=None):
+        if not torch.cuda.is_available():
+            raise RuntimeError("platipy_b200 needs a CUDA device (sm_100a); no CPU fallback exists")
+        if device is None:
+            device = torch.cuda.current_device()
+        device = int(torch.device("cuda", device).index if not isinstance(device, int) else device)
+        with cls._lock:
+            if device not in cls._instances:
+                cls._instances[device] = cls(device)
+            return cls._instances[device]
+
+    def __init__(self, device):
+        self.lib = _abi.load()
+        self.device = torch.device("cuda", device)
+        with torch.cuda.device(self.device):
+            self.stream = torch.cuda.Stream(device=self.device)
+        ctx = C.c_void_p()
+        _abi.check(self.lib.b200reg_create(device, C.c_void_p(self.stream.cuda_stream), C.byref(ctx)))
+        self.ctx = ctx
+
+    # -- memory -------------------------------------------------------------------------------------
+    def empty(self, shape, np_dtype):
+        with torch.cuda.stream(self.stream):
+            return torch.empty(tuple(int(s) for s in shape), dtype=_DT[np.dtype(np_dtype)][1], device=self.device)
+
+    def zeros(self, shape, np_dtype):
+        with torch.cuda.stream(self.stream):
+            return torch.zeros(tuple(int(s) for s in shape), dtype=_DT[np.dtype(np_dtype)][1], device=self.device)
+
+    def synchronize(self):
+        _abi.check(self.lib.b200reg_synchronize(self.ctx))
+
+    def launch_count(self):
+        return int(self.lib.b200reg_launch_count(self.ctx))
+
+    def to_device(self, image):
+        """Host ``Image`` -> ``DeviceImage`` (vector images are converted AoS -> SoA on the device)."""
+        if isinstance(image, DeviceImage):
+            return image
+        image = sk.to_native(image)
+        host = _as_torch_host(image.array)
+        with torch.cuda.stream(self.stream):
+            dev = host.to(self.device, non_blocking=True)
+        if image.is_vector:
+            if image.array.dtype != np.float64 or image.array.shape[3] != 3:
+                raise RuntimeError("only 3-component sitkVectorFloat64 fields are supported")
+            n = image.GetNumberOfPixels()
+            z, y, x = image.array.shape[:3]
+            soa = self.empty((3, z, y, x), np.float64)
+            _abi.check(self.lib.b200reg_aos_to_soa(self.ctx, C.c_void_p(dev.data_ptr()), C.c_void_p(soa.data_ptr()), n))
+            dev.record_stream(self.stream)
+            dev = soa
+        return DeviceImage(dev, image.array.dtype, image.GetSpacing(), image.GetOrigin(), image.GetDirection(), image.is_vector)
+
+    def to_host(self, dimg, pinned=True):
+        """``DeviceImage`` -> host ``Image`` (vector fields come back as AoS ``[z, y, x, 3]``).  Synchronises."""
+        x, y, z = dimg.GetSize()
+        if dimg.is_vector:
+            aos = self.empty((z, y, x, 3), np.float64)
+            _abi.check(self.lib.b200reg_soa_to_aos(self.ctx, dimg.ptr, C.c_void_p(aos.data_ptr()), dimg.GetNumberOfPixels()))
+            src, shape = aos, (z, y, x, 3)
+        else:
+            src, shape = dimg.tensor, (z, y, x)
+        host = pinned_empty(shape, dimg.np_dtype) if pinned else np.empty(shape, dimg.np_dtype)
+        _abi.check(self.lib.b200reg_memcpy_d2h(self.ctx, host.ctypes.data_as(C.c_void_p), C.c_void_p(src.data_ptr()), host.nbytes))
+        self.synchronize()
+        out = Image.__new__(Image)
+        out._arr = host
+        out._spacing, out._origin, out._direction, out._is_vector = dimg.spacing, dimg.origin, dimg.direction, dimg.is_vector
+        return out
+
+    # -- transform chains ---------------------------------------------------------------------------
+    def chain(self, transform):
+        """sitk-style transform object -> (ctypes Transform array, n, keep-alive list).  Displacement fields
+        are uploaded once and cached on the transform object (reference multiatlas/run.py:331-345 re-uses
+        one transform for the CT and every structure)."""
+        flat = [] if transform is None else transform.flatten()
+        if len(flat) > _abi.MAX_TRANSFORMS:
+            raise ValueError(f"transform chain longer than {_abi.MAX_TRANSFORMS}")
+        arr = (_abi.Transform * max(len(flat), 1))()
+        keep = []
+        for i, t in enumerate(flat):
+            if isinstance(t, sk.DisplacementFieldTransform):
+                cache = t._device_cache
+                if cache is None or cache[0] is not self:
+                    d = self.to_device(t.GetDisplacementField())
+                    t._device_cache = cache = (self, d)
+                d = cache[1]
+                arr[i].kind = _abi.TFM_DVF
+                arr[i].d_dvf = d.tensor.data_ptr()
+                arr[i].dvf_geom = d.geom
+                keep.append(d)
+            elif isinstance(t, sk.AffineTransform):
+                arr[i].kind = _abi.TFM_AFFINE
+                m, o = t.matrix.reshape(9), t.offset
+                for k in range(9):
+                    arr[i].matrix[k] = float(m[k])
+                for k in range(3):
+                    arr[i].offset[k] = float(o[k])
+            else:
+                raise NotImplementedError(f"transform type {type(t).__name__} is not supported")
+        return arr, len(flat), keep
+
+    # -- ops ------------------------------------------------------------------------------------------
+    def cast(self, dimg, np_dtype):
+        np_dtype = np.dtype(np_dtype)
+        if np_dtype == dimg.np_dtype:
+            return dimg
+        out = self.empty(dimg.tensor.shape, np_dtype)
+        _abi.check(self.lib.b200reg_cast(self.ctx, dimg.ptr, dimg.dtype_id, C.c_void_p(out.data_ptr()), _DT[np_dtype][0], dimg.tensor.numel()))
+        return dimg.like(out, np_dtype)
+
+    def minmax(self, dimg):
+        mn, mx = C.c_double(), C.c_double()
+        _abi.check(self.lib.b200reg_minmax(self.ctx, dimg.ptr, dimg.dtype_id, dimg.tensor.numel(), C.byref(mn), C.byref(mx)))
+        return mn.value, mx.value
+
+    def discrete_gaussian(self, dimg, variance, maximum_kernel_width=32, maximum_error=0.01, use_image_spacing=True):
+        if dimg.np_dtype != np.float32:
+            raise NotImplementedError("DiscreteGaussian is implemented for Float32 images")
+        var = (C.c_double * 3)(*([float(variance)] * 3 if np.isscalar(variance) else [float(v) for v in variance]))
+        out = self.empty(dimg.tensor.shape, np.float32)
+        g = dimg.geom
+        _abi.check(self.lib.b200reg_discrete_gaussian_f32(self.ctx, dimg.ptr, C.c_void_p(out.data_ptr()), C.byref(g), var,
+                                                          int(maximum_kernel_width), float(maximum_error), int(bool(use_image_spacing))))
+        return dimg.like(out)
+
+    def resample_batch(self, images, out_geom_src, transform, interpolators, default_values):
+        """N images on one grid through one transform chain onto the grid of ``out_geom_src`` (anything
+        with GetSize/GetSpacing/GetOrigin/GetDirection)."""
+        n = len(images)
+        gin = images[0].geom
+        for im in images[1:]:
+            if im.GetSize() != images[0].GetSize():
+                raise ValueError("resample_batch: all inputs must share one grid")
+        gout = _abi.geom_of(out_geom_src)
+        x, y, z = out_geom_src.GetSize()
+        outs = [self.empty((z, y, x), im.np_dtype) for im in images]
+        ins_p = (C.c_void_p * n)(*[im.tensor.data_ptr() for im in images])
+        outs_p = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+        dts = (C.c_int * n)(*[im.dtype_id for im in images])
+        ips = (C.c_int * n)(*[int(i) for i in interpolators])
+        dvs = (C.c_double * n)(*[float(d) for d in default_values])
+        chain, nch, keep = self.chain(transform)
+        _abi.check(self.lib.b200reg_resample_batch(self.ctx, n, ins_p, dts, C.byref(gin), outs_p, C.byref(gout), chain, nch, ips, dvs))
+        sp, og, dr = out_geom_src.GetSpacing(), out_geom_src.GetOrigin(), out_geom_src.GetDirection()
+        return [DeviceImage(o, im.np_dtype, sp, og, dr, False) for o, im in zip(outs, images)]
+
+    def resample(self, dimg, out_geom_src=None, transform=None, interpolator=sk.sitkLinear, default_value=0.0):
+        if out_geom_src is None:
+            out_geom_src = dimg
+        if dimg.is_vector:
+            return self.resample_vec3(dimg, out_geom_src, transform, default_value)
+        return self.resample_batch([dimg], out_geom_src, transform, [interpolator], [default_value])[0]
+
+    def resample_vec3(self, dfield, out_geom_src, transform=None, default_value=0.0):
+        gin, gout = dfield.geom, _abi.geom_of(out_geom_src)
+        x, y, z = out_geom_src.GetSize()
+        out = self.empty((3, z, y, x), np.float64)
+        chain, nch, keep = self.chain(transform)
+        _abi.check(self.lib.b200reg_resample_vec3(self.ctx, dfield.ptr, C.byref(gin), C.c_void_p(out.data_ptr()), C.byref(gout), chain, nch,
+                                                  float(default_value)))
+        return DeviceImage(out, np.float64, out_geom_src.GetSpacing(), out_geom_src.GetOrigin(), out_geom_src.GetDirection(), True)
+
+    def compose_dvf(self, total, iter_field):
+        """total <- total + Resample(iter_field, DisplacementFieldTransform(total))  (deformable.py:154)."""
+        scratch = self.empty(total.tensor.shape, np.float64)
+        g = total.geom
+        _abi.check(self.lib.b200reg_compose_dvf(self.ctx, total.ptr, iter_field.ptr, C.byref(g), C.c_void_p(scratch.data_ptr())))
+        return total
+
+    def recursive_gaussian(self, dfield, sigma):
+        s = (C.c_double * 3)(*[float(v) for v in sigma])
+        g = dfield.geom
+        _abi.check(self.lib.b200reg_recursive_gaussian_vec3(self.ctx, dfield.ptr, C.byref(g), s))
+        return dfield
+
+    def pde_smooth_field(self, dfield, std_dev, max_error=0.1, max_kernel_width=30):
+        s = (C.c_double * 3)(*[float(v) for v in std_dev])
+        g = dfield.geom
+        _abi.check(self.lib.b200reg_pde_smooth_field(self.ctx, dfield.ptr, C.byref(g), s, float(max_error), int(max_kernel_width)))
+        return dfield
+
+    def pyramid_geom(self, src, isotropic, resolution):
+        gin, gout = _abi.geom_of(src), _abi.Geom()
+        _abi.check(self.lib.b200reg_pyramid_geom(C.byref(gin), int(bool(isotropic)), float(resolution), C.byref(gout)))
+        return gout
+
+    def demons_execute(self, fixed, moving, params):
+        x, y, z = fixed.GetSize()
+        out = self.empty((3, z, y, x), np.float64)
+        st = _abi.DemonsStats()
+        gf, gm = fixed.geom, moving.geom
+        _abi.check(self.lib.b200reg_demons_execute(self.ctx, fixed.ptr, C.byref(gf), moving.ptr, C.byref(gm), C.byref(params),
+                                                   C.c_void_p(out.data_ptr()), C.byref(st)))
+        stats = {"elapsed_iterations": st.elapsed_iterations, "metric": st.metric, "rms_change": st.rms_change, "gpu_ms": st.gpu_ms,
+                 "voxels": fixed.GetNumberOfPixels()}
+        return fixed.like(out, np.float64, True), stats
+
+    def demons_force(self, fixed, moving, field, params):
+        x, y, z = fixed.GetSize()
+        w = self.empty((z, y, x), np.float32)
+        u = self.empty((3, z, y, x), np.float64)
+        metric, rms = C.c_double(), C.c_double()
+        gf, gm = fixed.geom, moving.geom
+        _abi.check(self.lib.b200reg_demons_force(self.ctx, fixed.ptr, C.byref(gf), moving.ptr, C.byref(gm), field.ptr, C.byref(params),
+                                                 C.c_void_p(w.data_ptr()), C.c_void_p(u.data_ptr()), C.byref(metric), C.byref(rms)))
+        return fixed.like(w, np.float32, False), fixed.like(u, np.float64, True), metric.value, rms.value
+
+    def multiscale_demons(self, fixed, moving, cfg, initial_field=None):
+        x, y, z = fixed.GetSize()
+        out = self.empty((3, z, y, x), np.float64)
+        stats = (_abi.DemonsStats * max(cfg.n_levels, 1))()
+        gf, gm = fixed.geom, moving.geom
+        gi = initial_field.geom if initial_field is not None else None
+        _abi.check(self.lib.b200reg_multiscale_demons(
+            self.ctx, fixed.ptr, C.byref(gf), moving.ptr, C.byref(gm), C.byref(cfg),
+            initial_field.ptr if initial_field is not None else None, C.byref(gi) if gi is not None else None,
+            C.c_void_p(out.data_ptr()), stats))
+        level_stats = [{"elapsed_iterations": s.elapsed_iterations, "metric": s.metric, "rms_change": s.rms_change, "gpu_ms": s.gpu_ms,
+                        "voxels": s.voxels_lo} for s in stats[: cfg.n_levels]]
+        return fixed.like(out, np.float64, True), level_stats
+
+    # -- fusion ------------------------------------------------------------------------------------------
+    def weight_map(self, target, moving, vote_type, factor=1e12, sigma=2.0, epsilon=1e-5):
+        out = self.empty(target.tensor.shape, np.float32)
+        g = target.geom
+        _abi.check(self.lib.b200reg_weight_map(self.ctx, target.ptr, moving.ptr, C.byref(g), int(vote_type), float(factor), float(sigma),
+                                               float(epsilon), C.c_void_p(out.data_ptr())))
+        return target.like(out, np.float32, False)
+
+    def vote_accumulate(self, label, weight, num, den, first):
+        _abi.check(self.lib.b200reg_vote_accumulate(self.ctx, label.ptr, weight.ptr, C.c_void_p(num.data_ptr()),
+                                                    C.c_void_p(den.data_ptr()) if den is not None else None, label.tensor.numel(), int(bool(first))))
+
+    def vote_finalize(self, num, den, geom_src, smooth_variance, threshold):
+        out = self.empty(num.shape, np.float32)
+        g = _abi.geom_of(geom_src)
+        _abi.check(self.lib.b200reg_vote_finalize(self.ctx, C.c_void_p(num.data_ptr()), C.c_void_p(den.data_ptr()) if den is not None else None,
+                                                  C.byref(g), float(smooth_variance), float(threshold or 0.0), C.c_void_p(out.data_ptr())))
+        return DeviceImage(out, np.float32, geom_src.GetSpacing(), geom_src.GetOrigin(), geom_src.GetDirection(), False)
+
+    def staple(self, decisions, confidence_weight=1.0, max_iterations=0xFFFFFFFF, threshold=1e-4, rescale=True):
+        n = len(decisions)
+        ptrs = (C.c_void_p * n)(*[d.tensor.data_ptr() for d in decisions])
+        out = self.empty(decisions[0].tensor.shape, np.float64)
+        pq = (C.c_double * (2 * n))()
+        elapsed = C.c_int32()
+        _abi.check(self.lib.b200reg_staple(self.ctx, ptrs, n, decisions[0].tensor.numel(), float(confidence_weight), C.c_uint32(max_iterations),
+                                           float(threshold or 0.0), int(bool(rescale)), C.c_void_p(out.data_ptr()), pq, C.byref(elapsed)))
+        info = {"p": list(pq[:n]), "q": list(pq[n:]), "elapsed_iterations": elapsed.value}
+        return decisions[0].like(out, np.float64, False), info

@@ -1,0 +1,362 @@
+"""
+Drop-in replacements for the reference's registration entry points, running on one B200.
+
+    fast_symmetric_forces_demons_registration   platipy/imaging/registration/deformable.py:190-306
+    multiscale_demons                           platipy/imaging/registration/deformable.py:31-187
+    apply_transform / apply_linear_transform / apply_deformable_transform
+                                                platipy/imaging/registration/utils.py:54-192
+    smooth_and_resample                         platipy/imaging/registration/utils.py:195-267
+    FastSymmetricForcesDemonsRegistrationFilter the method set of the SimpleITK filter the reference uses
+                                                (deformable.py:244-257,143-149,157; utils.py:41)
+
+Signatures, defaults, argument meaning and error classes follow the reference.  Inputs may be host images
+(``sitk_compat.Image`` or real ``SimpleITK.Image``) or ``DeviceImage`` handles; host inputs give host outputs
+of the same kind, device inputs give device outputs (nothing leaves HBM).
+"""
+from __future__ import annotations
+
+import logging
+
+import numpy as np
+
+from . import _abi
+from . import sitk_compat as sk
+from .engine import DeviceImage, Engine
+
+logger = logging.getLogger(__name__)
+
+sitkNearestNeighbor, sitkLinear, sitkBSpline = sk.sitkNearestNeighbor, sk.sitkLinear, sk.sitkBSpline
+
+
+def _check_interp(interpolator):
+    if interpolator == sk.sitkBSpline:
+        raise NotImplementedError("B-spline interpolation is not implemented on the B200 path yet (SURVEY 8f-3)")
+    if interpolator not in (sk.sitkNearestNeighbor, sk.sitkLinear):
+        raise ValueError(f"unknown interpolator {interpolator!r}")
+    return int(interpolator)
+
+
+def _is_device(image):
+    return isinstance(image, DeviceImage)
+
+
+def _back(eng, dimg, like):
+    """Return ``dimg`` in the form of ``like``: device handle, stand-in Image or real SimpleITK image."""
+    if _is_device(like):
+        return dimg
+    return sk.from_native(eng.to_host(dimg), like)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# smooth_and_resample (utils.py:195-267)
+# ---------------------------------------------------------------------------------------------------------
+def smooth_and_resample(image, isotropic_voxel_size_mm=None, shrink_factor=None, smoothing_sigma=None,
+                        interpolator=sitkLinear):
+    eng = Engine.get()
+    d = eng.to_device(image)
+    if smoothing_sigma:
+        if hasattr(smoothing_sigma, "__iter__"):
+            variance = [s * s for s in smoothing_sigma]
+        else:
+            variance = (smoothing_sigma ** 2,) * 3
+        max_width = int(max(8 * v * sp for sp, v in zip(d.GetSpacing(), variance)))
+        d = eng.discrete_gaussian(d, variance, max_width)
+
+    size_o, spacing_o = d.GetSize(), d.GetSpacing()
+    if shrink_factor and isotropic_voxel_size_mm:
+        raise AttributeError("Function must be called with either isotropic_voxel_size_mm or shrink_factor, not both.")
+    elif isotropic_voxel_size_mm:
+        scale = isotropic_voxel_size_mm * np.ones_like(size_o) / np.array(spacing_o)
+        size_n = [int(sz / float(sf) + 0.5) for sz, sf in zip(size_o, scale)]
+    elif shrink_factor:
+        if isinstance(shrink_factor, list):
+            size_n = [int(sz / float(sf) + 0.5) for sz, sf in zip(size_o, shrink_factor)]
+        else:
+            size_n = [int(sz / float(shrink_factor) + 0.5) for sz in size_o]
+    else:
+        return _back(eng, d, image)
+    spacing_n = [((so - 1) * sp) / (sn - 1) for so, sp, sn in zip(size_o, spacing_o, size_n)]
+
+    class _Grid:
+        def GetSize(self):
+            return tuple(size_n)
+
+        def GetSpacing(self):
+            return tuple(spacing_n)
+
+        def GetOrigin(self):
+            return d.GetOrigin()
+
+        def GetDirection(self):
+            return d.GetDirection()
+
+    out = eng.resample(d, _Grid(), None, _check_interp(interpolator), 0.0)
+    return _back(eng, out, image)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# apply_transform family (utils.py:54-192)
+# ---------------------------------------------------------------------------------------------------------
+def apply_transform(input_image, reference_image=None, transform=None, default_value=0, interpolator=sitkNearestNeighbor):
+    """Resample ``input_image`` onto ``reference_image`` (or its own grid) through ``transform``.
+    Output pixel type = input pixel type (utils.py:174,190)."""
+    eng = Engine.get()
+    d = eng.to_device(input_image)
+    ref = reference_image if reference_image else input_image
+    out = eng.resample(d, ref, transform, _check_interp(interpolator), default_value)
+    return _back(eng, out, input_image)
+
+
+def apply_transform_batch(input_images, reference_image=None, transform=None, default_values=None, interpolators=None):
+    """Batched form of the reference's call pattern (multiatlas/run.py:331-345): one CT plus S label masks
+    on the same grid through the same transform; the transform (and the displacement field behind it) is
+    evaluated once per output voxel instead of S+1 times."""
+    eng = Engine.get()
+    n = len(input_images)
+    default_values = [0] * n if default_values is None else list(default_values)
+    interpolators = [sitkNearestNeighbor] * n if interpolators is None else list(interpolators)
+    ds = [eng.to_device(im) for im in input_images]
+    ref = reference_image if reference_image else input_images[0]
+    outs = []
+    for s in range(0, n, _abi.MAX_BATCH):
+        outs += eng.resample_batch(ds[s:s + _abi.MAX_BATCH], ref, transform, [_check_interp(i) for i in interpolators[s:s + _abi.MAX_BATCH]],
+                                   default_values[s:s + _abi.MAX_BATCH])
+    return [_back(eng, o, im) for o, im in zip(outs, input_images)]
+
+
+def apply_linear_transform(input_image, reference_image, transform, is_structure=False, default_value=0,
+                           interpolator=sitkNearestNeighbor):
+    if is_structure:
+        if default_value != 0 or interpolator != sitkNearestNeighbor:
+            logger.warning("is_structure is set to True, but you have set default_value and/or interpolator. "
+                           "default_value and/or interpolator will be overwritten.")
+        default_value = 0
+        interpolator = sitkNearestNeighbor
+    return apply_transform(input_image=input_image, reference_image=reference_image, transform=transform,
+                           default_value=default_value, interpolator=interpolator)
+
+
+def apply_deformable_transform(input_image, transform, is_structure=False, default_value=0, interpolator=sitkNearestNeighbor):
+    if is_structure:
+        if default_value != 0 or interpolator != sitkNearestNeighbor:
+            logger.warning("is_structure is set to True, but you have set default_value and/or interpolator. "
+                           "default_value and/or interpolator will be overwritten.")
+        default_value = 0
+        interpolator = sitkNearestNeighbor
+    return apply_transform(input_image=input_image, reference_image=None, transform=transform,
+                           default_value=default_value, interpolator=interpolator)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# The Demons filter object (duck-types sitk.FastSymmetricForcesDemonsRegistrationFilter)
+# ---------------------------------------------------------------------------------------------------------
+class FastSymmetricForcesDemonsRegistrationFilter:
+    """SimpleITK defaults: StandardDeviations 1.0, NumberOfIterations 10, MaximumRMSError 0.02,
+    MaximumUpdateStepLength 0.5, SmoothDisplacementField on, SmoothUpdateField off,
+    UpdateFieldStandardDeviations 1.0, MaximumKernelWidth 30, MaximumError 0.1,
+    IntensityDifferenceThreshold 0.001.  ``Execute`` can be handed to the reference's own
+    ``multiscale_demons`` (it needs SetNumberOfIterations / Execute / GetStandardDeviations)."""
+
+    def __init__(self):
+        self._std = [1.0, 1.0, 1.0]
+        self._ustd = [1.0, 1.0, 1.0]
+        self._iters = 10
+        self._smooth_field = True
+        self._smooth_update = False
+        self._max_rms = 0.02
+        self._max_step = 0.5
+        self._max_kw = 30
+        self._max_err = 0.1
+        self._idt = 0.001
+        self._commands = []
+        self._stats = {"elapsed_iterations": 0, "metric": 0.0, "rms_change": 0.0}
+
+    # setters / getters used by the reference ---------------------------------------------------------
+    def SetNumberOfThreads(self, n):  # meaningless on a GPU; accepted and ignored (deformable.py:247)
+        pass
+
+    def SetSmoothUpdateField(self, flag):
+        self._smooth_update = bool(flag)
+
+    def SetSmoothDisplacementField(self, flag):
+        self._smooth_field = bool(flag)
+
+    @staticmethod
+    def _vec3(v):
+        return [float(v)] * 3 if np.isscalar(v) else [float(s) for s in v]
+
+    def SetStandardDeviations(self, sd):
+        self._std = self._vec3(sd)
+
+    def GetStandardDeviations(self):
+        return tuple(self._std)
+
+    def SetUpdateFieldStandardDeviations(self, sd):
+        self._ustd = self._vec3(sd)
+
+    def SetNumberOfIterations(self, n):
+        self._iters = int(n)
+
+    def GetNumberOfIterations(self):
+        return self._iters
+
+    def SetMaximumRMSError(self, v):
+        self._max_rms = float(v)
+
+    def SetMaximumUpdateStepLength(self, v):
+        self._max_step = float(v)
+
+    def SetMaximumKernelWidth(self, v):
+        self._max_kw = int(v)
+
+    def SetMaximumError(self, v):
+        self._max_err = float(v)
+
+    def SetIntensityDifferenceThreshold(self, v):
+        self._idt = float(v)
+
+    def AddCommand(self, event, callback):
+        self._commands.append(callback)
+
+    def GetElapsedIterations(self):
+        return self._stats["elapsed_iterations"]
+
+    def GetMetric(self):
+        return self._stats["metric"]
+
+    def GetRMSChange(self):
+        return self._stats["rms_change"]
+
+    def params(self, iterations=None):
+        p = _abi.DemonsParams()
+        for i in range(3):
+            p.std_dev[i] = self._std[i]
+            p.update_std_dev[i] = self._ustd[i]
+        p.smooth_displacement_field = int(self._smooth_field)
+        p.smooth_update_field = int(self._smooth_update)
+        p.max_error = self._max_err
+        p.max_kernel_width = self._max_kw
+        p.number_of_iterations = self._iters if iterations is None else int(iterations)
+        p.max_rms_error = self._max_rms
+        p.max_update_step_length = self._max_step
+        p.intensity_difference_threshold = self._idt
+        p.denominator_threshold = 1e-9
+        return p
+
+    def Execute(self, fixed_image, moving_image):
+        eng = Engine.get()
+        f, m = eng.to_device(fixed_image), eng.to_device(moving_image)
+        if f.np_dtype != np.float32 or m.np_dtype != np.float32:
+            raise RuntimeError("FastSymmetricForcesDemonsRegistrationFilter: fixed and moving images must be sitkFloat32")
+        dvf, self._stats = eng.demons_execute(f, m, self.params())
+        for cb in self._commands:
+            cb()
+        return _back(eng, dvf, fixed_image)
+
+
+B200DemonsFilter = FastSymmetricForcesDemonsRegistrationFilter
+
+
+def _multires_config(reg, resolution_staging, smoothing_sigmas, iteration_staging, isotropic_resample, interp_order):
+    n = len(resolution_staging)
+    if not (len(smoothing_sigmas) >= n and len(iteration_staging) >= n):
+        raise ValueError("resolution_staging, smoothing_sigmas and iteration_staging must have one entry per level")
+    if n > _abi.MAX_LEVELS:
+        raise ValueError(f"at most {_abi.MAX_LEVELS} resolution levels are supported")
+    cfg = _abi.MultiresConfig()
+    cfg.n_levels = n
+    cfg.isotropic_resample = int(bool(isotropic_resample))
+    for i in range(n):
+        cfg.resolution_staging[i] = float(resolution_staging[i] or 0.0)
+        cfg.smoothing_sigmas[i] = float(smoothing_sigmas[i] or 0.0)
+        cfg.iteration_staging[i] = int(iteration_staging[i])
+    cfg.interp_order = _check_interp(interp_order)
+    cfg.demons = reg.params()
+    return cfg
+
+
+def multiscale_demons(registration_algorithm, fixed_image, moving_image, initial_transform=None,
+                      initial_displacement_field=None, isotropic_resample=None, resolution_staging=None,
+                      smoothing_sigmas=None, iteration_staging=None, interp_order=sitkLinear):
+    """Multi-resolution driver (deformable.py:31-187).  With the B200 filter the whole pyramid / level loop
+    runs inside one C-ABI call and nothing leaves the device; returns the displacement field
+    (VectorFloat64 on the fixed grid)."""
+    if not isinstance(registration_algorithm, FastSymmetricForcesDemonsRegistrationFilter):
+        raise TypeError("multiscale_demons on the B200 path needs platipy_b200's FastSymmetricForcesDemonsRegistrationFilter "
+                        "(hand that filter to the reference's multiscale_demons to drive it from SimpleITK code)")
+    eng = Engine.get()
+    f, m = eng.to_device(fixed_image), eng.to_device(moving_image)
+    if f.np_dtype != np.float32 or m.np_dtype != np.float32:
+        raise RuntimeError("multiscale_demons: fixed and moving images must be sitkFloat32")
+    init = None
+    if initial_displacement_field:
+        init = eng.to_device(initial_displacement_field)
+    elif initial_transform:
+        raise NotImplementedError("initial_transform (TransformToDisplacementField) is not implemented; pass "
+                                  "initial_displacement_field instead (no caller in the reference passes initial_transform)")
+    cfg = _multires_config(registration_algorithm, resolution_staging, smoothing_sigmas, iteration_staging, isotropic_resample, interp_order)
+    dvf, level_stats = eng.multiscale_demons(f, m, cfg, init)
+    registration_algorithm.level_stats = level_stats
+    if level_stats:
+        registration_algorithm._stats = level_stats[-1]
+    return _back(eng, dvf, fixed_image)
+
+
+def fast_symmetric_forces_demons_registration(fixed_image, moving_image, resolution_staging=[8, 4, 1],
+                                              iteration_staging=[10, 10, 10], isotropic_resample=False,
+                                              initial_displacement_field=None, regularisation_kernel_mm=1.5,
+                                              smoothing_sigma_factor=1, smoothing_sigmas=False, default_value=None,
+                                              ncores=1, interp_order=sitkLinear, verbose=False):
+    """Deformable image propagation using Fast Symmetric-Forces Demons (deformable.py:190-306).
+
+    Returns ``(registered_image, DisplacementFieldTransform, displacement_field)``.  For ``DeviceImage``
+    inputs the three results stay on the device (the transform object then wraps the device field).
+    """
+    eng = Engine.get()
+    device_io = _is_device(fixed_image) and _is_device(moving_image)
+    f0, m0 = eng.to_device(fixed_image), eng.to_device(moving_image)
+    moving_dtype = m0.np_dtype
+
+    # deformable.py:238-241: cast to Float32 unless the pixel id is 6 (Int64 -- the reference's quirk)
+    if f0.GetPixelID() == 6 or m0.GetPixelID() == 6:
+        raise RuntimeError("FastSymmetricForcesDemonsRegistrationFilter: Int64 images are not cast by the reference "
+                           "(GetPixelID() != 6 test) and the ITK filter then rejects them")
+    f = eng.cast(f0, np.float32)
+    m = eng.cast(m0, np.float32)
+
+    reg = FastSymmetricForcesDemonsRegistrationFilter()
+    reg.SetNumberOfThreads(ncores)
+    reg.SetSmoothUpdateField(True)
+    reg.SetSmoothDisplacementField(True)
+    # deformable.py:253-257: voxel-unit sigmas from the full-resolution spacing, reused at every level
+    reg.SetStandardDeviations((np.array(regularisation_kernel_mm) / np.array(f.GetSpacing())).tolist())
+
+    if not smoothing_sigmas:
+        smoothing_sigmas = [i * smoothing_sigma_factor for i in resolution_staging]
+
+    dvf = multiscale_demons(reg, f, m, resolution_staging=resolution_staging, smoothing_sigmas=smoothing_sigmas,
+                            iteration_staging=iteration_staging, isotropic_resample=isotropic_resample,
+                            initial_displacement_field=initial_displacement_field, interp_order=interp_order)
+    if verbose:
+        for lvl, st in enumerate(reg.level_stats):
+            print("level {0}: {1:3} = {2:10.5f}".format(lvl, st["elapsed_iterations"], st["metric"]))
+
+    # deformable.py:286-293: CT-like default value
+    if default_value is None:
+        default_value = 0
+        if eng.minmax(m)[0] <= -1000:
+            default_value = -1000
+
+    tfm = sk.DisplacementFieldTransform.__new__(sk.DisplacementFieldTransform)
+    tfm._field = None
+    tfm._device_cache = (eng, dvf)
+    # deformable.py:281-304: final resample on the fixed grid, cast back to the moving image's pixel type
+    reg_img = eng.resample(m, f, tfm, _check_interp(interp_order), default_value)
+    reg_img = eng.cast(reg_img, moving_dtype)
+
+    if device_io:
+        tfm._field = dvf
+        return reg_img, tfm, dvf
+    dvf_host = eng.to_host(dvf)
+    tfm._field = dvf_host
+    return sk.from_native(eng.to_host(reg_img), moving_image), tfm, sk.from_native(dvf_host, fixed_image)

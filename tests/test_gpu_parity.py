@@ -1,0 +1,261 @@
+"""GPU parity tests: every CUDA entry point against the CPU oracle on the same seeded inputs, through the
+C ABI (ctypes -> libb200reg.so).  Integer / index work and everything computed in the oracle's operation
+order is required to be BIT-EXACT; the documented floating-point tolerances are the north-star ones:
+DVF within 1e-4 mm per component, resampled float intensities within 1e-5 relative, labels bit-exact."""
+import numpy as np
+import pytest
+
+from oracle import itk_oracle as orc
+from oracle import platipy_ref as ref
+from platipy_b200 import registration as reg
+from platipy_b200 import sitk_compat as sk
+from platipy_b200.sitk_compat import Image
+from platipy_b200.synth import smooth_random_dvf, synth_labels, synth_pair
+
+pytestmark = pytest.mark.gpu
+
+IDENT = (1, 0, 0, 0, 1, 0, 0, 0, 1)
+DVF_TOL_MM = 1e-4
+REL_TOL = 1e-5
+
+
+def rot_direction(ax=0.05, az=0.1):
+    cx, sx, cz, sz = np.cos(ax), np.sin(ax), np.cos(az), np.sin(az)
+    rx = np.array([[1, 0, 0], [0, cx, -sx], [0, sx, cx]])
+    rz = np.array([[cz, -sz, 0], [sz, cz, 0], [0, 0, 1]])
+    return tuple((rz @ rx).reshape(9))
+
+
+def host(engine, d):
+    return engine.to_host(d, pinned=False)
+
+
+# ---------------------------------------------------------------------------------------------------------
+def test_discrete_gaussian_bit_exact(engine):
+    rng = np.random.default_rng(0)
+    for size, spacing, var, mw in [((33, 20, 17), (1.0, 1.0, 1.0), 4.0, 32), ((24, 31, 9), (0.9, 0.9, 2.5), (16.0, 16.0, 16.0), 128),
+                                   ((16, 16, 16), (1.0, 1.0, 1.0), 64.0, 3), ((70, 5, 6), (0.5, 1.0, 1.0), (1.0, 0.0001, 9.0), 32)]:
+        a = (rng.normal(size=size[::-1]) * 300).astype(np.float32)
+        im = Image(a, spacing)
+        out = host(engine, engine.discrete_gaussian(engine.to_device(im), var, mw)).array
+        exp = orc.discrete_gaussian_f32(a, orc.geom_of(im), var, mw)
+        assert np.array_equal(out, exp)
+
+
+@pytest.mark.parametrize("dtype", [np.uint8, np.int8, np.int16, np.uint16, np.int32, np.uint32, np.int64, np.uint64, np.float32, np.float64])
+def test_resample_all_pixel_types_bit_exact(engine, dtype):
+    rng = np.random.default_rng(1)
+    if np.issubdtype(dtype, np.integer):
+        info = np.iinfo(dtype)
+        a = rng.integers(max(info.min, -30000), min(info.max, 30000), size=(11, 13, 15)).astype(dtype)
+    else:
+        a = (rng.normal(size=(11, 13, 15)) * 500).astype(dtype)
+    src = Image(a, (0.9, 1.1, 2.5), (3.0, -2.0, 10.0), rot_direction())
+    ref_img = Image(np.zeros((9, 17, 12), np.uint8), (1.3, 0.8, 2.0), (2.0, -1.0, 9.0), rot_direction(0.02, -0.07))
+    th = 0.08
+    aff = sk.AffineTransform([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1.02]], (0.6, -0.3, 0.4), center=(8, 6, 20))
+    dvf = Image(smooth_random_dvf((10, 9, 8), seed=3, peak_mm=2.0), (1.7, 1.9, 3.0), (1.0, -3.0, 8.0), IDENT, True)
+    dtf = sk.DisplacementFieldTransform(dvf)
+    for tfm in [None, aff, dtf, sk.CompositeTransform([aff, dtf]), sk.CompositeTransform([dtf, aff])]:
+        for interp in (sk.sitkNearestNeighbor, sk.sitkLinear):
+            out = reg.apply_transform(src, ref_img, tfm, default_value=-7 if np.issubdtype(dtype, np.signedinteger) or np.issubdtype(dtype, np.floating) else 3,
+                                      interpolator=interp)
+            exp = ref.apply_transform(src, ref_img, tfm, default_value=-7 if np.issubdtype(dtype, np.signedinteger) or np.issubdtype(dtype, np.floating) else 3,
+                                      interpolator=interp)
+            assert out.array.dtype == dtype and out.GetSize() == ref_img.GetSize() and out.GetSpacing() == ref_img.GetSpacing()
+            assert np.array_equal(out.array, exp.array), (tfm, interp)
+    # reference_image=None -> the input's own grid (utils.py:178-181)
+    out = reg.apply_transform(src, None, aff, 0, sk.sitkLinear)
+    assert np.array_equal(out.array, ref.apply_transform(src, None, aff, 0, sk.sitkLinear).array)
+
+
+def test_resample_batch_equals_single_calls(engine):
+    fixed, moving = synth_pair((40, 36, 28), seed=2, spacing=(1.0, 1.0, 1.5))
+    labels = [Image(l, fixed.GetSpacing()) for l in synth_labels((40, 36, 28), 11, seed=200)]
+    dvf = Image(smooth_random_dvf((40, 36, 28), seed=5, peak_mm=4.0), fixed.GetSpacing(), fixed.GetOrigin(), IDENT, True)
+    tfm = sk.DisplacementFieldTransform(dvf)
+    imgs = [moving] + labels
+    outs = reg.apply_transform_batch(imgs, fixed, tfm, [-1000] + [0] * 11, [sk.sitkLinear] + [sk.sitkNearestNeighbor] * 11)
+    for im, o, dv, ip in zip(imgs, outs, [-1000] + [0] * 11, [sk.sitkLinear] + [sk.sitkNearestNeighbor] * 11):
+        exp = ref.apply_transform(im, fixed, tfm, dv, ip)
+        assert np.array_equal(o.array, exp.array)
+    with pytest.raises(NotImplementedError):
+        reg.apply_transform(moving, fixed, tfm, 0, sk.sitkBSpline)
+
+
+def test_resample_vec3_and_compose_bit_exact(engine):
+    f = Image(smooth_random_dvf((20, 18, 16), seed=7, peak_mm=3.0), (2.0, 2.1, 3.0), (5, 5, 5), rot_direction(), True)
+    grid = Image(np.zeros((31, 35, 39), np.uint8), (1.0, 1.05, 1.5), (5.2, 4.9, 5.1), rot_direction())
+    d = engine.to_device(f)
+    out = host(engine, engine.resample_vec3(d, grid)).array
+    exp = ref.resample(f, grid).array
+    assert np.array_equal(out, exp)
+    # dvf_total + Resample(dvf_iter, DisplacementFieldTransform(dvf_total))  (deformable.py:154)
+    tot = Image(smooth_random_dvf((20, 18, 16), seed=8, peak_mm=5.0), f.GetSpacing(), f.GetOrigin(), f.GetDirection(), True)
+    tfm = sk.DisplacementFieldTransform(sk.Cast(tot, sk.sitkVectorFloat64))
+    exp2 = tot.array + ref.resample(f, f, tfm).array
+    got = host(engine, engine.compose_dvf(engine.to_device(tot), d)).array
+    assert np.array_equal(got, exp2)
+
+
+def test_recursive_gaussian_bit_exact(engine):
+    arr = smooth_random_dvf((23, 19, 14), seed=9, peak_mm=3.0) + np.random.default_rng(0).normal(size=(14, 19, 23, 3))
+    f = Image(arr, (0.9, 0.9, 2.5), is_vector=True)
+    sigma = (1.5 / 0.9, 1.5 / 0.9, 1.5 / 2.5)  # the reference passes voxel-unit numbers as physical sigmas
+    got = host(engine, engine.recursive_gaussian(engine.to_device(f), sigma)).array
+    exp = orc.recursive_gaussian_vec3(f.array, orc.geom_of(f), sigma)
+    assert np.array_equal(got, exp)
+    with pytest.raises(RuntimeError):
+        engine.recursive_gaussian(engine.to_device(Image(np.zeros((3, 8, 8, 3)), is_vector=True)), (1, 1, 1))
+
+
+def _params(std, iters, smooth_update=True):
+    f = reg.FastSymmetricForcesDemonsRegistrationFilter()
+    f.SetStandardDeviations(std)
+    f.SetSmoothUpdateField(smooth_update)
+    return f.params(iters)
+
+
+def test_demons_force_and_smoothing_bit_exact(engine):
+    fixed, moving = synth_pair((37, 29, 21), seed=11, spacing=(0.97, 0.97, 2.0), origin=(-20.0, 4.0, 100.0), peak_mm=3.0)
+    # moving image on a different, shifted grid so part of the fixed grid maps outside it (FLT_MAX logic)
+    moving = Image(moving.array[:, :, 3:], moving.GetSpacing(), (-20.0 + 5 * 0.97, 4.0, 100.0), IDENT)
+    D = smooth_random_dvf((37, 29, 21), seed=12, peak_mm=2.0)
+    std = (1.5 / 0.97, 1.5 / 0.97, 0.75)
+    W, U, metric, rms = orc.demons_force(fixed.array, orc.geom_of(fixed), moving.array, orc.geom_of(moving), D, orc.demons_params(std, 1))
+    dF, dM = engine.to_device(fixed), engine.to_device(moving)
+    dD = engine.to_device(Image(D, fixed.GetSpacing(), fixed.GetOrigin(), IDENT, True))
+    gW, gU, gmetric, grms = engine.demons_force(dF, dM, dD, _params(std, 1))
+    assert (W == np.finfo(np.float32).max).sum() > 100
+    assert np.array_equal(host(engine, gW).array, W)
+    assert np.array_equal(host(engine, gU).array, U)
+    assert abs(gmetric - metric) <= 1e-12 * abs(metric) and abs(grms - rms) <= 1e-12 * abs(rms)
+    # PDE smoothing (x, y, z; clamp boundary) of a field
+    sm = orc.pde_smooth_field(U, orc.geom_of(fixed), std)
+    gsm = host(engine, engine.pde_smooth_field(gU, std)).array
+    assert np.array_equal(gsm, sm)
+
+
+def test_demons_execute_config1(engine):
+    """BASELINE.json configs[0]: 64x64x32, one level, 10 iterations."""
+    fixed, moving = synth_pair((64, 64, 32), seed=0)
+    std = (1.5, 1.5, 1.5)
+    D, st = orc.demons_execute(fixed.array, orc.geom_of(fixed), moving.array, orc.geom_of(moving), orc.demons_params(std, 10, smooth_update_field=True))
+    gD, gst = engine.demons_execute(engine.to_device(fixed), engine.to_device(moving), _params(std, 10))
+    got = host(engine, gD).array
+    assert gst["elapsed_iterations"] == st["elapsed_iterations"] == 10
+    assert np.abs(got - D).max() <= DVF_TOL_MM
+    assert np.array_equal(got, D), "same operation order as the oracle: expected bit-exact"
+    assert abs(gst["metric"] - st["metric"]) <= 1e-10 * st["metric"] and abs(gst["rms_change"] - st["rms_change"]) <= 1e-10
+
+
+def test_demons_halt_rules(engine):
+    fixed, _ = synth_pair((32, 32, 16), seed=1)
+    dF = engine.to_device(fixed)
+    # identical images -> zero update -> RMS 0 < 0.02 -> exactly one iteration, zero field
+    gD, st = engine.demons_execute(dF, dF, _params((1.5,) * 3, 25))
+    assert st["elapsed_iterations"] == 1 and st["metric"] == 0.0 and float(gD.tensor.abs().max()) == 0.0
+    # zero iterations -> zero field, nothing elapsed
+    gD, st = engine.demons_execute(dF, dF, _params((1.5,) * 3, 0))
+    assert st["elapsed_iterations"] == 0 and float(gD.tensor.abs().max()) == 0.0
+    # early stop happens at the same iteration as in the oracle
+    f2, m2 = synth_pair((32, 32, 16), seed=4, peak_mm=0.3, noise_hu=0.0)
+    p = orc.demons_params((1.5,) * 3, 200, smooth_update_field=True)
+    D, so = orc.demons_execute(f2.array, orc.geom_of(f2), m2.array, orc.geom_of(m2), p)
+    gD, sg = engine.demons_execute(engine.to_device(f2), engine.to_device(m2), _params((1.5,) * 3, 200))
+    assert sg["elapsed_iterations"] == so["elapsed_iterations"]
+    assert np.abs(host(engine, gD).array - D).max() <= DVF_TOL_MM
+
+
+CASES = {
+    "cfg1_sigma0": dict(size=(64, 64, 32), kw=dict(resolution_staging=[1], iteration_staging=[10], smoothing_sigmas=[0])),
+    "cfg1_default_sigma": dict(size=(64, 64, 32), kw=dict(resolution_staging=[1], iteration_staging=[10])),
+    "three_levels": dict(size=(64, 56, 40), kw=dict(resolution_staging=[4, 2, 1], iteration_staging=[20, 10, 5])),
+    "platipy_defaults": dict(size=(72, 64, 48), kw=dict()),
+    "anisotropic_offset_rotated": dict(size=(60, 50, 28), spacing=(0.9, 0.9, 2.5), origin=(320.0, -52.0, 60.0), direction=rot_direction(0.03, 0.05),
+                                       kw=dict(resolution_staging=[2, 1], iteration_staging=[10, 5], regularisation_kernel_mm=[1.5, 1.5, 2.0])),
+    "isotropic_resample": dict(size=(60, 50, 28), spacing=(0.9, 0.9, 2.5), origin=(320.0, -52.0, 60.0),
+                               kw=dict(resolution_staging=[6, 3, 1.5], iteration_staging=[10, 8, 5], isotropic_resample=True, smoothing_sigmas=[0, 0, 0])),
+    "nn_interp_int16": dict(size=(48, 40, 24), dtype=np.int16, kw=dict(resolution_staging=[2, 1], iteration_staging=[6, 4], interp_order=sk.sitkNearestNeighbor)),
+}
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_fast_symmetric_forces_demons_registration_parity(engine, name):
+    c = CASES[name]
+    fixed, moving = synth_pair(c["size"], seed=21, spacing=c.get("spacing", (1.0, 1.0, 1.0)), origin=c.get("origin", (0.0, 0.0, 0.0)), peak_mm=4.0)
+    if "direction" in c:
+        fixed = Image(fixed.array, fixed.GetSpacing(), fixed.GetOrigin(), c["direction"])
+        moving = Image(moving.array, moving.GetSpacing(), moving.GetOrigin(), c["direction"])
+    if "dtype" in c:
+        fixed, moving = sk.Cast(fixed, sk.dtype_to_pixel_id(c["dtype"])), sk.Cast(moving, sk.dtype_to_pixel_id(c["dtype"]))
+    img, tfm, dvf = reg.fast_symmetric_forces_demons_registration(fixed, moving, **c["kw"])
+    stats = []
+    img_o, tfm_o, dvf_o = ref.fast_symmetric_forces_demons_registration(fixed, moving, level_stats=stats, **c["kw"])
+    assert dvf.GetPixelID() == sk.sitkVectorFloat64 and dvf.GetSize() == fixed.GetSize() and dvf.GetSpacing() == fixed.GetSpacing()
+    assert img.GetPixelID() == moving.GetPixelID() and img.GetOrigin() == fixed.GetOrigin()
+    err = np.abs(dvf.array - dvf_o.array).max()
+    assert err <= DVF_TOL_MM, f"DVF max error {err} mm"
+    if np.issubdtype(img.array.dtype, np.floating):
+        assert np.abs(img.array - img_o.array).max() <= REL_TOL * max(1.0, np.abs(img_o.array).max())
+    else:
+        assert np.array_equal(img.array, img_o.array)
+    # the transform object is usable by apply_transform (labels bit-exact)
+    lab = Image(synth_labels(c["size"], 1, seed=300)[0], fixed.GetSpacing(), fixed.GetOrigin(), fixed.GetDirection())
+    assert np.array_equal(reg.apply_transform(lab, fixed, tfm, 0, sk.sitkNearestNeighbor).array,
+                          ref.apply_transform(lab, fixed, tfm_o, 0, sk.sitkNearestNeighbor).array)
+
+
+def test_initial_displacement_field_and_device_io(engine):
+    fixed, moving = synth_pair((40, 40, 24), seed=31, peak_mm=3.0)
+    init = Image(smooth_random_dvf((20, 20, 12), seed=32, peak_mm=1.0), (2.0, 2.0, 2.0), (0.5, 0.5, 0.5), IDENT, True)
+    kw = dict(resolution_staging=[2, 1], iteration_staging=[5, 5], initial_displacement_field=init)
+    _, _, dvf = reg.fast_symmetric_forces_demons_registration(fixed, moving, **kw)
+    _, _, dvf_o = ref.fast_symmetric_forces_demons_registration(fixed, moving, **kw)
+    assert np.abs(dvf.array - dvf_o.array).max() <= DVF_TOL_MM
+    # device in -> device out, nothing copied back
+    dF, dM = engine.to_device(fixed), engine.to_device(moving)
+    img_d, tfm_d, dvf_d = reg.fast_symmetric_forces_demons_registration(dF, dM, resolution_staging=[2, 1], iteration_staging=[5, 5])
+    from platipy_b200.engine import DeviceImage
+
+    assert isinstance(img_d, DeviceImage) and isinstance(dvf_d, DeviceImage)
+    _, _, dvf_h = reg.fast_symmetric_forces_demons_registration(fixed, moving, resolution_staging=[2, 1], iteration_staging=[5, 5])
+    assert np.array_equal(host(engine, dvf_d).array, dvf_h.array)
+    lab = engine.to_device(Image(synth_labels((40, 40, 24), 1)[0]))
+    out = reg.apply_transform(lab, dF, tfm_d, 0, sk.sitkNearestNeighbor)
+    assert isinstance(out, DeviceImage)
+
+
+def test_smooth_and_resample_parity_and_errors(engine):
+    fixed, _ = synth_pair((50, 44, 30), seed=41, spacing=(0.9, 0.9, 2.5))
+    for kw in [dict(shrink_factor=2, smoothing_sigma=2), dict(shrink_factor=[2, 2, 1], smoothing_sigma=[1.0, 1.0, 2.5]), dict(isotropic_voxel_size_mm=3, smoothing_sigma=0),
+               dict(smoothing_sigma=1.5), dict(shrink_factor=4, interpolator=sk.sitkNearestNeighbor)]:
+        out, exp = reg.smooth_and_resample(fixed, **kw), ref.smooth_and_resample(fixed, **kw)
+        assert out.GetSize() == exp.GetSize() and np.allclose(out.GetSpacing(), exp.GetSpacing(), rtol=0, atol=0)
+        assert np.array_equal(out.array, exp.array), kw
+    with pytest.raises(AttributeError):
+        reg.smooth_and_resample(fixed, isotropic_voxel_size_mm=2, shrink_factor=2)
+    with pytest.raises(ZeroDivisionError):
+        reg.smooth_and_resample(fixed, shrink_factor=64)  # a level collapsing to one voxel: utils.py:252-255 divides by zero
+
+
+def test_reference_acceptance_sphere_phantom_dice_gpu(engine):
+    """The reference's only acceptance criterion for this path (test_cardiac.py:35-71,142), on the GPU."""
+    from platipy_b200.synth import insert_sphere
+
+    def case(i):
+        ct = insert_sphere(np.ones((60, 128, 128)) * -1000, 25, (30 + i, 64 + i, 64))
+        mask = insert_sphere(np.zeros((60, 128, 128)), 25, (30 + i, 64 + i, 64))
+        sp = (0.94, 0.94, 2.54)
+        return Image(ct.astype(np.float32), sp, (320, -52, 60)), Image(mask.astype(np.uint8), sp, (320, -52, 60))
+
+    target_ct, target_mask = case(4)
+    atlas_ct, atlas_mask = case(2)
+    kw = dict(resolution_staging=[8, 4, 2], iteration_staging=[5, 5, 5], smoothing_sigmas=[0, 0, 0], isotropic_resample=True, default_value=-1000)
+    _, tfm, dvf = reg.fast_symmetric_forces_demons_registration(target_ct, atlas_ct, **kw)
+    _, tfm_o, dvf_o = ref.fast_symmetric_forces_demons_registration(target_ct, atlas_ct, **kw)
+    assert np.abs(dvf.array - dvf_o.array).max() <= DVF_TOL_MM
+    prop = reg.apply_transform(atlas_mask, target_ct, tfm, 0, sk.sitkNearestNeighbor).array
+    assert np.array_equal(prop, ref.apply_transform(atlas_mask, target_ct, tfm_o, 0, sk.sitkNearestNeighbor).array)
+    dice = 2.0 * (prop & target_mask.array).sum() / (prop.sum() + target_mask.array.sum())
+    assert dice > 0.95
