@@ -27,6 +27,9 @@ logger = logging.getLogger(__name__)
 
 sitkNearestNeighbor, sitkLinear, sitkBSpline = sk.sitkNearestNeighbor, sk.sitkLinear, sk.sitkBSpline
 
+# per-level statistics of the most recent multiscale_demons call (elapsed iterations, metric, RMS change, device ms)
+LAST_LEVEL_STATS = []
+
 
 def _check_interp(interpolator):
     if interpolator == sk.sitkBSpline:
@@ -297,6 +300,7 @@ def multiscale_demons(registration_algorithm, fixed_image, moving_image, initial
     cfg = _multires_config(registration_algorithm, resolution_staging, smoothing_sigmas, iteration_staging, isotropic_resample, interp_order)
     dvf, level_stats = eng.multiscale_demons(f, m, cfg, init)
     registration_algorithm.level_stats = level_stats
+    LAST_LEVEL_STATS[:] = level_stats
     if level_stats:
         registration_algorithm._stats = level_stats[-1]
     return _back(eng, dvf, fixed_image)
