@@ -1,4 +1,6 @@
 // b200reg.cu -- C ABI of libb200reg.so (see include/b200reg.h).  sm_100a only, -fmad=false.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "demons.cuh"
 #include "deriche.cuh"
@@ -62,6 +64,8 @@ API int b200reg_create(int device, void* stream, b200reg_ctx** out)
     uint64_t thr = UINT64_MAX;
     B200_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     B200_CUDA(cudaMallocHost(&ctx->h_scratch, 64 * sizeof(double)));
+    if (const char* e = getenv("B200REG_FORCE_SEPARABLE")) ctx->force_separable = (e[0] == '1');
+    if (const char* e = getenv("B200REG_FORCE_ZM1")) ctx->force_zm1 = (e[0] == '1');
     *out = ctx;
     return B200REG_OK;
 }
@@ -324,12 +328,16 @@ API int b200reg_pde_smooth_field(b200reg_ctx* ctx, double* d_field_soa, const b2
     ENTER(ctx);
     REQUIRE(d_field_soa && valid_geom(geom) && std_dev, "invalid argument");
     const size_t n = nvox(*geom);
-    TempBuf t1, t2;
+    TempBuf t1, t2, t3;
     B200_TRY(t1.alloc(ctx, 3 * n * sizeof(double)));
     B200_TRY(t2.alloc(ctx, 3 * n * sizeof(double)));
+    B200_TRY(t3.alloc(ctx, 3 * n * sizeof(double)));
     KernelCoeffs kc[3];
     B200_TRY(make_pde_coeffs(std_dev, max_error, max_kernel_width, kc));
-    return pde_smooth(ctx, d_field_soa, nullptr, t1.as<double>(), t2.as<double>(), geom->size[0], geom->size[1], geom->size[2], kc, nullptr, 0);
+    B200_TRY(pde_smooth(ctx, d_field_soa, nullptr, t1.as<double>(), t2.as<double>(), t3.as<double>(), geom->size[0], geom->size[1], geom->size[2], kc,
+                        nullptr, 0));
+    B200_CUDA(cudaMemcpyAsync(d_field_soa, t1.p, 3 * n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+    return B200REG_OK;
 }
 
 // ---- N8 --------------------------------------------------------------------------------------------------------------

@@ -56,6 +56,8 @@ struct b200reg_ctx {
     int sm_count = 148;
     // pinned scratch for small read-backs
     double* h_scratch = nullptr;  // 64 doubles
+    bool force_separable = false;  // B200REG_FORCE_SEPARABLE=1: unfused smoothing passes (A/B testing)
+    bool force_zm1 = false;        // B200REG_FORCE_ZM1=1: first-generation fused smoothing kernel
 };
 
 namespace b200 {

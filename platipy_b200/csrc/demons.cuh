@@ -231,7 +231,7 @@ __global__ void demons_ctrl_init_kernel(DemonsCtrl* ctrl, int n_iters)
 }
 
 struct DemonsWorkspace {
-    TempBuf U, T1, T2, W, partials, ctrl, trace;
+    TempBuf U, T1, T2, P1, W, partials, ctrl, trace;
     size_t nblocks = 0;
 };
 
@@ -241,6 +241,7 @@ inline int demons_prepare(b200reg_ctx* ctx, const b200reg_geom& gF, int n_iters,
     B200_TRY(ws->U.alloc(ctx, 3 * n * sizeof(double)));
     B200_TRY(ws->T1.alloc(ctx, 3 * n * sizeof(double)));
     B200_TRY(ws->T2.alloc(ctx, 3 * n * sizeof(double)));
+    B200_TRY(ws->P1.alloc(ctx, 3 * n * sizeof(double)));
     B200_TRY(ws->W.alloc(ctx, n * sizeof(float)));
     const dim3 g = grid3(gF.size[0], gF.size[1], gF.size[2]);
     ws->nblocks = (size_t)g.x * g.y * g.z;
@@ -280,22 +281,32 @@ inline int demons_calculate_change(b200reg_ctx* ctx, const float* F, const GeomD
 }
 
 // PDEDeformableRegistrationFilter::Smooth{Update,Displacement}Field: x -> y -> z, variance = sd^2 (voxel
-// units), clamp boundary, f64.  `add` != nullptr: the first pass reads field + add (AddImageFilter fused).
-// Result lands in `field`.  t1/t2: scratch fields.
-inline int pde_smooth(b200reg_ctx* ctx, double* field, const double* add, double* t1, double* t2, int nx, int ny, int nz,
+// units), clamp boundary, f64.  `add` != nullptr: the first pass reads src + add (AddImageFilter fused).
+// Out of place: src/add -> dst, using s1/s2 as scratch for the separable fallback (dst, s1, s2, src, add
+// all distinct).  Small radii take the fused z-marching kernel (one read + one write per voxel).
+inline int pde_smooth(b200reg_ctx* ctx, const double* src, const double* add, double* dst, double* s1, double* s2, int nx, int ny, int nz,
                       const KernelCoeffs kc[3], const DemonsCtrl* ctrl, int it)
 {
-    if (add) B200_TRY((launch_conv_axis<double, true>(ctx, 0, field, add, t1, nx, ny, nz, 3, kc[0], ctrl, it)));
-    else B200_TRY((launch_conv_axis<double, false>(ctx, 0, field, nullptr, t1, nx, ny, nz, 3, kc[0], ctrl, it)));
-    B200_TRY((launch_conv_axis<double, false>(ctx, 1, t1, nullptr, t2, nx, ny, nz, 3, kc[1], ctrl, it)));
-    B200_TRY((launch_conv_axis<double, false>(ctx, 2, t2, nullptr, field, nx, ny, nz, 3, kc[2], ctrl, it)));
+    if (zmarch_supported(kc) && !ctx->force_separable) return launch_conv3d_zmarch(ctx, src, add, dst, nx, ny, nz, 3, kc, ctrl, it);
+    if (add) B200_TRY((launch_conv_axis<double, true>(ctx, 0, src, add, s1, nx, ny, nz, 3, kc[0], ctrl, it)));
+    else B200_TRY((launch_conv_axis<double, false>(ctx, 0, src, nullptr, s1, nx, ny, nz, 3, kc[0], ctrl, it)));
+    B200_TRY((launch_conv_axis<double, false>(ctx, 1, s1, nullptr, s2, nx, ny, nz, 3, kc[1], ctrl, it)));
+    B200_TRY((launch_conv_axis<double, false>(ctx, 2, s2, nullptr, dst, nx, ny, nz, 3, kc[2], ctrl, it)));
     return B200REG_OK;
 }
 
-__global__ void add_inplace_kernel(double* __restrict__ a, const double* __restrict__ b, size_t n, const DemonsCtrl* __restrict__ ctrl, int it)
+__global__ void add_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out, size_t n,
+                           const DemonsCtrl* __restrict__ ctrl, int it)
 {
     if (ctrl && it >= ctrl->halt_iter) return;
-    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) a[q] = a[q] + b[q];
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) out[q] = a[q] + b[q];
+}
+// The field ping-pongs between two buffers; after `elapsed` iterations it lives in buffer elapsed % 2.
+// Decided on the device: copy P1 -> P0 when the elapsed count is odd.
+__global__ void select_copy_kernel(const double* __restrict__ p1, double* __restrict__ p0, size_t n, const DemonsCtrl* __restrict__ ctrl)
+{
+    if ((ctrl->elapsed & 1) == 0) return;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) p0[q] = p1[q];
 }
 
 inline int make_pde_coeffs(const double sd[3], double max_error, int max_width, KernelCoeffs kc[3])
@@ -306,6 +317,8 @@ inline int make_pde_coeffs(const double sd[3], double max_error, int max_width, 
 
 // registration_algorithm.Execute(f_image, m_image): zero initial field, FiniteDifferenceImageFilter loop.
 // Everything is enqueued on the stream; stats are read back by the caller after synchronising.
+// Per iteration: CalculateChange (P[it%2] -> U), SmoothUpdateField (U -> T1), Add + SmoothDisplacementField
+// ((P[it%2] + T1) -> P[(it+1)%2]).
 inline int demons_enqueue(b200reg_ctx* ctx, const float* F, const b200reg_geom& gF, const float* M, const b200reg_geom& gM,
                           const b200reg_demons_params& p, double* D, DemonsWorkspace* ws)
 {
@@ -324,17 +337,28 @@ inline int demons_enqueue(b200reg_ctx* ctx, const float* F, const b200reg_geom& 
     double* U = ws->U.as<double>();
     double* T1 = ws->T1.as<double>();
     double* T2 = ws->T2.as<double>();
+    double* P[2] = { D, ws->P1.as<double>() };
     for (int it = 0; it < n_iters; ++it) {
-        B200_TRY(demons_calculate_change(ctx, F, gf, M, gm, D, fp, ws, it, n_iters));
-        if (p.smooth_update_field) B200_TRY(pde_smooth(ctx, U, nullptr, T1, T2, nx, ny, nz, ku, ctrl, it));
+        double* cur = P[it & 1];
+        double* nxt = P[(it + 1) & 1];
+        B200_TRY(demons_calculate_change(ctx, F, gf, M, gm, cur, fp, ws, it, n_iters));
+        const double* upd = U;
+        if (p.smooth_update_field) {
+            B200_TRY(pde_smooth(ctx, U, nullptr, T1, T2, nxt, nx, ny, nz, ku, ctrl, it));  // nxt is free scratch here
+            upd = T1;
+        }
         if (p.smooth_displacement_field) {
-            B200_TRY(pde_smooth(ctx, D, U, T1, T2, nx, ny, nz, kd, ctrl, it));
+            // scratch: T2 and whichever of U / T1 does not hold the update
+            B200_TRY(pde_smooth(ctx, cur, upd, nxt, T2, upd == U ? T1 : U, nx, ny, nz, kd, ctrl, it));
         } else {
-            add_inplace_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(D, U, 3 * n, ctrl, it);
+            add_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(cur, upd, nxt, 3 * n, ctrl, it);
             ctx->launches++;
             B200_CHECK_LAUNCH();
         }
     }
+    select_copy_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(P[1], P[0], 3 * n, ctrl);
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
     return B200REG_OK;
 }
 

@@ -156,6 +156,348 @@ inline int launch_conv_axis(b200reg_ctx* ctx, int axis, const T* a, const T* b, 
     return B200REG_OK;
 }
 
+// ---- fused 3-D separable smoothing, z-marching ---------------------------------------------------------------
+// One CTA owns a TX x TY column of one component plane-stack and marches along z.  Per z step it stages the
+// input plane (tile + x/y halo, index-clamped = ZeroFluxNeumann) in shared memory, runs the x pass and the
+// y pass out of shared memory, and keeps the last 2*RZ+1 x/y-smoothed planes of its own voxels in a register
+// ring; the z pass is an inner product over that ring.  Every input voxel is read from HBM once (halo
+// re-reads are L2 hits) and every output written once: 16 B/voxel/component instead of 48 for three
+// separable passes.  Operation order per output (x taps -r..r, then y, then z; each rounded to double)
+// is identical to three sequential passes, so results are bit-identical to them (and to the oracle).
+constexpr int ZM_TX = 64, ZM_TY = 16, ZM_NT = 256, ZM_RXY = 4, ZM_RMAX = 4;
+constexpr int ZM_PER = ZM_TY / (ZM_NT / ZM_TX);                                            // own voxels per thread
+constexpr int ZM_MAXLD = ((ZM_TX + 2 * ZM_RXY) * (ZM_TY + 2 * ZM_RXY) + ZM_NT - 1) / ZM_NT;  // staged loads per thread
+struct SmallCoeffs {
+    int r[3];
+    double k[3][2 * ZM_RMAX + 1];
+};
+
+template <int RZ, bool ADD>
+__global__ void __launch_bounds__(ZM_NT, 2) conv3d_zmarch_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out,
+                                                                  int nx, int ny, int nz, int zchunk, int nchunks,
+                                                                  const __grid_constant__ SmallCoeffs kc, const DemonsCtrl* __restrict__ ctrl, int it)
+{
+    if (ctrl && it >= ctrl->halt_iter) return;
+    __shared__ double A[(ZM_TY + 2 * ZM_RXY) * (ZM_TX + 2 * ZM_RXY)];
+    __shared__ double B[(ZM_TY + 2 * ZM_RXY) * ZM_TX];
+    const int rx = kc.r[0], ry = kc.r[1];
+    const int AW = ZM_TX + 2 * rx, AH = ZM_TY + 2 * ry, NA = AW * AH;
+    const int tid = threadIdx.x, tx = tid % ZM_TX, ty = tid / ZM_TX;
+    const int x0 = blockIdx.x * ZM_TX, y0 = blockIdx.y * ZM_TY;
+    const int comp = blockIdx.z / nchunks, chunk = blockIdx.z % nchunks;
+    const int z0 = chunk * zchunk, z1 = min(nz, z0 + zchunk);
+    const size_t plane = (size_t)nx * ny, vol = plane * nz;
+    const double* __restrict__ ap = a + (size_t)comp * vol;
+    const double* __restrict__ bp = ADD ? b + (size_t)comp * vol : nullptr;
+    double* __restrict__ op = out + (size_t)comp * vol;
+
+    // staged-load bookkeeping: element e of A <-> (clamped) global offset within a plane
+    int goff[ZM_MAXLD];
+#pragma unroll
+    for (int l = 0; l < ZM_MAXLD; ++l) {
+        const int e = tid + l * ZM_NT;
+        int yy = e / AW, xx = e - yy * AW;
+        int gx = x0 - rx + xx, gy = y0 - ry + yy;
+        gx = gx < 0 ? 0 : (gx > nx - 1 ? nx - 1 : gx);
+        gy = gy < 0 ? 0 : (gy > ny - 1 ? ny - 1 : gy);
+        goff[l] = e < NA ? gy * nx + gx : -1;
+    }
+    double pre[ZM_MAXLD];
+    auto fetch = [&](int z) {
+        const int zc = z < 0 ? 0 : (z > nz - 1 ? nz - 1 : z);
+        const size_t zo = (size_t)zc * plane;
+#pragma unroll
+        for (int l = 0; l < ZM_MAXLD; ++l)
+            if (goff[l] >= 0) {
+                if (ADD) pre[l] = ap[zo + goff[l]] + bp[zo + goff[l]];
+                else pre[l] = ap[zo + goff[l]];
+            }
+    };
+
+    double ring[ZM_PER][2 * RZ + 1];
+    double cur[ZM_PER];
+    const int zbeg = z0 - RZ, zend = z1 - 1 + RZ;
+    int prev_zc = -1;
+    fetch(zbeg);
+    for (int z = zbeg; z <= zend; ++z) {
+        const int zc = z < 0 ? 0 : (z > nz - 1 ? nz - 1 : z);
+        if (zc != prev_zc) {  // clamped repeats of a border plane reuse `cur`
+#pragma unroll
+            for (int l = 0; l < ZM_MAXLD; ++l)
+                if (goff[l] >= 0) A[tid + l * ZM_NT] = pre[l];
+            __syncthreads();
+            if (z < zend) fetch(z + 1);  // in flight during the passes below
+            // x pass over tile rows + y halo
+            for (int e = tid; e < AH * ZM_TX; e += ZM_NT) {
+                const int yy = e / ZM_TX, xx = e - yy * ZM_TX;
+                const double* row = A + yy * AW + xx;
+                double sum = 0.0;
+                for (int t = 0; t <= 2 * rx; ++t) sum += kc.k[0][t] * row[t];
+                B[e] = sum;
+            }
+            __syncthreads();
+            // y pass for the thread's own voxels
+#pragma unroll
+            for (int j = 0; j < ZM_PER; ++j) {
+                const int y = ty + j * (ZM_NT / ZM_TX);
+                const double* col = B + y * ZM_TX + tx;
+                double sum = 0.0;
+                for (int t = 0; t <= 2 * ry; ++t) sum += kc.k[1][t] * col[t * ZM_TX];
+                cur[j] = sum;
+            }
+            prev_zc = zc;
+        } else if (z < zend) {
+            // the next distinct plane still has to be fetched once the clamped run ends
+            const int zn = z + 1 < 0 ? 0 : (z + 1 > nz - 1 ? nz - 1 : z + 1);
+            if (zn != zc) fetch(z + 1);
+        }
+        // ring shift + z pass
+#pragma unroll
+        for (int j = 0; j < ZM_PER; ++j) {
+#pragma unroll
+            for (int t = 0; t < 2 * RZ; ++t) ring[j][t] = ring[j][t + 1];
+            ring[j][2 * RZ] = cur[j];
+        }
+        const int zo = z - RZ;
+        if (zo >= z0) {
+            const int gx = x0 + tx;
+#pragma unroll
+            for (int j = 0; j < ZM_PER; ++j) {
+                const int gy = y0 + ty + j * (ZM_NT / ZM_TX);
+                double sum = 0.0;
+#pragma unroll
+                for (int t = 0; t <= 2 * RZ; ++t) sum += kc.k[2][t] * ring[j][t];
+                if (gx < nx && gy < ny) op[(size_t)zo * plane + (size_t)gy * nx + gx] = sum;
+            }
+        }
+    }
+}
+
+// ---- fused 3-D smoothing, second generation: compile-time radii, cp.async double-buffered planes -------------
+// Same z-marching scheme and the same operation order (bit-identical results), engineered for instruction
+// count: radii are template parameters (taps fully unrolled, coefficients are constant-bank operands), the
+// x pass works on 4 consecutive outputs per thread out of 128-bit shared loads, the y pass slides a register
+// window over 4 consecutive rows, the z ring is addressed by compile-time rotation (no register moves), and
+// the next plane is staged global -> shared with cp.async (LDGSTS) while the current one is processed.
+// R: x/y radius (equal), RZ: z radius, ADD: input is a + b.
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gsrc));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
+
+template <int R, int RZ, bool ADD>
+__global__ void __launch_bounds__(ZM_NT, 2) conv3d_zm2_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out,
+                                                               int nx, int ny, int nz, int zchunk, int nchunks,
+                                                               const __grid_constant__ SmallCoeffs kc, const DemonsCtrl* __restrict__ ctrl, int it)
+{
+    if (ctrl && it >= ctrl->halt_iter) return;
+    constexpr int RP = (R + 1) & ~1;  // x halo padded to an even count: 16-byte aligned shared rows
+    constexpr int AW = ZM_TX + 2 * RP, AH = ZM_TY + 2 * R, NA = AW * AH;
+    constexpr int NR = 2 * RZ + 1;
+    constexpr int NLD = (NA + ZM_NT - 1) / ZM_NT;
+    constexpr int WIN = 4 + 2 * RP;
+    extern __shared__ __align__(16) double zm_smem[];
+    double* Aa = zm_smem;                       // [2][NA]
+    double* Ab = zm_smem + 2 * NA;              // [2][NA] (ADD only)
+    double* B = zm_smem + (ADD ? 4 : 2) * NA;   // [AH][TX]
+
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * ZM_TX, y0 = blockIdx.y * ZM_TY;
+    const int comp = blockIdx.z / nchunks, chunk = blockIdx.z % nchunks;
+    const int z0 = chunk * zchunk, z1 = min(nz, z0 + zchunk);
+    const size_t plane = (size_t)nx * ny, vol = plane * nz;
+    const double* __restrict__ ap = a + (size_t)comp * vol;
+    const double* __restrict__ bp = ADD ? b + (size_t)comp * vol : nullptr;
+    double* __restrict__ op = out + (size_t)comp * vol;
+
+    int goff[NLD];
+#pragma unroll
+    for (int l = 0; l < NLD; ++l) {
+        const int e = tid + l * ZM_NT;
+        const int yy = e / AW, xx = e - yy * AW;
+        int gx = x0 - RP + xx, gy = y0 - R + yy;
+        gx = gx < 0 ? 0 : (gx > nx - 1 ? nx - 1 : gx);
+        gy = gy < 0 ? 0 : (gy > ny - 1 ? ny - 1 : gy);
+        goff[l] = e < NA ? gy * nx + gx : -1;
+    }
+    auto stage = [&](int z, int buf) {
+        const int zc = z < 0 ? 0 : (z > nz - 1 ? nz - 1 : z);
+        const size_t zo = (size_t)zc * plane;
+#pragma unroll
+        for (int l = 0; l < NLD; ++l)
+            if (goff[l] >= 0) {
+                cp_async8(Aa + buf * NA + tid + l * ZM_NT, ap + zo + goff[l]);
+                if (ADD) cp_async8(Ab + buf * NA + tid + l * ZM_NT, bp + zo + goff[l]);
+            }
+        cp_async_commit();
+    };
+
+    // y/z-pass ownership: column x = tid % 64, rows 4*yb .. 4*yb+3
+    const int ox = tid & (ZM_TX - 1), yb = tid >> 6;
+    const int gx = x0 + ox;
+    double ring[NR][4];
+    const int zbeg = z0 - RZ, nsteps = (z1 - z0) + 2 * RZ;
+    stage(zbeg, 0);
+    for (int q0 = 0; q0 < nsteps; q0 += NR) {
+#pragma unroll
+        for (int s = 0; s < NR; ++s) {
+            const int q = q0 + s;
+            if (q < nsteps) {
+                const int buf = q & 1;
+                cp_async_wait_all();
+                __syncthreads();
+                if (q + 1 < nsteps) stage(zbeg + q + 1, buf ^ 1);
+                // ---- x pass: 4 consecutive outputs per task, rows incl. y halo
+                for (int task = tid; task < AH * (ZM_TX / 4); task += ZM_NT) {
+                    const int yy = task >> 4, cx = task & 15;
+                    const double2* ra = reinterpret_cast<const double2*>(Aa + buf * NA + yy * AW + 4 * cx);
+                    double w[WIN];
+#pragma unroll
+                    for (int v = 0; v < WIN / 2; ++v) {
+                        double2 t2 = ra[v];
+                        if (ADD) {
+                            const double2 u2 = reinterpret_cast<const double2*>(Ab + buf * NA + yy * AW + 4 * cx)[v];
+                            t2.x = t2.x + u2.x;
+                            t2.y = t2.y + u2.y;
+                        }
+                        w[2 * v] = t2.x;
+                        w[2 * v + 1] = t2.y;
+                    }
+                    double o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        double sum = 0.0;
+#pragma unroll
+                        for (int t = 0; t <= 2 * R; ++t) sum += kc.k[0][t] * w[j + (RP - R) + t];
+                        o[j] = sum;
+                    }
+                    double2* rb = reinterpret_cast<double2*>(B + yy * ZM_TX + 4 * cx);
+                    rb[0] = make_double2(o[0], o[1]);
+                    rb[1] = make_double2(o[2], o[3]);
+                }
+                __syncthreads();
+                // ---- y pass: sliding window over 4 + 2R rows of this thread's column
+                {
+                    double col[4 + 2 * R];
+#pragma unroll
+                    for (int i = 0; i < 4 + 2 * R; ++i) col[i] = B[(4 * yb + i) * ZM_TX + ox];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        double sum = 0.0;
+#pragma unroll
+                        for (int t = 0; t <= 2 * R; ++t) sum += kc.k[1][t] * col[j + t];
+                        ring[s][j] = sum;
+                    }
+                }
+                // ---- z pass over the ring (slot s is the newest plane; oldest is slot (s + 1) % NR)
+                if (q >= 2 * RZ) {
+                    const int zo = zbeg + q - RZ;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        double sum = 0.0;
+#pragma unroll
+                        for (int t = 0; t < NR; ++t) sum += kc.k[2][t] * ring[(s + 1 + t) % NR][j];
+                        const int gy = y0 + 4 * yb + j;
+                        if (gx < nx && gy < ny) op[(size_t)zo * plane + (size_t)gy * nx + gx] = sum;
+                    }
+                }
+            }
+        }
+    }
+}
+
+template <int R, int RZ>
+inline int launch_zm2_rz(b200reg_ctx* ctx, const double* a, const double* b, double* out, int nx, int ny, int nz, dim3 g, int zchunk, int nchunks,
+                         const SmallCoeffs& sc, const DemonsCtrl* ctrl, int it)
+{
+    constexpr int RP = (R + 1) & ~1;
+    constexpr int NA = (ZM_TX + 2 * RP) * (ZM_TY + 2 * R);
+    constexpr int NB = (ZM_TY + 2 * R) * ZM_TX;
+    if (b) {
+        constexpr size_t smem = (size_t)(4 * NA + NB) * sizeof(double);
+        static bool attr_set = false;
+        if (!attr_set) {
+            B200_CUDA(cudaFuncSetAttribute(conv3d_zm2_kernel<R, RZ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        conv3d_zm2_kernel<R, RZ, true><<<g, ZM_NT, smem, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it);
+    } else {
+        constexpr size_t smem = (size_t)(2 * NA + NB) * sizeof(double);
+        static bool attr_set = false;
+        if (!attr_set) {
+            B200_CUDA(cudaFuncSetAttribute(conv3d_zm2_kernel<R, RZ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_set = true;
+        }
+        conv3d_zm2_kernel<R, RZ, false><<<g, ZM_NT, smem, ctx->stream>>>(a, nullptr, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it);
+    }
+    return B200REG_OK;
+}
+template <int R>
+inline int launch_zm2_r(b200reg_ctx* ctx, int rz, const double* a, const double* b, double* out, int nx, int ny, int nz, dim3 g, int zchunk,
+                        int nchunks, const SmallCoeffs& sc, const DemonsCtrl* ctrl, int it)
+{
+    switch (rz) {
+    case 1: return launch_zm2_rz<R, 1>(ctx, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it);
+    case 2: return launch_zm2_rz<R, 2>(ctx, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it);
+    case 3: return launch_zm2_rz<R, 3>(ctx, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it);
+    default: return launch_zm2_rz<R, 4>(ctx, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it);
+    }
+}
+
+inline bool zmarch_supported(const KernelCoeffs kc[3])
+{
+    return kc[0].r <= ZM_RXY && kc[1].r <= ZM_RXY && kc[2].r >= 1 && kc[2].r <= ZM_RMAX;
+}
+
+// out <- G_z G_y G_x (a [+ b]) for `nplanes` component volumes; a/b/out must not alias.
+inline int launch_conv3d_zmarch(b200reg_ctx* ctx, const double* a, const double* b, double* out, int nx, int ny, int nz, int nplanes,
+                                const KernelCoeffs kc[3], const DemonsCtrl* ctrl, int it)
+{
+    SmallCoeffs sc;
+    for (int ax = 0; ax < 3; ++ax) {
+        sc.r[ax] = kc[ax].r;
+        for (int t = 0; t <= 2 * kc[ax].r; ++t) sc.k[ax][t] = kc[ax].k[t];
+    }
+    const int tiles = ((nx + ZM_TX - 1) / ZM_TX) * ((ny + ZM_TY - 1) / ZM_TY) * nplanes;
+    // enough CTAs for ~4 waves of 2 CTAs/SM, but chunks of at least 16 planes (each chunk re-reads 2*rz planes)
+    int nchunks = (ctx->sm_count * 8 + tiles - 1) / tiles;
+    const int max_chunks = (nz + 15) / 16;
+    if (nchunks > max_chunks) nchunks = max_chunks;
+    if (nchunks < 1) nchunks = 1;
+    const int zchunk = (nz + nchunks - 1) / nchunks;
+    nchunks = (nz + zchunk - 1) / zchunk;
+    dim3 g((nx + ZM_TX - 1) / ZM_TX, (ny + ZM_TY - 1) / ZM_TY, nplanes * nchunks);
+    if (kc[0].r == kc[1].r && kc[0].r >= 1 && !ctx->force_zm1) {
+        int rc;
+        switch (kc[0].r) {
+        case 1: rc = launch_zm2_r<1>(ctx, kc[2].r, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it); break;
+        case 2: rc = launch_zm2_r<2>(ctx, kc[2].r, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it); break;
+        case 3: rc = launch_zm2_r<3>(ctx, kc[2].r, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it); break;
+        default: rc = launch_zm2_r<4>(ctx, kc[2].r, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it); break;
+        }
+        B200_TRY(rc);
+        ctx->launches++;
+        B200_CHECK_LAUNCH();
+        return B200REG_OK;
+    }
+#define ZM_LAUNCH(RZ)                                                                                                                       \
+    if (b) conv3d_zmarch_kernel<RZ, true><<<g, ZM_NT, 0, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it);              \
+    else conv3d_zmarch_kernel<RZ, false><<<g, ZM_NT, 0, ctx->stream>>>(a, nullptr, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it)
+    switch (kc[2].r) {
+    case 1: ZM_LAUNCH(1); break;
+    case 2: ZM_LAUNCH(2); break;
+    case 3: ZM_LAUNCH(3); break;
+    default: ZM_LAUNCH(4); break;
+    }
+#undef ZM_LAUNCH
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+
 // DiscreteGaussianImageFilter on a Float32 image: variance (mm^2) -> voxel^2 per axis when
 // use_image_spacing, passes z -> y -> x, float32 intermediates.
 inline int discrete_gaussian_f32(b200reg_ctx* ctx, const float* d_in, float* d_out, const b200reg_geom& g, const double* variance,
