@@ -65,6 +65,7 @@ API int b200reg_create(int device, void* stream, b200reg_ctx** out)
     B200_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     B200_CUDA(cudaMallocHost(&ctx->h_scratch, 64 * sizeof(double)));
     if (const char* e = getenv("B200REG_FORCE_SEPARABLE")) ctx->force_separable = (e[0] == '1');
+    if (const char* e = getenv("B200REG_UNFUSED_FORCE")) ctx->unfused_force = (e[0] == '1');
     if (const char* e = getenv("B200REG_FORCE_ZM1")) ctx->force_zm1 = (e[0] == '1');
     *out = ctx;
     return B200REG_OK;
@@ -311,7 +312,7 @@ API int b200reg_demons_force(b200reg_ctx* ctx, const float* d_fixed, const b200r
     demons_ctrl_init_kernel<<<1, 1, 0, ctx->stream>>>(ws.ctrl.as<DemonsCtrl>(), 1);
     ctx->launches++;
     const GeomD gf = make_geomd(*fixed_geom), gm = make_geomd(*moving_geom);
-    B200_TRY(demons_calculate_change(ctx, d_fixed, gf, d_moving, gm, d_field_soa, make_force_params(*fixed_geom, *params), &ws, 0, 1));
+    B200_TRY(demons_calculate_change(ctx, d_fixed, gf, d_moving, gm, d_field_soa, make_force_params(*fixed_geom, *params), &ws, 0, 1, true));
     const size_t n = nvox(*fixed_geom);
     B200_CUDA(cudaMemcpyAsync(d_w, ws.W.p, n * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
     B200_CUDA(cudaMemcpyAsync(d_u_soa, ws.U.p, 3 * n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));

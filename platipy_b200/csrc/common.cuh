@@ -57,6 +57,7 @@ struct b200reg_ctx {
     // pinned scratch for small read-backs
     double* h_scratch = nullptr;  // 64 doubles
     bool force_separable = false;  // B200REG_FORCE_SEPARABLE=1: unfused smoothing passes (A/B testing)
+    bool unfused_force = false;    // B200REG_UNFUSED_FORCE=1: separate warp and force kernels (W through HBM)
     bool force_zm1 = false;        // B200REG_FORCE_ZM1=1: first-generation fused smoothing kernel
 };
 

@@ -21,6 +21,8 @@ struct ForceParams {
     double intensity_thresh;   // 0.001
     double denom_thresh;       // 1e-9
     double max_rms_error;      // 0.02
+    double half_inv_sp[3];     // 0.5 / spacing (the factor ITK's central differences multiply by)
+    double inv_normalizer;     // exact reciprocal when the normalizer is a power of two, else 0
 };
 
 // WarpImageFilter with the field on the output (fixed) grid: point = index->physical + D; linear
@@ -222,6 +224,325 @@ __global__ void __launch_bounds__(1024) demons_finish_kernel(const double* __res
     }
 }
 
+// ---- fused warp + force, z-marching -------------------------------------------------------------------------------
+// One CTA owns a 64 x 16 column of the fixed grid and marches along z.  Per step every thread produces the
+// warped-moving value W (rounded through float32 exactly as WarpImageFilter stores it) and the fixed value F of
+// its voxels on plane z+1 -- plus one voxel of the one-voxel x/y halo -- into 4-deep shared-memory rings held as
+// doubles (FLT_MAX sentinel kept), then computes the ESM update of plane z from the rings.  W never travels to
+// HBM, every F / D value is read once, index -> physical arithmetic that does not depend on z is hoisted out of
+// the loop, and the SSD / count / |U|^2 partial sums stay in registers until one block reduction at the end.
+// Arithmetic per voxel is the same sequence of IEEE operations as demons_warp_kernel + demons_force_kernel.
+constexpr int UP_TX = 64, UP_TY = 16, UP_NT = 256, UP_HW = UP_TX + 2, UP_HH = UP_TY + 2, UP_NP = UP_HW * UP_HH, UP_RING = 4;
+constexpr int UP_NHALO = UP_NP - UP_TX * UP_TY;  // 164
+constexpr size_t UP_SMEM = (size_t)2 * UP_RING * UP_NP * sizeof(double);
+
+template <bool DIAG>
+__global__ void __launch_bounds__(UP_NT, 2) demons_update_kernel(const float* __restrict__ F, const float* __restrict__ M, const double* __restrict__ D,
+                                                                  double* __restrict__ U, double* __restrict__ partials,
+                                                                  const __grid_constant__ GeomD gf, const __grid_constant__ GeomD gm,
+                                                                  const __grid_constant__ ForceParams fp, int zchunk, int nchunks,
+                                                                  const DemonsCtrl* __restrict__ ctrl, int it)
+{
+    if (it >= ctrl->halt_iter) return;
+    extern __shared__ __align__(16) double up_smem[];
+    double* Wr = up_smem;                     // [UP_RING][UP_NP]
+    double* Fr = up_smem + UP_RING * UP_NP;   // [UP_RING][UP_NP]
+    // sent[slot] == p  <=>  plane p (held in that slot) contains at least one FLT_MAX sentinel inside this CTA's
+    // tile + halo.  Stale entries name older planes and never match, so no reset is needed.
+    __shared__ int sent[UP_RING];
+    const int tid = threadIdx.x;
+    if (tid < UP_RING) sent[tid] = -0x7fffffff;
+    __syncthreads();
+    const int nx = gf.nx, ny = gf.ny, nz = gf.nz;
+    const int x0 = blockIdx.x * UP_TX, y0 = blockIdx.y * UP_TY;
+    const int z0 = blockIdx.z * zchunk, z1 = min(nz, z0 + zchunk);
+    const int plane = nx * ny;
+    const size_t n = (size_t)plane * nz;
+    const double WMAX = (double)FLT_MAX;
+
+    // positions this thread produces: 4 own voxels (column ox, rows 4*yb..4*yb+3) and at most one halo voxel
+    const int ox = tid & (UP_TX - 1), yb = tid >> 6;
+    int hx[5], hy[5];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        hx[j] = ox + 1;
+        hy[j] = 4 * yb + j + 1;
+    }
+    {
+        const int e = tid;
+        if (e < UP_HW) { hx[4] = e; hy[4] = 0; }
+        else if (e < 2 * UP_HW) { hx[4] = e - UP_HW; hy[4] = UP_HH - 1; }
+        else if (e < 2 * UP_HW + UP_TY) { hx[4] = 0; hy[4] = e - 2 * UP_HW + 1; }
+        else { hx[4] = UP_HW - 1; hy[4] = e - 2 * UP_HW - UP_TY + 1; }
+    }
+    const int npos = tid < UP_NHALO ? 5 : 4;
+    int poff[5];      // offset within a plane, or -1 when the position lies outside the image
+    double px[5], py[5];  // DIAG: z-independent part of the physical point
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        const int gx = x0 - 1 + hx[q], gy = y0 - 1 + hy[q];
+        const bool ok = q < npos && gx >= 0 && gx < nx && gy >= 0 && gy < ny;
+        poff[q] = ok ? gy * nx + gx : -1;
+        if (DIAG) {
+            // idx2pt with a diagonal index-to-physical matrix: the zero terms add exact zeros
+            px[q] = gf.i2p[0] * (double)gx + gf.origin[0];
+            py[q] = gf.i2p[4] * (double)gy + gf.origin[1];
+        }
+    }
+
+    int soff[5];  // always-in-bounds offset for unconditional loads
+#pragma unroll
+    for (int q = 0; q < 5; ++q) soff[q] = poff[q] < 0 ? 0 : poff[q];
+
+    // W / F of plane z for this thread's positions.  Branch-free up to the shared-memory stores so that the
+    // loads of all positions are in flight together (field loads first, then the 8-point gathers).
+    auto produce = [&](int z) {
+        if (z < 0 || z >= nz) return;
+        const int slot = z & (UP_RING - 1);
+        const size_t zo = (size_t)z * plane;
+        double pz = 0.0;
+        if (DIAG) pz = gf.i2p[8] * (double)z + gf.origin[2];
+        double dd[5][3];
+        float fv[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            const size_t o = zo + soff[q];
+            dd[q][0] = D[o];
+            dd[q][1] = D[o + n];
+            dd[q][2] = D[o + 2 * n];
+            fv[q] = F[o];
+        }
+        LinW lw[5];
+        bool ins[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            double p[3], c[3];
+            if (DIAG) {
+                p[0] = px[q];
+                p[1] = py[q];
+                p[2] = pz;
+            } else {
+                const int gy = soff[q] / nx, gx = soff[q] - gy * nx;
+                idx2pt(gf, (double)gx, (double)gy, (double)z, p);
+            }
+            p[0] += dd[q][0];
+            p[1] += dd[q][1];
+            p[2] += dd[q][2];
+            if (DIAG) {
+                c[0] = gm.p2i[0] * (p[0] - gm.origin[0]);
+                c[1] = gm.p2i[4] * (p[1] - gm.origin[1]);
+                c[2] = gm.p2i[8] * (p[2] - gm.origin[2]);
+            } else {
+                pt2cidx(gm, p, c);
+            }
+            ins[q] = inside_buffer(gm, c);
+            lw[q] = lin_setup(gm, c);
+            // points outside the moving buffer are never interpolated; keep their (unused) gather in bounds
+            lw[q].b0 = min(lw[q].b0, gm.nx - 1);
+            lw[q].b1 = min(lw[q].b1, gm.ny - 1);
+            lw[q].b2 = min(lw[q].b2, gm.nz - 1);
+        }
+        double wv[5];
+#pragma unroll
+        for (int q = 0; q < 5; ++q) wv[q] = lin_eval<float>(M, gm, lw[q]);
+#pragma unroll
+        for (int q = 0; q < 5; ++q) {
+            if (poff[q] >= 0) {
+                const int si = slot * UP_NP + hy[q] * UP_HW + hx[q];
+                Wr[si] = ins[q] ? (double)(float)wv[q] : WMAX;
+                Fr[si] = (double)fv[q];
+                if (!ins[q]) sent[slot] = z;
+            }
+        }
+    };
+
+    double ssd = 0.0, cnt = 0.0, ssc = 0.0;
+    const int gxo = x0 + ox;
+    // voxels whose x/y neighbours all exist (z is checked per step)
+    bool inner_xy[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int gy = y0 + 4 * yb + j;
+        inner_xy[j] = poff[j] >= 0 && gxo >= 1 && gxo <= nx - 2 && gy >= 1 && gy <= ny - 2;
+    }
+
+    // generic ESM update of one voxel (all border / sentinel cases), identical to demons_force_kernel
+    auto slow_voxel = [&](int j, int z, int sc, int sm1, int sp1, double& u0, double& u1, double& u2) {
+        const int gy = y0 + 4 * yb + j;
+        const int ci = hy[j] * UP_HW + hx[j];
+        const double movingValue = Wr[sc + ci];
+        if (movingValue == WMAX) return;
+        const double fixedValue = Fr[sc + ci];
+        const int idx[3] = { gxo, gy, z };
+        const int dims[3] = { nx, ny, nz };
+        const int nb_p[3] = { sc + ci + 1, sc + ci + UP_HW, sp1 + ci };
+        const int nb_m[3] = { sc + ci - 1, sc + ci - UP_HW, sm1 + ci };
+        double g2[3];
+#pragma unroll
+        for (int dim = 0; dim < 3; ++dim) {
+            const int nd = dims[dim];
+            double wg;
+            if (idx[dim] == 0) {
+                if (nd < 2) wg = 0.0;
+                else {
+                    const double nb = Wr[nb_p[dim]];
+                    if (nb == WMAX) wg = 0.0;
+                    else {
+                        wg = nb - movingValue;
+                        wg /= gf.spacing[dim];
+                    }
+                }
+            } else if (idx[dim] == nd - 1) {
+                const double nb = Wr[nb_m[dim]];
+                if (nb == WMAX) wg = 0.0;
+                else {
+                    wg = movingValue - nb;
+                    wg /= gf.spacing[dim];
+                }
+            } else {
+                const double nb = Wr[nb_p[dim]];
+                const double pb = Wr[nb_m[dim]];
+                if (nb == WMAX) {
+                    if (pb == WMAX) wg = 0.0;
+                    else {
+                        wg = movingValue - pb;
+                        wg /= gf.spacing[dim];
+                    }
+                } else if (pb == WMAX) {
+                    wg = nb - movingValue;
+                    wg /= gf.spacing[dim];
+                } else {
+                    wg = nb - pb;
+                    wg *= fp.half_inv_sp[dim];
+                }
+            }
+            double fg;
+            if (idx[dim] < 1 || idx[dim] > nd - 2) fg = 0.0;
+            else {
+                fg = Fr[nb_p[dim]] - Fr[nb_m[dim]];
+                fg *= fp.half_inv_sp[dim];
+            }
+            g2[dim] = fg + wg;
+        }
+        double J[3];
+        if (DIAG) {
+            J[0] = g2[0];
+            J[1] = g2[1];
+            J[2] = g2[2];
+        } else {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                double sum = 0.0;
+                sum += gf.direction[r * 3 + 0] * g2[0];
+                sum += gf.direction[r * 3 + 1] * g2[1];
+                sum += gf.direction[r * 3 + 2] * g2[2];
+                J[r] = sum;
+            }
+        }
+        const double gm2 = J[0] * J[0] + J[1] * J[1] + J[2] * J[2];
+        const double speed = fixedValue - movingValue;
+        if (!(fabs(speed) < fp.intensity_thresh)) {
+            const double denom = (fp.normalizer > 0.0) ? gm2 + (speed * speed) / fp.normalizer : gm2;
+            if (!(denom < fp.denom_thresh)) {
+                const double factor = 2.0 * speed / denom;
+                u0 = factor * J[0];
+                u1 = factor * J[1];
+                u2 = factor * J[2];
+            }
+        }
+        ssd += speed * speed;
+        cnt += 1.0;
+        ssc += u0 * u0 + u1 * u1 + u2 * u2;
+    };
+
+    produce(z0 - 1);
+    produce(z0);
+    for (int z = z0; z < z1; ++z) {
+        produce(z + 1);
+        __syncthreads();
+        const int sc = (z & (UP_RING - 1)) * UP_NP, sm1 = ((z - 1) & (UP_RING - 1)) * UP_NP, sp1 = ((z + 1) & (UP_RING - 1)) * UP_NP;
+        const size_t zo = (size_t)z * plane;
+        const bool inner_z = z >= 1 && z <= nz - 2;
+        // interior planes without any sentinel in the three ring planes take the branch-free path
+        const bool clean = inner_z && sent[sc / UP_NP] != z && sent[sm1 / UP_NP] != z - 1 && sent[sp1 / UP_NP] != z + 1;
+        const bool all_fast = clean && inner_xy[0] && inner_xy[1] && inner_xy[2] && inner_xy[3];
+        if (all_fast) {
+            // branch-free interior path: central differences everywhere (same operations as the generic path)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int ci = hy[j] * UP_HW + hx[j];
+                const double fc = Fr[sc + ci], wcj = Wr[sc + ci];
+                double g0 = (Fr[sc + ci + 1] - Fr[sc + ci - 1]) * fp.half_inv_sp[0] + (Wr[sc + ci + 1] - Wr[sc + ci - 1]) * fp.half_inv_sp[0];
+                double g1 = (Fr[sc + ci + UP_HW] - Fr[sc + ci - UP_HW]) * fp.half_inv_sp[1] + (Wr[sc + ci + UP_HW] - Wr[sc + ci - UP_HW]) * fp.half_inv_sp[1];
+                double g2 = (Fr[sp1 + ci] - Fr[sm1 + ci]) * fp.half_inv_sp[2] + (Wr[sp1 + ci] - Wr[sm1 + ci]) * fp.half_inv_sp[2];
+                if (!DIAG) {
+                    const double a0 = g0, a1 = g1, a2 = g2;
+                    g0 = ((0.0 + gf.direction[0] * a0) + gf.direction[1] * a1) + gf.direction[2] * a2;
+                    g1 = ((0.0 + gf.direction[3] * a0) + gf.direction[4] * a1) + gf.direction[5] * a2;
+                    g2 = ((0.0 + gf.direction[6] * a0) + gf.direction[7] * a1) + gf.direction[8] * a2;
+                }
+                const double gm2 = g0 * g0 + g1 * g1 + g2 * g2;
+                const double speed = fc - wcj;
+                const double s2 = speed * speed;
+                double denom = gm2;
+                if (fp.normalizer > 0.0) denom = gm2 + (fp.inv_normalizer != 0.0 ? s2 * fp.inv_normalizer : s2 / fp.normalizer);
+                const bool live = !(fabs(speed) < fp.intensity_thresh) && !(denom < fp.denom_thresh);
+                const double factor = live ? 2.0 * speed / denom : 0.0;
+                const double u0 = live ? factor * g0 : 0.0, u1 = live ? factor * g1 : 0.0, u2 = live ? factor * g2 : 0.0;
+                ssd += s2;
+                cnt += 1.0;
+                ssc += u0 * u0 + u1 * u1 + u2 * u2;
+                const size_t o = zo + poff[j];
+                U[o] = u0;
+                U[o + n] = u1;
+                U[o + 2 * n] = u2;
+            }
+        } else {
+#pragma unroll 1
+            for (int j = 0; j < 4; ++j) {
+                if (poff[j] < 0) continue;
+                double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+                slow_voxel(j, z, sc, sm1, sp1, u0, u1, u2);
+                const size_t o = zo + poff[j];
+                U[o] = u0;
+                U[o + n] = u1;
+                U[o + 2 * n] = u2;
+            }
+        }
+    }
+    // one block reduction per CTA
+    __shared__ double sh[3][UP_NT / 32];
+    const int lane = tid & 31, wid = tid >> 5;
+    ssd = warp_sum(ssd);
+    cnt = warp_sum(cnt);
+    ssc = warp_sum(ssc);
+    if (lane == 0) {
+        sh[0][wid] = ssd;
+        sh[1][wid] = cnt;
+        sh[2][wid] = ssc;
+    }
+    __syncthreads();
+    if (wid == 0) {
+        constexpr int NW = UP_NT / 32;
+        double a = lane < NW ? sh[0][lane] : 0.0, b = lane < NW ? sh[1][lane] : 0.0, c = lane < NW ? sh[2][lane] : 0.0;
+        a = warp_sum(a);
+        b = warp_sum(b);
+        c = warp_sum(c);
+        if (lane == 0) {
+            const size_t bid = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+            partials[bid * 3 + 0] = a;
+            partials[bid * 3 + 1] = b;
+            partials[bid * 3 + 2] = c;
+        }
+    }
+}
+
+inline bool geom_is_diag(const GeomD& g)
+{
+    const double* d = g.direction;
+    return d[0] == 1.0 && d[4] == 1.0 && d[8] == 1.0 && d[1] == 0.0 && d[2] == 0.0 && d[3] == 0.0 && d[5] == 0.0 && d[6] == 0.0 && d[7] == 0.0;
+}
+
 __global__ void demons_ctrl_init_kernel(DemonsCtrl* ctrl, int n_iters)
 {
     ctrl->halt_iter = n_iters <= 0 ? 0 : 0x7fffffff;
@@ -260,22 +581,69 @@ inline ForceParams make_force_params(const b200reg_geom& gF, const b200reg_demon
         nrm *= p.max_update_step_length * p.max_update_step_length / 3.0;
         fp.normalizer = nrm;
     } else fp.normalizer = -1.0;
+    for (int k = 0; k < 3; ++k) fp.half_inv_sp[k] = 0.5 / gF.spacing[k];
+    {
+        // x / 2^k == x * 2^-k exactly (barring overflow/underflow), so a power-of-two normalizer lets the kernel
+        // replace the division by a multiplication without changing a single bit
+        int e = 0;
+        const double m = std::frexp(fp.normalizer, &e);
+        fp.inv_normalizer = (fp.normalizer > 0.0 && m == 0.5 && e > -500 && e < 500) ? 1.0 / fp.normalizer : 0.0;
+    }
     fp.intensity_thresh = p.intensity_difference_threshold;
     fp.denom_thresh = p.denominator_threshold;
     fp.max_rms_error = p.max_rms_error;
     return fp;
 }
 
-inline int demons_calculate_change(b200reg_ctx* ctx, const float* F, const GeomD& gf, const float* M, const GeomD& gm, const double* D,
-                                   const ForceParams& fp, DemonsWorkspace* ws, int it, int n_iters)
+inline dim3 update_grid(b200reg_ctx* ctx, const GeomD& gf, int* zchunk)
 {
-    const dim3 g = grid3(gf.nx, gf.ny, gf.nz), b = block3();
+    const int tx = (gf.nx + UP_TX - 1) / UP_TX, ty = (gf.ny + UP_TY - 1) / UP_TY;
+    int nchunks = (ctx->sm_count * 8 + tx * ty - 1) / (tx * ty);
+    const int max_chunks = (gf.nz + 15) / 16;
+    if (nchunks > max_chunks) nchunks = max_chunks;
+    if (nchunks < 1) nchunks = 1;
+    *zchunk = (gf.nz + nchunks - 1) / nchunks;
+    nchunks = (gf.nz + *zchunk - 1) / *zchunk;
+    return dim3(tx, ty, nchunks);
+}
+
+inline int demons_calculate_change(b200reg_ctx* ctx, const float* F, const GeomD& gf, const float* M, const GeomD& gm, const double* D,
+                                   const ForceParams& fp, DemonsWorkspace* ws, int it, int n_iters, bool want_w = false)
+{
     DemonsCtrl* ctrl = ws->ctrl.as<DemonsCtrl>();
-    demons_warp_kernel<<<g, b, 0, ctx->stream>>>(M, D, ws->W.as<float>(), gf, gm, ctrl, it);
-    demons_force_kernel<<<g, b, 0, ctx->stream>>>(F, ws->W.as<float>(), ws->U.as<double>(), ws->partials.as<double>(), gf, fp, ctrl, it);
-    demons_finish_kernel<<<1, 1024, 0, ctx->stream>>>(ws->partials.as<double>(), ws->nblocks, ctrl, fp.max_rms_error, it, n_iters,
-                                                      ws->trace.as<double>());
-    ctx->launches += 3;
+    size_t nblocks;
+    // the z-marching kernel needs a few CTAs per SM to hide its per-plane latency: small (coarse-level) grids
+    // run the one-thread-per-voxel kernels instead
+    int zchunk_probe;
+    const dim3 gprobe = update_grid(ctx, gf, &zchunk_probe);
+    const bool small_grid = (size_t)gprobe.x * gprobe.y * gprobe.z < (size_t)ctx->sm_count * 4;
+    if (want_w || ctx->unfused_force || small_grid) {
+        const dim3 g = grid3(gf.nx, gf.ny, gf.nz), b = block3();
+        nblocks = (size_t)g.x * g.y * g.z;
+        demons_warp_kernel<<<g, b, 0, ctx->stream>>>(M, D, ws->W.as<float>(), gf, gm, ctrl, it);
+        demons_force_kernel<<<g, b, 0, ctx->stream>>>(F, ws->W.as<float>(), ws->U.as<double>(), ws->partials.as<double>(), gf, fp, ctrl, it);
+        ctx->launches += 2;
+    } else {
+        int zchunk;
+        const dim3 g = update_grid(ctx, gf, &zchunk);
+        nblocks = (size_t)g.x * g.y * g.z;
+        static bool attr_set[2] = { false, false };
+        const bool diag = geom_is_diag(gf) && geom_is_diag(gm);
+        if (!attr_set[diag]) {
+            if (diag) B200_CUDA(cudaFuncSetAttribute(demons_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UP_SMEM));
+            else B200_CUDA(cudaFuncSetAttribute(demons_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UP_SMEM));
+            attr_set[diag] = true;
+        }
+        if (diag)
+            demons_update_kernel<true><<<g, UP_NT, UP_SMEM, ctx->stream>>>(F, M, D, ws->U.as<double>(), ws->partials.as<double>(), gf, gm, fp, zchunk,
+                                                                            (int)g.z, ctrl, it);
+        else
+            demons_update_kernel<false><<<g, UP_NT, UP_SMEM, ctx->stream>>>(F, M, D, ws->U.as<double>(), ws->partials.as<double>(), gf, gm, fp, zchunk,
+                                                                             (int)g.z, ctrl, it);
+        ctx->launches += 1;
+    }
+    demons_finish_kernel<<<1, 1024, 0, ctx->stream>>>(ws->partials.as<double>(), nblocks, ctrl, fp.max_rms_error, it, n_iters, ws->trace.as<double>());
+    ctx->launches += 1;
     B200_CHECK_LAUNCH();
     return B200REG_OK;
 }

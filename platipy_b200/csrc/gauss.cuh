@@ -298,7 +298,6 @@ __global__ void __launch_bounds__(ZM_NT, 2) conv3d_zm2_kernel(const double* __re
     constexpr int AW = ZM_TX + 2 * RP, AH = ZM_TY + 2 * R, NA = AW * AH;
     constexpr int NR = 2 * RZ + 1;
     constexpr int NLD = (NA + ZM_NT - 1) / ZM_NT;
-    constexpr int WIN = 4 + 2 * RP;
     extern __shared__ __align__(16) double zm_smem[];
     double* Aa = zm_smem;                       // [2][NA]
     double* Ab = zm_smem + 2 * NA;              // [2][NA] (ADD only)
@@ -350,33 +349,36 @@ __global__ void __launch_bounds__(ZM_NT, 2) conv3d_zm2_kernel(const double* __re
                 cp_async_wait_all();
                 __syncthreads();
                 if (q + 1 < nsteps) stage(zbeg + q + 1, buf ^ 1);
-                // ---- x pass: 4 consecutive outputs per task, rows incl. y halo
+                // ---- x pass: per task two output pairs {2cx, 2cx+1} and {32+2cx, 32+2cx+1} of one row (rows incl. the
+                // y halo).  Lanes read consecutive 16-byte words: conflict-free 128-bit shared loads and stores.
                 for (int task = tid; task < AH * (ZM_TX / 4); task += ZM_NT) {
                     const int yy = task >> 4, cx = task & 15;
-                    const double2* ra = reinterpret_cast<const double2*>(Aa + buf * NA + yy * AW + 4 * cx);
-                    double w[WIN];
 #pragma unroll
-                    for (int v = 0; v < WIN / 2; ++v) {
-                        double2 t2 = ra[v];
-                        if (ADD) {
-                            const double2 u2 = reinterpret_cast<const double2*>(Ab + buf * NA + yy * AW + 4 * cx)[v];
-                            t2.x = t2.x + u2.x;
-                            t2.y = t2.y + u2.y;
+                    for (int h = 0; h < 2; ++h) {
+                        const int xb = 2 * cx + h * (ZM_TX / 2);
+                        const double2* ra = reinterpret_cast<const double2*>(Aa + buf * NA + yy * AW + xb);
+                        double w[2 + 2 * RP];
+#pragma unroll
+                        for (int v = 0; v < 1 + RP; ++v) {
+                            double2 t2 = ra[v];
+                            if (ADD) {
+                                const double2 u2 = reinterpret_cast<const double2*>(Ab + buf * NA + yy * AW + xb)[v];
+                                t2.x = t2.x + u2.x;
+                                t2.y = t2.y + u2.y;
+                            }
+                            w[2 * v] = t2.x;
+                            w[2 * v + 1] = t2.y;
                         }
-                        w[2 * v] = t2.x;
-                        w[2 * v + 1] = t2.y;
-                    }
-                    double o[4];
+                        double o[2];
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        double sum = 0.0;
+                        for (int j = 0; j < 2; ++j) {
+                            double sum = 0.0;
 #pragma unroll
-                        for (int t = 0; t <= 2 * R; ++t) sum += kc.k[0][t] * w[j + (RP - R) + t];
-                        o[j] = sum;
+                            for (int t = 0; t <= 2 * R; ++t) sum += kc.k[0][t] * w[j + (RP - R) + t];
+                            o[j] = sum;
+                        }
+                        *reinterpret_cast<double2*>(B + yy * ZM_TX + xb) = make_double2(o[0], o[1]);
                     }
-                    double2* rb = reinterpret_cast<double2*>(B + yy * ZM_TX + 4 * cx);
-                    rb[0] = make_double2(o[0], o[1]);
-                    rb[1] = make_double2(o[2], o[3]);
                 }
                 __syncthreads();
                 // ---- y pass: sliding window over 4 + 2R rows of this thread's column
