@@ -201,6 +201,8 @@ int b200reg_vote_accumulate(b200reg_ctx* ctx, const uint8_t* d_label, const floa
  * d_num is overwritten; d_out may alias d_num.  Synchronises (global min/max). */
 int b200reg_vote_finalize(b200reg_ctx* ctx, float* d_num, const float* d_den, const b200reg_geom* geom,
                           double smooth_variance, double threshold, float* d_out);
+/* sitk.BinaryThreshold(img, lowerThreshold, upperThreshold) -> UInt8 {0,1} (fusion.py:217-220) */
+int b200reg_binary_threshold(b200reg_ctx* ctx, const void* d_in, int dtype, size_t n, double lower, double upper, uint8_t* d_out);
 /* ---- N14: sitk.STAPLE + RescaleIntensity + Threshold (fusion.py:217-232) --------------------------------- */
 /* d_decisions: n_raters pointers (host array of device pointers) to u8 volumes already binarised
  * (>= 0.5).  d_out: f64.  h_pq (optional): 2*n_raters doubles (p then q).  Synchronises. */

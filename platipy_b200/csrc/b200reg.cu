@@ -539,6 +539,17 @@ API int b200reg_vote_finalize(b200reg_ctx* ctx, float* d_num, const float* d_den
     return vote_finalize(ctx, d_num, d_den, *geom, smooth_variance, threshold, d_out);
 }
 
+API int b200reg_binary_threshold(b200reg_ctx* ctx, const void* d_in, int dtype, size_t n, double lower, double upper, uint8_t* d_out)
+{
+    ENTER(ctx);
+    REQUIRE(d_in && d_out, "invalid argument");
+    const int nb = ctx->sm_count * 8;
+    B200_DISPATCH_DTYPE(dtype, T, { binary_threshold_kernel<T><<<nb, 256, 0, ctx->stream>>>((const T*)d_in, d_out, n, lower, upper); });
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+
 API int b200reg_staple(b200reg_ctx* ctx, const uint8_t* const* d_decisions, int n_raters, size_t n, double confidence_weight,
                        uint32_t max_iterations, double threshold, int rescale, double* d_out, double* h_pq, int32_t* h_elapsed)
 {

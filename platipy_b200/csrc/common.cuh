@@ -195,6 +195,7 @@ struct Px;
             if (w > (double)(HI)) w = (double)(HI);                                 \
             return (T)w;                                                            \
         }                                                                           \
+        static double cast_host(double v) { return v < (double)(LO) ? (double)(LO) : (v > (double)(HI) ? (double)(HI) : v); } \
     };
 B200_INT_PX(int8_t, INT8_MIN, INT8_MAX)
 B200_INT_PX(uint8_t, 0, UINT8_MAX)
@@ -206,6 +207,7 @@ B200_INT_PX(uint32_t, 0, UINT32_MAX)
 template <>
 struct Px<int64_t> {
     __device__ static __forceinline__ double ld(const int64_t* p, size_t i) { return (double)p[i]; }
+    static double cast_host(double v) { return v < -9.2e18 ? -9.2e18 : (v > 9.2e18 ? 9.2e18 : v); }
     __device__ static __forceinline__ int64_t cast(double v)
     {
         if (v <= -9223372036854775808.0) return INT64_MIN;
@@ -216,6 +218,7 @@ struct Px<int64_t> {
 template <>
 struct Px<uint64_t> {
     __device__ static __forceinline__ double ld(const uint64_t* p, size_t i) { return (double)p[i]; }
+    static double cast_host(double v) { return v < 0 ? 0 : (v > 1.8e19 ? 1.8e19 : v); }
     __device__ static __forceinline__ uint64_t cast(double v)
     {
         if (v <= 0.0) return 0;
@@ -226,6 +229,7 @@ struct Px<uint64_t> {
 template <>
 struct Px<float> {
     __device__ static __forceinline__ double ld(const float* p, size_t i) { return (double)p[i]; }
+    static double cast_host(double v) { return v; }
     __device__ static __forceinline__ float cast(double v)
     {
         double w = v;
@@ -237,6 +241,7 @@ struct Px<float> {
 template <>
 struct Px<double> {
     __device__ static __forceinline__ double ld(const double* p, size_t i) { return p[i]; }
+    static double cast_host(double v) { return v; }
     __device__ static __forceinline__ double cast(double v) { return v; }
 };
 

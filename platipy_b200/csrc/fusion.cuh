@@ -249,6 +249,19 @@ inline int vote_finalize(b200reg_ctx* ctx, float* d_num, const float* d_den, con
     return B200REG_OK;
 }
 
+// BinaryThresholdImageFilter: (lower <= x <= upper) ? 1 : 0, compared as real numbers.
+// (SimpleITK may cast the double thresholds to the pixel type first, which would turn 0.5 into 0 for integer
+// label images; the real-valued comparison is what fusion.py:217-220 intends and is identical for float images.
+// See DESIGN.md "uncertain ITK semantics".)
+template <typename T>
+__global__ void binary_threshold_kernel(const T* __restrict__ in, uint8_t* __restrict__ out, size_t n, double lower, double upper)
+{
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) {
+        const double v = (double)in[q];
+        out[q] = (lower <= v && v <= upper) ? 1 : 0;
+    }
+}
+
 // ---- sitk.STAPLE (itk::STAPLEImageFilter), binary EM ---------------------------------------------------
 constexpr int STAPLE_MAX_RATERS = 32;
 struct StaplePtrs {

@@ -357,6 +357,12 @@ class Engine:
                                                   C.byref(g), float(smooth_variance), float(threshold or 0.0), C.c_void_p(out.data_ptr())))
         return DeviceImage(out, np.float32, geom_src.GetSpacing(), geom_src.GetOrigin(), geom_src.GetDirection(), False)
 
+    def binary_threshold(self, dimg, lower, upper=255.0):
+        out = self.empty(dimg.tensor.shape, np.uint8)
+        _abi.check(self.lib.b200reg_binary_threshold(self.ctx, dimg.ptr, dimg.dtype_id, dimg.tensor.numel(), float(lower), float(upper),
+                                                     C.c_void_p(out.data_ptr())))
+        return dimg.like(out, np.uint8, False)
+
     def staple(self, decisions, confidence_weight=1.0, max_iterations=0xFFFFFFFF, threshold=1e-4, rescale=True):
         n = len(decisions)
         ptrs = (C.c_void_p * n)(*[d.tensor.data_ptr() for d in decisions])

@@ -1,0 +1,139 @@
+"""
+Drop-in replacements for the reference's label-fusion entry points (platipy/imaging/label/fusion.py):
+
+    compute_weight_map      fusion.py:56-202   (vote types: unweighted, global, local)
+    combine_labels          fusion.py:239-292  (weighted vote -> DiscreteGaussian -> RescaleIntensity -> Threshold)
+    combine_labels_staple   fusion.py:205-236  (BinaryThreshold -> STAPLE -> RescaleIntensity -> Threshold)
+
+plus the sharded forms used by ``platipy_b200.multiatlas``: every rank accumulates the votes of its local
+atlases and ONE all-reduce (NCCL on GPUs, gloo in the CPU tests of the host logic) exchanges the per-voxel
+vote volume before the replicated finalisation.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import sitk_compat as sk
+from .engine import DeviceImage, Engine
+
+VOTE_TYPES = {"unweighted": 0, "global": 1, "local": 2}
+
+DEFAULT_VOTE_PARAMS = {
+    "sigma": 2.0,
+    "epsilon": 1e-5,
+    "factor": 1e12,
+    "gain": 6,
+    "blockSize": 5,
+    "normalise": False,
+}
+
+
+def _back(eng, dimg, like):
+    if isinstance(like, DeviceImage):
+        return dimg
+    return sk.from_native(eng.to_host(dimg), like)
+
+
+def compute_weight_map(target_image, moving_image, vote_type="unweighted", vote_params=DEFAULT_VOTE_PARAMS):
+    """Weight map of one atlas (fusion.py:56-202).  ``vote_params=None`` is valid for ``unweighted`` only,
+    as in the reference (multiatlas/run.py:92-96)."""
+    eng = Engine.get()
+    vt = vote_type.lower()
+    if vt not in VOTE_TYPES:
+        # block / patch_correlation: SURVEY 8f-3 ("next")
+        raise NotImplementedError(f"vote_type {vote_type!r} is not implemented on the B200 path (unweighted, global, local are)")
+    t, m = eng.to_device(target_image), eng.to_device(moving_image)
+    # fusion.py:76-80: cast to Float32 unless the pixel id is 6
+    t, m = eng.cast(t, np.float32), eng.cast(m, np.float32)
+    if t.GetSize() != m.GetSize():
+        raise RuntimeError("compute_weight_map: target and moving images do not occupy the same grid")
+    factor = sigma = eps = 0.0
+    if vt == "global":
+        factor = float(vote_params["factor"])
+    elif vt == "local":
+        sigma, eps = float(vote_params["sigma"]), float(vote_params["epsilon"])
+        if vote_params.get("normalise", False) is not False:
+            raise NotImplementedError("normalise=True / mask for local weight maps is not implemented on the B200 path")
+    w = eng.weight_map(t, m, VOTE_TYPES[vt], factor=factor, sigma=sigma, epsilon=eps)
+    return _back(eng, w, target_image)
+
+
+def _structure_names(structure_name):
+    if isinstance(structure_name, str):
+        return [structure_name]
+    return list(structure_name)
+
+
+def accumulate_votes(eng, atlas_set, s_name, label="DIR", num=None, den=None):
+    """Local part of combine_labels for one structure: num += w * L, den += w over the atlases of
+    ``atlas_set`` that contain the structure (fusion.py:255-276), float32 arithmetic in atlas order."""
+    first = num is None
+    ref = None
+    for case_id in atlas_set:
+        entry = atlas_set[case_id][label]
+        if s_name not in entry:
+            continue
+        lab = eng.cast(eng.to_device(entry[s_name]), np.uint8)
+        w = eng.to_device(entry["Weight Map"])
+        if ref is None:
+            ref = lab
+        if first:
+            num = eng.empty(lab.tensor.shape, np.float32)
+            den = eng.empty(lab.tensor.shape, np.float32)
+        eng.vote_accumulate(lab, w, num, den, first)
+        first = False
+    return num, den, ref
+
+
+def combine_labels(atlas_set, structure_name, label="DIR", threshold=1e-4, smooth_sigma=1.0, process_group=None):
+    """Combine labels using weight maps (fusion.py:239-292).  With ``process_group`` (torch.distributed) every
+    rank passes its LOCAL atlases and the vote volumes are summed with one all-reduce per structure."""
+    eng = Engine.get()
+    out = {}
+    any_like = None
+    for s_name in _structure_names(structure_name):
+        num, den, ref = accumulate_votes(eng, atlas_set, s_name, label)
+        if process_group is not None:
+            num, den, ref = _allreduce_votes(eng, num, den, ref, atlas_set, label, process_group)
+        if ref is None:
+            raise KeyError(s_name)
+        for case_id in atlas_set:
+            if s_name in atlas_set[case_id][label]:
+                any_like = atlas_set[case_id][label][s_name]
+                break
+        prob = eng.vote_finalize(num, den, ref, smooth_sigma * smooth_sigma, threshold)
+        out[s_name] = _back(eng, prob, any_like if any_like is not None else ref)
+    return out
+
+
+def _allreduce_votes(eng, num, den, ref, atlas_set, label, process_group):
+    import torch
+    import torch.distributed as dist
+
+    if num is None:
+        # this rank holds no atlas with the structure: contribute zeros on the common grid
+        any_img = next(iter(next(iter(atlas_set.values()))[label].values()))
+        ref = eng.to_device(any_img)
+        num = eng.zeros(ref.tensor.shape, np.float32)
+        den = eng.zeros(ref.tensor.shape, np.float32)
+    with torch.cuda.stream(eng.stream):
+        dist.all_reduce(num, group=process_group if process_group is not True else None)
+        dist.all_reduce(den, group=process_group if process_group is not True else None)
+    return num, den, ref
+
+
+def combine_labels_staple(label_list_dict, threshold=1e-4):
+    """Combine labels using STAPLE (fusion.py:205-236)."""
+    eng = Engine.get()
+    names = np.unique([n for d in label_list_dict.values() for n in d.keys()])
+    out = {}
+    for s_name in names:
+        imgs = [label_list_dict[i][s_name] for i in label_list_dict]  # KeyError if an atlas lacks it, as in the reference
+        dec = []
+        for im in imgs:
+            d = eng.to_device(im)
+            # sitk.BinaryThreshold(lowerThreshold=0.5) (upper 255) -> UInt8 {0, 1}
+            dec.append(eng.binary_threshold(d, 0.5, 255.0))
+        w, _info = eng.staple(dec, threshold=threshold, rescale=True)
+        out[str(s_name)] = _back(eng, w, imgs[0])
+    return out

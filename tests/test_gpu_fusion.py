@@ -1,0 +1,92 @@
+"""GPU parity of the label-fusion path (platipy/imaging/label/fusion.py) against the CPU oracle."""
+import numpy as np
+import pytest
+
+from oracle import itk_oracle as orc
+from oracle import platipy_ref as ref
+from platipy_b200 import fusion
+from platipy_b200 import sitk_compat as sk
+from platipy_b200.sitk_compat import Image
+from platipy_b200.synth import synth_labels, synth_pair
+
+pytestmark = pytest.mark.gpu
+REL_TOL = 1e-5
+
+
+def _atlas_set(n_atlas, size, n_struct, weights, missing=None):
+    rng = np.random.default_rng(5)
+    sp = (1.0, 1.0, 1.5)
+    atlas_set = {}
+    base = synth_labels(size, n_struct, seed=400)
+    for a in range(n_atlas):
+        entry = {}
+        for s in range(n_struct):
+            if missing and (a, s) in missing:
+                continue
+            lab = np.roll(base[s], shift=(a % 3 - 1, (a * 2) % 5 - 2, a % 4 - 1), axis=(0, 1, 2))
+            entry[f"S{s}"] = Image(lab.astype(np.uint8), sp)
+        entry["Weight Map"] = Image(weights(a, size, rng), sp)
+        atlas_set[f"{a:03d}"] = {"DIR": entry}
+    return atlas_set
+
+
+def test_weight_maps_match_oracle(engine):
+    t, m = synth_pair((40, 36, 20), seed=51, spacing=(1.0, 1.0, 2.0))
+    params = {"sigma": 2.0, "epsilon": 1e-5, "factor": 1e12, "normalise": False}
+    for vt in ("unweighted", "global", "local"):
+        got = fusion.compute_weight_map(t, m, vt, params)
+        exp = ref.compute_weight_map(t, m, vt, params)
+        assert got.GetPixelID() == sk.sitkFloat32
+        if vt == "global":  # one scalar from a 28k-term double sum: reduction order differs
+            assert np.allclose(got.array, exp.array, rtol=1e-6, atol=0)
+        elif vt == "local":  # pow(x, -1) on the device is not bit-identical to libm
+            assert np.allclose(got.array, exp.array, rtol=REL_TOL, atol=0)
+        else:
+            assert np.array_equal(got.array, exp.array)
+    assert np.array_equal(fusion.compute_weight_map(t, m, "unweighted", None).array, np.ones(t.array.shape, np.float32))
+    with pytest.raises(NotImplementedError):
+        fusion.compute_weight_map(t, m, "block", params)
+
+
+def test_combine_labels_bit_exact(engine):
+    size = (36, 30, 22)
+    flat = _atlas_set(5, size, 3, lambda a, s, rng: np.ones(s[::-1], np.float32))
+    rnd = _atlas_set(4, size, 2, lambda a, s, rng: (rng.random(s[::-1]) * (rng.random(s[::-1]) > 0.2)).astype(np.float32), missing={(1, 1)})
+    for atlas_set, names in ((flat, ["S0", "S1", "S2"]), (rnd, ["S0", "S1"]), (flat, "S1")):
+        got = fusion.combine_labels(atlas_set, names)
+        exp = ref.combine_labels(atlas_set, names)
+        assert list(got) == list(exp)
+        for k in got:
+            assert got[k].GetPixelID() == sk.sitkFloat32
+            assert np.array_equal(got[k].array, exp[k].array), k
+            assert got[k].array.max() == 1.0 and np.all((got[k].array == 0) | (got[k].array >= np.float32(1e-4)))
+    # threshold=0 / different smoothing
+    got = fusion.combine_labels(flat, "S0", threshold=0, smooth_sigma=2.0)
+    exp = ref.combine_labels(flat, "S0", threshold=0, smooth_sigma=2.0)
+    assert np.array_equal(got["S0"].array, exp["S0"].array)
+
+
+def test_staple_matches_oracle(engine):
+    size = (40, 32, 24)
+    truth = synth_labels(size, 1, seed=77)[0]
+    rng = np.random.default_rng(6)
+    raters = {}
+    for k in range(7):
+        r = truth.copy()
+        r[rng.random(truth.shape) < 0.02 * (k + 1)] ^= 1
+        raters[str(k)] = {"HEART": Image(r.astype(np.float32) * (1.0 if k % 2 else 0.75)), "OTHER": Image(np.roll(r, k, axis=2))}
+    got = fusion.combine_labels_staple(raters)
+    exp = ref.combine_labels_staple(raters)
+    assert sorted(got) == sorted(exp) == ["HEART", "OTHER"]
+    for k in got:
+        assert got[k].GetPixelID() == sk.sitkFloat64
+        # serial double sums over the whole volume on the CPU vs tree sums on the GPU: p, q agree to ~1e-15
+        assert np.allclose(got[k].array, exp[k].array, rtol=1e-9, atol=1e-12), k
+        assert got[k].array.max() == 1.0 and np.all((got[k].array == 0) | (got[k].array >= 1e-4))
+    # p / q / iteration count of the EM itself
+    dec = [(raters[k]["HEART"].array >= 0.5).astype(np.uint8) for k in raters]
+    W, p, q, it = orc.staple(dec)
+    gW, info = engine.staple([engine.to_device(Image(d)) for d in dec], threshold=0.0, rescale=False)
+    assert info["elapsed_iterations"] == it
+    assert np.allclose(info["p"], p, rtol=1e-12) and np.allclose(info["q"], q, rtol=1e-12)
+    assert np.allclose(engine.to_host(gW, pinned=False).array, W, rtol=1e-10, atol=1e-14)
