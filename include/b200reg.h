@@ -203,6 +203,10 @@ int b200reg_vote_finalize(b200reg_ctx* ctx, float* d_num, const float* d_den, co
                           double smooth_variance, double threshold, float* d_out);
 /* sitk.BinaryThreshold(img, lowerThreshold, upperThreshold) -> UInt8 {0,1} (fusion.py:217-220) */
 int b200reg_binary_threshold(b200reg_ctx* ctx, const void* d_in, int dtype, size_t n, double lower, double upper, uint8_t* d_out);
+/* STAPLE exchange: acc |= (label != 0) << bit ; out = (acc >> bit) & 1.  With disjoint bits per atlas a SUM
+ * all-reduce of the int32 volume equals the bitwise OR, after which every rank holds all decisions. */
+int b200reg_pack_decision(b200reg_ctx* ctx, const uint8_t* d_label, int bit, int32_t* d_packed, size_t n, int first);
+int b200reg_unpack_decision(b200reg_ctx* ctx, const int32_t* d_packed, int bit, uint8_t* d_out, size_t n);
 /* ---- N14: sitk.STAPLE + RescaleIntensity + Threshold (fusion.py:217-232) --------------------------------- */
 /* d_decisions: n_raters pointers (host array of device pointers) to u8 volumes already binarised
  * (>= 0.5).  d_out: f64.  h_pq (optional): 2*n_raters doubles (p then q).  Synchronises. */

@@ -550,6 +550,25 @@ API int b200reg_binary_threshold(b200reg_ctx* ctx, const void* d_in, int dtype, 
     return B200REG_OK;
 }
 
+API int b200reg_pack_decision(b200reg_ctx* ctx, const uint8_t* d_label, int bit, int32_t* d_packed, size_t n, int first)
+{
+    ENTER(ctx);
+    REQUIRE(d_label && d_packed && bit >= 0 && bit < 31, "invalid argument");
+    pack_decision_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_label, bit, d_packed, n, first);
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+API int b200reg_unpack_decision(b200reg_ctx* ctx, const int32_t* d_packed, int bit, uint8_t* d_out, size_t n)
+{
+    ENTER(ctx);
+    REQUIRE(d_packed && d_out && bit >= 0 && bit < 31, "invalid argument");
+    unpack_decision_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_packed, bit, d_out, n);
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+
 API int b200reg_staple(b200reg_ctx* ctx, const uint8_t* const* d_decisions, int n_raters, size_t n, double confidence_weight,
                        uint32_t max_iterations, double threshold, int rescale, double* d_out, double* h_pq, int32_t* h_elapsed)
 {

@@ -262,6 +262,18 @@ __global__ void binary_threshold_kernel(const T* __restrict__ in, uint8_t* __res
     }
 }
 
+__global__ void pack_decision_kernel(const uint8_t* __restrict__ label, int bit, int32_t* __restrict__ packed, size_t n, int first)
+{
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) {
+        const int32_t v = (label[q] != 0 ? 1 : 0) << bit;
+        packed[q] = first ? v : (packed[q] | v);
+    }
+}
+__global__ void unpack_decision_kernel(const int32_t* __restrict__ packed, int bit, uint8_t* __restrict__ out, size_t n)
+{
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) out[q] = (uint8_t)((packed[q] >> bit) & 1);
+}
+
 // ---- sitk.STAPLE (itk::STAPLEImageFilter), binary EM ---------------------------------------------------
 constexpr int STAPLE_MAX_RATERS = 32;
 struct StaplePtrs {

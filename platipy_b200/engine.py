@@ -363,6 +363,14 @@ class Engine:
                                                      C.c_void_p(out.data_ptr())))
         return dimg.like(out, np.uint8, False)
 
+    def pack_decision(self, label, bit, packed, first):
+        _abi.check(self.lib.b200reg_pack_decision(self.ctx, label.ptr, int(bit), C.c_void_p(packed.data_ptr()), label.tensor.numel(), int(bool(first))))
+
+    def unpack_decision(self, packed, bit, like):
+        out = self.empty(packed.shape, np.uint8)
+        _abi.check(self.lib.b200reg_unpack_decision(self.ctx, C.c_void_p(packed.data_ptr()), int(bit), C.c_void_p(out.data_ptr()), packed.numel()))
+        return like.like(out, np.uint8, False)
+
     def staple(self, decisions, confidence_weight=1.0, max_iterations=0xFFFFFFFF, threshold=1e-4, rescale=True):
         n = len(decisions)
         ptrs = (C.c_void_p * n)(*[d.tensor.data_ptr() for d in decisions])

@@ -1,0 +1,168 @@
+"""
+Multi-atlas segmentation, one atlas per GPU.
+
+The reference processes atlases strictly serially (platipy/imaging/projects/multiatlas/run.py:261-362:
+for every atlas -> Demons registration -> propagate CT + S labels -> weight map) and then fuses
+(run.py:364 ``combine_labels``; fusion.py:205 ``combine_labels_staple``).  Atlases are independent units, so
+they are partitioned over the ranks of a ``torch.distributed`` process group (atlas ``a`` -> rank
+``a mod world``) and the path's ONE exchange step is an all-reduce (sum) of the per-voxel vote volume:
+
+    weighted vote   float32 [num = sum_a w_a L_a , den = sum_a w_a] per structure          (8 B/voxel/structure)
+    STAPLE          int32 bit mask, bit a = decision of atlas a (sum == OR, bits are disjoint) (4 B/voxel/structure)
+
+followed by the replicated finalisation (normalise -> DiscreteGaussian -> rescale -> threshold, or the
+STAPLE EM).  A single Demons registration is not sharded.  The linear pre-registration stage of the
+reference pipeline (run.py:261-300) is outside this path: atlases are expected on the target
+grid already (the state after ``apply_transform`` with the rigid transform).
+
+``shard_atlases`` / ``exchange_sum`` are plain host logic and are exercised on CPU with the gloo backend.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import sitk_compat as sk
+
+MULTIATLAS_SETTINGS_DEFAULTS = {
+    "deformable_registration_settings": {
+        "isotropic_resample": True,
+        "resolution_staging": [16, 8, 4],
+        "iteration_staging": [5, 5, 5],
+        "smoothing_sigmas": [0, 0, 0],
+        "ncores": 8,
+        "default_value": -1000,
+        "verbose": False,
+    },
+    "label_fusion_settings": {
+        "vote_type": "unweighted",
+        "vote_params": None,
+        "optimal_threshold": {},
+        "fusion": "vote",  # "vote" = combine_labels (reference pipeline), "staple" = combine_labels_staple
+    },
+}
+
+
+def shard_atlases(atlas_ids, rank, world_size):
+    """Atlas ids handled by ``rank``: sorted ids, round-robin (atlas a -> rank a mod world)."""
+    ids = sorted(atlas_ids)
+    return [a for i, a in enumerate(ids) if i % world_size == rank]
+
+
+def atlas_bit(atlas_ids, atlas_id):
+    """Global bit index of an atlas in the STAPLE decision mask."""
+    return sorted(atlas_ids).index(atlas_id)
+
+
+def exchange_sum(tensors, group=None):
+    """The path's one collective: in-place sum over ranks of every tensor in ``tensors`` (NCCL for CUDA
+    tensors, gloo for CPU tensors).  No-op without an initialised process group."""
+    import torch.distributed as dist
+
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return tensors
+    for t in tensors:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return tensors
+
+
+def _dist_info(group=None):
+    import torch.distributed as dist
+
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
+def register_atlas(target, atlas_ct, atlas_labels, settings):
+    """Steps 3 of the reference pipeline for one atlas (run.py:312-347), device resident: Demons registration
+    of the atlas CT to the target, then the CT (linear, -1000) and every label (nearest neighbour, 0) through
+    the one transform in a single batched pass.  Returns ``{"CT Image", <structures>..., "Transform"}``."""
+    from . import registration as reg
+    from .engine import Engine
+
+    eng = Engine.get()
+    t, m = eng.to_device(target), eng.to_device(atlas_ct)
+    kw = dict(settings["deformable_registration_settings"])
+    _, tfm, _ = reg.fast_symmetric_forces_demons_registration(t, m, **kw)
+    names = list(atlas_labels)
+    imgs = [m] + [eng.to_device(atlas_labels[n]) for n in names]
+    outs = reg.apply_transform_batch(imgs, t, tfm, [-1000] + [0] * len(names), [sk.sitkLinear] + [sk.sitkNearestNeighbor] * len(names))
+    out = {"CT Image": outs[0], "Transform": tfm}
+    for n, o in zip(names, outs[1:]):
+        out[n] = o
+    return out
+
+
+def run_segmentation(img, atlas_set, settings=MULTIATLAS_SETTINGS_DEFAULTS, group=None):
+    """In-memory form of ``run_segmentation`` (run.py:106) from the deformable stage on.
+
+    img        target image (host ``Image`` or ``DeviceImage``)
+    atlas_set  ``{atlas_id: {"CT Image": image, "<structure>": label image, ...}}`` on the target grid; every rank
+               passes the FULL dictionary (or at least its own shard) and processes ``shard_atlases(...)`` of it.
+    returns    ``(results, results_prob)``: binary UInt8 masks and fused probability images per structure
+               (host images on every rank).
+    """
+    import torch
+
+    from . import fusion
+    from .engine import Engine
+
+    eng = Engine.get()
+    rank, world = _dist_info(group)
+    all_ids = sorted(atlas_set)
+    mine = shard_atlases(all_ids, rank, world)
+    structures = sorted({k for a in all_ids for k in atlas_set[a] if k != "CT Image"})
+    fs = settings["label_fusion_settings"]
+    vote_type, vote_params = fs.get("vote_type", "unweighted"), fs.get("vote_params", None)
+    target = eng.to_device(img)
+    tgt_f32 = eng.cast(target, np.float32)
+    z, y, x = target.tensor.shape
+
+    # ---- per-atlas work (independent units) --------------------------------------------------------------
+    local = {}
+    for a in mine:
+        labels = {k: v for k, v in atlas_set[a].items() if k != "CT Image"}
+        d = register_atlas(target, atlas_set[a]["CT Image"], labels, settings)
+        d["Weight Map"] = fusion.compute_weight_map(tgt_f32, eng.cast(d["CT Image"], np.float32), vote_type, vote_params)
+        local[a] = {"DIR": d}
+
+    # ---- the one exchange + replicated finalisation -------------------------------------------------------
+    results_prob = {}
+    if fs.get("fusion", "vote") == "staple":
+        packed = {}
+        for s in structures:
+            acc = eng.zeros((z, y, x), np.int32)
+            for a in mine:
+                if s in local[a]["DIR"]:
+                    lab = eng.binary_threshold(local[a]["DIR"][s], 0.5, 255.0)
+                    eng.pack_decision(lab, atlas_bit(all_ids, a), acc, False)
+            packed[s] = acc
+        with torch.cuda.stream(eng.stream):
+            exchange_sum(list(packed.values()), group)
+        for s in structures:
+            holders = [a for a in all_ids if s in atlas_set[a]]
+            dec = [eng.unpack_decision(packed[s], atlas_bit(all_ids, a), target) for a in holders]
+            prob, _ = eng.staple(dec, threshold=1e-4, rescale=True)
+            results_prob[s] = prob
+    else:
+        nums, dens = {}, {}
+        for s in structures:
+            num, den, _ = fusion.accumulate_votes(eng, local, s, "DIR")
+            if num is None:
+                num, den = eng.zeros((z, y, x), np.float32), eng.zeros((z, y, x), np.float32)
+            nums[s], dens[s] = num, den
+        with torch.cuda.stream(eng.stream):
+            exchange_sum(list(nums.values()) + list(dens.values()), group)
+        for s in structures:
+            results_prob[s] = eng.vote_finalize(nums[s], dens[s], target, 1.0, 1e-4)
+
+    # ---- binary masks (run.py:370-404; fill-hole / largest-component post-processing is SURVEY 8f-2) -------
+    results, probs_host = {}, {}
+    for s in structures:
+        thr = fs.get("optimal_threshold", {}).get(s, 0.5)
+        ph = eng.to_host(results_prob[s])
+        mx = float(ph.array.max())
+        mask = (ph.array / mx >= thr) if mx > 0 else np.zeros(ph.array.shape, bool)
+        results[s] = sk.Image(mask.astype(np.uint8), ph.GetSpacing(), ph.GetOrigin(), ph.GetDirection())
+        probs_host[s] = ph
+    return results, probs_host
