@@ -111,6 +111,101 @@ __global__ void __launch_bounds__(128) deriche_line_kernel(const double* __restr
     }
 }
 
+// Lines along x (the contiguous axis): one WARP owns 32 lines (32 consecutive y of one z / component) and walks
+// them in chunks of 32 samples staged through a padded shared-memory tile, so that global loads and stores are
+// coalesced along x while each lane still runs the sequential recurrence of its own line.  Same arithmetic as
+// deriche_line_kernel.
+constexpr int DX_WARPS = 4;
+__global__ void __launch_bounds__(32 * DX_WARPS) deriche_x_kernel(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, size_t nlines,
+                                                                    const __grid_constant__ DericheC c)
+{
+    __shared__ double tile[DX_WARPS][32][33];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const size_t line0 = ((size_t)blockIdx.x * DX_WARPS + wid) * 32;  // first line of this warp (lines = rows of nx samples)
+    if (line0 >= nlines) return;
+    double(*T)[33] = tile[wid];
+    const size_t myline = line0 + lane;
+    const bool mine = myline < nlines;
+    const int nchunk = (nx + 31) / 32;
+    // ---- causal
+    {
+        double v1 = 0.0, xm1 = 0.0, xm2 = 0.0, xm3 = 0.0, sm1 = 0, sm2 = 0, sm3 = 0, sm4 = 0;
+        for (int ch = 0; ch < nchunk; ++ch) {
+            const int x0 = ch * 32, x = x0 + lane;
+            for (int i = 0; i < 32; ++i) {
+                const size_t l = line0 + i;
+                T[i][lane] = (l < nlines && x < nx) ? in[l * nx + x] : 0.0;
+            }
+            __syncwarp();
+            if (mine) {
+                if (ch == 0) {
+                    v1 = T[lane][0];
+                    xm1 = xm2 = xm3 = v1;
+                }
+                const int lim = min(32, nx - x0);
+                for (int j = 0; j < lim; ++j) {
+                    const int i = x0 + j;
+                    const double xi = T[lane][j];
+                    double acc = xi * c.N0 + xm1 * c.N1 + xm2 * c.N2 + xm3 * c.N3;
+                    const double t1 = i >= 1 ? sm1 * c.D1 : v1 * c.BN1;
+                    const double t2 = i >= 2 ? sm2 * c.D2 : v1 * c.BN2;
+                    const double t3 = i >= 3 ? sm3 * c.D3 : v1 * c.BN3;
+                    const double t4 = i >= 4 ? sm4 * c.D4 : v1 * c.BN4;
+                    acc -= t1 + t2 + t3 + t4;
+                    T[lane][j] = acc;
+                    xm3 = xm2; xm2 = xm1; xm1 = xi;
+                    sm4 = sm3; sm3 = sm2; sm2 = sm1; sm1 = acc;
+                }
+            }
+            __syncwarp();
+            for (int i = 0; i < 32; ++i) {
+                const size_t l = line0 + i;
+                if (l < nlines && x < nx) out[l * nx + x] = T[i][lane];
+            }
+            __syncwarp();
+        }
+    }
+    // ---- anti-causal (right to left); out += anticausal
+    {
+        double v2 = 0.0, xp1 = 0.0, xp2 = 0.0, xp3 = 0.0, xp4 = 0.0, sp1 = 0, sp2 = 0, sp3 = 0, sp4 = 0;
+        for (int ch = nchunk - 1; ch >= 0; --ch) {
+            const int x0 = ch * 32, x = x0 + lane;
+            for (int i = 0; i < 32; ++i) {
+                const size_t l = line0 + i;
+                T[i][lane] = (l < nlines && x < nx) ? in[l * nx + x] : 0.0;
+            }
+            __syncwarp();
+            if (mine) {
+                const int lim = min(32, nx - x0);
+                if (ch == nchunk - 1) {
+                    v2 = T[lane][lim - 1];
+                    xp1 = xp2 = xp3 = xp4 = v2;
+                }
+                for (int j = lim - 1; j >= 0; --j) {
+                    const int i = x0 + j;
+                    const int m = nx - 1 - i;
+                    double acc = xp1 * c.M1 + xp2 * c.M2 + xp3 * c.M3 + xp4 * c.M4;
+                    const double t1 = m >= 1 ? sp1 * c.D1 : v2 * c.BM1;
+                    const double t2 = m >= 2 ? sp2 * c.D2 : v2 * c.BM2;
+                    const double t3 = m >= 3 ? sp3 * c.D3 : v2 * c.BM3;
+                    const double t4 = m >= 4 ? sp4 * c.D4 : v2 * c.BM4;
+                    acc -= t1 + t2 + t3 + t4;
+                    const double xi = T[lane][j];
+                    T[lane][j] = acc;
+                    xp4 = xp3; xp3 = xp2; xp2 = xp1; xp1 = xi;
+                    sp4 = sp3; sp3 = sp2; sp2 = sp1; sp1 = acc;
+                }
+            }
+            __syncwarp();
+            for (int i = 0; i < 32; ++i) {
+                const size_t l = line0 + i;
+                if (l < nlines && x < nx) out[l * nx + x] += T[i][lane];
+            }
+            __syncwarp();
+        }
+    }
+}
+
 // axis order z, x, y (SmoothingRecursiveGaussianImageFilter: first filter on the last dimension, then
 // dimensions 0 .. N-2); sigma is physical, ITK divides by the spacing of each axis.
 inline int recursive_gaussian_vec3(b200reg_ctx* ctx, double* field, const b200reg_geom& g, const double* sigma)
@@ -132,9 +227,15 @@ inline int recursive_gaussian_vec3(b200reg_ctx* ctx, double* field, const b200re
         // thread axes: a = the lowest remaining axis (x unless axis == 0), b = the other
         const int aa = axis == 0 ? 1 : 0;
         const int ab = axis == 2 ? 1 : 2;
-        dim3 blk(128, 1, 1), grd((dims[aa] + 127) / 128, dims[ab], 3);
-        deriche_line_kernel<<<grd, blk, 0, ctx->stream>>>(bufs[cur], bufs[cur ^ 1], dims[axis], strides[axis], dims[aa], strides[aa], dims[ab],
-                                                          strides[ab], n, c);
+        if (axis == 0) {
+            const size_t nlines = (size_t)ny * nz * 3;  // the three component volumes are contiguous: lines are rows of nx samples
+            const unsigned nblk = (unsigned)((nlines + 32 * DX_WARPS - 1) / (32 * DX_WARPS));
+            deriche_x_kernel<<<nblk, 32 * DX_WARPS, 0, ctx->stream>>>(bufs[cur], bufs[cur ^ 1], nx, ny, nlines, c);
+        } else {
+            dim3 blk(128, 1, 1), grd((dims[aa] + 127) / 128, dims[ab], 3);
+            deriche_line_kernel<<<grd, blk, 0, ctx->stream>>>(bufs[cur], bufs[cur ^ 1], dims[axis], strides[axis], dims[aa], strides[aa], dims[ab],
+                                                              strides[ab], n, c);
+        }
         ctx->launches++;
         B200_CHECK_LAUNCH();
         cur ^= 1;

@@ -500,6 +500,84 @@ inline int launch_conv3d_zmarch(b200reg_ctx* ctx, const double* a, const double*
     return B200REG_OK;
 }
 
+// ---- shared-memory tiled separable pass for Float32 images (DiscreteGaussianImageFilter, any radius <= KMAX_R) ---
+// Inputs are converted to double once when staged (the per-tap f32->f64 conversion of the naive kernel saturates
+// the 16-lane XU pipe); taps are accumulated in double in ascending order, result rounded to float32.
+// AXIS 0: one block = 256 consecutive outputs of one row.
+__global__ void __launch_bounds__(256) conv_x_f32_tiled_kernel(const float* __restrict__ in, float* __restrict__ out, int nx, int ny, int nz,
+                                                                const __grid_constant__ KernelCoeffs kc)
+{
+    __shared__ double sm[256 + 2 * KMAX_R];
+    const int r = kc.r;
+    const int x0 = blockIdx.x * 256, y = blockIdx.y, z = blockIdx.z;
+    const size_t row = ((size_t)z * ny + y) * nx;
+    for (int e = threadIdx.x; e < 256 + 2 * r; e += 256) {
+        int gx = x0 - r + e;
+        gx = gx < 0 ? 0 : (gx > nx - 1 ? nx - 1 : gx);
+        sm[e] = (double)in[row + gx];
+    }
+    __syncthreads();
+    const int x = x0 + threadIdx.x;
+    if (x >= nx) return;
+    double sum = 0.0;
+    const double* w = sm + threadIdx.x;
+    for (int t = 0; t <= 2 * r; ++t) sum += kc.k[t] * w[t];
+    out[row + x] = (float)sum;
+}
+// AXIS 1 / 2: tile of 32 x-columns by 32 positions along the axis; each thread owns 4 consecutive positions and
+// slides over 4 + 2r staged values, feeding the four accumulators in ascending tap order.
+template <int AXIS>
+__global__ void __launch_bounds__(256) conv_yz_f32_tiled_kernel(const float* __restrict__ in, float* __restrict__ out, int nx, int ny, int nz,
+                                                                 const __grid_constant__ KernelCoeffs kc)
+{
+    __shared__ double sm[(32 + 2 * KMAX_R) * 32];
+    const int r = kc.r;
+    const int n = AXIS == 1 ? ny : nz;
+    const size_t sa = AXIS == 1 ? (size_t)nx : (size_t)nx * ny;
+    const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int x = blockIdx.x * 32 + lane;
+    const int a0 = blockIdx.y * 32;             // first output position along the axis
+    const int other = blockIdx.z;               // z for AXIS 1, y for AXIS 2
+    const size_t base = AXIS == 1 ? (size_t)other * nx * ny : (size_t)other * nx;
+    const int xc = x < nx ? x : nx - 1;
+    for (int e = ty; e < 32 + 2 * r; e += 8) {
+        int q = a0 - r + e;
+        q = q < 0 ? 0 : (q > n - 1 ? n - 1 : q);
+        sm[e * 32 + lane] = (double)in[base + (size_t)q * sa + xc];
+    }
+    __syncthreads();
+    double acc[4] = { 0.0, 0.0, 0.0, 0.0 };
+    const double* col = sm + (ty * 4) * 32 + lane;
+    for (int i = 0; i < 4 + 2 * r; ++i) {
+        const double v = col[i * 32];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int t = i - j;
+            if (t >= 0 && t <= 2 * r) acc[j] += kc.k[t] * v;
+        }
+    }
+    if (x < nx) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int q = a0 + ty * 4 + j;
+            if (q < n) out[base + (size_t)q * sa + x] = (float)acc[j];
+        }
+    }
+}
+inline int launch_conv_axis_f32_tiled(b200reg_ctx* ctx, int axis, const float* in, float* out, int nx, int ny, int nz, const KernelCoeffs& kc)
+{
+    if (axis == 0) {
+        conv_x_f32_tiled_kernel<<<dim3((nx + 255) / 256, ny, nz), 256, 0, ctx->stream>>>(in, out, nx, ny, nz, kc);
+    } else if (axis == 1) {
+        conv_yz_f32_tiled_kernel<1><<<dim3((nx + 31) / 32, (ny + 31) / 32, nz), 256, 0, ctx->stream>>>(in, out, nx, ny, nz, kc);
+    } else {
+        conv_yz_f32_tiled_kernel<2><<<dim3((nx + 31) / 32, (nz + 31) / 32, ny), 256, 0, ctx->stream>>>(in, out, nx, ny, nz, kc);
+    }
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+
 // DiscreteGaussianImageFilter on a Float32 image: variance (mm^2) -> voxel^2 per axis when
 // use_image_spacing, passes z -> y -> x, float32 intermediates.
 inline int discrete_gaussian_f32(b200reg_ctx* ctx, const float* d_in, float* d_out, const b200reg_geom& g, const double* variance,
@@ -518,7 +596,8 @@ inline int discrete_gaussian_f32(b200reg_ctx* ctx, const float* d_in, float* d_o
         if (use_spacing) t = t / (g.spacing[axis] * g.spacing[axis]);
         KernelCoeffs kc;
         B200_TRY(make_coeffs(gaussian_operator(t, max_error, max_width), &kc));
-        B200_TRY((launch_conv_axis<float, false>(ctx, axis, src, nullptr, dsts[pass], nx, ny, nz, 1, kc, nullptr, 0)));
+        if (nz <= 65535 && ny <= 65535) B200_TRY(launch_conv_axis_f32_tiled(ctx, axis, src, dsts[pass], nx, ny, nz, kc));
+        else B200_TRY((launch_conv_axis<float, false>(ctx, axis, src, nullptr, dsts[pass], nx, ny, nz, 1, kc, nullptr, 0)));
         src = dsts[pass];
     }
     return B200REG_OK;

@@ -1,0 +1,55 @@
+"""Generates tests/golden/*.npz.  These fixtures are ORACLE-generated (oracle/itk_oracle.c): the reference cannot run
+here (SimpleITK is not installable offline) and its tests hold no golden vectors for this path, so parity stays
+"unpinned" (DESIGN.md section 5).  The fixtures pin the oracle against regressions and give the GPU tests a
+reference that does not depend on the oracle being rebuilt identically.
+
+    python tests/golden/make_golden.py
+"""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+from oracle import platipy_ref as ref  # noqa: E402
+from platipy_b200 import sitk_compat as sk  # noqa: E402
+from platipy_b200.sitk_compat import Image  # noqa: E402
+
+
+def phantom(shape, seed):
+    rng = np.random.default_rng(seed)
+    z, y, x = np.meshgrid(*[np.arange(s, dtype=np.float64) for s in shape], indexing="ij")
+    v = -1000.0 + 1000.0 / (1.0 + np.exp(-(1.0 - (((x - shape[2] / 2) / (0.4 * shape[2])) ** 2 + ((y - shape[1] / 2) / (0.4 * shape[1])) ** 2 +
+                                                   ((z - shape[0] / 2) / (0.4 * shape[0])) ** 2)) * 20.0))
+    for _ in range(6):
+        c = rng.uniform(0.3, 0.7, 3) * np.array(shape)
+        v += rng.uniform(-300, 600) * np.exp(-((z - c[0]) ** 2 + (y - c[1]) ** 2 + (x - c[2]) ** 2) / (2 * rng.uniform(2, 5) ** 2))
+    return v
+
+
+def main():
+    shape = (20, 28, 32)
+    spacing, origin = (0.9, 0.95, 2.5), (320.0, -52.0, 60.0)
+    fixed = phantom(shape, 1)
+    z, y, x = np.meshgrid(*[np.arange(s, dtype=np.float64) for s in shape], indexing="ij")
+    from scipy.ndimage import map_coordinates
+
+    moving = map_coordinates(fixed, [z + 0.8 * np.sin(x / 9.0), y + 1.2 * np.cos(z / 5.0), x + 1.5 * np.sin(y / 7.0)], order=1, mode="nearest")
+    rng = np.random.default_rng(2)
+    fixed = (fixed + rng.normal(0, 3, shape)).astype(np.float32)
+    moving = (moving + rng.normal(0, 3, shape)).astype(np.float32)
+    label = ((z - 10) ** 2 / 36 + (y - 14) ** 2 / 64 + (x - 15) ** 2 / 81 <= 1).astype(np.uint8)
+    F, M, L = Image(fixed, spacing, origin), Image(moving, spacing, origin), Image(label, spacing, origin)
+    kw = dict(resolution_staging=[2, 1], iteration_staging=[6, 4])
+    reg, tfm, dvf = ref.fast_symmetric_forces_demons_registration(F, M, **kw)
+    lab = ref.apply_transform(L, F, tfm, 0, sk.sitkNearestNeighbor)
+    np.savez_compressed(os.path.join(HERE, "demons_small.npz"), fixed=fixed, moving=moving, label=label, spacing=np.array(spacing),
+                        origin=np.array(origin), resolution_staging=np.array([2, 1]), iteration_staging=np.array([6, 4]),
+                        dvf=dvf.array, registered=reg.array, warped_label=lab.array)
+    print("wrote demons_small.npz", dvf.array.shape, float(np.abs(dvf.array).max()))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,72 @@
+"""BASELINE.json full sizes (512x512x256): what the oracle can check in seconds is checked against it (one
+full-resolution Demons iteration, label / image resampling); the rest through size-independent properties
+(identical images -> zero field after one iteration; zero displacement -> identity resampling; batched ==
+per-image resampling)."""
+import numpy as np
+import pytest
+
+from oracle import itk_oracle as orc
+from platipy_b200 import registration as reg
+from platipy_b200 import sitk_compat as sk
+from platipy_b200.sitk_compat import Image
+from platipy_b200.synth import smooth_random_dvf, synth_labels, synth_pair
+
+pytestmark = pytest.mark.gpu
+SIZE = (512, 512, 256)
+
+
+@pytest.fixture(scope="module")
+def pair():
+    return synth_pair(SIZE, seed=0, moving_seed=100)
+
+
+def _params(iters):
+    f = reg.FastSymmetricForcesDemonsRegistrationFilter()
+    f.SetStandardDeviations((1.5, 1.5, 1.5))
+    f.SetSmoothUpdateField(True)
+    return f.params(iters)
+
+
+def test_one_full_resolution_iteration_matches_oracle(engine, pair):
+    fixed, moving = pair
+    D, st = orc.demons_execute(fixed.array, orc.geom_of(fixed), moving.array, orc.geom_of(moving), orc.demons_params((1.5,) * 3, 2, smooth_update_field=True))
+    gD, gst = engine.demons_execute(engine.to_device(fixed), engine.to_device(moving), _params(2))
+    got = engine.to_host(gD, pinned=False).array
+    assert gst["elapsed_iterations"] == st["elapsed_iterations"] == 2
+    assert np.abs(got - D).max() <= 1e-4
+    assert np.array_equal(got, D)
+    assert abs(gst["metric"] - st["metric"]) <= 1e-9 * st["metric"]
+
+
+def test_identical_images_give_zero_field(engine, pair):
+    fixed, _ = pair
+    dF = engine.to_device(fixed)
+    img, tfm, dvf = reg.fast_symmetric_forces_demons_registration(dF, dF, resolution_staging=[4, 2, 1], iteration_staging=[100, 50, 25])
+    assert [s["elapsed_iterations"] for s in reg.LAST_LEVEL_STATS] == [1, 1, 1]
+    assert float(dvf.tensor.abs().max()) == 0.0
+    assert bool((img.tensor == dF.tensor).all())
+
+
+def test_config3_apply_transform_labels_and_image(engine, pair):
+    """BASELINE.json configs[2]: CT (linear, -1000) + 20 UInt8 masks (nearest neighbour, 0) through one dense DVF."""
+    fixed, moving = pair
+    labels = [Image(l) for l in synth_labels(SIZE, 20, seed=200)]
+    dvf = Image(smooth_random_dvf(SIZE, seed=9, peak_mm=6.0), is_vector=True)
+    tfm = sk.DisplacementFieldTransform(dvf)
+    d_imgs = [engine.to_device(moving)] + [engine.to_device(l) for l in labels]
+    outs = reg.apply_transform_batch(d_imgs, d_imgs[0], tfm, [-1000] + [0] * 20, [sk.sitkLinear] + [sk.sitkNearestNeighbor] * 20)
+    # per-call API gives the same bits as the batched one
+    one = reg.apply_transform(d_imgs[3], d_imgs[0], tfm, 0, sk.sitkNearestNeighbor)
+    assert bool((one.tensor == outs[3].tensor).all())
+    # oracle on the image and two of the masks (full size, seconds on the host cores)
+    g = orc.geom_of(fixed)
+    chain = [("dvf", dvf.array, g)]
+    exp_img = orc.resample_scalar(moving.array, g, g, chain, 2, -1000.0)
+    assert np.array_equal(engine.to_host(outs[0], pinned=False).array, exp_img)
+    for k in (1, 20):
+        exp = orc.resample_scalar(labels[k - 1].array, g, g, chain, 1, 0)
+        assert np.array_equal(engine.to_host(outs[k], pinned=False).array, exp)
+    # zero displacement -> identity for nearest-neighbour labels
+    zero = sk.DisplacementFieldTransform(Image(np.zeros(SIZE[::-1] + (3,)), is_vector=True))
+    ident = reg.apply_transform(d_imgs[5], d_imgs[0], zero, 0, sk.sitkNearestNeighbor)
+    assert bool((ident.tensor == d_imgs[5].tensor).all())
