@@ -232,12 +232,15 @@ __global__ void __launch_bounds__(1024) demons_finish_kernel(const double* __res
 // HBM, every F / D value is read once, index -> physical arithmetic that does not depend on z is hoisted out of
 // the loop, and the SSD / count / |U|^2 partial sums stay in registers until one block reduction at the end.
 // Arithmetic per voxel is the same sequence of IEEE operations as demons_warp_kernel + demons_force_kernel.
-constexpr int UP_TX = 64, UP_TY = 16, UP_NT = 256, UP_HW = UP_TX + 2, UP_HH = UP_TY + 2, UP_NP = UP_HW * UP_HH, UP_RING = 4;
+#ifndef UP_RING_DEPTH
+#define UP_RING_DEPTH 4
+#endif
+constexpr int UP_TX = 64, UP_TY = 16, UP_NT = 256, UP_HW = UP_TX + 2, UP_HH = UP_TY + 2, UP_NP = UP_HW * UP_HH, UP_RING = UP_RING_DEPTH;
 constexpr int UP_NHALO = UP_NP - UP_TX * UP_TY;  // 164
 constexpr size_t UP_SMEM = (size_t)2 * UP_RING * UP_NP * sizeof(double);
 
 template <bool DIAG>
-__global__ void __launch_bounds__(UP_NT, 2) demons_update_kernel(const float* __restrict__ F, const float* __restrict__ M, const double* __restrict__ D,
+__global__ void __launch_bounds__(UP_NT, UP_RING_DEPTH == 3 ? 3 : 2) demons_update_kernel(const float* __restrict__ F, const float* __restrict__ M, const double* __restrict__ D,
                                                                   double* __restrict__ U, double* __restrict__ partials,
                                                                   const __grid_constant__ GeomD gf, const __grid_constant__ GeomD gm,
                                                                   const __grid_constant__ ForceParams fp, int zchunk, int nchunks,
@@ -298,7 +301,7 @@ __global__ void __launch_bounds__(UP_NT, 2) demons_update_kernel(const float* __
     // loads of all positions are in flight together (field loads first, then the 8-point gathers).
     auto produce = [&](int z) {
         if (z < 0 || z >= nz) return;
-        const int slot = z & (UP_RING - 1);
+        const int slot = (z + UP_RING) % UP_RING;
         const size_t zo = (size_t)z * plane;
         double pz = 0.0;
         if (DIAG) pz = gf.i2p[8] * (double)z + gf.origin[2];
@@ -460,7 +463,7 @@ __global__ void __launch_bounds__(UP_NT, 2) demons_update_kernel(const float* __
     for (int z = z0; z < z1; ++z) {
         produce(z + 1);
         __syncthreads();
-        const int sc = (z & (UP_RING - 1)) * UP_NP, sm1 = ((z - 1) & (UP_RING - 1)) * UP_NP, sp1 = ((z + 1) & (UP_RING - 1)) * UP_NP;
+        const int sc = ((z + UP_RING) % UP_RING) * UP_NP, sm1 = ((z - 1 + UP_RING) % UP_RING) * UP_NP, sp1 = ((z + 1 + UP_RING) % UP_RING) * UP_NP;
         const size_t zo = (size_t)z * plane;
         const bool inner_z = z >= 1 && z <= nz - 2;
         // interior planes without any sentinel in the three ring planes take the branch-free path
@@ -509,6 +512,7 @@ __global__ void __launch_bounds__(UP_NT, 2) demons_update_kernel(const float* __
                 U[o + 2 * n] = u2;
             }
         }
+        if (UP_RING == 3) __syncthreads();  // 3-deep ring: plane z-1's slot is refilled by the next step
     }
     // one block reduction per CTA
     __shared__ double sh[3][UP_NT / 32];

@@ -164,6 +164,9 @@ inline int launch_conv_axis(b200reg_ctx* ctx, int axis, const T* a, const T* b, 
 // re-reads are L2 hits) and every output written once: 16 B/voxel/component instead of 48 for three
 // separable passes.  Operation order per output (x taps -r..r, then y, then z; each rounded to double)
 // is identical to three sequential passes, so results are bit-identical to them (and to the oracle).
+#ifndef ZM_MINB
+#define ZM_MINB 2
+#endif
 constexpr int ZM_TX = 64, ZM_TY = 16, ZM_NT = 256, ZM_RXY = 4, ZM_RMAX = 4;
 constexpr int ZM_PER = ZM_TY / (ZM_NT / ZM_TX);                                            // own voxels per thread
 constexpr int ZM_MAXLD = ((ZM_TX + 2 * ZM_RXY) * (ZM_TY + 2 * ZM_RXY) + ZM_NT - 1) / ZM_NT;  // staged loads per thread
@@ -289,7 +292,7 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
 template <int R, int RZ, bool ADD>
-__global__ void __launch_bounds__(ZM_NT, 2) conv3d_zm2_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out,
+__global__ void __launch_bounds__(ZM_NT, (RZ <= 2 && R <= 2) ? ZM_MINB : 2) conv3d_zm2_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out,
                                                                int nx, int ny, int nz, int zchunk, int nchunks,
                                                                const __grid_constant__ SmallCoeffs kc, const DemonsCtrl* __restrict__ ctrl, int it)
 {

@@ -147,12 +147,22 @@ class Engine:
     def synchronize(self):
         _abi.check(self.lib.b200reg_synchronize(self.ctx))
 
+    # The engine works on its own stream.  Device handles cross the public API in both directions, so the
+    # API wrappers order the engine stream after the caller's current stream on entry (wait_caller) and the
+    # caller's current stream after the engine stream on exit (release_to_caller): event waits, no host sync.
+    def wait_caller(self):
+        self.stream.wait_stream(torch.cuda.current_stream(self.device))
+
+    def release_to_caller(self):
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+
     def launch_count(self):
         return int(self.lib.b200reg_launch_count(self.ctx))
 
     def to_device(self, image):
         """Host ``Image`` -> ``DeviceImage`` (vector images are converted AoS -> SoA on the device)."""
         if isinstance(image, DeviceImage):
+            self.wait_caller()
             return image
         image = sk.to_native(image)
         host = _as_torch_host(image.array)

@@ -30,6 +30,7 @@ DEFAULT_VOTE_PARAMS = {
 
 def _back(eng, dimg, like):
     if isinstance(like, DeviceImage):
+        eng.release_to_caller()
         return dimg
     return sk.from_native(eng.to_host(dimg), like)
 

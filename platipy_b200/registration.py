@@ -46,6 +46,7 @@ def _is_device(image):
 def _back(eng, dimg, like):
     """Return ``dimg`` in the form of ``like``: device handle, stand-in Image or real SimpleITK image."""
     if _is_device(like):
+        eng.release_to_caller()
         return dimg
     return sk.from_native(eng.to_host(dimg), like)
 
@@ -360,6 +361,7 @@ def fast_symmetric_forces_demons_registration(fixed_image, moving_image, resolut
 
     if device_io:
         tfm._field = dvf
+        eng.release_to_caller()
         return reg_img, tfm, dvf
     dvf_host = eng.to_host(dvf)
     tfm._field = dvf_host

@@ -176,6 +176,12 @@ CASES = {
                                        kw=dict(resolution_staging=[2, 1], iteration_staging=[10, 5], regularisation_kernel_mm=[1.5, 1.5, 2.0])),
     "isotropic_resample": dict(size=(60, 50, 28), spacing=(0.9, 0.9, 2.5), origin=(320.0, -52.0, 60.0),
                                kw=dict(resolution_staging=[6, 3, 1.5], iteration_staging=[10, 8, 5], isotropic_resample=True, smoothing_sigmas=[0, 0, 0])),
+    # regularisation radius 8 voxels (> the fused kernel's limit): separable large-radius smoothing path
+    "fine_spacing_large_radius": dict(size=(56, 48, 40), spacing=(0.3, 0.3, 0.3), kw=dict(resolution_staging=[2, 1], iteration_staging=[6, 4])),
+    # different x / y radii (3 vs 2) and z radius 1: generic fused kernel path
+    "anisotropic_radii": dict(size=(56, 48, 24), spacing=(0.75, 1.0, 2.5), kw=dict(resolution_staging=[2, 1], iteration_staging=[6, 4])),
+    # very small volume (tiles mostly empty) and a non-smoothed field (update smoothing only is fixed on by the reference)
+    "tiny_volume": dict(size=(9, 7, 6), kw=dict(resolution_staging=[1], iteration_staging=[5], smoothing_sigmas=[0])),
     "nn_interp_int16": dict(size=(48, 40, 24), dtype=np.int16, kw=dict(resolution_staging=[2, 1], iteration_staging=[6, 4], interp_order=sk.sitkNearestNeighbor)),
 }
 
