@@ -66,6 +66,7 @@ API int b200reg_create(int device, void* stream, b200reg_ctx** out)
     B200_CUDA(cudaMallocHost(&ctx->h_scratch, 64 * sizeof(double)));
     if (const char* e = getenv("B200REG_FORCE_SEPARABLE")) ctx->force_separable = (e[0] == '1');
     if (const char* e = getenv("B200REG_UNFUSED_FORCE")) ctx->unfused_force = (e[0] == '1');
+    if (const char* e = getenv("B200REG_STAPLE_VOXELWISE")) ctx->staple_voxelwise = (e[0] == '1');
     if (const char* e = getenv("B200REG_FORCE_ZM1")) ctx->force_zm1 = (e[0] == '1');
     *out = ctx;
     return B200REG_OK;
@@ -580,6 +581,39 @@ API int b200reg_staple(b200reg_ctx* ctx, const uint8_t* const* d_decisions, int 
     for (int j = 0; j < n_raters; ++j) {
         REQUIRE(d_decisions[j] != nullptr, "null decision volume");
         ptrs.d[j] = d_decisions[j];
+    }
+    if (n_raters <= STAPLE_PATTERN_MAX && !ctx->staple_voxelwise) {
+        // pattern-histogram EM: two passes over the volume, the whole iteration loop inside one block
+        const int nbins = 1 << n_raters;
+        TempBuf pat, hist, tabw, tabo, state;
+        B200_TRY(pat.alloc(ctx, n * sizeof(uint32_t)));
+        B200_TRY(hist.alloc(ctx, (size_t)nbins * sizeof(unsigned long long)));
+        B200_TRY(tabw.alloc(ctx, (size_t)nbins * sizeof(double)));
+        B200_TRY(tabo.alloc(ctx, (size_t)nbins * sizeof(double)));
+        B200_TRY(state.alloc(ctx, sizeof(StapleState)));
+        B200_CUDA(cudaMemsetAsync(hist.p, 0, (size_t)nbins * sizeof(unsigned long long), ctx->stream));
+        const size_t shbytes = n_raters <= 12 ? (size_t)nbins * sizeof(unsigned int) : 0;
+        staple_pattern_kernel<<<ctx->sm_count * 8, 256, shbytes, ctx->stream>>>(ptrs, pat.as<uint32_t>(), n, hist.as<unsigned long long>());
+        staple_em_table_kernel<<<1, 1024, 0, ctx->stream>>>(hist.as<unsigned long long>(), n_raters, confidence_weight, max_iterations, threshold, rescale,
+                                                             tabw.as<double>(), tabo.as<double>(), state.as<StapleState>());
+        staple_write_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(pat.as<uint32_t>(), tabo.as<double>(), d_out, n);
+        ctx->launches += 3;
+        B200_CHECK_LAUNCH();
+        StapleState* h_state = nullptr;
+        B200_CUDA(cudaMallocHost(&h_state, sizeof(StapleState)));
+        cudaError_t e = cudaMemcpyAsync(h_state, state.p, sizeof(StapleState), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess) {
+            if (h_pq)
+                for (int j = 0; j < n_raters; ++j) {
+                    h_pq[j] = h_state->p[j];
+                    h_pq[n_raters + j] = h_state->q[j];
+                }
+            if (h_elapsed) *h_elapsed = h_state->elapsed;
+        }
+        cudaFreeHost(h_state);
+        B200_CUDA(e);
+        return B200REG_OK;
     }
     const int nb = ctx->sm_count * 4;
     const int stride = 2 * n_raters + 2;

@@ -58,6 +58,7 @@ struct b200reg_ctx {
     double* h_scratch = nullptr;  // 64 doubles
     bool force_separable = false;  // B200REG_FORCE_SEPARABLE=1: unfused smoothing passes (A/B testing)
     bool unfused_force = false;    // B200REG_UNFUSED_FORCE=1: separate warp and force kernels (W through HBM)
+    bool staple_voxelwise = false; // B200REG_STAPLE_VOXELWISE=1: per-voxel EM kernels instead of the pattern-histogram EM
     bool force_zm1 = false;        // B200REG_FORCE_ZM1=1: first-generation fused smoothing kernel
 };
 

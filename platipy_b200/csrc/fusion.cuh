@@ -418,4 +418,224 @@ __global__ void staple_converge_kernel(StapleState* st, int n_raters, unsigned i
     if (flag) st->converged = 1;
 }
 
+
+// ---- STAPLE by decision pattern ------------------------------------------------------------------------------
+// In binary STAPLE the posterior W_i depends on voxel i only through its decision pattern (D_i1 .. D_iN): after the
+// initialisation W = mean_j D_j (also a function of the pattern) every E-step gives W_i = f(pattern_i).  The EM over
+// 67 M voxels is therefore an EM over the 2^N-bin histogram of patterns: one pass over the volume to build the
+// histogram, the whole iteration loop on the table inside ONE thread block (no host round trips), one pass to write
+// W = table[pattern].  Same formulas and rater order as itk::STAPLEImageFilter; only the association of the sums
+// differs (histogram-weighted instead of voxel-serial), which the reference itself does not fix across thread
+// counts.  Used for N <= STAPLE_PATTERN_MAX raters.
+constexpr int STAPLE_PATTERN_MAX = 16;
+
+__global__ void __launch_bounds__(256) staple_pattern_kernel(const __grid_constant__ StaplePtrs ptrs, uint32_t* __restrict__ pattern, size_t n,
+                                                              unsigned long long* __restrict__ hist)
+{
+    // block-private histogram for up to 2^12 bins, direct (warp-aggregated) atomics above
+    extern __shared__ unsigned int shist[];
+    const int nbins = 1 << ptrs.n;
+    const bool priv = ptrs.n <= 12;
+    if (priv) {
+        for (int b = threadIdx.x; b < nbins; b += blockDim.x) shist[b] = 0;
+        __syncthreads();
+    }
+    unsigned long long zero_count = 0;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (size_t)gridDim.x * blockDim.x) {
+        uint32_t pat = 0;
+        for (int j = 0; j < ptrs.n; ++j) pat |= (ptrs.d[j][v] == 1 ? 1u : 0u) << j;
+        pattern[v] = pat;
+        if (priv) atomicAdd(&shist[pat], 1u);
+        else if (pat == 0) ++zero_count;
+        else atomicAdd(&hist[pat], 1ull);
+    }
+    if (priv) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < nbins; b += blockDim.x)
+            if (shist[b]) atomicAdd(&hist[b], (unsigned long long)shist[b]);
+    } else {
+        // the all-background pattern dominates: one atomic per warp
+        for (int o = 16; o > 0; o >>= 1) zero_count += __shfl_down_sync(0xffffffffu, zero_count, o);
+        if ((threadIdx.x & 31) == 0 && zero_count) atomicAdd(&hist[0], zero_count);
+    }
+}
+// same, from an already packed decision mask (the multi-GPU exchange format)
+__global__ void __launch_bounds__(256) staple_hist_packed_kernel(const int32_t* __restrict__ packed, uint32_t mask, size_t n,
+                                                                  unsigned long long* __restrict__ hist, uint32_t* __restrict__ pattern)
+{
+    unsigned long long zero_count = 0;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t pat = (uint32_t)packed[v] & mask;
+        pattern[v] = pat;
+        if (pat == 0) ++zero_count;
+        else atomicAdd(&hist[pat], 1ull);
+    }
+    for (int o = 16; o > 0; o >>= 1) zero_count += __shfl_down_sync(0xffffffffu, zero_count, o);
+    if ((threadIdx.x & 31) == 0 && zero_count) atomicAdd(&hist[0], zero_count);
+}
+
+__device__ __forceinline__ double block_sum_1024(double v, double* sh)
+{
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    v = warp_sum(v);
+    __syncthreads();
+    if (lane == 0) sh[wid] = v;
+    __syncthreads();
+    double r = 0.0;
+    if (wid == 0) {
+        r = warp_sum(sh[lane]);
+        if (lane == 0) sh[0] = r;
+    }
+    __syncthreads();
+    r = sh[0];
+    return r;
+}
+
+// One block runs the whole EM on the table.  table_w[b]: posterior of pattern b; out_tab[b]: value written to voxels
+// (optionally rescaled to [0,1] over the patterns that occur, and thresholded).
+__global__ void __launch_bounds__(1024) staple_em_table_kernel(const unsigned long long* __restrict__ hist, int n_raters, double confidence,
+                                                                unsigned max_iter, double threshold, int rescale, double* __restrict__ table_w,
+                                                                double* __restrict__ out_tab, StapleState* st)
+{
+    __shared__ double sh[32];
+    __shared__ double p[STAPLE_MAX_RATERS], q[STAPLE_MAX_RATERS], lp[STAPLE_MAX_RATERS], lq[STAPLE_MAX_RATERS];
+    __shared__ int flag;
+    const int nbins = 1 << n_raters;
+    const int tid = threadIdx.x;
+    // W = mean_j D_j ; g = mean(W) * confidence
+    double sw = 0.0, tot = 0.0;
+    for (int b = tid; b < nbins; b += 1024) {
+        const double h = (double)hist[b];
+        const double w = (double)__popc(b) / (double)n_raters;
+        table_w[b] = w;
+        sw += h * w;
+        tot += h;
+    }
+    sw = block_sum_1024(sw, sh);
+    tot = block_sum_1024(tot, sh);
+    const double g = (sw / tot) * confidence;
+    if (tid < n_raters) {
+        lp[tid] = -10.0;
+        lq[tid] = -10.0;
+    }
+    unsigned iter = 0;
+    for (; iter < max_iter; ++iter) {
+        // M step
+        double s_w = 0.0, s_1w = 0.0;
+        for (int b = tid; b < nbins; b += 1024) {
+            const double h = (double)hist[b], w = table_w[b];
+            s_w += h * w;
+            s_1w += h * (1.0 - w);
+        }
+        s_w = block_sum_1024(s_w, sh);
+        s_1w = block_sum_1024(s_1w, sh);
+        for (int j = 0; j < n_raters; ++j) {
+            double pn = 0.0, qn = 0.0;
+            for (int b = tid; b < nbins; b += 1024) {
+                const double h = (double)hist[b], w = table_w[b];
+                if ((b >> j) & 1) pn += h * w;
+                else qn += h * (1.0 - w);
+            }
+            pn = block_sum_1024(pn, sh);
+            qn = block_sum_1024(qn, sh);
+            if (tid == 0) {
+                p[j] = pn / s_w;
+                q[j] = qn / s_1w;
+            }
+        }
+        __syncthreads();
+        // E step
+        for (int b = tid; b < nbins; b += 1024) {
+            double alpha1 = 1.0, beta1 = 1.0;
+            for (int j = 0; j < n_raters; ++j) {
+                if ((b >> j) & 1) {
+                    alpha1 = alpha1 * p[j];
+                    beta1 = beta1 * (1.0 - q[j]);
+                } else {
+                    alpha1 = alpha1 * (1.0 - p[j]);
+                    beta1 = beta1 * q[j];
+                }
+            }
+            table_w[b] = g * alpha1 / (g * alpha1 + (1.0 - g) * beta1);
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int f = 0;
+            if (iter != 0) {
+                f = 1;
+                for (int j = 0; j < n_raters; ++j) {
+                    if (((p[j] - lp[j]) * (p[j] - lp[j])) > 1.0e-14) { f = 0; break; }
+                    if (((q[j] - lq[j]) * (q[j] - lq[j])) > 1.0e-14) { f = 0; break; }
+                }
+            }
+            for (int j = 0; j < n_raters; ++j) {
+                lp[j] = p[j];
+                lq[j] = q[j];
+            }
+            flag = f;
+        }
+        __syncthreads();
+        if (flag) break;
+    }
+    // RescaleIntensity(0,1) + Threshold over the values that actually occur in the volume
+    double mn = DBL_MAX, mx = -DBL_MAX;
+    for (int b = tid; b < nbins; b += 1024)
+        if (hist[b]) {
+            mn = fmin(mn, table_w[b]);
+            mx = fmax(mx, table_w[b]);
+        }
+    mn = warp_min(mn);
+    mx = warp_max(mx);
+    __syncthreads();
+    if ((tid & 31) == 0) {
+        sh[tid >> 5] = mn;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        double v = warp_min(sh[tid]);
+        if (tid == 0) sh[0] = v;
+    }
+    __syncthreads();
+    mn = sh[0];
+    __syncthreads();
+    if ((tid & 31) == 0) sh[tid >> 5] = mx;
+    __syncthreads();
+    if (tid < 32) {
+        double v = warp_max(sh[tid]);
+        if (tid == 0) sh[0] = v;
+    }
+    __syncthreads();
+    mx = sh[0];
+    double scale, shift;
+    if (fabs(mx - mn) > DBL_EPSILON) scale = 1.0 / (mx - mn);
+    else if (mx != 0.0) scale = 1.0 / mx;
+    else scale = 0.0;
+    shift = 0.0 - mn * scale;
+    for (int b = tid; b < nbins; b += 1024) {
+        double r = table_w[b];
+        if (rescale) {
+            r = r * scale + shift;
+            r = (r > 1.0) ? 1.0 : r;
+            r = (r < 0.0) ? 0.0 : r;
+        }
+        if (threshold != 0.0) {
+            if (!(r >= threshold && r <= 1.0)) r = 0.0;
+        }
+        out_tab[b] = r;
+    }
+    if (tid == 0) {
+        st->elapsed = (int)iter;
+        st->converged = 1;
+        st->g = g;
+        for (int j = 0; j < n_raters; ++j) {
+            st->p[j] = p[j];
+            st->q[j] = q[j];
+        }
+    }
+}
+__global__ void staple_write_kernel(const uint32_t* __restrict__ pattern, const double* __restrict__ out_tab, double* __restrict__ out, size_t n)
+{
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (size_t)gridDim.x * blockDim.x) out[v] = __ldg(out_tab + pattern[v]);
+}
+
 }  // namespace b200

@@ -206,7 +206,7 @@ struct BatchItem {
     int interp;
     double default_value;
 };
-constexpr int RESAMPLE_BATCH = 8;
+constexpr int RESAMPLE_BATCH = 24;
 struct BatchD {
     int n;
     BatchItem item[RESAMPLE_BATCH];
