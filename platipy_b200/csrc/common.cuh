@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <set>
 #include <string>
 #include <vector>
 
@@ -56,9 +57,11 @@ struct b200reg_ctx {
     int sm_count = 148;
     // pinned scratch for small read-backs
     double* h_scratch = nullptr;  // 64 doubles
+    std::set<const void*> smem_optin;  // kernels whose dynamic shared-memory limit was raised on this device
     bool force_separable = false;  // B200REG_FORCE_SEPARABLE=1: unfused smoothing passes (A/B testing)
     bool unfused_force = false;    // B200REG_UNFUSED_FORCE=1: separate warp and force kernels (W through HBM)
     bool staple_voxelwise = false; // B200REG_STAPLE_VOXELWISE=1: per-voxel EM kernels instead of the pattern-histogram EM
+    bool update_ws = false;        // B200REG_UPDATE_WS=1: warp-specialised (producer/consumer) fused update kernel
     bool force_zm1 = false;        // B200REG_FORCE_ZM1=1: first-generation fused smoothing kernel
 };
 
@@ -91,6 +94,17 @@ struct TempBuf {
         return reinterpret_cast<T*>(p);
     }
 };
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: opt in once per context and kernel.
+template <typename K>
+inline int ensure_dynamic_smem(b200reg_ctx* ctx, K kernel, size_t bytes)
+{
+    const void* key = reinterpret_cast<const void*>(kernel);
+    if (ctx->smem_optin.count(key)) return B200REG_OK;
+    B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+    ctx->smem_optin.insert(key);
+    return B200REG_OK;
+}
 
 // ---- geometry --------------------------------------------------------------------------------------
 struct GeomD {

@@ -541,6 +541,294 @@ __global__ void __launch_bounds__(UP_NT, UP_RING_DEPTH == 3 ? 3 : 2) demons_upda
     }
 }
 
+// ---- fused warp + force, warp-specialised (producer / consumer) ---------------------------------------------------
+// Same tile, rings and arithmetic as demons_update_kernel, but the two phases run on different warps of one 512-thread
+// CTA: 10 producer warps keep filling the W / F rings (field loads, 8-point gathers, XU conversions) up to three planes
+// ahead while 6 consumer warps compute the ESM update (FP64 chains, two IEEE divisions) of the planes already complete.
+// Hand-off through named barriers (bar.arrive / bar.sync), one "full" and one "empty" barrier per ring slot, so the
+// memory-latency phase and the FP64-latency phase overlap inside every SM instead of alternating.
+constexpr int WS_NT = 512, WS_PW = 10, WS_PT = WS_PW * 32, WS_CT = WS_NT - WS_PT;   // 320 producer / 192 consumer threads
+constexpr int WS_PPOS = (UP_NP + WS_PT - 1) / WS_PT;                                 // 4 positions per producer thread
+constexpr int WS_CVOX = (UP_TX * UP_TY + WS_CT - 1) / WS_CT;                         // 6 voxel slots per consumer thread
+constexpr int WS_RING = 4;
+constexpr size_t WS_SMEM = (size_t)2 * WS_RING * UP_NP * sizeof(double);
+
+__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
+
+template <bool DIAG>
+__global__ void __launch_bounds__(WS_NT, 1) demons_update_ws_kernel(const float* __restrict__ F, const float* __restrict__ M, const double* __restrict__ D,
+                                                                     double* __restrict__ U, double* __restrict__ partials,
+                                                                     const __grid_constant__ GeomD gf, const __grid_constant__ GeomD gm,
+                                                                     const __grid_constant__ ForceParams fp, int zchunk, int nchunks,
+                                                                     const DemonsCtrl* __restrict__ ctrl, int it)
+{
+    if (it >= ctrl->halt_iter) return;
+    extern __shared__ __align__(16) double up_smem[];
+    double* Wr = up_smem;
+    double* Fr = up_smem + WS_RING * UP_NP;
+    __shared__ int sent[WS_RING];
+    __shared__ double sh[3][WS_NT / 32];
+    const int tid = threadIdx.x;
+    if (tid < WS_RING) sent[tid] = -0x7fffffff;
+    __syncthreads();
+    const int nx = gf.nx, ny = gf.ny, nz = gf.nz;
+    const int x0 = blockIdx.x * UP_TX, y0 = blockIdx.y * UP_TY;
+    const int z0 = blockIdx.z * zchunk, z1 = min(nz, z0 + zchunk);
+    const int plane = nx * ny;
+    const size_t n = (size_t)plane * nz;
+    const double WMAX = (double)FLT_MAX;
+    // barrier ids: 1..4 full[slot], 5..8 empty[slot]   (0 is __syncthreads)
+    double ssd = 0.0, cnt = 0.0, ssc = 0.0;
+
+    if (tid < WS_PT) {
+        // ================================ producer warps ================================
+        int hxy[WS_PPOS], poff[WS_PPOS], soff[WS_PPOS];
+        double px[WS_PPOS], py[WS_PPOS];
+#pragma unroll
+        for (int q = 0; q < WS_PPOS; ++q) {
+            const int e = q * WS_PT + tid;
+            const int hy = e / UP_HW, hx = e - hy * UP_HW;
+            const int gx = x0 - 1 + hx, gy = y0 - 1 + hy;
+            const bool ok = e < UP_NP && gx >= 0 && gx < nx && gy >= 0 && gy < ny;
+            hxy[q] = e < UP_NP ? e : 0;
+            poff[q] = ok ? gy * nx + gx : -1;
+            soff[q] = ok ? gy * nx + gx : 0;
+            if (DIAG) {
+                px[q] = gf.i2p[0] * (double)gx + gf.origin[0];
+                py[q] = gf.i2p[4] * (double)gy + gf.origin[1];
+            }
+        }
+        for (int pz = z0 - 1; pz <= z1; ++pz) {
+            const int slot = (pz + WS_RING) & (WS_RING - 1);
+            if (pz - (z0 - 1) >= WS_RING) named_bar_sync(5 + slot, WS_NT);  // consumers are done with plane pz - 4
+            if (pz >= 0 && pz < nz) {
+                const size_t zo = (size_t)pz * plane;
+                double pzc = 0.0;
+                if (DIAG) pzc = gf.i2p[8] * (double)pz + gf.origin[2];
+                double dd[WS_PPOS][3];
+                float fv[WS_PPOS];
+#pragma unroll
+                for (int q = 0; q < WS_PPOS; ++q) {
+                    const size_t o = zo + soff[q];
+                    dd[q][0] = D[o];
+                    dd[q][1] = D[o + n];
+                    dd[q][2] = D[o + 2 * n];
+                    fv[q] = F[o];
+                }
+                LinW lw[WS_PPOS];
+                bool ins[WS_PPOS];
+#pragma unroll
+                for (int q = 0; q < WS_PPOS; ++q) {
+                    double p[3], c[3];
+                    if (DIAG) {
+                        p[0] = px[q];
+                        p[1] = py[q];
+                        p[2] = pzc;
+                    } else {
+                        const int gy = soff[q] / nx, gx = soff[q] - gy * nx;
+                        idx2pt(gf, (double)gx, (double)gy, (double)pz, p);
+                    }
+                    p[0] += dd[q][0];
+                    p[1] += dd[q][1];
+                    p[2] += dd[q][2];
+                    if (DIAG) {
+                        c[0] = gm.p2i[0] * (p[0] - gm.origin[0]);
+                        c[1] = gm.p2i[4] * (p[1] - gm.origin[1]);
+                        c[2] = gm.p2i[8] * (p[2] - gm.origin[2]);
+                    } else {
+                        pt2cidx(gm, p, c);
+                    }
+                    ins[q] = inside_buffer(gm, c);
+                    lw[q] = lin_setup(gm, c);
+                    lw[q].b0 = min(lw[q].b0, gm.nx - 1);
+                    lw[q].b1 = min(lw[q].b1, gm.ny - 1);
+                    lw[q].b2 = min(lw[q].b2, gm.nz - 1);
+                }
+                double wv[WS_PPOS];
+#pragma unroll
+                for (int q = 0; q < WS_PPOS; ++q) wv[q] = lin_eval<float>(M, gm, lw[q]);
+#pragma unroll
+                for (int q = 0; q < WS_PPOS; ++q) {
+                    if (poff[q] >= 0) {
+                        const int si = slot * UP_NP + hxy[q];
+                        Wr[si] = ins[q] ? (double)(float)wv[q] : WMAX;
+                        Fr[si] = (double)fv[q];
+                        if (!ins[q]) sent[slot] = pz;
+                    }
+                }
+            }
+            __threadfence_block();              // ring stores visible before the hand-off
+            named_bar_arrive(1 + slot, WS_NT);  // plane pz is complete
+        }
+    } else {
+        // ================================ consumer warps ================================
+        const int ct = tid - WS_PT;
+        const int ox = ct & (UP_TX - 1), yb = ct >> 6;  // column ox, rows yb, yb + 3, yb + 6, ...
+        const int gxo = x0 + ox;
+        // wait for the first three planes
+        named_bar_sync(1 + ((z0 - 1 + WS_RING) & (WS_RING - 1)), WS_NT);
+        named_bar_sync(1 + ((z0 + WS_RING) & (WS_RING - 1)), WS_NT);
+        for (int z = z0; z < z1; ++z) {
+            named_bar_sync(1 + ((z + 1 + WS_RING) & (WS_RING - 1)), WS_NT);
+            const int sc = ((z + WS_RING) & (WS_RING - 1)) * UP_NP, sm1 = ((z - 1 + WS_RING) & (WS_RING - 1)) * UP_NP,
+                      sp1 = ((z + 1 + WS_RING) & (WS_RING - 1)) * UP_NP;
+            const size_t zo = (size_t)z * plane;
+            const bool clean = z >= 1 && z <= nz - 2 && sent[sc / UP_NP] != z && sent[sm1 / UP_NP] != z - 1 && sent[sp1 / UP_NP] != z + 1;
+#pragma unroll 2
+            for (int r = 0; r < WS_CVOX; ++r) {
+                const int ly = yb + 3 * r;
+                if (ly >= UP_TY) break;
+                const int gy = y0 + ly;
+                if (gxo >= nx || gy >= ny) continue;
+                const int ci = (ly + 1) * UP_HW + ox + 1;
+                const size_t o = zo + (size_t)gy * nx + gxo;
+                double u0 = 0.0, u1 = 0.0, u2 = 0.0;
+                const bool inner = clean && gxo >= 1 && gxo <= nx - 2 && gy >= 1 && gy <= ny - 2;
+                if (inner) {
+                    const double fc = Fr[sc + ci], wcj = Wr[sc + ci];
+                    double g0 = (Fr[sc + ci + 1] - Fr[sc + ci - 1]) * fp.half_inv_sp[0] + (Wr[sc + ci + 1] - Wr[sc + ci - 1]) * fp.half_inv_sp[0];
+                    double g1 = (Fr[sc + ci + UP_HW] - Fr[sc + ci - UP_HW]) * fp.half_inv_sp[1] + (Wr[sc + ci + UP_HW] - Wr[sc + ci - UP_HW]) * fp.half_inv_sp[1];
+                    double g2 = (Fr[sp1 + ci] - Fr[sm1 + ci]) * fp.half_inv_sp[2] + (Wr[sp1 + ci] - Wr[sm1 + ci]) * fp.half_inv_sp[2];
+                    if (!DIAG) {
+                        const double a0 = g0, a1 = g1, a2 = g2;
+                        g0 = ((0.0 + gf.direction[0] * a0) + gf.direction[1] * a1) + gf.direction[2] * a2;
+                        g1 = ((0.0 + gf.direction[3] * a0) + gf.direction[4] * a1) + gf.direction[5] * a2;
+                        g2 = ((0.0 + gf.direction[6] * a0) + gf.direction[7] * a1) + gf.direction[8] * a2;
+                    }
+                    const double gm2 = g0 * g0 + g1 * g1 + g2 * g2;
+                    const double speed = fc - wcj;
+                    const double s2 = speed * speed;
+                    double denom = gm2;
+                    if (fp.normalizer > 0.0) denom = gm2 + (fp.inv_normalizer != 0.0 ? s2 * fp.inv_normalizer : s2 / fp.normalizer);
+                    const bool live = !(fabs(speed) < fp.intensity_thresh) && !(denom < fp.denom_thresh);
+                    const double factor = live ? 2.0 * speed / denom : 0.0;
+                    u0 = live ? factor * g0 : 0.0;
+                    u1 = live ? factor * g1 : 0.0;
+                    u2 = live ? factor * g2 : 0.0;
+                    ssd += s2;
+                    cnt += 1.0;
+                    ssc += u0 * u0 + u1 * u1 + u2 * u2;
+                } else {
+                    // generic path (borders, FLT_MAX sentinels): identical to demons_force_kernel
+                    const double movingValue = Wr[sc + ci];
+                    if (movingValue != WMAX) {
+                        const double fixedValue = Fr[sc + ci];
+                        const int idx[3] = { gxo, gy, z };
+                        const int dims[3] = { nx, ny, nz };
+                        const int nb_p[3] = { sc + ci + 1, sc + ci + UP_HW, sp1 + ci };
+                        const int nb_m[3] = { sc + ci - 1, sc + ci - UP_HW, sm1 + ci };
+                        double g2v[3];
+#pragma unroll
+                        for (int dim = 0; dim < 3; ++dim) {
+                            const int nd = dims[dim];
+                            double wg;
+                            if (idx[dim] == 0) {
+                                if (nd < 2) wg = 0.0;
+                                else {
+                                    const double nb = Wr[nb_p[dim]];
+                                    if (nb == WMAX) wg = 0.0;
+                                    else {
+                                        wg = nb - movingValue;
+                                        wg /= gf.spacing[dim];
+                                    }
+                                }
+                            } else if (idx[dim] == nd - 1) {
+                                const double nb = Wr[nb_m[dim]];
+                                if (nb == WMAX) wg = 0.0;
+                                else {
+                                    wg = movingValue - nb;
+                                    wg /= gf.spacing[dim];
+                                }
+                            } else {
+                                const double nb = Wr[nb_p[dim]];
+                                const double pb = Wr[nb_m[dim]];
+                                if (nb == WMAX) {
+                                    if (pb == WMAX) wg = 0.0;
+                                    else {
+                                        wg = movingValue - pb;
+                                        wg /= gf.spacing[dim];
+                                    }
+                                } else if (pb == WMAX) {
+                                    wg = nb - movingValue;
+                                    wg /= gf.spacing[dim];
+                                } else {
+                                    wg = nb - pb;
+                                    wg *= fp.half_inv_sp[dim];
+                                }
+                            }
+                            double fg;
+                            if (idx[dim] < 1 || idx[dim] > nd - 2) fg = 0.0;
+                            else {
+                                fg = Fr[nb_p[dim]] - Fr[nb_m[dim]];
+                                fg *= fp.half_inv_sp[dim];
+                            }
+                            g2v[dim] = fg + wg;
+                        }
+                        double J[3];
+                        if (DIAG) {
+                            J[0] = g2v[0];
+                            J[1] = g2v[1];
+                            J[2] = g2v[2];
+                        } else {
+#pragma unroll
+                            for (int rr = 0; rr < 3; ++rr) {
+                                double sum = 0.0;
+                                sum += gf.direction[rr * 3 + 0] * g2v[0];
+                                sum += gf.direction[rr * 3 + 1] * g2v[1];
+                                sum += gf.direction[rr * 3 + 2] * g2v[2];
+                                J[rr] = sum;
+                            }
+                        }
+                        const double gm2 = J[0] * J[0] + J[1] * J[1] + J[2] * J[2];
+                        const double speed = fixedValue - movingValue;
+                        if (!(fabs(speed) < fp.intensity_thresh)) {
+                            const double denom = (fp.normalizer > 0.0) ? gm2 + (speed * speed) / fp.normalizer : gm2;
+                            if (!(denom < fp.denom_thresh)) {
+                                const double factor = 2.0 * speed / denom;
+                                u0 = factor * J[0];
+                                u1 = factor * J[1];
+                                u2 = factor * J[2];
+                            }
+                        }
+                        ssd += speed * speed;
+                        cnt += 1.0;
+                        ssc += u0 * u0 + u1 * u1 + u2 * u2;
+                    }
+                }
+                U[o] = u0;
+                U[o + n] = u1;
+                U[o + 2 * n] = u2;
+            }
+            named_bar_arrive(5 + ((z - 1 + WS_RING) & (WS_RING - 1)), WS_NT);  // plane z-1 may be overwritten
+        }
+    }
+    // one block reduction per CTA (producer threads contribute zeros)
+    const int lane = tid & 31, wid = tid >> 5;
+    ssd = warp_sum(ssd);
+    cnt = warp_sum(cnt);
+    ssc = warp_sum(ssc);
+    if (lane == 0) {
+        sh[0][wid] = ssd;
+        sh[1][wid] = cnt;
+        sh[2][wid] = ssc;
+    }
+    __syncthreads();
+    if (wid == 0) {
+        constexpr int NW = WS_NT / 32;
+        double a = lane < NW ? sh[0][lane] : 0.0, b = lane < NW ? sh[1][lane] : 0.0, c = lane < NW ? sh[2][lane] : 0.0;
+        a = warp_sum(a);
+        b = warp_sum(b);
+        c = warp_sum(c);
+        if (lane == 0) {
+            const size_t bid = ((size_t)blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+            partials[bid * 3 + 0] = a;
+            partials[bid * 3 + 1] = b;
+            partials[bid * 3 + 2] = c;
+        }
+    }
+}
+
 inline bool geom_is_diag(const GeomD& g)
 {
     const double* d = g.direction;
@@ -631,19 +919,26 @@ inline int demons_calculate_change(b200reg_ctx* ctx, const float* F, const GeomD
         int zchunk;
         const dim3 g = update_grid(ctx, gf, &zchunk);
         nblocks = (size_t)g.x * g.y * g.z;
-        static bool attr_set[2] = { false, false };
         const bool diag = geom_is_diag(gf) && geom_is_diag(gm);
-        if (!attr_set[diag]) {
-            if (diag) B200_CUDA(cudaFuncSetAttribute(demons_update_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UP_SMEM));
-            else B200_CUDA(cudaFuncSetAttribute(demons_update_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)UP_SMEM));
-            attr_set[diag] = true;
-        }
+        if (ctx->update_ws) {
+            if (diag) B200_TRY(ensure_dynamic_smem(ctx, demons_update_ws_kernel<true>, WS_SMEM));
+            else B200_TRY(ensure_dynamic_smem(ctx, demons_update_ws_kernel<false>, WS_SMEM));
+            if (diag)
+                demons_update_ws_kernel<true><<<g, WS_NT, WS_SMEM, ctx->stream>>>(F, M, D, ws->U.as<double>(), ws->partials.as<double>(), gf, gm, fp, zchunk,
+                                                                                  (int)g.z, ctrl, it);
+            else
+                demons_update_ws_kernel<false><<<g, WS_NT, WS_SMEM, ctx->stream>>>(F, M, D, ws->U.as<double>(), ws->partials.as<double>(), gf, gm, fp, zchunk,
+                                                                                   (int)g.z, ctrl, it);
+        } else {
+        if (diag) B200_TRY(ensure_dynamic_smem(ctx, demons_update_kernel<true>, UP_SMEM));
+        else B200_TRY(ensure_dynamic_smem(ctx, demons_update_kernel<false>, UP_SMEM));
         if (diag)
             demons_update_kernel<true><<<g, UP_NT, UP_SMEM, ctx->stream>>>(F, M, D, ws->U.as<double>(), ws->partials.as<double>(), gf, gm, fp, zchunk,
                                                                             (int)g.z, ctrl, it);
         else
             demons_update_kernel<false><<<g, UP_NT, UP_SMEM, ctx->stream>>>(F, M, D, ws->U.as<double>(), ws->partials.as<double>(), gf, gm, fp, zchunk,
                                                                              (int)g.z, ctrl, it);
+        }
         ctx->launches += 1;
     }
     demons_finish_kernel<<<1, 1024, 0, ctx->stream>>>(ws->partials.as<double>(), nblocks, ctrl, fp.max_rms_error, it, n_iters, ws->trace.as<double>());

@@ -291,8 +291,14 @@ __device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
+// Threads per CTA: one x-pass task (row, column group) per thread -> (TY + 2R) * 16 threads; the first 256 of them
+// also own the tile's voxels in the y and z passes.
+template <int R>
+struct Zm2Threads {
+    static constexpr int value = (ZM_TY + 2 * R) * (ZM_TX / 4);
+};
 template <int R, int RZ, bool ADD>
-__global__ void __launch_bounds__(ZM_NT, (RZ <= 2 && R <= 2) ? ZM_MINB : 2) conv3d_zm2_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out,
+__global__ void __launch_bounds__(Zm2Threads<R>::value, 2) conv3d_zm2_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out,
                                                                int nx, int ny, int nz, int zchunk, int nchunks,
                                                                const __grid_constant__ SmallCoeffs kc, const DemonsCtrl* __restrict__ ctrl, int it)
 {
@@ -300,7 +306,8 @@ __global__ void __launch_bounds__(ZM_NT, (RZ <= 2 && R <= 2) ? ZM_MINB : 2) conv
     constexpr int RP = (R + 1) & ~1;  // x halo padded to an even count: 16-byte aligned shared rows
     constexpr int AW = ZM_TX + 2 * RP, AH = ZM_TY + 2 * R, NA = AW * AH;
     constexpr int NR = 2 * RZ + 1;
-    constexpr int NLD = (NA + ZM_NT - 1) / ZM_NT;
+    constexpr int NT = Zm2Threads<R>::value;
+    constexpr int NLD = (NA + NT - 1) / NT;
     extern __shared__ __align__(16) double zm_smem[];
     double* Aa = zm_smem;                       // [2][NA]
     double* Ab = zm_smem + 2 * NA;              // [2][NA] (ADD only)
@@ -318,7 +325,7 @@ __global__ void __launch_bounds__(ZM_NT, (RZ <= 2 && R <= 2) ? ZM_MINB : 2) conv
     int goff[NLD];
 #pragma unroll
     for (int l = 0; l < NLD; ++l) {
-        const int e = tid + l * ZM_NT;
+        const int e = tid + l * NT;
         const int yy = e / AW, xx = e - yy * AW;
         int gx = x0 - RP + xx, gy = y0 - R + yy;
         gx = gx < 0 ? 0 : (gx > nx - 1 ? nx - 1 : gx);
@@ -331,8 +338,8 @@ __global__ void __launch_bounds__(ZM_NT, (RZ <= 2 && R <= 2) ? ZM_MINB : 2) conv
 #pragma unroll
         for (int l = 0; l < NLD; ++l)
             if (goff[l] >= 0) {
-                cp_async8(Aa + buf * NA + tid + l * ZM_NT, ap + zo + goff[l]);
-                if (ADD) cp_async8(Ab + buf * NA + tid + l * ZM_NT, bp + zo + goff[l]);
+                cp_async8(Aa + buf * NA + tid + l * NT, ap + zo + goff[l]);
+                if (ADD) cp_async8(Ab + buf * NA + tid + l * NT, bp + zo + goff[l]);
             }
         cp_async_commit();
     };
@@ -354,8 +361,8 @@ __global__ void __launch_bounds__(ZM_NT, (RZ <= 2 && R <= 2) ? ZM_MINB : 2) conv
                 if (q + 1 < nsteps) stage(zbeg + q + 1, buf ^ 1);
                 // ---- x pass: per task two output pairs {2cx, 2cx+1} and {32+2cx, 32+2cx+1} of one row (rows incl. the
                 // y halo).  Lanes read consecutive 16-byte words: conflict-free 128-bit shared loads and stores.
-                for (int task = tid; task < AH * (ZM_TX / 4); task += ZM_NT) {
-                    const int yy = task >> 4, cx = task & 15;
+                {
+                    const int yy = tid >> 4, cx = tid & 15;
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int xb = 2 * cx + h * (ZM_TX / 2);
@@ -385,7 +392,7 @@ __global__ void __launch_bounds__(ZM_NT, (RZ <= 2 && R <= 2) ? ZM_MINB : 2) conv
                 }
                 __syncthreads();
                 // ---- y pass: sliding window over 4 + 2R rows of this thread's column
-                {
+                if (tid < ZM_NT) {
                     double col[4 + 2 * R];
 #pragma unroll
                     for (int i = 0; i < 4 + 2 * R; ++i) col[i] = B[(4 * yb + i) * ZM_TX + ox];
@@ -398,7 +405,7 @@ __global__ void __launch_bounds__(ZM_NT, (RZ <= 2 && R <= 2) ? ZM_MINB : 2) conv
                     }
                 }
                 // ---- z pass over the ring (slot s is the newest plane; oldest is slot (s + 1) % NR)
-                if (q >= 2 * RZ) {
+                if (tid < ZM_NT && q >= 2 * RZ) {
                     const int zo = zbeg + q - RZ;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -423,20 +430,12 @@ inline int launch_zm2_rz(b200reg_ctx* ctx, const double* a, const double* b, dou
     constexpr int NB = (ZM_TY + 2 * R) * ZM_TX;
     if (b) {
         constexpr size_t smem = (size_t)(4 * NA + NB) * sizeof(double);
-        static bool attr_set = false;
-        if (!attr_set) {
-            B200_CUDA(cudaFuncSetAttribute(conv3d_zm2_kernel<R, RZ, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = true;
-        }
-        conv3d_zm2_kernel<R, RZ, true><<<g, ZM_NT, smem, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it);
+        B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, true>, smem));
+        conv3d_zm2_kernel<R, RZ, true><<<g, Zm2Threads<R>::value, smem, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it);
     } else {
         constexpr size_t smem = (size_t)(2 * NA + NB) * sizeof(double);
-        static bool attr_set = false;
-        if (!attr_set) {
-            B200_CUDA(cudaFuncSetAttribute(conv3d_zm2_kernel<R, RZ, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_set = true;
-        }
-        conv3d_zm2_kernel<R, RZ, false><<<g, ZM_NT, smem, ctx->stream>>>(a, nullptr, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it);
+        B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, false>, smem));
+        conv3d_zm2_kernel<R, RZ, false><<<g, Zm2Threads<R>::value, smem, ctx->stream>>>(a, nullptr, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it);
     }
     return B200REG_OK;
 }
