@@ -162,6 +162,10 @@ int b200reg_resample_vec3(b200reg_ctx* ctx, const double* d_in_soa, const b200re
 int b200reg_compose_dvf(b200reg_ctx* ctx, double* d_total_soa, const double* d_iter_soa, const b200reg_geom* geom,
                         double* d_scratch_soa);
 
+/* ---- N11: sitk.TransformToDisplacementField (deformable.py:101-108): D(x) = T(x) - x on the given grid -------- */
+int b200reg_transform_to_dvf(b200reg_ctx* ctx, const b200reg_geom* out_geom, const b200reg_transform* chain, int n_chain,
+                             double* d_out_soa);
+
 /* ---- N6: sitk.FastSymmetricForcesDemonsRegistrationFilter.Execute (deformable.py:149) ---------------- */
 /* Starts from a zero field on the fixed grid; d_out_soa receives the field.  h_stats is filled after an
  * internal stream synchronisation. */
@@ -181,7 +185,8 @@ int b200reg_pde_smooth_field(b200reg_ctx* ctx, double* d_field_soa, const b200re
 int b200reg_recursive_gaussian_vec3(b200reg_ctx* ctx, double* d_field_soa, const b200reg_geom* geom, const double sigma[3]);
 
 /* ---- a2: multiscale_demons (deformable.py:31-187), device resident ------------------------------------ */
-/* d_initial_soa may be NULL (zero field).  d_out_soa: field on the fixed grid.  h_level_stats[n_levels]
+/* d_initial_soa may be NULL (zero field); with initial_geom == NULL it is a field already on the fixed grid (sampled from
+ * initial_transform, deformable.py:101-108).  d_out_soa: field on the fixed grid.  h_level_stats[n_levels]
  * filled after an internal synchronisation. */
 int b200reg_multiscale_demons(b200reg_ctx* ctx, const float* d_fixed, const b200reg_geom* fixed_geom, const float* d_moving,
                               const b200reg_geom* moving_geom, const b200reg_multires_config* cfg,

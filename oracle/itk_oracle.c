@@ -398,6 +398,28 @@ ORC_API int orc_resample_vec3(const double* in, const orc_geom* gin, double* out
     return 0;
 }
 
+/* TransformToDisplacementFieldFilter (reference deformable.py:101-108): D(x) = T(x) - x on the reference grid,
+ * non-linear path (per-voxel TransformPoint); SimpleITK instantiates it for VectorFloat64. */
+ORC_API int orc_transform_to_dvf(const orc_geom* gout, const orc_transform* tf, int ntf, double* out)
+{
+    geomx go;
+    geomx_init(&go, gout);
+    tfmx* t = chain_prepare(tf, ntf);
+#pragma omp parallel for schedule(static)
+    for (int k = 0; k < go.nz; ++k)
+        for (int j = 0; j < go.ny; ++j)
+            for (int i = 0; i < go.nx; ++i) {
+                double p[3], q[3];
+                idx2pt(&go, (double)i, (double)j, (double)k, p);
+                q[0] = p[0]; q[1] = p[1]; q[2] = p[2];
+                apply_chain(t, ntf, q);
+                size_t o = (((size_t)k * go.ny + j) * go.nx + i) * 3;
+                out[o] = q[0] - p[0]; out[o + 1] = q[1] - p[1]; out[o + 2] = q[2] - p[2];
+            }
+    free(t);
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------------------ */
 /* GaussianOperator (itkGaussianOperator.hxx): discrete Gaussian e^{-t} I_n(t), Numerical-Recipes     */
 /* polynomial Bessel functions                                                                       */

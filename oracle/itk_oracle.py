@@ -66,6 +66,7 @@ def lib():
         _lib.orc_demons_force.argtypes = [C.c_void_p] * 10
         _lib.orc_pde_smooth_field.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int]
         _lib.orc_recursive_gaussian_vec3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.orc_transform_to_dvf.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib.orc_set_num_threads.argtypes = [C.c_int]
     return _lib
 
@@ -154,6 +155,14 @@ def resample_vec3(arr, gin, gout, transforms=(), default_value=0.0):
     out = np.empty((gout.size[2], gout.size[1], gout.size[0], 3), dtype=np.float64)
     ch, n, keep = _chain(list(transforms))
     rc = lib().orc_resample_vec3(_ptr(arr), C.byref(gin), _ptr(out), C.byref(gout), ch, n, float(default_value))
+    assert rc == 0
+    return out
+
+
+def transform_to_dvf(gout, transforms):
+    out = np.empty((gout.size[2], gout.size[1], gout.size[0], 3), dtype=np.float64)
+    ch, n, keep = _chain(list(transforms))
+    rc = lib().orc_transform_to_dvf(C.byref(gout), ch, n, _ptr(out))
     assert rc == 0
     return out
 

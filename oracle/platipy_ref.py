@@ -161,9 +161,12 @@ def multiscale_demons(registration_algorithm, fixed_image, moving_image, initial
     # deformable.py:99-125
     if not initial_displacement_field:
         if initial_transform:
-            raise NotImplementedError("oracle: TransformToDisplacementField (no in-repo caller passes initial_transform)")
-        zeros = np.zeros(fixed_image.array.shape + (3,), dtype=np.float64)
-        initial_displacement_field = _like(zeros, fixed_image, True)
+            # deformable.py:101-108 sitk.TransformToDisplacementField on the fixed grid
+            arr = orc.transform_to_dvf(orc.geom_of(fixed_image), _chain_of(initial_transform))
+            initial_displacement_field = _like(arr, fixed_image, True)
+        else:
+            zeros = np.zeros(fixed_image.array.shape + (3,), dtype=np.float64)
+            initial_displacement_field = _like(zeros, fixed_image, True)
     else:
         initial_displacement_field = resample(initial_displacement_field, fixed_image)
 

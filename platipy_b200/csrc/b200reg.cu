@@ -231,6 +231,19 @@ API int b200reg_resample_vec3(b200reg_ctx* ctx, const double* d_in_soa, const b2
     return resample_vec3(ctx, d_in_soa, *in_geom, d_out_soa, *out_geom, chain, n_chain, default_value);
 }
 
+API int b200reg_transform_to_dvf(b200reg_ctx* ctx, const b200reg_geom* out_geom, const b200reg_transform* chain, int n_chain, double* d_out_soa)
+{
+    ENTER(ctx);
+    REQUIRE(d_out_soa && valid_geom(out_geom), "invalid argument");
+    ChainD ch;
+    B200_TRY(make_chain(chain, n_chain, &ch));
+    const GeomD go = make_geomd(*out_geom);
+    transform_to_dvf_kernel<<<grid3(go.nx, go.ny, go.nz), block3(), 0, ctx->stream>>>(d_out_soa, go, ch);
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+
 static b200reg_transform dvf_transform(const double* d_soa, const b200reg_geom& g)
 {
     b200reg_transform t;
@@ -448,12 +461,16 @@ API int b200reg_multiscale_demons(b200reg_ctx* ctx, const float* d_fixed, const 
     TempBuf total, next;
     b200reg_geom g_total = gF;
     B200_TRY(total.alloc(ctx, 3 * nF * sizeof(double)));
-    if (d_initial_soa) {
+    if (d_initial_soa && initial_geom) {
+        // a given field: deformable.py:125 re-grids it onto the fixed image, then :130 once more
         REQUIRE(valid_geom(initial_geom), "invalid initial field geometry");
         TempBuf tmp;
         B200_TRY(tmp.alloc(ctx, 3 * nF * sizeof(double)));
         B200_TRY(resample_vec3(ctx, d_initial_soa, *initial_geom, tmp.as<double>(), gF, nullptr, 0, 0.0));
         B200_TRY(resample_vec3(ctx, tmp.as<double>(), gF, total.as<double>(), gF, nullptr, 0, 0.0));
+    } else if (d_initial_soa) {
+        // a field sampled from initial_transform on the fixed grid (deformable.py:101-108): only the :130 re-grid
+        B200_TRY(resample_vec3(ctx, d_initial_soa, gF, total.as<double>(), gF, nullptr, 0, 0.0));
     } else {
         B200_CUDA(cudaMemsetAsync(total.p, 0, 3 * nF * sizeof(double), ctx->stream));
     }

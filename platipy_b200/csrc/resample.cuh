@@ -336,4 +336,23 @@ inline int resample_vec3(b200reg_ctx* ctx, const double* d_in, const b200reg_geo
     return B200REG_OK;
 }
 
+// TransformToDisplacementFieldFilter: D(x) = T(x) - x (per-voxel TransformPoint), SoA f64 output.
+__global__ void __launch_bounds__(BX* BY) transform_to_dvf_kernel(double* __restrict__ out, const __grid_constant__ GeomD go, const __grid_constant__ ChainD ch)
+{
+    const int i = blockIdx.x * BX + threadIdx.x;
+    const int j = blockIdx.y * BY + threadIdx.y;
+    const int k = blockIdx.z;
+    if (i >= go.nx || j >= go.ny) return;
+    double p[3], q[3];
+    idx2pt(go, (double)i, (double)j, (double)k, p);
+    q[0] = p[0];
+    q[1] = p[1];
+    q[2] = p[2];
+    apply_chain(ch, q);
+    const size_t o = ((size_t)k * go.ny + j) * go.nx + i, n = (size_t)go.nx * go.ny * go.nz;
+    out[o] = q[0] - p[0];
+    out[o + n] = q[1] - p[1];
+    out[o + 2 * n] = q[2] - p[2];
+}
+
 }  // namespace b200

@@ -289,6 +289,15 @@ class Engine:
                                                   float(default_value)))
         return DeviceImage(out, np.float64, out_geom_src.GetSpacing(), out_geom_src.GetOrigin(), out_geom_src.GetDirection(), True)
 
+    def transform_to_dvf(self, transform, grid):
+        """sitk.TransformToDisplacementField on the grid of ``grid`` (deformable.py:101-108)."""
+        x, y, z = grid.GetSize()
+        out = self.empty((3, z, y, x), np.float64)
+        g = _abi.geom_of(grid)
+        chain, nch, keep = self.chain(transform)
+        _abi.check(self.lib.b200reg_transform_to_dvf(self.ctx, C.byref(g), chain, nch, C.c_void_p(out.data_ptr())))
+        return DeviceImage(out, np.float64, grid.GetSpacing(), grid.GetOrigin(), grid.GetDirection(), True)
+
     def compose_dvf(self, total, iter_field):
         """total <- total + Resample(iter_field, DisplacementFieldTransform(total))  (deformable.py:154)."""
         scratch = self.empty(total.tensor.shape, np.float64)
@@ -334,12 +343,12 @@ class Engine:
                                                  C.c_void_p(w.data_ptr()), C.c_void_p(u.data_ptr()), C.byref(metric), C.byref(rms)))
         return fixed.like(w, np.float32, False), fixed.like(u, np.float64, True), metric.value, rms.value
 
-    def multiscale_demons(self, fixed, moving, cfg, initial_field=None):
+    def multiscale_demons(self, fixed, moving, cfg, initial_field=None, initial_on_fixed_grid=False):
         x, y, z = fixed.GetSize()
         out = self.empty((3, z, y, x), np.float64)
         stats = (_abi.DemonsStats * max(cfg.n_levels, 1))()
         gf, gm = fixed.geom, moving.geom
-        gi = initial_field.geom if initial_field is not None else None
+        gi = initial_field.geom if (initial_field is not None and not initial_on_fixed_grid) else None
         _abi.check(self.lib.b200reg_multiscale_demons(
             self.ctx, fixed.ptr, C.byref(gf), moving.ptr, C.byref(gm), C.byref(cfg),
             initial_field.ptr if initial_field is not None else None, C.byref(gi) if gi is not None else None,

@@ -292,14 +292,13 @@ def multiscale_demons(registration_algorithm, fixed_image, moving_image, initial
     f, m = eng.to_device(fixed_image), eng.to_device(moving_image)
     if f.np_dtype != np.float32 or m.np_dtype != np.float32:
         raise RuntimeError("multiscale_demons: fixed and moving images must be sitkFloat32")
-    init = None
+    init, init_on_fixed_grid = None, False
     if initial_displacement_field:
         init = eng.to_device(initial_displacement_field)
     elif initial_transform:
-        raise NotImplementedError("initial_transform (TransformToDisplacementField) is not implemented; pass "
-                                  "initial_displacement_field instead (no caller in the reference passes initial_transform)")
+        init, init_on_fixed_grid = eng.transform_to_dvf(initial_transform, f), True  # deformable.py:101-108
     cfg = _multires_config(registration_algorithm, resolution_staging, smoothing_sigmas, iteration_staging, isotropic_resample, interp_order)
-    dvf, level_stats = eng.multiscale_demons(f, m, cfg, init)
+    dvf, level_stats = eng.multiscale_demons(f, m, cfg, init, init_on_fixed_grid)
     registration_algorithm.level_stats = level_stats
     LAST_LEVEL_STATS[:] = level_stats
     if level_stats:

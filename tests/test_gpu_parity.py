@@ -232,6 +232,26 @@ def test_initial_displacement_field_and_device_io(engine):
     assert isinstance(out, DeviceImage)
 
 
+def test_multiscale_demons_with_initial_transform(engine):
+    """deformable.py:101-108: the initial field sampled from a transform (TransformToDisplacementField)."""
+    fixed, moving = synth_pair((40, 36, 24), seed=61, spacing=(1.0, 1.1, 1.5), peak_mm=3.0)
+    th = 0.03
+    aff = sk.AffineTransform([[np.cos(th), -np.sin(th), 0], [np.sin(th), np.cos(th), 0], [0, 0, 1]], (0.8, -0.5, 0.3), center=(20, 20, 18))
+    kw = dict(resolution_staging=[2, 1], smoothing_sigmas=[2, 1], iteration_staging=[5, 5], initial_transform=aff)
+    f_reg = reg.FastSymmetricForcesDemonsRegistrationFilter()
+    f_reg.SetSmoothUpdateField(True)
+    f_reg.SetStandardDeviations((1.5, 1.5 / 1.1, 1.0))
+    f_ref = ref.DemonsFilter()
+    f_ref.SetSmoothUpdateField(True)
+    f_ref.SetStandardDeviations((1.5, 1.5 / 1.1, 1.0))
+    got = reg.multiscale_demons(f_reg, fixed, moving, **kw)
+    exp = ref.multiscale_demons(f_ref, fixed, moving, **kw)
+    assert np.abs(got.array - exp.array).max() <= DVF_TOL_MM
+    # the sampled field itself
+    d = engine.to_host(engine.transform_to_dvf(aff, engine.to_device(fixed)), pinned=False).array
+    assert np.array_equal(d, orc.transform_to_dvf(orc.geom_of(fixed), [("affine", aff.matrix, aff.offset)]))
+
+
 def test_smooth_and_resample_parity_and_errors(engine):
     fixed, _ = synth_pair((50, 44, 30), seed=41, spacing=(0.9, 0.9, 2.5))
     for kw in [dict(shrink_factor=2, smoothing_sigma=2), dict(shrink_factor=[2, 2, 1], smoothing_sigma=[1.0, 1.0, 2.5]), dict(isotropic_voxel_size_mm=3, smoothing_sigma=0),
