@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(128) deriche_line_kernel(const double* __restr
 // coalesced along x while each lane still runs the sequential recurrence of its own line.  Same arithmetic as
 // deriche_line_kernel.
 constexpr int DX_WARPS = 4;
-__global__ void __launch_bounds__(32 * DX_WARPS) deriche_x_kernel(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, size_t nlines,
+__global__ void __launch_bounds__(32 * DX_WARPS, 6) deriche_x_kernel(const double* __restrict__ in, double* __restrict__ out, int nx, int ny, size_t nlines,
                                                                     const __grid_constant__ DericheC c)
 {
     __shared__ double tile[DX_WARPS][32][33];
@@ -132,6 +132,7 @@ __global__ void __launch_bounds__(32 * DX_WARPS) deriche_x_kernel(const double* 
         double v1 = 0.0, xm1 = 0.0, xm2 = 0.0, xm3 = 0.0, sm1 = 0, sm2 = 0, sm3 = 0, sm4 = 0;
         for (int ch = 0; ch < nchunk; ++ch) {
             const int x0 = ch * 32, x = x0 + lane;
+#pragma unroll 8
             for (int i = 0; i < 32; ++i) {
                 const size_t l = line0 + i;
                 T[i][lane] = (l < nlines && x < nx) ? in[l * nx + x] : 0.0;
@@ -143,6 +144,7 @@ __global__ void __launch_bounds__(32 * DX_WARPS) deriche_x_kernel(const double* 
                     xm1 = xm2 = xm3 = v1;
                 }
                 const int lim = min(32, nx - x0);
+#pragma unroll 4
                 for (int j = 0; j < lim; ++j) {
                     const int i = x0 + j;
                     const double xi = T[lane][j];
@@ -158,6 +160,7 @@ __global__ void __launch_bounds__(32 * DX_WARPS) deriche_x_kernel(const double* 
                 }
             }
             __syncwarp();
+#pragma unroll 8
             for (int i = 0; i < 32; ++i) {
                 const size_t l = line0 + i;
                 if (l < nlines && x < nx) out[l * nx + x] = T[i][lane];
@@ -170,6 +173,7 @@ __global__ void __launch_bounds__(32 * DX_WARPS) deriche_x_kernel(const double* 
         double v2 = 0.0, xp1 = 0.0, xp2 = 0.0, xp3 = 0.0, xp4 = 0.0, sp1 = 0, sp2 = 0, sp3 = 0, sp4 = 0;
         for (int ch = nchunk - 1; ch >= 0; --ch) {
             const int x0 = ch * 32, x = x0 + lane;
+#pragma unroll 8
             for (int i = 0; i < 32; ++i) {
                 const size_t l = line0 + i;
                 T[i][lane] = (l < nlines && x < nx) ? in[l * nx + x] : 0.0;
@@ -181,6 +185,7 @@ __global__ void __launch_bounds__(32 * DX_WARPS) deriche_x_kernel(const double* 
                     v2 = T[lane][lim - 1];
                     xp1 = xp2 = xp3 = xp4 = v2;
                 }
+#pragma unroll 4
                 for (int j = lim - 1; j >= 0; --j) {
                     const int i = x0 + j;
                     const int m = nx - 1 - i;
@@ -197,6 +202,7 @@ __global__ void __launch_bounds__(32 * DX_WARPS) deriche_x_kernel(const double* 
                 }
             }
             __syncwarp();
+#pragma unroll 8
             for (int i = 0; i < 32; ++i) {
                 const size_t l = line0 + i;
                 if (l < nlines && x < nx) out[l * nx + x] += T[i][lane];
