@@ -285,3 +285,47 @@ def test_reference_acceptance_sphere_phantom_dice_gpu(engine):
     assert np.array_equal(prop, ref.apply_transform(atlas_mask, target_ct, tfm_o, 0, sk.sitkNearestNeighbor).array)
     dice = 2.0 * (prop & target_mask.array).sum() / (prop.sum() + target_mask.array.sum())
     assert dice > 0.95
+
+
+def test_randomised_resample_chains(engine):
+    """40 random (geometry, transform chain, pixel type, interpolator) draws: bit-exact against the oracle."""
+    rng = np.random.default_rng(2024)
+    dtypes = [np.uint8, np.int16, np.uint16, np.int32, np.float32, np.float64]
+    for trial in range(40):
+        sz_in = tuple(int(v) for v in rng.integers(5, 24, 3))
+        sz_out = tuple(int(v) for v in rng.integers(4, 26, 3))
+        dt = dtypes[trial % len(dtypes)]
+        a = (rng.normal(size=sz_in[::-1]) * 200).astype(dt) if np.issubdtype(dt, np.floating) else rng.integers(0, 200, sz_in[::-1]).astype(dt)
+        src = Image(a, tuple(rng.uniform(0.5, 2.5, 3)), tuple(rng.uniform(-20, 20, 3)), rot_direction(*rng.uniform(-0.2, 0.2, 2)))
+        grid = Image(np.zeros(sz_out[::-1], np.uint8), tuple(rng.uniform(0.5, 2.5, 3)), tuple(np.array(src.GetOrigin()) + rng.uniform(-3, 3, 3)),
+                     rot_direction(*rng.uniform(-0.2, 0.2, 2)))
+        parts = []
+        for _ in range(int(rng.integers(0, 4))):
+            if rng.random() < 0.5:
+                m = np.eye(3) + rng.normal(scale=0.05, size=(3, 3))
+                parts.append(sk.AffineTransform(m, rng.uniform(-2, 2, 3), center=rng.uniform(0, 10, 3)))
+            else:
+                fs = tuple(int(v) for v in rng.integers(4, 12, 3))
+                f = Image(rng.normal(scale=1.5, size=fs[::-1] + (3,)), tuple(rng.uniform(1.0, 4.0, 3)), tuple(np.array(src.GetOrigin()) + rng.uniform(-5, 5, 3)),
+                          IDENT, True)
+                parts.append(sk.DisplacementFieldTransform(f))
+        tfm = sk.CompositeTransform(parts) if parts else None
+        interp = sk.sitkLinear if trial % 2 else sk.sitkNearestNeighbor
+        dv = float(rng.integers(0, 50))
+        got = reg.apply_transform(src, grid, tfm, dv, interp)
+        exp = ref.apply_transform(src, grid, tfm, dv, interp)
+        assert np.array_equal(got.array, exp.array), trial
+
+
+def test_randomised_small_registrations(engine):
+    """Random small volumes / spacings / stagings: DVF within 1e-4 mm (in fact identical) of the oracle."""
+    rng = np.random.default_rng(7)
+    for trial in range(6):
+        size = tuple(int(v) for v in rng.integers(14, 40, 3))
+        sp = tuple(float(v) for v in rng.uniform(0.6, 2.6, 3))
+        fixed, moving = synth_pair(size, seed=100 + trial, spacing=sp, origin=tuple(rng.uniform(-50, 50, 3)), peak_mm=2.0)
+        kw = dict(resolution_staging=[2, 1], iteration_staging=[int(rng.integers(1, 7)), int(rng.integers(1, 5))],
+                  regularisation_kernel_mm=float(rng.uniform(1.0, 2.5)), smoothing_sigma_factor=float(rng.uniform(0.5, 1.5)))
+        _, _, dvf = reg.fast_symmetric_forces_demons_registration(fixed, moving, **kw)
+        _, _, dvf_o = ref.fast_symmetric_forces_demons_registration(fixed, moving, **kw)
+        assert np.abs(dvf.array - dvf_o.array).max() <= DVF_TOL_MM, (trial, size, sp)

@@ -204,3 +204,18 @@ def test_reference_acceptance_sphere_phantom_dice():
     dice = 2.0 * (prop & target_mask.array).sum() / (prop.sum() + target_mask.array.sum())
     assert dice > dice0
     assert dice > 0.95, (dice0, dice)
+
+
+def test_oracle_is_deterministic_across_thread_counts():
+    """Per-slice partial sums merged in z order: metric / RMS and the field do not depend on the OpenMP team size."""
+    f, m = synth_pair((30, 26, 18), seed=9, peak_mm=2.0)
+    p = orc.demons_params((1.5, 1.5, 1.5), 6, smooth_update_field=True)
+    n0 = orc.num_threads()
+    try:
+        orc.set_num_threads(1)
+        D1, s1 = orc.demons_execute(f.array, orc.geom_of(f), m.array, orc.geom_of(m), p)
+        orc.set_num_threads(max(2, n0))
+        D2, s2 = orc.demons_execute(f.array, orc.geom_of(f), m.array, orc.geom_of(m), p)
+    finally:
+        orc.set_num_threads(n0)
+    assert np.array_equal(D1, D2) and s1 == s2
