@@ -114,6 +114,7 @@ struct GeomD {
     double p2i[9];  // inverse
     double spacing[3];
     double direction[9];
+    double hi[3];  // size - 0.5: upper bound of the continuous-index range inside the buffer
 };
 
 inline void inv3(const double* m, double* o)
@@ -154,6 +155,9 @@ inline GeomD make_geomd(const b200reg_geom& s)
         }
     }
     inv3(g.i2p, g.p2i);
+    g.hi[0] = g.nx - 0.5;
+    g.hi[1] = g.ny - 0.5;
+    g.hi[2] = g.nz - 0.5;
     return g;
 }
 inline size_t nvox(const b200reg_geom& g) { return (size_t)g.size[0] * g.size[1] * g.size[2]; }
@@ -193,7 +197,7 @@ __device__ __forceinline__ void pt2cidx(const GeomD& g, const double* p, double*
 // ImageFunction::IsInsideBuffer(ContinuousIndex): [-0.5, size - 0.5), NaN -> outside
 __device__ __forceinline__ bool inside_buffer(const GeomD& g, const double* c)
 {
-    return (c[0] >= -0.5 && c[0] < g.nx - 0.5 && c[1] >= -0.5 && c[1] < g.ny - 0.5 && c[2] >= -0.5 && c[2] < g.nz - 0.5);
+    return (c[0] >= -0.5 && c[0] < g.hi[0] && c[1] >= -0.5 && c[1] < g.hi[1] && c[2] >= -0.5 && c[2] < g.hi[2]);
 }
 
 // ---- pixel traits: load as double; store with CastPixelWithBoundsChecking ------------------------------

@@ -262,6 +262,12 @@ __global__ void __launch_bounds__(UP_NT, UP_RING_DEPTH == 3 ? 3 : 2) demons_upda
     const int plane = nx * ny;
     const size_t n = (size_t)plane * nz;
     const double WMAX = (double)FLT_MAX;
+    const double* __restrict__ D0 = D;
+    const double* __restrict__ D1 = D + n;
+    const double* __restrict__ D2 = D + 2 * n;
+    double* __restrict__ U0 = U;
+    double* __restrict__ U1 = U + n;
+    double* __restrict__ U2 = U + 2 * n;
 
     // positions this thread produces: 4 own voxels (column ox, rows 4*yb..4*yb+3) and at most one halo voxel
     const int ox = tid & (UP_TX - 1), yb = tid >> 6;
@@ -302,17 +308,17 @@ __global__ void __launch_bounds__(UP_NT, UP_RING_DEPTH == 3 ? 3 : 2) demons_upda
     auto produce = [&](int z) {
         if (z < 0 || z >= nz) return;
         const int slot = (z + UP_RING) % UP_RING;
-        const size_t zo = (size_t)z * plane;
+        const int zo = z * plane;  // volumes handled by this kernel have fewer than 2^31 voxels (checked on the host)
         double pz = 0.0;
         if (DIAG) pz = gf.i2p[8] * (double)z + gf.origin[2];
         double dd[5][3];
         float fv[5];
 #pragma unroll
         for (int q = 0; q < 5; ++q) {
-            const size_t o = zo + soff[q];
-            dd[q][0] = D[o];
-            dd[q][1] = D[o + n];
-            dd[q][2] = D[o + 2 * n];
+            const int o = zo + soff[q];
+            dd[q][0] = D0[o];
+            dd[q][1] = D1[o];
+            dd[q][2] = D2[o];
             fv[q] = F[o];
         }
         LinW lw[5];
@@ -341,13 +347,16 @@ __global__ void __launch_bounds__(UP_NT, UP_RING_DEPTH == 3 ? 3 : 2) demons_upda
             ins[q] = inside_buffer(gm, c);
             lw[q] = lin_setup(gm, c);
             // points outside the moving buffer are never interpolated; keep their (unused) gather in bounds
-            lw[q].b0 = min(lw[q].b0, gm.nx - 1);
-            lw[q].b1 = min(lw[q].b1, gm.ny - 1);
-            lw[q].b2 = min(lw[q].b2, gm.nz - 1);
+            lw[q].b0 = (int)min((unsigned)lw[q].b0, (unsigned)(gm.nx - 1));
+            lw[q].b1 = (int)min((unsigned)lw[q].b1, (unsigned)(gm.ny - 1));
+            lw[q].b2 = (int)min((unsigned)lw[q].b2, (unsigned)(gm.nz - 1));
+            lw[q].u0 = min(lw[q].b0 + 1, gm.nx - 1);
+            lw[q].u1 = min(lw[q].b1 + 1, gm.ny - 1);
+            lw[q].u2 = min(lw[q].b2 + 1, gm.nz - 1);
         }
         double wv[5];
 #pragma unroll
-        for (int q = 0; q < 5; ++q) wv[q] = lin_eval<float>(M, gm, lw[q]);
+        for (int q = 0; q < 5; ++q) wv[q] = lin_eval_i32<float>(M, gm.nx, gm.nx * gm.ny, lw[q]);
 #pragma unroll
         for (int q = 0; q < 5; ++q) {
             if (poff[q] >= 0) {
@@ -464,7 +473,7 @@ __global__ void __launch_bounds__(UP_NT, UP_RING_DEPTH == 3 ? 3 : 2) demons_upda
         produce(z + 1);
         __syncthreads();
         const int sc = ((z + UP_RING) % UP_RING) * UP_NP, sm1 = ((z - 1 + UP_RING) % UP_RING) * UP_NP, sp1 = ((z + 1 + UP_RING) % UP_RING) * UP_NP;
-        const size_t zo = (size_t)z * plane;
+        const int zo = z * plane;
         const bool inner_z = z >= 1 && z <= nz - 2;
         // interior planes without any sentinel in the three ring planes take the branch-free path
         const bool clean = inner_z && sent[sc / UP_NP] != z && sent[sm1 / UP_NP] != z - 1 && sent[sp1 / UP_NP] != z + 1;
@@ -495,10 +504,10 @@ __global__ void __launch_bounds__(UP_NT, UP_RING_DEPTH == 3 ? 3 : 2) demons_upda
                 ssd += s2;
                 cnt += 1.0;
                 ssc += u0 * u0 + u1 * u1 + u2 * u2;
-                const size_t o = zo + poff[j];
-                U[o] = u0;
-                U[o + n] = u1;
-                U[o + 2 * n] = u2;
+                const int o = zo + poff[j];
+                U0[o] = u0;
+                U1[o] = u1;
+                U2[o] = u2;
             }
         } else {
 #pragma unroll 1
@@ -506,10 +515,10 @@ __global__ void __launch_bounds__(UP_NT, UP_RING_DEPTH == 3 ? 3 : 2) demons_upda
                 if (poff[j] < 0) continue;
                 double u0 = 0.0, u1 = 0.0, u2 = 0.0;
                 slow_voxel(j, z, sc, sm1, sp1, u0, u1, u2);
-                const size_t o = zo + poff[j];
-                U[o] = u0;
-                U[o + n] = u1;
-                U[o + 2 * n] = u2;
+                const int o = zo + poff[j];
+                U0[o] = u0;
+                U1[o] = u1;
+                U2[o] = u2;
             }
         }
         if (UP_RING == 3) __syncthreads();  // 3-deep ring: plane z-1's slot is refilled by the next step
@@ -641,9 +650,12 @@ __global__ void __launch_bounds__(WS_NT, 1) demons_update_ws_kernel(const float*
                     }
                     ins[q] = inside_buffer(gm, c);
                     lw[q] = lin_setup(gm, c);
-                    lw[q].b0 = min(lw[q].b0, gm.nx - 1);
-                    lw[q].b1 = min(lw[q].b1, gm.ny - 1);
-                    lw[q].b2 = min(lw[q].b2, gm.nz - 1);
+                    lw[q].b0 = (int)min((unsigned)lw[q].b0, (unsigned)(gm.nx - 1));
+                    lw[q].b1 = (int)min((unsigned)lw[q].b1, (unsigned)(gm.ny - 1));
+                    lw[q].b2 = (int)min((unsigned)lw[q].b2, (unsigned)(gm.nz - 1));
+                    lw[q].u0 = min(lw[q].b0 + 1, gm.nx - 1);
+                    lw[q].u1 = min(lw[q].b1 + 1, gm.ny - 1);
+                    lw[q].u2 = min(lw[q].b2 + 1, gm.nz - 1);
                 }
                 double wv[WS_PPOS];
 #pragma unroll
@@ -909,7 +921,8 @@ inline int demons_calculate_change(b200reg_ctx* ctx, const float* F, const GeomD
     int zchunk_probe;
     const dim3 gprobe = update_grid(ctx, gf, &zchunk_probe);
     const bool small_grid = (size_t)gprobe.x * gprobe.y * gprobe.z < (size_t)ctx->sm_count * 4;
-    if (want_w || ctx->unfused_force || small_grid) {
+    const bool huge = (size_t)gf.nx * gf.ny * gf.nz >= (1ull << 31) || (size_t)gm.nx * gm.ny * gm.nz >= (1ull << 31);  // 32-bit offsets inside
+    if (want_w || ctx->unfused_force || small_grid || huge) {
         const dim3 g = grid3(gf.nx, gf.ny, gf.nz), b = block3();
         nblocks = (size_t)g.x * g.y * g.z;
         demons_warp_kernel<<<g, b, 0, ctx->stream>>>(M, D, ws->W.as<float>(), gf, gm, ctrl, it);

@@ -143,40 +143,31 @@ struct LinW {
     int b0, b1, b2, u0, u1, u2;
     double d0, d1, d2;
 };
-// floor() of a continuous index without the XU-pipe conversions (F2I + I2F run at 16 lanes/clk/SM on sm_100):
-// adding 1.5 * 2^52 leaves round-to-nearest-even(c) in the low mantissa word; one compare turns it into floor.
-// Exact for |c| < 2^31 (every point inside an image buffer); other inputs only ever reach clamped, unused gathers.
-__device__ __forceinline__ void floor_id(double c, int& bi, double& bd)
+// Base index and distance of LinearInterpolateImageFunction::EvaluateOptimized without XU-pipe conversions
+// (F2I / I2F run at 16 lanes/clk/SM on sm_100) and with three instructions per axis:
+//   * a continuous index in [-0.5, 0) gives base 0 / distance 0 in ITK (base clamped up to the start index, the
+//     negative distance treated as 0) -- exactly what clamping the index itself to 0 gives;
+//   * floor(c) for 0 <= c < 2^31 is the low mantissa word of c + 1.5 * 2^52 added with round-toward-minus-infinity
+//     (one DADD.RM), and the same sum minus the constant is floor(c) as a double (exact).
+// Indices beyond 2^31 or NaN never belong to a point inside a buffer; callers that gather unconditionally clamp the
+// resulting integers.
+__device__ __forceinline__ void base_and_distance(double c, int& b, double& d)
 {
     const double magic = 6755399441055744.0;
-    const double t = c + magic;
-    bi = __double2loint(t);
-    bd = t - magic;
-    if (bd > c) {
-        bi -= 1;
-        bd -= 1.0;
-    }
+    const double cc = c < 0.0 ? 0.0 : c;
+    const double t = __dadd_rd(cc, magic);
+    b = __double2loint(t);
+    d = cc - (t - magic);
 }
 __device__ __forceinline__ LinW lin_setup(const GeomD& g, const double* c)
 {
     LinW w;
-    double f0, f1, f2;
-    floor_id(c[0], w.b0, f0);
-    floor_id(c[1], w.b1, f1);
-    floor_id(c[2], w.b2, f2);
-    // base index clamped up to the first index: the distance is then taken from 0 (and is <= 0 -> treated as 0)
-    if (w.b0 < 0) { w.b0 = 0; f0 = 0.0; }
-    if (w.b1 < 0) { w.b1 = 0; f1 = 0.0; }
-    if (w.b2 < 0) { w.b2 = 0; f2 = 0.0; }
-    w.d0 = c[0] - f0;
-    w.d1 = c[1] - f1;
-    w.d2 = c[2] - f2;
-    if (w.d0 <= 0.) w.d0 = 0.;
-    if (w.d1 <= 0.) w.d1 = 0.;
-    if (w.d2 <= 0.) w.d2 = 0.;
-    w.u0 = w.b0 + 1 > g.nx - 1 ? g.nx - 1 : w.b0 + 1;
-    w.u1 = w.b1 + 1 > g.ny - 1 ? g.ny - 1 : w.b1 + 1;
-    w.u2 = w.b2 + 1 > g.nz - 1 ? g.nz - 1 : w.b2 + 1;
+    base_and_distance(c[0], w.b0, w.d0);
+    base_and_distance(c[1], w.b1, w.d1);
+    base_and_distance(c[2], w.b2, w.d2);
+    w.u0 = min(w.b0 + 1, g.nx - 1);
+    w.u1 = min(w.b1 + 1, g.ny - 1);
+    w.u2 = min(w.b2 + 1, g.nz - 1);
     return w;
 }
 template <typename T>
@@ -189,6 +180,28 @@ __device__ __forceinline__ double lin_eval(const T* __restrict__ img, const Geom
     const double v010 = (double)__ldg(img + r10 + w.b0), v110 = (double)__ldg(img + r10 + w.u0);
     const double v001 = (double)__ldg(img + r01 + w.b0), v101 = (double)__ldg(img + r01 + w.u0);
     const double v011 = (double)__ldg(img + r11 + w.b0), v111 = (double)__ldg(img + r11 + w.u0);
+    const double vx00 = v000 + (v100 - v000) * w.d0;
+    const double vx10 = v010 + (v110 - v010) * w.d0;
+    const double vxx0 = vx00 + (vx10 - vx00) * w.d1;
+    const double vx01 = v001 + (v101 - v001) * w.d0;
+    const double vx11 = v011 + (v111 - v011) * w.d0;
+    const double vxx1 = vx01 + (vx11 - vx01) * w.d1;
+    return vxx0 + (vxx1 - vxx0) * w.d2;
+}
+
+// Same interpolation with 32-bit element offsets (volumes below 2^31 voxels): one base offset, three neighbour
+// deltas, eight loads addressed as base pointer + 32-bit offset.  Identical values, far less integer arithmetic than
+// forming eight 64-bit indices.
+template <typename T>
+__device__ __forceinline__ double lin_eval_i32(const T* __restrict__ img, int nx, int nxy, const LinW& w)
+{
+    const int o000 = (w.b2 * nxy) + (w.b1 * nx) + w.b0;
+    const int dx = w.u0 - w.b0, dy = (w.u1 - w.b1) * nx, dz = (w.u2 - w.b2) * nxy;
+    const int o010 = o000 + dy, o001 = o000 + dz, o011 = o010 + dz;
+    const double v000 = (double)__ldg(img + o000), v100 = (double)__ldg(img + o000 + dx);
+    const double v010 = (double)__ldg(img + o010), v110 = (double)__ldg(img + o010 + dx);
+    const double v001 = (double)__ldg(img + o001), v101 = (double)__ldg(img + o001 + dx);
+    const double v011 = (double)__ldg(img + o011), v111 = (double)__ldg(img + o011 + dx);
     const double vx00 = v000 + (v100 - v000) * w.d0;
     const double vx10 = v010 + (v110 - v010) * w.d0;
     const double vxx0 = vx00 + (vx10 - vx00) * w.d1;
