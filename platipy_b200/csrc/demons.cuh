@@ -232,6 +232,9 @@ __global__ void __launch_bounds__(1024) demons_finish_kernel(const double* __res
 // HBM, every F / D value is read once, index -> physical arithmetic that does not depend on z is hoisted out of
 // the loop, and the SSD / count / |U|^2 partial sums stay in registers until one block reduction at the end.
 // Arithmetic per voxel is the same sequence of IEEE operations as demons_warp_kernel + demons_force_kernel.
+#ifndef UP_MINB
+#define UP_MINB 2
+#endif
 #ifndef UP_RING_DEPTH
 #define UP_RING_DEPTH 4
 #endif
@@ -240,7 +243,7 @@ constexpr int UP_NHALO = UP_NP - UP_TX * UP_TY;  // 164
 constexpr size_t UP_SMEM = (size_t)2 * UP_RING * UP_NP * sizeof(double);
 
 template <bool DIAG>
-__global__ void __launch_bounds__(UP_NT, UP_RING_DEPTH == 3 ? 3 : 2) demons_update_kernel(const float* __restrict__ F, const float* __restrict__ M, const double* __restrict__ D,
+__global__ void __launch_bounds__(UP_NT, UP_MINB) demons_update_kernel(const float* __restrict__ F, const float* __restrict__ M, const double* __restrict__ D,
                                                                   double* __restrict__ U, double* __restrict__ partials,
                                                                   const __grid_constant__ GeomD gf, const __grid_constant__ GeomD gm,
                                                                   const __grid_constant__ ForceParams fp, int zchunk, int nchunks,
