@@ -115,6 +115,7 @@ struct GeomD {
     double spacing[3];
     double direction[9];
     double hi[3];  // size - 0.5: upper bound of the continuous-index range inside the buffer
+    int small;     // fewer than 2^31 voxels: kernels may use 32-bit element offsets
 };
 
 inline void inv3(const double* m, double* o)
@@ -158,6 +159,7 @@ inline GeomD make_geomd(const b200reg_geom& s)
     g.hi[0] = g.nx - 0.5;
     g.hi[1] = g.ny - 0.5;
     g.hi[2] = g.nz - 0.5;
+    g.small = ((size_t)g.nx * g.ny * g.nz < (1ull << 31)) ? 1 : 0;
     return g;
 }
 inline size_t nvox(const b200reg_geom& g) { return (size_t)g.size[0] * g.size[1] * g.size[2]; }

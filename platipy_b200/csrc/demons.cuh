@@ -27,6 +27,7 @@ struct ForceParams {
 
 // WarpImageFilter with the field on the output (fixed) grid: point = index->physical + D; linear
 // interpolation of the moving image; edge padding NumericTraits<float>::max().
+template <bool SMALL>
 __global__ void __launch_bounds__(BX* BY) demons_warp_kernel(const float* __restrict__ M, const double* __restrict__ D, float* __restrict__ W,
                                                               const __grid_constant__ GeomD gf, const __grid_constant__ GeomD gm,
                                                               const DemonsCtrl* __restrict__ ctrl, int it)
@@ -47,7 +48,7 @@ __global__ void __launch_bounds__(BX* BY) demons_warp_kernel(const float* __rest
     float w = FLT_MAX;
     if (inside_buffer(gm, c)) {
         const LinW lw = lin_setup(gm, c);
-        w = (float)lin_eval<float>(M, gm, lw);
+        w = (float)(SMALL ? lin_eval_i32<float>(M, gm.nx, gm.nx * gm.ny, lw) : lin_eval<float>(M, gm, lw));
     }
     W[o] = w;
 }
@@ -928,7 +929,8 @@ inline int demons_calculate_change(b200reg_ctx* ctx, const float* F, const GeomD
     if (want_w || ctx->unfused_force || small_grid || huge) {
         const dim3 g = grid3(gf.nx, gf.ny, gf.nz), b = block3();
         nblocks = (size_t)g.x * g.y * g.z;
-        demons_warp_kernel<<<g, b, 0, ctx->stream>>>(M, D, ws->W.as<float>(), gf, gm, ctrl, it);
+        if (gm.small) demons_warp_kernel<true><<<g, b, 0, ctx->stream>>>(M, D, ws->W.as<float>(), gf, gm, ctrl, it);
+        else demons_warp_kernel<false><<<g, b, 0, ctx->stream>>>(M, D, ws->W.as<float>(), gf, gm, ctrl, it);
         demons_force_kernel<<<g, b, 0, ctx->stream>>>(F, ws->W.as<float>(), ws->U.as<double>(), ws->partials.as<double>(), gf, fp, ctrl, it);
         ctx->launches += 2;
     } else {

@@ -49,8 +49,12 @@ inline int make_chain(const b200reg_transform* chain, int n_chain, ChainD* out)
 // buffer, zero-overlap neighbours skipped, early exit when the accumulated overlap is exactly 1.
 __device__ __forceinline__ void interp_wsum_vec3(const double* __restrict__ f, const GeomD& g, const double* c, double* out)
 {
-    const int b[3] = { (int)floor(c[0]), (int)floor(c[1]), (int)floor(c[2]) };
-    const double d[3] = { c[0] - (double)b[0], c[1] - (double)b[1], c[2] - (double)b[2] };
+    // floor without XU conversions: c + 1.5 * 2^52 rounded toward -inf holds floor(c) in its low mantissa word
+    // (two's complement, so negative indices down to -2^31 work too); only called for points inside the buffer.
+    const double magic = 6755399441055744.0;
+    const double t0 = __dadd_rd(c[0], magic), t1 = __dadd_rd(c[1], magic), t2 = __dadd_rd(c[2], magic);
+    const int b[3] = { __double2loint(t0), __double2loint(t1), __double2loint(t2) };
+    const double d[3] = { c[0] - (t0 - magic), c[1] - (t1 - magic), c[2] - (t2 - magic) };
     const int n[3] = { g.nx, g.ny, g.nz };
     const size_t plane = (size_t)g.nx * g.ny * g.nz;
     out[0] = out[1] = out[2] = 0.0;
@@ -219,13 +223,13 @@ struct BatchItem {
     int interp;
     double default_value;
 };
-constexpr int RESAMPLE_BATCH = 24;
+constexpr int RESAMPLE_BATCH = 8;
 struct BatchD {
     int n;
     BatchItem item[RESAMPLE_BATCH];
 };
 
-template <typename T>
+template <typename T, bool SMALL>
 __device__ __forceinline__ void resample_one(const BatchItem& it, const GeomD& gi, const double* c, bool inside, size_t o)
 {
     const T* in = reinterpret_cast<const T*>(it.in);
@@ -238,7 +242,7 @@ __device__ __forceinline__ void resample_one(const BatchItem& it, const GeomD& g
             v = Px<T>::ld(in, ((size_t)i2 * gi.ny + i1) * gi.nx + i0);
         } else {
             const LinW w = lin_setup(gi, c);
-            v = lin_eval<T>(in, gi, w);
+            v = SMALL ? lin_eval_i32<T>(in, gi.nx, gi.nx * gi.ny, w) : lin_eval<T>(in, gi, w);
         }
         out[o] = Px<T>::cast(v);
     } else {
@@ -246,7 +250,8 @@ __device__ __forceinline__ void resample_one(const BatchItem& it, const GeomD& g
     }
 }
 
-__global__ void __launch_bounds__(BX* BY) resample_batch_kernel(const __grid_constant__ BatchD batch, const __grid_constant__ GeomD gi,
+template <bool SMALL>
+__global__ void __launch_bounds__(BX* BY, 4) resample_batch_kernel(const __grid_constant__ BatchD batch, const __grid_constant__ GeomD gi,
                                                                  const __grid_constant__ GeomD go, const __grid_constant__ ChainD ch)
 {
     const int i = blockIdx.x * BX + threadIdx.x;
@@ -260,16 +265,16 @@ __global__ void __launch_bounds__(BX* BY) resample_batch_kernel(const __grid_con
     for (int b = 0; b < batch.n; ++b) {
         const BatchItem& it = batch.item[b];
         switch (it.dtype) {
-        case B200REG_I8: resample_one<int8_t>(it, gi, c, inside, o); break;
-        case B200REG_U8: resample_one<uint8_t>(it, gi, c, inside, o); break;
-        case B200REG_I16: resample_one<int16_t>(it, gi, c, inside, o); break;
-        case B200REG_U16: resample_one<uint16_t>(it, gi, c, inside, o); break;
-        case B200REG_I32: resample_one<int32_t>(it, gi, c, inside, o); break;
-        case B200REG_U32: resample_one<uint32_t>(it, gi, c, inside, o); break;
-        case B200REG_I64: resample_one<int64_t>(it, gi, c, inside, o); break;
-        case B200REG_U64: resample_one<uint64_t>(it, gi, c, inside, o); break;
-        case B200REG_F32: resample_one<float>(it, gi, c, inside, o); break;
-        default: resample_one<double>(it, gi, c, inside, o); break;
+        case B200REG_I8: resample_one<int8_t, SMALL>(it, gi, c, inside, o); break;
+        case B200REG_U8: resample_one<uint8_t, SMALL>(it, gi, c, inside, o); break;
+        case B200REG_I16: resample_one<int16_t, SMALL>(it, gi, c, inside, o); break;
+        case B200REG_U16: resample_one<uint16_t, SMALL>(it, gi, c, inside, o); break;
+        case B200REG_I32: resample_one<int32_t, SMALL>(it, gi, c, inside, o); break;
+        case B200REG_U32: resample_one<uint32_t, SMALL>(it, gi, c, inside, o); break;
+        case B200REG_I64: resample_one<int64_t, SMALL>(it, gi, c, inside, o); break;
+        case B200REG_U64: resample_one<uint64_t, SMALL>(it, gi, c, inside, o); break;
+        case B200REG_F32: resample_one<float, SMALL>(it, gi, c, inside, o); break;
+        default: resample_one<double, SMALL>(it, gi, c, inside, o); break;
         }
     }
 }
@@ -291,7 +296,8 @@ inline int resample_batch(b200reg_ctx* ctx, int n, const void* const* d_in, cons
         BatchD b;
         b.n = (n - start) < RESAMPLE_BATCH ? (n - start) : RESAMPLE_BATCH;
         for (int q = 0; q < b.n; ++q) b.item[q] = BatchItem{ d_in[start + q], d_out[start + q], dtypes[start + q], interps[start + q], defaults[start + q] };
-        resample_batch_kernel<<<grid3(go.nx, go.ny, go.nz), block3(), 0, ctx->stream>>>(b, gi, go, ch);
+        if (gi.small) resample_batch_kernel<true><<<grid3(go.nx, go.ny, go.nz), block3(), 0, ctx->stream>>>(b, gi, go, ch);
+        else resample_batch_kernel<false><<<grid3(go.nx, go.ny, go.nz), block3(), 0, ctx->stream>>>(b, gi, go, ch);
         ctx->launches++;
         B200_CHECK_LAUNCH();
     }
@@ -301,8 +307,8 @@ inline int resample_batch(b200reg_ctx* ctx, int n, const void* const* d_in, cons
 // ---- vector (f64 x 3, SoA) --------------------------------------------------------------------------
 // LinearInterpolateImageFunction on a VectorImage: the same nested-lerp form, per component.
 // ACCUM: out = acc + value (dvf_total + Resample(dvf_iter, tfm_total), deformable.py:154).
-template <bool ACCUM>
-__global__ void __launch_bounds__(BX* BY) resample_vec3_kernel(const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ acc,
+template <bool ACCUM, bool SMALL>
+__global__ void __launch_bounds__(BX* BY, 4) resample_vec3_kernel(const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ acc,
                                                                 const __grid_constant__ GeomD gi, const __grid_constant__ GeomD go,
                                                                 const __grid_constant__ ChainD ch, double default_value)
 {
@@ -317,9 +323,15 @@ __global__ void __launch_bounds__(BX* BY) resample_vec3_kernel(const double* __r
     double v[3];
     if (inside_buffer(gi, c)) {
         const LinW w = lin_setup(gi, c);
-        v[0] = lin_eval<double>(in, gi, w);
-        v[1] = lin_eval<double>(in + pi, gi, w);
-        v[2] = lin_eval<double>(in + 2 * pi, gi, w);
+        if (SMALL) {
+            v[0] = lin_eval_i32<double>(in, gi.nx, gi.nx * gi.ny, w);
+            v[1] = lin_eval_i32<double>(in + pi, gi.nx, gi.nx * gi.ny, w);
+            v[2] = lin_eval_i32<double>(in + 2 * pi, gi.nx, gi.nx * gi.ny, w);
+        } else {
+            v[0] = lin_eval<double>(in, gi, w);
+            v[1] = lin_eval<double>(in + pi, gi, w);
+            v[2] = lin_eval<double>(in + 2 * pi, gi, w);
+        }
     } else {
         v[0] = v[1] = v[2] = default_value;
     }
@@ -340,10 +352,14 @@ inline int resample_vec3(b200reg_ctx* ctx, const double* d_in, const b200reg_geo
     ChainD ch;
     B200_TRY(make_chain(chain, n_chain, &ch));
     const GeomD gi = make_geomd(gin), go = make_geomd(gout);
-    if (d_acc)
-        resample_vec3_kernel<true><<<grid3(go.nx, go.ny, go.nz), block3(), 0, ctx->stream>>>(d_in, d_out, d_acc, gi, go, ch, default_value);
-    else
-        resample_vec3_kernel<false><<<grid3(go.nx, go.ny, go.nz), block3(), 0, ctx->stream>>>(d_in, d_out, nullptr, gi, go, ch, default_value);
+    const dim3 g = grid3(go.nx, go.ny, go.nz), b = block3();
+    if (d_acc) {
+        if (gi.small) resample_vec3_kernel<true, true><<<g, b, 0, ctx->stream>>>(d_in, d_out, d_acc, gi, go, ch, default_value);
+        else resample_vec3_kernel<true, false><<<g, b, 0, ctx->stream>>>(d_in, d_out, d_acc, gi, go, ch, default_value);
+    } else {
+        if (gi.small) resample_vec3_kernel<false, true><<<g, b, 0, ctx->stream>>>(d_in, d_out, nullptr, gi, go, ch, default_value);
+        else resample_vec3_kernel<false, false><<<g, b, 0, ctx->stream>>>(d_in, d_out, nullptr, gi, go, ch, default_value);
+    }
     ctx->launches++;
     B200_CHECK_LAUNCH();
     return B200REG_OK;
