@@ -68,6 +68,7 @@ API int b200reg_create(int device, void* stream, b200reg_ctx** out)
     if (const char* e = getenv("B200REG_UNFUSED_FORCE")) ctx->unfused_force = (e[0] == '1');
     if (const char* e = getenv("B200REG_STAPLE_VOXELWISE")) ctx->staple_voxelwise = (e[0] == '1');
     if (const char* e = getenv("B200REG_UPDATE_WS")) ctx->update_ws = (e[0] == '1');
+    if (const char* e = getenv("B200REG_ZM_TMA")) ctx->zm_tma = (e[0] != '0');
     if (const char* e = getenv("B200REG_FORCE_ZM1")) ctx->force_zm1 = (e[0] == '1');
     *out = ctx;
     return B200REG_OK;

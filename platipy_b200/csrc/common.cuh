@@ -62,6 +62,7 @@ struct b200reg_ctx {
     bool unfused_force = false;    // B200REG_UNFUSED_FORCE=1: separate warp and force kernels (W through HBM)
     bool staple_voxelwise = false; // B200REG_STAPLE_VOXELWISE=1: per-voxel EM kernels instead of the pattern-histogram EM
     bool update_ws = false;        // B200REG_UPDATE_WS=1: warp-specialised (producer/consumer) fused update kernel
+    bool zm_tma = true;            // B200REG_ZM_TMA=0: stage every tile of the fused smoothing kernel with cp.async instead of TMA bulk copies
     bool force_zm1 = false;        // B200REG_FORCE_ZM1=1: first-generation fused smoothing kernel
 };
 
