@@ -202,10 +202,13 @@ __device__ __forceinline__ double lin_eval_i32(const T* __restrict__ img, int nx
     const int o000 = (w.b2 * nxy) + (w.b1 * nx) + w.b0;
     const int dx = w.u0 - w.b0, dy = (w.u1 - w.b1) * nx, dz = (w.u2 - w.b2) * nxy;
     const int o010 = o000 + dy, o001 = o000 + dz, o011 = o010 + dz;
-    const double v000 = (double)__ldg(img + o000), v100 = (double)__ldg(img + o000 + dx);
-    const double v010 = (double)__ldg(img + o010), v110 = (double)__ldg(img + o010 + dx);
-    const double v001 = (double)__ldg(img + o001), v101 = (double)__ldg(img + o001 + dx);
-    const double v011 = (double)__ldg(img + o011), v111 = (double)__ldg(img + o011 + dx);
+    // offsets are summed as 32-bit integers before they meet the pointer: one IMAD.WIDE per load instead of a
+    // 64-bit add chain
+    const int o100 = o000 + dx, o110 = o010 + dx, o101 = o001 + dx, o111 = o011 + dx;
+    const double v000 = (double)__ldg(img + o000), v100 = (double)__ldg(img + o100);
+    const double v010 = (double)__ldg(img + o010), v110 = (double)__ldg(img + o110);
+    const double v001 = (double)__ldg(img + o001), v101 = (double)__ldg(img + o101);
+    const double v011 = (double)__ldg(img + o011), v111 = (double)__ldg(img + o111);
     const double vx00 = v000 + (v100 - v000) * w.d0;
     const double vx10 = v010 + (v110 - v010) * w.d0;
     const double vxx0 = vx00 + (vx10 - vx00) * w.d1;
