@@ -63,6 +63,11 @@ struct b200reg_ctx {
     bool staple_voxelwise = false; // B200REG_STAPLE_VOXELWISE=1: per-voxel EM kernels instead of the pattern-histogram EM
     bool update_ws = false;        // B200REG_UPDATE_WS=1: warp-specialised (producer/consumer) fused update kernel
     bool zm_tma = true;            // B200REG_ZM_TMA=0: stage every tile of the fused smoothing kernel with cp.async instead of TMA bulk copies
+    bool update_branchy = false;   // B200REG_UPDATE_BRANCHY=1: first version of the fused update kernel's force phase (per-voxel branches)
+    bool zm_regadd = false;        // B200REG_ZM_REGADD=0: add + smooth stages both operands in shared memory (first version)
+    bool update_split = true;      // B200REG_UPDATE_SPLIT=0: fused z-marching warp + force kernel instead of the two high-occupancy kernels
+    int pf_warp = 0;               // B200REG_PF_WARP=n: warp kernel prefetches the field n planes ahead into L2
+    int pf_force = 0;              // B200REG_PF_FORCE=n: force kernel prefetches W / F n steps ahead into L2
     bool force_zm1 = false;        // B200REG_FORCE_ZM1=1: first-generation fused smoothing kernel
 };
 

@@ -13,17 +13,9 @@
 #include "common.cuh"
 #include "gauss.cuh"
 #include "resample.cuh"
+#include "demons_split.cuh"
 
 namespace b200 {
-
-struct ForceParams {
-    double normalizer;         // mean(spacing^2) * MaximumUpdateStepLength^2, or -1
-    double intensity_thresh;   // 0.001
-    double denom_thresh;       // 1e-9
-    double max_rms_error;      // 0.02
-    double half_inv_sp[3];     // 0.5 / spacing (the factor ITK's central differences multiply by)
-    double inv_normalizer;     // exact reciprocal when the normalizer is a power of two, else 0
-};
 
 // WarpImageFilter with the field on the output (fixed) grid: point = index->physical + D; linear
 // interpolation of the moving image; edge padding NumericTraits<float>::max().
@@ -241,9 +233,16 @@ __global__ void __launch_bounds__(1024) demons_finish_kernel(const double* __res
 #endif
 constexpr int UP_TX = 64, UP_TY = 16, UP_NT = 256, UP_HW = UP_TX + 2, UP_HH = UP_TY + 2, UP_NP = UP_HW * UP_HH, UP_RING = UP_RING_DEPTH;
 constexpr int UP_NHALO = UP_NP - UP_TX * UP_TY;  // 164
+#ifndef UP_GROUP
+#define UP_GROUP 2
+#endif
+constexpr int UP_G = UP_GROUP;  // voxels of a thread whose force-phase dependency chains are interleaved (1, 2 or 4)
 constexpr size_t UP_SMEM = (size_t)2 * UP_RING * UP_NP * sizeof(double);
 
-template <bool DIAG>
+// CONSUME 0: per-voxel branches in the force phase (first version).  CONSUME 1..3: branch-free force phase, the four
+// voxels of a thread interleaved; the intensity normalisation is a compile-time case (1: none, 2: multiplication by
+// the exact reciprocal of a power-of-two normalizer, 3: division).
+template <bool DIAG, int CONSUME>
 __global__ void __launch_bounds__(UP_NT, UP_MINB) demons_update_kernel(const float* __restrict__ F, const float* __restrict__ M, const double* __restrict__ D,
                                                                   double* __restrict__ U, double* __restrict__ partials,
                                                                   const __grid_constant__ GeomD gf, const __grid_constant__ GeomD gm,
@@ -367,7 +366,7 @@ __global__ void __launch_bounds__(UP_NT, UP_MINB) demons_update_kernel(const flo
                 const int si = slot * UP_NP + hy[q] * UP_HW + hx[q];
                 Wr[si] = ins[q] ? (double)(float)wv[q] : WMAX;
                 Fr[si] = (double)fv[q];
-                if (!ins[q]) sent[slot] = z;
+                if (CONSUME == 0 && !ins[q]) sent[slot] = z;
             }
         }
     };
@@ -383,7 +382,7 @@ __global__ void __launch_bounds__(UP_NT, UP_MINB) demons_update_kernel(const flo
     }
 
     // generic ESM update of one voxel (all border / sentinel cases), identical to demons_force_kernel
-    auto slow_voxel = [&](int j, int z, int sc, int sm1, int sp1, double& u0, double& u1, double& u2) {
+    auto slow_voxel = [&](int j, int z, int sc, int sm1, int sp1, double& u0, double& u1, double& u2, double& ds, double& dc, double& du) {
         const int gy = y0 + 4 * yb + j;
         const int ci = hy[j] * UP_HW + hx[j];
         const double movingValue = Wr[sc + ci];
@@ -466,9 +465,9 @@ __global__ void __launch_bounds__(UP_NT, UP_MINB) demons_update_kernel(const flo
                 u2 = factor * J[2];
             }
         }
-        ssd += speed * speed;
-        cnt += 1.0;
-        ssc += u0 * u0 + u1 * u1 + u2 * u2;
+        ds = speed * speed;
+        dc = 1.0;
+        du = u0 * u0 + u1 * u1 + u2 * u2;
     };
 
     produce(z0 - 1);
@@ -482,7 +481,109 @@ __global__ void __launch_bounds__(UP_NT, UP_MINB) demons_update_kernel(const flo
         // interior planes without any sentinel in the three ring planes take the branch-free path
         const bool clean = inner_z && sent[sc / UP_NP] != z && sent[sm1 / UP_NP] != z - 1 && sent[sp1 / UP_NP] != z + 1;
         const bool all_fast = clean && inner_xy[0] && inner_xy[1] && inner_xy[2] && inner_xy[3];
-        if (all_fast) {
+        if (CONSUME > 0) {
+            // Straight-line force phase.  Every voxel is first computed with central differences (the same IEEE
+            // operations as the generic path); a voxel whose stencil touches the image border or a FLT_MAX sentinel
+            // is flagged and redone by the generic path afterwards -- per voxel, not per CTA.  The sentinel test
+            // compares high words only: (double)FLT_MAX is 0x47EFFFFF'E0000000, so a hit may also be one of the
+            // seven next-largest floats, which merely sends that voxel through the (always correct) generic path.
+#pragma unroll
+            for (int h = 0; h < 4; h += UP_G) {
+                double u0[UP_G], u1[UP_G], u2[UP_G], ds[UP_G], dc[UP_G], du[UP_G];
+                bool bad[UP_G], anybad = false;
+                {
+                    double g0[UP_G], g1[UP_G], g2[UP_G], sp[UP_G], den[UP_G], num[UP_G], fac[UP_G];
+                    bool live[UP_G], okd[UP_G];
+#pragma unroll
+                    for (int q = 0; q < UP_G; ++q) {
+                        const int j = h + q;
+                        const int ci = hy[j] * UP_HW + hx[j];
+                        const double fc = Fr[sc + ci], wc = Wr[sc + ci];
+                        const double wxp = Wr[sc + ci + 1], wxm = Wr[sc + ci - 1], wyp = Wr[sc + ci + UP_HW], wym = Wr[sc + ci - UP_HW];
+                        const double wzp = Wr[sp1 + ci], wzm = Wr[sm1 + ci];
+                        constexpr int SH = 0x47EFFFFF;
+                        const bool snt = __double2hiint(wc) == SH || __double2hiint(wxp) == SH || __double2hiint(wxm) == SH ||
+                                         __double2hiint(wyp) == SH || __double2hiint(wym) == SH || __double2hiint(wzp) == SH || __double2hiint(wzm) == SH;
+                        bad[q] = snt || !inner_z || !inner_xy[j];
+                        anybad = anybad || bad[q];
+                        g0[q] = (Fr[sc + ci + 1] - Fr[sc + ci - 1]) * fp.half_inv_sp[0] + (wxp - wxm) * fp.half_inv_sp[0];
+                        g1[q] = (Fr[sc + ci + UP_HW] - Fr[sc + ci - UP_HW]) * fp.half_inv_sp[1] + (wyp - wym) * fp.half_inv_sp[1];
+                        g2[q] = (Fr[sp1 + ci] - Fr[sm1 + ci]) * fp.half_inv_sp[2] + (wzp - wzm) * fp.half_inv_sp[2];
+                        if (!DIAG) {
+                            const double a0 = g0[q], a1 = g1[q], a2 = g2[q];
+                            g0[q] = ((0.0 + gf.direction[0] * a0) + gf.direction[1] * a1) + gf.direction[2] * a2;
+                            g1[q] = ((0.0 + gf.direction[3] * a0) + gf.direction[4] * a1) + gf.direction[5] * a2;
+                            g2[q] = ((0.0 + gf.direction[6] * a0) + gf.direction[7] * a1) + gf.direction[8] * a2;
+                        }
+                        sp[q] = fc - wc;
+                        ds[q] = sp[q] * sp[q];
+                        dc[q] = 1.0;
+                        den[q] = g0[q] * g0[q] + g1[q] * g1[q] + g2[q] * g2[q];
+                    }
+                    if (CONSUME == 2) {
+#pragma unroll
+                        for (int q = 0; q < UP_G; ++q) den[q] = den[q] + ds[q] * fp.inv_normalizer;
+                    } else if (CONSUME == 3) {
+                        double qn[UP_G];
+                        bool okn[UP_G], redo = false;
+#pragma unroll
+                        for (int q = 0; q < UP_G; ++q) {
+                            qn[q] = div_fast_path(ds[q], fp.normalizer, okn[q]);
+                            redo = redo || (!okn[q] && !bad[q]);
+                        }
+                        if (redo) {
+#pragma unroll
+                            for (int q = 0; q < UP_G; ++q)
+                                if (!okn[q] && !bad[q]) qn[q] = ds[q] / fp.normalizer;
+                        }
+#pragma unroll
+                        for (int q = 0; q < UP_G; ++q) den[q] = den[q] + qn[q];
+                    }
+                    bool redo = false;
+#pragma unroll
+                    for (int q = 0; q < UP_G; ++q) {
+                        live[q] = !(fabs(sp[q]) < fp.intensity_thresh) && !(den[q] < fp.denom_thresh);
+                        num[q] = 2.0 * sp[q];
+                        fac[q] = div_fast_path(num[q], den[q], okd[q]);
+                        redo = redo || (live[q] && !okd[q] && !bad[q]);
+                    }
+                    if (redo) {
+#pragma unroll
+                        for (int q = 0; q < UP_G; ++q)
+                            if (live[q] && !okd[q] && !bad[q]) fac[q] = num[q] / den[q];
+                    }
+#pragma unroll
+                    for (int q = 0; q < UP_G; ++q) {
+                        u0[q] = live[q] ? fac[q] * g0[q] : 0.0;
+                        u1[q] = live[q] ? fac[q] * g1[q] : 0.0;
+                        u2[q] = live[q] ? fac[q] * g2[q] : 0.0;
+                        du[q] = u0[q] * u0[q] + u1[q] * u1[q] + u2[q] * u2[q];
+                    }
+                }
+                if (anybad) {
+#pragma unroll
+                    for (int q = 0; q < UP_G; ++q) {
+                        if (bad[q]) {
+                            u0[q] = u1[q] = u2[q] = 0.0;
+                            ds[q] = dc[q] = du[q] = 0.0;
+                            if (poff[h + q] >= 0) slow_voxel(h + q, z, sc, sm1, sp1, u0[q], u1[q], u2[q], ds[q], dc[q], du[q]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < UP_G; ++q) {
+                    ssd += ds[q];
+                    cnt += dc[q];
+                    ssc += du[q];
+                    if (poff[h + q] >= 0) {
+                        const int o = zo + poff[h + q];
+                        U0[o] = u0[q];
+                        U1[o] = u1[q];
+                        U2[o] = u2[q];
+                    }
+                }
+            }
+        } else if (all_fast) {
             // branch-free interior path: central differences everywhere (same operations as the generic path)
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
@@ -517,8 +618,11 @@ __global__ void __launch_bounds__(UP_NT, UP_MINB) demons_update_kernel(const flo
 #pragma unroll 1
             for (int j = 0; j < 4; ++j) {
                 if (poff[j] < 0) continue;
-                double u0 = 0.0, u1 = 0.0, u2 = 0.0;
-                slow_voxel(j, z, sc, sm1, sp1, u0, u1, u2);
+                double u0 = 0.0, u1 = 0.0, u2 = 0.0, ds = 0.0, dc = 0.0, du = 0.0;
+                slow_voxel(j, z, sc, sm1, sp1, u0, u1, u2, ds, dc, du);
+                ssd += ds;
+                cnt += dc;
+                ssc += du;
                 const int o = zo + poff[j];
                 U0[o] = u0;
                 U1[o] = u1;
@@ -926,7 +1030,12 @@ inline int demons_calculate_change(b200reg_ctx* ctx, const float* F, const GeomD
     const dim3 gprobe = update_grid(ctx, gf, &zchunk_probe);
     const bool small_grid = (size_t)gprobe.x * gprobe.y * gprobe.z < (size_t)ctx->sm_count * 4;
     const bool huge = (size_t)gf.nx * gf.ny * gf.nz >= (1ull << 31) || (size_t)gm.nx * gm.ny * gm.nz >= (1ull << 31);  // 32-bit offsets inside
-    if (want_w || ctx->unfused_force || small_grid || huge) {
+    const bool fits32 = (size_t)gf.nx * gf.ny * gf.nz * 3 < (1ull << 31) && (size_t)gm.nx * gm.ny * gm.nz < (1ull << 31);
+    if (ctx->update_split && fits32) {
+        // two high-occupancy kernels, W through HBM (demons_split.cuh)
+        B200_TRY(launch_update_split(ctx, F, gf, M, gm, D, ws->W.as<float>(), ws->U.as<double>(), ws->partials.as<double>(), fp,
+                                     geom_is_diag(gf) && geom_is_diag(gm), ctrl, it, &nblocks));
+    } else if (want_w || ctx->unfused_force || small_grid || huge) {
         const dim3 g = grid3(gf.nx, gf.ny, gf.nz), b = block3();
         nblocks = (size_t)g.x * g.y * g.z;
         if (gm.small) demons_warp_kernel<true><<<g, b, 0, ctx->stream>>>(M, D, ws->W.as<float>(), gf, gm, ctrl, it);
@@ -948,14 +1057,30 @@ inline int demons_calculate_change(b200reg_ctx* ctx, const float* F, const GeomD
                 demons_update_ws_kernel<false><<<g, WS_NT, WS_SMEM, ctx->stream>>>(F, M, D, ws->U.as<double>(), ws->partials.as<double>(), gf, gm, fp, zchunk,
                                                                                    (int)g.z, ctrl, it);
         } else {
-        if (diag) B200_TRY(ensure_dynamic_smem(ctx, demons_update_kernel<true>, UP_SMEM));
-        else B200_TRY(ensure_dynamic_smem(ctx, demons_update_kernel<false>, UP_SMEM));
-        if (diag)
-            demons_update_kernel<true><<<g, UP_NT, UP_SMEM, ctx->stream>>>(F, M, D, ws->U.as<double>(), ws->partials.as<double>(), gf, gm, fp, zchunk,
-                                                                            (int)g.z, ctrl, it);
-        else
-            demons_update_kernel<false><<<g, UP_NT, UP_SMEM, ctx->stream>>>(F, M, D, ws->U.as<double>(), ws->partials.as<double>(), gf, gm, fp, zchunk,
-                                                                             (int)g.z, ctrl, it);
+        // force-phase variant: 0 = per-voxel branches, else the straight-line form specialised on the normalisation
+        const int consume = ctx->update_branchy ? 0 : (fp.normalizer > 0.0 ? (fp.inv_normalizer != 0.0 ? 2 : 3) : 1);
+#define UP_LAUNCH(DG, CS)                                                                                                                     \
+    do {                                                                                                                                      \
+        B200_TRY(ensure_dynamic_smem(ctx, demons_update_kernel<DG, CS>, UP_SMEM));                                                            \
+        demons_update_kernel<DG, CS><<<g, UP_NT, UP_SMEM, ctx->stream>>>(F, M, D, ws->U.as<double>(), ws->partials.as<double>(), gf, gm, fp, \
+                                                                         zchunk, (int)g.z, ctrl, it);                                         \
+    } while (0)
+        if (diag) {
+            switch (consume) {
+            case 0: UP_LAUNCH(true, 0); break;
+            case 1: UP_LAUNCH(true, 1); break;
+            case 2: UP_LAUNCH(true, 2); break;
+            default: UP_LAUNCH(true, 3); break;
+            }
+        } else {
+            switch (consume) {
+            case 0: UP_LAUNCH(false, 0); break;
+            case 1: UP_LAUNCH(false, 1); break;
+            case 2: UP_LAUNCH(false, 2); break;
+            default: UP_LAUNCH(false, 3); break;
+            }
+        }
+#undef UP_LAUNCH
         }
         ctx->launches += 1;
     }

@@ -334,12 +334,17 @@ __device__ __forceinline__ void tma_bulk_g2s(double* smem_dst, const double* gsr
                  : "memory");
 }
 
-template <int R, int RZ, bool ADD>
+// MODE 0: out = G(a).  MODE 1: out = G(a + b), both operands staged with cp.async and added in the x pass.
+// MODE 2: out = G(a + b), the next plane's operands are loaded into registers while the current plane is processed and
+// their sum is what gets staged: one shared buffer less, half the staging writes and x-pass reads of MODE 1.
+template <int R, int RZ, int MODE>
 __global__ void __launch_bounds__(Zm2Threads<R>::value, 2) conv3d_zm2_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out,
                                                                int nx, int ny, int nz, int zchunk, int nchunks,
                                                                const __grid_constant__ SmallCoeffs kc, const DemonsCtrl* __restrict__ ctrl, int it, int use_tma)
 {
     if (ctrl && it >= ctrl->halt_iter) return;
+    constexpr bool ADD = MODE == 1;     // second operand staged in shared memory
+    constexpr bool REGADD = MODE == 2;  // operands summed in registers before staging
     constexpr int RP = (R + 1) & ~1;  // x halo padded to an even count: 16-byte aligned shared rows
     constexpr int AW = ZM_TX + 2 * RP, AH = ZM_TY + 2 * R, NA = AW * AH;
     constexpr int NR = 2 * RZ + 1;
@@ -356,7 +361,7 @@ __global__ void __launch_bounds__(Zm2Threads<R>::value, 2) conv3d_zm2_kernel(con
     const int z0 = chunk * zchunk, z1 = min(nz, z0 + zchunk);
     const size_t plane = (size_t)nx * ny, vol = plane * nz;
     const double* __restrict__ ap = a + (size_t)comp * vol;
-    const double* __restrict__ bp = ADD ? b + (size_t)comp * vol : nullptr;
+    const double* __restrict__ bp = MODE != 0 ? b + (size_t)comp * vol : nullptr;
     double* __restrict__ op = out + (size_t)comp * vol;
 
     int goff[NLD];
@@ -393,6 +398,22 @@ __global__ void __launch_bounds__(Zm2Threads<R>::value, 2) conv3d_zm2_kernel(con
         gy = gy < 0 ? 0 : (gy > ny - 1 ? ny - 1 : gy);
         row_off = gy * nx + (x0 - RP);
     }
+    double pre_a[REGADD ? NLD : 1], pre_b[REGADD ? NLD : 1];  // MODE 2: operands of the next plane, in flight
+    auto load_next = [&](int z) {
+        const int zc = z < 0 ? 0 : (z > nz - 1 ? nz - 1 : z);
+        const size_t zo = (size_t)zc * plane;
+#pragma unroll
+        for (int l = 0; l < NLD; ++l)
+            if (goff[l] >= 0) {
+                pre_a[l] = ap[zo + goff[l]];
+                pre_b[l] = bp[zo + goff[l]];
+            }
+    };
+    auto store_next = [&](int buf) {
+#pragma unroll
+        for (int l = 0; l < NLD; ++l)
+            if (goff[l] >= 0) Aa[buf * NA + tid + l * NT] = pre_a[l] + pre_b[l];
+    };
     auto stage = [&](int z, int buf) {
         const int zc = z < 0 ? 0 : (z > nz - 1 ? nz - 1 : z);
         const size_t zo = (size_t)zc * plane;
@@ -419,17 +440,27 @@ __global__ void __launch_bounds__(Zm2Threads<R>::value, 2) conv3d_zm2_kernel(con
     const int gx = x0 + ox;
     double ring[NR][4];
     const int zbeg = z0 - RZ, nsteps = (z1 - z0) + 2 * RZ;
-    stage(zbeg, 0);
+    if (REGADD) {
+        load_next(zbeg);
+        store_next(0);
+    } else {
+        stage(zbeg, 0);
+    }
     for (int q0 = 0; q0 < nsteps; q0 += NR) {
 #pragma unroll
         for (int s = 0; s < NR; ++s) {
             const int q = q0 + s;
             if (q < nsteps) {
                 const int buf = q & 1;
+                if (REGADD) {
+                    __syncthreads();  // plane q (summed and stored at the end of step q - 1) is visible; B may be rewritten
+                    if (q + 1 < nsteps) load_next(zbeg + q + 1);
+                } else {
                 if (interior) mbar_wait(&full_bar[buf], (unsigned)((q >> 1) & 1));
                 else cp_async_wait_all();
                 __syncthreads();
                 if (q + 1 < nsteps) stage(zbeg + q + 1, buf ^ 1);
+                }
                 // ---- x pass: per task two output pairs {2cx, 2cx+1} and {32+2cx, 32+2cx+1} of one row (rows incl. the
                 // y halo).  Lanes read consecutive 16-byte words: conflict-free 128-bit shared loads and stores.
                 {
@@ -487,6 +518,8 @@ __global__ void __launch_bounds__(Zm2Threads<R>::value, 2) conv3d_zm2_kernel(con
                         if (gx < nx && gy < ny) op[(size_t)zo * plane + (size_t)gy * nx + gx] = sum;
                     }
                 }
+                // MODE 2: buffer buf ^ 1 was last read by the x pass of step q - 1, two barriers ago
+                if (REGADD && q + 1 < nsteps) store_next(buf ^ 1);
             }
         }
     }
@@ -499,14 +532,18 @@ inline int launch_zm2_rz(b200reg_ctx* ctx, const double* a, const double* b, dou
     constexpr int RP = (R + 1) & ~1;
     constexpr int NA = (ZM_TX + 2 * RP) * (ZM_TY + 2 * R);
     constexpr int NB = (ZM_TY + 2 * R) * ZM_TX;
-    if (b) {
+    if (b && ctx->zm_regadd) {
+        constexpr size_t smem = (size_t)(2 * NA + NB) * sizeof(double);
+        B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, 2>, smem));
+        conv3d_zm2_kernel<R, RZ, 2><<<g, Zm2Threads<R>::value, smem, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, 0);
+    } else if (b) {
         constexpr size_t smem = (size_t)(4 * NA + NB) * sizeof(double);
-        B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, true>, smem));
-        conv3d_zm2_kernel<R, RZ, true><<<g, Zm2Threads<R>::value, smem, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, ctx->zm_tma ? 1 : 0);
+        B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, 1>, smem));
+        conv3d_zm2_kernel<R, RZ, 1><<<g, Zm2Threads<R>::value, smem, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, ctx->zm_tma ? 1 : 0);
     } else {
         constexpr size_t smem = (size_t)(2 * NA + NB) * sizeof(double);
-        B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, false>, smem));
-        conv3d_zm2_kernel<R, RZ, false><<<g, Zm2Threads<R>::value, smem, ctx->stream>>>(a, nullptr, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, ctx->zm_tma ? 1 : 0);
+        B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, 0>, smem));
+        conv3d_zm2_kernel<R, RZ, 0><<<g, Zm2Threads<R>::value, smem, ctx->stream>>>(a, nullptr, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, ctx->zm_tma ? 1 : 0);
     }
     return B200REG_OK;
 }
