@@ -68,6 +68,7 @@ struct b200reg_ctx {
     bool update_split = true;      // B200REG_UPDATE_SPLIT=0: fused z-marching warp + force kernel instead of the two high-occupancy kernels
     int pf_warp = 0;               // B200REG_PF_WARP=n: warp kernel prefetches the field n planes ahead into L2
     int pf_force = 0;              // B200REG_PF_FORCE=n: force kernel prefetches W / F n steps ahead into L2
+    int warp_march = 0;            // B200REG_WARP_MARCH=n: z-marching warp kernel with n planes per thread (0: one-shot kernel)
     bool force_zm1 = false;        // B200REG_FORCE_ZM1=1: first-generation fused smoothing kernel
 };
 

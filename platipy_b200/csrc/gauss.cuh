@@ -575,8 +575,11 @@ inline int launch_conv3d_zmarch(b200reg_ctx* ctx, const double* a, const double*
     }
     const int tiles = ((nx + ZM_TX - 1) / ZM_TX) * ((ny + ZM_TY - 1) / ZM_TY) * nplanes;
     // enough CTAs for ~4 waves of 2 CTAs/SM, but chunks of at least 16 planes (each chunk re-reads 2*rz planes)
+    // (coarse pyramid levels have so few tiles that chunks as short as 4 planes are worth their halo planes: the
+    // whole field is L2 resident there and the GPU is otherwise idle)
     int nchunks = (ctx->sm_count * 8 + tiles - 1) / tiles;
-    const int max_chunks = (nz + 15) / 16;
+    const int min_chunk = tiles * ((nz + 15) / 16) >= ctx->sm_count * 4 ? 16 : 4;
+    const int max_chunks = (nz + min_chunk - 1) / min_chunk;
     if (nchunks > max_chunks) nchunks = max_chunks;
     if (nchunks < 1) nchunks = 1;
     const int zchunk = (nz + nchunks - 1) / nchunks;
