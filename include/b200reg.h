@@ -218,6 +218,21 @@ int b200reg_unpack_decision(b200reg_ctx* ctx, const int32_t* d_packed, int bit, 
 int b200reg_staple(b200reg_ctx* ctx, const uint8_t* const* d_decisions, int n_raters, size_t n, double confidence_weight,
                    uint32_t max_iterations, double threshold, int rescale, double* d_out, double* h_pq, int32_t* h_elapsed);
 
+/* ---- N15: process_probability_image (fusion.py:295-328) and the binary post-processing around it ---------- */
+/* sitk.BinaryFillhole(img) (fusion.py:311; FullyConnected=False, foreground 1): background components that do not
+ * reach the image border become foreground.  size = (x, y, z); d_out may alias d_in. */
+int b200reg_binary_fillhole(b200reg_ctx* ctx, const uint8_t* d_in, const int32_t size[3], int fully_connected, uint8_t* d_out);
+/* sitk.ConnectedComponent -> LabelShapeStatistics -> argmax(GetNumberOfPixels) -> (labels == k) -> Cast(UInt8)
+ * (fusion.py:314-328), equivalently sitk.RelabelComponent(sitk.ConnectedComponent(x)) == 1 (multiatlas/run.py:423):
+ * the largest face-connected object, the first in raster order on ties.  h_n_components / h_voxels (optional) are
+ * filled after a stream synchronisation; with no object the output is all zeros. */
+int b200reg_largest_component(b200reg_ctx* ctx, const uint8_t* d_in, const int32_t size[3], int fully_connected, uint8_t* d_out,
+                              int64_t* h_n_components, int64_t* h_voxels);
+/* The whole of process_probability_image on the device: p / max(p) -> BinaryThreshold(lower = threshold) ->
+ * BinaryFillhole -> largest connected component -> UInt8.  dtype: B200REG_F32 or B200REG_F64. */
+int b200reg_process_probability(b200reg_ctx* ctx, const void* d_prob, int dtype, const int32_t size[3], double threshold,
+                                uint8_t* d_out, int64_t* h_n_components);
+
 #ifdef __cplusplus
 }
 #endif

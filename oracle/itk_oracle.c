@@ -1022,6 +1022,77 @@ ORC_API int orc_rescale_threshold_f64(double* img, size_t n, double threshold)
     return 0;
 }
 
+/* ---- binary post-processing (reference fusion.py:295-328 process_probability_image) ------------------------- */
+/* Face-connected flood fill with an explicit stack: every voxel of `cls` reachable from `seed` gets `label`. */
+static void flood6(const uint8_t* in, int cls, int32_t* lab, int32_t label, int nx, int ny, int nz, size_t seed, size_t* stack, size_t* count)
+{
+    size_t top = 0, c = 0;
+    const size_t pz = (size_t)nx * ny;
+    stack[top++] = seed;
+    lab[seed] = label;
+    while (top) {
+        const size_t i = stack[--top];
+        ++c;
+        const int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / pz);
+#define ORC_TRY(cond, j) if (cond) { const size_t q = (j); if (lab[q] == 0 && ((in[q] != 0) == cls)) { lab[q] = label; stack[top++] = q; } }
+        ORC_TRY(x > 0, i - 1)
+        ORC_TRY(x < nx - 1, i + 1)
+        ORC_TRY(y > 0, i - nx)
+        ORC_TRY(y < ny - 1, i + nx)
+        ORC_TRY(z > 0, i - pz)
+        ORC_TRY(z < nz - 1, i + pz)
+#undef ORC_TRY
+    }
+    if (count) *count = c;
+}
+
+/* itk::BinaryFillholeImageFilter, FullyConnected = false, ForegroundValue = 1 (sitk.BinaryFillhole, fusion.py:311):
+ * the image is padded with background, the background is labelled (face connectivity) and only the object on
+ * the border is kept as background -- i.e. background voxels not connected to the image border become 1. */
+ORC_API int orc_binary_fillhole(const uint8_t* in, int nx, int ny, int nz, uint8_t* out)
+{
+    const size_t n = (size_t)nx * ny * nz, pz = (size_t)nx * ny;
+    int32_t* lab = (int32_t*)calloc(n, sizeof(int32_t));
+    size_t* stack = (size_t*)malloc(n * sizeof(size_t));
+    if (!lab || !stack) { free(lab); free(stack); return -1; }
+    for (size_t i = 0; i < n; ++i) {
+        const int x = (int)(i % nx), y = (int)((i / nx) % ny), z = (int)(i / pz);
+        const int border = x == 0 || x == nx - 1 || y == 0 || y == ny - 1 || z == 0 || z == nz - 1;
+        if (border && in[i] == 0 && lab[i] == 0) flood6(in, 0, lab, 1, nx, ny, nz, i, stack, NULL);
+    }
+    for (size_t i = 0; i < n; ++i) out[i] = (in[i] != 0 || lab[i] == 0) ? 1 : 0;
+    free(lab);
+    free(stack);
+    return 0;
+}
+
+/* sitk.ConnectedComponent (FullyConnected = false; objects numbered 1.. in raster order of their first voxel)
+ * -> LabelShapeStatistics.GetNumberOfPixels -> np.argmax (first maximum) -> labels == k -> UInt8
+ * (fusion.py:314-328).  labels_out (optional, int32) receives the ConnectedComponent image.
+ * Returns the number of objects; with none, out is all zeros. */
+ORC_API int orc_largest_component(const uint8_t* in, int nx, int ny, int nz, uint8_t* out, int32_t* labels_out, int64_t* largest_voxels)
+{
+    const size_t n = (size_t)nx * ny * nz;
+    int32_t* lab = (int32_t*)calloc(n, sizeof(int32_t));
+    size_t* stack = (size_t*)malloc(n * sizeof(size_t));
+    if (!lab || !stack) { free(lab); free(stack); return -1; }
+    int32_t nlab = 0, best = 0;
+    size_t best_count = 0;
+    for (size_t i = 0; i < n; ++i) {
+        if (in[i] != 0 && lab[i] == 0) {
+            size_t c = 0;
+            flood6(in, 1, lab, ++nlab, nx, ny, nz, i, stack, &c);
+            if (c > best_count) { best_count = c; best = nlab; }
+        }
+    }
+    for (size_t i = 0; i < n; ++i) out[i] = (best != 0 && lab[i] == best) ? 1 : 0;
+    if (labels_out) memcpy(labels_out, lab, n * sizeof(int32_t));
+    if (largest_voxels) *largest_voxels = (int64_t)best_count;
+    free(lab);
+    free(stack);
+    return (int)nlab;
+}
+
 ORC_API int orc_num_threads(void)
 {
 #ifdef _OPENMP

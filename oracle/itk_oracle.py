@@ -68,6 +68,8 @@ def lib():
         _lib.orc_recursive_gaussian_vec3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.orc_transform_to_dvf.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib.orc_set_num_threads.argtypes = [C.c_int]
+        _lib.orc_binary_fillhole.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        _lib.orc_largest_component.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     return _lib
 
 
@@ -268,3 +270,27 @@ def rescale_threshold_f64(img, threshold):
     out = np.array(img, dtype=np.float64, order="C", copy=True)
     lib().orc_rescale_threshold_f64(_ptr(out), out.size, float(threshold or 0.0))
     return out
+
+
+def binary_fillhole(mask):
+    """sitk.BinaryFillhole (face connectivity, foreground 1) on a [z, y, x] uint8 array."""
+    m = np.ascontiguousarray(mask, dtype=np.uint8)
+    out = np.empty_like(m)
+    nz, ny, nx = m.shape
+    if lib().orc_binary_fillhole(_ptr(m), nx, ny, nz, _ptr(out)) != 0:
+        raise MemoryError
+    return out
+
+
+def largest_component(mask, want_labels=False):
+    """ConnectedComponent -> largest object (first in raster order on ties) as uint8; also returns the object count,
+    the size of the largest and (optionally) the ConnectedComponent label image."""
+    m = np.ascontiguousarray(mask, dtype=np.uint8)
+    out = np.empty_like(m)
+    nz, ny, nx = m.shape
+    labels = np.empty(m.shape, dtype=np.int32) if want_labels else None
+    nvox = C.c_int64(0)
+    ncomp = lib().orc_largest_component(_ptr(m), nx, ny, nz, _ptr(out), _ptr(labels) if want_labels else None, C.byref(nvox))
+    if ncomp < 0:
+        raise MemoryError
+    return (out, ncomp, nvox.value, labels) if want_labels else (out, ncomp, nvox.value)

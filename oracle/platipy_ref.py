@@ -269,3 +269,25 @@ def combine_labels_staple(label_list_dict, threshold=1e-4):
         W = orc.rescale_threshold_f64(W, threshold)
         out[str(s)] = _like(W, imgs[0])
     return out
+
+
+def process_probability_image(probability_image, threshold=0.5):
+    """fusion.py:295-328: normalise by the maximum, BinaryThreshold(lowerThreshold=threshold), BinaryFillhole,
+    ConnectedComponent, keep the largest object; returns a UInt8 image."""
+    if isinstance(probability_image, np.ndarray):
+        probability_image = sk.Image(probability_image)  # fusion.py:301-302
+    arr = probability_image.array
+    mx = arr.max()
+    # sitk image / float: itk::Functor::Div<T, double, T> -- A / B in double, cast back to the pixel type (fusion.py:305)
+    if mx != 0:
+        norm = (arr.astype(np.float64) / float(mx)).astype(arr.dtype)
+    else:
+        norm = np.full(arr.shape, np.finfo(arr.dtype).max, dtype=arr.dtype)
+    # sitk.BinaryThreshold(lowerThreshold=threshold): upper 255, inside 1, outside 0, UInt8 (fusion.py:308)
+    nd = norm.astype(np.float64)
+    binary = ((nd >= threshold) & (nd <= 255.0)).astype(np.uint8)
+    binary = orc.binary_fillhole(binary)                       # fusion.py:311
+    largest, ncomp, _ = orc.largest_component(binary)          # fusion.py:314-326
+    if ncomp == 0:
+        return _like(binary, probability_image)                # fusion.py:322-323
+    return _like(largest, probability_image)

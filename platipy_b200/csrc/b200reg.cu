@@ -5,6 +5,7 @@
 #include "demons.cuh"
 #include "deriche.cuh"
 #include "fusion.cuh"
+#include "morph.cuh"
 #include "gauss.cuh"
 #include "resample.cuh"
 
@@ -693,6 +694,67 @@ API int b200reg_staple(b200reg_ctx* ctx, const uint8_t* const* d_decisions, int 
         ctx->launches++;
         B200_CHECK_LAUNCH();
         B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
+    return B200REG_OK;
+}
+
+// ---- a12: process_probability_image building blocks (fusion.py:295-328; multiatlas/run.py:423) -------------------------
+API int b200reg_binary_fillhole(b200reg_ctx* ctx, const uint8_t* d_in, const int32_t size[3], int fully_connected, uint8_t* d_out)
+{
+    ENTER(ctx);
+    REQUIRE(d_in && d_out && size, "invalid argument");
+    if (fully_connected) return set_error(B200REG_ERR_UNSUPPORTED, "BinaryFillhole: FullyConnected=True is not implemented (the reference uses the default, False)");
+    return binary_fillhole(ctx, d_in, size, 1, d_out);
+}
+
+API int b200reg_largest_component(b200reg_ctx* ctx, const uint8_t* d_in, const int32_t size[3], int fully_connected, uint8_t* d_out,
+                                  int64_t* h_n_components, int64_t* h_voxels)
+{
+    ENTER(ctx);
+    REQUIRE(d_in && d_out && size, "invalid argument");
+    if (fully_connected) return set_error(B200REG_ERR_UNSUPPORTED, "ConnectedComponent: FullyConnected=True is not implemented (the reference uses the default, False)");
+    TempBuf info;
+    B200_TRY(info.alloc(ctx, 2 * sizeof(unsigned long long)));
+    B200_TRY(largest_component(ctx, d_in, size, d_out, info.as<unsigned long long>()));
+    if (h_n_components || h_voxels) {
+        unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->h_scratch);
+        B200_CUDA(cudaMemcpyAsync(h, info.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        B200_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (h_voxels) *h_voxels = (int64_t)(h[0] >> 32);
+        if (h_n_components) *h_n_components = (int64_t)h[1];
+    }
+    return B200REG_OK;
+}
+
+API int b200reg_process_probability(b200reg_ctx* ctx, const void* d_prob, int dtype, const int32_t size[3], double threshold, uint8_t* d_out,
+                                    int64_t* h_n_components)
+{
+    ENTER(ctx);
+    REQUIRE(d_prob && d_out && size, "invalid argument");
+    REQUIRE(dtype == B200REG_F32 || dtype == B200REG_F64, "process_probability_image: Float32 or Float64 probability image expected");
+    B200_TRY(check_ccl_size(size));
+    const size_t n = (size_t)size[0] * size[1] * size[2];
+    TempBuf part, mm, info;
+    B200_TRY(mm.alloc(ctx, 2 * sizeof(double)));
+    B200_TRY(info.alloc(ctx, 2 * sizeof(unsigned long long)));
+    const int nb = ctx->sm_count * 8;
+    if (dtype == B200REG_F32) {
+        B200_TRY(minmax_device<float>(ctx, (const float*)d_prob, n, mm.as<double>(), &part));
+        normalise_threshold_kernel<float><<<nb, 256, 0, ctx->stream>>>((const float*)d_prob, mm.as<double>(), threshold, 255.0, d_out, n);
+    } else {
+        B200_TRY(minmax_device<double>(ctx, (const double*)d_prob, n, mm.as<double>(), &part));
+        normalise_threshold_kernel<double><<<nb, 256, 0, ctx->stream>>>((const double*)d_prob, mm.as<double>(), threshold, 255.0, d_out, n);
+    }
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    B200_TRY(binary_fillhole(ctx, d_out, size, 1, d_out));
+    // no object: the reference returns the (empty) filled image; the selection below writes zeros as well
+    B200_TRY(largest_component(ctx, d_out, size, d_out, info.as<unsigned long long>()));
+    if (h_n_components) {
+        unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->h_scratch);
+        B200_CUDA(cudaMemcpyAsync(h, info.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        B200_CUDA(cudaStreamSynchronize(ctx->stream));
+        *h_n_components = (int64_t)h[1];
     }
     return B200REG_OK;
 }

@@ -382,6 +382,29 @@ class Engine:
                                                      C.c_void_p(out.data_ptr())))
         return dimg.like(out, np.uint8, False)
 
+    def _size3(self, dimg):
+        x, y, z = dimg.GetSize()
+        return (C.c_int32 * 3)(x, y, z)
+
+    def binary_fillhole(self, dimg, fully_connected=False):
+        out = self.empty(dimg.tensor.shape, np.uint8)
+        _abi.check(self.lib.b200reg_binary_fillhole(self.ctx, dimg.ptr, self._size3(dimg), int(bool(fully_connected)), C.c_void_p(out.data_ptr())))
+        return dimg.like(out, np.uint8, False)
+
+    def largest_component(self, dimg, fully_connected=False, want_info=False):
+        out = self.empty(dimg.tensor.shape, np.uint8)
+        ncomp, nvox = C.c_int64(), C.c_int64()
+        _abi.check(self.lib.b200reg_largest_component(self.ctx, dimg.ptr, self._size3(dimg), int(bool(fully_connected)), C.c_void_p(out.data_ptr()),
+                                                      C.byref(ncomp) if want_info else None, C.byref(nvox) if want_info else None))
+        res = dimg.like(out, np.uint8, False)
+        return (res, {"n_components": ncomp.value, "voxels": nvox.value}) if want_info else res
+
+    def process_probability(self, dimg, threshold=0.5):
+        out = self.empty(dimg.tensor.shape, np.uint8)
+        _abi.check(self.lib.b200reg_process_probability(self.ctx, dimg.ptr, dimg.dtype_id, self._size3(dimg), float(threshold),
+                                                        C.c_void_p(out.data_ptr()), None))
+        return dimg.like(out, np.uint8, False)
+
     def pack_decision(self, label, bit, packed, first):
         _abi.check(self.lib.b200reg_pack_decision(self.ctx, label.ptr, int(bit), C.c_void_p(packed.data_ptr()), label.tensor.numel(), int(bool(first))))
 

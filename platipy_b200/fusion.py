@@ -4,6 +4,7 @@ Drop-in replacements for the reference's label-fusion entry points (platipy/imag
     compute_weight_map      fusion.py:56-202   (vote types: unweighted, global, local)
     combine_labels          fusion.py:239-292  (weighted vote -> DiscreteGaussian -> RescaleIntensity -> Threshold)
     combine_labels_staple   fusion.py:205-236  (BinaryThreshold -> STAPLE -> RescaleIntensity -> Threshold)
+    process_probability_image fusion.py:295-328 (normalise -> BinaryThreshold -> BinaryFillhole -> largest component)
 
 plus the sharded forms used by ``platipy_b200.multiatlas``: every rank accumulates the votes of its local
 atlases and ONE all-reduce (NCCL on GPUs, gloo in the CPU tests of the host logic) exchanges the per-voxel
@@ -138,3 +139,20 @@ def combine_labels_staple(label_list_dict, threshold=1e-4):
         w, _info = eng.staple(dec, threshold=threshold, rescale=True)
         out[str(s_name)] = _back(eng, w, imgs[0])
     return out
+
+
+def process_probability_image(probability_image, threshold=0.5):
+    """Generate a mask given a probability image, performing some basic post processing as well
+    (fusion.py:295-328): p / max(p) -> BinaryThreshold(lowerThreshold=threshold) -> BinaryFillhole ->
+    ConnectedComponent -> largest object -> UInt8.  One device-resident call; integer work, bit-exact.
+    A numpy array is accepted like in the reference (fusion.py:301-302: identity geometry)."""
+    eng = Engine.get()
+    if isinstance(probability_image, np.ndarray):
+        probability_image = sk.Image(probability_image)
+    d = eng.to_device(probability_image)
+    if d.np_dtype not in (np.dtype(np.float32), np.dtype(np.float64)):
+        # integer probability images: the reference's image / float division keeps the integer pixel type; the fused
+        # probabilities this path produces are always Float32 (combine_labels) or Float64 (combine_labels_staple)
+        raise NotImplementedError("process_probability_image expects a Float32 or Float64 probability image")
+    mask = eng.process_probability(d, threshold)
+    return _back(eng, mask, probability_image)

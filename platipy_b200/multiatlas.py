@@ -156,13 +156,10 @@ def run_segmentation(img, atlas_set, settings=MULTIATLAS_SETTINGS_DEFAULTS, grou
         for s in structures:
             results_prob[s] = eng.vote_finalize(nums[s], dens[s], target, 1.0, 1e-4)
 
-    # ---- binary masks (run.py:370-404; fill-hole / largest-component post-processing is SURVEY 8f-2) -------
+    # ---- binary masks (run.py:370-404): process_probability_image on the device, only the masks travel ------
     results, probs_host = {}, {}
     for s in structures:
         thr = fs.get("optimal_threshold", {}).get(s, 0.5)
-        ph = eng.to_host(results_prob[s])
-        mx = float(ph.array.max())
-        mask = (ph.array / mx >= thr) if mx > 0 else np.zeros(ph.array.shape, bool)
-        results[s] = sk.Image(mask.astype(np.uint8), ph.GetSpacing(), ph.GetOrigin(), ph.GetDirection())
-        probs_host[s] = ph
+        results[s] = eng.to_host(eng.process_probability(results_prob[s], thr))
+        probs_host[s] = eng.to_host(results_prob[s])
     return results, probs_host
