@@ -199,6 +199,13 @@ int b200reg_pyramid_geom(const b200reg_geom* in_geom, int isotropic, double reso
 /* compute_weight_map: vote_type 0 = unweighted, 1 = global (factor / sum SSD), 2 = local (1/(G*SD + eps)) */
 int b200reg_weight_map(b200reg_ctx* ctx, const float* d_target, const float* d_moving, const b200reg_geom* geom, int vote_type,
                        double factor, double sigma, double epsilon, float* d_weight);
+/* vote_type "block" (fusion.py:179-200): factor * Pow(BoxMean(SSD, radius), -1) ** |gain / 2|, Float32 stages.
+ * radius = blockSize per axis (x, y, z) as passed to sitk.BoxMean. */
+int b200reg_weight_map_block(b200reg_ctx* ctx, const float* d_target, const float* d_moving, const b200reg_geom* geom,
+                             const int32_t radius[3], double factor, double gain, float* d_weight);
+/* normalise=True / normalise=<mask image> (fusion.py:171-177,196-200): weight /= max(weight) or
+ * max(sitk.Mask(weight, mask)); d_mask may be NULL.  In place, no host round trip. */
+int b200reg_normalise_by_max(b200reg_ctx* ctx, float* d_weight, const uint8_t* d_mask, size_t n);
 /* acc_num += w * label ; acc_den += w  (fusion.py:263,269-276), f32 arithmetic in atlas order */
 int b200reg_vote_accumulate(b200reg_ctx* ctx, const uint8_t* d_label, const float* d_weight, float* d_acc_num,
                             float* d_acc_den, size_t n, int first);

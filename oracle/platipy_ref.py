@@ -220,8 +220,40 @@ def fast_symmetric_forces_demons_registration(fixed_image, moving_image, resolut
     return registered, tfm, dvf
 
 
+def box_mean_f32(arr, radius_xyz):
+    """sitk.BoxMean on a Float32 [z, y, x] array: mean over the window [i - r, i + r] cropped to the image
+    (itk::BoxMeanImageFilter divides the box sum by the number of pixels inside), sums in double, Float32 result."""
+    a = arr.astype(np.float64)
+    for axis, r in zip((2, 1, 0), radius_xyz):
+        n = a.shape[axis]
+        c = np.concatenate([np.zeros_like(np.take(a, [0], axis=axis)), np.cumsum(a, axis=axis)], axis=axis)
+        idx = np.arange(n)
+        hi, lo = np.minimum(idx + r, n - 1) + 1, np.maximum(idx - r, 0)
+        a = np.take(c, hi, axis=axis) - np.take(c, lo, axis=axis)
+    cnt = np.ones((), np.float64)
+    for axis, r in zip((2, 1, 0), radius_xyz):
+        n = arr.shape[axis]
+        idx = np.arange(n)
+        ln = (np.minimum(idx + r, n - 1) - np.maximum(idx - r, 0) + 1).astype(np.float64)
+        shape = [1, 1, 1]
+        shape[axis] = n
+        cnt = cnt * ln.reshape(shape)
+    return (a / cnt).astype(np.float32)
+
+
+def _normalise(w, normalise):
+    # fusion.py:171-177: bool -> divide by the global maximum; image -> by the maximum inside the mask (sitk.Mask zeroes outside)
+    if isinstance(normalise, bool):
+        if normalise:
+            w = (w.astype(np.float64) / float(w.max())).astype(np.float32)
+        return w
+    mask = normalise.array != 0
+    mx = float(np.where(mask, w, np.float32(0)).max())
+    return (w.astype(np.float64) / mx).astype(np.float32)
+
+
 def compute_weight_map(target_image, moving_image, vote_type="unweighted", vote_params=None):
-    # fusion.py:76-80,148-177,202 (unweighted / global / local)
+    # fusion.py:76-80,148-202 (unweighted / global / local / block)
     if target_image.GetPixelID() != 6:
         target_image = sk.Cast(target_image, sk.sitkFloat32)
     if moving_image.GetPixelID() != 6:
@@ -237,9 +269,20 @@ def compute_weight_map(target_image, moving_image, vote_type="unweighted", vote_
     elif vt == "local":
         sigma, eps = vote_params["sigma"], vote_params["epsilon"]
         raw = orc.discrete_gaussian_f32(sq, orc.geom_of(target_image), sigma * sigma)
-        w = np.power((raw + np.float32(eps)).astype(np.float64), -1.0).astype(np.float32)
-        if isinstance(vote_params.get("normalise", False), bool) and vote_params.get("normalise", False):
-            w = (w / w.max()).astype(np.float32)
+        # image + double constant: sum in double, cast to Float32; sitk.Pow: std::pow in double, cast to Float32
+        w = np.power((raw.astype(np.float64) + eps).astype(np.float32).astype(np.float64), -1.0).astype(np.float32)
+        w = _normalise(w, vote_params.get("normalise", False))
+    elif vt == "block":
+        # fusion.py:179-200
+        factor, gain, block_size = vote_params["factor"], vote_params["gain"], vote_params["blockSize"]
+        if isinstance(block_size, int):
+            block_size = (block_size,) * 3
+        raw = box_mean_f32(sq, block_size)
+        with np.errstate(divide="ignore", over="ignore", invalid="ignore"):
+            inv = np.power(raw.astype(np.float64), -1.0).astype(np.float32)
+            pw = np.power(inv.astype(np.float64), abs(gain / 2.0)).astype(np.float32)
+            w = (pw.astype(np.float64) * factor).astype(np.float32)
+        w = _normalise(w, vote_params.get("normalise", False))
     else:
         raise NotImplementedError(vote_type)
     return _like(w, target_image)

@@ -88,6 +88,8 @@ SIGNATURES = {
                                             C.POINTER(DemonsStats)]),
     "b200reg_pyramid_geom": (C.c_int, [C.POINTER(Geom), C.c_int, C.c_double, C.POINTER(Geom)]),
     "b200reg_weight_map": (C.c_int, [_P, _P, _P, C.POINTER(Geom), C.c_int, C.c_double, C.c_double, C.c_double, _P]),
+    "b200reg_weight_map_block": (C.c_int, [_P, _P, _P, C.POINTER(Geom), C.POINTER(C.c_int32), C.c_double, C.c_double, _P]),
+    "b200reg_normalise_by_max": (C.c_int, [_P, _P, _P, C.c_size_t]),
     "b200reg_vote_accumulate": (C.c_int, [_P, _P, _P, _P, _P, C.c_size_t, C.c_int]),
     "b200reg_vote_finalize": (C.c_int, [_P, _P, _P, C.POINTER(Geom), C.c_double, C.c_double, _P]),
     "b200reg_binary_threshold": (C.c_int, [_P, _P, C.c_int, C.c_size_t, C.c_double, C.c_double, _P]),

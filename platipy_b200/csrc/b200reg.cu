@@ -548,6 +548,20 @@ API int b200reg_weight_map(b200reg_ctx* ctx, const float* d_target, const float*
     REQUIRE(d_target && d_moving && d_weight && valid_geom(geom), "invalid argument");
     return weight_map(ctx, d_target, d_moving, *geom, vote_type, factor, sigma, epsilon, d_weight);
 }
+API int b200reg_weight_map_block(b200reg_ctx* ctx, const float* d_target, const float* d_moving, const b200reg_geom* geom, const int32_t radius[3],
+                                 double factor, double gain, float* d_weight)
+{
+    ENTER(ctx);
+    REQUIRE(d_target && d_moving && d_weight && radius && valid_geom(geom), "invalid argument");
+    REQUIRE(radius[0] >= 0 && radius[1] >= 0 && radius[2] >= 0, "negative block radius");
+    return weight_map_block(ctx, d_target, d_moving, *geom, radius, factor, gain, d_weight);
+}
+API int b200reg_normalise_by_max(b200reg_ctx* ctx, float* d_weight, const uint8_t* d_mask, size_t n)
+{
+    ENTER(ctx);
+    REQUIRE(d_weight && n > 0, "invalid argument");
+    return normalise_by_max(ctx, d_weight, d_mask, n);
+}
 API int b200reg_vote_accumulate(b200reg_ctx* ctx, const uint8_t* d_label, const float* d_weight, float* d_acc_num, float* d_acc_den, size_t n,
                                 int first)
 {

@@ -175,6 +175,90 @@ inline int weight_map(b200reg_ctx* ctx, const float* d_target, const float* d_mo
     return B200REG_OK;
 }
 
+// ---- compute_weight_map, vote_type "block" (fusion.py:179-200) ------------------------------------------
+// sitk.BoxMean(square_difference, radius): mean over the window [i - r, i + r] cropped to the image (itk::BoxMeanImageFilter
+// divides by the number of pixels inside), accumulated in double (NumericTraits<float>::RealType).  ITK sums through an
+// integral image; here the window is summed directly, separably, which differs from it only by double rounding.
+template <typename TIN>
+__global__ void __launch_bounds__(256) box_sum_axis_kernel(const TIN* __restrict__ in, double* __restrict__ out, int nx, int ny, int nz, int axis, int r)
+{
+    const size_t n = (size_t)nx * ny * nz;
+    const int dims[3] = { nx, ny, nz };
+    const size_t strides[3] = { 1, (size_t)nx, (size_t)nx * ny };
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) {
+        const int idx[3] = { (int)(q % nx), (int)((q / nx) % ny), (int)(q / ((size_t)nx * ny)) };
+        const int c = idx[axis], lo = max(c - r, 0), hi = min(c + r, dims[axis] - 1);
+        const size_t base = q - (size_t)c * strides[axis];
+        double s = 0.0;
+        for (int t = lo; t <= hi; ++t) s += (double)in[base + (size_t)t * strides[axis]];
+        out[q] = s;
+    }
+}
+// raw = float(sum / count); weight = factor * Pow(raw, -1.0) ** |gain / 2|, every stage a Float32 image (fusion.py:191-192)
+__global__ void __launch_bounds__(256) block_weight_kernel(const double* __restrict__ sum, float* __restrict__ out, int nx, int ny, int nz, int rx, int ry,
+                                                           int rz, double factor, double half_gain)
+{
+    const size_t n = (size_t)nx * ny * nz;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(q % nx), y = (int)((q / nx) % ny), z = (int)(q / ((size_t)nx * ny));
+        const double cnt = (double)(min(x + rx, nx - 1) - max(x - rx, 0) + 1) * (double)(min(y + ry, ny - 1) - max(y - ry, 0) + 1) *
+                           (double)(min(z + rz, nz - 1) - max(z - rz, 0) + 1);
+        const float raw = (float)(sum[q] / cnt);
+        const float inv = (float)pow((double)raw, -1.0);
+        const float pw = (float)pow((double)inv, half_gain);
+        out[q] = (float)((double)pw * factor);
+    }
+}
+inline int weight_map_block(b200reg_ctx* ctx, const float* d_target, const float* d_moving, const b200reg_geom& g, const int32_t radius[3],
+                            double factor, double gain, float* d_weight)
+{
+    const size_t n = nvox(g);
+    const int nb = ctx->sm_count * 8;
+    const int nx = g.size[0], ny = g.size[1], nz = g.size[2];
+    TempBuf sq, s1, s2;
+    B200_TRY(sq.alloc(ctx, n * sizeof(float)));
+    B200_TRY(s1.alloc(ctx, n * sizeof(double)));
+    B200_TRY(s2.alloc(ctx, n * sizeof(double)));
+    sqdiff_kernel<<<nb, 256, 0, ctx->stream>>>(d_target, d_moving, sq.as<float>(), n);
+    box_sum_axis_kernel<float><<<nb, 256, 0, ctx->stream>>>(sq.as<float>(), s1.as<double>(), nx, ny, nz, 0, radius[0]);
+    box_sum_axis_kernel<double><<<nb, 256, 0, ctx->stream>>>(s1.as<double>(), s2.as<double>(), nx, ny, nz, 1, radius[1]);
+    box_sum_axis_kernel<double><<<nb, 256, 0, ctx->stream>>>(s2.as<double>(), s1.as<double>(), nx, ny, nz, 2, radius[2]);
+    block_weight_kernel<<<nb, 256, 0, ctx->stream>>>(s1.as<double>(), d_weight, nx, ny, nz, radius[0], radius[1], radius[2], factor, fabs(gain / 2.0));
+    ctx->launches += 5;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+
+// weight_map / max(weight_map) or / max(sitk.Mask(weight_map, mask)) (fusion.py:171-177,196-200): Float32 / double constant
+__global__ void __launch_bounds__(256) mask_f32_kernel(const float* __restrict__ in, const uint8_t* __restrict__ mask, float* __restrict__ out, size_t n)
+{
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) out[q] = mask[q] ? in[q] : 0.0f;
+}
+__global__ void __launch_bounds__(256) divide_by_max_kernel(float* __restrict__ io, const double* __restrict__ d_minmax, size_t n)
+{
+    const double mx = d_minmax[1];
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x)
+        io[q] = mx != 0.0 ? (float)((double)io[q] / mx) : FLT_MAX;  // itk::Functor::Div: B == 0 -> NumericTraits<float>::max()
+}
+inline int normalise_by_max(b200reg_ctx* ctx, float* d_weight, const uint8_t* d_mask, size_t n)
+{
+    const int nb = ctx->sm_count * 8;
+    TempBuf part, mm, masked;
+    B200_TRY(mm.alloc(ctx, 2 * sizeof(double)));
+    const float* src = d_weight;
+    if (d_mask) {
+        B200_TRY(masked.alloc(ctx, n * sizeof(float)));
+        mask_f32_kernel<<<nb, 256, 0, ctx->stream>>>(d_weight, d_mask, masked.as<float>(), n);
+        ctx->launches++;
+        src = masked.as<float>();
+    }
+    B200_TRY(minmax_device<float>(ctx, src, n, mm.as<double>(), &part));
+    divide_by_max_kernel<<<nb, 256, 0, ctx->stream>>>(d_weight, mm.as<double>(), n);
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+
 // ---- combine_labels (fusion.py:253-288) ---------------------------------------------------------------
 // float32 arithmetic in atlas order: num = sum_a w_a * float(L_a), den = sum_a w_a
 __global__ void vote_accumulate_kernel(const uint8_t* __restrict__ label, const float* __restrict__ w, float* __restrict__ num,

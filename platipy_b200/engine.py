@@ -365,6 +365,18 @@ class Engine:
                                                float(epsilon), C.c_void_p(out.data_ptr())))
         return target.like(out, np.float32, False)
 
+    def weight_map_block(self, target, moving, radius, factor, gain):
+        out = self.empty(target.tensor.shape, np.float32)
+        g = target.geom
+        r = (C.c_int32 * 3)(*[int(v) for v in radius])
+        _abi.check(self.lib.b200reg_weight_map_block(self.ctx, target.ptr, moving.ptr, C.byref(g), r, float(factor), float(gain),
+                                                     C.c_void_p(out.data_ptr())))
+        return target.like(out, np.float32, False)
+
+    def normalise_by_max(self, weight, mask=None):
+        _abi.check(self.lib.b200reg_normalise_by_max(self.ctx, weight.ptr, mask.ptr if mask is not None else None, weight.tensor.numel()))
+        return weight
+
     def vote_accumulate(self, label, weight, num, den, first):
         _abi.check(self.lib.b200reg_vote_accumulate(self.ctx, label.ptr, weight.ptr, C.c_void_p(num.data_ptr()),
                                                     C.c_void_p(den.data_ptr()) if den is not None else None, label.tensor.numel(), int(bool(first))))

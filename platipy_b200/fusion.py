@@ -1,7 +1,7 @@
 """
 Drop-in replacements for the reference's label-fusion entry points (platipy/imaging/label/fusion.py):
 
-    compute_weight_map      fusion.py:56-202   (vote types: unweighted, global, local)
+    compute_weight_map      fusion.py:56-202   (vote types: unweighted, global, local, block; normalise)
     combine_labels          fusion.py:239-292  (weighted vote -> DiscreteGaussian -> RescaleIntensity -> Threshold)
     combine_labels_staple   fusion.py:205-236  (BinaryThreshold -> STAPLE -> RescaleIntensity -> Threshold)
     process_probability_image fusion.py:295-328 (normalise -> BinaryThreshold -> BinaryFillhole -> largest component)
@@ -37,26 +37,41 @@ def _back(eng, dimg, like):
 
 
 def compute_weight_map(target_image, moving_image, vote_type="unweighted", vote_params=DEFAULT_VOTE_PARAMS):
-    """Weight map of one atlas (fusion.py:56-202).  ``vote_params=None`` is valid for ``unweighted`` only,
+    """Weight map of one atlas (fusion.py:56-202): ``unweighted``, ``global``, ``local`` and ``block`` votes, with the
+    ``normalise`` option (bool or mask image) of the last two.  ``vote_params=None`` is valid for ``unweighted`` only,
     as in the reference (multiatlas/run.py:92-96)."""
     eng = Engine.get()
     vt = vote_type.lower()
-    if vt not in VOTE_TYPES:
-        # block / patch_correlation: SURVEY 8f-3 ("next")
-        raise NotImplementedError(f"vote_type {vote_type!r} is not implemented on the B200 path (unweighted, global, local are)")
+    if vt not in VOTE_TYPES and vt != "block":
+        # patch_correlation (fusion.py:82-146) is a host-side scipy / skimage loop in the reference: SURVEY 8f-3 ("next")
+        raise NotImplementedError(f"vote_type {vote_type!r} is not implemented on the B200 path (unweighted, global, local, block are)")
     t, m = eng.to_device(target_image), eng.to_device(moving_image)
     # fusion.py:76-80: cast to Float32 unless the pixel id is 6
     t, m = eng.cast(t, np.float32), eng.cast(m, np.float32)
     if t.GetSize() != m.GetSize():
         raise RuntimeError("compute_weight_map: target and moving images do not occupy the same grid")
-    factor = sigma = eps = 0.0
-    if vt == "global":
-        factor = float(vote_params["factor"])
-    elif vt == "local":
-        sigma, eps = float(vote_params["sigma"]), float(vote_params["epsilon"])
-        if vote_params.get("normalise", False) is not False:
-            raise NotImplementedError("normalise=True / mask for local weight maps is not implemented on the B200 path")
-    w = eng.weight_map(t, m, VOTE_TYPES[vt], factor=factor, sigma=sigma, epsilon=eps)
+    normalise = False
+    if vt == "block":
+        factor, gain, block_size = float(vote_params["factor"]), float(vote_params["gain"]), vote_params["blockSize"]
+        normalise = vote_params["normalise"]
+        if isinstance(block_size, int):
+            block_size = (block_size,) * 3  # fusion.py:185-186
+        w = eng.weight_map_block(t, m, block_size, factor, gain)
+    else:
+        factor = sigma = eps = 0.0
+        if vt == "global":
+            factor = float(vote_params["factor"])
+        elif vt == "local":
+            sigma, eps = float(vote_params["sigma"]), float(vote_params["epsilon"])
+            normalise = vote_params["normalise"]
+        w = eng.weight_map(t, m, VOTE_TYPES[vt], factor=factor, sigma=sigma, epsilon=eps)
+    # fusion.py:171-177,196-200
+    if isinstance(normalise, bool):
+        if normalise:
+            eng.normalise_by_max(w)
+    else:
+        mask = eng.cast(eng.to_device(normalise), np.uint8)
+        eng.normalise_by_max(w, mask)
     return _back(eng, w, target_image)
 
 

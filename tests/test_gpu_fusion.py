@@ -45,7 +45,29 @@ def test_weight_maps_match_oracle(engine):
             assert np.array_equal(got.array, exp.array)
     assert np.array_equal(fusion.compute_weight_map(t, m, "unweighted", None).array, np.ones(t.array.shape, np.float32))
     with pytest.raises(NotImplementedError):
-        fusion.compute_weight_map(t, m, "block", params)
+        fusion.compute_weight_map(t, m, "patch_correlation", params)
+
+
+def test_block_weight_map_and_normalise_match_oracle(engine):
+    """vote_type "block" (fusion.py:179-200: BoxMean -> Pow -> ** |gain/2| -> * factor) and the normalise option
+    (bool / mask image, fusion.py:171-177,196-200).  Float32 stages; tolerance = the north star's 1e-5 relative
+    (device pow() is not bit-identical to libm, the box sums differ from ITK's integral image by double rounding)."""
+    t, m = synth_pair((40, 36, 20), seed=52, spacing=(1.0, 1.0, 2.0))
+    mask = Image((np.random.default_rng(2).random(t.array.shape) > 0.7).astype(np.uint8), t.GetSpacing())
+    for block, gain, normalise in ((5, 6, False), ((2, 3, 1), 4, False), (3, 6, True), (1, 2, mask), (0, 6, False)):
+        params = {"factor": 1e12, "gain": gain, "blockSize": block, "normalise": normalise}
+        got = fusion.compute_weight_map(t, m, "block", params)
+        exp = ref.compute_weight_map(t, m, "block", params)
+        assert got.GetPixelID() == sk.sitkFloat32
+        assert np.all(np.isfinite(exp.array))
+        assert np.allclose(got.array, exp.array, rtol=REL_TOL, atol=0), (block, gain)
+    for normalise in (True, mask):
+        params = {"sigma": 2.0, "epsilon": 1e-5, "normalise": normalise}
+        got = fusion.compute_weight_map(t, m, "local", params)
+        exp = ref.compute_weight_map(t, m, "local", params)
+        assert np.allclose(got.array, exp.array, rtol=REL_TOL, atol=0)
+        if normalise is True:
+            assert got.array.max() == 1.0
 
 
 def test_combine_labels_bit_exact(engine):

@@ -67,3 +67,14 @@ def test_process_probability_image_steps():
     exp[1:5, 2:9, 2:9] = 1     # hole filled, small object (0.4 / 0.8 = 0.5 >= 0.45) removed as the smaller component
     assert np.array_equal(out.array, exp)
     assert ref.process_probability_image(np.zeros((3, 4, 5), np.float32)).array.sum() == 0
+
+
+def test_box_mean_matches_scipy_cropped_window():
+    # sitk.BoxMean (fusion.py:190): window cropped at the border, divided by the pixels inside
+    a = np.random.default_rng(0).random((9, 12, 14)).astype(np.float32)
+    got = ref.box_mean_f32(a, (2, 3, 1))  # radius (x, y, z)
+    size = (3, 7, 5)                      # scipy window (z, y, x)
+    s = ndi.uniform_filter(a.astype(np.float64), size=size, mode="constant", cval=0.0)
+    c = ndi.uniform_filter(np.ones(a.shape), size=size, mode="constant", cval=0.0)
+    assert np.allclose(got, (s / c).astype(np.float32), rtol=3e-7, atol=0)
+    assert np.array_equal(ref.box_mean_f32(a, (0, 0, 0)), a)
