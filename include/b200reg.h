@@ -240,6 +240,19 @@ int b200reg_largest_component(b200reg_ctx* ctx, const uint8_t* d_in, const int32
 int b200reg_process_probability(b200reg_ctx* ctx, const void* d_prob, int dtype, const int32_t size[3], double threshold,
                                 uint8_t* d_out, int64_t* h_n_components);
 
+/* ---- linear_registration (linear.py:50-260): sitk.ImageRegistrationMethod metric evaluation ---------------------- */
+/* MeanSquares metric with linear interpolation over every `stride`-th fixed voxel in raster order (REGULAR sampling,
+ * linear.py:150-152), optional fixed / moving masks (linear.py:159-163; u8 volumes on the fixed / moving grid).
+ * The point map is y = total_matrix x + total_offset (optimised transform followed by the moving-initial transform,
+ * linear.py:135-138); initial_matrix is the moving-initial transform's matrix and center the optimised transform's
+ * centre.  h_out (after a stream synchronisation): [0] sum of squared differences, [1] number of valid samples,
+ * [2..4] s = sum w, [5..13] S = sum w (x - center)^T row-major, w = 2 (M - F) initial_matrix^T grad M:
+ * d(sum sq)/d(translation) = s, d(sum sq)/d(matrix parameter k) = <dR/dp_k, S>. */
+int b200reg_linreg_meansq(b200reg_ctx* ctx, const float* d_fixed, const b200reg_geom* fixed_geom, const float* d_moving,
+                          const b200reg_geom* moving_geom, const double total_matrix[9], const double total_offset[3],
+                          const double initial_matrix[9], const double center[3], const uint8_t* d_fixed_mask,
+                          const uint8_t* d_moving_mask, int stride, double h_out[14]);
+
 #ifdef __cplusplus
 }
 #endif

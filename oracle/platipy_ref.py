@@ -334,3 +334,59 @@ def process_probability_image(probability_image, threshold=0.5):
     if ncomp == 0:
         return _like(binary, probability_image)                # fusion.py:322-323
     return _like(largest, probability_image)
+
+
+def linreg_meansq(fixed, moving, total_matrix, total_offset, initial_matrix, center, fixed_mask=None, moving_mask=None, stride=1):
+    """Mean-squares metric sums of linear_registration (linear.py:141-163: SetMetricAsMeanSquares, linear interpolator,
+    REGULAR sampling, optional masks), restated in numpy for every ``stride``-th fixed voxel in raster order:
+    [sum (M - F)^2, count, s (3), S (9 row-major)] with w = 2 (M - F) initial_matrix^T grad M, s = sum w,
+    S = sum w (x - center)^T.  Points mapping outside the moving buffer ([-0.5, size - 0.5), as
+    ImageFunction::IsInsideBuffer) or outside a mask are skipped."""
+    F, M = fixed.array.astype(np.float64), moving.array.astype(np.float64)
+    nz, ny, nx = F.shape
+    q = np.arange(0, F.size, int(stride))
+    k, j, i = np.unravel_index(q, F.shape)
+    keep = np.ones(q.shape, bool)
+    if fixed_mask is not None:
+        keep &= fixed_mask.array.reshape(-1)[q] != 0
+    df = np.asarray(fixed.GetDirection(), np.float64).reshape(3, 3)
+    idx = np.stack([i, j, k], axis=1).astype(np.float64)
+    x = (idx * np.asarray(fixed.GetSpacing())) @ df.T + np.asarray(fixed.GetOrigin())
+    y = x @ np.asarray(total_matrix, np.float64).reshape(3, 3).T + np.asarray(total_offset, np.float64)
+    dm = np.asarray(moving.GetDirection(), np.float64).reshape(3, 3)
+    i2p = dm * np.asarray(moving.GetSpacing())[None, :]
+    p2i = np.linalg.inv(i2p)
+    c = (y - np.asarray(moving.GetOrigin())) @ p2i.T
+    mz, my, mx = M.shape
+    size = np.array([mx, my, mz], np.float64)
+    keep &= np.all((c >= -0.5) & (c < size - 0.5), axis=1)
+    if moving_mask is not None:
+        r = np.floor(np.where(keep[:, None], c, 0.0) + 0.5).astype(np.int64)
+        keep &= moving_mask.array[r[:, 2], r[:, 1], r[:, 0]] != 0
+    c, x, fv = c[keep], x[keep], F.reshape(-1)[q][keep]
+    cc = np.maximum(c, 0.0)                      # LinearInterpolateImageFunction: base clamped up to 0, distance 0 there
+    b = np.floor(cc).astype(np.int64)
+    d = cc - b
+    u = np.minimum(b + 1, (size - 1).astype(np.int64))
+    b = np.minimum(b, (size - 1).astype(np.int64))
+    g = lambda zz, yy, xx: M[zz, yy, xx]
+    v000, v100 = g(b[:, 2], b[:, 1], b[:, 0]), g(b[:, 2], b[:, 1], u[:, 0])
+    v010, v110 = g(b[:, 2], u[:, 1], b[:, 0]), g(b[:, 2], u[:, 1], u[:, 0])
+    v001, v101 = g(u[:, 2], b[:, 1], b[:, 0]), g(u[:, 2], b[:, 1], u[:, 0])
+    v011, v111 = g(u[:, 2], u[:, 1], b[:, 0]), g(u[:, 2], u[:, 1], u[:, 0])
+    d0, d1, d2 = d[:, 0], d[:, 1], d[:, 2]
+    a00, a10, a01, a11 = v100 - v000, v110 - v010, v101 - v001, v111 - v011
+    vx00, vx10, vx01, vx11 = v000 + a00 * d0, v010 + a10 * d0, v001 + a01 * d0, v011 + a11 * d0
+    vxx0, vxx1 = vx00 + (vx10 - vx00) * d1, vx01 + (vx11 - vx01) * d1
+    mval = vxx0 + (vxx1 - vxx0) * d2
+    gx0, gx1 = a00 + (a10 - a00) * d1, a01 + (a11 - a01) * d1
+    gi = np.stack([gx0 + (gx1 - gx0) * d2, (vx10 - vx00) + ((vx11 - vx01) - (vx10 - vx00)) * d2, vxx1 - vxx0], axis=1)
+    gy = gi @ p2i                                 # d/dy_j = sum_i g_i P2I[i][j]
+    h = gy @ np.asarray(initial_matrix, np.float64).reshape(3, 3)   # A_i^T gy, row-vector form
+    dd = mval - fv
+    w = 2.0 * dd[:, None] * h
+    out = np.zeros(14)
+    out[0], out[1] = float((dd * dd).sum()), float(dd.size)
+    out[2:5] = w.sum(axis=0)
+    out[5:14] = (w[:, :, None] * (x - np.asarray(center, np.float64))[:, None, :]).sum(axis=0).reshape(9)
+    return out

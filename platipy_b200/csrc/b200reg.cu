@@ -6,6 +6,7 @@
 #include "deriche.cuh"
 #include "fusion.cuh"
 #include "morph.cuh"
+#include "linreg.cuh"
 #include "gauss.cuh"
 #include "resample.cuh"
 
@@ -771,4 +772,26 @@ API int b200reg_process_probability(b200reg_ctx* ctx, const void* d_prob, int dt
         *h_n_components = (int64_t)h[1];
     }
     return B200REG_OK;
+}
+
+// ---- f1: linear_registration (linear.py:50-260), mean-squares metric + derivative accumulators -------------------------
+API int b200reg_linreg_meansq(b200reg_ctx* ctx, const float* d_fixed, const b200reg_geom* fixed_geom, const float* d_moving,
+                              const b200reg_geom* moving_geom, const double total_matrix[9], const double total_offset[3],
+                              const double initial_matrix[9], const double center[3], const uint8_t* d_fixed_mask, const uint8_t* d_moving_mask,
+                              int stride, double h_out[14])
+{
+    ENTER(ctx);
+    REQUIRE(d_fixed && d_moving && valid_geom(fixed_geom) && valid_geom(moving_geom) && total_matrix && total_offset && initial_matrix && center && h_out,
+            "invalid argument");
+    REQUIRE(stride >= 1, "sampling stride must be >= 1");
+    LinRegPose ps;
+    for (int r = 0; r < 3; ++r) {
+        ps.b[r] = total_offset[r];
+        ps.c[r] = center[r];
+        for (int c = 0; c < 3; ++c) {
+            ps.A[r * 3 + c] = total_matrix[r * 3 + c];
+            ps.Bt[r * 3 + c] = initial_matrix[c * 3 + r];
+        }
+    }
+    return linreg_meansq(ctx, d_fixed, *fixed_geom, d_moving, *moving_geom, ps, d_fixed_mask, d_moving_mask, stride, h_out);
 }

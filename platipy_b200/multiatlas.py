@@ -11,9 +11,11 @@ they are partitioned over the ranks of a ``torch.distributed`` process group (at
     STAPLE          int32 bit mask, bit a = decision of atlas a (sum == OR, bits are disjoint) (4 B/voxel/structure)
 
 followed by the replicated finalisation (normalise -> DiscreteGaussian -> rescale -> threshold, or the
-STAPLE EM).  A single Demons registration is not sharded.  The linear pre-registration stage of the
-reference pipeline (run.py:261-300) is outside this path: atlases are expected on the target
-grid already (the state after ``apply_transform`` with the rigid transform).
+STAPLE EM) and ``process_probability_image``.  A single Demons registration is not sharded.  With
+``settings["linear_registration_settings"]`` the atlases may live in their own space and are first aligned with
+``linear_registration`` (run.py:261-300); without it they are expected on the target grid already (the state
+after ``apply_transform`` with the rigid transform).  The auto-crop of run.py:200-259 is not performed: it only
+shrinks the working domain of the reference's CPU pipeline.
 
 ``shard_atlases`` / ``exchange_sum`` are plain host logic and are exercised on CPU with the gloo backend.
 """
@@ -73,6 +75,24 @@ def _dist_info(group=None):
     return 0, 1
 
 
+def rigid_align_atlas(target, atlas_ct, atlas_labels, settings):
+    """Step 2 of the reference pipeline for one atlas (run.py:261-300): linear_registration of the atlas CT to the
+    target, then the CT (linear, -1000) and every structure (nearest neighbour, 0) through that transform onto the
+    target grid, in one batched pass.  Returns ``(ct, {structure: label}, transform)`` as device images."""
+    from . import linear
+    from . import registration as reg
+    from .engine import Engine
+
+    eng = Engine.get()
+    t, m = eng.to_device(target), eng.to_device(atlas_ct)
+    kw = {k: v for k, v in settings["linear_registration_settings"].items()}
+    _, tfm = linear.linear_registration(t, m, **kw)
+    names = list(atlas_labels)
+    imgs = [m] + [eng.to_device(atlas_labels[n]) for n in names]
+    outs = reg.apply_transform_batch(imgs, t, tfm, [-1000] + [0] * len(names), [sk.sitkLinear] + [sk.sitkNearestNeighbor] * len(names))
+    return outs[0], dict(zip(names, outs[1:])), tfm
+
+
 def register_atlas(target, atlas_ct, atlas_labels, settings):
     """Steps 3 of the reference pipeline for one atlas (run.py:312-347), device resident: Demons registration
     of the atlas CT to the target, then the CT (linear, -1000) and every label (nearest neighbour, 0) through
@@ -122,7 +142,11 @@ def run_segmentation(img, atlas_set, settings=MULTIATLAS_SETTINGS_DEFAULTS, grou
     local = {}
     for a in mine:
         labels = {k: v for k, v in atlas_set[a].items() if k != "CT Image"}
-        d = register_atlas(target, atlas_set[a]["CT Image"], labels, settings)
+        ct = atlas_set[a]["CT Image"]
+        if settings.get("linear_registration_settings"):
+            # run.py:261-300: atlases arrive in their own space and are first aligned linearly
+            ct, labels, _ = rigid_align_atlas(target, ct, labels, settings)
+        d = register_atlas(target, ct, labels, settings)
         d["Weight Map"] = fusion.compute_weight_map(tgt_f32, eng.cast(d["CT Image"], np.float32), vote_type, vote_params)
         local[a] = {"DIR": d}
 

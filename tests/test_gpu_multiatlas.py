@@ -66,3 +66,40 @@ def test_run_segmentation_matches_oracle_pipeline(engine, fusion_mode):
         # (bit-exact integer post-processing; the STAPLE map itself carries the 1e-9 reduction-order tolerance)
         thr = settings["label_fusion_settings"]["optimal_threshold"].get(s, 0.5)
         assert np.array_equal(results[s].array, ref.process_probability_image(probs[s], thr).array), s
+
+
+def test_run_segmentation_with_linear_prealignment(engine):
+    """Atlases in their own space (shifted / rotated copies): linear_registration -> label propagation -> Demons ->
+    fusion -> process_probability_image (multiatlas/run.py:261-404).  Functional bar of the reference's own test
+    (platipy/imaging/tests/test_cardiac.py:231,237): Dice > 0.9 against the structure the atlases were made from."""
+    from platipy_b200 import registration as reg
+    from platipy_b200 import linear
+
+    size, sp = (96, 64, 48), (1.0, 1.0, 1.5)
+    target, _ = synth_pair(size, seed=3, spacing=sp, peak_mm=2.0)
+    truth = [Image(l, sp) for l in synth_labels(size, 2, seed=520)]
+    c = linear.image_center(target)
+    atlas_set = {}
+    for a, (ang, shift) in enumerate([(0.04, (3.0, -2.0, 1.5)), (-0.03, (-2.5, 2.0, -1.0)), (0.02, (1.0, 3.0, 2.0))]):
+        ca, sa = np.cos(ang), np.sin(ang)
+        t = sk.AffineTransform([[ca, -sa, 0], [sa, ca, 0], [0, 0, 1]], shift, c)
+        inv = sk.AffineTransform(np.linalg.inv(t.matrix), -np.linalg.inv(t.matrix) @ t.offset, (0, 0, 0))
+        _, ct = synth_pair(size, seed=3, spacing=sp, peak_mm=2.0, moving_seed=200 + a)  # target anatomy, deformed a little
+        entry = {"CT Image": reg.apply_transform(ct, target, inv, -1000, sk.sitkLinear)}
+        for k, lab in enumerate(truth):
+            entry[f"S{k}"] = reg.apply_transform(lab, target, inv, 0, sk.sitkNearestNeighbor)
+        atlas_set[f"{a:03d}"] = entry
+    settings = {
+        "linear_registration_settings": {"reg_method": "rigid", "shrink_factors": [4, 2], "smooth_sigmas": [2, 1], "sampling_rate": 0.5,
+                                         "default_value": -1000, "number_of_iterations": 50, "metric": "mean_squares",
+                                         "optimiser": "gradient_descent_line_search", "verbose": False},
+        "deformable_registration_settings": {"isotropic_resample": False, "resolution_staging": [2, 1], "iteration_staging": [20, 10],
+                                             "ncores": 8, "default_value": -1000, "verbose": False},
+        "label_fusion_settings": {"vote_type": "unweighted", "vote_params": None, "optimal_threshold": {}, "fusion": "vote"},
+    }
+    results, probs = multiatlas.run_segmentation(target, atlas_set, settings)
+    for k, lab in enumerate(truth):
+        a, b = results[f"S{k}"].array > 0, lab.array > 0
+        dice = 2.0 * (a & b).sum() / max(a.sum() + b.sum(), 1)
+        print(f"S{k}: Dice {dice:.3f}")
+        assert dice > 0.9, (k, dice)

@@ -1,0 +1,137 @@
+"""CPU tests of linear_registration's host logic (platipy_b200/linear.py: transform parameterisations, scales from
+physical shift, learning-rate estimation, convergence window, pyramid geometry) -- the optimiser is driven by the
+oracle's numpy metric here (test infrastructure), on the GPU box by b200reg_linreg_meansq."""
+import numpy as np
+import pytest
+
+from oracle import platipy_ref as ref
+from platipy_b200 import linear
+from platipy_b200 import sitk_compat as sk
+from platipy_b200.sitk_compat import Image
+
+
+def _fd(model, p, eps=1e-6):
+    out = []
+    for k in range(model.n):
+        d = np.zeros(model.n)
+        d[k] = eps
+        out.append((model.matrix(p + d) - model.matrix(p - d)) / (2 * eps))
+    return out
+
+
+def test_matrix_derivatives_match_finite_differences():
+    rng = np.random.default_rng(0)
+    for name in ("rigid", "similarity", "affine", "scale"):
+        m = linear.make_model(name)
+        p = m.identity() + 0.1 * rng.standard_normal(m.n)
+        fd = _fd(m, p)
+        got = dict(m.matrix_bases(p))
+        for k in range(m.n):
+            exp = fd[k]
+            if k in got:
+                assert np.allclose(got[k], exp, atol=1e-7), (name, k)
+            else:
+                assert np.allclose(exp, 0, atol=1e-9), (name, k)  # translation parameters do not move the matrix
+
+
+def test_versor_update_composes_rotations():
+    m = linear.make_model("rigid")
+    p = m.identity()
+    p = m.updated(p, np.array([0, 0, 0.3, 1.0, 2.0, 3.0]))  # angle 0.3 about z, translation added
+    c, s = np.cos(0.3), np.sin(0.3)
+    assert np.allclose(m.matrix(p), [[c, -s, 0], [s, c, 0], [0, 0, 1]])
+    assert np.allclose(m.translation(p), [1, 2, 3])
+    p2 = m.updated(p, np.array([0, 0, 0.2, 0, 0, 0]))
+    c, s = np.cos(0.5), np.sin(0.5)
+    assert np.allclose(m.matrix(p2), [[c, -s, 0], [s, c, 0], [0, 0, 1]])
+    r = m.matrix(m.updated(p2, np.array([0.4, -0.2, 0.1, 0, 0, 0])))
+    assert np.allclose(r @ r.T, np.eye(3), atol=1e-12) and np.isclose(np.linalg.det(r), 1.0)
+
+
+def test_shrink_grid_and_initialiser():
+    im = Image(np.zeros((32, 40, 64), np.float32), (1.0, 1.5, 2.5), (10.0, -5.0, 3.0))
+    g = linear.shrink_grid(im, 8)
+    assert g.GetSize() == (8, 5, 4) and g.GetSpacing() == (8.0, 12.0, 20.0)
+    assert np.allclose(linear.image_center(g), linear.image_center(im))  # ShrinkImageFilter keeps the physical centre
+    mv = Image(np.zeros((10, 10, 10), np.float32), (2.0, 2.0, 2.0), (100.0, 0.0, 0.0))
+    t = linear.centered_transform_initializer(im, mv)
+    assert np.allclose(t.TransformPoint(linear.image_center(im)), linear.image_center(mv))
+    with pytest.raises(ValueError):
+        linear.make_model("nonsense")
+    with pytest.raises(NotImplementedError):
+        linear.make_model("ScaleSkewVersor")
+
+
+def test_scales_and_convergence_value():
+    m = linear.make_model("similarity")
+    corners = linear.image_corners(Image(np.zeros((50, 100, 200), np.float32)))
+    sc = linear.estimate_scales(m, m.identity(), corners)
+    assert np.allclose(sc[3:6], 1.0)  # a unit translation shifts every point by one unit
+    far = np.linalg.norm(corners, axis=1).max()
+    assert np.isclose(sc[6], far ** 2, rtol=1e-6)  # scaling about the origin moves the farthest corner by its distance
+    assert sc[0] > 1e3
+    assert linear.convergence_value([5.0] * 10) == pytest.approx(0.0, abs=1e-12)
+    assert linear.convergence_value(list(np.linspace(10, 1, 10))) > 1e-2
+
+
+def _blob_image(size, center, spacing=(1.0, 1.0, 1.0), sig=(7.0, 5.0, 4.0)):
+    nx, ny, nz = size
+    z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    p = [x * spacing[0], y * spacing[1], z * spacing[2]]
+    v = sum(((pi - ci) / si) ** 2 for pi, ci, si in zip(p, center, sig))
+    return Image((1000.0 * np.exp(-0.5 * v)).astype(np.float32), spacing)
+
+
+def test_metric_gradient_is_the_derivative_of_the_value():
+    f = _blob_image((24, 20, 16), (12.0, 10.0, 8.0))
+    # the moving grid is larger than the fixed one, so every sample stays inside the buffer and the sample count
+    # does not depend on the parameters (ITK's derivative ignores that dependence as well)
+    big = _blob_image((36, 32, 28), (19.5, 15.0, 14.5))
+    mv = Image(big.array, big.GetSpacing(), (-6.0, -6.0, -6.0))
+    init = linear.centered_transform_initializer(f, mv)
+    for name in ("translation", "rigid", "similarity", "affine"):
+        m = linear.make_model(name)
+        rng = np.random.default_rng(3)
+        p = m.identity() + 0.01 * rng.standard_normal(m.n)
+
+        def value(q):
+            acc = ref.linreg_meansq(f, mv, init.matrix @ m.matrix(q), init.matrix @ m.offset(q) + init.offset, init.matrix, m.center)
+            return acc[0] / acc[1], acc
+
+        v0, acc = value(p)
+        g = m.gradient(acc, p)
+        for k in range(m.n):
+            d = np.zeros(m.n)
+            d[k] = 1e-5
+            fd = (value(p + d)[0] - value(p - d)[0]) / 2e-5
+            assert np.isclose(g[k], fd, rtol=2e-3, atol=1e-3 * abs(g).max()), (name, k, g[k], fd)
+
+
+def test_optimiser_recovers_a_translation_with_the_oracle_metric():
+    f = _blob_image((24, 20, 16), (12.0, 10.0, 8.0))
+    mv = _blob_image((24, 20, 16), (14.0, 8.5, 9.0))   # moving = fixed shifted by (+2, -1.5, +1)
+    init = linear.centered_transform_initializer(f, mv)
+    m = linear.make_model("translation")
+
+    def evaluate(p):
+        return ref.linreg_meansq(f, mv, init.matrix @ m.matrix(p), init.matrix @ m.offset(p) + init.offset, init.matrix, m.center, stride=2)
+
+    hist = linear.optimise_level(m, evaluate, linear.image_corners(f), 1.0, 60)
+    assert hist[-1] < 0.02 * hist[0]
+    assert np.allclose(m.p, [2.0, -1.5, 1.0], atol=0.15)
+
+
+def test_golden_section_and_line_search_optimiser():
+    assert linear.golden_section(lambda x: (x - 1.7) ** 2, 0.0, 1.0, 5.0) == pytest.approx(1.7, abs=0.03)
+    assert linear.golden_section(lambda x: (x - 0.2) ** 2, 0.0, 1.0, 5.0) == pytest.approx(0.2, abs=0.03)
+    f = _blob_image((24, 20, 16), (12.0, 10.0, 8.0))
+    mv = _blob_image((24, 20, 16), (14.0, 8.5, 9.0))
+    init = linear.centered_transform_initializer(f, mv)
+    m = linear.make_model("translation")
+
+    def evaluate(p):
+        return ref.linreg_meansq(f, mv, init.matrix @ m.matrix(p), init.matrix @ m.offset(p) + init.offset, init.matrix, m.center, stride=2)
+
+    hist = linear.optimise_level_line_search(m, evaluate, linear.image_corners(f), 1.0, 15)
+    assert hist[-1] < 0.01 * hist[0]
+    assert np.allclose(m.p, [2.0, -1.5, 1.0], atol=0.1)
