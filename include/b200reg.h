@@ -50,7 +50,7 @@ typedef enum {
 } b200reg_dtype;
 
 /* sitkNearestNeighbor / sitkLinear (deformable.py:221-224) */
-typedef enum { B200REG_INTERP_NN = 1, B200REG_INTERP_LINEAR = 2 } b200reg_interp;
+typedef enum { B200REG_INTERP_NN = 1, B200REG_INTERP_LINEAR = 2, B200REG_INTERP_BSPLINE = 3 } b200reg_interp; /* sitk enum values */
 
 /* itk::ImageBase geometry: size (x,y,z), spacing, origin, direction cosines (row-major 3x3) */
 typedef struct {

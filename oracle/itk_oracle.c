@@ -347,6 +347,104 @@ static inline void out_to_in_cidx(const geomx* go, const geomx* gi, const tfmx* 
     }
 }
 
+/* ---- itk::BSplineInterpolateImageFunction, spline order 3 (sitk.sitkBSpline; reference deformable.py:221-224
+ * interp_order, utils.py:148-192 interpolator) ------------------------------------------------------------------ */
+/* itk::BSplineDecompositionImageFilter::DataToCoefficients1D on one line (stride s, length n), in place:
+ * gain, causal initialisation (truncated at the horizon ceil(log(1e-10) / log|z|), exact mirror sum for short
+ * lines), causal and anti-causal recursions with the cubic pole z = sqrt(3) - 2. */
+static void bspline3_line(double* c, size_t s, int n)
+{
+    if (n == 1) return;
+    const double z = sqrt(3.0) - 2.0, tol = 1e-10;
+    double c0 = 1.0;
+    c0 = c0 * (1.0 - z) * (1.0 - 1.0 / z);
+    for (int k = 0; k < n; ++k) c[k * s] *= c0;
+    {
+        double zn = z, sum;
+        long horizon = (long)ceil(log(tol) / log(fabs(z)));
+        if (horizon < n) {
+            sum = c[0];
+            for (long k = 1; k < horizon; ++k) { sum += zn * c[k * s]; zn *= z; }
+            c[0] = sum;
+        } else {
+            const double iz = 1.0 / z;
+            double z2n = pow(z, (double)(n - 1));
+            sum = c[0] + z2n * c[(size_t)(n - 1) * s];
+            z2n *= z2n * iz;
+            for (int k = 1; k <= n - 2; ++k) { sum += (zn + z2n) * c[k * s]; zn *= z; z2n *= iz; }
+            c[0] = sum / (1.0 - zn * zn);
+        }
+    }
+    for (int k = 1; k < n; ++k) c[k * s] += z * c[(k - 1) * s];
+    c[(size_t)(n - 1) * s] = (z / (z * z - 1.0)) * (z * c[(size_t)(n - 2) * s] + c[(size_t)(n - 1) * s]);
+    for (int k = n - 2; k >= 0; --k) c[k * s] = z * (c[(k + 1) * s] - c[k * s]);
+}
+/* coefficients of the whole volume: dimensions x, y, z in turn (DataToCoefficientsND) */
+static double* bspline3_coefficients(const void* in, int dtype, const geomx* g)
+{
+    const size_t n = (size_t)g->nx * g->ny * g->nz;
+    double* c = (double*)malloc(n * sizeof(double));
+    if (!c) return NULL;
+    for (size_t i = 0; i < n; ++i) c[i] = ld(in, dtype, i);
+    const size_t sy = (size_t)g->nx, sz = (size_t)g->nx * g->ny;
+#pragma omp parallel for schedule(static)
+    for (long r = 0; r < (long)g->ny * g->nz; ++r) bspline3_line(c + (size_t)r * sy, 1, g->nx);
+#pragma omp parallel for schedule(static)
+    for (long r = 0; r < (long)g->nx * g->nz; ++r) bspline3_line(c + (size_t)(r / g->nx) * sz + (size_t)(r % g->nx), sy, g->ny);
+#pragma omp parallel for schedule(static)
+    for (long r = 0; r < (long)g->nx * g->ny; ++r) bspline3_line(c + (size_t)r, sz, g->nz);
+    return c;
+}
+/* EvaluateAtContinuousIndexInternal: support floor((float)x) - 1 .. + 2, cubic weights, mirror boundary, sum over the
+ * 64 points with x fastest, weight = ((1 * wx) * wy) * wz */
+static inline double interp_bspline3(const double* coef, const geomx* g, const double* x)
+{
+    const int n[3] = { g->nx, g->ny, g->nz };
+    long idx[3][4];
+    double w[3][4];
+    for (int d = 0; d < 3; ++d) {
+        long indx = (long)floor((float)x[d]) - 1;
+        for (int k = 0; k < 4; ++k) idx[d][k] = indx++;
+        const double t = x[d] - (double)idx[d][1];
+        w[d][3] = (1.0 / 6.0) * t * t * t;
+        w[d][0] = (1.0 / 6.0) + 0.5 * t * (t - 1.0) - w[d][3];
+        w[d][2] = t + w[d][0] - 2.0 * w[d][3];
+        w[d][1] = 1.0 - w[d][0] - w[d][2] - w[d][3];
+        for (int k = 0; k < 4; ++k) {
+            if (n[d] == 1) idx[d][k] = 0;
+            else {
+                if (idx[d][k] < 0) idx[d][k] = -idx[d][k];
+                if (idx[d][k] > n[d] - 1) idx[d][k] = (n[d] - 1) - (idx[d][k] - (n[d] - 1));
+                /* lines shorter than the support: keep the single reflection inside the buffer */
+                if (idx[d][k] < 0) idx[d][k] = 0;
+                if (idx[d][k] > n[d] - 1) idx[d][k] = n[d] - 1;
+            }
+        }
+    }
+    double v = 0.0;
+    for (int kz = 0; kz < 4; ++kz)
+        for (int ky = 0; ky < 4; ++ky)
+            for (int kx = 0; kx < 4; ++kx) {
+                double ww = 1.0;
+                ww *= w[0][kx];
+                ww *= w[1][ky];
+                ww *= w[2][kz];
+                v += ww * coef[((size_t)idx[2][kz] * n[1] + (size_t)idx[1][ky]) * n[0] + (size_t)idx[0][kx]];
+            }
+    return v;
+}
+
+ORC_API int orc_bspline3_coefficients(const void* in, int dtype, const orc_geom* gin, double* out)
+{
+    geomx gi;
+    geomx_init(&gi, gin);
+    double* c = bspline3_coefficients(in, dtype, &gi);
+    if (!c) return -1;
+    memcpy(out, c, (size_t)gi.nx * gi.ny * gi.nz * sizeof(double));
+    free(c);
+    return 0;
+}
+
 ORC_API int orc_resample_scalar(const void* in, int dtype, const orc_geom* gin, void* out, const orc_geom* gout,
                                 const orc_transform* tf, int ntf, int interp, double default_value)
 {
@@ -355,6 +453,23 @@ ORC_API int orc_resample_scalar(const void* in, int dtype, const orc_geom* gin, 
     geomx_init(&go, gout);
     tfmx* t = chain_prepare(tf, ntf);
     int linear = chain_is_linear(t, ntf);
+    if (interp == 3) { /* sitk.sitkBSpline */
+        double* coef = bspline3_coefficients(in, dtype, &gi);
+        if (!coef) { free(t); return -1; }
+#pragma omp parallel for schedule(static)
+        for (int k = 0; k < go.nz; ++k)
+            for (int j = 0; j < go.ny; ++j)
+                for (int i = 0; i < go.nx; ++i) {
+                    double c[3];
+                    size_t o = ((size_t)k * go.ny + j) * go.nx + i;
+                    out_to_in_cidx(&go, &gi, t, ntf, linear, i, j, k, c);
+                    if (inside_buffer(&gi, c)) st(out, dtype, o, interp_bspline3(coef, &gi, c));
+                    else st_default(out, dtype, o, default_value);
+                }
+        free(coef);
+        free(t);
+        return 0;
+    }
 #pragma omp parallel for schedule(static)
     for (int k = 0; k < go.nz; ++k)
         for (int j = 0; j < go.ny; ++j)

@@ -68,6 +68,7 @@ def lib():
         _lib.orc_recursive_gaussian_vec3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.orc_transform_to_dvf.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib.orc_set_num_threads.argtypes = [C.c_int]
+        _lib.orc_bspline3_coefficients.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _lib.orc_binary_fillhole.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _lib.orc_largest_component.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     return _lib
@@ -294,3 +295,12 @@ def largest_component(mask, want_labels=False):
     if ncomp < 0:
         raise MemoryError
     return (out, ncomp, nvox.value, labels) if want_labels else (out, ncomp, nvox.value)
+
+
+def bspline3_coefficients(arr, geom):
+    """itk::BSplineDecompositionImageFilter (order 3) coefficients of a scalar [z, y, x] array, as float64."""
+    a = np.ascontiguousarray(arr)
+    out = np.empty(a.shape, dtype=np.float64)
+    if lib().orc_bspline3_coefficients(_ptr(a), _NP_TO_ORC[a.dtype], C.byref(geom), _ptr(out)) != 0:
+        raise MemoryError
+    return out

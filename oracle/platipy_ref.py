@@ -57,8 +57,8 @@ def resample(image, reference_geom_image=None, transform=None, interpolator=sk.s
     if image.is_vector:
         out = orc.resample_vec3(image.array, gin, gout, chain, default_value)
         return Image(out, sp, og, dr, True)
-    if interpolator not in (sk.sitkNearestNeighbor, sk.sitkLinear):
-        raise NotImplementedError("oracle: only nearest-neighbour and linear interpolation")
+    if interpolator not in (sk.sitkNearestNeighbor, sk.sitkLinear, sk.sitkBSpline):
+        raise NotImplementedError("oracle: nearest-neighbour, linear and B-spline (order 3) interpolation")
     out = orc.resample_scalar(image.array, gin, gout, chain, interpolator, default_value)
     return Image(out, sp, og, dr, False)
 

@@ -422,8 +422,8 @@ API int b200reg_multiscale_demons(b200reg_ctx* ctx, const float* d_fixed, const 
     ENTER(ctx);
     REQUIRE(d_fixed && d_moving && d_out_soa && cfg && valid_geom(fixed_geom) && valid_geom(moving_geom), "invalid argument");
     REQUIRE(cfg->n_levels >= 0 && cfg->n_levels <= B200REG_MAX_LEVELS, "number of levels %d not in [0, %d]", cfg->n_levels, B200REG_MAX_LEVELS);
-    REQUIRE(cfg->interp_order == B200REG_INTERP_NN || cfg->interp_order == B200REG_INTERP_LINEAR ? true : false,
-            "interpolator %d is not supported (nearest neighbour = 1, linear = 2)", cfg->interp_order);
+    REQUIRE(cfg->interp_order == B200REG_INTERP_NN || cfg->interp_order == B200REG_INTERP_LINEAR || cfg->interp_order == B200REG_INTERP_BSPLINE,
+            "interpolator %d is not supported (nearest neighbour = 1, linear = 2, B-spline = 3)", cfg->interp_order);
     B200_TRY(check_demons_params(&cfg->demons));
     const int L = cfg->n_levels;
     const b200reg_geom gF = *fixed_geom, gM = *moving_geom;

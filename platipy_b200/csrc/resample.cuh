@@ -225,7 +225,115 @@ struct BatchItem {
     int dtype;
     int interp;
     double default_value;
+    const double* coeff;  // B-spline coefficients of `in` (interp == B200REG_INTERP_BSPLINE)
 };
+
+// ---- itk::BSplineInterpolateImageFunction, spline order 3 (sitk.sitkBSpline) ------------------------------------------
+// Coefficients: itk::BSplineDecompositionImageFilter::DataToCoefficients1D along x, y, z in turn, one thread per line,
+// in place on a float64 copy of the image.  The constants that involve libm (pole, gain, horizon, z^(n-1)) come from
+// the host so that the recursion is the same sequence of IEEE operations as the CPU oracle's.
+struct BsplinePole {
+    double z, gain, z2n0, anti;  // pole, (1 - z)(1 - 1/z), z^(n-1), z / (z^2 - 1)
+    int horizon;
+};
+template <int AXIS>
+__global__ void __launch_bounds__(128) bspline3_prefilter_kernel(double* __restrict__ c, int nx, int ny, int nz, const __grid_constant__ BsplinePole pp)
+{
+    const int n = AXIS == 0 ? nx : (AXIS == 1 ? ny : nz);
+    const size_t nlines = AXIS == 0 ? (size_t)ny * nz : (AXIS == 1 ? (size_t)nx * nz : (size_t)nx * ny);
+    const size_t s = AXIS == 0 ? 1 : (AXIS == 1 ? (size_t)nx : (size_t)nx * ny);
+    const size_t r = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= nlines || n == 1) return;
+    double* l = AXIS == 0 ? c + r * (size_t)nx : (AXIS == 1 ? c + (r / nx) * (size_t)nx * ny + (r % nx) : c + r);
+    const double z = pp.z;
+    for (int k = 0; k < n; ++k) l[k * s] *= pp.gain;
+    {
+        double zn = z, sum;
+        if (pp.horizon < n) {
+            sum = l[0];
+            for (int k = 1; k < pp.horizon; ++k) {
+                sum += zn * l[k * s];
+                zn *= z;
+            }
+            l[0] = sum;
+        } else {
+            const double iz = 1.0 / z;
+            double z2n = pp.z2n0;
+            sum = l[0] + z2n * l[(size_t)(n - 1) * s];
+            z2n *= z2n * iz;
+            for (int k = 1; k <= n - 2; ++k) {
+                sum += (zn + z2n) * l[k * s];
+                zn *= z;
+                z2n *= iz;
+            }
+            l[0] = sum / (1.0 - zn * zn);
+        }
+    }
+    for (int k = 1; k < n; ++k) l[k * s] += z * l[(k - 1) * s];
+    l[(size_t)(n - 1) * s] = pp.anti * (z * l[(size_t)(n - 2) * s] + l[(size_t)(n - 1) * s]);
+    for (int k = n - 2; k >= 0; --k) l[k * s] = z * (l[(k + 1) * s] - l[k * s]);
+}
+inline BsplinePole bspline3_pole(int n)
+{
+    BsplinePole p;
+    p.z = std::sqrt(3.0) - 2.0;
+    double c0 = 1.0;
+    c0 = c0 * (1.0 - p.z) * (1.0 - 1.0 / p.z);
+    p.gain = c0;
+    p.horizon = (int)std::ceil(std::log(1e-10) / std::log(std::fabs(p.z)));
+    p.z2n0 = std::pow(p.z, (double)(n - 1));
+    p.anti = p.z / (p.z * p.z - 1.0);
+    return p;
+}
+template <typename T>
+__global__ void __launch_bounds__(256) to_f64_kernel(const T* __restrict__ in, double* __restrict__ out, size_t n)
+{
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) out[q] = (double)in[q];
+}
+// EvaluateAtContinuousIndexInternal: support floor((float)x) - 1 .. + 2, cubic weights, mirror boundary, 64-point sum with
+// x fastest and weight ((1 * wx) * wy) * wz
+__device__ __forceinline__ double bspline3_eval(const double* __restrict__ coef, const GeomD& g, const double* x)
+{
+    const int n[3] = { g.nx, g.ny, g.nz };
+    int idx[3][4];
+    double w[3][4];
+#pragma unroll
+    for (int d = 0; d < 3; ++d) {
+        const int i0 = (int)floorf((float)x[d]) - 1;
+        const double t = x[d] - (double)(i0 + 1);
+        w[d][3] = (1.0 / 6.0) * t * t * t;
+        w[d][0] = (1.0 / 6.0) + 0.5 * t * (t - 1.0) - w[d][3];
+        w[d][2] = t + w[d][0] - 2.0 * w[d][3];
+        w[d][1] = 1.0 - w[d][0] - w[d][2] - w[d][3];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            int q = i0 + k;
+            if (n[d] == 1) q = 0;
+            else {
+                if (q < 0) q = -q;
+                if (q > n[d] - 1) q = (n[d] - 1) - (q - (n[d] - 1));
+                q = q < 0 ? 0 : (q > n[d] - 1 ? n[d] - 1 : q);
+            }
+            idx[d][k] = q;
+        }
+    }
+    double v = 0.0;
+#pragma unroll
+    for (int kz = 0; kz < 4; ++kz)
+#pragma unroll
+        for (int ky = 0; ky < 4; ++ky) {
+            const size_t row = ((size_t)idx[2][kz] * n[1] + (size_t)idx[1][ky]) * n[0];
+#pragma unroll
+            for (int kx = 0; kx < 4; ++kx) {
+                double ww = 1.0;
+                ww *= w[0][kx];
+                ww *= w[1][ky];
+                ww *= w[2][kz];
+                v += ww * __ldg(coef + row + idx[0][kx]);
+            }
+        }
+    return v;
+}
 constexpr int RESAMPLE_BATCH = 8;
 struct BatchD {
     int n;
@@ -239,7 +347,9 @@ __device__ __forceinline__ void resample_one(const BatchItem& it, const GeomD& g
     T* out = reinterpret_cast<T*>(it.out);
     if (inside) {
         double v;
-        if (it.interp == B200REG_INTERP_NN) {
+        if (it.interp == B200REG_INTERP_BSPLINE) {
+            v = bspline3_eval(it.coeff, gi, c);
+        } else if (it.interp == B200REG_INTERP_NN) {
             // NearestNeighborInterpolateImageFunction: RoundHalfIntegerUp = floor(x + 0.5)
             const int i0 = (int)floor(c[0] + 0.5), i1 = (int)floor(c[1] + 0.5), i2 = (int)floor(c[2] + 0.5);
             v = Px<T>::ld(in, ((size_t)i2 * gi.ny + i1) * gi.nx + i0);
@@ -292,13 +402,30 @@ inline int resample_batch(b200reg_ctx* ctx, int n, const void* const* d_in, cons
     for (int i = 0; i < n; ++i) {
         if (!d_in[i] || !d_out[i]) return set_error(B200REG_ERR_ARG, "null image pointer in resample batch");
         if (dtype_size(dtypes[i]) == 0) return set_error(B200REG_ERR_ARG, "unsupported pixel type %d", dtypes[i]);
-        if (interps[i] != B200REG_INTERP_NN && interps[i] != B200REG_INTERP_LINEAR)
-            return set_error(B200REG_ERR_UNSUPPORTED, "interpolator %d is not supported (nearest neighbour = 1, linear = 2)", interps[i]);
+        if (interps[i] != B200REG_INTERP_NN && interps[i] != B200REG_INTERP_LINEAR && interps[i] != B200REG_INTERP_BSPLINE)
+            return set_error(B200REG_ERR_UNSUPPORTED, "interpolator %d is not supported (nearest neighbour = 1, linear = 2, B-spline = 3)", interps[i]);
     }
+    const size_t n_in = nvox(gin);
     for (int start = 0; start < n; start += RESAMPLE_BATCH) {
         BatchD b;
         b.n = (n - start) < RESAMPLE_BATCH ? (n - start) : RESAMPLE_BATCH;
-        for (int q = 0; q < b.n; ++q) b.item[q] = BatchItem{ d_in[start + q], d_out[start + q], dtypes[start + q], interps[start + q], defaults[start + q] };
+        TempBuf coef[RESAMPLE_BATCH];
+        for (int q = 0; q < b.n; ++q) {
+            b.item[q] = BatchItem{ d_in[start + q], d_out[start + q], dtypes[start + q], interps[start + q], defaults[start + q], nullptr };
+            if (interps[start + q] == B200REG_INTERP_BSPLINE) {
+                B200_TRY(coef[q].alloc(ctx, n_in * sizeof(double)));
+                double* c = coef[q].as<double>();
+                const int nb = ctx->sm_count * 8;
+                B200_DISPATCH_DTYPE(dtypes[start + q], T, { to_f64_kernel<T><<<nb, 256, 0, ctx->stream>>>((const T*)d_in[start + q], c, n_in); });
+                const size_t l0 = (size_t)gi.ny * gi.nz, l1 = (size_t)gi.nx * gi.nz, l2 = (size_t)gi.nx * gi.ny;
+                bspline3_prefilter_kernel<0><<<(unsigned)((l0 + 127) / 128), 128, 0, ctx->stream>>>(c, gi.nx, gi.ny, gi.nz, bspline3_pole(gi.nx));
+                bspline3_prefilter_kernel<1><<<(unsigned)((l1 + 127) / 128), 128, 0, ctx->stream>>>(c, gi.nx, gi.ny, gi.nz, bspline3_pole(gi.ny));
+                bspline3_prefilter_kernel<2><<<(unsigned)((l2 + 127) / 128), 128, 0, ctx->stream>>>(c, gi.nx, gi.ny, gi.nz, bspline3_pole(gi.nz));
+                ctx->launches += 4;
+                B200_CHECK_LAUNCH();
+                b.item[q].coeff = c;
+            }
+        }
         if (gi.small) resample_batch_kernel<true><<<grid3(go.nx, go.ny, go.nz), block3(), 0, ctx->stream>>>(b, gi, go, ch);
         else resample_batch_kernel<false><<<grid3(go.nx, go.ny, go.nz), block3(), 0, ctx->stream>>>(b, gi, go, ch);
         ctx->launches++;

@@ -32,10 +32,10 @@ LAST_LEVEL_STATS = []
 
 
 def _check_interp(interpolator):
-    if interpolator == sk.sitkBSpline:
-        raise NotImplementedError("B-spline interpolation is not implemented on the B200 path yet (SURVEY 8f-3)")
-    if interpolator not in (sk.sitkNearestNeighbor, sk.sitkLinear):
-        raise ValueError(f"unknown interpolator {interpolator!r}")
+    # SimpleITK enum values (deformable.py:221-224): 1 nearest neighbour, 2 linear, 3 B-spline (order 3)
+    if interpolator not in (sk.sitkNearestNeighbor, sk.sitkLinear, sk.sitkBSpline):
+        raise NotImplementedError(f"interpolator {interpolator!r} is not implemented on the B200 path "
+                                  "(sitkNearestNeighbor, sitkLinear and sitkBSpline are)")
     return int(interpolator)
 
 

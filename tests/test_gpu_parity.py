@@ -80,7 +80,32 @@ def test_resample_batch_equals_single_calls(engine):
         exp = ref.apply_transform(im, fixed, tfm, dv, ip)
         assert np.array_equal(o.array, exp.array)
     with pytest.raises(NotImplementedError):
-        reg.apply_transform(moving, fixed, tfm, 0, sk.sitkBSpline)
+        reg.apply_transform(moving, fixed, tfm, 0, 4)  # sitkGaussian: not one of the interpolators the path implements
+
+
+def test_bspline_interpolation_bit_exact(engine):
+    """sitk.sitkBSpline (order 3; deformable.py:221-224, utils.py:148-192): coefficient decomposition + 64-point
+    evaluation are the same IEEE operations as the oracle's restatement of itk::BSplineInterpolateImageFunction."""
+    fixed, moving = synth_pair((44, 37, 23), seed=21, spacing=(1.0, 1.3, 2.1), origin=(-3.0, 8.0, 1.5))
+    dvf = Image(smooth_random_dvf((44, 37, 23), seed=22, peak_mm=5.0), fixed.GetSpacing(), fixed.GetOrigin(), fixed.GetDirection(), is_vector=True)
+    tfm = sk.DisplacementFieldTransform(dvf)
+    aff = sk.AffineTransform([[0.99, -0.05, 0.01], [0.05, 1.01, 0.0], [0.0, 0.02, 0.98]], (1.5, -2.0, 0.7), (20.0, 20.0, 20.0))
+    small = Image(moving.array[:3, :9, :5].copy(), moving.GetSpacing())  # lines shorter than the filter horizon
+    cases = [(moving, fixed, tfm, -1000), (moving, fixed, aff, -1000), (moving, None, None, 0), (small, small, sk.AffineTransform(translation=(0.4, 0.3, 0.2)), 0),
+             (Image(moving.array.astype(np.int16), moving.GetSpacing(), moving.GetOrigin()), fixed, aff, -1000),
+             (Image((moving.array > -500).astype(np.uint8) * 200, moving.GetSpacing(), moving.GetOrigin()), fixed, tfm, 0),
+             (Image(moving.array.astype(np.float64), moving.GetSpacing(), moving.GetOrigin()), fixed, tfm, 0)]
+    for img, ref_img, t, dv in cases:
+        got = reg.apply_transform(img, ref_img, t, dv, sk.sitkBSpline)
+        exp = ref.apply_transform(img, ref_img, t, dv, sk.sitkBSpline)
+        assert got.array.dtype == img.array.dtype
+        assert np.array_equal(got.array, exp.array), (img.array.dtype, type(t).__name__)
+    # the Demons driver accepts interp_order=3 as well (pyramid, per-level and final resampling, deformable.py:281-304)
+    kw = dict(resolution_staging=[2, 1], iteration_staging=[5, 3], interp_order=sk.sitkBSpline)
+    img, _, dvf_g = reg.fast_symmetric_forces_demons_registration(fixed, moving, **kw)
+    img_o, _, dvf_o = ref.fast_symmetric_forces_demons_registration(fixed, moving, **kw)
+    assert np.abs(dvf_g.array - dvf_o.array).max() <= DVF_TOL_MM
+    assert np.abs(img.array - img_o.array).max() <= REL_TOL * max(1.0, np.abs(img_o.array).max())
 
 
 def test_resample_vec3_and_compose_bit_exact(engine):

@@ -71,8 +71,9 @@ def test_reference_facing_argument_errors(built):
         reg.smooth_and_resample(im, shrink_factor=2)
     with pytest.raises(RuntimeError):
         reg.fast_symmetric_forces_demons_registration(im, im)
+    assert reg._check_interp(sk.sitkBSpline) == 3
     with pytest.raises(NotImplementedError):
-        reg._check_interp(sk.sitkBSpline)
+        reg._check_interp(4)
     f = reg.FastSymmetricForcesDemonsRegistrationFilter()
     f.SetStandardDeviations(2.0)
     assert f.GetStandardDeviations() == (2.0, 2.0, 2.0)
