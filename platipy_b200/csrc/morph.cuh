@@ -68,26 +68,28 @@ __global__ void __launch_bounds__(256) ccl_init_kernel(const uint8_t* __restrict
     L[i] = i - (threadIdx.x - start);
 }
 
-template <bool CLS>
-__global__ void __launch_bounds__(256) ccl_merge_kernel(const uint8_t* __restrict__ in, int* L, int nx, int ny, int nz)
+// Class membership of the neighbours is read from L (>= 0), not from the image, so that the union-find only ever
+// follows labels the init kernel wrote.
+__global__ void __launch_bounds__(256) ccl_merge_kernel(int* L, int nx, int ny, int nz)
 {
     const int x = blockIdx.x * 32 + threadIdx.x;
     const int row = blockIdx.y * 8 + threadIdx.y;
     if (row >= ny * nz || x >= nx) return;
     const int i = row * nx + x;
-    if (L[i] < 0) return;
+    const volatile int* V = L;
+    if (V[i] < 0) return;
     const int y = row % ny, z = row / ny;
-    const bool prev = x > 0 && ((in[i - 1] != 0) == CLS);
+    const bool prev = x > 0 && V[i - 1] >= 0;
     // run continues across the chunk boundary
     if (threadIdx.x == 0 && prev) uf_union(L, i, i - 1);
-    if (y > 0 && ((in[i - nx] != 0) == CLS)) {
-        const bool implied = prev && ((in[i - 1 - nx] != 0) == CLS);
+    if (y > 0 && V[i - nx] >= 0) {
+        const bool implied = prev && V[i - 1 - nx] >= 0;
         if (!implied) uf_union(L, i, i - nx);
     }
     if (z > 0) {
         const int pz = nx * ny;
-        if ((in[i - pz] != 0) == CLS) {
-            const bool implied = prev && ((in[i - 1 - pz] != 0) == CLS);
+        if (V[i - pz] >= 0) {
+            const bool implied = prev && V[i - 1 - pz] >= 0;
             if (!implied) uf_union(L, i, i - pz);
         }
     }
@@ -167,7 +169,7 @@ inline int ccl_label(b200reg_ctx* ctx, const uint8_t* d_in, int* L, int nx, int 
     const dim3 blk(32, 8, 1);
     const dim3 grd((nx + 31) / 32, (unsigned)(((size_t)ny * nz + 7) / 8), 1);
     ccl_init_kernel<CLS><<<grd, blk, 0, ctx->stream>>>(d_in, L, nx, ny, nz);
-    ccl_merge_kernel<CLS><<<grd, blk, 0, ctx->stream>>>(d_in, L, nx, ny, nz);
+    ccl_merge_kernel<<<grd, blk, 0, ctx->stream>>>(L, nx, ny, nz);
     ccl_flatten_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(L, n);
     ctx->launches += 3;
     B200_CHECK_LAUNCH();

@@ -340,14 +340,14 @@ struct BatchD {
     BatchItem item[RESAMPLE_BATCH];
 };
 
-template <typename T, bool SMALL>
+template <typename T, bool SMALL, bool BSP>
 __device__ __forceinline__ void resample_one(const BatchItem& it, const GeomD& gi, const double* c, bool inside, size_t o)
 {
     const T* in = reinterpret_cast<const T*>(it.in);
     T* out = reinterpret_cast<T*>(it.out);
     if (inside) {
         double v;
-        if (it.interp == B200REG_INTERP_BSPLINE) {
+        if (BSP && it.interp == B200REG_INTERP_BSPLINE) {
             v = bspline3_eval(it.coeff, gi, c);
         } else if (it.interp == B200REG_INTERP_NN) {
             // NearestNeighborInterpolateImageFunction: RoundHalfIntegerUp = floor(x + 0.5)
@@ -363,8 +363,10 @@ __device__ __forceinline__ void resample_one(const BatchItem& it, const GeomD& g
     }
 }
 
-template <bool SMALL>
-__global__ void __launch_bounds__(BX* BY, 4) resample_batch_kernel(const __grid_constant__ BatchD batch, const __grid_constant__ GeomD gi,
+// BSP: the batch contains a B-spline item (the 64-point evaluation needs far more registers than the other two
+// interpolators, so it lives in its own instantiation and the common one keeps 4 blocks per SM)
+template <bool SMALL, bool BSP>
+__global__ void __launch_bounds__(BX* BY, BSP ? 2 : 4) resample_batch_kernel(const __grid_constant__ BatchD batch, const __grid_constant__ GeomD gi,
                                                                  const __grid_constant__ GeomD go, const __grid_constant__ ChainD ch)
 {
     const int i = blockIdx.x * BX + threadIdx.x;
@@ -378,16 +380,16 @@ __global__ void __launch_bounds__(BX* BY, 4) resample_batch_kernel(const __grid_
     for (int b = 0; b < batch.n; ++b) {
         const BatchItem& it = batch.item[b];
         switch (it.dtype) {
-        case B200REG_I8: resample_one<int8_t, SMALL>(it, gi, c, inside, o); break;
-        case B200REG_U8: resample_one<uint8_t, SMALL>(it, gi, c, inside, o); break;
-        case B200REG_I16: resample_one<int16_t, SMALL>(it, gi, c, inside, o); break;
-        case B200REG_U16: resample_one<uint16_t, SMALL>(it, gi, c, inside, o); break;
-        case B200REG_I32: resample_one<int32_t, SMALL>(it, gi, c, inside, o); break;
-        case B200REG_U32: resample_one<uint32_t, SMALL>(it, gi, c, inside, o); break;
-        case B200REG_I64: resample_one<int64_t, SMALL>(it, gi, c, inside, o); break;
-        case B200REG_U64: resample_one<uint64_t, SMALL>(it, gi, c, inside, o); break;
-        case B200REG_F32: resample_one<float, SMALL>(it, gi, c, inside, o); break;
-        default: resample_one<double, SMALL>(it, gi, c, inside, o); break;
+        case B200REG_I8: resample_one<int8_t, SMALL, BSP>(it, gi, c, inside, o); break;
+        case B200REG_U8: resample_one<uint8_t, SMALL, BSP>(it, gi, c, inside, o); break;
+        case B200REG_I16: resample_one<int16_t, SMALL, BSP>(it, gi, c, inside, o); break;
+        case B200REG_U16: resample_one<uint16_t, SMALL, BSP>(it, gi, c, inside, o); break;
+        case B200REG_I32: resample_one<int32_t, SMALL, BSP>(it, gi, c, inside, o); break;
+        case B200REG_U32: resample_one<uint32_t, SMALL, BSP>(it, gi, c, inside, o); break;
+        case B200REG_I64: resample_one<int64_t, SMALL, BSP>(it, gi, c, inside, o); break;
+        case B200REG_U64: resample_one<uint64_t, SMALL, BSP>(it, gi, c, inside, o); break;
+        case B200REG_F32: resample_one<float, SMALL, BSP>(it, gi, c, inside, o); break;
+        default: resample_one<double, SMALL, BSP>(it, gi, c, inside, o); break;
         }
     }
 }
@@ -426,8 +428,16 @@ inline int resample_batch(b200reg_ctx* ctx, int n, const void* const* d_in, cons
                 b.item[q].coeff = c;
             }
         }
-        if (gi.small) resample_batch_kernel<true><<<grid3(go.nx, go.ny, go.nz), block3(), 0, ctx->stream>>>(b, gi, go, ch);
-        else resample_batch_kernel<false><<<grid3(go.nx, go.ny, go.nz), block3(), 0, ctx->stream>>>(b, gi, go, ch);
+        bool bsp = false;
+        for (int q = 0; q < b.n; ++q) bsp = bsp || b.item[q].interp == B200REG_INTERP_BSPLINE;
+        const dim3 g3 = grid3(go.nx, go.ny, go.nz);
+        if (bsp) {
+            if (gi.small) resample_batch_kernel<true, true><<<g3, block3(), 0, ctx->stream>>>(b, gi, go, ch);
+            else resample_batch_kernel<false, true><<<g3, block3(), 0, ctx->stream>>>(b, gi, go, ch);
+        } else {
+            if (gi.small) resample_batch_kernel<true, false><<<g3, block3(), 0, ctx->stream>>>(b, gi, go, ch);
+            else resample_batch_kernel<false, false><<<g3, block3(), 0, ctx->stream>>>(b, gi, go, ch);
+        }
         ctx->launches++;
         B200_CHECK_LAUNCH();
     }

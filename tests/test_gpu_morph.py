@@ -92,6 +92,7 @@ def test_full_size_properties(engine):
     from platipy_b200.engine import DeviceImage
 
     d = DeviceImage(m.contiguous(), np.uint8, (1.0, 1.0, 1.0), (0.0, 0.0, 0.0), (1, 0, 0, 0, 1, 0, 0, 0, 1), False)
+    d = engine.to_device(d)  # orders the engine's stream after the torch stream that produced the mask
     f1 = engine.binary_fillhole(d)
     f2 = engine.binary_fillhole(f1)
     engine.synchronize()
