@@ -484,9 +484,10 @@ __global__ void __launch_bounds__(Zm2Threads<R>::value, 2) conv3d_zm2_kernel(con
                         double o[2];
 #pragma unroll
                         for (int j = 0; j < 2; ++j) {
-                            double sum = 0.0;
+                            // first tap without the leading "0.0 +": same value (only the sign of an all-zero sum can differ)
+                            double sum = kc.k[0][0] * w[j + (RP - R)];
 #pragma unroll
-                            for (int t = 0; t <= 2 * R; ++t) sum += kc.k[0][t] * w[j + (RP - R) + t];
+                            for (int t = 1; t <= 2 * R; ++t) sum += kc.k[0][t] * w[j + (RP - R) + t];
                             o[j] = sum;
                         }
                         *reinterpret_cast<double2*>(B + yy * ZM_TX + xb) = make_double2(o[0], o[1]);
@@ -500,9 +501,9 @@ __global__ void __launch_bounds__(Zm2Threads<R>::value, 2) conv3d_zm2_kernel(con
                     for (int i = 0; i < 4 + 2 * R; ++i) col[i] = B[(4 * yb + i) * ZM_TX + ox];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        double sum = 0.0;
+                        double sum = kc.k[1][0] * col[j];
 #pragma unroll
-                        for (int t = 0; t <= 2 * R; ++t) sum += kc.k[1][t] * col[j + t];
+                        for (int t = 1; t <= 2 * R; ++t) sum += kc.k[1][t] * col[j + t];
                         ring[s][j] = sum;
                     }
                 }
@@ -511,9 +512,9 @@ __global__ void __launch_bounds__(Zm2Threads<R>::value, 2) conv3d_zm2_kernel(con
                     const int zo = zbeg + q - RZ;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
-                        double sum = 0.0;
+                        double sum = kc.k[2][0] * ring[(s + 1) % NR][j];
 #pragma unroll
-                        for (int t = 0; t < NR; ++t) sum += kc.k[2][t] * ring[(s + 1 + t) % NR][j];
+                        for (int t = 1; t < NR; ++t) sum += kc.k[2][t] * ring[(s + 1 + t) % NR][j];
                         const int gy = y0 + 4 * yb + j;
                         if (gx < nx && gy < ny) op[(size_t)zo * plane + (size_t)gy * nx + gx] = sum;
                     }
