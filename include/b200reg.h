@@ -253,6 +253,21 @@ int b200reg_linreg_meansq(b200reg_ctx* ctx, const float* d_fixed, const b200reg_
                           const double initial_matrix[9], const double center[3], const uint8_t* d_fixed_mask,
                           const uint8_t* d_moving_mask, int stride, double h_out[14]);
 
+/* ---- label utilities around the fusion step (multiatlas/run.py:200-259, 387-437) -------------------------------------- */
+/* sitk.LabelStatisticsImageFilter.GetBoundingBox (utils/crop.py:44-46) of the non-zero voxels of a UInt8 mask:
+ * h_bbox = (min x, min y, min z, max x, max y, max z); an empty mask gives max < min.  Synchronises. */
+int b200reg_bounding_box(b200reg_ctx* ctx, const uint8_t* d_mask, const int32_t size[3], int32_t h_bbox[6]);
+/* sitk.RegionOfInterest (crop_to_roi, utils/crop.py:74-76) and sitk.Paste (run.py:387-404): copy a region between two
+ * volumes of the same pixel type.  A region outside either volume is an error (ITK raises). */
+int b200reg_region_copy(b200reg_ctx* ctx, const void* d_src, const int32_t src_size[3], const int32_t src_index[3], void* d_dst,
+                        const int32_t dst_size[3], const int32_t dst_index[3], const int32_t region_size[3], int dtype);
+/* correct_volume_overlap (label/utils.py:23-58): labels in rank order; out[s] = labels[s] > 0 and no earlier label has the voxel */
+int b200reg_resolve_overlap(b200reg_ctx* ctx, const uint8_t* const* d_labels_ranked, uint8_t* const* d_out, int n_labels, size_t n);
+/* sitk.BinaryMorphologicalClosing(img, radius) (run.py:424; SafeBorder on, foreground 1): dilation then erosion with the
+ * structuring element given as n_offsets (dx, dy, dz) triples (host memory).  Synchronises. */
+int b200reg_binary_closing(b200reg_ctx* ctx, const uint8_t* d_in, const int32_t size[3], const int32_t radius[3],
+                           const int32_t* h_offsets, int n_offsets, uint8_t* d_out);
+
 #ifdef __cplusplus
 }
 #endif

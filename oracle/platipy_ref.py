@@ -390,3 +390,74 @@ def linreg_meansq(fixed, moving, total_matrix, total_offset, initial_matrix, cen
     out[2:5] = w.sum(axis=0)
     out[5:14] = (w[:, :, None] * (x - np.asarray(center, np.float64))[:, None, :]).sum(axis=0).reshape(9)
     return out
+
+
+# ---- label utilities (utils/crop.py:24-99, label/utils.py:23-58, multiatlas/run.py:387-437) -----------------------------
+def label_to_roi(label, expansion_mm=[0, 0, 0], return_as_list=False):
+    """crop.py:24-71 with LabelStatisticsImageFilter.GetBoundingBox restated in numpy."""
+    if isinstance(label, (list, tuple)):
+        ref_lab = sum(l.array.astype(np.float64) for l in label) > 0
+        spacing, full = np.array(label[0].GetSpacing()), np.array(label[0].GetSize())
+    else:
+        ref_lab = label.array > 0
+        spacing, full = np.array(label.GetSpacing()), np.array(label.GetSize())
+    zz, yy, xx = np.nonzero(ref_lab)
+    bounding_box = [xx.min(), xx.max(), yy.min(), yy.max(), zz.min(), zz.max()]
+    index = [bounding_box[x * 2] for x in range(3)]
+    size = [bounding_box[(x * 2) + 1] - bounding_box[x * 2] + 1 for x in range(3)]
+    expansion = (np.array(expansion_mm) / spacing).astype(int)
+    crop_box_index = np.max([index - expansion, np.array([0, 0, 0])], axis=0)
+    crop_box_size = np.min([full - crop_box_index, np.array(size) + 2 * expansion], axis=0)
+    crop_box_size = [int(i) for i in crop_box_size]
+    crop_box_index = [int(i) for i in crop_box_index]
+    if return_as_list:
+        return crop_box_index + crop_box_size
+    return crop_box_size, crop_box_index
+
+
+def crop_to_roi(image, size, index):
+    """sitk.RegionOfInterest: array slice, origin moved to the first voxel kept."""
+    x, y, z = index
+    sx, sy, sz = size
+    arr = image.array[z:z + sz, y:y + sy, x:x + sx].copy()
+    d = np.asarray(image.GetDirection(), np.float64).reshape(3, 3)
+    origin = np.asarray(image.GetOrigin()) + d @ (np.asarray(image.GetSpacing()) * np.asarray(index, np.float64))
+    return Image(arr, image.GetSpacing(), tuple(origin), image.GetDirection())
+
+
+def paste(destination_image, source_image, source_size, source_index, destination_index):
+    out = destination_image.array.copy()
+    sx, sy, sz = source_size
+    x, y, z = source_index
+    dx, dy, dz = destination_index
+    out[dz:dz + sz, dy:dy + sy, dx:dx + sx] = source_image.array[z:z + sz, y:y + sy, x:x + sx]
+    return _like(out, destination_image)
+
+
+def correct_volume_overlap(binary_label_dict, assign_overlap_to_largest=True):
+    """label/utils.py:23-58 (prime encoding restated as set logic: a voxel stays with the first structure, in volume rank
+    order, that contains it)."""
+    keys = list(binary_label_dict.keys())
+    vals = [int(binary_label_dict[k].array.sum()) for k in keys]
+    rank = np.argsort(vals)[::-1] if assign_overlap_to_largest else np.argsort(vals)
+    ranked = [keys[i] for i in rank]
+    combined = sum((binary_label_dict[k].array > 0).astype(np.int64) for k in keys) > 0
+    out = {}
+    for k in ranked:
+        o = combined & (binary_label_dict[k].array > 0)
+        out[k] = _like(o.astype(np.uint8), binary_label_dict[k])
+        combined = combined & ~o
+    return out
+
+
+def binary_morphological_closing(image, kernel_radius, structure):
+    """sitk.BinaryMorphologicalClosing (SafeBorder on): scipy dilation then erosion on a grid padded with background;
+    ``structure`` is the [z, y, x] boolean structuring element."""
+    import scipy.ndimage as ndi
+
+    r = [int(v) for v in kernel_radius]
+    a = np.pad(image.array > 0, ((r[2], r[2]), (r[1], r[1]), (r[0], r[0])))
+    d = ndi.binary_dilation(a, structure=structure)
+    e = ndi.binary_erosion(d, structure=structure, border_value=0)
+    e = e[r[2]:e.shape[0] - r[2], r[1]:e.shape[1] - r[1], r[0]:e.shape[2] - r[0]]
+    return _like(e.astype(np.uint8), image)

@@ -100,6 +100,11 @@ SIGNATURES = {
     "b200reg_process_probability": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_int32), C.c_double, _P, C.POINTER(C.c_int64)]),
     "b200reg_linreg_meansq": (C.c_int, [_P, _P, C.POINTER(Geom), _P, C.POINTER(Geom), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                         C.POINTER(C.c_double), C.POINTER(C.c_double), _P, _P, C.c_int, C.POINTER(C.c_double)]),
+    "b200reg_bounding_box": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
+    "b200reg_region_copy": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32),
+                                      C.POINTER(C.c_int32), C.c_int]),
+    "b200reg_resolve_overlap": (C.c_int, [_P, C.POINTER(_P), C.POINTER(_P), C.c_int, C.c_size_t]),
+    "b200reg_binary_closing": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, _P]),
     "b200reg_staple": (C.c_int, [_P, C.POINTER(_P), C.c_int, C.c_size_t, C.c_double, C.c_uint32, C.c_double, C.c_int, _P,
                                  C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
 }

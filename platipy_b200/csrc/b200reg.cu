@@ -7,6 +7,7 @@
 #include "fusion.cuh"
 #include "morph.cuh"
 #include "linreg.cuh"
+#include "postproc.cuh"
 #include "gauss.cuh"
 #include "resample.cuh"
 
@@ -795,4 +796,57 @@ API int b200reg_linreg_meansq(b200reg_ctx* ctx, const float* d_fixed, const b200
         }
     }
     return linreg_meansq(ctx, d_fixed, *fixed_geom, d_moving, *moving_geom, ps, d_fixed_mask, d_moving_mask, stride, h_out);
+}
+
+// ---- label utilities of the atlas pipeline (utils/crop.py:24-76, label/utils.py:23-58, multiatlas/run.py:387-437) -----------
+API int b200reg_bounding_box(b200reg_ctx* ctx, const uint8_t* d_mask, const int32_t size[3], int32_t h_bbox[6])
+{
+    ENTER(ctx);
+    REQUIRE(d_mask && size && h_bbox && size[0] > 0 && size[1] > 0 && size[2] > 0, "invalid argument");
+    TempBuf bb;
+    B200_TRY(bb.alloc(ctx, 6 * sizeof(int)));
+    bbox_init_kernel<<<1, 32, 0, ctx->stream>>>(bb.as<int>());
+    bbox_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_mask, size[0], size[1], size[2], bb.as<int>());
+    ctx->launches += 2;
+    B200_CHECK_LAUNCH();
+    int* h = reinterpret_cast<int*>(ctx->h_scratch);
+    B200_CUDA(cudaMemcpyAsync(h, bb.p, 6 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int d = 0; d < 6; ++d) h_bbox[d] = h[d];
+    return B200REG_OK;
+}
+API int b200reg_region_copy(b200reg_ctx* ctx, const void* d_src, const int32_t src_size[3], const int32_t src_index[3], void* d_dst,
+                            const int32_t dst_size[3], const int32_t dst_index[3], const int32_t region_size[3], int dtype)
+{
+    ENTER(ctx);
+    REQUIRE(d_src && d_dst && src_size && src_index && dst_size && dst_index && region_size, "invalid argument");
+    const size_t elem = dtype_size(dtype);
+    REQUIRE(elem > 0, "unsupported pixel type %d", dtype);
+    return region_copy(ctx, d_src, src_size, src_index, d_dst, dst_size, dst_index, region_size, elem);
+}
+API int b200reg_resolve_overlap(b200reg_ctx* ctx, const uint8_t* const* d_labels_ranked, uint8_t* const* d_out, int n_labels, size_t n)
+{
+    ENTER(ctx);
+    REQUIRE(d_labels_ranked && d_out && n > 0, "invalid argument");
+    REQUIRE(n_labels >= 1 && n_labels <= OVERLAP_MAX, "number of structures %d not in [1, %d]", n_labels, OVERLAP_MAX);
+    LabelPtrs lp;
+    lp.n = n_labels;
+    for (int s = 0; s < n_labels; ++s) {
+        REQUIRE(d_labels_ranked[s] && d_out[s], "null label pointer");
+        lp.in[s] = d_labels_ranked[s];
+        lp.out[s] = d_out[s];
+    }
+    overlap_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(lp, n);
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+API int b200reg_binary_closing(b200reg_ctx* ctx, const uint8_t* d_in, const int32_t size[3], const int32_t radius[3], const int32_t* h_offsets,
+                               int n_offsets, uint8_t* d_out)
+{
+    ENTER(ctx);
+    REQUIRE(d_in && d_out && size && radius && h_offsets && n_offsets >= 1, "invalid argument");
+    REQUIRE(d_in != d_out, "in-place closing is not supported");
+    for (int d = 0; d < 3; ++d) REQUIRE(size[d] > 0 && radius[d] >= 0, "invalid size / radius");
+    return binary_closing(ctx, d_in, size, radius, h_offsets, n_offsets, d_out);
 }

@@ -429,6 +429,33 @@ class Engine:
                                                         C.c_void_p(out.data_ptr()), None))
         return dimg.like(out, np.uint8, False)
 
+    # -- label utilities (utils/crop.py, label/utils.py, multiatlas/run.py:387-437) ----------------------------------
+    def bounding_box(self, mask):
+        bb = (C.c_int32 * 6)()
+        _abi.check(self.lib.b200reg_bounding_box(self.ctx, mask.ptr, self._size3(mask), bb))
+        return list(bb)
+
+    def region_copy(self, src, src_index, dst, dst_index, region_size):
+        i3 = C.c_int32 * 3
+        _abi.check(self.lib.b200reg_region_copy(self.ctx, src.ptr, self._size3(src), i3(*[int(v) for v in src_index]), dst.ptr, self._size3(dst),
+                                                i3(*[int(v) for v in dst_index]), i3(*[int(v) for v in region_size]), src.dtype_id))
+        return dst
+
+    def resolve_overlap(self, labels_ranked):
+        n = len(labels_ranked)
+        outs = [self.empty(l.tensor.shape, np.uint8) for l in labels_ranked]
+        pin = (C.c_void_p * n)(*[l.tensor.data_ptr() for l in labels_ranked])
+        pout = (C.c_void_p * n)(*[o.data_ptr() for o in outs])
+        _abi.check(self.lib.b200reg_resolve_overlap(self.ctx, pin, pout, n, labels_ranked[0].tensor.numel()))
+        return [l.like(o, np.uint8, False) for l, o in zip(labels_ranked, outs)]
+
+    def binary_closing(self, mask, radius, offsets):
+        out = self.empty(mask.tensor.shape, np.uint8)
+        offs = np.ascontiguousarray(offsets, dtype=np.int32).reshape(-1, 3)
+        _abi.check(self.lib.b200reg_binary_closing(self.ctx, mask.ptr, self._size3(mask), (C.c_int32 * 3)(*[int(v) for v in radius]),
+                                                   offs.ctypes.data_as(C.POINTER(C.c_int32)), int(offs.shape[0]), C.c_void_p(out.data_ptr())))
+        return mask.like(out, np.uint8, False)
+
     def pack_decision(self, label, bit, packed, first):
         _abi.check(self.lib.b200reg_pack_decision(self.ctx, label.ptr, int(bit), C.c_void_p(packed.data_ptr()), label.tensor.numel(), int(bool(first))))
 

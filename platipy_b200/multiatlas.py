@@ -127,6 +127,8 @@ def run_segmentation(img, atlas_set, settings=MULTIATLAS_SETTINGS_DEFAULTS, grou
     from . import fusion
     from .engine import Engine
 
+    from . import label_utils as lu
+
     eng = Engine.get()
     rank, world = _dist_info(group)
     all_ids = sorted(atlas_set)
@@ -134,7 +136,28 @@ def run_segmentation(img, atlas_set, settings=MULTIATLAS_SETTINGS_DEFAULTS, grou
     structures = sorted({k for a in all_ids for k in atlas_set[a] if k != "CT Image"})
     fs = settings["label_fusion_settings"]
     vote_type, vote_params = fs.get("vote_type", "unweighted"), fs.get("vote_params", None)
-    target = eng.to_device(img)
+    full = eng.to_device(img)
+    target, crop_box = full, None
+    if settings.get("auto_crop_target_image_settings") and settings.get("linear_registration_settings"):
+        # Step 1 (run.py:200-246): quick similarity registration of up to 8 atlases, bounding box of the mean registered
+        # image > -1000 expanded by expansion_mm, crop the target.  Sharded: local sums, one all-reduce.
+        from . import linear
+
+        quick = {"reg_method": "similarity", "shrink_factors": [8], "smooth_sigmas": [0], "sampling_rate": 0.75, "default_value": -1000,
+                 "number_of_iterations": 25, "final_interp": sk.sitkLinear, "metric": "mean_squares", "optimiser": "gradient_descent_line_search"}
+        crop_ids = all_ids[: min(8, len(all_ids))]
+        acc = eng.zeros(full.tensor.shape, np.float32)
+        for a in crop_ids:
+            if a in mine:
+                reg_image, _ = linear.linear_registration(full, eng.to_device(atlas_set[a]["CT Image"]), **quick)
+                with torch.cuda.stream(eng.stream):
+                    acc += eng.cast(reg_image, np.float32).tensor
+        with torch.cuda.stream(eng.stream):
+            exchange_sum([acc], group)
+            combined = full.like((acc / float(len(crop_ids)) > -1000).to(torch.uint8), np.uint8, False)
+        crop_size, crop_index = lu.label_to_roi(combined, expansion_mm=settings["auto_crop_target_image_settings"]["expansion_mm"])
+        target = lu.crop_to_roi(full, crop_size, crop_index)
+        crop_box = (crop_size, crop_index)
     tgt_f32 = eng.cast(target, np.float32)
     z, y, x = target.tensor.shape
 
@@ -180,10 +203,36 @@ def run_segmentation(img, atlas_set, settings=MULTIATLAS_SETTINGS_DEFAULTS, grou
         for s in structures:
             results_prob[s] = eng.vote_finalize(nums[s], dens[s], target, 1.0, 1e-4)
 
-    # ---- binary masks (run.py:370-404): process_probability_image on the device, only the masks travel ------
-    results, probs_host = {}, {}
+    # ---- binary masks (run.py:370-404): process_probability_image on the device, pasted back into the uncropped grid ----
+    masks = {}
     for s in structures:
         thr = fs.get("optimal_threshold", {}).get(s, 0.5)
-        results[s] = eng.to_host(eng.process_probability(results_prob[s], thr))
+        masks[s] = eng.process_probability(results_prob[s], thr)
+        if crop_box is not None:
+            with torch.cuda.stream(eng.stream):
+                tmpl_b = full.like(torch.zeros(full.tensor.shape, dtype=torch.uint8, device=full.tensor.device), np.uint8, False)
+                tmpl_p = full.like(torch.zeros(full.tensor.shape, dtype=results_prob[s].tensor.dtype, device=full.tensor.device),
+                                   results_prob[s].np_dtype, False)
+            masks[s] = eng.region_copy(masks[s], (0, 0, 0), tmpl_b, crop_box[1], crop_box[0])
+            results_prob[s] = eng.region_copy(results_prob[s], (0, 0, 0), tmpl_p, crop_box[1], crop_box[0])
+
+    # ---- post-processing (run.py:409-437) ----------------------------------------------------------------------------
+    pp = settings.get("postprocessing_settings") or {}
+    if pp.get("run_postprocessing"):
+        radius = [int(pp["binaryfillhole_mm"] / sp) for sp in full.GetSpacing()]
+        for s in pp.get("structures_for_binaryfillhole", []):
+            if s not in masks:
+                continue
+            # sitk.RelabelComponent(sitk.ConnectedComponent(x)) == 1, then BinaryMorphologicalClosing
+            masks[s] = eng.binary_closing(eng.largest_component(masks[s]), radius, lu.ball_offsets(radius))
+        oc = [s for s in pp.get("structures_for_overlap_correction", [])]
+        if len(oc) >= 2:
+            fixed = lu.correct_volume_overlap({s: masks[s] for s in oc})
+            for s in oc:
+                masks[s] = fixed[s]
+
+    results, probs_host = {}, {}
+    for s in structures:
+        results[s] = eng.to_host(masks[s])
         probs_host[s] = eng.to_host(results_prob[s])
     return results, probs_host

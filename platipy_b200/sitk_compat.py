@@ -274,6 +274,11 @@ class CompositeTransform(Transform):
         return out
 
 
+def is_native_sitk(obj):
+    """True for a real ``SimpleITK.Image`` (only when SimpleITK is importable)."""
+    return bool(HAVE_SITK and isinstance(obj, _sitk.Image))
+
+
 # -- boundary conversion -----------------------------------------------------------------------------
 def to_native(image):
     """Accept a stand-in ``Image`` or a real ``SimpleITK.Image``; return a stand-in ``Image``."""

@@ -103,3 +103,16 @@ def test_run_segmentation_with_linear_prealignment(engine):
         dice = 2.0 * (a & b).sum() / max(a.sum() + b.sum(), 1)
         print(f"S{k}: Dice {dice:.3f}")
         assert dice > 0.9, (k, dice)
+    # the whole reference flow: auto-crop (run.py:200-246), paste back (run.py:387-404), post-processing (run.py:409-437)
+    settings["auto_crop_target_image_settings"] = {"expansion_mm": [4, 4, 6]}
+    settings["postprocessing_settings"] = {"run_postprocessing": True, "binaryfillhole_mm": 2, "structures_for_binaryfillhole": ["S0"],
+                                           "structures_for_overlap_correction": ["S0", "S1"]}
+    results2, probs2 = multiatlas.run_segmentation(target, atlas_set, settings)
+    for k, lab in enumerate(truth):
+        assert results2[f"S{k}"].GetSize() == target.GetSize() and probs2[f"S{k}"].GetSize() == target.GetSize()
+        assert results2[f"S{k}"].GetPixelID() == sk.sitkUInt8
+        a, b = results2[f"S{k}"].array > 0, lab.array > 0
+        dice = 2.0 * (a & b).sum() / max(a.sum() + b.sum(), 1)
+        print(f"S{k} (auto-crop + post-processing): Dice {dice:.3f}")
+        assert dice > 0.88, (k, dice)
+    assert not np.any((results2["S0"].array > 0) & (results2["S1"].array > 0))
