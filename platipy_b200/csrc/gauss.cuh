@@ -581,14 +581,15 @@ inline int launch_conv3d_zmarch(b200reg_ctx* ctx, const double* a, const double*
     int nchunks = (ctx->sm_count * 8 + tiles - 1) / tiles;
     const int min_chunk = tiles * ((nz + 15) / 16) >= ctx->sm_count * 4 ? 16 : 4;
     const int max_chunks = (nz + min_chunk - 1) / min_chunk;
-    if (min_chunk == 16) {
+    {
         // Every CTA of this kernel takes the same time, so the launch runs in ceil(CTAs / resident CTAs) rounds of
-        // (chunk + halo) plane steps: pick the chunk count with the least total (measured: 3.25 -> 3.20 ms / iteration at
-        // 512 x 512 x 256, where 3 chunks give 7.8 -> 8 rounds instead of 5.2 -> 6).
+        // (chunk + halo) plane steps: pick the chunk count with the least total.  Measured at 512 x 512 x 256: 3 chunks
+        // (7.8 -> 8 rounds) instead of 2 (5.2 -> 6 rounds), 3.25 -> 3.20 ms / iteration; at 128 x 128 x 64 the model picks
+        // 6 chunks = 288 CTAs, all resident in one round of 15 steps, instead of three rounds of 8.
         const long slots = (long)ctx->sm_count * 2;
         long best_cost = -1;
         int best_k = nchunks;
-        for (int k = 1; k <= 8 && k <= max_chunks; ++k) {
+        for (int k = 1; k <= 32 && k <= max_chunks; ++k) {
             const long rounds = ((long)tiles * k + slots - 1) / slots;
             const long cost = rounds * ((nz + k - 1) / k + 2 * kc[2].r);
             if (best_cost < 0 || cost < best_cost) {

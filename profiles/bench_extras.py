@@ -65,6 +65,29 @@ t0 = time.perf_counter()
 _, info = eng.staple(rng_labels, threshold=1e-4, rescale=True)
 eng.synchronize()
 ms_staple = 1e3 * (time.perf_counter() - t0)
+# ---- rows added in the second session (512 x 512 x 256 each) --------------------------------------------------------
+from platipy_b200 import fusion, label_utils as lu, linear
+
+prob = eng.vote_finalize(num, den, dF, 1.0, 1e-4)
+ms_ppi = timed(lambda: eng.process_probability(prob, 0.5), 3)
+ms_fill = timed(lambda: eng.binary_fillhole(labels[0]), 3)
+ms_cc = timed(lambda: eng.largest_component(labels[0]), 3)
+ms_block = timed(lambda: eng.weight_map_block(dF, dM, (5, 5, 5), 1e12, 6), 3)
+ms_bspline = timed(lambda: reg.apply_transform(dM, dF, tfm, -1000, sk.sitkBSpline), 3)
+ms_closing = timed(lambda: eng.binary_closing(labels[0], (3, 3, 3), lu.ball_offsets((3, 3, 3))), 2)
+ms_overlap = timed(lambda: eng.resolve_overlap(labels[:5]), 3)
+t0 = time.perf_counter()
+_, ltfm = linear.linear_registration(dF, dM, reg_method="similarity", shrink_factors=[8, 2, 1], smooth_sigmas=[4, 2, 0], default_value=-1000)
+eng.synchronize()
+ms_linear = 1e3 * (time.perf_counter() - t0)
+n_eval = sum(len(h) for h in linear.LAST_HISTORY)
+ms_metric = timed(lambda: eng.linreg_meansq(dF, dM, np.eye(3), np.zeros(3), np.eye(3), np.zeros(3), None, None, 4), 10)
+extra = {"process_probability_image_ms": ms_ppi, "binary_fillhole_ms": ms_fill, "largest_component_ms": ms_cc,
+         "weight_map_block_r5_ms": ms_block, "apply_transform_bspline_f32_ms": ms_bspline, "binary_closing_r3_ms": ms_closing,
+         "correct_volume_overlap_5_ms": ms_overlap, "linear_registration_similarity_8_2_1_ms": ms_linear,
+         "linear_registration_iterations": n_eval, "linreg_meansq_fullres_stride4_ms": ms_metric,
+         "linreg_meansq_fullres_Gsamples_per_s": N / 4 / (ms_metric * 1e-3) / 1e9}
+print(json.dumps(extra))
 print(json.dumps({"apply_transform_21_calls_ms": ms_calls, "apply_transform_21_calls_GBs": bytes_calls / ms_calls / 1e6,
                   "apply_transform_batched_ms": ms_batch, "apply_transform_batched_GBs": bytes_batch / ms_batch / 1e6,
                   "voxels_per_s_batched": 21 * N / (ms_batch * 1e-3),
