@@ -70,6 +70,7 @@ struct b200reg_ctx {
     int pf_force = 0;              // B200REG_PF_FORCE=n: force kernel prefetches W / F n steps ahead into L2
     int warp_march = 0;            // B200REG_WARP_MARCH=n: z-marching warp kernel with n planes per thread (0: one-shot kernel)
     int zm_chunks = 0;             // B200REG_ZM_CHUNKS=n: z-chunks per tile column of the fused smoothing kernel (0: automatic)
+    bool zm_split_rows = false;    // B200REG_ZM_SPLIT_ROWS=1: third-generation fused smoothing kernel (pair-split shared rows; measured equal)
     bool force_zm1 = false;        // B200REG_FORCE_ZM1=1: first-generation fused smoothing kernel
 };
 

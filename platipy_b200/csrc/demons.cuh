@@ -977,7 +977,8 @@ inline int demons_prepare(b200reg_ctx* ctx, const b200reg_geom& gF, int n_iters,
     B200_TRY(ws->P1.alloc(ctx, 3 * n * sizeof(double)));
     B200_TRY(ws->W.alloc(ctx, n * sizeof(float)));
     const dim3 g = grid3(gF.size[0], gF.size[1], gF.size[2]);
-    ws->nblocks = (size_t)g.x * g.y * g.z + border_blocks(gF.size[0], gF.size[1], gF.size[2]) + 1;  // either update path + the border kernel
+    // either update path; the split path appends whole z slices of border blocks (demons_split.cuh)
+    ws->nblocks = (size_t)g.x * g.y * g.z + border_blocks(gF.size[0], gF.size[1], gF.size[2]) + (size_t)g.x * g.y + 1;
     B200_TRY(ws->partials.alloc(ctx, ws->nblocks * 3 * sizeof(double)));
     B200_TRY(ws->ctrl.alloc(ctx, sizeof(DemonsCtrl)));
     if (want_trace) B200_TRY(ws->trace.alloc(ctx, sizeof(double) * 2 * (size_t)(n_iters > 0 ? n_iters : 1)));

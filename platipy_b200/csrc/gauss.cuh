@@ -526,6 +526,163 @@ __global__ void __launch_bounds__(Zm2Threads<R>::value, 2) conv3d_zm2_kernel(con
     }
 }
 
+// ---- fused 3-D smoothing, third generation: even / odd pair-split shared rows ------------------------------------------
+// Same scheme, same operation order and bit-identical results as conv3d_zm2_kernel; what changes is the shared-memory
+// layout.  Every row (staged input rows and x-pass output rows alike) stores its 16-byte pairs of doubles split by
+// parity -- even pairs first, odd pairs after -- so that a thread can own FOUR consecutive x outputs: its 2 + RP input
+// pairs 2t, 2t+1, ... alternate between the two halves, and within each half the lanes of a warp read consecutive
+// 16-byte words (conflict-free LDS.128).  The x pass then needs 2 + RP 128-bit loads per 4 outputs instead of
+// 2 (1 + RP) (R = 2: 4 instead of 6; with the add fused: 8 instead of 12); stores and the y pass keep their wavefront
+// counts.  Shared-memory wavefronts per 128 outputs: 67 -> 57 (plain), 108 -> 88 (add).
+// Row geometry of a pair-split row that holds W doubles: the odd half starts at the first offset >= the even half's
+// size that is 8 doubles (mod 16), so that the 8 + 8 doubles a half-warp touches in the two halves fall on disjoint
+// banks (64-bit accesses are served per half-warp); the row stride keeps 16-byte alignment.
+template <int W>
+struct Zm3Row {
+    static constexpr int NE = (W / 2 + 1) / 2;                               // even pairs
+    static constexpr int NO = W / 2 - NE;                                    // odd pairs
+    static constexpr int OBASE = ((2 * NE + 7) / 16) * 16 + 8 >= 2 * NE ? ((2 * NE + 7) / 16) * 16 + 8 : ((2 * NE + 7) / 16) * 16 + 24;  // doubles
+    static constexpr int STRIDE = OBASE + 2 * NO;                            // doubles (even)
+};
+template <int W>
+__device__ __forceinline__ int zm3_pos(int xx)
+{
+    // position (in doubles) of x coordinate xx inside a pair-split row
+    const int p = xx >> 1;
+    return ((p & 1) ? Zm3Row<W>::OBASE + ((p >> 1) << 1) : ((p >> 1) << 1)) + (xx & 1);
+}
+template <int R, int RZ, bool ADD>
+__global__ void __launch_bounds__(Zm2Threads<R>::value, 2) conv3d_zm3_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out,
+                                                               int nx, int ny, int nz, int zchunk, int nchunks,
+                                                               const __grid_constant__ SmallCoeffs kc, const DemonsCtrl* __restrict__ ctrl, int it)
+{
+    if (ctrl && it >= ctrl->halt_iter) return;
+    constexpr int RP = (R + 1) & ~1;
+    constexpr int AW = ZM_TX + 2 * RP, AH = ZM_TY + 2 * R;
+    constexpr int AS = Zm3Row<AW>::STRIDE, BS = Zm3Row<ZM_TX>::STRIDE;   // row strides (doubles)
+    constexpr int NA = AS * AH;                    // doubles per staged plane
+    constexpr int NEL = AW * AH;                   // elements per staged plane
+    constexpr int NR = 2 * RZ + 1;
+    constexpr int NT = Zm2Threads<R>::value;
+    constexpr int NLD = (NEL + NT - 1) / NT;
+    constexpr int NPAIR = 2 + RP;                  // input pairs of one x-pass task
+    constexpr int OA2 = Zm3Row<AW>::OBASE / 2;     // odd half of a staged row, in pairs
+    constexpr int OB2 = Zm3Row<ZM_TX>::OBASE / 2;  // odd half of an x-pass output row, in pairs
+    extern __shared__ __align__(16) double zm_smem[];
+    double* Aa = zm_smem;                       // [2][NA]
+    double* Ab = zm_smem + 2 * NA;              // [2][NA] (ADD only)
+    double* B = zm_smem + (ADD ? 4 : 2) * NA;   // [AH][BS]
+
+    const int tid = threadIdx.x;
+    const int x0 = blockIdx.x * ZM_TX, y0 = blockIdx.y * ZM_TY;
+    const int comp = blockIdx.z / nchunks, chunk = blockIdx.z % nchunks;
+    const int z0 = chunk * zchunk, z1 = min(nz, z0 + zchunk);
+    const size_t plane = (size_t)nx * ny, vol = plane * nz;
+    const double* __restrict__ ap = a + (size_t)comp * vol;
+    const double* __restrict__ bp = ADD ? b + (size_t)comp * vol : nullptr;
+    double* __restrict__ op = out + (size_t)comp * vol;
+
+    int goff[NLD], spos[NLD];
+#pragma unroll
+    for (int l = 0; l < NLD; ++l) {
+        const int e = tid + l * NT;
+        const int yy = e / AW, xx = e - yy * AW;
+        int gx = x0 - RP + xx, gy = y0 - R + yy;
+        gx = gx < 0 ? 0 : (gx > nx - 1 ? nx - 1 : gx);
+        gy = gy < 0 ? 0 : (gy > ny - 1 ? ny - 1 : gy);
+        goff[l] = e < NEL ? gy * nx + gx : -1;
+        spos[l] = yy * AS + zm3_pos<AW>(xx);
+    }
+    auto stage = [&](int z, int buf) {
+        const int zc = z < 0 ? 0 : (z > nz - 1 ? nz - 1 : z);
+        const size_t zo = (size_t)zc * plane;
+#pragma unroll
+        for (int l = 0; l < NLD; ++l)
+            if (goff[l] >= 0) {
+                cp_async8(Aa + buf * NA + spos[l], ap + zo + goff[l]);
+                if (ADD) cp_async8(Ab + buf * NA + spos[l], bp + zo + goff[l]);
+            }
+        cp_async_commit();
+    };
+
+    // y/z-pass ownership: column x = tid % 64, rows 4*yb .. 4*yb+3
+    const int ox = tid & (ZM_TX - 1), yb = tid >> 6;
+    const int gx = x0 + ox;
+    const int bpos = zm3_pos<ZM_TX>(ox);
+    double ring[NR][4];
+    const int zbeg = z0 - RZ, nsteps = (z1 - z0) + 2 * RZ;
+    stage(zbeg, 0);
+    for (int q0 = 0; q0 < nsteps; q0 += NR) {
+#pragma unroll
+        for (int s = 0; s < NR; ++s) {
+            const int q = q0 + s;
+            if (q < nsteps) {
+                const int buf = q & 1;
+                cp_async_wait_all();
+                __syncthreads();
+                if (q + 1 < nsteps) stage(zbeg + q + 1, buf ^ 1);
+                // ---- x pass: task (row yy, quad cx) -> outputs 4cx .. 4cx+3 from input pairs 2cx .. 2cx+1+RP
+                {
+                    const int yy = tid >> 4, cx = tid & 15;
+                    const double2* ra = reinterpret_cast<const double2*>(Aa + buf * NA + yy * AS);
+                    const double2* rb = reinterpret_cast<const double2*>(Ab + buf * NA + yy * AS);
+                    double w[2 * NPAIR];
+#pragma unroll
+                    for (int v = 0; v < NPAIR; ++v) {
+                        // pair 2cx + v: even v -> even half at index cx + v/2, odd v -> odd half at index cx + (v-1)/2
+                        const int idx = (v & 1) ? OA2 + cx + (v >> 1) : cx + (v >> 1);
+                        double2 t2 = ra[idx];
+                        if (ADD) {
+                            const double2 u2 = rb[idx];
+                            t2.x = t2.x + u2.x;
+                            t2.y = t2.y + u2.y;
+                        }
+                        w[2 * v] = t2.x;
+                        w[2 * v + 1] = t2.y;
+                    }
+                    double o[4];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        double sum = kc.k[0][0] * w[j + (RP - R)];
+#pragma unroll
+                        for (int t = 1; t <= 2 * R; ++t) sum += kc.k[0][t] * w[j + (RP - R) + t];
+                        o[j] = sum;
+                    }
+                    double2* wb = reinterpret_cast<double2*>(B + yy * BS);
+                    wb[cx] = make_double2(o[0], o[1]);         // pair 2cx   (even half)
+                    wb[OB2 + cx] = make_double2(o[2], o[3]);   // pair 2cx+1 (odd half)
+                }
+                __syncthreads();
+                // ---- y pass: sliding window over 4 + 2R rows of this thread's column
+                if (tid < ZM_NT) {
+                    double col[4 + 2 * R];
+#pragma unroll
+                    for (int i = 0; i < 4 + 2 * R; ++i) col[i] = B[(4 * yb + i) * BS + bpos];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        double sum = kc.k[1][0] * col[j];
+#pragma unroll
+                        for (int t = 1; t <= 2 * R; ++t) sum += kc.k[1][t] * col[j + t];
+                        ring[s][j] = sum;
+                    }
+                }
+                // ---- z pass over the ring (slot s is the newest plane; oldest is slot (s + 1) % NR)
+                if (tid < ZM_NT && q >= 2 * RZ) {
+                    const int zo = zbeg + q - RZ;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        double sum = kc.k[2][0] * ring[(s + 1) % NR][j];
+#pragma unroll
+                        for (int t = 1; t < NR; ++t) sum += kc.k[2][t] * ring[(s + 1 + t) % NR][j];
+                        const int gy = y0 + 4 * yb + j;
+                        if (gx < nx && gy < ny) op[(size_t)zo * plane + (size_t)gy * nx + gx] = sum;
+                    }
+                }
+            }
+        }
+    }
+}
+
 template <int R, int RZ>
 inline int launch_zm2_rz(b200reg_ctx* ctx, const double* a, const double* b, double* out, int nx, int ny, int nz, dim3 g, int zchunk, int nchunks,
                          const SmallCoeffs& sc, const DemonsCtrl* ctrl, int it)
@@ -533,7 +690,18 @@ inline int launch_zm2_rz(b200reg_ctx* ctx, const double* a, const double* b, dou
     constexpr int RP = (R + 1) & ~1;
     constexpr int NA = (ZM_TX + 2 * RP) * (ZM_TY + 2 * R);
     constexpr int NB = (ZM_TY + 2 * R) * ZM_TX;
-    if (b && ctx->zm_regadd) {
+    if (ctx->zm_split_rows) {
+        constexpr int NA3 = Zm3Row<ZM_TX + 2 * RP>::STRIDE * (ZM_TY + 2 * R), NB3 = Zm3Row<ZM_TX>::STRIDE * (ZM_TY + 2 * R);
+        if (b) {
+            constexpr size_t smem = (size_t)(4 * NA3 + NB3) * sizeof(double);
+            B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm3_kernel<R, RZ, true>, smem));
+            conv3d_zm3_kernel<R, RZ, true><<<g, Zm2Threads<R>::value, smem, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it);
+        } else {
+            constexpr size_t smem = (size_t)(2 * NA3 + NB3) * sizeof(double);
+            B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm3_kernel<R, RZ, false>, smem));
+            conv3d_zm3_kernel<R, RZ, false><<<g, Zm2Threads<R>::value, smem, ctx->stream>>>(a, nullptr, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it);
+        }
+    } else if (b && ctx->zm_regadd) {
         constexpr size_t smem = (size_t)(2 * NA + NB) * sizeof(double);
         B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, 2>, smem));
         conv3d_zm2_kernel<R, RZ, 2><<<g, Zm2Threads<R>::value, smem, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, 0);

@@ -29,3 +29,8 @@ for r in rows[2:]:
             except ValueError:
                 pass
     print('  stalls/issue:', ', '.join(f'{n} {v:.2f}' for v, n in sorted(st, reverse=True)[:6]))
+    for k in ['l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'smsp__inst_executed_op_shared_ld.sum',
+              'smsp__inst_executed_op_shared_st.sum', 'smsp__inst_executed_op_ldgsts.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_lgds.sum',
+              'l1tex__data_pipe_lsu_wavefronts.sum', 'smsp__inst_executed_op_global_st.sum']:
+        if k in hdr:
+            print(f'  {k} {r[hdr.index(k)]}')
