@@ -71,6 +71,7 @@ struct b200reg_ctx {
     int warp_march = 0;            // B200REG_WARP_MARCH=n: z-marching warp kernel with n planes per thread (0: one-shot kernel)
     int zm_chunks = 0;             // B200REG_ZM_CHUNKS=n: z-chunks per tile column of the fused smoothing kernel (0: automatic)
     bool zm_split_rows = false;    // B200REG_ZM_SPLIT_ROWS=1: third-generation fused smoothing kernel (pair-split shared rows; measured equal)
+    bool zm_tx32 = true;           // B200REG_ZM_TX32=0: 64-wide tiles (320 threads, 2 CTAs per SM) in the fused smoothing kernel; 32-wide: 4 CTAs per SM, -1 %
     bool force_zm1 = false;        // B200REG_FORCE_ZM1=1: first-generation fused smoothing kernel
 };
 

@@ -296,11 +296,12 @@ __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gsrc)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;\n" ::: "memory"); }
 
-// Threads per CTA: one x-pass task (row, column group) per thread -> (TY + 2R) * 16 threads; the first 256 of them
-// also own the tile's voxels in the y and z passes.
-template <int R>
+// Threads per CTA: one x-pass task (row, column group) per thread -> (TY + 2R) * (TXW / 4) threads; the first 4 * TXW of
+// them also own the tile's voxels in the y and z passes.  TXW = 64: 2 CTAs per SM; TXW = 32: 4 CTAs per SM (same warps,
+// twice the independent barrier domains).
+template <int R, int TXW = ZM_TX>
 struct Zm2Threads {
-    static constexpr int value = (ZM_TY + 2 * R) * (ZM_TX / 4);
+    static constexpr int value = (ZM_TY + 2 * R) * (TXW / 4);
 };
 // ---- TMA bulk-copy staging (cp.async.bulk -> SASS UBLKCP) with mbarrier completion -----------------------------------
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
@@ -337,8 +338,8 @@ __device__ __forceinline__ void tma_bulk_g2s(double* smem_dst, const double* gsr
 // MODE 0: out = G(a).  MODE 1: out = G(a + b), both operands staged with cp.async and added in the x pass.
 // MODE 2: out = G(a + b), the next plane's operands are loaded into registers while the current plane is processed and
 // their sum is what gets staged: one shared buffer less, half the staging writes and x-pass reads of MODE 1.
-template <int R, int RZ, int MODE>
-__global__ void __launch_bounds__(Zm2Threads<R>::value, 2) conv3d_zm2_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out,
+template <int R, int RZ, int MODE, int TXW>
+__global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, 128 / TXW) conv3d_zm2_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out,
                                                                int nx, int ny, int nz, int zchunk, int nchunks,
                                                                const __grid_constant__ SmallCoeffs kc, const DemonsCtrl* __restrict__ ctrl, int it, int use_tma)
 {
@@ -346,9 +347,10 @@ __global__ void __launch_bounds__(Zm2Threads<R>::value, 2) conv3d_zm2_kernel(con
     constexpr bool ADD = MODE == 1;     // second operand staged in shared memory
     constexpr bool REGADD = MODE == 2;  // operands summed in registers before staging
     constexpr int RP = (R + 1) & ~1;  // x halo padded to an even count: 16-byte aligned shared rows
-    constexpr int AW = ZM_TX + 2 * RP, AH = ZM_TY + 2 * R, NA = AW * AH;
+    constexpr int AW = TXW + 2 * RP, AH = ZM_TY + 2 * R, NA = AW * AH;
     constexpr int NR = 2 * RZ + 1;
-    constexpr int NT = Zm2Threads<R>::value;
+    constexpr int NT = Zm2Threads<R, TXW>::value;
+    constexpr int NYZ = 4 * TXW;  // threads that own voxels in the y / z passes
     constexpr int NLD = (NA + NT - 1) / NT;
     extern __shared__ __align__(16) double zm_smem[];
     double* Aa = zm_smem;                       // [2][NA]
@@ -356,7 +358,7 @@ __global__ void __launch_bounds__(Zm2Threads<R>::value, 2) conv3d_zm2_kernel(con
     double* B = zm_smem + (ADD ? 4 : 2) * NA;   // [AH][TX]
 
     const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * ZM_TX, y0 = blockIdx.y * ZM_TY;
+    const int x0 = blockIdx.x * TXW, y0 = blockIdx.y * ZM_TY;
     const int comp = blockIdx.z / nchunks, chunk = blockIdx.z % nchunks;
     const int z0 = chunk * zchunk, z1 = min(nz, z0 + zchunk);
     const size_t plane = (size_t)nx * ny, vol = plane * nz;
@@ -379,7 +381,7 @@ __global__ void __launch_bounds__(Zm2Threads<R>::value, 2) conv3d_zm2_kernel(con
     // clamp in y simply by their source address.  Border tiles keep the per-element cp.async (LDGSTS) path.
     __shared__ __align__(8) unsigned long long full_bar[2];
 #ifdef B200REG_ENABLE_ZM_TMA  // measured slower than the cp.async path (4.46 vs 3.96 ms / iteration): compiled out by default
-    const bool interior = use_tma && x0 - RP >= 0 && x0 + ZM_TX + RP <= nx && (nx % 2) == 0;
+    const bool interior = use_tma && x0 - RP >= 0 && x0 + TXW + RP <= nx && (nx % 2) == 0;
 #else
     constexpr bool interior = false;
     (void)use_tma;
@@ -436,7 +438,7 @@ __global__ void __launch_bounds__(Zm2Threads<R>::value, 2) conv3d_zm2_kernel(con
     };
 
     // y/z-pass ownership: column x = tid % 64, rows 4*yb .. 4*yb+3
-    const int ox = tid & (ZM_TX - 1), yb = tid >> 6;
+    const int ox = tid & (TXW - 1), yb = tid / TXW;
     const int gx = x0 + ox;
     double ring[NR][4];
     const int zbeg = z0 - RZ, nsteps = (z1 - z0) + 2 * RZ;
@@ -464,10 +466,10 @@ __global__ void __launch_bounds__(Zm2Threads<R>::value, 2) conv3d_zm2_kernel(con
                 // ---- x pass: per task two output pairs {2cx, 2cx+1} and {32+2cx, 32+2cx+1} of one row (rows incl. the
                 // y halo).  Lanes read consecutive 16-byte words: conflict-free 128-bit shared loads and stores.
                 {
-                    const int yy = tid >> 4, cx = tid & 15;
+                    const int yy = tid / (TXW / 4), cx = tid & (TXW / 4 - 1);
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
-                        const int xb = 2 * cx + h * (ZM_TX / 2);
+                        const int xb = 2 * cx + h * (TXW / 2);
                         const double2* ra = reinterpret_cast<const double2*>(Aa + buf * NA + yy * AW + xb);
                         double w[2 + 2 * RP];
 #pragma unroll
@@ -490,15 +492,15 @@ __global__ void __launch_bounds__(Zm2Threads<R>::value, 2) conv3d_zm2_kernel(con
                             for (int t = 1; t <= 2 * R; ++t) sum += kc.k[0][t] * w[j + (RP - R) + t];
                             o[j] = sum;
                         }
-                        *reinterpret_cast<double2*>(B + yy * ZM_TX + xb) = make_double2(o[0], o[1]);
+                        *reinterpret_cast<double2*>(B + yy * TXW + xb) = make_double2(o[0], o[1]);
                     }
                 }
                 __syncthreads();
                 // ---- y pass: sliding window over 4 + 2R rows of this thread's column
-                if (tid < ZM_NT) {
+                if (tid < NYZ) {
                     double col[4 + 2 * R];
 #pragma unroll
-                    for (int i = 0; i < 4 + 2 * R; ++i) col[i] = B[(4 * yb + i) * ZM_TX + ox];
+                    for (int i = 0; i < 4 + 2 * R; ++i) col[i] = B[(4 * yb + i) * TXW + ox];
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         double sum = kc.k[1][0] * col[j];
@@ -508,7 +510,7 @@ __global__ void __launch_bounds__(Zm2Threads<R>::value, 2) conv3d_zm2_kernel(con
                     }
                 }
                 // ---- z pass over the ring (slot s is the newest plane; oldest is slot (s + 1) % NR)
-                if (tid < ZM_NT && q >= 2 * RZ) {
+                if (tid < NYZ && q >= 2 * RZ) {
                     const int zo = zbeg + q - RZ;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
@@ -683,13 +685,35 @@ __global__ void __launch_bounds__(Zm2Threads<R>::value, 2) conv3d_zm3_kernel(con
     }
 }
 
+template <int R, int RZ, int TXW>
+inline int launch_zm2_tx(b200reg_ctx* ctx, const double* a, const double* b, double* out, int nx, int ny, int nz, dim3 g, int zchunk, int nchunks,
+                         const SmallCoeffs& sc, const DemonsCtrl* ctrl, int it)
+{
+    constexpr int RP = (R + 1) & ~1;
+    constexpr int NA = (TXW + 2 * RP) * (ZM_TY + 2 * R);
+    constexpr int NB = (ZM_TY + 2 * R) * TXW;
+    constexpr int NT = Zm2Threads<R, TXW>::value;
+    g.x = (nx + TXW - 1) / TXW;
+    if (b && ctx->zm_regadd) {
+        constexpr size_t smem = (size_t)(2 * NA + NB) * sizeof(double);
+        B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, 2, TXW>, smem));
+        conv3d_zm2_kernel<R, RZ, 2, TXW><<<g, NT, smem, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, 0);
+    } else if (b) {
+        constexpr size_t smem = (size_t)(4 * NA + NB) * sizeof(double);
+        B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, 1, TXW>, smem));
+        conv3d_zm2_kernel<R, RZ, 1, TXW><<<g, NT, smem, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, ctx->zm_tma ? 1 : 0);
+    } else {
+        constexpr size_t smem = (size_t)(2 * NA + NB) * sizeof(double);
+        B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, 0, TXW>, smem));
+        conv3d_zm2_kernel<R, RZ, 0, TXW><<<g, NT, smem, ctx->stream>>>(a, nullptr, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, ctx->zm_tma ? 1 : 0);
+    }
+    return B200REG_OK;
+}
 template <int R, int RZ>
 inline int launch_zm2_rz(b200reg_ctx* ctx, const double* a, const double* b, double* out, int nx, int ny, int nz, dim3 g, int zchunk, int nchunks,
                          const SmallCoeffs& sc, const DemonsCtrl* ctrl, int it)
 {
     constexpr int RP = (R + 1) & ~1;
-    constexpr int NA = (ZM_TX + 2 * RP) * (ZM_TY + 2 * R);
-    constexpr int NB = (ZM_TY + 2 * R) * ZM_TX;
     if (ctx->zm_split_rows) {
         constexpr int NA3 = Zm3Row<ZM_TX + 2 * RP>::STRIDE * (ZM_TY + 2 * R), NB3 = Zm3Row<ZM_TX>::STRIDE * (ZM_TY + 2 * R);
         if (b) {
@@ -701,20 +725,10 @@ inline int launch_zm2_rz(b200reg_ctx* ctx, const double* a, const double* b, dou
             B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm3_kernel<R, RZ, false>, smem));
             conv3d_zm3_kernel<R, RZ, false><<<g, Zm2Threads<R>::value, smem, ctx->stream>>>(a, nullptr, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it);
         }
-    } else if (b && ctx->zm_regadd) {
-        constexpr size_t smem = (size_t)(2 * NA + NB) * sizeof(double);
-        B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, 2>, smem));
-        conv3d_zm2_kernel<R, RZ, 2><<<g, Zm2Threads<R>::value, smem, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, 0);
-    } else if (b) {
-        constexpr size_t smem = (size_t)(4 * NA + NB) * sizeof(double);
-        B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, 1>, smem));
-        conv3d_zm2_kernel<R, RZ, 1><<<g, Zm2Threads<R>::value, smem, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, ctx->zm_tma ? 1 : 0);
-    } else {
-        constexpr size_t smem = (size_t)(2 * NA + NB) * sizeof(double);
-        B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, 0>, smem));
-        conv3d_zm2_kernel<R, RZ, 0><<<g, Zm2Threads<R>::value, smem, ctx->stream>>>(a, nullptr, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, ctx->zm_tma ? 1 : 0);
+        return B200REG_OK;
     }
-    return B200REG_OK;
+    if (ctx->zm_tx32) return launch_zm2_tx<R, RZ, 32>(ctx, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it);
+    return launch_zm2_tx<R, RZ, 64>(ctx, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it);
 }
 template <int R>
 inline int launch_zm2_r(b200reg_ctx* ctx, int rz, const double* a, const double* b, double* out, int nx, int ny, int nz, dim3 g, int zchunk,
@@ -742,7 +756,8 @@ inline int launch_conv3d_zmarch(b200reg_ctx* ctx, const double* a, const double*
         sc.r[ax] = kc[ax].r;
         for (int t = 0; t <= 2 * kc[ax].r; ++t) sc.k[ax][t] = kc[ax].k[t];
     }
-    const int tiles = ((nx + ZM_TX - 1) / ZM_TX) * ((ny + ZM_TY - 1) / ZM_TY) * nplanes;
+    const int txw = (ctx->zm_tx32 && !ctx->zm_split_rows) ? 32 : ZM_TX;
+    const int tiles = ((nx + txw - 1) / txw) * ((ny + ZM_TY - 1) / ZM_TY) * nplanes;
     // enough CTAs for ~4 waves of 2 CTAs/SM, but chunks of at least 16 planes (each chunk re-reads 2*rz planes)
     // (coarse pyramid levels have so few tiles that chunks as short as 4 planes are worth their halo planes: the
     // whole field is L2 resident there and the GPU is otherwise idle)
@@ -754,7 +769,7 @@ inline int launch_conv3d_zmarch(b200reg_ctx* ctx, const double* a, const double*
         // (chunk + halo) plane steps: pick the chunk count with the least total.  Measured at 512 x 512 x 256: 3 chunks
         // (7.8 -> 8 rounds) instead of 2 (5.2 -> 6 rounds), 3.25 -> 3.20 ms / iteration; at 128 x 128 x 64 the model picks
         // 6 chunks = 288 CTAs, all resident in one round of 15 steps, instead of three rounds of 8.
-        const long slots = (long)ctx->sm_count * 2;
+        const long slots = (long)ctx->sm_count * (txw == 32 ? 4 : 2);
         long best_cost = -1;
         int best_k = nchunks;
         for (int k = 1; k <= 32 && k <= max_chunks; ++k) {
