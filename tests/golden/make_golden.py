@@ -51,5 +51,35 @@ def main():
     print("wrote demons_small.npz", dvf.array.shape, float(np.abs(dvf.array).max()))
 
 
+def main_rows():
+    """Second fixture: the rows added around the Demons loop (B-spline resampling, process_probability_image,
+    block weight map, label utilities, mean-squares sums of linear_registration)."""
+    from oracle import itk_oracle as orc
+
+    g = np.load(os.path.join(HERE, "demons_small.npz"))
+    spacing, origin = tuple(g["spacing"]), tuple(g["origin"])
+    F, M = Image(g["fixed"], spacing, origin), Image(g["moving"], spacing, origin)
+    tfm = sk.DisplacementFieldTransform(Image(g["dvf"], spacing, origin, is_vector=True))
+    bsp = ref.apply_transform(M, F, tfm, -1000, sk.sitkBSpline)
+    rng = np.random.default_rng(5)
+    import scipy.ndimage as ndi
+
+    v = ndi.gaussian_filter(rng.standard_normal(F.array.shape), 2.0)
+    prob = np.clip((v - v.min()) / (v.max() - v.min()) * 0.9, 0, 1).astype(np.float32)
+    mask = ref.process_probability_image(Image(prob, spacing, origin), 0.45)
+    block = ref.compute_weight_map(F, M, "block", {"factor": 1e12, "gain": 6, "blockSize": (2, 2, 1), "normalise": True})
+    labs = {"A": Image((prob > 0.5).astype(np.uint8), spacing, origin), "B": Image((np.roll(prob, 3, axis=2) > 0.55).astype(np.uint8), spacing, origin)}
+    fixed_overlap = ref.correct_volume_overlap(labs)
+    roi = ref.label_to_roi(labs["A"], [1, 1, 2.5], return_as_list=True)
+    a = np.array([[0.99, -0.04, 0.01], [0.04, 1.01, 0.0], [0.0, 0.02, 0.98]])
+    b = np.array([1.5, -2.0, 0.7]) + np.array(origin) - a @ np.array(origin)
+    acc = ref.linreg_meansq(F, M, a, b, np.eye(3), np.array(origin), stride=3)
+    np.savez_compressed(os.path.join(HERE, "rows_small.npz"), bspline=bsp.array, prob=prob, mask=mask.array, block=block.array,
+                        overlap_a=fixed_overlap["A"].array, overlap_b=fixed_overlap["B"].array, roi=np.array(roi), lin_matrix=a, lin_offset=b,
+                        lin_acc=acc)
+    print("wrote rows_small.npz", int(mask.array.sum()), roi, acc[:2])
+
+
 if __name__ == "__main__":
     main()
+    main_rows()

@@ -35,3 +35,47 @@ def test_gpu_matches_golden(engine):
     assert np.abs(dvf.array - G["dvf"]).max() <= 1e-4  # mm
     assert np.abs(img.array - G["registered"]).max() <= 1e-5 * np.abs(G["registered"]).max()
     assert np.array_equal(reg.apply_transform(L, F, tfm, 0, sk.sitkNearestNeighbor).array, G["warped_label"])
+
+
+# ---- second fixture: the rows around the Demons loop --------------------------------------------------------------
+R = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "rows_small.npz"))
+BLOCK_PARAMS = {"factor": 1e12, "gain": 6, "blockSize": (2, 2, 1), "normalise": True}
+
+
+def _row_inputs():
+    sp, og = tuple(G["spacing"]), tuple(G["origin"])
+    F, M = Image(G["fixed"], sp, og), Image(G["moving"], sp, og)
+    tfm = sk.DisplacementFieldTransform(Image(G["dvf"], sp, og, is_vector=True))
+    prob = Image(R["prob"], sp, og)
+    labs = {"A": Image((R["prob"] > 0.5).astype(np.uint8), sp, og), "B": Image((np.roll(R["prob"], 3, axis=2) > 0.55).astype(np.uint8), sp, og)}
+    return F, M, tfm, prob, labs, og
+
+
+def test_oracle_reproduces_row_golden():
+    from oracle import platipy_ref as ref
+
+    F, M, tfm, prob, labs, og = _row_inputs()
+    assert np.array_equal(ref.apply_transform(M, F, tfm, -1000, sk.sitkBSpline).array, R["bspline"])
+    assert np.array_equal(ref.process_probability_image(prob, 0.45).array, R["mask"])
+    assert np.array_equal(ref.compute_weight_map(F, M, "block", BLOCK_PARAMS).array, R["block"])
+    fx = ref.correct_volume_overlap(labs)
+    assert np.array_equal(fx["A"].array, R["overlap_a"]) and np.array_equal(fx["B"].array, R["overlap_b"])
+    assert ref.label_to_roi(labs["A"], [1, 1, 2.5], return_as_list=True) == [int(v) for v in R["roi"]]
+    acc = ref.linreg_meansq(F, M, R["lin_matrix"], R["lin_offset"], np.eye(3), np.array(og), stride=3)
+    assert np.allclose(acc, R["lin_acc"], rtol=1e-12, atol=0)
+
+
+@pytest.mark.gpu
+def test_gpu_matches_row_golden(engine):
+    from platipy_b200 import fusion, label_utils as lu
+    from platipy_b200 import registration as reg
+
+    F, M, tfm, prob, labs, og = _row_inputs()
+    assert np.array_equal(reg.apply_transform(M, F, tfm, -1000, sk.sitkBSpline).array, R["bspline"])
+    assert np.array_equal(fusion.process_probability_image(prob, 0.45).array, R["mask"])
+    assert np.allclose(fusion.compute_weight_map(F, M, "block", BLOCK_PARAMS).array, R["block"], rtol=1e-5, atol=0)
+    fx = lu.correct_volume_overlap(labs)
+    assert np.array_equal(fx["A"].array, R["overlap_a"]) and np.array_equal(fx["B"].array, R["overlap_b"])
+    assert lu.label_to_roi(labs["A"], [1, 1, 2.5], return_as_list=True) == [int(v) for v in R["roi"]]
+    acc = engine.linreg_meansq(engine.to_device(F), engine.to_device(M), R["lin_matrix"], R["lin_offset"], np.eye(3), np.array(og), None, None, 3)
+    assert acc[1] == R["lin_acc"][1] and np.allclose(acc, R["lin_acc"], rtol=1e-9, atol=1e-9 * np.abs(R["lin_acc"]).max())
