@@ -658,6 +658,7 @@ __global__ void __launch_bounds__(UP_NT, UP_MINB) demons_update_kernel(const flo
     }
 }
 
+#ifdef B200REG_AB_VARIANTS
 // ---- fused warp + force, warp-specialised (producer / consumer) ---------------------------------------------------
 // Same tile, rings and arithmetic as demons_update_kernel, but the two phases run on different warps of one 512-thread
 // CTA: 10 producer warps keep filling the W / F rings (field loads, 8-point gathers, XU conversions) up to three planes
@@ -949,6 +950,8 @@ __global__ void __launch_bounds__(WS_NT, 1) demons_update_ws_kernel(const float*
     }
 }
 
+#endif  // B200REG_AB_VARIANTS
+
 inline bool geom_is_diag(const GeomD& g)
 {
     const double* d = g.direction;
@@ -1048,6 +1051,7 @@ inline int demons_calculate_change(b200reg_ctx* ctx, const float* F, const GeomD
         const dim3 g = update_grid(ctx, gf, &zchunk);
         nblocks = (size_t)g.x * g.y * g.z;
         const bool diag = geom_is_diag(gf) && geom_is_diag(gm);
+#ifdef B200REG_AB_VARIANTS
         if (ctx->update_ws) {
             if (diag) B200_TRY(ensure_dynamic_smem(ctx, demons_update_ws_kernel<true>, WS_SMEM));
             else B200_TRY(ensure_dynamic_smem(ctx, demons_update_ws_kernel<false>, WS_SMEM));
@@ -1058,8 +1062,14 @@ inline int demons_calculate_change(b200reg_ctx* ctx, const float* F, const GeomD
                 demons_update_ws_kernel<false><<<g, WS_NT, WS_SMEM, ctx->stream>>>(F, M, D, ws->U.as<double>(), ws->partials.as<double>(), gf, gm, fp, zchunk,
                                                                                    (int)g.z, ctrl, it);
         } else {
+#else
+        {
+#endif
         // force-phase variant: 0 = per-voxel branches, else the straight-line form specialised on the normalisation
-        const int consume = ctx->update_branchy ? 0 : (fp.normalizer > 0.0 ? (fp.inv_normalizer != 0.0 ? 2 : 3) : 1);
+        int consume = fp.normalizer > 0.0 ? (fp.inv_normalizer != 0.0 ? 2 : 3) : 1;
+#ifdef B200REG_AB_VARIANTS
+        if (ctx->update_branchy) consume = 0;
+#endif
 #define UP_LAUNCH(DG, CS)                                                                                                                     \
     do {                                                                                                                                      \
         B200_TRY(ensure_dynamic_smem(ctx, demons_update_kernel<DG, CS>, UP_SMEM));                                                            \
@@ -1068,14 +1078,18 @@ inline int demons_calculate_change(b200reg_ctx* ctx, const float* F, const GeomD
     } while (0)
         if (diag) {
             switch (consume) {
+#ifdef B200REG_AB_VARIANTS
             case 0: UP_LAUNCH(true, 0); break;
+#endif
             case 1: UP_LAUNCH(true, 1); break;
             case 2: UP_LAUNCH(true, 2); break;
             default: UP_LAUNCH(true, 3); break;
             }
         } else {
             switch (consume) {
+#ifdef B200REG_AB_VARIANTS
             case 0: UP_LAUNCH(false, 0); break;
+#endif
             case 1: UP_LAUNCH(false, 1); break;
             case 2: UP_LAUNCH(false, 2); break;
             default: UP_LAUNCH(false, 3); break;

@@ -694,11 +694,14 @@ inline int launch_zm2_tx(b200reg_ctx* ctx, const double* a, const double* b, dou
     constexpr int NB = (ZM_TY + 2 * R) * TXW;
     constexpr int NT = Zm2Threads<R, TXW>::value;
     g.x = (nx + TXW - 1) / TXW;
+#ifdef B200REG_AB_VARIANTS
     if (b && ctx->zm_regadd) {
         constexpr size_t smem = (size_t)(2 * NA + NB) * sizeof(double);
         B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, 2, TXW>, smem));
         conv3d_zm2_kernel<R, RZ, 2, TXW><<<g, NT, smem, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, 0);
-    } else if (b) {
+    } else
+#endif
+    if (b) {
         constexpr size_t smem = (size_t)(4 * NA + NB) * sizeof(double);
         B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, 1, TXW>, smem));
         conv3d_zm2_kernel<R, RZ, 1, TXW><<<g, NT, smem, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, ctx->zm_tma ? 1 : 0);
@@ -713,6 +716,7 @@ template <int R, int RZ>
 inline int launch_zm2_rz(b200reg_ctx* ctx, const double* a, const double* b, double* out, int nx, int ny, int nz, dim3 g, int zchunk, int nchunks,
                          const SmallCoeffs& sc, const DemonsCtrl* ctrl, int it)
 {
+#ifdef B200REG_AB_VARIANTS  // measured alternatives (profiles/r01_summary.md), compiled with make EXTRA=-DB200REG_AB_VARIANTS
     constexpr int RP = (R + 1) & ~1;
     if (ctx->zm_split_rows) {
         constexpr int NA3 = Zm3Row<ZM_TX + 2 * RP>::STRIDE * (ZM_TY + 2 * R), NB3 = Zm3Row<ZM_TX>::STRIDE * (ZM_TY + 2 * R);
@@ -727,8 +731,9 @@ inline int launch_zm2_rz(b200reg_ctx* ctx, const double* a, const double* b, dou
         }
         return B200REG_OK;
     }
-    if (ctx->zm_tx32) return launch_zm2_tx<R, RZ, 32>(ctx, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it);
-    return launch_zm2_tx<R, RZ, 64>(ctx, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it);
+    if (!ctx->zm_tx32) return launch_zm2_tx<R, RZ, 64>(ctx, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it);
+#endif
+    return launch_zm2_tx<R, RZ, 32>(ctx, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it);
 }
 template <int R>
 inline int launch_zm2_r(b200reg_ctx* ctx, int rz, const double* a, const double* b, double* out, int nx, int ny, int nz, dim3 g, int zchunk,
@@ -756,7 +761,11 @@ inline int launch_conv3d_zmarch(b200reg_ctx* ctx, const double* a, const double*
         sc.r[ax] = kc[ax].r;
         for (int t = 0; t <= 2 * kc[ax].r; ++t) sc.k[ax][t] = kc[ax].k[t];
     }
+#ifdef B200REG_AB_VARIANTS
     const int txw = (ctx->zm_tx32 && !ctx->zm_split_rows) ? 32 : ZM_TX;
+#else
+    const int txw = 32;
+#endif
     const int tiles = ((nx + txw - 1) / txw) * ((ny + ZM_TY - 1) / ZM_TY) * nplanes;
     // enough CTAs for ~4 waves of 2 CTAs/SM, but chunks of at least 16 planes (each chunk re-reads 2*rz planes)
     // (coarse pyramid levels have so few tiles that chunks as short as 4 planes are worth their halo planes: the

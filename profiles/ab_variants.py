@@ -5,7 +5,8 @@ bit-identical to the first configuration.
 
     python profiles/ab_variants.py [name=ENV1=v,ENV2=v[,lib=libb200reg_x.so]] ...
 
-Without arguments: the built-in list below."""
+Without arguments: the built-in list below.  The environment switches that select rejected kernel variants only act on a
+library built with them: `make -C platipy_b200/csrc OUT=../libb200reg_ab.so EXTRA=-DB200REG_AB_VARIANTS` and `lib=libb200reg_ab.so`."""
 import json
 import os
 import subprocess
