@@ -1168,6 +1168,14 @@ inline int demons_enqueue(b200reg_ctx* ctx, const float* F, const b200reg_geom& 
         double* nxt = P[(it + 1) & 1];
         B200_TRY(demons_calculate_change(ctx, F, gf, M, gm, cur, fp, ws, it, n_iters));
         const double* upd = U;
+        if (p.smooth_update_field && p.smooth_displacement_field && !ctx->force_separable && ctx->zm_addout && zmarch2_supported(ctx, ku) &&
+            zmarch2_supported(ctx, kd)) {
+            // T1 = D + G_u * U (the sum is formed when the smoothed update is stored), then D' = G_d * T1: the same IEEE
+            // additions as AddImageFilter, and the displacement smoothing reads one operand instead of two
+            B200_TRY(launch_conv3d_zmarch(ctx, U, cur, T1, nx, ny, nz, 3, ku, ctrl, it, true));
+            B200_TRY(launch_conv3d_zmarch(ctx, T1, nullptr, nxt, nx, ny, nz, 3, kd, ctrl, it));
+            continue;
+        }
         if (p.smooth_update_field) {
             B200_TRY(pde_smooth(ctx, U, nullptr, T1, T2, nxt, nx, ny, nz, ku, ctrl, it));  // nxt is free scratch here
             upd = T1;

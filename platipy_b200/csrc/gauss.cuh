@@ -338,6 +338,9 @@ __device__ __forceinline__ void tma_bulk_g2s(double* smem_dst, const double* gsr
 // MODE 0: out = G(a).  MODE 1: out = G(a + b), both operands staged with cp.async and added in the x pass.
 // MODE 2: out = G(a + b), the next plane's operands are loaded into registers while the current plane is processed and
 // their sum is what gets staged: one shared buffer less, half the staging writes and x-pass reads of MODE 1.
+// MODE 3: out = b + G(a): the second operand is added to the finished value when it is stored (one coalesced load per
+// output, no shared-memory traffic).  The Demons loop uses it to form D + G_u * U at the end of the update smoothing, so
+// that the displacement smoothing that follows is a plain MODE 0 pass instead of a MODE 1 pass.
 template <int R, int RZ, int MODE, int TXW>
 __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, 128 / TXW) conv3d_zm2_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out,
                                                                int nx, int ny, int nz, int zchunk, int nchunks,
@@ -454,6 +457,16 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, 128 / TXW) conv3d_z
             const int q = q0 + s;
             if (q < nsteps) {
                 const int buf = q & 1;
+                // MODE 3: the operand added at the store is fetched now, a whole plane step before it is needed
+                double addv[4] = { 0.0, 0.0, 0.0, 0.0 };
+                if (MODE == 3 && tid < NYZ && q >= 2 * RZ) {
+                    const int zo = zbeg + q - RZ;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int gy = y0 + 4 * yb + j;
+                        if (gx < nx && gy < ny) addv[j] = bp[(size_t)zo * plane + (size_t)gy * nx + gx];
+                    }
+                }
                 if (REGADD) {
                     __syncthreads();  // plane q (summed and stored at the end of step q - 1) is visible; B may be rewritten
                     if (q + 1 < nsteps) load_next(zbeg + q + 1);
@@ -518,7 +531,10 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, 128 / TXW) conv3d_z
 #pragma unroll
                         for (int t = 1; t < NR; ++t) sum += kc.k[2][t] * ring[(s + 1 + t) % NR][j];
                         const int gy = y0 + 4 * yb + j;
-                        if (gx < nx && gy < ny) op[(size_t)zo * plane + (size_t)gy * nx + gx] = sum;
+                        if (gx < nx && gy < ny) {
+                            const size_t oi = (size_t)zo * plane + (size_t)gy * nx + gx;
+                            op[oi] = MODE == 3 ? addv[j] + sum : sum;
+                        }
                     }
                 }
                 // MODE 2: buffer buf ^ 1 was last read by the x pass of step q - 1, two barriers ago
@@ -687,13 +703,19 @@ __global__ void __launch_bounds__(Zm2Threads<R>::value, 2) conv3d_zm3_kernel(con
 
 template <int R, int RZ, int TXW>
 inline int launch_zm2_tx(b200reg_ctx* ctx, const double* a, const double* b, double* out, int nx, int ny, int nz, dim3 g, int zchunk, int nchunks,
-                         const SmallCoeffs& sc, const DemonsCtrl* ctrl, int it)
+                         const SmallCoeffs& sc, const DemonsCtrl* ctrl, int it, bool addout)
 {
     constexpr int RP = (R + 1) & ~1;
     constexpr int NA = (TXW + 2 * RP) * (ZM_TY + 2 * R);
     constexpr int NB = (ZM_TY + 2 * R) * TXW;
     constexpr int NT = Zm2Threads<R, TXW>::value;
     g.x = (nx + TXW - 1) / TXW;
+    if (b && addout) {
+        constexpr size_t smem = (size_t)(2 * NA + NB) * sizeof(double);
+        B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, 3, TXW>, smem));
+        conv3d_zm2_kernel<R, RZ, 3, TXW><<<g, NT, smem, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, 0);
+        return B200REG_OK;
+    }
 #ifdef B200REG_AB_VARIANTS
     if (b && ctx->zm_regadd) {
         constexpr size_t smem = (size_t)(2 * NA + NB) * sizeof(double);
@@ -714,11 +736,11 @@ inline int launch_zm2_tx(b200reg_ctx* ctx, const double* a, const double* b, dou
 }
 template <int R, int RZ>
 inline int launch_zm2_rz(b200reg_ctx* ctx, const double* a, const double* b, double* out, int nx, int ny, int nz, dim3 g, int zchunk, int nchunks,
-                         const SmallCoeffs& sc, const DemonsCtrl* ctrl, int it)
+                         const SmallCoeffs& sc, const DemonsCtrl* ctrl, int it, bool addout)
 {
 #ifdef B200REG_AB_VARIANTS  // measured alternatives (profiles/r01_summary.md), compiled with make EXTRA=-DB200REG_AB_VARIANTS
     constexpr int RP = (R + 1) & ~1;
-    if (ctx->zm_split_rows) {
+    if (ctx->zm_split_rows && !addout) {
         constexpr int NA3 = Zm3Row<ZM_TX + 2 * RP>::STRIDE * (ZM_TY + 2 * R), NB3 = Zm3Row<ZM_TX>::STRIDE * (ZM_TY + 2 * R);
         if (b) {
             constexpr size_t smem = (size_t)(4 * NA3 + NB3) * sizeof(double);
@@ -731,19 +753,19 @@ inline int launch_zm2_rz(b200reg_ctx* ctx, const double* a, const double* b, dou
         }
         return B200REG_OK;
     }
-    if (!ctx->zm_tx32) return launch_zm2_tx<R, RZ, 64>(ctx, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it);
+    if (!ctx->zm_tx32) return launch_zm2_tx<R, RZ, 64>(ctx, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it, addout);
 #endif
-    return launch_zm2_tx<R, RZ, 32>(ctx, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it);
+    return launch_zm2_tx<R, RZ, 32>(ctx, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it, addout);
 }
 template <int R>
 inline int launch_zm2_r(b200reg_ctx* ctx, int rz, const double* a, const double* b, double* out, int nx, int ny, int nz, dim3 g, int zchunk,
-                        int nchunks, const SmallCoeffs& sc, const DemonsCtrl* ctrl, int it)
+                        int nchunks, const SmallCoeffs& sc, const DemonsCtrl* ctrl, int it, bool addout)
 {
     switch (rz) {
-    case 1: return launch_zm2_rz<R, 1>(ctx, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it);
-    case 2: return launch_zm2_rz<R, 2>(ctx, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it);
-    case 3: return launch_zm2_rz<R, 3>(ctx, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it);
-    default: return launch_zm2_rz<R, 4>(ctx, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it);
+    case 1: return launch_zm2_rz<R, 1>(ctx, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it, addout);
+    case 2: return launch_zm2_rz<R, 2>(ctx, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it, addout);
+    case 3: return launch_zm2_rz<R, 3>(ctx, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it, addout);
+    default: return launch_zm2_rz<R, 4>(ctx, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it, addout);
     }
 }
 
@@ -751,10 +773,15 @@ inline bool zmarch_supported(const KernelCoeffs kc[3])
 {
     return kc[0].r <= ZM_RXY && kc[1].r <= ZM_RXY && kc[2].r >= 1 && kc[2].r <= ZM_RMAX;
 }
+// the compile-time-radii kernel (needed for the add-at-output form)
+inline bool zmarch2_supported(b200reg_ctx* ctx, const KernelCoeffs kc[3])
+{
+    return zmarch_supported(kc) && kc[0].r == kc[1].r && kc[0].r >= 1 && !ctx->force_zm1;
+}
 
-// out <- G_z G_y G_x (a [+ b]) for `nplanes` component volumes; a/b/out must not alias.
+// out <- G_z G_y G_x (a [+ b]) for `nplanes` component volumes, or (addout) out <- b + G_z G_y G_x a; a/b/out must not alias.
 inline int launch_conv3d_zmarch(b200reg_ctx* ctx, const double* a, const double* b, double* out, int nx, int ny, int nz, int nplanes,
-                                const KernelCoeffs kc[3], const DemonsCtrl* ctrl, int it)
+                                const KernelCoeffs kc[3], const DemonsCtrl* ctrl, int it, bool addout = false)
 {
     SmallCoeffs sc;
     for (int ax = 0; ax < 3; ++ax) {
@@ -800,10 +827,10 @@ inline int launch_conv3d_zmarch(b200reg_ctx* ctx, const double* a, const double*
     if (kc[0].r == kc[1].r && kc[0].r >= 1 && !ctx->force_zm1) {
         int rc;
         switch (kc[0].r) {
-        case 1: rc = launch_zm2_r<1>(ctx, kc[2].r, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it); break;
-        case 2: rc = launch_zm2_r<2>(ctx, kc[2].r, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it); break;
-        case 3: rc = launch_zm2_r<3>(ctx, kc[2].r, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it); break;
-        default: rc = launch_zm2_r<4>(ctx, kc[2].r, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it); break;
+        case 1: rc = launch_zm2_r<1>(ctx, kc[2].r, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it, addout); break;
+        case 2: rc = launch_zm2_r<2>(ctx, kc[2].r, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it, addout); break;
+        case 3: rc = launch_zm2_r<3>(ctx, kc[2].r, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it, addout); break;
+        default: rc = launch_zm2_r<4>(ctx, kc[2].r, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it, addout); break;
         }
         B200_TRY(rc);
         ctx->launches++;
