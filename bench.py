@@ -163,6 +163,9 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist
 
+        # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION, or unset on some images) off it
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from platipy_b200 import registration as reg
