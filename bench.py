@@ -163,9 +163,10 @@ def run_b200(args):
     if world > 1:
         import torch.distributed as dist
 
-        # rank 0 prints ONE JSON line on stdout: keep NCCL's version banner (NCCL_DEBUG=VERSION, or unset on some images) off it
-        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
-            os.environ["NCCL_DEBUG"] = "WARN"
+        # rank 0 prints ONE JSON line on stdout: the image exports NCCL_DEBUG=VERSION, which makes NCCL print its version banner
+        # there (NCCL_DEBUG_FILE does not move it).  An explicit WARN / INFO / TRACE choice of the caller is left alone.
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "NONE"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from platipy_b200 import registration as reg
