@@ -113,8 +113,32 @@ def register_atlas(target, atlas_ct, atlas_labels, settings):
     return out
 
 
-def run_segmentation(img, atlas_set, settings=MULTIATLAS_SETTINGS_DEFAULTS, group=None):
-    """In-memory form of ``run_segmentation`` (run.py:106) from the deformable stage on.
+def load_atlas_set(settings):
+    """Initialisation step of the reference (run.py:147-190): read every atlas image and structure named by
+    ``settings["atlas_settings"]`` (``atlas_path``, ``atlas_id_list``, ``atlas_structure_list``, ``atlas_image_format``,
+    ``atlas_label_format``) and, with ``crop_atlas_to_structures``, crop each atlas to the bounding box of its structures
+    expanded by ``crop_atlas_expansion_mm``.  Returns ``{atlas_id: {"CT Image": image, structure: label, ...}}``."""
+    from . import label_utils as lu
+
+    a = settings["atlas_settings"]
+    atlas_set = {}
+    for atlas_id in a["atlas_id_list"]:
+        image = sk.ReadImage(f"{a['atlas_path']}/{a['atlas_image_format'].format(atlas_id)}")
+        structures = {s: sk.ReadImage(f"{a['atlas_path']}/{a['atlas_label_format'].format(atlas_id, s)}") for s in a["atlas_structure_list"]}
+        if a.get("crop_atlas_to_structures", False):
+            size, index = lu.label_to_roi(list(structures.values()), expansion_mm=a["crop_atlas_expansion_mm"])
+            image = lu.crop_to_roi(image, size=size, index=index)
+            structures = {s: lu.crop_to_roi(v, size=size, index=index) for s, v in structures.items()}
+        entry = {"CT Image": image}
+        entry.update(structures)
+        atlas_set[atlas_id] = entry
+    return atlas_set
+
+
+def run_segmentation(img, atlas_set=None, settings=MULTIATLAS_SETTINGS_DEFAULTS, group=None):
+    """``run_segmentation`` (run.py:106-441).  Called like the reference -- ``run_segmentation(img, settings)`` with an
+    ``atlas_settings`` block -- the atlases are read from disk (``load_atlas_set``); an in-memory ``atlas_set`` may be
+    passed instead.
 
     img        target image (host ``Image`` or ``DeviceImage``)
     atlas_set  ``{atlas_id: {"CT Image": image, "<structure>": label image, ...}}`` on the target grid; every rank
@@ -129,6 +153,10 @@ def run_segmentation(img, atlas_set, settings=MULTIATLAS_SETTINGS_DEFAULTS, grou
 
     from . import label_utils as lu
 
+    if isinstance(atlas_set, dict) and "atlas_settings" in atlas_set:  # the reference's positional form: (img, settings)
+        atlas_set, settings = None, atlas_set
+    if atlas_set is None:
+        atlas_set = load_atlas_set(settings)
     eng = Engine.get()
     rank, world = _dist_info(group)
     all_ids = sorted(atlas_set)

@@ -187,6 +187,25 @@ def Cast(image, pixel_id):
     return Image(out, image.GetSpacing(), image.GetOrigin(), image.GetDirection(), image.is_vector)
 
 
+def ReadImage(path, outputPixelType=sitkUnknown):
+    """``sitk.ReadImage``: real SimpleITK when it is importable, otherwise the NIfTI-1 reader of ``nifti_io``."""
+    if HAVE_SITK:  # pragma: no cover
+        return _sitk.ReadImage(str(path)) if outputPixelType == sitkUnknown else _sitk.ReadImage(str(path), outputPixelType)
+    from . import nifti_io
+
+    img = nifti_io.read_image(path)
+    return img if outputPixelType == sitkUnknown else Cast(img, outputPixelType)
+
+
+def WriteImage(image, path):
+    """``sitk.WriteImage`` (NIfTI-1 without SimpleITK)."""
+    if HAVE_SITK and isinstance(image, _sitk.Image):  # pragma: no cover
+        return _sitk.WriteImage(image, str(path))
+    from . import nifti_io
+
+    nifti_io.write_image(image, path)
+
+
 # -- transforms -----------------------------------------------------------------------------------
 class Transform:
     """``sitk.Transform()``: identity."""

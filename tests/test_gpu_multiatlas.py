@@ -116,3 +116,35 @@ def test_run_segmentation_with_linear_prealignment(engine):
         print(f"S{k} (auto-crop + post-processing): Dice {dice:.3f}")
         assert dice > 0.88, (k, dice)
     assert not np.any((results2["S0"].array > 0) & (results2["S1"].array > 0))
+
+
+def test_run_segmentation_from_disk_like_the_reference(engine, tmp_path):
+    """``run_segmentation(img, settings)`` with an ``atlas_settings`` block (run.py:106-190): atlases are NIfTI files named by
+    the format strings, optionally cropped to their structures; the result equals the in-memory call on the same data."""
+    target, atlas_set = make_case(n_atlas=2)
+    names = sorted(k for k in atlas_set["000"] if k != "CT Image")
+    for a, entry in atlas_set.items():
+        (tmp_path / f"Case_{a}" / "Images").mkdir(parents=True)
+        (tmp_path / f"Case_{a}" / "Structures").mkdir(parents=True)
+        sk.WriteImage(entry["CT Image"], str(tmp_path / f"Case_{a}" / "Images" / f"Case_{a}_CROP.nii.gz"))
+        for n in names:
+            sk.WriteImage(entry[n], str(tmp_path / f"Case_{a}" / "Structures" / f"Case_{a}_{n}_CROP.nii.gz"))
+    settings = {
+        "atlas_settings": {"atlas_id_list": sorted(atlas_set), "atlas_structure_list": names, "atlas_path": str(tmp_path),
+                           "atlas_image_format": "Case_{0}/Images/Case_{0}_CROP.nii.gz",
+                           "atlas_label_format": "Case_{0}/Structures/Case_{0}_{1}_CROP.nii.gz",
+                           "crop_atlas_to_structures": False, "crop_atlas_expansion_mm": (20, 20, 40)},
+        "deformable_registration_settings": {"isotropic_resample": False, "resolution_staging": [2, 1], "iteration_staging": [8, 4], "ncores": 8,
+                                             "default_value": -1000, "verbose": False},
+        "label_fusion_settings": {"vote_type": "unweighted", "vote_params": None, "optimal_threshold": {}},
+    }
+    res_disk, prob_disk = multiatlas.run_segmentation(target, settings)            # the reference's call form
+    res_mem, prob_mem = multiatlas.run_segmentation(target, atlas_set, settings)
+    for n in names:
+        assert np.array_equal(res_disk[n].array, res_mem[n].array) and np.array_equal(prob_disk[n].array, prob_mem[n].array)
+    # crop_atlas_to_structures: the loader crops image and structures to the structures' bounding box + expansion
+    settings["atlas_settings"].update(crop_atlas_to_structures=True, crop_atlas_expansion_mm=(6, 6, 6))
+    loaded = multiatlas.load_atlas_set(settings)
+    exp_size, exp_index = ref.label_to_roi([atlas_set["000"][n] for n in names], [6, 6, 6])
+    assert loaded["000"]["CT Image"].GetSize() == tuple(exp_size)
+    assert np.array_equal(loaded["000"][names[0]].array, ref.crop_to_roi(atlas_set["000"][names[0]], exp_size, exp_index).array)
