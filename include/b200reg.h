@@ -268,6 +268,42 @@ int b200reg_resolve_overlap(b200reg_ctx* ctx, const uint8_t* const* d_labels_ran
 int b200reg_binary_closing(b200reg_ctx* ctx, const uint8_t* d_in, const int32_t size[3], const int32_t radius[3],
                            const int32_t* h_offsets, int n_offsets, uint8_t* d_out);
 
+/* ---- distance maps, contours, binary morphology, masking (registration/utils.py:270-344, label/projection.py:9-92) ------- */
+/* sitk.SignedMaurerDistanceMap(mask, insideIsPositive, squaredDistance, useImageSpacing) -> Float32 (utils.py:289-294,
+ * projection.py:22-31,80-82; background value 0).  Distance to the nearest object voxel that has a background voxel among its
+ * 26 neighbours (0 on those voxels), computed in single precision like ITK's filter does in its output pixel type. */
+int b200reg_signed_maurer_distance_map(b200reg_ctx* ctx, const uint8_t* d_mask, const b200reg_geom* geom, int inside_is_positive,
+                                       int squared_distance, int use_image_spacing, float* d_out);
+/* sitk.LabelContour(image, fullyConnected) (projection.py:33,85; background 0): labelled voxels with a differently labelled
+ * neighbour keep their value, everything else becomes 0.  Not in place. */
+int b200reg_label_contour(b200reg_ctx* ctx, const uint8_t* d_in, const int32_t size[3], int fully_connected, uint8_t* d_out);
+/* sitk.BinaryDilate / sitk.BinaryErode (utils.py:331, generation/dvf.py:269-287): foreground 1, background 0, structuring
+ * element as n_offsets (dx, dy, dz) triples in host memory; boundary_to_foreground as in SimpleITK (default false for the
+ * dilation, true for the erosion).  Not in place.  Synchronises. */
+int b200reg_binary_dilate(b200reg_ctx* ctx, const uint8_t* d_in, const int32_t size[3], const int32_t* h_offsets, int n_offsets,
+                          int boundary_to_foreground, uint8_t* d_out);
+int b200reg_binary_erode(b200reg_ctx* ctx, const uint8_t* d_in, const int32_t size[3], const int32_t* h_offsets, int n_offsets,
+                         int boundary_to_foreground, uint8_t* d_out);
+/* mask_a | mask_b, &, + (modulo 256), ^ on UInt8 volumes (generation/dvf.py:66,249,290) */
+typedef enum { B200REG_OP_OR = 0, B200REG_OP_AND = 1, B200REG_OP_ADD = 2, B200REG_OP_XOR = 3 } b200reg_u8_op;
+int b200reg_u8_binary_op(b200reg_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, int op, uint8_t* d_out, size_t n);
+/* sitk.Mask(image, mask, outsideValue) (utils.py:337-340; generation/dvf.py:66,121,200): `planes` planes of n voxels (3 for a
+ * SoA displacement field); d_out may alias d_in. */
+int b200reg_mask_image(b200reg_ctx* ctx, const void* d_in, int dtype, const uint8_t* d_mask, size_t n, int planes, double outside_value,
+                       void* d_out);
+/* image / constant on a Float32 or Float64 image (utils.py:297,342); d_out may alias d_in. */
+int b200reg_divide_scalar(b200reg_ctx* ctx, const void* d_in, int dtype, size_t n, double divisor, void* d_out);
+
+/* ---- field templates of the synthetic-deformation generators (generation/dvf.py:29-415) --------------------------------- */
+/* The constant displacement `vector` (dx, dy, dz) inside d_mask (everywhere when d_mask is NULL), 0 outside
+ * (dvf.py:54-66,114-121,187-200: np.zeros + vector, CopyInformation, sitk.Mask). */
+int b200reg_constant_field(b200reg_ctx* ctx, const uint8_t* d_mask, size_t n, const double vector[3], double* d_out_soa);
+/* generate_field_radial_bend (dvf.py:362-394): scale * cross(voxel index - reference_index, axis), all in (x, y, z) order,
+ * inside the body mask cut by a half space through the reference voxel: clip_axis -1 none, 0 x, 1 y, 2 z; voxels with
+ * index >= reference are kept when clip_keep_upper, else those with index < reference. */
+int b200reg_radial_bend_field(b200reg_ctx* ctx, const uint8_t* d_mask, const int32_t size[3], const int32_t reference_index[3],
+                              const double axis[3], double scale, int clip_axis, int clip_keep_upper, double* d_out_soa);
+
 #ifdef __cplusplus
 }
 #endif

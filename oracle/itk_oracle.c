@@ -1224,3 +1224,167 @@ ORC_API void orc_set_num_threads(int n)
     (void)n;
 #endif
 }
+
+/* ------------------------------------------------------------------------------------------------ */
+/* Distance maps, contours, binary morphology (rows after the hot path: SURVEY 8f-3 / 8f-4)             */
+/* ------------------------------------------------------------------------------------------------ */
+/* itk::SignedMaurerDistanceMapImageFilter as SimpleITK instantiates it (output Float32, background value 0):
+ * sitk.SignedMaurerDistanceMap(mask, insideIsPositive, squaredDistance, useImageSpacing)
+ * (registration/utils.py:289-294; label/projection.py:22-31,80-82).  [ITK-recall]
+ *  GenerateData: BinaryThreshold (background -> max, object -> 0), BinaryContour with FullyConnected = true (object voxels
+ *  with a background voxel among their 26 neighbours stay 0, every other voxel becomes max), then one Voronoi pass per
+ *  dimension (x, y, z); all of Voronoi()'s arithmetic -- line coordinate i * spacing, squared distances, Remove() -- is in the
+ *  output pixel type, i.e. single precision.  Each pass stores +-d with the sign of the final result and reads |d| back.
+ *  The last pass is followed by sqrt(|d|) unless squared distances were asked for. */
+static int maurer_remove_f(float d1, float d2, float df, float x1, float x2, float xf)
+{
+    const float a = x2 - x1, b = xf - x2, c = xf - x1;
+    const float value = c * fabsf(d2) - b * fabsf(d1) - a * fabsf(df) - a * b * c;
+    return value > 0.0f;
+}
+static void maurer_line(float* out, const uint8_t* mask, size_t base, size_t stride, int nd, float sp, int inside_pos, float* g, float* h)
+{
+    int l = -1;
+    for (int i = 0; i < nd; ++i) {
+        const float di = out[base + (size_t)i * stride];
+        const float iw = (float)i * sp;
+        if (di != FLT_MAX) {
+            if (l < 1) {
+                ++l; g[l] = di; h[l] = iw;
+            } else {
+                while (l >= 1 && maurer_remove_f(g[l - 1], g[l], di, h[l - 1], h[l], iw)) --l;
+                ++l; g[l] = di; h[l] = iw;
+            }
+        }
+    }
+    if (l == -1) return;
+    const int ns = l;
+    l = 0;
+    for (int i = 0; i < nd; ++i) {
+        const float iw = (float)i * sp;
+        float d1 = fabsf(g[l]) + (h[l] - iw) * (h[l] - iw);
+        while (l < ns) {
+            const float d2 = fabsf(g[l + 1]) + (h[l + 1] - iw) * (h[l + 1] - iw);
+            if (d1 <= d2) break;
+            ++l;
+            d1 = d2;
+        }
+        const size_t q = base + (size_t)i * stride;
+        if (mask[q] != 0) out[q] = inside_pos ? d1 : -d1;
+        else out[q] = inside_pos ? -d1 : d1;
+    }
+}
+ORC_API int orc_signed_maurer(const uint8_t* mask, int nx, int ny, int nz, const double* spacing, int inside_pos, int squared, int use_spacing,
+                              float* out)
+{
+    const size_t n = (size_t)nx * ny * nz, pz = (size_t)nx * ny;
+    int nmax = nx > ny ? nx : ny;
+    if (nz > nmax) nmax = nz;
+    /* threshold + contour */
+    for (size_t q = 0; q < n; ++q) {
+        float v = FLT_MAX;
+        if (mask[q]) {
+            const int x = (int)(q % nx), y = (int)((q / nx) % ny), z = (int)(q / pz);
+            int border = 0;
+            for (int dz = -1; dz <= 1 && !border; ++dz)
+                for (int dy = -1; dy <= 1 && !border; ++dy)
+                    for (int dx = -1; dx <= 1 && !border; ++dx) {
+                        const int xx = x + dx, yy = y + dy, zz = z + dz;
+                        if (xx < 0 || yy < 0 || zz < 0 || xx >= nx || yy >= ny || zz >= nz) continue;
+                        if (!mask[(size_t)zz * pz + (size_t)yy * nx + xx]) border = 1;
+                    }
+            if (border) v = 0.0f;
+        }
+        out[q] = v;
+    }
+    float* g = (float*)malloc(sizeof(float) * (size_t)nmax);
+    float* h = (float*)malloc(sizeof(float) * (size_t)nmax);
+    if (!g || !h) { free(g); free(h); return -1; }
+    const float sx = use_spacing ? (float)spacing[0] : 1.0f, sy = use_spacing ? (float)spacing[1] : 1.0f, sz = use_spacing ? (float)spacing[2] : 1.0f;
+    for (int z = 0; z < nz; ++z)
+        for (int y = 0; y < ny; ++y) maurer_line(out, mask, (size_t)z * pz + (size_t)y * nx, 1, nx, sx, inside_pos, g, h);
+    for (int z = 0; z < nz; ++z)
+        for (int x = 0; x < nx; ++x) maurer_line(out, mask, (size_t)z * pz + x, (size_t)nx, ny, sy, inside_pos, g, h);
+    for (int y = 0; y < ny; ++y)
+        for (int x = 0; x < nx; ++x) maurer_line(out, mask, (size_t)y * nx + x, pz, nz, sz, inside_pos, g, h);
+    if (!squared) {
+        for (size_t q = 0; q < n; ++q) {
+            const float r = sqrtf(fabsf(out[q]));
+            if (mask[q] != 0) out[q] = inside_pos ? r : -r;
+            else out[q] = inside_pos ? -r : r;
+        }
+    }
+    free(g);
+    free(h);
+    return 0;
+}
+
+/* itk::LabelContourImageFilter (sitk.LabelContour, label/projection.py:33,85): background 0; a labelled voxel is kept when a
+ * neighbour inside the image -- face neighbours, or all 26 when fully connected -- has another value.  [ITK-recall] */
+ORC_API void orc_label_contour(const uint8_t* in, int nx, int ny, int nz, int fully, uint8_t* out)
+{
+    const size_t pz = (size_t)nx * ny;
+    for (int z = 0; z < nz; ++z)
+        for (int y = 0; y < ny; ++y)
+            for (int x = 0; x < nx; ++x) {
+                const size_t q = (size_t)z * pz + (size_t)y * nx + x;
+                const uint8_t v = in[q];
+                int edge = 0;
+                if (v) {
+                    for (int dz = -1; dz <= 1; ++dz)
+                        for (int dy = -1; dy <= 1; ++dy)
+                            for (int dx = -1; dx <= 1; ++dx) {
+                                const int manhattan = abs(dx) + abs(dy) + abs(dz);
+                                if (manhattan == 0 || (!fully && manhattan != 1)) continue;
+                                const int xx = x + dx, yy = y + dy, zz = z + dz;
+                                if (xx < 0 || yy < 0 || zz < 0 || xx >= nx || yy >= ny || zz >= nz) continue;
+                                if (in[(size_t)zz * pz + (size_t)yy * nx + xx] != v) edge = 1;
+                            }
+                }
+                out[q] = edge ? v : 0;
+            }
+}
+
+/* itk::BinaryDilateImageFilter / itk::BinaryErodeImageFilter (sitk.BinaryDilate / BinaryErode: registration/utils.py:331,
+ * generation/dvf.py:269-287), foreground 1, background 0, flat structuring element given as offsets.  Dilation: the element is
+ * painted around every foreground voxel; erosion: a foreground voxel survives when the element around it holds only
+ * foreground (outside the image counts as foreground with boundaryToForeground, SimpleITK's default for the erosion). */
+ORC_API void orc_binary_morph(const uint8_t* in, int nx, int ny, int nz, const int32_t* offs, int noffs, int dilate, int boundary_fg, uint8_t* out)
+{
+    const size_t pz = (size_t)nx * ny, n = pz * nz;
+    memcpy(out, in, n);
+    for (int z = 0; z < nz; ++z)
+        for (int y = 0; y < ny; ++y)
+            for (int x = 0; x < nx; ++x) {
+                const size_t q = (size_t)z * pz + (size_t)y * nx + x;
+                if (dilate) {
+                    if (in[q] != 1) continue;
+                    for (int t = 0; t < noffs; ++t) {
+                        const int xx = x + offs[3 * t], yy = y + offs[3 * t + 1], zz = z + offs[3 * t + 2];
+                        if (xx < 0 || yy < 0 || zz < 0 || xx >= nx || yy >= ny || zz >= nz) continue;
+                        out[(size_t)zz * pz + (size_t)yy * nx + xx] = 1;
+                    }
+                } else if (in[q] == 1) {
+                    int keep = 1;
+                    for (int t = 0; t < noffs && keep; ++t) {
+                        const int xx = x + offs[3 * t], yy = y + offs[3 * t + 1], zz = z + offs[3 * t + 2];
+                        if (xx < 0 || yy < 0 || zz < 0 || xx >= nx || yy >= ny || zz >= nz) keep = boundary_fg != 0;
+                        else keep = in[(size_t)zz * pz + (size_t)yy * nx + xx] == 1;
+                    }
+                    if (!keep) out[q] = 0;
+                }
+            }
+    if (dilate && boundary_fg) {
+        /* foreground outside the image: a voxel within the element's reach of the outside is painted too */
+        for (int z = 0; z < nz; ++z)
+            for (int y = 0; y < ny; ++y)
+                for (int x = 0; x < nx; ++x) {
+                    const size_t q = (size_t)z * pz + (size_t)y * nx + x;
+                    if (out[q] == 1) continue;
+                    for (int t = 0; t < noffs; ++t) {
+                        const int xx = x - offs[3 * t], yy = y - offs[3 * t + 1], zz = z - offs[3 * t + 2];
+                        if (xx < 0 || yy < 0 || zz < 0 || xx >= nx || yy >= ny || zz >= nz) { out[q] = 1; break; }
+                    }
+                }
+    }
+}

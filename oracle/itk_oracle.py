@@ -71,6 +71,11 @@ def lib():
         _lib.orc_bspline3_coefficients.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _lib.orc_binary_fillhole.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _lib.orc_largest_component.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        _lib.orc_signed_maurer.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        _lib.orc_label_contour.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        _lib.orc_label_contour.restype = None
+        _lib.orc_binary_morph.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
+        _lib.orc_binary_morph.restype = None
     return _lib
 
 
@@ -303,4 +308,37 @@ def bspline3_coefficients(arr, geom):
     out = np.empty(a.shape, dtype=np.float64)
     if lib().orc_bspline3_coefficients(_ptr(a), _NP_TO_ORC[a.dtype], C.byref(geom), _ptr(out)) != 0:
         raise MemoryError
+    return out
+
+
+def signed_maurer_distance_map(mask, spacing=(1.0, 1.0, 1.0), inside_is_positive=False, squared_distance=False, use_image_spacing=True):
+    """sitk.SignedMaurerDistanceMap on a [z, y, x] mask (background 0) -> float32; ``spacing`` is (x, y, z)."""
+    m = np.ascontiguousarray(mask != 0, dtype=np.uint8)
+    out = np.empty(m.shape, dtype=np.float32)
+    nz, ny, nx = m.shape
+    sp = np.ascontiguousarray(spacing, dtype=np.float64)
+    if lib().orc_signed_maurer(_ptr(m), nx, ny, nz, _ptr(sp), int(bool(inside_is_positive)), int(bool(squared_distance)),
+                               int(bool(use_image_spacing)), _ptr(out)) != 0:
+        raise MemoryError
+    return out
+
+
+def label_contour(mask, fully_connected=False):
+    """sitk.LabelContour on a [z, y, x] uint8 label array (background 0)."""
+    m = np.ascontiguousarray(mask, dtype=np.uint8)
+    out = np.empty_like(m)
+    nz, ny, nx = m.shape
+    lib().orc_label_contour(_ptr(m), nx, ny, nz, int(bool(fully_connected)), _ptr(out))
+    return out
+
+
+def binary_morph(mask, offsets, dilate, boundary_to_foreground=None):
+    """sitk.BinaryDilate / sitk.BinaryErode (foreground 1) with the structuring element given as (dx, dy, dz) offsets."""
+    m = np.ascontiguousarray(mask, dtype=np.uint8)
+    out = np.empty_like(m)
+    nz, ny, nx = m.shape
+    offs = np.ascontiguousarray(offsets, dtype=np.int32).reshape(-1, 3)
+    if boundary_to_foreground is None:
+        boundary_to_foreground = not dilate  # SimpleITK defaults
+    lib().orc_binary_morph(_ptr(m), nx, ny, nz, _ptr(offs), int(offs.shape[0]), int(bool(dilate)), int(bool(boundary_to_foreground)), _ptr(out))
     return out

@@ -20,6 +20,7 @@ MAX_BATCH = 64
 
 OK, ERR_CUDA, ERR_ARG, ERR_UNSUPPORTED, ERR_RUNTIME = 0, 1, 2, 3, 4
 TFM_AFFINE, TFM_DVF = 0, 1
+OP_OR, OP_AND, OP_ADD, OP_XOR = 0, 1, 2, 3
 
 
 class Geom(C.Structure):
@@ -107,6 +108,16 @@ SIGNATURES = {
     "b200reg_binary_closing": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, _P]),
     "b200reg_staple": (C.c_int, [_P, C.POINTER(_P), C.c_int, C.c_size_t, C.c_double, C.c_uint32, C.c_double, C.c_int, _P,
                                  C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
+    "b200reg_signed_maurer_distance_map": (C.c_int, [_P, _P, C.POINTER(Geom), C.c_int, C.c_int, C.c_int, _P]),
+    "b200reg_label_contour": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.c_int, _P]),
+    "b200reg_binary_dilate": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, C.c_int, _P]),
+    "b200reg_binary_erode": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, C.c_int, _P]),
+    "b200reg_u8_binary_op": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_size_t]),
+    "b200reg_mask_image": (C.c_int, [_P, _P, C.c_int, _P, C.c_size_t, C.c_int, C.c_double, _P]),
+    "b200reg_divide_scalar": (C.c_int, [_P, _P, C.c_int, C.c_size_t, C.c_double, _P]),
+    "b200reg_constant_field": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_double), _P]),
+    "b200reg_radial_bend_field": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_double, C.c_int,
+                                            C.c_int, _P]),
 }
 
 _lib = None

@@ -8,6 +8,7 @@
 #include "morph.cuh"
 #include "linreg.cuh"
 #include "postproc.cuh"
+#include "distmap.cuh"
 #include "gauss.cuh"
 #include "resample.cuh"
 
@@ -852,4 +853,96 @@ API int b200reg_binary_closing(b200reg_ctx* ctx, const uint8_t* d_in, const int3
     REQUIRE(d_in != d_out, "in-place closing is not supported");
     for (int d = 0; d < 3; ++d) REQUIRE(size[d] > 0 && radius[d] >= 0, "invalid size / radius");
     return binary_closing(ctx, d_in, size, radius, h_offsets, n_offsets, d_out);
+}
+
+// ---- distance maps, contours, binary morphology, masking (registration/utils.py:270-344, label/projection.py:9-92) ----------
+API int b200reg_signed_maurer_distance_map(b200reg_ctx* ctx, const uint8_t* d_mask, const b200reg_geom* geom, int inside_is_positive,
+                                           int squared_distance, int use_image_spacing, float* d_out)
+{
+    ENTER(ctx);
+    REQUIRE(d_mask && d_out && valid_geom(geom), "invalid argument");
+    return signed_maurer(ctx, d_mask, *geom, inside_is_positive, squared_distance, use_image_spacing, d_out);
+}
+API int b200reg_label_contour(b200reg_ctx* ctx, const uint8_t* d_in, const int32_t size[3], int fully_connected, uint8_t* d_out)
+{
+    ENTER(ctx);
+    REQUIRE(d_in && d_out && size && size[0] > 0 && size[1] > 0 && size[2] > 0, "invalid argument");
+    REQUIRE(d_in != d_out, "in-place LabelContour is not supported");
+    return label_contour(ctx, d_in, size, fully_connected, d_out);
+}
+API int b200reg_binary_dilate(b200reg_ctx* ctx, const uint8_t* d_in, const int32_t size[3], const int32_t* h_offsets, int n_offsets,
+                              int boundary_to_foreground, uint8_t* d_out)
+{
+    ENTER(ctx);
+    REQUIRE(d_in && d_out && size && h_offsets && n_offsets >= 1 && size[0] > 0 && size[1] > 0 && size[2] > 0, "invalid argument");
+    REQUIRE(d_in != d_out, "in-place dilation is not supported");
+    return binary_morph(ctx, true, d_in, size, h_offsets, n_offsets, boundary_to_foreground, d_out);
+}
+API int b200reg_binary_erode(b200reg_ctx* ctx, const uint8_t* d_in, const int32_t size[3], const int32_t* h_offsets, int n_offsets,
+                             int boundary_to_foreground, uint8_t* d_out)
+{
+    ENTER(ctx);
+    REQUIRE(d_in && d_out && size && h_offsets && n_offsets >= 1 && size[0] > 0 && size[1] > 0 && size[2] > 0, "invalid argument");
+    REQUIRE(d_in != d_out, "in-place erosion is not supported");
+    return binary_morph(ctx, false, d_in, size, h_offsets, n_offsets, boundary_to_foreground, d_out);
+}
+API int b200reg_u8_binary_op(b200reg_ctx* ctx, const uint8_t* d_a, const uint8_t* d_b, int op, uint8_t* d_out, size_t n)
+{
+    ENTER(ctx);
+    REQUIRE(d_a && d_b && d_out && n > 0, "invalid argument");
+    REQUIRE(op >= B200REG_OP_OR && op <= B200REG_OP_XOR, "unknown operation %d", op);
+    u8_binary_op_kernel<<<elementwise_blocks(ctx, n, 256), 256, 0, ctx->stream>>>(d_a, d_b, op, d_out, n);
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+API int b200reg_mask_image(b200reg_ctx* ctx, const void* d_in, int dtype, const uint8_t* d_mask, size_t n, int planes, double outside_value,
+                           void* d_out)
+{
+    ENTER(ctx);
+    REQUIRE(d_in && d_mask && d_out && n > 0 && planes >= 1, "invalid argument");
+    const int nb = elementwise_blocks(ctx, n, 256);
+    B200_DISPATCH_DTYPE(dtype, T, mask_image_kernel<T><<<nb, 256, 0, ctx->stream>>>((const T*)d_in, d_mask, n, planes, (T)Px<T>::cast_host(outside_value), (T*)d_out));
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+API int b200reg_divide_scalar(b200reg_ctx* ctx, const void* d_in, int dtype, size_t n, double divisor, void* d_out)
+{
+    ENTER(ctx);
+    REQUIRE(d_in && d_out && n > 0, "invalid argument");
+    REQUIRE(dtype == B200REG_F32 || dtype == B200REG_F64, "divide_scalar: Float32 or Float64 image expected");
+    const int nb = elementwise_blocks(ctx, n, 256);
+    if (dtype == B200REG_F32)
+        divide_scalar_kernel<float><<<nb, 256, 0, ctx->stream>>>((const float*)d_in, (float)divisor, (float*)d_out, n);
+    else
+        divide_scalar_kernel<double><<<nb, 256, 0, ctx->stream>>>((const double*)d_in, divisor, (double*)d_out, n);
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+
+// ---- field templates of the synthetic-deformation generators (generation/dvf.py:29-415) ---------------------------------------
+API int b200reg_constant_field(b200reg_ctx* ctx, const uint8_t* d_mask, size_t n, const double vector[3], double* d_out_soa)
+{
+    ENTER(ctx);
+    REQUIRE(d_out_soa && vector && n > 0, "invalid argument");
+    constant_field_kernel<<<elementwise_blocks(ctx, n, 256), 256, 0, ctx->stream>>>(d_mask, n, vector[0], vector[1], vector[2], d_out_soa);
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+API int b200reg_radial_bend_field(b200reg_ctx* ctx, const uint8_t* d_mask, const int32_t size[3], const int32_t reference_index[3],
+                                  const double axis[3], double scale, int clip_axis, int clip_keep_upper, double* d_out_soa)
+{
+    ENTER(ctx);
+    REQUIRE(d_mask && d_out_soa && size && reference_index && axis && size[0] > 0 && size[1] > 0 && size[2] > 0, "invalid argument");
+    REQUIRE(clip_axis >= -1 && clip_axis <= 2, "clip_axis must be -1 (none), 0 (x), 1 (y) or 2 (z)");
+    const size_t n = (size_t)size[0] * size[1] * size[2];
+    radial_bend_kernel<<<elementwise_blocks(ctx, n, 256), 256, 0, ctx->stream>>>(d_mask, size[0], size[1], size[2], reference_index[0], reference_index[1],
+                                                                                reference_index[2], axis[0], axis[1], axis[2], scale, clip_axis,
+                                                                                clip_keep_upper, d_out_soa);
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
 }

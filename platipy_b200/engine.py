@@ -456,6 +456,69 @@ class Engine:
                                                    offs.ctypes.data_as(C.POINTER(C.c_int32)), int(offs.shape[0]), C.c_void_p(out.data_ptr())))
         return mask.like(out, np.uint8, False)
 
+    # -- distance maps, contours, binary morphology, masking (registration/utils.py:270-344, label/projection.py) ------
+    def signed_maurer_distance_map(self, mask, inside_is_positive=False, squared_distance=False, use_image_spacing=True):
+        """sitk.SignedMaurerDistanceMap of a UInt8 mask (background 0) -> Float32."""
+        out = self.empty(mask.tensor.shape, np.float32)
+        g = mask.geom
+        _abi.check(self.lib.b200reg_signed_maurer_distance_map(self.ctx, mask.ptr, C.byref(g), int(bool(inside_is_positive)),
+                                                               int(bool(squared_distance)), int(bool(use_image_spacing)), C.c_void_p(out.data_ptr())))
+        return mask.like(out, np.float32, False)
+
+    def label_contour(self, mask, fully_connected=False):
+        out = self.empty(mask.tensor.shape, np.uint8)
+        _abi.check(self.lib.b200reg_label_contour(self.ctx, mask.ptr, self._size3(mask), int(bool(fully_connected)), C.c_void_p(out.data_ptr())))
+        return mask.like(out, np.uint8, False)
+
+    def _binary_morph(self, fn, mask, offsets, boundary_to_foreground):
+        out = self.empty(mask.tensor.shape, np.uint8)
+        offs = np.ascontiguousarray(offsets, dtype=np.int32).reshape(-1, 3)
+        _abi.check(fn(self.ctx, mask.ptr, self._size3(mask), offs.ctypes.data_as(C.POINTER(C.c_int32)), int(offs.shape[0]),
+                      int(bool(boundary_to_foreground)), C.c_void_p(out.data_ptr())))
+        return mask.like(out, np.uint8, False)
+
+    def binary_dilate(self, mask, offsets, boundary_to_foreground=False):
+        return self._binary_morph(self.lib.b200reg_binary_dilate, mask, offsets, boundary_to_foreground)
+
+    def binary_erode(self, mask, offsets, boundary_to_foreground=True):
+        return self._binary_morph(self.lib.b200reg_binary_erode, mask, offsets, boundary_to_foreground)
+
+    def u8_binary_op(self, a, b, op):
+        if a.tensor.shape != b.tensor.shape:
+            raise RuntimeError("both images must have the same size")  # ITK: "Inputs do not occupy the same physical space!"
+        out = self.empty(a.tensor.shape, np.uint8)
+        _abi.check(self.lib.b200reg_u8_binary_op(self.ctx, a.ptr, b.ptr, int(op), C.c_void_p(out.data_ptr()), a.tensor.numel()))
+        return a.like(out, np.uint8, False)
+
+    def mask_image(self, dimg, mask, outside_value=0.0):
+        """sitk.Mask(image, mask): scalar images of any pixel type and SoA displacement fields."""
+        out = self.empty(dimg.tensor.shape, dimg.np_dtype)
+        planes = 3 if dimg.is_vector else 1
+        _abi.check(self.lib.b200reg_mask_image(self.ctx, dimg.ptr, dimg.dtype_id, mask.ptr, mask.tensor.numel(), planes, float(outside_value),
+                                               C.c_void_p(out.data_ptr())))
+        return dimg.like(out)
+
+    def divide_scalar(self, dimg, divisor):
+        out = self.empty(dimg.tensor.shape, dimg.np_dtype)
+        _abi.check(self.lib.b200reg_divide_scalar(self.ctx, dimg.ptr, dimg.dtype_id, dimg.tensor.numel(), float(divisor), C.c_void_p(out.data_ptr())))
+        return dimg.like(out)
+
+    def constant_field(self, grid, vector, mask=None):
+        """VectorFloat64 field on the grid of ``grid``: ``vector`` (dx, dy, dz) inside ``mask`` (everywhere without), 0 outside."""
+        x, y, z = grid.GetSize()
+        out = self.empty((3, z, y, x), np.float64)
+        _abi.check(self.lib.b200reg_constant_field(self.ctx, mask.ptr if mask is not None else None, x * y * z,
+                                                   (C.c_double * 3)(*[float(v) for v in vector]), C.c_void_p(out.data_ptr())))
+        return DeviceImage(out, np.float64, grid.GetSpacing(), grid.GetOrigin(), grid.GetDirection(), True)
+
+    def radial_bend_field(self, mask, reference_index, axis, scale, clip_axis=-1, clip_keep_upper=True):
+        x, y, z = mask.GetSize()
+        out = self.empty((3, z, y, x), np.float64)
+        _abi.check(self.lib.b200reg_radial_bend_field(self.ctx, mask.ptr, self._size3(mask), (C.c_int32 * 3)(*[int(v) for v in reference_index]),
+                                                      (C.c_double * 3)(*[float(v) for v in axis]), float(scale), int(clip_axis),
+                                                      int(bool(clip_keep_upper)), C.c_void_p(out.data_ptr())))
+        return mask.like(out, np.float64, True)
+
     def pack_decision(self, label, bit, packed, first):
         _abi.check(self.lib.b200reg_pack_decision(self.ctx, label.ptr, int(bit), C.c_void_p(packed.data_ptr()), label.tensor.numel(), int(bool(first))))
 

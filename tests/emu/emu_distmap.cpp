@@ -1,0 +1,59 @@
+// emu_distmap.cpp -- TEST INFRASTRUCTURE: runs the kernels of platipy_b200/csrc/distmap_kernels.cuh under the serial host
+// emulation of cuda_emu.h, with the launch sequence of platipy_b200/csrc/distmap.cuh.  Built by tests/test_emu_distmap.py.
+#include "cuda_emu.h"
+
+#include <vector>
+
+#include "../../platipy_b200/csrc/distmap_kernels.cuh"
+
+using namespace b200;
+
+#define EMU_API extern "C" __attribute__((visibility("default")))
+
+EMU_API void emu_signed_maurer(const uint8_t* mask, int nx, int ny, int nz, const double* spacing, int inside_pos, int squared, int use_spacing,
+                               float* out, unsigned grid, unsigned block)
+{
+    const size_t n = (size_t)nx * ny * nz;
+    std::vector<float> g(n);
+    std::vector<int> h(n);
+    emu_launch(maurer_init_kernel, grid, block, mask, nx, ny, nz, out);
+    for (int axis = 0; axis < 3; ++axis) {
+        const float spf = use_spacing ? (float)spacing[axis] : 1.0f;
+        if (axis == 2)
+            emu_launch(maurer_voronoi_kernel<true>, grid, block, out, mask, nx, ny, nz, axis, spf, inside_pos, squared, g.data(), h.data());
+        else
+            emu_launch(maurer_voronoi_kernel<false>, grid, block, out, mask, nx, ny, nz, axis, spf, inside_pos, squared, g.data(), h.data());
+    }
+}
+EMU_API void emu_label_contour(const uint8_t* in, int nx, int ny, int nz, int fully, uint8_t* out, unsigned grid, unsigned block)
+{
+    if (fully) emu_launch(label_contour_kernel<true>, grid, block, in, nx, ny, nz, out);
+    else emu_launch(label_contour_kernel<false>, grid, block, in, nx, ny, nz, out);
+}
+EMU_API void emu_binary_morph(const uint8_t* in, int nx, int ny, int nz, const int* offs, int noffs, int dilate, int boundary_fg, uint8_t* out,
+                              unsigned grid, unsigned block)
+{
+    if (dilate) emu_launch(binary_morph_kernel<true>, grid, block, in, nx, ny, nz, out, offs, noffs, boundary_fg);
+    else emu_launch(binary_morph_kernel<false>, grid, block, in, nx, ny, nz, out, offs, noffs, boundary_fg);
+}
+EMU_API void emu_u8_binary_op(const uint8_t* a, const uint8_t* b, int op, uint8_t* out, size_t n, unsigned grid, unsigned block)
+{
+    emu_launch(u8_binary_op_kernel, grid, block, a, b, op, out, n);
+}
+EMU_API void emu_mask_f64(const double* in, const uint8_t* mask, size_t n, int planes, double outside, double* out, unsigned grid, unsigned block)
+{
+    emu_launch(mask_image_kernel<double>, grid, block, in, mask, n, planes, outside, out);
+}
+EMU_API void emu_divide_f64(const double* in, double divisor, double* out, size_t n, unsigned grid, unsigned block)
+{
+    emu_launch(divide_scalar_kernel<double>, grid, block, in, divisor, out, n);
+}
+EMU_API void emu_constant_field(const uint8_t* mask, size_t n, double vx, double vy, double vz, double* out, unsigned grid, unsigned block)
+{
+    emu_launch(constant_field_kernel, grid, block, mask, n, vx, vy, vz, out);
+}
+EMU_API void emu_radial_bend(const uint8_t* mask, int nx, int ny, int nz, int rx, int ry, int rz, double ax, double ay, double az, double scale,
+                             int clip_axis, int clip_keep_upper, double* out, unsigned grid, unsigned block)
+{
+    emu_launch(radial_bend_kernel, grid, block, mask, nx, ny, nz, rx, ry, rz, ax, ay, az, scale, clip_axis, clip_keep_upper, out);
+}
