@@ -304,6 +304,16 @@ int b200reg_constant_field(b200reg_ctx* ctx, const uint8_t* d_mask, size_t n, co
 int b200reg_radial_bend_field(b200reg_ctx* ctx, const uint8_t* d_mask, const int32_t size[3], const int32_t reference_index[3],
                               const double axis[3], double scale, int clip_axis, int clip_keep_upper, double* d_out_soa);
 
+/* ---- compute_weight_map, vote_type "patch_correlation" (fusion.py:82-146) ------------------------------------------------ */
+/* Pearson correlation of target and moving over the window (wx, wy, wz voxels) around every voxel, clipped to the image: output
+ * voxel i covers [i - (w - 1) / 2, i + w / 2] per axis (fusion.py:96-103).  Float64 arithmetic and scipy.stats.pearsonr's special
+ * cases (constant patch -> NaN -> 0 by fusion.py:124, two samples, clipping to [-1, 1]).  d_out: Float64 on the same grid. */
+int b200reg_patch_correlation(b200reg_ctx* ctx, const float* d_target, const float* d_moving, const int32_t size[3], const int32_t window[3],
+                              double* d_out);
+/* out = (take_abs ? |in| : in) * mul + add on a Float32 / Float64 image, constants in the pixel type: the image-with-constant
+ * operators a correlation_function is made of (fusion.py:138-146: x + 1, sitk.Abs(x)).  d_out may alias d_in. */
+int b200reg_scale_shift(b200reg_ctx* ctx, const void* d_in, int dtype, size_t n, int take_abs, double mul, double add, void* d_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -283,9 +283,43 @@ def compute_weight_map(target_image, moving_image, vote_type="unweighted", vote_
             pw = np.power(inv.astype(np.float64), abs(gain / 2.0)).astype(np.float32)
             w = (pw.astype(np.float64) * factor).astype(np.float32)
         w = _normalise(w, vote_params.get("normalise", False))
+    elif vt == "patch_correlation":
+        w = _patch_correlation(target_image, moving_image, vote_params)
     else:
         raise NotImplementedError(vote_type)
     return _like(w, target_image)
+
+
+def _patch_correlation(target_image, moving_image, vote_params):
+    """fusion.py:82-146 with numpy's sliding_window_view in place of skimage's view_as_windows and scipy.stats.pearsonr on
+    Float64 copies of the patches (the arithmetic pearsonr uses for Float32 data under the reference's pinned numpy 1.24.4 /
+    scipy 1.9.3: dtype = type(1.0 + x[0] + y[0]) is float64 there)."""
+    import warnings
+
+    from numpy.lib.stride_tricks import sliding_window_view
+    from scipy.stats import pearsonr
+
+    voxel_size = vote_params["resampled_voxel_size_mm"]
+    t_res = smooth_and_resample(target_image, isotropic_voxel_size_mm=voxel_size)
+    m_res = smooth_and_resample(moving_image, isotropic_voxel_size_mm=voxel_size)
+    arr_t, arr_m = t_res.array, m_res.array
+    arr_mask = 0 * arr_t + 1
+    window = [int(vote_params["patch_window_mm"] / i) for i in t_res.GetSpacing()[::-1]]
+    padder = [((i - 1) // 2, i // 2) for i in window]
+    arr_t, arr_m, arr_mask = np.pad(arr_t, padder), np.pad(arr_m, padder), np.pad(arr_mask, padder)
+    v_t, v_m, v_k = (sliding_window_view(a, window) for a in (arr_t, arr_m, arr_mask))
+    shape = v_t.shape[:3]
+    corr = np.empty(int(np.prod(shape)), dtype=np.float64)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        for i, idx in enumerate(np.ndindex(*shape)):
+            keep = v_k[idx].ravel() != 0
+            corr[i] = pearsonr(v_t[idx].ravel()[keep].astype(np.float64), v_m[idx].ravel()[keep].astype(np.float64))[0]
+    corr = corr.reshape(t_res.GetSize()[::-1])
+    corr[np.isnan(corr)] = 0
+    corr_img = resample(_like(corr, t_res), target_image)  # sitk.Resample(corr_img, target_image): linear, default 0
+    w = vote_params["correlation_function"](corr_img)
+    return w.array.astype(np.float32)
 
 
 def combine_labels(atlas_set, structure_name, label="DIR", threshold=1e-4, smooth_sigma=1.0):

@@ -116,6 +116,8 @@ SIGNATURES = {
     "b200reg_mask_image": (C.c_int, [_P, _P, C.c_int, _P, C.c_size_t, C.c_int, C.c_double, _P]),
     "b200reg_divide_scalar": (C.c_int, [_P, _P, C.c_int, C.c_size_t, C.c_double, _P]),
     "b200reg_constant_field": (C.c_int, [_P, _P, C.c_size_t, C.POINTER(C.c_double), _P]),
+    "b200reg_patch_correlation": (C.c_int, [_P, _P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P]),
+    "b200reg_scale_shift": (C.c_int, [_P, _P, C.c_int, C.c_size_t, C.c_int, C.c_double, C.c_double, _P]),
     "b200reg_radial_bend_field": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_double, C.c_int,
                                             C.c_int, _P]),
 }

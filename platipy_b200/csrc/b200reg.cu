@@ -9,6 +9,7 @@
 #include "linreg.cuh"
 #include "postproc.cuh"
 #include "distmap.cuh"
+#include "patchcorr_kernels.cuh"
 #include "gauss.cuh"
 #include "resample.cuh"
 
@@ -942,6 +943,39 @@ API int b200reg_radial_bend_field(b200reg_ctx* ctx, const uint8_t* d_mask, const
     radial_bend_kernel<<<elementwise_blocks(ctx, n, 256), 256, 0, ctx->stream>>>(d_mask, size[0], size[1], size[2], reference_index[0], reference_index[1],
                                                                                 reference_index[2], axis[0], axis[1], axis[2], scale, clip_axis,
                                                                                 clip_keep_upper, d_out_soa);
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+
+// ---- compute_weight_map, vote_type "patch_correlation" (label/fusion.py:82-146) -------------------------------------------------
+API int b200reg_patch_correlation(b200reg_ctx* ctx, const float* d_target, const float* d_moving, const int32_t size[3], const int32_t window[3],
+                                  double* d_out)
+{
+    ENTER(ctx);
+    REQUIRE(d_target && d_moving && d_out && size && window, "invalid argument");
+    for (int d = 0; d < 3; ++d) REQUIRE(size[d] > 0 && window[d] >= 1, "invalid size / window");
+    // scipy.stats.pearsonr: "x and y must have length at least 2" -- only a 1 x 1 x 1 window (or a one-voxel image) can get there
+    const long long largest = (long long)(window[0] < size[0] ? window[0] : size[0]) * (window[1] < size[1] ? window[1] : size[1]) *
+                              (window[2] < size[2] ? window[2] : size[2]);
+    REQUIRE(largest >= 2, "x and y must have length at least 2.");
+    const size_t n = (size_t)size[0] * size[1] * size[2];
+    patch_correlation_kernel<<<elementwise_blocks(ctx, n, 128), 128, 0, ctx->stream>>>(d_target, d_moving, size[0], size[1], size[2], window[0], window[1],
+                                                                                       window[2], d_out);
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+API int b200reg_scale_shift(b200reg_ctx* ctx, const void* d_in, int dtype, size_t n, int take_abs, double mul, double add, void* d_out)
+{
+    ENTER(ctx);
+    REQUIRE(d_in && d_out && n > 0, "invalid argument");
+    REQUIRE(dtype == B200REG_F32 || dtype == B200REG_F64, "scale_shift: Float32 or Float64 image expected");
+    const int nb = elementwise_blocks(ctx, n, 256);
+    if (dtype == B200REG_F32)
+        scale_shift_kernel<float><<<nb, 256, 0, ctx->stream>>>((const float*)d_in, n, take_abs, (float)mul, (float)add, (float*)d_out);
+    else
+        scale_shift_kernel<double><<<nb, 256, 0, ctx->stream>>>((const double*)d_in, n, take_abs, mul, add, (double*)d_out);
     ctx->launches++;
     B200_CHECK_LAUNCH();
     return B200REG_OK;

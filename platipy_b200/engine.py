@@ -85,6 +85,40 @@ class DeviceImage:
         return DeviceImage(tensor, self.np_dtype if np_dtype is None else np_dtype, self.spacing, self.origin, self.direction,
                            self.is_vector if is_vector is None else is_vector)
 
+    # image-with-constant arithmetic (SimpleITK's Image operators), as far as a ``correlation_function`` needs it
+    # (fusion.py:138-146: ``lambda x: x + 1``, ``abs``); each is one kernel on the engine's stream
+    def _affine(self, mul, add, take_abs=False):
+        if not np.isscalar(mul) or not np.isscalar(add):
+            raise TypeError("DeviceImage arithmetic supports scalar constants only")
+        return Engine.get(self.tensor.device.index).scale_shift(self, mul, add, take_abs)
+
+    def __add__(self, c):
+        return self._affine(1.0, c)
+
+    __radd__ = __add__
+
+    def __sub__(self, c):
+        return self._affine(1.0, -c) if np.isscalar(c) else NotImplemented
+
+    def __rsub__(self, c):
+        return self._affine(-1.0, c)
+
+    def __mul__(self, c):
+        return self._affine(c, 0.0)
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, c):
+        if not np.isscalar(c):
+            raise TypeError("DeviceImage arithmetic supports scalar constants only")
+        return Engine.get(self.tensor.device.index).divide_scalar(self, c)
+
+    def __neg__(self):
+        return self._affine(-1.0, 0.0)
+
+    def __abs__(self):
+        return self._affine(1.0, 0.0, True)
+
 
 def pinned_empty(shape, dtype):
     """numpy array backed by pinned host memory (keeps the owning tensor alive through ``.base``)."""
@@ -518,6 +552,22 @@ class Engine:
                                                       (C.c_double * 3)(*[float(v) for v in axis]), float(scale), int(clip_axis),
                                                       int(bool(clip_keep_upper)), C.c_void_p(out.data_ptr())))
         return mask.like(out, np.float64, True)
+
+    def patch_correlation(self, target, moving, window):
+        """Pearson correlation over the window (x, y, z voxels) around every voxel -> Float64 (fusion.py:82-124)."""
+        out = self.empty(target.tensor.shape, np.float64)
+        _abi.check(self.lib.b200reg_patch_correlation(self.ctx, target.ptr, moving.ptr, self._size3(target), (C.c_int32 * 3)(*[int(v) for v in window]),
+                                                      C.c_void_p(out.data_ptr())))
+        return target.like(out, np.float64, False)
+
+    def scale_shift(self, dimg, mul=1.0, add=0.0, take_abs=False):
+        """(|x| if take_abs else x) * mul + add on a Float32 / Float64 image."""
+        if dimg.np_dtype not in (np.dtype(np.float32), np.dtype(np.float64)) or dimg.is_vector:
+            raise TypeError("image arithmetic on the device is implemented for scalar Float32 / Float64 images")
+        out = self.empty(dimg.tensor.shape, dimg.np_dtype)
+        _abi.check(self.lib.b200reg_scale_shift(self.ctx, dimg.ptr, dimg.dtype_id, dimg.tensor.numel(), int(bool(take_abs)), float(mul), float(add),
+                                                C.c_void_p(out.data_ptr())))
+        return dimg.like(out)
 
     def pack_decision(self, label, bit, packed, first):
         _abi.check(self.lib.b200reg_pack_decision(self.ctx, label.ptr, int(bit), C.c_void_p(packed.data_ptr()), label.tensor.numel(), int(bool(first))))

@@ -26,6 +26,9 @@ DEFAULT_VOTE_PARAMS = {
     "gain": 6,
     "blockSize": 5,
     "normalise": False,
+    "patch_window_mm": 25,
+    "resampled_voxel_size_mm": 3,
+    "correlation_function": lambda x: x + 1,
 }
 
 
@@ -42,16 +45,18 @@ def compute_weight_map(target_image, moving_image, vote_type="unweighted", vote_
     as in the reference (multiatlas/run.py:92-96)."""
     eng = Engine.get()
     vt = vote_type.lower()
-    if vt not in VOTE_TYPES and vt != "block":
-        # patch_correlation (fusion.py:82-146) is a host-side scipy / skimage loop in the reference: SURVEY 8f-3 ("next")
-        raise NotImplementedError(f"vote_type {vote_type!r} is not implemented on the B200 path (unweighted, global, local, block are)")
+    if vt not in VOTE_TYPES and vt not in ("block", "patch_correlation"):
+        # the reference falls through its if / elif chain and fails on the unbound weight_map (fusion.py:151-202)
+        raise UnboundLocalError(f"vote_type {vote_type!r}: local variable 'weight_map' referenced before assignment")
     t, m = eng.to_device(target_image), eng.to_device(moving_image)
     # fusion.py:76-80: cast to Float32 unless the pixel id is 6
     t, m = eng.cast(t, np.float32), eng.cast(m, np.float32)
     if t.GetSize() != m.GetSize():
         raise RuntimeError("compute_weight_map: target and moving images do not occupy the same grid")
     normalise = False
-    if vt == "block":
+    if vt == "patch_correlation":
+        w = _patch_correlation(eng, t, m, vote_params, target_image)
+    elif vt == "block":
         factor, gain, block_size = float(vote_params["factor"]), float(vote_params["gain"]), vote_params["blockSize"]
         normalise = vote_params["normalise"]
         if isinstance(block_size, int):
@@ -73,6 +78,28 @@ def compute_weight_map(target_image, moving_image, vote_type="unweighted", vote_
         mask = eng.cast(eng.to_device(normalise), np.uint8)
         eng.normalise_by_max(w, mask)
     return _back(eng, w, target_image)
+
+
+def _patch_correlation(eng, t, m, vote_params, like):
+    """fusion.py:82-146: both images resampled to isotropic voxels (linear, no smoothing), Pearson correlation of the two over
+    a cubic window around every voxel of that grid (one kernel instead of the reference's Python loop over patches),
+    resampled back onto the target grid (linear, default 0), ``correlation_function`` applied, cast to Float32."""
+    from .registration import smooth_and_resample
+
+    voxel_size = vote_params["resampled_voxel_size_mm"]
+    t_res = smooth_and_resample(t, isotropic_voxel_size_mm=voxel_size)
+    m_res = smooth_and_resample(m, isotropic_voxel_size_mm=voxel_size)
+    eng.wait_caller()
+    window_zyx = [int(vote_params["patch_window_mm"] / i) for i in t_res.GetSpacing()[::-1]]  # fusion.py:97
+    corr = eng.patch_correlation(t_res, m_res, window_zyx[::-1])
+    corr = eng.resample(corr, t, None, sk.sitkLinear, 0.0)  # sitk.Resample(corr_img, target_image)
+    fn = vote_params["correlation_function"]
+    try:
+        w = fn(corr)  # device arithmetic: x + 1, abs(x), 2 * x ...
+    except (TypeError, AttributeError):
+        # a function written against the SimpleITK API (sitk.Abs(x) ...): hand it the image in the caller's representation
+        w = fn(sk.from_native(eng.to_host(corr), like))
+    return eng.cast(eng.to_device(w), np.float32)
 
 
 def _structure_names(structure_name):

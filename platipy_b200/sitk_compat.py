@@ -145,6 +145,36 @@ class Image:
     def is_vector(self):
         return self._is_vector
 
+    # image-with-constant operators of SimpleITK's Image, for user callbacks such as compute_weight_map's
+    # ``correlation_function`` (fusion.py:138-146).  Host numpy on the container; the product's own paths never use them.
+    def _with(self, arr):
+        return Image(np.asarray(arr, dtype=self._arr.dtype), self._spacing, self._origin, self._direction, self._is_vector)
+
+    def __add__(self, c):
+        return self._with(self._arr + self._arr.dtype.type(c)) if np.isscalar(c) else NotImplemented
+
+    __radd__ = __add__
+
+    def __sub__(self, c):
+        return self._with(self._arr - self._arr.dtype.type(c)) if np.isscalar(c) else NotImplemented
+
+    def __rsub__(self, c):
+        return self._with(self._arr.dtype.type(c) - self._arr) if np.isscalar(c) else NotImplemented
+
+    def __mul__(self, c):
+        return self._with(self._arr * self._arr.dtype.type(c)) if np.isscalar(c) else NotImplemented
+
+    __rmul__ = __mul__
+
+    def __truediv__(self, c):
+        return self._with(self._arr / self._arr.dtype.type(c)) if np.isscalar(c) else NotImplemented
+
+    def __neg__(self):
+        return self._with(-self._arr)
+
+    def __abs__(self):
+        return self._with(np.abs(self._arr))
+
     def same_space(self, other, tol=1e-6):
         return (
             self.GetSize() == tuple(other.GetSize())

@@ -9,6 +9,10 @@
 #include <cstddef>
 #include <cstdint>
 
+#include <algorithm>
+using std::max;
+using std::min;
+
 #define __global__
 #define __device__
 #define __host__

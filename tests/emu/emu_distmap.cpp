@@ -5,6 +5,7 @@
 #include <vector>
 
 #include "../../platipy_b200/csrc/distmap_kernels.cuh"
+#include "../../platipy_b200/csrc/patchcorr_kernels.cuh"
 
 using namespace b200;
 
@@ -56,4 +57,17 @@ EMU_API void emu_radial_bend(const uint8_t* mask, int nx, int ny, int nz, int rx
                              int clip_axis, int clip_keep_upper, double* out, unsigned grid, unsigned block)
 {
     emu_launch(radial_bend_kernel, grid, block, mask, nx, ny, nz, rx, ry, rz, ax, ay, az, scale, clip_axis, clip_keep_upper, out);
+}
+EMU_API void emu_patch_correlation(const float* t, const float* m, int nx, int ny, int nz, int wx, int wy, int wz, double* out, unsigned grid,
+                                   unsigned block)
+{
+    emu_launch(patch_correlation_kernel, grid, block, t, m, nx, ny, nz, wx, wy, wz, out);
+}
+EMU_API void emu_scale_shift_f64(const double* in, size_t n, int take_abs, double mul, double add, double* out, unsigned grid, unsigned block)
+{
+    emu_launch(scale_shift_kernel<double>, grid, block, in, n, take_abs, mul, add, out);
+}
+EMU_API void emu_scale_shift_f32(const float* in, size_t n, int take_abs, float mul, float add, float* out, unsigned grid, unsigned block)
+{
+    emu_launch(scale_shift_kernel<float>, grid, block, in, n, take_abs, mul, add, out);
 }

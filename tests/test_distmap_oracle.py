@@ -236,3 +236,59 @@ def test_iar_statistics_flag_the_outlier():
         iar.z_scores(g_vals[0], g_vals[1:], "median")
     with pytest.raises(AttributeError):
         iar.run_iar({}, "S", project_on_sphere=True)
+
+
+# ---- compute_weight_map(vote_type="patch_correlation"): kernel (host emulation) against scipy.stats.pearsonr ------------------------
+def test_emulated_patch_correlation_matches_pearsonr(emu):
+    from scipy.stats import pearsonr
+
+    rng = np.random.default_rng(12)
+    shape = (9, 11, 13)
+    nz, ny, nx = shape
+    t = ndi.gaussian_filter(rng.standard_normal(shape), 1.0).astype(np.float32)
+    m = (0.6 * t + 0.4 * ndi.gaussian_filter(rng.standard_normal(shape), 1.0)).astype(np.float32)
+    t[:3, :4, :5] = 2.5  # a constant corner: pearsonr -> NaN -> 0
+    for window in ((4, 4, 4), (5, 3, 2), (1, 1, 2), (8, 8, 8)):  # (z, y, x) like window_box_im
+        out = np.empty(shape, np.float64)
+        emu.emu_patch_correlation(_P(t), _P(m), nx, ny, nz, window[2], window[1], window[0], _P(out), C.c_uint(3), C.c_uint(64))
+        exp = np.empty(shape, np.float64)
+        for z, y, x in np.ndindex(*shape):
+            sl = tuple(slice(max(c - (w - 1) // 2, 0), min(c + w // 2, n - 1) + 1) for c, w, n in zip((z, y, x), window, shape))
+            a, b = t[sl].ravel().astype(np.float64), m[sl].ravel().astype(np.float64)
+            if (a == a[0]).all() or (b == b[0]).all():
+                exp[z, y, x] = 0.0
+            else:
+                exp[z, y, x] = pearsonr(a, b)[0]
+        assert np.allclose(out, exp, rtol=0, atol=1e-12), window
+        assert np.all(np.abs(out) <= 1.0) and (max(window) > 4 or out[0, 0, 0] == 0.0)
+    vals = rng.standard_normal(1000)
+    out = np.empty_like(vals)
+    emu.emu_scale_shift_f64(_P(vals), C.c_size_t(vals.size), 1, C.c_double(2.0), C.c_double(1.0), _P(out), C.c_uint(3), C.c_uint(32))
+    assert np.array_equal(out, np.abs(vals) * 2.0 + 1.0)
+    v32 = vals.astype(np.float32)
+    o32 = np.empty_like(v32)
+    emu.emu_scale_shift_f32(_P(v32), C.c_size_t(v32.size), 0, C.c_float(1.0), C.c_float(1e-5), _P(o32), C.c_uint(3), C.c_uint(32))
+    assert np.array_equal(o32, v32 + np.float32(1e-5))
+
+
+def test_patch_correlation_weight_map_chain_on_the_cpu(emu):
+    """The whole vote as the product composes it -- resample both images, the correlation kernel, resample back, the correlation
+    function, cast -- with the oracle standing in for the two resampling steps, against the reference-shaped restatement
+    (padding, window views, pearsonr per patch)."""
+    from oracle import platipy_ref as ref
+    from platipy_b200 import sitk_compat as sk
+    from platipy_b200.synth import synth_pair
+
+    f, m = synth_pair((40, 36, 24), seed=5, spacing=(1.0, 1.0, 2.0))
+    for fn in (lambda x: x + 1, abs):
+        vp = dict(patch_window_mm=12, resampled_voxel_size_mm=3, correlation_function=fn)
+        exp = ref.compute_weight_map(f, m, "patch_correlation", vp)
+        t_res, m_res = ref.smooth_and_resample(f, isotropic_voxel_size_mm=3), ref.smooth_and_resample(m, isotropic_voxel_size_mm=3)
+        window = [int(12 / i) for i in t_res.GetSpacing()[::-1]]
+        nz, ny, nx = t_res.array.shape
+        corr = np.empty(t_res.array.shape, np.float64)
+        emu.emu_patch_correlation(_P(t_res.array), _P(m_res.array), nx, ny, nz, window[2], window[1], window[0], _P(corr), C.c_uint(4), C.c_uint(64))
+        back = ref.resample(Image(corr, t_res.GetSpacing(), t_res.GetOrigin(), t_res.GetDirection()), f)
+        got = fn(back).array.astype(np.float32)
+        assert exp.array.dtype == np.float32 and np.allclose(got, exp.array, rtol=1e-6, atol=1e-7)
+        assert exp.array.min() >= 0.0

@@ -44,8 +44,8 @@ def test_weight_maps_match_oracle(engine):
         else:
             assert np.array_equal(got.array, exp.array)
     assert np.array_equal(fusion.compute_weight_map(t, m, "unweighted", None).array, np.ones(t.array.shape, np.float32))
-    with pytest.raises(NotImplementedError):
-        fusion.compute_weight_map(t, m, "patch_correlation", params)
+    with pytest.raises(UnboundLocalError):  # the reference falls through its if / elif chain (fusion.py:151-202)
+        fusion.compute_weight_map(t, m, "no_such_vote", params)
 
 
 def test_block_weight_map_and_normalise_match_oracle(engine):

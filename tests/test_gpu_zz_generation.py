@@ -221,3 +221,29 @@ def test_iterative_atlas_removal(engine):
     assert all(k in atlas_set for k in kept)
     one = iar.run_iar(atlas_set, "HEART", min_best_atlases=8, single_step=True, z_score_statistic="STD", outlier_method="STD")
     assert "A12" not in one and len(one) >= 8
+
+
+def test_patch_correlation_weight_map(engine):
+    """vote_type "patch_correlation" (fusion.py:82-146): one kernel instead of a Python loop of scipy.stats.pearsonr calls.
+    Float64 sums in window order vs numpy's pairwise / BLAS order: the Float32 weight map agrees to the north star's 1e-5."""
+    from oracle import platipy_ref as ref
+    from platipy_b200 import fusion
+    from platipy_b200 import sitk_compat as sk
+    from platipy_b200.synth import synth_pair
+
+    t, m = synth_pair((40, 36, 24), seed=5, spacing=(1.0, 1.0, 2.0))
+    for fn in (lambda x: x + 1, abs, lambda x: 0.5 * x + 1.5):
+        vp = dict(patch_window_mm=12, resampled_voxel_size_mm=3, correlation_function=fn)
+        got, exp = fusion.compute_weight_map(t, m, "patch_correlation", vp), ref.compute_weight_map(t, m, "patch_correlation", vp)
+        assert got.GetPixelID() == sk.sitkFloat32 and got.array.shape == t.array.shape
+        assert np.allclose(got.array, exp.array, rtol=1e-5, atol=1e-6)
+    # a correlation function written against the host image API gets a host image
+    vp["correlation_function"] = lambda x: Image(np.abs(x.array), x.GetSpacing(), x.GetOrigin(), x.GetDirection())
+    got2 = fusion.compute_weight_map(t, m, "patch_correlation", vp)
+    vp["correlation_function"] = abs
+    assert np.array_equal(got2.array, fusion.compute_weight_map(t, m, "patch_correlation", vp).array)
+    # device in -> device out, and the default parameters carry the reference's keys
+    dw = fusion.compute_weight_map(engine.to_device(t), engine.to_device(m), "patch_correlation",
+                                   dict(fusion.DEFAULT_VOTE_PARAMS, patch_window_mm=12, resampled_voxel_size_mm=3))
+    vp["correlation_function"] = lambda x: x + 1
+    assert np.array_equal(engine.to_host(dw).array, fusion.compute_weight_map(t, m, "patch_correlation", vp).array)
