@@ -1,6 +1,7 @@
 """
-NIfTI-1 reading and writing for scalar 3-D images -- the on-disk format either side of the atlas pipeline
-(reference multiatlas/run.py:160-164 ``sitk.ReadImage``; service code writes results with ``sitk.WriteImage``).
+NIfTI-1 reading and writing for 3-D scalar images and 3-D vector images (displacement fields) -- the on-disk format
+either side of the atlas pipeline (reference multiatlas/run.py:160-164 ``sitk.ReadImage``; service code writes results
+and deformation fields with ``sitk.WriteImage``).
 
 Host-side only (numpy + gzip); no device work.  Geometry follows itk::NiftiImageIO:
 
@@ -14,6 +15,10 @@ Host-side only (numpy + gzip); no device work.  Geometry follows itk::NiftiImage
   ``scl_inter`` = 0, single-file magic ``n+1`` with ``vox_offset`` = 352.  Header geometry fields are float32, so a
   round trip reproduces spacing / origin / direction to float32 precision (as with SimpleITK).
 * ``scl_slope`` / ``scl_inter`` other than (0 | 1, 0) rescale the data to float32 on reading, like ITK.
+
+* Vector images follow itk::NiftiImageIO: ``dim`` = (5, nx, ny, nz, 1, components), ``intent_code`` =
+  NIFTI_INTENT_VECTOR (1007), components stored as the slowest file dimension (planar) and interleaved in memory;
+  component values are stored as they are (ITK's ConvertRASVectors is off by default).
 
 Paths ending in ``.gz`` are gzip-compressed.
 """
@@ -113,14 +118,17 @@ def read_image(path):
     qb, qc, qd, qx, qy, qz = struct.unpack(e + "6f", raw[256:280])
     srow = np.array(struct.unpack(e + "12f", raw[280:328]), dtype=np.float64).reshape(3, 4)
     ndim = dim[0]
-    if ndim < 1 or ndim > 7 or any(d > 1 for d in dim[4:ndim + 1]):
-        raise NotImplementedError(f"{path}: only 3-D scalar images are supported (dim = {dim})")
+    ncomp = int(dim[5]) if ndim == 5 and dim[4] <= 1 and dim[5] > 1 else 1
+    if ndim < 1 or ndim > 7 or (ncomp == 1 and any(d > 1 for d in dim[4:ndim + 1])) or any(d > 1 for d in dim[6:ndim + 1]):
+        raise NotImplementedError(f"{path}: only 3-D scalar and 3-D vector images are supported (dim = {dim})")
     nx, ny, nz = (max(int(dim[k]), 1) if k <= ndim else 1 for k in (1, 2, 3))
     if datatype not in _CODE_TO_DTYPE:
         raise NotImplementedError(f"{path}: NIfTI datatype {datatype} is not supported")
     dt = np.dtype(_CODE_TO_DTYPE[datatype]).newbyteorder(e)
     off = int(vox_offset) if vox_offset >= 352 else 352
-    arr = np.frombuffer(raw, dtype=dt, count=nx * ny * nz, offset=off).reshape(nz, ny, nx).astype(dt.newbyteorder("="), copy=True)
+    arr = np.frombuffer(raw, dtype=dt, count=ncomp * nx * ny * nz, offset=off).astype(dt.newbyteorder("="), copy=True)
+    # the file holds one plane set per component; a vector image interleaves them: [z, y, x, c]
+    arr = arr.reshape(nz, ny, nx) if ncomp == 1 else np.ascontiguousarray(np.moveaxis(arr.reshape(ncomp, nz, ny, nx), 0, -1))
     if scl_slope not in (0.0, 1.0) or (scl_slope != 0.0 and scl_inter != 0.0):
         arr = (arr.astype(np.float32) * np.float32(scl_slope) + np.float32(scl_inter)).astype(np.float32)
     spacing = np.array([abs(pixdim[k]) if k <= ndim and pixdim[k] != 0 else 1.0 for k in (1, 2, 3)], dtype=np.float64)
@@ -137,22 +145,24 @@ def read_image(path):
         origin = _LPS @ srow[:, 3]
     else:
         direction, origin = np.eye(3), np.zeros(3)
-    return Image(arr, tuple(spacing), tuple(origin), tuple(direction.reshape(9)))
+    return Image(arr, tuple(spacing), tuple(origin), tuple(direction.reshape(9)), is_vector=ncomp > 1)
 
 
 def write_image(image, path):
-    """``sitk.WriteImage`` for a 3-D scalar image as single-file NIfTI-1 (``.nii`` or ``.nii.gz``)."""
+    """``sitk.WriteImage`` for a 3-D scalar or vector image as single-file NIfTI-1 (``.nii`` or ``.nii.gz``)."""
     from . import sitk_compat as sk
 
     image = sk.to_native(image)
-    if image.is_vector:
-        raise NotImplementedError("writing vector images as NIfTI is not supported")
     arr = np.ascontiguousarray(image.array)
     if arr.dtype == np.bool_:
         arr = arr.astype(np.uint8)
     if arr.dtype not in _DTYPE_TO_CODE:
         raise NotImplementedError(f"pixel type {arr.dtype} cannot be written as NIfTI")
-    nz, ny, nx = arr.shape
+    ncomp = 1
+    if image.is_vector:
+        ncomp = arr.shape[3]
+        arr = np.ascontiguousarray(np.moveaxis(arr, -1, 0))  # planar in the file
+    nz, ny, nx = arr.shape[-3:]
     spacing = np.asarray(image.GetSpacing(), dtype=np.float64)
     direction = np.asarray(image.GetDirection(), dtype=np.float64).reshape(3, 3)
     ras_rot = _LPS @ direction
@@ -161,10 +171,14 @@ def write_image(image, path):
     srow = np.hstack([ras_rot * spacing[None, :], ras_org[:, None]])
     hdr = bytearray(348)
     struct.pack_into("<i", hdr, 0, 348)
-    struct.pack_into("<8h", hdr, 40, 3, nx, ny, nz, 1, 1, 1, 1)
+    if ncomp == 1:
+        struct.pack_into("<8h", hdr, 40, 3, nx, ny, nz, 1, 1, 1, 1)
+    else:
+        struct.pack_into("<8h", hdr, 40, 5, nx, ny, nz, 1, ncomp, 1, 1)
+        struct.pack_into("<h", hdr, 68, 1007)  # intent_code: NIFTI_INTENT_VECTOR
     struct.pack_into("<h", hdr, 70, _DTYPE_TO_CODE[arr.dtype])
     struct.pack_into("<h", hdr, 72, arr.dtype.itemsize * 8)
-    struct.pack_into("<8f", hdr, 76, qfac, spacing[0], spacing[1], spacing[2], 0.0, 0.0, 0.0, 0.0)
+    struct.pack_into("<8f", hdr, 76, qfac, spacing[0], spacing[1], spacing[2], 0.0, 1.0 if ncomp > 1 else 0.0, 0.0, 0.0)
     struct.pack_into("<fff", hdr, 108, 352.0, 1.0, 0.0)
     struct.pack_into("<B", hdr, 123, 2 | 8)  # xyzt_units: millimetres, seconds
     struct.pack_into("<hh", hdr, 252, 1, 1)   # qform_code, sform_code: NIFTI_XFORM_SCANNER_ANAT

@@ -104,8 +104,33 @@ def test_quaternion_round_trip_and_errors(tmp_path):
     with pytest.raises(RuntimeError):
         nio.read_image(bad)
     with pytest.raises(NotImplementedError):
-        nio.write_image(Image(np.zeros((2, 2, 2, 3)), is_vector=True), tmp_path / "v.nii")
+        nio.write_image(Image(np.zeros((2, 2, 2, 3), np.complex64), is_vector=True), tmp_path / "v.nii")
     four_d = tmp_path / "4d.nii"
     four_d.write_bytes(_hand_header((4, 2, 2, 2, 5, 1, 1, 1), 2, 8, (1, 1, 1, 1, 1, 0, 0, 0)) + bytes(40))
     with pytest.raises(NotImplementedError):
         nio.read_image(four_d)
+
+
+def test_vector_image_round_trip(tmp_path):
+    """Displacement fields (sitkVectorFloat64 / Float32) as itk::NiftiImageIO lays them out: dim = (5, x, y, z, 1, 3),
+    NIFTI_INTENT_VECTOR, components planar in the file and interleaved in memory, values stored as they are."""
+    import struct
+
+    rng = np.random.default_rng(3)
+    r = _rot(rng.standard_normal(3), 0.4)
+    for dtype, name in ((np.float64, "dvf.nii.gz"), (np.float32, "dvf32.nii")):
+        field = Image(rng.standard_normal((5, 6, 7, 3)).astype(dtype), (0.9, 1.1, 2.5), (-12.0, 30.5, 4.0), tuple(r.reshape(9)), is_vector=True)
+        path = tmp_path / name
+        sk.WriteImage(field, path)
+        back = sk.ReadImage(path)
+        assert back.is_vector and back.array.dtype == dtype and back.array.shape == (5, 6, 7, 3)
+        assert np.array_equal(back.array, field.array)
+        assert back.GetPixelID() == (sk.sitkVectorFloat64 if dtype == np.float64 else sk.sitkVectorFloat32)
+        assert np.allclose(back.GetSpacing(), field.GetSpacing(), rtol=1e-6) and np.allclose(back.GetOrigin(), field.GetOrigin(), rtol=1e-6)
+        assert np.allclose(back.GetDirection(), field.GetDirection(), atol=2e-6)  # header geometry is float32
+    raw = (tmp_path / "dvf32.nii").read_bytes()
+    assert struct.unpack("<8h", raw[40:56])[:6] == (5, 7, 6, 5, 1, 3) and struct.unpack("<h", raw[68:70])[0] == 1007
+    planes = np.frombuffer(raw, np.float32, offset=352).reshape(3, 5, 6, 7)
+    assert np.array_equal(planes[1], field.array[..., 1])  # component 1 is one contiguous block of the file
+    tfm = sk.DisplacementFieldTransform(sk.ReadImage(tmp_path / "dvf.nii.gz"))  # what a caller does with a stored field
+    assert tfm.GetDisplacementField().array.shape == (5, 6, 7, 3)
