@@ -14,8 +14,8 @@ followed by the replicated finalisation (normalise -> DiscreteGaussian -> rescal
 STAPLE EM) and ``process_probability_image``.  A single Demons registration is not sharded.  With
 ``settings["linear_registration_settings"]`` the atlases may live in their own space and are first aligned with
 ``linear_registration`` (run.py:261-300); without it they are expected on the target grid already (the state
-after ``apply_transform`` with the rigid transform).  The auto-crop of run.py:200-259 is not performed: it only
-shrinks the working domain of the reference's CPU pipeline.
+after ``apply_transform`` with the rigid transform).  With ``auto_crop_target_image_settings`` the target is first cropped
+to the region the atlases cover (run.py:200-259) and the results are pasted back into the full grid (run.py:387-404).
 
 ``shard_atlases`` / ``exchange_sum`` are plain host logic and are exercised on CPU with the gloo backend.
 """
