@@ -99,6 +99,9 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+CPU_SAMPLE_ITERS = 10  # full-resolution iterations per bounded CPU sample: 10-25 s on 16-64 host cores
+
+
 def oracle_sample(size, fixed, moving, iters):
     """Bounded CPU sample: `iters` full-resolution Demons iterations of the oracle on all host cores."""
     from oracle import itk_oracle as orc
@@ -115,7 +118,7 @@ def oracle_sample(size, fixed, moving, iters):
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  SimpleITK/ITK cannot be installed
     offline, so this arm times the oracle port (the C restatement of the ITK filters, OpenMP on all host
-    cores); each step is a bounded sample: 2 full-resolution Demons iterations."""
+    cores); each step is a bounded sample: CPU_SAMPLE_ITERS full-resolution Demons iterations."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -125,13 +128,15 @@ def run_reference(args):
     fixed, moving = synth_pair(size, seed=0, moving_seed=100)
     vals = []
     cores = None
+    # bounded: the whole --steps K --warmup W run stays within a few minutes whatever K + W is
+    iters = max(2, min(CPU_SAMPLE_ITERS, 60 // max(1, args.warmup + args.steps)))
     for s in range(args.warmup + args.steps):
-        v, dt, it, cores = oracle_sample(size, fixed, moving, 2)
+        v, dt, it, cores = oracle_sample(size, fixed, moving, iters)
         if s >= args.warmup:
             vals.append((v, dt))
     value = sum(v for v, _ in vals) / len(vals)
     ms = 1e3 * sum(dt for _, dt in vals) / len(vals)
-    sample = f"2 full-resolution Demons iterations ({size[0]}x{size[1]}x{size[2]}) of the oracle port per step"
+    sample = f"{iters} full-resolution Demons iterations ({size[0]}x{size[1]}x{size[2]}) of the oracle port per step"
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(size, args.gpus),
@@ -292,9 +297,9 @@ def run_b200(args):
         # bounded CPU sample on the host cores of this box (rank 0, N = 1 only)
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            v, dt, it, cores = oracle_sample(size, fixed, moving, 2)
+            v, dt, it, cores = oracle_sample(size, fixed, moving, CPU_SAMPLE_ITERS)
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                   "sample": f"2 full-resolution Demons iterations ({size[0]}x{size[1]}x{size[2]}) of the oracle port, {dt:.1f} s; "
+                   "sample": f"{it} full-resolution Demons iterations ({size[0]}x{size[1]}x{size[2]}) of the oracle port, {dt:.1f} s; "
                              "CPU restatement of the ITK filters, not SimpleITK"}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(size, world),
