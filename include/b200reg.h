@@ -253,6 +253,16 @@ int b200reg_linreg_meansq(b200reg_ctx* ctx, const float* d_fixed, const b200reg_
                           const double initial_matrix[9], const double center[3], const uint8_t* d_fixed_mask,
                           const uint8_t* d_moving_mask, int stride, double h_out[14]);
 
+/* Metric "correlation" (linear.py:141-146, SetMetricAsCorrelation -> itk::CorrelationImageToImageMetricv4), same sampling and
+ * arguments as b200reg_linreg_meansq.  h_out (after a stream synchronisation): [0] number of valid samples N, [1] sum F, [2] sum M,
+ * [3] sum F^2, [4] sum M^2, [5] sum F M, then for each weight w in (1, F, M) twelve numbers: s_w = sum w h (3) and
+ * S_w = sum w h (x - center)^T (9, row-major), h = initial_matrix^T grad M.  value = -sFM^2 / (sFF sMM) with mean-centred sums;
+ * its derivative is alpha (G_F - mF G_1) + beta (G_M - mM G_1), alpha = -2 sFM / (sFF sMM), beta = 2 sFM^2 / (sFF sMM^2). */
+int b200reg_linreg_correlation(b200reg_ctx* ctx, const float* d_fixed, const b200reg_geom* fixed_geom, const float* d_moving,
+                               const b200reg_geom* moving_geom, const double total_matrix[9], const double total_offset[3],
+                               const double initial_matrix[9], const double center[3], const uint8_t* d_fixed_mask,
+                               const uint8_t* d_moving_mask, int stride, double h_out[42]);
+
 /* ---- label utilities around the fusion step (multiatlas/run.py:200-259, 387-437) -------------------------------------- */
 /* sitk.LabelStatisticsImageFilter.GetBoundingBox (utils/crop.py:44-46) of the non-zero voxels of a UInt8 mask:
  * h_bbox = (min x, min y, min z, max x, max y, max z); an empty mask gives max < min.  Synchronises. */

@@ -371,6 +371,17 @@ def process_probability_image(probability_image, threshold=0.5):
 
 
 def linreg_meansq(fixed, moving, total_matrix, total_offset, initial_matrix, center, fixed_mask=None, moving_mask=None, stride=1):
+    return _linreg_sums(fixed, moving, total_matrix, total_offset, initial_matrix, center, fixed_mask, moving_mask, stride, "mean_squares")
+
+
+def linreg_correlation(fixed, moving, total_matrix, total_offset, initial_matrix, center, fixed_mask=None, moving_mask=None, stride=1):
+    """Sums behind itk::CorrelationImageToImageMetricv4 (linear.py:141-146 ``SetMetricAsCorrelation``) over the same samples as
+    ``linreg_meansq``: [N, sum F, sum M, sum F^2, sum M^2, sum F M] followed, for each weight w in (1, F, M), by
+    s_w = sum w h (3) and S_w = sum w h (x - center)^T (9, row-major), h = initial_matrix^T grad M."""
+    return _linreg_sums(fixed, moving, total_matrix, total_offset, initial_matrix, center, fixed_mask, moving_mask, stride, "correlation")
+
+
+def _linreg_sums(fixed, moving, total_matrix, total_offset, initial_matrix, center, fixed_mask, moving_mask, stride, kind):
     """Mean-squares metric sums of linear_registration (linear.py:141-163: SetMetricAsMeanSquares, linear interpolator,
     REGULAR sampling, optional masks), restated in numpy for every ``stride``-th fixed voxel in raster order:
     [sum (M - F)^2, count, s (3), S (9 row-major)] with w = 2 (M - F) initial_matrix^T grad M, s = sum w,
@@ -417,6 +428,15 @@ def linreg_meansq(fixed, moving, total_matrix, total_offset, initial_matrix, cen
     gi = np.stack([gx0 + (gx1 - gx0) * d2, (vx10 - vx00) + ((vx11 - vx01) - (vx10 - vx00)) * d2, vxx1 - vxx0], axis=1)
     gy = gi @ p2i                                 # d/dy_j = sum_i g_i P2I[i][j]
     h = gy @ np.asarray(initial_matrix, np.float64).reshape(3, 3)   # A_i^T gy, row-vector form
+    if kind == "correlation":
+        xc = x - np.asarray(center, np.float64)
+        out = np.zeros(42)
+        out[0:6] = [float(fv.size), fv.sum(), mval.sum(), (fv * fv).sum(), (mval * mval).sum(), (fv * mval).sum()]
+        for k, wt in enumerate((np.ones_like(fv), fv, mval)):
+            wh = wt[:, None] * h
+            out[6 + 12 * k: 9 + 12 * k] = wh.sum(axis=0)
+            out[9 + 12 * k: 18 + 12 * k] = (wh[:, :, None] * xc[:, None, :]).sum(axis=0).reshape(9)
+        return out
     dd = mval - fv
     w = 2.0 * dd[:, None] * h
     out = np.zeros(14)

@@ -10,6 +10,7 @@
 #include "postproc.cuh"
 #include "distmap.cuh"
 #include "patchcorr_kernels.cuh"
+#include "linreg_corr_kernels.cuh"
 #include "gauss.cuh"
 #include "resample.cuh"
 
@@ -978,5 +979,59 @@ API int b200reg_scale_shift(b200reg_ctx* ctx, const void* d_in, int dtype, size_
         scale_shift_kernel<double><<<nb, 256, 0, ctx->stream>>>((const double*)d_in, n, take_abs, mul, add, (double*)d_out);
     ctx->launches++;
     B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+
+// ---- linear_registration, metric "correlation" (linear.py:141-146): the sums behind CorrelationImageToImageMetricv4 -------------
+namespace {
+CorrGeom make_corr_geom(const b200reg_geom& g)
+{
+    const GeomD d = make_geomd(g);
+    CorrGeom c;
+    c.nx = d.nx;
+    c.ny = d.ny;
+    c.nz = d.nz;
+    for (int r = 0; r < 3; ++r) c.origin[r] = d.origin[r];
+    for (int r = 0; r < 9; ++r) {
+        c.i2p[r] = d.i2p[r];
+        c.p2i[r] = d.p2i[r];
+    }
+    return c;
+}
+}  // namespace
+API int b200reg_linreg_correlation(b200reg_ctx* ctx, const float* d_fixed, const b200reg_geom* fixed_geom, const float* d_moving,
+                                   const b200reg_geom* moving_geom, const double total_matrix[9], const double total_offset[3],
+                                   const double initial_matrix[9], const double center[3], const uint8_t* d_fixed_mask,
+                                   const uint8_t* d_moving_mask, int stride, double h_out[42])
+{
+    ENTER(ctx);
+    REQUIRE(d_fixed && d_moving && valid_geom(fixed_geom) && valid_geom(moving_geom) && total_matrix && total_offset && initial_matrix && center && h_out,
+            "invalid argument");
+    REQUIRE(stride >= 1, "sampling stride must be >= 1");
+    CorrPose ps;
+    for (int r = 0; r < 3; ++r) {
+        ps.b[r] = total_offset[r];
+        ps.c[r] = center[r];
+        for (int c = 0; c < 3; ++c) {
+            ps.A[r * 3 + c] = total_matrix[r * 3 + c];
+            ps.Bt[r * 3 + c] = initial_matrix[c * 3 + r];
+        }
+    }
+    const size_t n = nvox(*fixed_geom);
+    const size_t nsamples = (n + (size_t)stride - 1) / (size_t)stride;
+    int nb = (int)((nsamples + 127) / 128);
+    if (nb > ctx->sm_count * 8) nb = ctx->sm_count * 8;
+    if (nb < 1) nb = 1;
+    TempBuf part, out;
+    B200_TRY(part.alloc(ctx, sizeof(double) * LINREG_CORR_NV * (size_t)nb));
+    B200_TRY(out.alloc(ctx, sizeof(double) * LINREG_CORR_NV));
+    linreg_corr_kernel<<<nb, 128, 0, ctx->stream>>>(d_fixed, d_moving, d_fixed_mask, d_moving_mask, make_corr_geom(*fixed_geom), make_corr_geom(*moving_geom), ps,
+                                                    stride, nsamples, part.as<double>());
+    linreg_corr_final_kernel<<<1, 64, 0, ctx->stream>>>(part.as<double>(), nb, out.as<double>());
+    ctx->launches += 2;
+    B200_CHECK_LAUNCH();
+    B200_CUDA(cudaMemcpyAsync(ctx->h_scratch, out.p, sizeof(double) * LINREG_CORR_NV, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int v = 0; v < LINREG_CORR_NV; ++v) h_out[v] = ctx->h_scratch[v];
     return B200REG_OK;
 }

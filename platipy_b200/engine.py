@@ -440,6 +440,18 @@ class Engine:
             moving_mask.ptr if moving_mask is not None else None, int(stride), out))
         return np.array(out[:], dtype=np.float64)
 
+    def linreg_correlation(self, fixed, moving, total_matrix, total_offset, initial_matrix, center, fixed_mask=None, moving_mask=None, stride=1):
+        """The 42 sums behind the correlation metric of linear_registration (see include/b200reg.h).  Synchronises."""
+        out = (C.c_double * 42)()
+        gf, gm = fixed.geom, moving.geom
+        d9, d3 = C.c_double * 9, C.c_double * 3
+        _abi.check(self.lib.b200reg_linreg_correlation(
+            self.ctx, fixed.ptr, C.byref(gf), moving.ptr, C.byref(gm), d9(*np.asarray(total_matrix, float).reshape(9)),
+            d3(*np.asarray(total_offset, float).reshape(3)), d9(*np.asarray(initial_matrix, float).reshape(9)),
+            d3(*np.asarray(center, float).reshape(3)), fixed_mask.ptr if fixed_mask is not None else None,
+            moving_mask.ptr if moving_mask is not None else None, int(stride), out))
+        return np.array(out[:], dtype=np.float64)
+
     def _size3(self, dimg):
         x, y, z = dimg.GetSize()
         return (C.c_int32 * 3)(x, y, z)

@@ -10,7 +10,9 @@ Gaussian, Demons -- and therefore stay device resident end to end):
     generate_field_radial_bend           platipy/imaging/generation/dvf.py:327-415
     convert_mask_to_distance_map         platipy/imaging/registration/utils.py:270-299
     convert_mask_to_reg_structure        platipy/imaging/registration/utils.py:302-344
-    ShiftAugment / ExpandAugment / ContractAugment / apply_augmentation   platipy/imaging/generation/augment.py:33-205
+    ShiftAugment / ExpandAugment / ContractAugment / apply_augmentation / generate_random_augmentation
+                                         platipy/imaging/generation/augment.py:33-205
+    get_bone_mask                        platipy/imaging/generation/mask.py:21-47
 
 Same arguments, defaults and return values (``(deformed image, DisplacementFieldTransform, displacement field)``).
 Vectors follow the reference's convention: given as (z, y, x) in millimetres.  Inputs may be host images or
@@ -260,6 +262,28 @@ def generate_field_radial_bend(reference_image, body_mask, reference_point, axis
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# generation/mask.py
+# ---------------------------------------------------------------------------------------------------------------------
+def get_bone_mask(image, lower_threshold=350, upper_threshold=3500, max_hole_size=5):
+    """Binary mask of the bones of a CT image (mask.py:21-47): BinaryThreshold, then BinaryMorphologicalClosing with
+    ``max_hole_size`` handed to SimpleITK as the kernel radius (voxels, (x, y, z) for a vector -- the reference passes it
+    through unchanged although its docstring speaks of millimetres and (z, y, x))."""
+    from .label_utils import binary_morphological_closing
+
+    eng = Engine.get()
+    d = eng.to_device(image)
+    bone = eng.binary_threshold(d, float(lower_threshold), float(upper_threshold))
+    if max_hole_size is False:
+        # mask.py:41-45: the closing runs in any case; SimpleITK rejects a bool radius
+        raise TypeError("BinaryMorphologicalClosing: kernelRadius must be an int or a sequence of ints, not bool")
+    if not hasattr(max_hole_size, "__iter__"):
+        max_hole_size = (max_hole_size,) * 3
+    closed = binary_morphological_closing(bone, max_hole_size)
+    eng.wait_caller()
+    return _back(eng, closed, image)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # generation/augment.py
 # ---------------------------------------------------------------------------------------------------------------------
 class DeformableAugment(ABC):
@@ -333,3 +357,31 @@ def apply_augmentation(image, augmentation, masks=[]):
     if masks:
         return image_deformed, masks_deformed, dvf_out
     return image_deformed, dvf_out
+
+
+def generate_random_augmentation(ct_image, masks):
+    """One randomly chosen and randomly parameterised augmentation per mask (augment.py:86-141): shifts of up to 10 mm,
+    contractions and expansions of up to 10 mm with the bone mask held fixed, field smoothing of 3-5 mm."""
+    import random
+
+    random.shuffle(masks)
+    augmentation_types = [
+        {"class": ShiftAugment, "args": {"vector_shift": [(-10, 10), (10, 10), (-10, 10)], "gaussian_smooth": (3, 5)}},
+        {"class": ContractAugment, "args": {"vector_contract": [(0, 10), (0, 10), (0, 10)], "gaussian_smooth": (3, 5), "bone_mask": True}},
+        {"class": ExpandAugment, "args": {"vector_expand": [(0, 10), (0, 10), (0, 10)], "gaussian_smooth": (3, 5), "bone_mask": True}},
+    ]
+    augmentation = []
+    for mask in masks:
+        aug = random.choice(augmentation_types)
+        aug_args = {}
+        for arg, spec in aug["args"].items():
+            value = spec
+            if isinstance(spec, list):  # one draw per dimension
+                value = [random.randint(lo, hi) for lo, hi in spec]
+            elif isinstance(spec, tuple):
+                value = random.randint(spec[0], spec[1])
+            if arg == "bone_mask" and spec:
+                value = get_bone_mask(ct_image)
+            aug_args[arg] = value
+        augmentation.append(aug["class"](mask, **aug_args))
+    return augmentation

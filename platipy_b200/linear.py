@@ -15,7 +15,7 @@ parity -- recovering a known transform / the reference tests' Dice thresholds --
 metric sums with the CPU oracle at identical poses.
 
 Supported: reg_method translation | rigid | similarity | affine | scale (or an ``AffineTransform`` to start from);
-metric mean_squares; optimiser gradient_descent | gradient_descent_line_search.  The other options of the reference raise NotImplementedError
+metric mean_squares | correlation; optimiser gradient_descent | gradient_descent_line_search.  The other options of the reference raise NotImplementedError
 (ValueError for names the reference itself rejects).
 """
 from __future__ import annotations
@@ -463,6 +463,31 @@ def optimise_level(model, evaluate, corners, max_step_mm, number_of_iterations, 
     return history
 
 
+def correlation_in_meansq_form(sums):
+    """itk::CorrelationImageToImageMetricv4 from the kernel's 42 sums (include/b200reg.h), in the 14-number form the optimisers
+    consume: [value * N, N, N * d value / d translation (3), N * S (9)], so that ``acc[0] / acc[1]`` is the metric value
+    -sFM^2 / (sFF sMM) (in [-1, 0], lower is better) and ``model.gradient`` yields its derivative.  A constant fixed or moving
+    sample set has no defined correlation: value 0 and a zero derivative, as ITK returns."""
+    sums = np.asarray(sums, dtype=np.float64)
+    n = sums[0]
+    out = np.zeros(14)
+    out[1] = n
+    if n <= 0:
+        return out
+    mean_f, mean_m = sums[1] / n, sums[2] / n
+    sff = sums[3] - n * mean_f * mean_f
+    smm = sums[4] - n * mean_m * mean_m
+    sfm = sums[5] - n * mean_f * mean_m
+    if not (sff > 0.0 and smm > 0.0):
+        return out
+    g1, gf, gm = sums[6:18], sums[18:30], sums[30:42]
+    alpha = -2.0 * sfm / (sff * smm)
+    beta = 2.0 * sfm * sfm / (sff * smm * smm)
+    out[0] = -(sfm * sfm) / (sff * smm) * n
+    out[2:14] = (alpha * (gf - mean_f * g1) + beta * (gm - mean_m * g1)) * n
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # public entry points
 # ---------------------------------------------------------------------------------------------------------------------
@@ -497,10 +522,11 @@ def linear_registration(fixed_image, moving_image, fixed_structure=None, moving_
     (registered image in the moving image's pixel type, CompositeTransform([initial, optimised]))."""
     from . import registration as reg
 
-    if metric.lower() != "mean_squares":
-        if metric.lower() in ("correlation", "mattes_mi", "joint_hist_mi"):
-            raise NotImplementedError(f"metric {metric!r} is not implemented on the B200 path (mean_squares is)")
+    if metric.lower() not in ("mean_squares", "correlation"):
+        if metric.lower() in ("mattes_mi", "joint_hist_mi"):
+            raise NotImplementedError(f"metric {metric!r} is not implemented on the B200 path (mean_squares and correlation are)")
         raise ValueError(f"unknown metric {metric!r}")
+    use_correlation = metric.lower() == "correlation"
     if optimiser.lower() not in ("gradient_descent", "gradient_descent_line_search"):
         if optimiser.lower() in ("lbfgsb", "exhaustive"):
             raise NotImplementedError(f"optimiser {optimiser!r} is not implemented on the B200 path (gradient_descent[_line_search] are)")
@@ -541,6 +567,9 @@ def linear_registration(fixed_image, moving_image, fixed_structure=None, moving_
 
         def evaluate(p, f_l=f_l, m_l=m_l, fm_l=fm_l, mm_l=mm_l):
             a_o, b_o = model.matrix(p), model.offset(p)
+            if use_correlation:
+                return correlation_in_meansq_form(
+                    eng.linreg_correlation(f_l, m_l, a_init @ a_o, a_init @ b_o + b_init, a_init, model.center, fm_l, mm_l, stride))
             return eng.linreg_meansq(f_l, m_l, a_init @ a_o, a_init @ b_o + b_init, a_init, model.center, fm_l, mm_l, stride)
 
         log = None

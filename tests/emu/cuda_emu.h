@@ -18,6 +18,8 @@ using std::min;
 #define __host__
 #define __forceinline__ inline
 #define __launch_bounds__(...)
+#define __grid_constant__
+#define B200_HOST_EMU 1
 
 struct emu_dim3 {
     unsigned x = 1, y = 1, z = 1;

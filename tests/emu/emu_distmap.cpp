@@ -6,6 +6,7 @@
 
 #include "../../platipy_b200/csrc/distmap_kernels.cuh"
 #include "../../platipy_b200/csrc/patchcorr_kernels.cuh"
+#include "../../platipy_b200/csrc/linreg_corr_kernels.cuh"
 
 using namespace b200;
 
@@ -70,4 +71,21 @@ EMU_API void emu_scale_shift_f64(const double* in, size_t n, int take_abs, doubl
 EMU_API void emu_scale_shift_f32(const float* in, size_t n, int take_abs, float mul, float add, float* out, unsigned grid, unsigned block)
 {
     emu_launch(scale_shift_kernel<float>, grid, block, in, n, take_abs, mul, add, out);
+}
+// geometry: size (3 ints), origin (3), i2p (9), p2i (9) as the host wrapper fills them; pose: A (9), b (3), Bt (9), c (3).
+// partials: [grid * block][42] per-thread sums (the CUDA build reduces them per block instead).
+EMU_API void emu_linreg_corr(const float* F, const float* M, const uint8_t* fmask, const uint8_t* mmask, const int* fsize, const double* fgeo,
+                             const int* msize, const double* mgeo, const double* pose, int stride, double* partials, unsigned grid, unsigned block)
+{
+    CorrGeom gf, gm;
+    CorrPose ps;
+    gf.nx = fsize[0]; gf.ny = fsize[1]; gf.nz = fsize[2];
+    gm.nx = msize[0]; gm.ny = msize[1]; gm.nz = msize[2];
+    for (int r = 0; r < 3; ++r) { gf.origin[r] = fgeo[r]; gm.origin[r] = mgeo[r]; }
+    for (int r = 0; r < 9; ++r) { gf.i2p[r] = fgeo[3 + r]; gf.p2i[r] = fgeo[12 + r]; gm.i2p[r] = mgeo[3 + r]; gm.p2i[r] = mgeo[12 + r]; }
+    for (int r = 0; r < 9; ++r) { ps.A[r] = pose[r]; ps.Bt[r] = pose[12 + r]; }
+    for (int r = 0; r < 3; ++r) { ps.b[r] = pose[9 + r]; ps.c[r] = pose[21 + r]; }
+    const size_t n = (size_t)gf.nx * gf.ny * gf.nz;
+    const size_t nsamples = (n + (size_t)stride - 1) / (size_t)stride;
+    emu_launch(linreg_corr_kernel, grid, block, F, M, fmask, mmask, gf, gm, ps, stride, nsamples, partials);
 }

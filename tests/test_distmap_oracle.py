@@ -10,7 +10,6 @@
 """
 import ctypes as C
 import os
-import subprocess
 
 import numpy as np
 import pytest
@@ -31,19 +30,6 @@ def _blobs(shape, seed, level=0.02, sigma=2.5):
 
 def _P(a):
     return a.ctypes.data_as(C.c_void_p)
-
-
-@pytest.fixture(scope="module")
-def emu():
-    """The kernels of distmap_kernels.cuh compiled for the host (g++, no FMA contraction) behind cuda_emu.h."""
-    build = os.path.join(HERE, "emu", "_build")
-    os.makedirs(build, exist_ok=True)
-    so = os.path.join(build, "libemu_distmap.so")
-    srcs = [os.path.join(HERE, "emu", "emu_distmap.cpp"), os.path.join(HERE, "emu", "cuda_emu.h"),
-            os.path.join(ROOT, "platipy_b200", "csrc", "distmap_kernels.cuh")]
-    if not os.path.exists(so) or os.path.getmtime(so) < max(os.path.getmtime(s) for s in srcs):
-        subprocess.check_call(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-fPIC", "-shared", "-o", so, srcs[0]])
-    return C.CDLL(so)
 
 
 # ---- the oracle against scipy -----------------------------------------------------------------------------------------------

@@ -247,3 +247,71 @@ def test_patch_correlation_weight_map(engine):
                                    dict(fusion.DEFAULT_VOTE_PARAMS, patch_window_mm=12, resampled_voxel_size_mm=3))
     vp["correlation_function"] = lambda x: x + 1
     assert np.array_equal(engine.to_host(dw).array, fusion.compute_weight_map(t, m, "patch_correlation", vp).array)
+
+
+def test_linear_registration_correlation_metric(engine):
+    """metric="correlation" (linear.py:141-146): the 42 sums of the kernel against the numpy restatement at identical poses, and a
+    registration between images with different intensity scales (functional parity, like the mean-squares tests)."""
+    from oracle import platipy_ref as ref
+    from platipy_b200 import linear
+    from platipy_b200 import sitk_compat as sk
+
+    def blob(size, center, spacing=(1.0, 1.0, 1.0), sig=(7.0, 5.0, 4.0), origin=(0.0, 0.0, 0.0), direction=(1, 0, 0, 0, 1, 0, 0, 0, 1)):
+        nx, ny, nz = size
+        z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+        p = [x * spacing[0], y * spacing[1], z * spacing[2]]
+        v = sum(((pi - ci) / si) ** 2 for pi, ci, si in zip(p, center, sig))
+        return Image((1000.0 * np.exp(-0.5 * v)).astype(np.float32), spacing, origin, direction)
+
+    rng = np.random.default_rng(9)
+    ang = 0.15
+    rot = (np.cos(ang), -np.sin(ang), 0, np.sin(ang), np.cos(ang), 0, 0, 0, 1.0)
+    f = blob((24, 20, 16), (12.0, 10.0, 8.0), (1.0, 1.2, 1.5))
+    mv = blob((30, 26, 20), (15.0, 13.5, 12.0), (1.1, 1.0, 1.4), origin=(-3.0, 2.0, -1.0), direction=rot)
+    fmask = Image((rng.random(f.array.shape) > 0.3).astype(np.uint8), f.GetSpacing())
+    mmask = Image((rng.random(mv.array.shape) > 0.2).astype(np.uint8), mv.GetSpacing(), mv.GetOrigin(), mv.GetDirection())
+    init = linear.centered_transform_initializer(f, mv)
+    m = linear.make_model("affine")
+    p = m.identity() + 0.02 * rng.standard_normal(m.n)
+    A, b = init.matrix @ m.matrix(p), init.matrix @ m.offset(p) + init.offset
+    df, dm, dfm, dmm = (engine.to_device(i) for i in (f, mv, fmask, mmask))
+    for fm, mm, dfm_, dmm_, stride in ((None, None, None, None, 1), (fmask, None, dfm, None, 3), (fmask, mmask, dfm, dmm, 2)):
+        got = engine.linreg_correlation(df, dm, A, b, init.matrix, m.center, dfm_, dmm_, stride)
+        exp = ref.linreg_correlation(f, mv, A, b, init.matrix, m.center, fm, mm, stride)
+        assert got.shape == (42,) and got[0] == exp[0]
+        assert np.allclose(got, exp, rtol=1e-9, atol=1e-6 * np.abs(exp).max()), stride
+        again = engine.linreg_correlation(df, dm, A, b, init.matrix, m.center, dfm_, dmm_, stride)
+        assert np.array_equal(got, again)  # fixed-order sums: deterministic
+    # moving = 2 * fixed + 100, shifted by (+2, -1.5, +1) mm
+    fixed = blob((48, 40, 32), (24.0, 20.0, 16.0))
+    shifted = blob((48, 40, 32), (26.0, 18.5, 17.0))
+    moving = Image(shifted.array * 2.0 + 100.0, shifted.GetSpacing())
+    for optimiser in ("gradient_descent", "gradient_descent_line_search"):
+        registered, tfm = linear.linear_registration(fixed, moving, reg_method="translation", metric="correlation", optimiser=optimiser,
+                                                     shrink_factors=[2, 1], smooth_sigmas=[1, 0], sampling_rate=0.5, number_of_iterations=60,
+                                                     default_value=100)
+        pt = np.array(tfm.flatten()[0].TransformPoint((24.0, 20.0, 16.0)))
+        for t in tfm.flatten()[1:]:
+            pt = np.array(t.TransformPoint(pt))
+        assert np.allclose(pt, (26.0, 18.5, 17.0), atol=0.3), (optimiser, pt)
+        r = np.corrcoef(registered.array.ravel(), fixed.array.ravel())[0, 1]
+        assert r > 0.995 and min(linear.LAST_HISTORY[-1]) < -0.98
+    with pytest.raises(NotImplementedError):
+        linear.linear_registration(fixed, moving, metric="mattes_mi")
+
+
+def test_get_bone_mask(engine):
+    """generation/mask.py:21-47: BinaryThreshold then BinaryMorphologicalClosing with max_hole_size as the kernel radius."""
+    from oracle import platipy_ref as ref
+
+    rng = np.random.default_rng(2)
+    ct = Image((ndi.gaussian_filter(rng.standard_normal((20, 40, 44)), 2.0) * 4000).astype(np.float32), (1.0, 1.0, 2.5))
+    for hole in (2, (1, 2, 1)):
+        got = gen.get_bone_mask(ct, 350, 3500, hole)
+        thr = Image(((ct.array >= 350) & (ct.array <= 3500)).astype(np.uint8), ct.GetSpacing())
+        r = [hole] * 3 if np.isscalar(hole) else list(hole)
+        offs = ball_offsets(r)
+        st = np.zeros((2 * r[2] + 1, 2 * r[1] + 1, 2 * r[0] + 1), bool)
+        st[offs[:, 2] + r[2], offs[:, 1] + r[1], offs[:, 0] + r[0]] = True
+        assert got.array.dtype == np.uint8 and np.array_equal(got.array, ref.binary_morphological_closing(thr, r, st).array)
+        assert got.array.sum() >= thr.array.sum() > 0

@@ -135,3 +135,96 @@ def test_golden_section_and_line_search_optimiser():
     hist = linear.optimise_level_line_search(m, evaluate, linear.image_corners(f), 1.0, 15)
     assert hist[-1] < 0.01 * hist[0]
     assert np.allclose(m.p, [2.0, -1.5, 1.0], atol=0.1)
+
+
+# ---- metric "correlation" (linear.py:141-146) --------------------------------------------------------------------------------
+def _corr_value(f, mv, init, m, q, **kw):
+    sums = ref.linreg_correlation(f, mv, init.matrix @ m.matrix(q), init.matrix @ m.offset(q) + init.offset, init.matrix, m.center, **kw)
+    acc = linear.correlation_in_meansq_form(sums)
+    return acc[0] / acc[1], acc
+
+
+def test_correlation_value_and_gradient():
+    f = _blob_image((24, 20, 16), (12.0, 10.0, 8.0))
+    big = _blob_image((36, 32, 28), (19.5, 15.0, 14.5))
+    mv = Image(big.array * 0.5 + 40.0, big.GetSpacing(), (-6.0, -6.0, -6.0))  # another intensity scale: correlation does not care
+    init = linear.centered_transform_initializer(f, mv)
+    m = linear.make_model("translation")
+    v_aligned, _ = _corr_value(f, mv, init, m, np.array([0.0, -0.5, 0.0]))
+    assert -1.0 <= v_aligned < -0.9
+    # the value is Pearson's r squared (negated) of the sampled pairs
+    sums = ref.linreg_correlation(f, mv, init.matrix, init.offset, init.matrix, m.center)
+    n, sf, sm, sff, smm, sfm = sums[:6]
+    r = (sfm - sf * sm / n) / np.sqrt((sff - sf * sf / n) * (smm - sm * sm / n))
+    acc = linear.correlation_in_meansq_form(sums)
+    assert acc[1] == n and np.isclose(acc[0] / n, -r * r, rtol=1e-12)
+    for name in ("translation", "rigid", "similarity", "affine"):
+        m = linear.make_model(name)
+        rng = np.random.default_rng(3)
+        p = m.identity() + 0.01 * rng.standard_normal(m.n)
+        v0, acc = _corr_value(f, mv, init, m, p)
+        g = m.gradient(acc, p)
+        for k in range(m.n):
+            d = np.zeros(m.n)
+            d[k] = 1e-5
+            fd = (_corr_value(f, mv, init, m, p + d)[0] - _corr_value(f, mv, init, m, p - d)[0]) / 2e-5
+            assert np.isclose(g[k], fd, rtol=2e-3, atol=1e-3 * abs(g).max()), (name, k, g[k], fd)
+    # degenerate sample sets: no valid sample, constant image
+    assert not linear.correlation_in_meansq_form(np.zeros(42)).any()
+    flat = Image(np.full_like(f.array, 3.0), f.GetSpacing())
+    acc = linear.correlation_in_meansq_form(ref.linreg_correlation(flat, mv, init.matrix, init.offset, init.matrix, m.center))
+    assert acc[0] == 0.0 and acc[1] > 0 and not acc[2:].any()
+
+
+def test_optimiser_recovers_a_translation_with_the_correlation_metric():
+    f = _blob_image((24, 20, 16), (12.0, 10.0, 8.0))
+    shifted = _blob_image((24, 20, 16), (14.0, 8.5, 9.0))
+    mv = Image(shifted.array * 2.0 + 100.0, shifted.GetSpacing())  # mean squares cannot align these; correlation can
+    init = linear.centered_transform_initializer(f, mv)
+    for run in (linear.optimise_level, linear.optimise_level_line_search):
+        m = linear.make_model("translation")
+
+        def evaluate(p):
+            return linear.correlation_in_meansq_form(
+                ref.linreg_correlation(f, mv, init.matrix @ m.matrix(p), init.matrix @ m.offset(p) + init.offset, init.matrix, m.center, stride=2))
+
+        hist = run(m, evaluate, linear.image_corners(f), 1.0, 60)
+        assert hist[-1] < -0.98 and hist[-1] < hist[0]
+        assert np.allclose(m.p, [2.0, -1.5, 1.0], atol=0.2), (run.__name__, m.p)
+
+
+def test_emulated_correlation_kernel_matches_the_numpy_sums(emu):
+    """The CUDA kernel's per-sample code, run on the host (tests/emu), against the numpy restatement -- masks, stride, a rotated
+    moving grid, samples falling outside the moving buffer."""
+    import ctypes as C
+
+    rng = np.random.default_rng(9)
+    f = _blob_image((24, 20, 16), (12.0, 10.0, 8.0), spacing=(1.0, 1.2, 1.5))
+    ang = 0.15
+    rot = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1.0]])
+    big = _blob_image((30, 26, 20), (15.0, 13.5, 12.0), spacing=(1.1, 1.0, 1.4))
+    mv = Image((big.array + rng.normal(0, 5, big.array.shape)).astype(np.float32), big.GetSpacing(), (-3.0, 2.0, -1.0), tuple(rot.reshape(9)))
+    fmask = Image((rng.random(f.array.shape) > 0.3).astype(np.uint8), f.GetSpacing())
+    mmask = Image((rng.random(mv.array.shape) > 0.2).astype(np.uint8), mv.GetSpacing(), mv.GetOrigin(), mv.GetDirection())
+    init = linear.centered_transform_initializer(f, mv)
+    m = linear.make_model("affine")
+    p = m.identity() + 0.02 * rng.standard_normal(m.n)
+    A, b = init.matrix @ m.matrix(p), init.matrix @ m.offset(p) + init.offset
+
+    def geo(img):
+        d = np.asarray(img.GetDirection(), np.float64).reshape(3, 3)
+        i2p = d * np.asarray(img.GetSpacing())[None, :]
+        return (np.array(img.GetSize(), np.int32), np.concatenate([np.asarray(img.GetOrigin(), np.float64), i2p.reshape(9), np.linalg.inv(i2p).reshape(9)]))
+
+    (fs, fg), (ms, mg) = geo(f), geo(mv)
+    pose = np.concatenate([A.reshape(9), b, init.matrix.T.reshape(9), m.center]).astype(np.float64)
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    for fm, mm, stride in ((None, None, 1), (fmask, None, 3), (fmask, mmask, 2)):
+        grid, block = 3, 64
+        partials = np.zeros((grid * block, 42))
+        emu.emu_linreg_corr(P(f.array), P(mv.array), P(fm.array) if fm else None, P(mm.array) if mm else None, P(fs), P(fg), P(ms), P(mg), P(pose),
+                            stride, P(partials), C.c_uint(grid), C.c_uint(block))
+        got = partials.sum(axis=0)
+        exp = ref.linreg_correlation(f, mv, A, b, init.matrix, m.center, fm, mm, stride)
+        assert got[0] == exp[0] and 0 < got[0] < f.array.size / stride + 1
+        assert np.allclose(got, exp, rtol=1e-9, atol=1e-6 * np.abs(exp).max()), (stride, np.abs(got - exp).max())
