@@ -263,6 +263,10 @@ int b200reg_linreg_correlation(b200reg_ctx* ctx, const float* d_fixed, const b20
                                const double initial_matrix[9], const double center[3], const uint8_t* d_fixed_mask,
                                const uint8_t* d_moving_mask, int stride, double h_out[42]);
 
+/* itk::ImageMomentsCalculator as sitk.CenteredTransformInitializer(fixed, moving, transform, MOMENTS) uses it (linear.py:40-43):
+ * h_out = [sum v, sum v x, sum v y, sum v z] over all voxels, (x, y, z) the voxel's physical position.  Synchronises. */
+int b200reg_image_moments(b200reg_ctx* ctx, const float* d_image, const b200reg_geom* geom, double h_out[4]);
+
 /* ---- label utilities around the fusion step (multiatlas/run.py:200-259, 387-437) -------------------------------------- */
 /* sitk.LabelStatisticsImageFilter.GetBoundingBox (utils/crop.py:44-46) of the non-zero voxels of a UInt8 mask:
  * h_bbox = (min x, min y, min z, max x, max y, max z); an empty mask gives max < min.  Synchronises. */

@@ -370,6 +370,18 @@ def process_probability_image(probability_image, threshold=0.5):
     return _like(largest, probability_image)
 
 
+def image_moments(image):
+    """itk::ImageMomentsCalculator (behind sitk.CenteredTransformInitializer MOMENTS, linear.py:40-43):
+    [sum v, sum v x, sum v y, sum v z] with (x, y, z) the physical position of every voxel."""
+    v = image.array.astype(np.float64)
+    nz, ny, nx = v.shape
+    k, j, i = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+    d = np.asarray(image.GetDirection(), np.float64).reshape(3, 3)
+    idx = np.stack([i, j, k], axis=-1).astype(np.float64)
+    pts = (idx * np.asarray(image.GetSpacing())) @ d.T + np.asarray(image.GetOrigin())
+    return np.concatenate([[v.sum()], (pts * v[..., None]).sum(axis=(0, 1, 2))])
+
+
 def linreg_meansq(fixed, moving, total_matrix, total_offset, initial_matrix, center, fixed_mask=None, moving_mask=None, stride=1):
     return _linreg_sums(fixed, moving, total_matrix, total_offset, initial_matrix, center, fixed_mask, moving_mask, stride, "mean_squares")
 

@@ -11,6 +11,7 @@
 #include "distmap.cuh"
 #include "patchcorr_kernels.cuh"
 #include "linreg_corr_kernels.cuh"
+#include "moments_kernels.cuh"
 #include "gauss.cuh"
 #include "resample.cuh"
 
@@ -1033,5 +1034,32 @@ API int b200reg_linreg_correlation(b200reg_ctx* ctx, const float* d_fixed, const
     B200_CUDA(cudaMemcpyAsync(ctx->h_scratch, out.p, sizeof(double) * LINREG_CORR_NV, cudaMemcpyDeviceToHost, ctx->stream));
     B200_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int v = 0; v < LINREG_CORR_NV; ++v) h_out[v] = ctx->h_scratch[v];
+    return B200REG_OK;
+}
+
+// ---- alignment_registration(moments=True) (linear.py:23-47): itk::ImageMomentsCalculator behind CenteredTransformInitializer ----
+API int b200reg_image_moments(b200reg_ctx* ctx, const float* d_image, const b200reg_geom* geom, double h_out[4])
+{
+    ENTER(ctx);
+    REQUIRE(d_image && valid_geom(geom) && h_out, "invalid argument");
+    const GeomD d = make_geomd(*geom);
+    MomentsGeom g;
+    g.nx = d.nx;
+    g.ny = d.ny;
+    g.nz = d.nz;
+    for (int r = 0; r < 3; ++r) g.origin[r] = d.origin[r];
+    for (int r = 0; r < 9; ++r) g.i2p[r] = d.i2p[r];
+    const size_t n = nvox(*geom);
+    const int nb = elementwise_blocks(ctx, n, 256);
+    TempBuf part, out;
+    B200_TRY(part.alloc(ctx, sizeof(double) * MOMENTS_NV * (size_t)nb));
+    B200_TRY(out.alloc(ctx, sizeof(double) * MOMENTS_NV));
+    image_moments_kernel<<<nb, 256, 0, ctx->stream>>>(d_image, g, part.as<double>());
+    image_moments_final_kernel<<<1, 32, 0, ctx->stream>>>(part.as<double>(), nb, out.as<double>());
+    ctx->launches += 2;
+    B200_CHECK_LAUNCH();
+    B200_CUDA(cudaMemcpyAsync(ctx->h_scratch, out.p, sizeof(double) * MOMENTS_NV, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (int v = 0; v < MOMENTS_NV; ++v) h_out[v] = ctx->h_scratch[v];
     return B200REG_OK;
 }

@@ -452,6 +452,13 @@ class Engine:
             moving_mask.ptr if moving_mask is not None else None, int(stride), out))
         return np.array(out[:], dtype=np.float64)
 
+    def image_moments(self, dimg):
+        """[sum v, sum v x, sum v y, sum v z] of a Float32 image in physical coordinates (ImageMomentsCalculator).  Synchronises."""
+        out = (C.c_double * 4)()
+        g = dimg.geom
+        _abi.check(self.lib.b200reg_image_moments(self.ctx, dimg.ptr, C.byref(g), out))
+        return np.array(out[:], dtype=np.float64)
+
     def _size3(self, dimg):
         x, y, z = dimg.GetSize()
         return (C.c_int32 * 3)(x, y, z)

@@ -15,7 +15,7 @@ parity -- recovering a known transform / the reference tests' Dice thresholds --
 metric sums with the CPU oracle at identical poses.
 
 Supported: reg_method translation | rigid | similarity | affine | scale (or an ``AffineTransform`` to start from);
-metric mean_squares | correlation; optimiser gradient_descent | gradient_descent_line_search.  The other options of the reference raise NotImplementedError
+metric mean_squares | correlation; optimiser gradient_descent | gradient_descent_line_search | lbfgsb.  The other options of the reference raise NotImplementedError
 (ValueError for names the reference itself rejects).
 """
 from __future__ import annotations
@@ -295,6 +295,14 @@ def shrink_grid(img, factor):
     return Grid(size, spacing, origin, img.GetDirection())
 
 
+def center_of_gravity(moments):
+    """itk::ImageMomentsCalculator::GetCenterOfGravity from [sum v, sum v x, sum v y, sum v z]."""
+    m = np.asarray(moments, dtype=np.float64)
+    if m[0] == 0.0:
+        raise RuntimeError("ImageMomentsCalculator: total mass of the image was zero; the centre of gravity is undefined")  # ITK's exception
+    return m[1:4] / m[0]
+
+
 def centered_transform_initializer(fixed, moving):
     """sitk.CenteredTransformInitializer(fixed, moving, Euler3DTransform(), False) (linear.py:128-130): GEOMETRY mode --
     centre of rotation = fixed image centre, translation = moving centre - fixed centre."""
@@ -415,6 +423,37 @@ def optimise_level_line_search(model, evaluate, corners, max_step_mm, number_of_
     return history
 
 
+def optimise_level_lbfgsb(model, evaluate, corners, max_step_mm, number_of_iterations, log=None):
+    """LBFGSBOptimizerv4 as the reference configures it (linear.py:208-216: gradientConvergenceTolerance 1e-5,
+    maximumNumberOfCorrections 50, maximumNumberOfFunctionEvaluations 1024, costFunctionConvergenceFactor 1e7, no bounds).  ITK
+    and scipy both drive the L-BFGS-B code of Zhu, Byrd, Lu and Nocedal, so the host side hands the same settings to
+    ``scipy.optimize.fmin_l_bfgs_b``.  The physical-shift scales act the way ITK's vnl cost-function adaptor applies them:
+    the optimiser works on x' = scale * x and sees the gradient divided by the scales.  Parameters are set directly (no
+    compositional versor update), as LBFGSB does in ITK.  ``max_step_mm`` is unused (L-BFGS-B chooses its own steps)."""
+    from scipy.optimize import fmin_l_bfgs_b
+
+    p0 = model.p.copy()
+    scales = estimate_scales(model, p0, corners)
+    history = []
+
+    def fun(xs):
+        p = xs / scales
+        acc = evaluate(p)
+        if acc[1] <= 0:
+            if not history:
+                raise RuntimeError("linear_registration: no valid sample point maps inside the moving image")
+            return 1e300, np.zeros(model.n)  # a trial point with every sample outside the moving image
+        value = acc[0] / acc[1]
+        history.append(value)
+        if log:
+            log(len(history) - 1, value, p)
+        return value, model.gradient(acc, p) / scales
+
+    xs, _, _ = fmin_l_bfgs_b(fun, p0 * scales, m=50, factr=1e7, pgtol=1e-5, maxfun=1024, maxiter=int(number_of_iterations))
+    model.p = xs / scales
+    return history
+
+
 def optimise_level(model, evaluate, corners, max_step_mm, number_of_iterations, log=None):
     """GradientDescentOptimizerv4, learning rate estimated once (at the first iteration of the level) so that the
     first step moves the farthest corner by ``max_step_mm``.  ``evaluate(p) -> 14 accumulators``.  Returns the history
@@ -501,16 +540,19 @@ def _back(eng, dimg, like):
 
 
 def alignment_registration(fixed_image, moving_image, moments=True):
-    """linear.py:23-47.  Only the geometry initialisation (moments=False) is implemented."""
-    if moments:
-        raise NotImplementedError("alignment_registration(moments=True) is not implemented on the B200 path")
+    """A single-step alignment (linear.py:23-47): sitk.CenteredTransformInitializer on a VersorRigid3DTransform, either from the
+    image centres (GEOMETRY, ``moments=False``) or from the intensity-weighted centres of gravity (MOMENTS, the default) --
+    the initialiser sets the centre of rotation and the translation only; the rotation stays the identity."""
     from . import registration as reg
 
     eng = Engine.get()
     f, m = eng.to_device(fixed_image), eng.to_device(moving_image)
-    cf, cm = image_center(f), image_center(m)
-    tfm = sk.AffineTransform(np.eye(3), cm - cf, cf)
     mf = eng.cast(m, np.float32)
+    if moments:
+        cf, cm = center_of_gravity(eng.image_moments(eng.cast(f, np.float32))), center_of_gravity(eng.image_moments(mf))
+    else:
+        cf, cm = image_center(f), image_center(m)
+    tfm = sk.AffineTransform(np.eye(3), cm - cf, cf)
     out = eng.cast(eng.resample(mf, f, tfm, sk.sitkLinear, 0.0), m.np_dtype)
     return reg._back(eng, out, moving_image), tfm
 
@@ -527,11 +569,12 @@ def linear_registration(fixed_image, moving_image, fixed_structure=None, moving_
             raise NotImplementedError(f"metric {metric!r} is not implemented on the B200 path (mean_squares and correlation are)")
         raise ValueError(f"unknown metric {metric!r}")
     use_correlation = metric.lower() == "correlation"
-    if optimiser.lower() not in ("gradient_descent", "gradient_descent_line_search"):
-        if optimiser.lower() in ("lbfgsb", "exhaustive"):
-            raise NotImplementedError(f"optimiser {optimiser!r} is not implemented on the B200 path (gradient_descent[_line_search] are)")
+    if optimiser.lower() not in ("gradient_descent", "gradient_descent_line_search", "lbfgsb"):
+        if optimiser.lower() == "exhaustive":  # "This isn't well implemented ... Use is not currently recommended" (linear.py:217-224)
+            raise NotImplementedError(f"optimiser {optimiser!r} is not implemented on the B200 path (gradient_descent[_line_search] and lbfgsb are)")
         raise ValueError(f"unknown optimiser {optimiser!r}")
-    run_level = optimise_level_line_search if optimiser.lower() == "gradient_descent_line_search" else optimise_level
+    run_level = {"gradient_descent": optimise_level, "gradient_descent_line_search": optimise_level_line_search,
+                 "lbfgsb": optimise_level_lbfgsb}[optimiser.lower()]
     model = make_model(reg_method)
     if len(shrink_factors) != len(smooth_sigmas):
         raise RuntimeError("shrink_factors and smooth_sigmas must have the same length")  # ITK raises through SimpleITK

@@ -7,6 +7,7 @@
 #include "../../platipy_b200/csrc/distmap_kernels.cuh"
 #include "../../platipy_b200/csrc/patchcorr_kernels.cuh"
 #include "../../platipy_b200/csrc/linreg_corr_kernels.cuh"
+#include "../../platipy_b200/csrc/moments_kernels.cuh"
 
 using namespace b200;
 
@@ -88,4 +89,12 @@ EMU_API void emu_linreg_corr(const float* F, const float* M, const uint8_t* fmas
     const size_t n = (size_t)gf.nx * gf.ny * gf.nz;
     const size_t nsamples = (n + (size_t)stride - 1) / (size_t)stride;
     emu_launch(linreg_corr_kernel, grid, block, F, M, fmask, mmask, gf, gm, ps, stride, nsamples, partials);
+}
+EMU_API void emu_image_moments(const float* img, const int* size, const double* geo, double* partials, unsigned grid, unsigned block)
+{
+    MomentsGeom g;
+    g.nx = size[0]; g.ny = size[1]; g.nz = size[2];
+    for (int r = 0; r < 3; ++r) g.origin[r] = geo[r];
+    for (int r = 0; r < 9; ++r) g.i2p[r] = geo[3 + r];
+    emu_launch(image_moments_kernel, grid, block, img, g, partials);
 }

@@ -315,3 +315,36 @@ def test_get_bone_mask(engine):
         st[offs[:, 2] + r[2], offs[:, 1] + r[1], offs[:, 0] + r[0]] = True
         assert got.array.dtype == np.uint8 and np.array_equal(got.array, ref.binary_morphological_closing(thr, r, st).array)
         assert got.array.sum() >= thr.array.sum() > 0
+
+
+def test_alignment_registration_with_moments_and_lbfgsb(engine):
+    """alignment_registration(moments=True) (linear.py:23-47: CenteredTransformInitializer MOMENTS) and optimiser="lbfgsb"."""
+    from oracle import platipy_ref as ref
+    from platipy_b200 import linear
+
+    def blob(size, center, spacing=(1.0, 1.0, 1.0), sig=(7.0, 5.0, 4.0), origin=(0.0, 0.0, 0.0)):
+        nx, ny, nz = size
+        z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+        p = [x * spacing[0], y * spacing[1], z * spacing[2]]
+        v = sum(((pi - ci) / si) ** 2 for pi, ci, si in zip(p, center, sig))
+        return Image((1000.0 * np.exp(-0.5 * v)).astype(np.float32), spacing, origin)
+
+    fixed = blob((48, 40, 32), (24.0, 20.0, 16.0))
+    moving = blob((40, 44, 30), (17.0, 25.0, 13.0), spacing=(1.2, 1.0, 1.1), origin=(5.0, -8.0, 2.0))
+    got = engine.image_moments(engine.to_device(moving))
+    assert np.allclose(got, ref.image_moments(moving), rtol=1e-10)
+    aligned, tfm = linear.alignment_registration(fixed, moving)  # moments=True is the reference's default
+    # fixed blob centre -> moving blob centre (physical): (24, 20, 16) -> origin + (17, 25, 13)
+    assert np.allclose(tfm.TransformPoint((24.0, 20.0, 16.0)), (22.0, 17.0, 15.0), atol=0.25)  # the moving blob is cut by its image border
+    assert aligned.array.dtype == np.float32 and aligned.array.shape == fixed.array.shape
+    assert np.corrcoef(aligned.array.ravel(), fixed.array.ravel())[0, 1] > 0.98
+    with pytest.raises(RuntimeError):
+        linear.alignment_registration(fixed, Image(np.zeros((8, 8, 8), np.float32)))
+    shifted = blob((48, 40, 32), (26.0, 18.5, 17.0))
+    for metric, mv in (("mean_squares", shifted), ("correlation", Image(shifted.array * 2.0 + 100.0, shifted.GetSpacing()))):
+        _, t = linear.linear_registration(fixed, mv, reg_method="translation", metric=metric, optimiser="lbfgsb", shrink_factors=[2, 1],
+                                          smooth_sigmas=[1, 0], sampling_rate=0.5, number_of_iterations=50)
+        pt = np.array((24.0, 20.0, 16.0))
+        for part in t.flatten():
+            pt = np.array(part.TransformPoint(pt))
+        assert np.allclose(pt, (26.0, 18.5, 17.0), atol=0.3), (metric, pt)

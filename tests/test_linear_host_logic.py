@@ -228,3 +228,51 @@ def test_emulated_correlation_kernel_matches_the_numpy_sums(emu):
         exp = ref.linreg_correlation(f, mv, A, b, init.matrix, m.center, fm, mm, stride)
         assert got[0] == exp[0] and 0 < got[0] < f.array.size / stride + 1
         assert np.allclose(got, exp, rtol=1e-9, atol=1e-6 * np.abs(exp).max()), (stride, np.abs(got - exp).max())
+
+
+def test_lbfgsb_optimiser_with_the_oracle_metrics():
+    """optimiser="lbfgsb" (linear.py:208-216): scipy's L-BFGS-B on the scaled parameters, for both metrics and for a
+    transform with a versor part (parameters set directly, not composed)."""
+    f = _blob_image((24, 20, 16), (12.0, 10.0, 8.0))
+    shifted = _blob_image((24, 20, 16), (14.0, 8.5, 9.0))
+    init = linear.centered_transform_initializer(f, shifted)
+    for name, metric, mv in (("translation", "mean_squares", shifted), ("translation", "correlation", Image(shifted.array * 2.0 + 100.0, shifted.GetSpacing())),
+                             ("rigid", "mean_squares", shifted)):
+        m = linear.make_model(name)
+        m.center = linear.image_center(f)
+
+        def evaluate(p):
+            args = (f, mv, init.matrix @ m.matrix(p), init.matrix @ m.offset(p) + init.offset, init.matrix, m.center)
+            if metric == "correlation":
+                return linear.correlation_in_meansq_form(ref.linreg_correlation(*args, stride=2))
+            return ref.linreg_meansq(*args, stride=2)
+
+        hist = linear.optimise_level_lbfgsb(m, evaluate, linear.image_corners(f), 1.0, 50)
+        assert len(hist) <= 1024 and (min(hist) < -0.98 if metric == "correlation" else min(hist) < 0.01 * hist[0])
+        assert np.allclose(m.translation(m.p), [2.0, -1.5, 1.0], atol=0.1), (name, metric, m.p)
+        if name == "rigid":
+            assert np.allclose(m.matrix(m.p), np.eye(3), atol=0.02)
+
+
+def test_emulated_image_moments_and_center_of_gravity(emu):
+    """alignment_registration(moments=True): the moments kernel (host emulation) against the numpy restatement; the centre of
+    gravity of a Gaussian blob is its centre."""
+    import ctypes as C
+
+    ang = 0.2
+    rot = (np.cos(ang), -np.sin(ang), 0, np.sin(ang), np.cos(ang), 0, 0, 0, 1.0)
+    blob = _blob_image((30, 26, 20), (15.0, 11.0, 12.0), spacing=(1.1, 1.0, 1.4))
+    img = Image(blob.array, blob.GetSpacing(), (-3.0, 2.0, -1.0), rot)
+    d = np.asarray(rot).reshape(3, 3)
+    geo = np.concatenate([np.asarray(img.GetOrigin()), (d * np.asarray(img.GetSpacing())[None, :]).reshape(9)])
+    size = np.array(img.GetSize(), np.int32)
+    grid, block = 3, 64
+    partials = np.zeros((grid * block, 4))
+    P = lambda a: a.ctypes.data_as(C.c_void_p)
+    emu.emu_image_moments(P(img.array), P(size), P(geo), P(partials), C.c_uint(grid), C.c_uint(block))
+    got, exp = partials.sum(axis=0), ref.image_moments(img)
+    assert np.allclose(got, exp, rtol=1e-12)
+    cog = linear.center_of_gravity(got)
+    assert np.allclose(cog, np.asarray(img.GetOrigin()) + d @ np.array([15.0, 11.0, 12.0]), atol=0.25)  # the blob is cut asymmetrically by the image border
+    with pytest.raises(RuntimeError):
+        linear.center_of_gravity(np.zeros(4))
