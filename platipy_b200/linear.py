@@ -14,7 +14,8 @@ ITKv4's optimiser cannot be matched bit for bit without ITK: the b
 parity -- recovering a known transform / the reference tests' Dice thresholds -- plus exact agreement of the
 metric sums with the CPU oracle at identical poses.
 
-Supported: reg_method translation | rigid | similarity | affine | scale (or an ``AffineTransform`` to start from);
+Supported: reg_method translation | rigid | similarity | affine | scale | scaleversor | scaleskewversor (or an ``AffineTransform``
+to start from);
 metric mean_squares | correlation; optimiser gradient_descent | gradient_descent_line_search | lbfgsb.  The other options of the reference raise NotImplementedError
 (ValueError for names the reference itself rejects).
 """
@@ -228,8 +229,46 @@ class _Scale(_Model):
         return []
 
 
-_MODELS = {"translation": _Translation, "rigid": _VersorRigid, "similarity": _Similarity, "affine": _Affine, "scale": _Scale}
-_KNOWN_UNSUPPORTED = ("scaleversor", "scaleskewversor")
+class _ScaleVersor(_VersorRigid):
+    """itk::ScaleVersor3DTransform: parameters (versor 3, translation 3, scale 3); ComputeMatrix adds ``scale - 1`` to the diagonal
+    of the rotation matrix (ITK's documented, non-multiplicative form).  [ITK-recall]"""
+
+    name, n = "scaleversor", 9
+    _SKEW_SLOTS = ()
+
+    def identity(self):
+        return np.concatenate([np.zeros(6), np.ones(3), np.zeros(len(self._SKEW_SLOTS))])
+
+    def matrix(self, p=None):
+        p = self.p if p is None else p
+        m = versor_matrix(p[:3])
+        for k in range(3):
+            m[k, k] += p[6 + k] - 1.0
+        for q, (r, c) in enumerate(self._SKEW_SLOTS):
+            m[r, c] += p[9 + q]
+        return m
+
+    def matrix_bases(self, p=None):
+        p = self.p if p is None else p
+        out = list(enumerate(versor_matrix_derivatives(p[:3])))
+        for q, (r, c) in enumerate([(0, 0), (1, 1), (2, 2)] + list(self._SKEW_SLOTS)):
+            e = np.zeros((3, 3))
+            e[r, c] = 1.0
+            out.append((6 + q, e))
+        return out
+
+
+class _ScaleSkewVersor(_ScaleVersor):
+    """itk::ScaleSkewVersor3DTransform: (versor 3, translation 3, scale 3, skew 6); the six skew parameters are added to the
+    off-diagonal entries in row-major order.  [ITK-recall]"""
+
+    name, n = "scaleskewversor", 15
+    _SKEW_SLOTS = ((0, 1), (0, 2), (1, 0), (1, 2), (2, 0), (2, 1))
+
+
+_MODELS = {"translation": _Translation, "rigid": _VersorRigid, "similarity": _Similarity, "affine": _Affine, "scale": _Scale,
+           "scaleversor": _ScaleVersor, "scaleskewversor": _ScaleSkewVersor}
+_KNOWN_UNSUPPORTED = ()
 
 
 def make_model(reg_method):

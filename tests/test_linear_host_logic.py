@@ -21,7 +21,7 @@ def _fd(model, p, eps=1e-6):
 
 def test_matrix_derivatives_match_finite_differences():
     rng = np.random.default_rng(0)
-    for name in ("rigid", "similarity", "affine", "scale"):
+    for name in ("rigid", "similarity", "affine", "scale", "ScaleVersor", "ScaleSkewVersor"):
         m = linear.make_model(name)
         p = m.identity() + 0.1 * rng.standard_normal(m.n)
         fd = _fd(m, p)
@@ -58,8 +58,11 @@ def test_shrink_grid_and_initialiser():
     assert np.allclose(t.TransformPoint(linear.image_center(im)), linear.image_center(mv))
     with pytest.raises(ValueError):
         linear.make_model("nonsense")
-    with pytest.raises(NotImplementedError):
-        linear.make_model("ScaleSkewVersor")
+    sv, ssv = linear.make_model("ScaleVersor"), linear.make_model("ScaleSkewVersor")
+    assert (sv.n, ssv.n) == (9, 15) and np.array_equal(sv.matrix(), np.eye(3)) and np.array_equal(ssv.matrix(), np.eye(3))
+    p = ssv.identity()
+    p[6:9], p[9:] = (1.1, 0.9, 1.2), (0.01, 0.02, 0.03, 0.04, 0.05, 0.06)
+    assert np.allclose(ssv.matrix(p), [[1.1, 0.01, 0.02], [0.03, 0.9, 0.04], [0.05, 0.06, 1.2]])  # identity rotation + scale - 1 + skew
 
 
 def test_scales_and_convergence_value():
@@ -89,7 +92,7 @@ def test_metric_gradient_is_the_derivative_of_the_value():
     big = _blob_image((36, 32, 28), (19.5, 15.0, 14.5))
     mv = Image(big.array, big.GetSpacing(), (-6.0, -6.0, -6.0))
     init = linear.centered_transform_initializer(f, mv)
-    for name in ("translation", "rigid", "similarity", "affine"):
+    for name in ("translation", "rigid", "similarity", "affine", "scaleversor", "scaleskewversor"):
         m = linear.make_model(name)
         rng = np.random.default_rng(3)
         p = m.identity() + 0.01 * rng.standard_normal(m.n)
