@@ -263,6 +263,26 @@ int b200reg_linreg_correlation(b200reg_ctx* ctx, const float* d_fixed, const b20
                                const double initial_matrix[9], const double center[3], const uint8_t* d_fixed_mask,
                                const uint8_t* d_moving_mask, int stride, double h_out[42]);
 
+/* Metric "mattes_mi" (linear.py:145-146, SetMetricAsMattesMutualInformation -> itk::MattesMutualInformationImageToImageMetricv4):
+ * same sampling as the two metrics above, in two calls around a little host arithmetic.  *_bins = (bin size, normalised minimum)
+ * = ((max - min) / (n_bins - 4), min / bin size - 2) of the fixed / moving image.
+ *  1. histogram: h_hist[f * n_bins + m] = sum over samples of B3(m - M / moving bin size + moving normalised minimum) in the row
+ *     of the sample's fixed bin (bins clamped to [2, n_bins - 3]); h_count = number of valid samples.  Deterministic (fixed-point
+ *     integer atomics).  With p = hist / count:  value = - sum p log(p / (p_F p_M)).
+ *  2. derivative: h_table[f * n_bins + m] = log(p(f, m) / p_M(m)) (0 where undefined); h_out = [s (3), S (9 row-major)] with
+ *     w = sum_m table[f][m] B3'(m - u) (-1 / moving bin size), s = sum w h, S = sum w h (x - center)^T, h = initial_matrix^T grad M:
+ *     d(value)/d(translation) = -s / count,  d(value)/d(matrix parameter k) = -<dR/dp_k, S> / count.
+ * Both synchronise. */
+int b200reg_linreg_mattes_histogram(b200reg_ctx* ctx, const float* d_fixed, const b200reg_geom* fixed_geom, const float* d_moving,
+                                    const b200reg_geom* moving_geom, const double total_matrix[9], const double total_offset[3],
+                                    const uint8_t* d_fixed_mask, const uint8_t* d_moving_mask, int stride, int n_bins, const double fixed_bins[2],
+                                    const double moving_bins[2], double* h_hist, double* h_count);
+int b200reg_linreg_mattes_derivative(b200reg_ctx* ctx, const float* d_fixed, const b200reg_geom* fixed_geom, const float* d_moving,
+                                     const b200reg_geom* moving_geom, const double total_matrix[9], const double total_offset[3],
+                                     const double initial_matrix[9], const double center[3], const uint8_t* d_fixed_mask,
+                                     const uint8_t* d_moving_mask, int stride, int n_bins, const double fixed_bins[2], const double moving_bins[2],
+                                     const double* h_table, double h_out[12]);
+
 /* itk::ImageMomentsCalculator as sitk.CenteredTransformInitializer(fixed, moving, transform, MOMENTS) uses it (linear.py:40-43):
  * h_out = [sum v, sum v x, sum v y, sum v z] over all voxels, (x, y, z) the voxel's physical position.  Synchronises. */
 int b200reg_image_moments(b200reg_ctx* ctx, const float* d_image, const b200reg_geom* geom, double h_out[4]);

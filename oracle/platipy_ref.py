@@ -393,6 +393,42 @@ def linreg_correlation(fixed, moving, total_matrix, total_offset, initial_matrix
     return _linreg_sums(fixed, moving, total_matrix, total_offset, initial_matrix, center, fixed_mask, moving_mask, stride, "correlation")
 
 
+def _bspline3(u):
+    a = np.abs(u)
+    return np.where(a < 1, (4 - 6 * a * a + 3 * a ** 3) / 6, np.where(a < 2, (2 - a) ** 3 / 6, 0.0))
+
+
+def _bspline3_derivative(u):
+    a = np.abs(u)
+    d = np.where(a < 1, -2 * a + 1.5 * a * a, np.where(a < 2, -0.5 * (2 - a) ** 2, 0.0))
+    return np.sign(u) * d
+
+
+def linreg_mattes(fixed, moving, total_matrix, total_offset, initial_matrix, center, fixed_bins, moving_bins, n_bins=50, table=None,
+                  fixed_mask=None, moving_mask=None, stride=1):
+    """itk::MattesMutualInformationImageToImageMetricv4 (linear.py:145-146) over the samples of ``linreg_meansq``: the joint Parzen
+    histogram [fixed bin, moving bin] (zero-order window on the fixed value, cubic B-spline on the moving value, bin indices clamped
+    to [2, n_bins - 3]) and the sample count; with ``table`` = log(p / p_M) also the derivative sums [s (3), S (9)] for the weight
+    w = sum_m table[f][m] B3'(m - u) (-1 / moving bin size).  *_bins = (bin size, normalised minimum)."""
+    fv, mval, h, xc = _linreg_sums(fixed, moving, total_matrix, total_offset, initial_matrix, center, fixed_mask, moving_mask, stride, "raw")
+    lo, hi = 2, n_bins - 3
+    fi = np.clip(np.floor(fv / fixed_bins[0] - fixed_bins[1]).astype(np.int64), lo, hi)
+    term = mval / moving_bins[0] - moving_bins[1]
+    mi = np.clip(np.floor(term).astype(np.int64), lo, hi)
+    hist = np.zeros((n_bins, n_bins))
+    w = np.zeros_like(term)
+    for off in (-1, 0, 1, 2):
+        b = mi + off
+        np.add.at(hist, (fi, b), _bspline3(b - term))
+        if table is not None:
+            w += np.asarray(table)[fi, b] * _bspline3_derivative(b - term)
+    if table is None:
+        return hist, float(fv.size)
+    w = -w / moving_bins[0]
+    wh = w[:, None] * h
+    return hist, float(fv.size), np.concatenate([wh.sum(axis=0), (wh[:, :, None] * xc[:, None, :]).sum(axis=0).reshape(9)])
+
+
 def _linreg_sums(fixed, moving, total_matrix, total_offset, initial_matrix, center, fixed_mask, moving_mask, stride, kind):
     """Mean-squares metric sums of linear_registration (linear.py:141-163: SetMetricAsMeanSquares, linear interpolator,
     REGULAR sampling, optional masks), restated in numpy for every ``stride``-th fixed voxel in raster order:
@@ -440,6 +476,8 @@ def _linreg_sums(fixed, moving, total_matrix, total_offset, initial_matrix, cent
     gi = np.stack([gx0 + (gx1 - gx0) * d2, (vx10 - vx00) + ((vx11 - vx01) - (vx10 - vx00)) * d2, vxx1 - vxx0], axis=1)
     gy = gi @ p2i                                 # d/dy_j = sum_i g_i P2I[i][j]
     h = gy @ np.asarray(initial_matrix, np.float64).reshape(3, 3)   # A_i^T gy, row-vector form
+    if kind == "raw":
+        return fv, mval, h, x - np.asarray(center, np.float64)
     if kind == "correlation":
         xc = x - np.asarray(center, np.float64)
         out = np.zeros(42)

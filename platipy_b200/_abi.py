@@ -103,6 +103,12 @@ SIGNATURES = {
                                         C.POINTER(C.c_double), C.POINTER(C.c_double), _P, _P, C.c_int, C.POINTER(C.c_double)]),
     "b200reg_linreg_correlation": (C.c_int, [_P, _P, C.POINTER(Geom), _P, C.POINTER(Geom), C.POINTER(C.c_double), C.POINTER(C.c_double),
                                              C.POINTER(C.c_double), C.POINTER(C.c_double), _P, _P, C.c_int, C.POINTER(C.c_double)]),
+    "b200reg_linreg_mattes_histogram": (C.c_int, [_P, _P, C.POINTER(Geom), _P, C.POINTER(Geom), C.POINTER(C.c_double), C.POINTER(C.c_double), _P, _P,
+                                                  C.c_int, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                                  C.POINTER(C.c_double)]),
+    "b200reg_linreg_mattes_derivative": (C.c_int, [_P, _P, C.POINTER(Geom), _P, C.POINTER(Geom), C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                                   C.POINTER(C.c_double), C.POINTER(C.c_double), _P, _P, C.c_int, C.c_int, C.POINTER(C.c_double),
+                                                   C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "b200reg_image_moments": (C.c_int, [_P, _P, C.POINTER(Geom), C.POINTER(C.c_double)]),
     "b200reg_bounding_box": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "b200reg_region_copy": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32),

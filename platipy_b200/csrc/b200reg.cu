@@ -11,6 +11,7 @@
 #include "distmap.cuh"
 #include "patchcorr_kernels.cuh"
 #include "linreg_corr_kernels.cuh"
+#include "linreg_mattes_kernels.cuh"
 #include "moments_kernels.cuh"
 #include "gauss.cuh"
 #include "resample.cuh"
@@ -1061,5 +1062,90 @@ API int b200reg_image_moments(b200reg_ctx* ctx, const float* d_image, const b200
     B200_CUDA(cudaMemcpyAsync(ctx->h_scratch, out.p, sizeof(double) * MOMENTS_NV, cudaMemcpyDeviceToHost, ctx->stream));
     B200_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int v = 0; v < MOMENTS_NV; ++v) h_out[v] = ctx->h_scratch[v];
+    return B200REG_OK;
+}
+
+// ---- linear_registration, metric "mattes_mi" (linear.py:145-146): MattesMutualInformationImageToImageMetricv4 in two passes ------
+namespace {
+int mattes_setup(const double total_matrix[9], const double total_offset[3], const double* initial_matrix, const double* center, int n_bins,
+                 const double fixed_bins[2], const double moving_bins[2], CorrPose& ps, MattesBins& mb)
+{
+    REQUIRE(total_matrix && total_offset && fixed_bins && moving_bins, "invalid argument");
+    REQUIRE(n_bins >= 5 && n_bins <= 256, "number of histogram bins %d not in [5, 256]", n_bins);
+    REQUIRE(fixed_bins[0] > 0.0 && moving_bins[0] > 0.0, "bin sizes must be positive (constant image?)");
+    for (int r = 0; r < 3; ++r) {
+        ps.b[r] = total_offset[r];
+        ps.c[r] = center ? center[r] : 0.0;
+        for (int c = 0; c < 3; ++c) {
+            ps.A[r * 3 + c] = total_matrix[r * 3 + c];
+            ps.Bt[r * 3 + c] = initial_matrix ? initial_matrix[c * 3 + r] : (r == c ? 1.0 : 0.0);
+        }
+    }
+    mb.n = n_bins;
+    mb.fbin = fixed_bins[0];
+    mb.fmin = fixed_bins[1];
+    mb.mbin = moving_bins[0];
+    mb.mmin = moving_bins[1];
+    return B200REG_OK;
+}
+}  // namespace
+API int b200reg_linreg_mattes_histogram(b200reg_ctx* ctx, const float* d_fixed, const b200reg_geom* fixed_geom, const float* d_moving,
+                                        const b200reg_geom* moving_geom, const double total_matrix[9], const double total_offset[3],
+                                        const uint8_t* d_fixed_mask, const uint8_t* d_moving_mask, int stride, int n_bins, const double fixed_bins[2],
+                                        const double moving_bins[2], double* h_hist, double* h_count)
+{
+    ENTER(ctx);
+    REQUIRE(d_fixed && d_moving && valid_geom(fixed_geom) && valid_geom(moving_geom) && h_hist && h_count, "invalid argument");
+    REQUIRE(stride >= 1, "sampling stride must be >= 1");
+    CorrPose ps;
+    MattesBins mb;
+    B200_TRY(mattes_setup(total_matrix, total_offset, nullptr, nullptr, n_bins, fixed_bins, moving_bins, ps, mb));
+    const size_t n = nvox(*fixed_geom), nsamples = (n + (size_t)stride - 1) / (size_t)stride;
+    const size_t cells = (size_t)n_bins * n_bins;
+    TempBuf hist;
+    B200_TRY(hist.alloc(ctx, sizeof(unsigned long long) * (cells + 1)));
+    B200_CUDA(cudaMemsetAsync(hist.p, 0, sizeof(unsigned long long) * (cells + 1), ctx->stream));
+    linreg_mattes_hist_kernel<<<elementwise_blocks(ctx, nsamples, 256), 256, 0, ctx->stream>>>(
+        d_fixed, d_moving, d_fixed_mask, d_moving_mask, make_corr_geom(*fixed_geom), make_corr_geom(*moving_geom), ps, mb, stride, nsamples,
+        hist.as<unsigned long long>(), hist.as<unsigned long long>() + cells);
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    std::vector<unsigned long long> host(cells + 1);
+    B200_CUDA(cudaMemcpyAsync(host.data(), hist.p, sizeof(unsigned long long) * (cells + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));
+    for (size_t q = 0; q < cells; ++q) h_hist[q] = (double)host[q] / MATTES_FIXED_POINT;
+    *h_count = (double)host[cells];
+    return B200REG_OK;
+}
+API int b200reg_linreg_mattes_derivative(b200reg_ctx* ctx, const float* d_fixed, const b200reg_geom* fixed_geom, const float* d_moving,
+                                         const b200reg_geom* moving_geom, const double total_matrix[9], const double total_offset[3],
+                                         const double initial_matrix[9], const double center[3], const uint8_t* d_fixed_mask,
+                                         const uint8_t* d_moving_mask, int stride, int n_bins, const double fixed_bins[2], const double moving_bins[2],
+                                         const double* h_table, double h_out[12])
+{
+    ENTER(ctx);
+    REQUIRE(d_fixed && d_moving && valid_geom(fixed_geom) && valid_geom(moving_geom) && initial_matrix && center && h_table && h_out, "invalid argument");
+    REQUIRE(stride >= 1, "sampling stride must be >= 1");
+    CorrPose ps;
+    MattesBins mb;
+    B200_TRY(mattes_setup(total_matrix, total_offset, initial_matrix, center, n_bins, fixed_bins, moving_bins, ps, mb));
+    const size_t n = nvox(*fixed_geom), nsamples = (n + (size_t)stride - 1) / (size_t)stride;
+    const size_t cells = (size_t)n_bins * n_bins;
+    int nb = (int)((nsamples + 127) / 128);
+    if (nb > ctx->sm_count * 8) nb = ctx->sm_count * 8;
+    if (nb < 1) nb = 1;
+    TempBuf table, part, out;
+    B200_TRY(table.alloc(ctx, sizeof(double) * cells));
+    B200_TRY(part.alloc(ctx, sizeof(double) * MATTES_NV * (size_t)nb));
+    B200_TRY(out.alloc(ctx, sizeof(double) * MATTES_NV));
+    B200_CUDA(cudaMemcpyAsync(table.p, h_table, sizeof(double) * cells, cudaMemcpyHostToDevice, ctx->stream));
+    linreg_mattes_deriv_kernel<<<nb, 128, 0, ctx->stream>>>(d_fixed, d_moving, d_fixed_mask, d_moving_mask, make_corr_geom(*fixed_geom),
+                                                            make_corr_geom(*moving_geom), ps, mb, stride, nsamples, table.as<double>(), part.as<double>());
+    linreg_mattes_final_kernel<<<1, 32, 0, ctx->stream>>>(part.as<double>(), nb, out.as<double>());
+    ctx->launches += 2;
+    B200_CHECK_LAUNCH();
+    B200_CUDA(cudaMemcpyAsync(ctx->h_scratch, out.p, sizeof(double) * MATTES_NV, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(cudaStreamSynchronize(ctx->stream));  // also: h_table is caller memory
+    for (int v = 0; v < MATTES_NV; ++v) h_out[v] = ctx->h_scratch[v];
     return B200REG_OK;
 }

@@ -31,11 +31,16 @@ struct CorrPose {
 };
 constexpr int LINREG_CORR_NV = 42;
 
-__device__ __forceinline__ void corr_sample(const float* __restrict__ F, const float* __restrict__ M, const uint8_t* __restrict__ fmask,
-                                            const uint8_t* __restrict__ mmask, const CorrGeom& gf, const CorrGeom& gm, const CorrPose& ps, size_t q,
-                                            double* acc)
+// One sampled fixed voxel q: maps it into the moving image and, when it is a valid sample (inside the masks and the moving buffer),
+// returns the fixed value, the trilinear moving value, h = A_i^T grad_y M and x - c.  Shared by the correlation and Mattes kernels.
+struct LinregPoint {
+    double fval, mval, h[3], xc[3];
+};
+__device__ __forceinline__ bool linreg_sample_point(const float* __restrict__ F, const float* __restrict__ M, const uint8_t* __restrict__ fmask,
+                                                    const uint8_t* __restrict__ mmask, const CorrGeom& gf, const CorrGeom& gm, const CorrPose& ps, size_t q,
+                                                    LinregPoint& pt)
 {
-    if (fmask && fmask[q] == 0) return;
+    if (fmask && fmask[q] == 0) return false;
     const size_t plane = (size_t)gf.nx * gf.ny;
     const int k = (int)(q / plane), j = (int)((q % plane) / gf.nx), i = (int)(q % gf.nx);
     double x[3], y[3], c[3];
@@ -59,10 +64,10 @@ __device__ __forceinline__ void corr_sample(const float* __restrict__ F, const f
         c[r] = sum;
     }
     // ImageFunction::IsInsideBuffer: [-0.5, size - 0.5); NaN -> outside
-    if (!(c[0] >= -0.5 && c[0] < (double)gm.nx - 0.5 && c[1] >= -0.5 && c[1] < (double)gm.ny - 0.5 && c[2] >= -0.5 && c[2] < (double)gm.nz - 0.5)) return;
+    if (!(c[0] >= -0.5 && c[0] < (double)gm.nx - 0.5 && c[1] >= -0.5 && c[1] < (double)gm.ny - 0.5 && c[2] >= -0.5 && c[2] < (double)gm.nz - 0.5)) return false;
     if (mmask) {
         const int i0 = (int)floor(c[0] + 0.5), i1 = (int)floor(c[1] + 0.5), i2 = (int)floor(c[2] + 0.5);
-        if (mmask[((size_t)i2 * gm.ny + i1) * gm.nx + i0] == 0) return;
+        if (mmask[((size_t)i2 * gm.ny + i1) * gm.nx + i0] == 0) return false;
     }
     // LinearInterpolateImageFunction: base clamped up to 0 (distance 0 there), upper neighbour clamped at the far edge
     int b[3], u[3];
@@ -84,32 +89,43 @@ __device__ __forceinline__ void corr_sample(const float* __restrict__ F, const f
     const double a00 = v100 - v000, a10 = v110 - v010, a01 = v101 - v001, a11 = v111 - v011;
     const double vx00 = v000 + a00 * d[0], vx10 = v010 + a10 * d[0], vx01 = v001 + a01 * d[0], vx11 = v011 + a11 * d[0];
     const double vxx0 = vx00 + (vx10 - vx00) * d[1], vxx1 = vx01 + (vx11 - vx01) * d[1];
-    const double mval = vxx0 + (vxx1 - vxx0) * d[2];
+    pt.mval = vxx0 + (vxx1 - vxx0) * d[2];
     const double gx0 = a00 + (a10 - a00) * d[1], gx1 = a01 + (a11 - a01) * d[1];
     const double gi[3] = { gx0 + (gx1 - gx0) * d[2], (vx10 - vx00) + ((vx11 - vx01) - (vx10 - vx00)) * d[2], vxx1 - vxx0 };
-    double gy[3], h[3];
+    double gy[3];
 #pragma unroll
     for (int r = 0; r < 3; ++r) gy[r] = gi[0] * gm.p2i[0 * 3 + r] + gi[1] * gm.p2i[1 * 3 + r] + gi[2] * gm.p2i[2 * 3 + r];
 #pragma unroll
-    for (int r = 0; r < 3; ++r) h[r] = ps.Bt[r * 3 + 0] * gy[0] + ps.Bt[r * 3 + 1] * gy[1] + ps.Bt[r * 3 + 2] * gy[2];
-    const double fval = (double)F[q];
+    for (int r = 0; r < 3; ++r) pt.h[r] = ps.Bt[r * 3 + 0] * gy[0] + ps.Bt[r * 3 + 1] * gy[1] + ps.Bt[r * 3 + 2] * gy[2];
+    pt.fval = (double)F[q];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) pt.xc[r] = x[r] - ps.c[r];
+    return true;
+}
+
+__device__ __forceinline__ void corr_sample(const float* __restrict__ F, const float* __restrict__ M, const uint8_t* __restrict__ fmask,
+                                            const uint8_t* __restrict__ mmask, const CorrGeom& gf, const CorrGeom& gm, const CorrPose& ps, size_t q,
+                                            double* acc)
+{
+    LinregPoint pt;
+    if (!linreg_sample_point(F, M, fmask, mmask, gf, gm, ps, q, pt)) return;
+    const double fval = pt.fval, mval = pt.mval;
     acc[0] += 1.0;
     acc[1] += fval;
     acc[2] += mval;
     acc[3] += fval * fval;
     acc[4] += mval * mval;
     acc[5] += fval * mval;
-    const double xc[3] = { x[0] - ps.c[0], x[1] - ps.c[1], x[2] - ps.c[2] };
     const double wt[3] = { 1.0, fval, mval };
 #pragma unroll
     for (int w = 0; w < 3; ++w) {
 #pragma unroll
         for (int r = 0; r < 3; ++r) {
-            const double wr = wt[w] * h[r];
+            const double wr = wt[w] * pt.h[r];
             acc[6 + 12 * w + r] += wr;
-            acc[6 + 12 * w + 3 + r * 3 + 0] += wr * xc[0];
-            acc[6 + 12 * w + 3 + r * 3 + 1] += wr * xc[1];
-            acc[6 + 12 * w + 3 + r * 3 + 2] += wr * xc[2];
+            acc[6 + 12 * w + 3 + r * 3 + 0] += wr * pt.xc[0];
+            acc[6 + 12 * w + 3 + r * 3 + 1] += wr * pt.xc[1];
+            acc[6 + 12 * w + 3 + r * 3 + 2] += wr * pt.xc[2];
         }
     }
 }

@@ -452,6 +452,35 @@ class Engine:
             moving_mask.ptr if moving_mask is not None else None, int(stride), out))
         return np.array(out[:], dtype=np.float64)
 
+    def linreg_mattes_histogram(self, fixed, moving, total_matrix, total_offset, fixed_bins, moving_bins, n_bins=50, fixed_mask=None, moving_mask=None,
+                                stride=1):
+        """Joint Parzen histogram [n_bins, n_bins] (fixed bin, moving bin) and the number of valid samples.  Synchronises."""
+        hist = np.empty((n_bins, n_bins), dtype=np.float64)
+        count = C.c_double()
+        gf, gm = fixed.geom, moving.geom
+        d9, d3, d2 = C.c_double * 9, C.c_double * 3, C.c_double * 2
+        _abi.check(self.lib.b200reg_linreg_mattes_histogram(
+            self.ctx, fixed.ptr, C.byref(gf), moving.ptr, C.byref(gm), d9(*np.asarray(total_matrix, float).reshape(9)),
+            d3(*np.asarray(total_offset, float).reshape(3)), fixed_mask.ptr if fixed_mask is not None else None,
+            moving_mask.ptr if moving_mask is not None else None, int(stride), int(n_bins), d2(*[float(v) for v in fixed_bins]),
+            d2(*[float(v) for v in moving_bins]), hist.ctypes.data_as(C.POINTER(C.c_double)), C.byref(count)))
+        return hist, count.value
+
+    def linreg_mattes_derivative(self, fixed, moving, total_matrix, total_offset, initial_matrix, center, fixed_bins, moving_bins, table, fixed_mask=None,
+                                 moving_mask=None, stride=1):
+        """[s (3), S (9)] of the Mattes derivative for the host's table log(p / p_M).  Synchronises."""
+        table = np.ascontiguousarray(table, dtype=np.float64)
+        out = (C.c_double * 12)()
+        gf, gm = fixed.geom, moving.geom
+        d9, d3, d2 = C.c_double * 9, C.c_double * 3, C.c_double * 2
+        _abi.check(self.lib.b200reg_linreg_mattes_derivative(
+            self.ctx, fixed.ptr, C.byref(gf), moving.ptr, C.byref(gm), d9(*np.asarray(total_matrix, float).reshape(9)),
+            d3(*np.asarray(total_offset, float).reshape(3)), d9(*np.asarray(initial_matrix, float).reshape(9)),
+            d3(*np.asarray(center, float).reshape(3)), fixed_mask.ptr if fixed_mask is not None else None,
+            moving_mask.ptr if moving_mask is not None else None, int(stride), int(table.shape[0]), d2(*[float(v) for v in fixed_bins]),
+            d2(*[float(v) for v in moving_bins]), table.ctypes.data_as(C.POINTER(C.c_double)), out))
+        return np.array(out[:], dtype=np.float64)
+
     def image_moments(self, dimg):
         """[sum v, sum v x, sum v y, sum v z] of a Float32 image in physical coordinates (ImageMomentsCalculator).  Synchronises."""
         out = (C.c_double * 4)()

@@ -19,7 +19,6 @@ import logging
 import numpy as np
 import torch
 
-from . import sitk_compat as sk
 from .engine import Engine
 from .fusion import combine_labels
 

@@ -16,7 +16,7 @@ metric sums with the CPU oracle at identical poses.
 
 Supported: reg_method translation | rigid | similarity | affine | scale | scaleversor | scaleskewversor (or an ``AffineTransform``
 to start from);
-metric mean_squares | correlation; optimiser gradient_descent | gradient_descent_line_search | lbfgsb.  The other options of the reference raise NotImplementedError
+metric mean_squares | correlation | mattes_mi; optimiser gradient_descent | gradient_descent_line_search | lbfgsb.  The other options of the reference raise NotImplementedError
 (ValueError for names the reference itself rejects).
 """
 from __future__ import annotations
@@ -566,6 +566,46 @@ def correlation_in_meansq_form(sums):
     return out
 
 
+MATTES_BINS = 50  # SimpleITK's default numberOfHistogramBins (linear.py:146 calls SetMetricAsMattesMutualInformation() bare)
+
+
+def mattes_bins(vmin, vmax, n_bins=MATTES_BINS):
+    """(bin size, normalised minimum) of MattesMutualInformationImageToImageMetricv4::Initialize: two padding bins at either
+    end of the intensity range."""
+    padding = 2
+    if not vmax > vmin:
+        raise RuntimeError("MattesMutualInformation: the image is constant (zero-width intensity range)")
+    binsize = (float(vmax) - float(vmin)) / (n_bins - 2 * padding)
+    return binsize, float(vmin) / binsize - padding
+
+
+def mattes_value_and_table(hist):
+    """From the joint Parzen histogram: the metric value -sum p log(p / (p_F p_M)) and the table log(p / p_M) the derivative pass
+    needs (Mattes et al. 2003, eq. 27; zero where a probability is below machine epsilon, like ITK skips those bins)."""
+    total = hist.sum()
+    if not total > 0:
+        return 0.0, np.zeros_like(hist), 0.0
+    p = hist / total
+    pf, pm = p.sum(axis=1), p.sum(axis=0)
+    eps = np.finfo(np.float64).eps
+    ok = (p > eps) & (pf[:, None] > eps) & (pm[None, :] > eps)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        value = -float(np.sum(np.where(ok, p * np.log(p / (pf[:, None] * pm[None, :])), 0.0)))
+        table = np.where(ok, np.log(p / pm[None, :]), 0.0)
+    return value, table, total
+
+
+def mattes_in_meansq_form(value, count, total, sums):
+    """The 14-number form the optimisers consume (see correlation_in_meansq_form): value -MI, derivative -(s, S) / total."""
+    out = np.zeros(14)
+    out[1] = count
+    if count <= 0 or not total > 0:
+        return out
+    out[0] = value * count
+    out[2:14] = -np.asarray(sums, dtype=np.float64) * (count / total)
+    return out
+
+
 # ---------------------------------------------------------------------------------------------------------------------
 # public entry points
 # ---------------------------------------------------------------------------------------------------------------------
@@ -603,11 +643,11 @@ def linear_registration(fixed_image, moving_image, fixed_structure=None, moving_
     (registered image in the moving image's pixel type, CompositeTransform([initial, optimised]))."""
     from . import registration as reg
 
-    if metric.lower() not in ("mean_squares", "correlation"):
-        if metric.lower() in ("mattes_mi", "joint_hist_mi"):
-            raise NotImplementedError(f"metric {metric!r} is not implemented on the B200 path (mean_squares and correlation are)")
+    if metric.lower() not in ("mean_squares", "correlation", "mattes_mi"):
+        if metric.lower() == "joint_hist_mi":
+            raise NotImplementedError(f"metric {metric!r} is not implemented on the B200 path (mean_squares, correlation and mattes_mi are)")
         raise ValueError(f"unknown metric {metric!r}")
-    use_correlation = metric.lower() == "correlation"
+    use_correlation, use_mattes = metric.lower() == "correlation", metric.lower() == "mattes_mi"
     if optimiser.lower() not in ("gradient_descent", "gradient_descent_line_search", "lbfgsb"):
         if optimiser.lower() == "exhaustive":  # "This isn't well implemented ... Use is not currently recommended" (linear.py:217-224)
             raise NotImplementedError(f"optimiser {optimiser!r} is not implemented on the B200 path (gradient_descent[_line_search] and lbfgsb are)")
@@ -646,9 +686,20 @@ def linear_registration(fixed_image, moving_image, fixed_structure=None, moving_
                 mm_l = eng.resample(mm_l, gm, None, sk.sitkNearestNeighbor, 0.0)
         corners = image_corners(f_l)
         max_step = float(min(f_l.GetSpacing()))
+        f_bins = m_bins = None
+        if use_mattes:  # the intensity ranges of this level's images fix the histogram bins
+            f_bins, m_bins = mattes_bins(*eng.minmax(f_l)), mattes_bins(*eng.minmax(m_l))
 
-        def evaluate(p, f_l=f_l, m_l=m_l, fm_l=fm_l, mm_l=mm_l):
+        def evaluate(p, f_l=f_l, m_l=m_l, fm_l=fm_l, mm_l=mm_l, f_bins=f_bins, m_bins=m_bins):
             a_o, b_o = model.matrix(p), model.offset(p)
+            if use_mattes:
+                a_t, b_t = a_init @ a_o, a_init @ b_o + b_init
+                hist, count = eng.linreg_mattes_histogram(f_l, m_l, a_t, b_t, f_bins, m_bins, MATTES_BINS, fm_l, mm_l, stride)
+                value, table, total = mattes_value_and_table(hist)
+                if count <= 0:
+                    return np.zeros(14)
+                sums = eng.linreg_mattes_derivative(f_l, m_l, a_t, b_t, a_init, model.center, f_bins, m_bins, table, fm_l, mm_l, stride)
+                return mattes_in_meansq_form(value, count, total, sums)
             if use_correlation:
                 return correlation_in_meansq_form(
                     eng.linreg_correlation(f_l, m_l, a_init @ a_o, a_init @ b_o + b_init, a_init, model.center, fm_l, mm_l, stride))

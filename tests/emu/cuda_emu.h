@@ -26,6 +26,15 @@ struct emu_dim3 {
 };
 static thread_local emu_dim3 threadIdx, blockIdx, blockDim, gridDim;
 
+// atomics of a serial emulation are plain read-modify-writes
+template <typename T>
+static T atomicAdd(T* address, T value)
+{
+    const T old = *address;
+    *address = old + value;
+    return old;
+}
+
 template <typename K, typename... A>
 static void emu_launch(K kernel, unsigned grid, unsigned block, A... args)
 {

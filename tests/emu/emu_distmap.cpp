@@ -8,6 +8,7 @@
 #include "../../platipy_b200/csrc/patchcorr_kernels.cuh"
 #include "../../platipy_b200/csrc/linreg_corr_kernels.cuh"
 #include "../../platipy_b200/csrc/moments_kernels.cuh"
+#include "../../platipy_b200/csrc/linreg_mattes_kernels.cuh"
 
 using namespace b200;
 
@@ -75,17 +76,36 @@ EMU_API void emu_scale_shift_f32(const float* in, size_t n, int take_abs, float 
 }
 // geometry: size (3 ints), origin (3), i2p (9), p2i (9) as the host wrapper fills them; pose: A (9), b (3), Bt (9), c (3).
 // partials: [grid * block][42] per-thread sums (the CUDA build reduces them per block instead).
-EMU_API void emu_linreg_corr(const float* F, const float* M, const uint8_t* fmask, const uint8_t* mmask, const int* fsize, const double* fgeo,
-                             const int* msize, const double* mgeo, const double* pose, int stride, double* partials, unsigned grid, unsigned block)
+static void unpack(const int* fsize, const double* fgeo, const int* msize, const double* mgeo, const double* pose, CorrGeom& gf, CorrGeom& gm, CorrPose& ps)
 {
-    CorrGeom gf, gm;
-    CorrPose ps;
     gf.nx = fsize[0]; gf.ny = fsize[1]; gf.nz = fsize[2];
     gm.nx = msize[0]; gm.ny = msize[1]; gm.nz = msize[2];
     for (int r = 0; r < 3; ++r) { gf.origin[r] = fgeo[r]; gm.origin[r] = mgeo[r]; }
     for (int r = 0; r < 9; ++r) { gf.i2p[r] = fgeo[3 + r]; gf.p2i[r] = fgeo[12 + r]; gm.i2p[r] = mgeo[3 + r]; gm.p2i[r] = mgeo[12 + r]; }
     for (int r = 0; r < 9; ++r) { ps.A[r] = pose[r]; ps.Bt[r] = pose[12 + r]; }
     for (int r = 0; r < 3; ++r) { ps.b[r] = pose[9 + r]; ps.c[r] = pose[21 + r]; }
+}
+// bins: n, fixed (bin size, normalised minimum), moving (bin size, normalised minimum); hist: [n * n + 1] integers (weights * 2^32, count last)
+EMU_API void emu_linreg_mattes(const float* F, const float* M, const uint8_t* fmask, const uint8_t* mmask, const int* fsize, const double* fgeo,
+                               const int* msize, const double* mgeo, const double* pose, int stride, int n_bins, const double* bins,
+                               unsigned long long* hist, const double* table, double* partials, unsigned grid, unsigned block)
+{
+    CorrGeom gf, gm;
+    CorrPose ps;
+    unpack(fsize, fgeo, msize, mgeo, pose, gf, gm, ps);
+    MattesBins mb;
+    mb.n = n_bins; mb.fbin = bins[0]; mb.fmin = bins[1]; mb.mbin = bins[2]; mb.mmin = bins[3];
+    const size_t n = (size_t)gf.nx * gf.ny * gf.nz;
+    const size_t nsamples = (n + (size_t)stride - 1) / (size_t)stride;
+    if (hist) emu_launch(linreg_mattes_hist_kernel, grid, block, F, M, fmask, mmask, gf, gm, ps, mb, stride, nsamples, hist, hist + (size_t)n_bins * n_bins);
+    if (table) emu_launch(linreg_mattes_deriv_kernel, grid, block, F, M, fmask, mmask, gf, gm, ps, mb, stride, nsamples, table, partials);
+}
+EMU_API void emu_linreg_corr(const float* F, const float* M, const uint8_t* fmask, const uint8_t* mmask, const int* fsize, const double* fgeo,
+                             const int* msize, const double* mgeo, const double* pose, int stride, double* partials, unsigned grid, unsigned block)
+{
+    CorrGeom gf, gm;
+    CorrPose ps;
+    unpack(fsize, fgeo, msize, mgeo, pose, gf, gm, ps);
     const size_t n = (size_t)gf.nx * gf.ny * gf.nz;
     const size_t nsamples = (n + (size_t)stride - 1) / (size_t)stride;
     emu_launch(linreg_corr_kernel, grid, block, F, M, fmask, mmask, gf, gm, ps, stride, nsamples, partials);

@@ -262,7 +262,6 @@ def test_patch_correlation_weight_map_chain_on_the_cpu(emu):
     function, cast -- with the oracle standing in for the two resampling steps, against the reference-shaped restatement
     (padding, window views, pearsonr per patch)."""
     from oracle import platipy_ref as ref
-    from platipy_b200 import sitk_compat as sk
     from platipy_b200.synth import synth_pair
 
     f, m = synth_pair((40, 36, 24), seed=5, spacing=(1.0, 1.0, 2.0))

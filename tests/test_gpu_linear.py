@@ -125,7 +125,7 @@ def test_masks_and_argument_errors(engine):
     with pytest.raises(ValueError):
         linear.linear_registration(fixed, moving, reg_method="nonsense")
     with pytest.raises(NotImplementedError):
-        linear.linear_registration(fixed, moving, metric="mattes_mi")
+        linear.linear_registration(fixed, moving, metric="joint_hist_mi")
     with pytest.raises(NotImplementedError):
         linear.linear_registration(fixed, moving, optimiser="exhaustive")
     far = Image(moving.array, moving.GetSpacing(), (1e5, 0.0, 0.0))

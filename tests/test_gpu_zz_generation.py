@@ -297,7 +297,7 @@ def test_linear_registration_correlation_metric(engine):
         r = np.corrcoef(registered.array.ravel(), fixed.array.ravel())[0, 1]
         assert r > 0.995 and min(linear.LAST_HISTORY[-1]) < -0.98
     with pytest.raises(NotImplementedError):
-        linear.linear_registration(fixed, moving, metric="mattes_mi")
+        linear.linear_registration(fixed, moving, metric="joint_hist_mi")
 
 
 def test_get_bone_mask(engine):
@@ -348,3 +348,57 @@ def test_alignment_registration_with_moments_and_lbfgsb(engine):
         for part in t.flatten():
             pt = np.array(part.TransformPoint(pt))
         assert np.allclose(pt, (26.0, 18.5, 17.0), atol=0.3), (metric, pt)
+
+
+def test_linear_registration_mattes_mutual_information(engine):
+    """metric="mattes_mi" (linear.py:145-146): histogram and derivative sums against the numpy restatement at identical poses, and
+    a registration of an inverted-contrast pair, which only a mutual-information metric can align."""
+    from oracle import platipy_ref as ref
+    from platipy_b200 import linear
+
+    def blob(size, center, spacing=(1.0, 1.0, 1.0), sig=(7.0, 5.0, 4.0), origin=(0.0, 0.0, 0.0), direction=(1, 0, 0, 0, 1, 0, 0, 0, 1)):
+        nx, ny, nz = size
+        z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
+        p = [x * spacing[0], y * spacing[1], z * spacing[2]]
+        v = sum(((pi - ci) / si) ** 2 for pi, ci, si in zip(p, center, sig))
+        return Image((1000.0 * np.exp(-0.5 * v)).astype(np.float32), spacing, origin, direction)
+
+    rng = np.random.default_rng(9)
+    ang = 0.15
+    rot = (np.cos(ang), -np.sin(ang), 0, np.sin(ang), np.cos(ang), 0, 0, 0, 1.0)
+    f = blob((24, 20, 16), (12.0, 10.0, 8.0), (1.0, 1.2, 1.5))
+    big = blob((30, 26, 20), (15.0, 13.5, 12.0), (1.1, 1.0, 1.4), origin=(-3.0, 2.0, -1.0), direction=rot)
+    mv = Image((900.0 - big.array).astype(np.float32), big.GetSpacing(), big.GetOrigin(), big.GetDirection())
+    fmask = Image((rng.random(f.array.shape) > 0.3).astype(np.uint8), f.GetSpacing())
+    mmask = Image((rng.random(mv.array.shape) > 0.2).astype(np.uint8), mv.GetSpacing(), mv.GetOrigin(), mv.GetDirection())
+    init = linear.centered_transform_initializer(f, mv)
+    m = linear.make_model("affine")
+    p = m.identity() + 0.02 * rng.standard_normal(m.n)
+    A, b = init.matrix @ m.matrix(p), init.matrix @ m.offset(p) + init.offset
+    df, dm, dfm, dmm = (engine.to_device(i) for i in (f, mv, fmask, mmask))
+    fb, mb = linear.mattes_bins(*engine.minmax(df)), linear.mattes_bins(*engine.minmax(dm))
+    assert np.allclose(fb, linear.mattes_bins(f.array.min(), f.array.max())) and np.allclose(mb, linear.mattes_bins(mv.array.min(), mv.array.max()))
+    for fm, mm, dfm_, dmm_, stride in ((None, None, None, None, 1), (fmask, mmask, dfm, dmm, 2)):
+        hist, count = engine.linreg_mattes_histogram(df, dm, A, b, fb, mb, 50, dfm_, dmm_, stride)
+        exp_hist, exp_count = ref.linreg_mattes(f, mv, A, b, init.matrix, m.center, fb, mb, 50, None, fm, mm, stride)
+        assert count == exp_count and np.allclose(hist, exp_hist, rtol=0, atol=exp_count * 2.0 ** -32)
+        again, _ = engine.linreg_mattes_histogram(df, dm, A, b, fb, mb, 50, dfm_, dmm_, stride)
+        assert np.array_equal(hist, again)  # fixed-point integer atomics: deterministic
+        _, table, _ = linear.mattes_value_and_table(exp_hist)
+        sums = engine.linreg_mattes_derivative(df, dm, A, b, init.matrix, m.center, fb, mb, table, dfm_, dmm_, stride)
+        _, _, exp_sums = ref.linreg_mattes(f, mv, A, b, init.matrix, m.center, fb, mb, 50, table, fm, mm, stride)
+        assert np.allclose(sums, exp_sums, rtol=1e-9, atol=1e-9 * np.abs(exp_sums).max())
+    fixed = blob((48, 40, 32), (24.0, 20.0, 16.0))
+    shifted = blob((48, 40, 32), (26.0, 18.5, 17.0))
+    moving = Image((1000.0 - shifted.array * 0.8).astype(np.float32), shifted.GetSpacing())
+    for optimiser in ("gradient_descent_line_search", "lbfgsb"):
+        _, tfm = linear.linear_registration(fixed, moving, reg_method="translation", metric="mattes_mi", optimiser=optimiser, shrink_factors=[2, 1],
+                                            smooth_sigmas=[1, 0], sampling_rate=0.5, number_of_iterations=50, default_value=1000)
+        pt = np.array((24.0, 20.0, 16.0))
+        for part in tfm.flatten():
+            pt = np.array(part.TransformPoint(pt))
+        assert np.allclose(pt, (26.0, 18.5, 17.0), atol=0.5), (optimiser, pt)
+    with pytest.raises(NotImplementedError):
+        linear.linear_registration(fixed, moving, metric="joint_hist_mi")
+    with pytest.raises(RuntimeError):
+        linear.linear_registration(fixed, Image(np.zeros((8, 8, 8), np.float32)), metric="mattes_mi", shrink_factors=[1], smooth_sigmas=[0])

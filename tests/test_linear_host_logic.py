@@ -279,3 +279,95 @@ def test_emulated_image_moments_and_center_of_gravity(emu):
     assert np.allclose(cog, np.asarray(img.GetOrigin()) + d @ np.array([15.0, 11.0, 12.0]), atol=0.25)  # the blob is cut asymmetrically by the image border
     with pytest.raises(RuntimeError):
         linear.center_of_gravity(np.zeros(4))
+
+
+# ---- metric "mattes_mi" (linear.py:145-146) -----------------------------------------------------------------------------------
+def _mattes_acc(f, mv, init, m, q, fb, mb, **kw):
+    A, b = init.matrix @ m.matrix(q), init.matrix @ m.offset(q) + init.offset
+    hist, count = ref.linreg_mattes(f, mv, A, b, init.matrix, m.center, fb, mb, **kw)
+    value, table, total = linear.mattes_value_and_table(hist)
+    _, _, sums = ref.linreg_mattes(f, mv, A, b, init.matrix, m.center, fb, mb, table=table, **kw)
+    return linear.mattes_in_meansq_form(value, count, total, sums)
+
+
+def test_mattes_value_gradient_and_optimisers():
+    f = _blob_image((24, 20, 16), (12.0, 10.0, 8.0))
+    big = _blob_image((36, 32, 28), (19.5, 15.0, 14.5))
+    mv = Image(1000.0 - big.array * 0.8, big.GetSpacing(), (-6.0, -6.0, -6.0))  # inverted contrast: mean squares and correlation^1 fail here
+    init = linear.centered_transform_initializer(f, mv)
+    fb, mb = linear.mattes_bins(f.array.min(), f.array.max()), linear.mattes_bins(mv.array.min(), mv.array.max())
+    assert np.isclose(fb[0] * 46, float(f.array.max()) - float(f.array.min())) and np.isclose(fb[1], f.array.min() / fb[0] - 2)
+    # histogram: partition of unity (every sample adds weight 1), marginal of the fixed axis = plain histogram of the fixed bins
+    m = linear.make_model("translation")
+    hist, count = ref.linreg_mattes(f, mv, init.matrix, init.offset, init.matrix, m.center, fb, mb)
+    assert count == f.array.size and np.isclose(hist.sum(), count, rtol=1e-9) and hist.shape == (50, 50)
+    assert not hist[:2].any() and not hist[-2:].any()  # the padding bins of the fixed axis stay empty
+    value, table, total = linear.mattes_value_and_table(hist)
+    assert value < -0.5 and np.isfinite(table).all()
+    for name in ("translation", "rigid", "affine"):
+        m = linear.make_model(name)
+        rng = np.random.default_rng(3)
+        p = m.identity() + 0.01 * rng.standard_normal(m.n)
+        acc = _mattes_acc(f, mv, init, m, p, fb, mb)
+        g = m.gradient(acc, p)
+        for k in range(m.n):
+            d = np.zeros(m.n)
+            d[k] = 1e-5
+            a1, a0 = _mattes_acc(f, mv, init, m, p + d, fb, mb), _mattes_acc(f, mv, init, m, p - d, fb, mb)
+            fd = (a1[0] / a1[1] - a0[0] / a0[1]) / 2e-5
+            assert np.isclose(g[k], fd, rtol=2e-3, atol=1e-3 * abs(g).max()), (name, k, g[k], fd)
+    # registration of the inverted-contrast pair
+    shifted = _blob_image((24, 20, 16), (14.0, 8.5, 9.0))
+    inv = Image(1000.0 - shifted.array * 0.8, shifted.GetSpacing())
+    init = linear.centered_transform_initializer(f, inv)
+    mb = linear.mattes_bins(inv.array.min(), inv.array.max())
+    for run in (linear.optimise_level, linear.optimise_level_line_search, linear.optimise_level_lbfgsb):
+        m = linear.make_model("translation")
+        hist = run(m, lambda p: _mattes_acc(f, inv, init, m, p, fb, mb, stride=2), linear.image_corners(f), 1.0, 60)
+        assert min(hist) < hist[0] - 0.2
+        assert np.allclose(m.p, [2.0, -1.5, 1.0], atol=0.3), (run.__name__, m.p)
+    with pytest.raises(RuntimeError):
+        linear.mattes_bins(3.0, 3.0)
+    assert not linear.mattes_in_meansq_form(0.0, 0, 0.0, np.zeros(12)).any()
+
+
+def test_emulated_mattes_kernels_match_the_numpy_restatement(emu):
+    import ctypes as C
+
+    rng = np.random.default_rng(9)
+    f = _blob_image((24, 20, 16), (12.0, 10.0, 8.0), spacing=(1.0, 1.2, 1.5))
+    ang = 0.15
+    rot = np.array([[np.cos(ang), -np.sin(ang), 0], [np.sin(ang), np.cos(ang), 0], [0, 0, 1.0]])
+    big = _blob_image((30, 26, 20), (15.0, 13.5, 12.0), spacing=(1.1, 1.0, 1.4))
+    mv = Image((900.0 - big.array + rng.normal(0, 5, big.array.shape)).astype(np.float32), big.GetSpacing(), (-3.0, 2.0, -1.0), tuple(rot.reshape(9)))
+    fmask = Image((rng.random(f.array.shape) > 0.3).astype(np.uint8), f.GetSpacing())
+    mmask = Image((rng.random(mv.array.shape) > 0.2).astype(np.uint8), mv.GetSpacing(), mv.GetOrigin(), mv.GetDirection())
+    init = linear.centered_transform_initializer(f, mv)
+    m = linear.make_model("affine")
+    p = m.identity() + 0.02 * rng.standard_normal(m.n)
+    A, b = init.matrix @ m.matrix(p), init.matrix @ m.offset(p) + init.offset
+    fb, mb = linear.mattes_bins(f.array.min(), f.array.max()), linear.mattes_bins(mv.array.min(), mv.array.max())
+
+    def geo(img):
+        d = np.asarray(img.GetDirection(), np.float64).reshape(3, 3)
+        i2p = d * np.asarray(img.GetSpacing())[None, :]
+        return (np.array(img.GetSize(), np.int32), np.concatenate([np.asarray(img.GetOrigin(), np.float64), i2p.reshape(9), np.linalg.inv(i2p).reshape(9)]))
+
+    (fs, fg), (ms, mg) = geo(f), geo(mv)
+    pose = np.concatenate([A.reshape(9), b, init.matrix.T.reshape(9), m.center]).astype(np.float64)
+    bins = np.array([fb[0], fb[1], mb[0], mb[1]])
+    P = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
+    for fm, mm, stride in ((None, None, 1), (fmask, mmask, 2)):
+        grid, block, nb = 3, 64, 50
+        hist_fp = np.zeros(nb * nb + 1, np.uint64)
+        emu.emu_linreg_mattes(P(f.array), P(mv.array), P(fm.array) if fm else None, P(mm.array) if mm else None, P(fs), P(fg), P(ms), P(mg), P(pose),
+                              stride, nb, P(bins), P(hist_fp), None, None, C.c_uint(grid), C.c_uint(block))
+        exp_hist, exp_count = ref.linreg_mattes(f, mv, A, b, init.matrix, m.center, fb, mb, nb, None, fm, mm, stride)
+        got_hist = hist_fp[:-1].astype(np.float64).reshape(nb, nb) / 2.0 ** 32
+        assert float(hist_fp[-1]) == exp_count and np.allclose(got_hist, exp_hist, rtol=0, atol=exp_count * 2.0 ** -32)
+        _, table, _ = linear.mattes_value_and_table(exp_hist)
+        partials = np.zeros((grid * block, 12))
+        emu.emu_linreg_mattes(P(f.array), P(mv.array), P(fm.array) if fm else None, P(mm.array) if mm else None, P(fs), P(fg), P(ms), P(mg), P(pose),
+                              stride, nb, P(bins), None, P(np.ascontiguousarray(table)), P(partials), C.c_uint(grid), C.c_uint(block))
+        _, _, exp_sums = ref.linreg_mattes(f, mv, A, b, init.matrix, m.center, fb, mb, nb, table, fm, mm, stride)
+        assert np.allclose(partials.sum(axis=0), exp_sums, rtol=1e-9, atol=1e-9 * np.abs(exp_sums).max())
