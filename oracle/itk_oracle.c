@@ -8,6 +8,10 @@
  * restatement of the *published* ITK 5.3 filter algorithms, written from the filter semantics, anchored
  * on the reference's call sites.  Nothing here was checked against a running SimpleITK.
  *
+ * EXCEPTION (pinned): orc_signed_maurer and orc_label_contour reproduce, through oracle/comparison_ref.py, the eleven golden numbers
+ * of the reference's own known-answer tests for the surface metrics (platipy/imaging/tests/test_metrics.py:6-67), which were
+ * produced by the real SimpleITK -- see tests/test_reference_golden_metrics.py.
+ *
  * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load
  * this library.  The product (platipy_b200) never imports it.
  *
