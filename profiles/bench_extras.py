@@ -66,7 +66,7 @@ _, info = eng.staple(rng_labels, threshold=1e-4, rescale=True)
 eng.synchronize()
 ms_staple = 1e3 * (time.perf_counter() - t0)
 # ---- rows added in the second session (512 x 512 x 256 each) --------------------------------------------------------
-from platipy_b200 import fusion, label_utils as lu, linear
+from platipy_b200 import comparison, fusion, generation, label_utils as lu, linear
 
 prob = eng.vote_finalize(num, den, dF, 1.0, 1e-4)
 ms_ppi = timed(lambda: eng.process_probability(prob, 0.5), 3)
@@ -82,6 +82,28 @@ eng.synchronize()
 ms_linear = 1e3 * (time.perf_counter() - t0)
 n_eval = sum(len(h) for h in linear.LAST_HISTORY)
 ms_metric = timed(lambda: eng.linreg_meansq(dF, dM, np.eye(3), np.zeros(3), np.eye(3), np.zeros(3), None, None, 4), 10)
+# rows added in the third session of round 1 (not yet measured on a GPU: the round's budget was spent)
+f_bins, m_bins = linear.mattes_bins(*eng.minmax(dF)), linear.mattes_bins(*eng.minmax(dM))
+_, table, _ = linear.mattes_value_and_table(eng.linreg_mattes_histogram(dF, dM, np.eye(3), np.zeros(3), f_bins, m_bins, 50, None, None, 4)[0])
+session3 = {
+    "signed_maurer_distance_map_ms": timed(lambda: eng.signed_maurer_distance_map(labels[0]), 3),
+    "label_contour_ms": timed(lambda: eng.label_contour(labels[0]), 3),
+    "binary_dilate_r3_ms": timed(lambda: eng.binary_dilate(labels[0], lu.ball_offsets((3, 3, 3))), 2),
+    "patch_correlation_3mm_w8_ms": timed(lambda: fusion.compute_weight_map(dF, dM, "patch_correlation", fusion.DEFAULT_VOTE_PARAMS), 2),
+    "linreg_correlation_fullres_stride4_ms": timed(lambda: eng.linreg_correlation(dF, dM, np.eye(3), np.zeros(3), np.eye(3), np.zeros(3), None, None, 4), 10),
+    "linreg_mattes_histogram_fullres_stride4_ms": timed(lambda: eng.linreg_mattes_histogram(dF, dM, np.eye(3), np.zeros(3), f_bins, m_bins, 50, None, None, 4), 10),
+    "linreg_mattes_derivative_fullres_stride4_ms": timed(
+        lambda: eng.linreg_mattes_derivative(dF, dM, np.eye(3), np.zeros(3), np.eye(3), np.zeros(3), f_bins, m_bins, table, None, None, 4), 10),
+    "image_moments_ms": timed(lambda: eng.image_moments(dF), 5),
+}
+t0 = time.perf_counter()
+comparison.compute_surface_metrics(labels[0], labels[1])
+session3["compute_surface_metrics_wall_ms"] = 1e3 * (time.perf_counter() - t0)
+t0 = time.perf_counter()
+generation.generate_field_shift(labels[0], (5, 5, 5), 3)
+eng.synchronize()
+session3["generate_field_shift_wall_ms"] = 1e3 * (time.perf_counter() - t0)
+print(json.dumps(session3))
 extra = {"process_probability_image_ms": ms_ppi, "binary_fillhole_ms": ms_fill, "largest_component_ms": ms_cc,
          "weight_map_block_r5_ms": ms_block, "apply_transform_bspline_f32_ms": ms_bspline, "binary_closing_r3_ms": ms_closing,
          "correct_volume_overlap_5_ms": ms_overlap, "linear_registration_similarity_8_2_1_ms": ms_linear,
