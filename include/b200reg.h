@@ -311,6 +311,9 @@ int b200reg_signed_maurer_distance_map(b200reg_ctx* ctx, const uint8_t* d_mask, 
 /* sitk.LabelContour(image, fullyConnected) (projection.py:33,85; background 0): labelled voxels with a differently labelled
  * neighbour keep their value, everything else becomes 0.  Not in place. */
 int b200reg_label_contour(b200reg_ctx* ctx, const uint8_t* d_in, const int32_t size[3], int fully_connected, uint8_t* d_out);
+/* sitk.LabelContour(image[:, :, k]) for every axial slice k (label/comparison.py:373-374, the added path length): the four
+ * in-plane face neighbours only.  Not in place. */
+int b200reg_label_contour_slicewise(b200reg_ctx* ctx, const uint8_t* d_in, const int32_t size[3], uint8_t* d_out);
 /* sitk.BinaryDilate / sitk.BinaryErode (utils.py:331, generation/dvf.py:269-287): foreground 1, background 0, structuring
  * element as n_offsets (dx, dy, dz) triples in host memory; boundary_to_foreground as in SimpleITK (default false for the
  * dilation, true for the erosion).  Not in place.  Synchronises. */

@@ -157,3 +157,28 @@ def compute_metric_hd(label_a, label_b, auto_crop=True):
     if label_a.array.sum() == 0 or label_b.array.sum() == 0:
         return np.nan
     return hausdorff_distance(label_a, label_b)
+
+
+def compute_apl(label_ref, label_test, distance_threshold_mm=3):
+    # comparison.py:346-387, slice by slice like the reference; the 2-D LabelContour / BinaryDilate are the 3-D restatements on a one-slice volume
+    from .generation_ref import ball
+
+    added = []
+    distance = int(np.ceil(distance_threshold_mm / np.mean(label_ref.GetSpacing()[:2])))
+    for i in range(label_ref.array.shape[0]):
+        ref_slice, test_slice = label_ref.array[i:i + 1], label_test.array[i:i + 1]
+        if int(ref_slice.sum()) + int(test_slice.sum()) == 0:
+            continue
+        ref_contour, test_contour = orc.label_contour(ref_slice, False), orc.label_contour(test_slice, False)
+        if distance_threshold_mm > 0:
+            test_contour = orc.binary_morph(test_contour, ball([distance, distance, 0]), True)
+        added.append(np.where(test_contour == 0, ref_contour, 0).sum())
+    return added
+
+
+def compute_metric_total_apl(label_ref, label_test, distance_threshold_mm=3):
+    return np.sum(compute_apl(label_ref, label_test, distance_threshold_mm)) * np.mean(label_ref.GetSpacing()[:2])
+
+
+def compute_metric_mean_apl(label_ref, label_test, distance_threshold_mm=3):
+    return np.mean(compute_apl(label_ref, label_test, distance_threshold_mm)) * np.mean(label_ref.GetSpacing()[:2])

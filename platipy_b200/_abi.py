@@ -119,6 +119,7 @@ SIGNATURES = {
                                  C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
     "b200reg_signed_maurer_distance_map": (C.c_int, [_P, _P, C.POINTER(Geom), C.c_int, C.c_int, C.c_int, _P]),
     "b200reg_label_contour": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.c_int, _P]),
+    "b200reg_label_contour_slicewise": (C.c_int, [_P, _P, C.POINTER(C.c_int32), _P]),
     "b200reg_binary_dilate": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, C.c_int, _P]),
     "b200reg_binary_erode": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, C.c_int, _P]),
     "b200reg_u8_binary_op": (C.c_int, [_P, _P, _P, C.c_int, _P, C.c_size_t]),

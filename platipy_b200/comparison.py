@@ -12,7 +12,7 @@ Float32 distances, median = centre of the histogram bin -- 128 bins over the dis
 count reaches half).  These are the functions the reference has known-answer tests for (platipy/imaging/tests/test_metrics.py);
 tests/test_gpu_zz_comparison.py asserts the same golden numbers.
 
-The added-path-length metrics (comparison.py:346-431, slice-wise 2-D contours and dilations) are not implemented.
+    compute_apl, compute_metric_total_apl, compute_metric_mean_apl                                comparison.py:346-431
 """
 from __future__ import annotations
 
@@ -211,8 +211,33 @@ def compute_metric_hd(label_a, label_b, auto_crop=True):
     return _hausdorff(eng, a, b)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# added path length
+# ---------------------------------------------------------------------------------------------------------------------
 def compute_apl(label_ref, label_test, distance_threshold_mm=3):
-    raise NotImplementedError("the added-path-length metrics (comparison.py:346-431) are not implemented on the B200 path")
+    """Added path length per axial slice, in voxels (comparison.py:346-387): the contour voxels of the reference that are not
+    within ``distance_threshold_mm`` (in-plane, rounded up to whole voxels) of the test contour.  All slices are processed at once:
+    slice-wise contours, an in-plane disc dilation, MaskNegated; the list holds one count per slice that contains either label."""
+    eng, ref, test = _pair(label_ref, label_test, False)
+    distance = int(np.ceil(distance_threshold_mm / np.mean(ref.GetSpacing()[:2])))
+    ref_contour, test_contour = eng.label_contour_slicewise(ref), eng.label_contour_slicewise(test)
+    if distance_threshold_mm > 0:
+        test_contour = eng.binary_dilate(test_contour, lu.ball_offsets([distance, distance, 0]))  # sitk.BinaryDilate on the 2-D slice: a disc
+    agreement_free = eng.binary_threshold(test_contour, -1.0, 0.5)  # 1 where the (dilated) test contour is 0
+    added_path = eng.mask_image(ref_contour, agreement_free)        # sitk.MaskNegated(ref_contour, test_contour)
+    with torch.cuda.stream(eng.stream):  # plumbing: per-slice sums of three label volumes
+        per_slice = torch.stack([added_path.tensor.sum(dim=(1, 2), dtype=torch.int64), ref.tensor.sum(dim=(1, 2), dtype=torch.int64),
+                                 test.tensor.sum(dim=(1, 2), dtype=torch.int64)]).cpu().numpy()
+    return [per_slice[0, i] for i in range(per_slice.shape[1]) if per_slice[1, i] + per_slice[2, i] != 0]
 
 
-compute_metric_total_apl = compute_metric_mean_apl = compute_apl
+def compute_metric_total_apl(label_ref, label_test, distance_threshold_mm=3):
+    """Total (slice-wise) added path length in mm (comparison.py:390-409)."""
+    added_path_length_list = compute_apl(label_ref, label_test, distance_threshold_mm=distance_threshold_mm)
+    return np.sum(added_path_length_list) * np.mean(label_ref.GetSpacing()[:2])
+
+
+def compute_metric_mean_apl(label_ref, label_test, distance_threshold_mm=3):
+    """Mean (slice-wise) added path length in mm (comparison.py:412-431)."""
+    added_path_length_list = compute_apl(label_ref, label_test, distance_threshold_mm=distance_threshold_mm)
+    return np.mean(added_path_length_list) * np.mean(label_ref.GetSpacing()[:2])

@@ -1149,3 +1149,16 @@ API int b200reg_linreg_mattes_derivative(b200reg_ctx* ctx, const float* d_fixed,
     for (int v = 0; v < MATTES_NV; ++v) h_out[v] = ctx->h_scratch[v];
     return B200REG_OK;
 }
+
+// ---- added path length (label/comparison.py:346-387): LabelContour of every axial slice on its own -------------------------------
+API int b200reg_label_contour_slicewise(b200reg_ctx* ctx, const uint8_t* d_in, const int32_t size[3], uint8_t* d_out)
+{
+    ENTER(ctx);
+    REQUIRE(d_in && d_out && size && size[0] > 0 && size[1] > 0 && size[2] > 0, "invalid argument");
+    REQUIRE(d_in != d_out, "in-place LabelContour is not supported");
+    const size_t n = (size_t)size[0] * size[1] * size[2];
+    label_contour_slicewise_kernel<<<elementwise_blocks(ctx, n, 256), 256, 0, ctx->stream>>>(d_in, size[0], size[1], size[2], d_out);
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}

@@ -165,6 +165,27 @@ __global__ void __launch_bounds__(256) label_contour_kernel(const uint8_t* __res
     }
 }
 
+// sitk.LabelContour applied to every axial slice image[:, :, k] on its own (label/comparison.py:373-374): the four in-plane face
+// neighbours only.
+__global__ void __launch_bounds__(256) label_contour_slicewise_kernel(const uint8_t* __restrict__ in, int nx, int ny, int nz, uint8_t* __restrict__ out)
+{
+    const size_t n = (size_t)nx * ny * nz;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) {
+        const uint8_t v = in[q];
+        uint8_t r = 0;
+        if (v) {
+            const int x = (int)(q % nx), y = (int)((q / nx) % ny);
+            bool edge = false;
+            if (x > 0 && in[q - 1] != v) edge = true;
+            if (x + 1 < nx && in[q + 1] != v) edge = true;
+            if (y > 0 && in[q - nx] != v) edge = true;
+            if (y + 1 < ny && in[q + nx] != v) edge = true;
+            if (edge) r = v;
+        }
+        out[q] = r;
+    }
+}
+
 // itk::BinaryDilateImageFilter / BinaryErodeImageFilter, foreground 1, background 0, structuring element given as offsets
 // (dx, dy, dz).  Voxels that are not foreground keep their value unless the dilation paints them; `boundary_fg`: what lies
 // outside the image counts as foreground (BinaryErode's default, boundaryToForeground = true) or background (BinaryDilate's).

@@ -552,6 +552,12 @@ class Engine:
         _abi.check(self.lib.b200reg_label_contour(self.ctx, mask.ptr, self._size3(mask), int(bool(fully_connected)), C.c_void_p(out.data_ptr())))
         return mask.like(out, np.uint8, False)
 
+    def label_contour_slicewise(self, mask):
+        """sitk.LabelContour of every axial slice on its own (in-plane face neighbours)."""
+        out = self.empty(mask.tensor.shape, np.uint8)
+        _abi.check(self.lib.b200reg_label_contour_slicewise(self.ctx, mask.ptr, self._size3(mask), C.c_void_p(out.data_ptr())))
+        return mask.like(out, np.uint8, False)
+
     def _binary_morph(self, fn, mask, offsets, boundary_to_foreground):
         out = self.empty(mask.tensor.shape, np.uint8)
         offs = np.ascontiguousarray(offsets, dtype=np.int32).reshape(-1, 3)

@@ -118,3 +118,7 @@ EMU_API void emu_image_moments(const float* img, const int* size, const double* 
     for (int r = 0; r < 9; ++r) g.i2p[r] = geo[3 + r];
     emu_launch(image_moments_kernel, grid, block, img, g, partials);
 }
+EMU_API void emu_label_contour_slicewise(const uint8_t* in, int nx, int ny, int nz, uint8_t* out, unsigned grid, unsigned block)
+{
+    emu_launch(label_contour_slicewise_kernel, grid, block, in, nx, ny, nz, out);
+}

@@ -86,5 +86,9 @@ def test_metrics_match_the_oracle_on_irregular_labels(engine):
     da, db = engine.to_device(a), engine.to_device(b)
     assert cmp.compute_metric_dsc(da, db) == cref.compute_metric_dsc(a, b)
     assert np.isclose(cmp.compute_metric_hd(da, db), cref.compute_metric_hd(a, b), rtol=1e-7)
-    with pytest.raises(NotImplementedError):
-        cmp.compute_metric_total_apl(a, b)
+    for thr in (3, 0, 1.5):
+        got_apl, exp_apl = cmp.compute_apl(a, b, thr), cref.compute_apl(a, b, thr)
+        assert [int(v) for v in got_apl] == [int(v) for v in exp_apl] and len(got_apl) > 5
+        assert np.isclose(cmp.compute_metric_total_apl(a, b, thr), cref.compute_metric_total_apl(a, b, thr))
+        assert np.isclose(cmp.compute_metric_mean_apl(a, b, thr), cref.compute_metric_mean_apl(a, b, thr))
+    assert sum(cmp.compute_apl(a, a, 3)) == 0

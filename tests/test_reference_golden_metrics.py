@@ -69,3 +69,26 @@ def test_other_comparison_metrics_are_consistent():
     assert np.isclose(cref.compute_metric_masd(a, b, auto_crop=False), 3.842314521867095)
     assert np.isnan(cref.compute_metric_hd(a, Image(np.zeros_like(a.array), a.GetSpacing())))
     assert 0 < cref.compute_metric_sensitivity(a, b) < 1 and 0 < cref.compute_metric_specificity(a, b) <= 1
+
+
+def test_added_path_length_restatement_and_emulated_slicewise_contour(emu):
+    import ctypes as C
+
+    import scipy.ndimage as ndi
+    from oracle import itk_oracle as orc
+
+    a, b = cube(30, 70), cube(35, 71)
+    # identical labels add nothing; a shifted cube adds the part of the reference outline farther than the threshold
+    assert sum(cref.compute_apl(a, a)) == 0 and len(cref.compute_apl(a, a)) == 40
+    apl = cref.compute_apl(a, b, 3)
+    assert len(apl) == 41 and sum(apl) > 0 and cref.compute_metric_total_apl(a, b, 3) == sum(apl) * 1.0
+    assert sum(cref.compute_apl(a, b, 0)) >= sum(apl)
+    # slices 30..34 hold the reference alone: its whole outline (4 * 40 - 4 voxels) is added path
+    assert all(int(v) == 156 for v in apl[:5])
+    # the slice-wise contour kernel (host emulation) against the per-slice restatement
+    r = np.random.default_rng(3)
+    lab = (ndi.gaussian_filter(r.standard_normal((9, 30, 34)), 2.0) > 0.02).astype(np.uint8)
+    out = np.empty_like(lab)
+    emu.emu_label_contour_slicewise(lab.ctypes.data_as(C.c_void_p), 34, 30, 9, out.ctypes.data_as(C.c_void_p), C.c_uint(3), C.c_uint(64))
+    exp = np.stack([orc.label_contour(lab[i:i + 1], False)[0] for i in range(9)])
+    assert np.array_equal(out, exp) and not np.array_equal(out, orc.label_contour(lab, False))
