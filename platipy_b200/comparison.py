@@ -10,7 +10,7 @@ counts, extrema and the distances AT the contour voxels (a few thousand numbers 
 itk::LabelIntensityStatisticsImageFilter are formed exactly as ITK forms them (float64 mean / unbiased standard deviation of the
 Float32 distances, median = centre of the histogram bin -- 128 bins over the distance map's global range -- where the cumulative
 count reaches half).  These are the functions the reference has known-answer tests for (platipy/imaging/tests/test_metrics.py);
-tests/test_gpu_zz_comparison.py asserts the same golden numbers.
+tests/test_gpu_zzz_session3.py asserts the same golden numbers.
 
     compute_apl, compute_metric_total_apl, compute_metric_mean_apl                                comparison.py:346-431
 """

@@ -222,183 +222,3 @@ def test_iterative_atlas_removal(engine):
     one = iar.run_iar(atlas_set, "HEART", min_best_atlases=8, single_step=True, z_score_statistic="STD", outlier_method="STD")
     assert "A12" not in one and len(one) >= 8
 
-
-def test_patch_correlation_weight_map(engine):
-    """vote_type "patch_correlation" (fusion.py:82-146): one kernel instead of a Python loop of scipy.stats.pearsonr calls.
-    Float64 sums in window order vs numpy's pairwise / BLAS order: the Float32 weight map agrees to the north star's 1e-5."""
-    from oracle import platipy_ref as ref
-    from platipy_b200 import fusion
-    from platipy_b200 import sitk_compat as sk
-    from platipy_b200.synth import synth_pair
-
-    t, m = synth_pair((40, 36, 24), seed=5, spacing=(1.0, 1.0, 2.0))
-    for fn in (lambda x: x + 1, abs, lambda x: 0.5 * x + 1.5):
-        vp = dict(patch_window_mm=12, resampled_voxel_size_mm=3, correlation_function=fn)
-        got, exp = fusion.compute_weight_map(t, m, "patch_correlation", vp), ref.compute_weight_map(t, m, "patch_correlation", vp)
-        assert got.GetPixelID() == sk.sitkFloat32 and got.array.shape == t.array.shape
-        assert np.allclose(got.array, exp.array, rtol=1e-5, atol=1e-6)
-    # a correlation function written against the host image API gets a host image
-    vp["correlation_function"] = lambda x: Image(np.abs(x.array), x.GetSpacing(), x.GetOrigin(), x.GetDirection())
-    got2 = fusion.compute_weight_map(t, m, "patch_correlation", vp)
-    vp["correlation_function"] = abs
-    assert np.array_equal(got2.array, fusion.compute_weight_map(t, m, "patch_correlation", vp).array)
-    # device in -> device out, and the default parameters carry the reference's keys
-    dw = fusion.compute_weight_map(engine.to_device(t), engine.to_device(m), "patch_correlation",
-                                   dict(fusion.DEFAULT_VOTE_PARAMS, patch_window_mm=12, resampled_voxel_size_mm=3))
-    vp["correlation_function"] = lambda x: x + 1
-    assert np.array_equal(engine.to_host(dw).array, fusion.compute_weight_map(t, m, "patch_correlation", vp).array)
-
-
-def test_linear_registration_correlation_metric(engine):
-    """metric="correlation" (linear.py:141-146): the 42 sums of the kernel against the numpy restatement at identical poses, and a
-    registration between images with different intensity scales (functional parity, like the mean-squares tests)."""
-    from oracle import platipy_ref as ref
-    from platipy_b200 import linear
-    from platipy_b200 import sitk_compat as sk
-
-    def blob(size, center, spacing=(1.0, 1.0, 1.0), sig=(7.0, 5.0, 4.0), origin=(0.0, 0.0, 0.0), direction=(1, 0, 0, 0, 1, 0, 0, 0, 1)):
-        nx, ny, nz = size
-        z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
-        p = [x * spacing[0], y * spacing[1], z * spacing[2]]
-        v = sum(((pi - ci) / si) ** 2 for pi, ci, si in zip(p, center, sig))
-        return Image((1000.0 * np.exp(-0.5 * v)).astype(np.float32), spacing, origin, direction)
-
-    rng = np.random.default_rng(9)
-    ang = 0.15
-    rot = (np.cos(ang), -np.sin(ang), 0, np.sin(ang), np.cos(ang), 0, 0, 0, 1.0)
-    f = blob((24, 20, 16), (12.0, 10.0, 8.0), (1.0, 1.2, 1.5))
-    mv = blob((30, 26, 20), (15.0, 13.5, 12.0), (1.1, 1.0, 1.4), origin=(-3.0, 2.0, -1.0), direction=rot)
-    fmask = Image((rng.random(f.array.shape) > 0.3).astype(np.uint8), f.GetSpacing())
-    mmask = Image((rng.random(mv.array.shape) > 0.2).astype(np.uint8), mv.GetSpacing(), mv.GetOrigin(), mv.GetDirection())
-    init = linear.centered_transform_initializer(f, mv)
-    m = linear.make_model("affine")
-    p = m.identity() + 0.02 * rng.standard_normal(m.n)
-    A, b = init.matrix @ m.matrix(p), init.matrix @ m.offset(p) + init.offset
-    df, dm, dfm, dmm = (engine.to_device(i) for i in (f, mv, fmask, mmask))
-    for fm, mm, dfm_, dmm_, stride in ((None, None, None, None, 1), (fmask, None, dfm, None, 3), (fmask, mmask, dfm, dmm, 2)):
-        got = engine.linreg_correlation(df, dm, A, b, init.matrix, m.center, dfm_, dmm_, stride)
-        exp = ref.linreg_correlation(f, mv, A, b, init.matrix, m.center, fm, mm, stride)
-        assert got.shape == (42,) and got[0] == exp[0]
-        assert np.allclose(got, exp, rtol=1e-9, atol=1e-6 * np.abs(exp).max()), stride
-        again = engine.linreg_correlation(df, dm, A, b, init.matrix, m.center, dfm_, dmm_, stride)
-        assert np.array_equal(got, again)  # fixed-order sums: deterministic
-    # moving = 2 * fixed + 100, shifted by (+2, -1.5, +1) mm
-    fixed = blob((48, 40, 32), (24.0, 20.0, 16.0))
-    shifted = blob((48, 40, 32), (26.0, 18.5, 17.0))
-    moving = Image(shifted.array * 2.0 + 100.0, shifted.GetSpacing())
-    for optimiser in ("gradient_descent", "gradient_descent_line_search"):
-        registered, tfm = linear.linear_registration(fixed, moving, reg_method="translation", metric="correlation", optimiser=optimiser,
-                                                     shrink_factors=[2, 1], smooth_sigmas=[1, 0], sampling_rate=0.5, number_of_iterations=60,
-                                                     default_value=100)
-        pt = np.array(tfm.flatten()[0].TransformPoint((24.0, 20.0, 16.0)))
-        for t in tfm.flatten()[1:]:
-            pt = np.array(t.TransformPoint(pt))
-        assert np.allclose(pt, (26.0, 18.5, 17.0), atol=0.3), (optimiser, pt)
-        r = np.corrcoef(registered.array.ravel(), fixed.array.ravel())[0, 1]
-        assert r > 0.995 and min(linear.LAST_HISTORY[-1]) < -0.98
-    with pytest.raises(NotImplementedError):
-        linear.linear_registration(fixed, moving, metric="joint_hist_mi")
-
-
-def test_get_bone_mask(engine):
-    """generation/mask.py:21-47: BinaryThreshold then BinaryMorphologicalClosing with max_hole_size as the kernel radius."""
-    from oracle import platipy_ref as ref
-
-    rng = np.random.default_rng(2)
-    ct = Image((ndi.gaussian_filter(rng.standard_normal((20, 40, 44)), 2.0) * 4000).astype(np.float32), (1.0, 1.0, 2.5))
-    for hole in (2, (1, 2, 1)):
-        got = gen.get_bone_mask(ct, 350, 3500, hole)
-        thr = Image(((ct.array >= 350) & (ct.array <= 3500)).astype(np.uint8), ct.GetSpacing())
-        r = [hole] * 3 if np.isscalar(hole) else list(hole)
-        offs = ball_offsets(r)
-        st = np.zeros((2 * r[2] + 1, 2 * r[1] + 1, 2 * r[0] + 1), bool)
-        st[offs[:, 2] + r[2], offs[:, 1] + r[1], offs[:, 0] + r[0]] = True
-        assert got.array.dtype == np.uint8 and np.array_equal(got.array, ref.binary_morphological_closing(thr, r, st).array)
-        assert got.array.sum() >= thr.array.sum() > 0
-
-
-def test_alignment_registration_with_moments_and_lbfgsb(engine):
-    """alignment_registration(moments=True) (linear.py:23-47: CenteredTransformInitializer MOMENTS) and optimiser="lbfgsb"."""
-    from oracle import platipy_ref as ref
-    from platipy_b200 import linear
-
-    def blob(size, center, spacing=(1.0, 1.0, 1.0), sig=(7.0, 5.0, 4.0), origin=(0.0, 0.0, 0.0)):
-        nx, ny, nz = size
-        z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
-        p = [x * spacing[0], y * spacing[1], z * spacing[2]]
-        v = sum(((pi - ci) / si) ** 2 for pi, ci, si in zip(p, center, sig))
-        return Image((1000.0 * np.exp(-0.5 * v)).astype(np.float32), spacing, origin)
-
-    fixed = blob((48, 40, 32), (24.0, 20.0, 16.0))
-    moving = blob((40, 44, 30), (17.0, 25.0, 13.0), spacing=(1.2, 1.0, 1.1), origin=(5.0, -8.0, 2.0))
-    got = engine.image_moments(engine.to_device(moving))
-    assert np.allclose(got, ref.image_moments(moving), rtol=1e-10)
-    aligned, tfm = linear.alignment_registration(fixed, moving)  # moments=True is the reference's default
-    # fixed blob centre -> moving blob centre (physical): (24, 20, 16) -> origin + (17, 25, 13)
-    assert np.allclose(tfm.TransformPoint((24.0, 20.0, 16.0)), (22.0, 17.0, 15.0), atol=0.25)  # the moving blob is cut by its image border
-    assert aligned.array.dtype == np.float32 and aligned.array.shape == fixed.array.shape
-    assert np.corrcoef(aligned.array.ravel(), fixed.array.ravel())[0, 1] > 0.98
-    with pytest.raises(RuntimeError):
-        linear.alignment_registration(fixed, Image(np.zeros((8, 8, 8), np.float32)))
-    shifted = blob((48, 40, 32), (26.0, 18.5, 17.0))
-    for metric, mv in (("mean_squares", shifted), ("correlation", Image(shifted.array * 2.0 + 100.0, shifted.GetSpacing()))):
-        _, t = linear.linear_registration(fixed, mv, reg_method="translation", metric=metric, optimiser="lbfgsb", shrink_factors=[2, 1],
-                                          smooth_sigmas=[1, 0], sampling_rate=0.5, number_of_iterations=50)
-        pt = np.array((24.0, 20.0, 16.0))
-        for part in t.flatten():
-            pt = np.array(part.TransformPoint(pt))
-        assert np.allclose(pt, (26.0, 18.5, 17.0), atol=0.3), (metric, pt)
-
-
-def test_linear_registration_mattes_mutual_information(engine):
-    """metric="mattes_mi" (linear.py:145-146): histogram and derivative sums against the numpy restatement at identical poses, and
-    a registration of an inverted-contrast pair, which only a mutual-information metric can align."""
-    from oracle import platipy_ref as ref
-    from platipy_b200 import linear
-
-    def blob(size, center, spacing=(1.0, 1.0, 1.0), sig=(7.0, 5.0, 4.0), origin=(0.0, 0.0, 0.0), direction=(1, 0, 0, 0, 1, 0, 0, 0, 1)):
-        nx, ny, nz = size
-        z, y, x = np.meshgrid(np.arange(nz), np.arange(ny), np.arange(nx), indexing="ij")
-        p = [x * spacing[0], y * spacing[1], z * spacing[2]]
-        v = sum(((pi - ci) / si) ** 2 for pi, ci, si in zip(p, center, sig))
-        return Image((1000.0 * np.exp(-0.5 * v)).astype(np.float32), spacing, origin, direction)
-
-    rng = np.random.default_rng(9)
-    ang = 0.15
-    rot = (np.cos(ang), -np.sin(ang), 0, np.sin(ang), np.cos(ang), 0, 0, 0, 1.0)
-    f = blob((24, 20, 16), (12.0, 10.0, 8.0), (1.0, 1.2, 1.5))
-    big = blob((30, 26, 20), (15.0, 13.5, 12.0), (1.1, 1.0, 1.4), origin=(-3.0, 2.0, -1.0), direction=rot)
-    mv = Image((900.0 - big.array).astype(np.float32), big.GetSpacing(), big.GetOrigin(), big.GetDirection())
-    fmask = Image((rng.random(f.array.shape) > 0.3).astype(np.uint8), f.GetSpacing())
-    mmask = Image((rng.random(mv.array.shape) > 0.2).astype(np.uint8), mv.GetSpacing(), mv.GetOrigin(), mv.GetDirection())
-    init = linear.centered_transform_initializer(f, mv)
-    m = linear.make_model("affine")
-    p = m.identity() + 0.02 * rng.standard_normal(m.n)
-    A, b = init.matrix @ m.matrix(p), init.matrix @ m.offset(p) + init.offset
-    df, dm, dfm, dmm = (engine.to_device(i) for i in (f, mv, fmask, mmask))
-    fb, mb = linear.mattes_bins(*engine.minmax(df)), linear.mattes_bins(*engine.minmax(dm))
-    assert np.allclose(fb, linear.mattes_bins(f.array.min(), f.array.max())) and np.allclose(mb, linear.mattes_bins(mv.array.min(), mv.array.max()))
-    for fm, mm, dfm_, dmm_, stride in ((None, None, None, None, 1), (fmask, mmask, dfm, dmm, 2)):
-        hist, count = engine.linreg_mattes_histogram(df, dm, A, b, fb, mb, 50, dfm_, dmm_, stride)
-        exp_hist, exp_count = ref.linreg_mattes(f, mv, A, b, init.matrix, m.center, fb, mb, 50, None, fm, mm, stride)
-        assert count == exp_count and np.allclose(hist, exp_hist, rtol=0, atol=exp_count * 2.0 ** -32)
-        again, _ = engine.linreg_mattes_histogram(df, dm, A, b, fb, mb, 50, dfm_, dmm_, stride)
-        assert np.array_equal(hist, again)  # fixed-point integer atomics: deterministic
-        _, table, _ = linear.mattes_value_and_table(exp_hist)
-        sums = engine.linreg_mattes_derivative(df, dm, A, b, init.matrix, m.center, fb, mb, table, dfm_, dmm_, stride)
-        _, _, exp_sums = ref.linreg_mattes(f, mv, A, b, init.matrix, m.center, fb, mb, 50, table, fm, mm, stride)
-        assert np.allclose(sums, exp_sums, rtol=1e-9, atol=1e-9 * np.abs(exp_sums).max())
-    fixed = blob((48, 40, 32), (24.0, 20.0, 16.0))
-    shifted = blob((48, 40, 32), (26.0, 18.5, 17.0))
-    moving = Image((1000.0 - shifted.array * 0.8).astype(np.float32), shifted.GetSpacing())
-    for optimiser in ("gradient_descent_line_search", "lbfgsb"):
-        _, tfm = linear.linear_registration(fixed, moving, reg_method="translation", metric="mattes_mi", optimiser=optimiser, shrink_factors=[2, 1],
-                                            smooth_sigmas=[1, 0], sampling_rate=0.5, number_of_iterations=50, default_value=1000)
-        pt = np.array((24.0, 20.0, 16.0))
-        for part in tfm.flatten():
-            pt = np.array(part.TransformPoint(pt))
-        assert np.allclose(pt, (26.0, 18.5, 17.0), atol=0.5), (optimiser, pt)
-    with pytest.raises(NotImplementedError):
-        linear.linear_registration(fixed, moving, metric="joint_hist_mi")
-    with pytest.raises(RuntimeError):
-        linear.linear_registration(fixed, Image(np.zeros((8, 8, 8), np.float32)), metric="mattes_mi", shrink_factors=[1], smooth_sigmas=[0])

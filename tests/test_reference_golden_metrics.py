@@ -3,7 +3,7 @@ the oracle.  The eleven golden numbers below were produced by the real SimpleITK
 reproducing them PINS the oracle's restatements of sitk.SignedMaurerDistanceMap, BinaryContour / LabelContour,
 HausdorffDistanceImageFilter and LabelIntensityStatisticsImageFilter against ITK itself -- the single place where this repository
 has golden vectors of the reference to anchor on.  The GPU path is then held to the oracle bit for bit
-(tests/test_gpu_zz_generation.py) and to the same golden numbers (tests/test_gpu_zz_comparison.py)."""
+(tests/test_gpu_zz_generation.py) and to the same golden numbers (tests/test_gpu_zzz_session3.py)."""
 import numpy as np
 
 from oracle import comparison_ref as cref
