@@ -5,6 +5,7 @@ Drop-in replacements for the label utilities the atlas pipeline calls around the
     correct_volume_overlap                            platipy/imaging/label/utils.py:23-58
     paste                                             sitk.Paste as used in multiatlas/run.py:387-404
     binary_morphological_closing                      sitk.BinaryMorphologicalClosing as used in multiatlas/run.py:424
+    get_com                                           platipy/imaging/label/utils.py:61-84
 
 Same arguments and return values; inputs may be host images or ``DeviceImage`` handles (device in -> device out).
 """
@@ -104,6 +105,27 @@ def correct_volume_overlap(binary_label_dict, assign_overlap_to_largest=True):
     binar = [eng.binary_threshold(dev[k], 1e-300, np.inf) for k in ranked]  # s_img > 0
     outs = eng.resolve_overlap(binar)
     return {k: _back(eng, o, binary_label_dict[k]) for k, o in zip(ranked, outs)}
+
+
+def get_com(label, as_int=True, real_coords=False):
+    """Centre of mass of a label image (label/utils.py:61-84; scipy.ndimage.center_of_mass of the array): array order
+    (z, y, x) -- truncated to ints by default --, or the physical point (x, y, z) with ``real_coords``."""
+    eng = Engine.get()
+    d = eng.cast(eng.to_device(label), np.float32)
+    if d.is_vector:
+        raise RuntimeError("a scalar image is expected")
+    # first moments in INDEX space: the moments kernel on the same pixels with an identity geometry
+    on_index_grid = DeviceImage(d.tensor, np.float32, (1.0, 1.0, 1.0), (0.0, 0.0, 0.0), (1, 0, 0, 0, 1, 0, 0, 0, 1), False)
+    m = eng.image_moments(on_index_grid)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        com_xyz = m[1:4] / m[0]  # scipy returns nan for an all-zero image (with a warning), and so does this
+    if real_coords:
+        direction = np.asarray(d.GetDirection(), dtype=np.float64).reshape(3, 3)
+        return tuple(np.asarray(d.GetOrigin()) + direction @ (np.asarray(d.GetSpacing()) * com_xyz))  # TransformContinuousIndexToPhysicalPoint
+    com = tuple(float(v) for v in com_xyz[::-1])
+    if as_int:
+        return [int(i) for i in com]
+    return com
 
 
 def ball_offsets(radius):

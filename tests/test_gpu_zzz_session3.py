@@ -280,3 +280,22 @@ def test_linear_registration_mattes_mutual_information(engine):
         linear.linear_registration(fixed, moving, metric="joint_hist_mi")
     with pytest.raises(RuntimeError):
         linear.linear_registration(fixed, Image(np.zeros((8, 8, 8), np.float32)), metric="mattes_mi", shrink_factors=[1], smooth_sigmas=[0])
+
+
+def test_get_com(engine):
+    """label/utils.py:61-84: scipy.ndimage.center_of_mass in array order, or the physical point."""
+    from platipy_b200 import label_utils as lu
+
+    arr = np.zeros((20, 30, 40), np.uint8)
+    arr[4:11, 10:25, 7:30] = 1
+    arr[12:15, 3:9, 30:38] = 1
+    ang = 0.3
+    rot = (np.cos(ang), -np.sin(ang), 0, np.sin(ang), np.cos(ang), 0, 0, 0, 1.0)
+    lab = Image(arr, (0.9, 1.1, 2.5), (5.0, -3.0, 10.0), rot)
+    exp = ndi.center_of_mass(arr)
+    assert np.allclose(lu.get_com(lab, as_int=False), exp, rtol=1e-12)
+    assert lu.get_com(lab) == [int(v) for v in exp]
+    d = np.asarray(rot).reshape(3, 3)
+    phys = np.asarray(lab.GetOrigin()) + d @ (np.asarray(lab.GetSpacing()) * np.asarray(exp[::-1]))
+    assert np.allclose(lu.get_com(lab, real_coords=True), phys, rtol=1e-12)
+    assert np.allclose(lu.get_com(engine.to_device(lab), as_int=False), exp, rtol=1e-12)
