@@ -76,7 +76,7 @@ API int b200reg_create(int device, void* stream, b200reg_ctx** out)
     if (const char* e = getenv("B200REG_UNFUSED_FORCE")) ctx->unfused_force = (e[0] == '1');
     if (const char* e = getenv("B200REG_STAPLE_VOXELWISE")) ctx->staple_voxelwise = (e[0] == '1');
     if (const char* e = getenv("B200REG_UPDATE_WS")) ctx->update_ws = (e[0] == '1');
-    if (const char* e = getenv("B200REG_ZM_TMA")) ctx->zm_tma = (e[0] != '0');
+    if (const char* e = getenv("B200REG_ZM_TMA")) ctx->zm_tma = atoi(e);
     if (const char* e = getenv("B200REG_UPDATE_BRANCHY")) ctx->update_branchy = (e[0] == '1');
     if (const char* e = getenv("B200REG_ZM_REGADD")) ctx->zm_regadd = (e[0] != '0');
     if (const char* e = getenv("B200REG_UPDATE_SPLIT")) ctx->update_split = (e[0] != '0');

@@ -62,7 +62,7 @@ struct b200reg_ctx {
     bool unfused_force = false;    // B200REG_UNFUSED_FORCE=1: separate warp and force kernels (W through HBM)
     bool staple_voxelwise = false; // B200REG_STAPLE_VOXELWISE=1: per-voxel EM kernels instead of the pattern-histogram EM
     bool update_ws = false;        // B200REG_UPDATE_WS=1: warp-specialised (producer/consumer) fused update kernel
-    bool zm_tma = true;            // B200REG_ZM_TMA=0: stage every tile of the fused smoothing kernel with cp.async instead of TMA bulk copies
+    int zm_tma = 1;                // B200REG_ZM_TMA (builds with -DB200REG_ENABLE_ZM_TMA only): 0 cp.async staging, 1 one TMA bulk copy per tile row, 2 one tensor-map copy per plane tile
     bool update_branchy = false;   // B200REG_UPDATE_BRANCHY=1: first version of the fused update kernel's force phase (per-voxel branches)
     bool zm_regadd = false;        // B200REG_ZM_REGADD=0: add + smooth stages both operands in shared memory (first version)
     bool update_split = true;      // B200REG_UPDATE_SPLIT=0: fused z-marching warp + force kernel instead of the two high-occupancy kernels

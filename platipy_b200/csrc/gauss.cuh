@@ -335,6 +335,57 @@ __device__ __forceinline__ void tma_bulk_g2s(double* smem_dst, const double* gsr
                  : "memory");
 }
 
+#ifdef B200REG_ENABLE_ZM_TMA
+}  // namespace b200
+#include <cuda.h>  // CUtensorMap and the cuTensorMapEncodeTiled prototype (the entry point itself comes from the runtime, no libcuda link)
+namespace b200 {
+// Tensor-map staging (B200REG_ZM_TMA=2): ONE cp.async.bulk.tensor.3d (SASS UTMALDG) per plane tile instead of one bulk copy per tile
+// row.  The field is described to the TMA unit as a 3-D tensor (x, y, component * nz + z) of float64; a tile that lies inside the
+// image in x and y is a box (AW, AH, 1) of it.  Replicated borders cannot be expressed (TMA fills out-of-range elements with
+// zeros), so border tiles keep the cp.async path; z is clamped by the coordinate.
+#define ZM_TMAP_PARAM , const __grid_constant__ CUtensorMap tmap
+#define ZM_TMAP_ARG(m) , m
+constexpr size_t ZM_SMEM_PAD = 128;  // the dynamic shared array is 128-byte aligned in this build
+typedef CUresult (*zm_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                       const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline zm_encode_tiled_fn zm_encode_tiled()
+{
+    static zm_encode_tiled_fn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<zm_encode_tiled_fn>(p);
+    }
+    return fn;
+}
+// false when the geometry cannot be described (odd nx: row pitch not a multiple of 16 bytes) or the driver entry point is missing
+inline bool zm_make_tensor_map(const double* base, int nx, int ny, int nz_total, int box_w, int box_h, CUtensorMap* out)
+{
+    zm_encode_tiled_fn enc = zm_encode_tiled();
+    if (!enc || (nx % 2) != 0 || (reinterpret_cast<uintptr_t>(base) % 16) != 0 || box_w > 256 || box_h > 256) return false;
+    const cuuint64_t dims[3] = { (cuuint64_t)nx, (cuuint64_t)ny, (cuuint64_t)nz_total };
+    const cuuint64_t strides[2] = { (cuuint64_t)nx * sizeof(double), (cuuint64_t)nx * ny * sizeof(double) };
+    const cuuint32_t box[3] = { (cuuint32_t)box_w, (cuuint32_t)box_h, 1u };
+    const cuuint32_t estr[3] = { 1u, 1u, 1u };
+    return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+__device__ __forceinline__ void tma_tensor3d_g2s(double* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(
+                     (unsigned)__cvta_generic_to_shared(smem_dst)),
+                 "l"(reinterpret_cast<unsigned long long>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"((unsigned)__cvta_generic_to_shared(bar))
+                 : "memory");
+}
+#else
+#define ZM_TMAP_PARAM
+#define ZM_TMAP_ARG(m)
+constexpr size_t ZM_SMEM_PAD = 0;
+#endif
+
 // MODE 0: out = G(a).  MODE 1: out = G(a + b), both operands staged with cp.async and added in the x pass.
 // MODE 2: out = G(a + b), the next plane's operands are loaded into registers while the current plane is processed and
 // their sum is what gets staged: one shared buffer less, half the staging writes and x-pass reads of MODE 1.
@@ -344,7 +395,7 @@ __device__ __forceinline__ void tma_bulk_g2s(double* smem_dst, const double* gsr
 template <int R, int RZ, int MODE, int TXW>
 __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, 128 / TXW) conv3d_zm2_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out,
                                                                int nx, int ny, int nz, int zchunk, int nchunks,
-                                                               const __grid_constant__ SmallCoeffs kc, const DemonsCtrl* __restrict__ ctrl, int it, int use_tma)
+                                                               const __grid_constant__ SmallCoeffs kc, const DemonsCtrl* __restrict__ ctrl, int it, int use_tma ZM_TMAP_PARAM)
 {
     if (ctrl && it >= ctrl->halt_iter) return;
     constexpr bool ADD = MODE == 1;     // second operand staged in shared memory
@@ -355,7 +406,12 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, 128 / TXW) conv3d_z
     constexpr int NT = Zm2Threads<R, TXW>::value;
     constexpr int NYZ = 4 * TXW;  // threads that own voxels in the y / z passes
     constexpr int NLD = (NA + NT - 1) / NT;
+#ifdef B200REG_ENABLE_ZM_TMA
+    extern __shared__ __align__(128) double zm_smem128[];  // tensor-map copies need a 128-byte aligned destination
+    double* zm_smem = zm_smem128;
+#else
     extern __shared__ __align__(16) double zm_smem[];
+#endif
     double* Aa = zm_smem;                       // [2][NA]
     double* Ab = zm_smem + 2 * NA;              // [2][NA] (ADD only)
     double* B = zm_smem + (ADD ? 4 : 2) * NA;   // [AH][TX]
@@ -383,10 +439,14 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, 128 / TXW) conv3d_z
     // (cp.async.bulk, completion counted in bytes on an mbarrier), issued by the first AH lanes of the CTA.  Rows
     // clamp in y simply by their source address.  Border tiles keep the per-element cp.async (LDGSTS) path.
     __shared__ __align__(8) unsigned long long full_bar[2];
-#ifdef B200REG_ENABLE_ZM_TMA  // measured slower than the cp.async path (4.46 vs 3.96 ms / iteration): compiled out by default
-    const bool interior = use_tma && x0 - RP >= 0 && x0 + TXW + RP <= nx && (nx % 2) == 0;
+#ifdef B200REG_ENABLE_ZM_TMA  // row-wise bulk copies measured slower than the cp.async path (4.46 vs 3.96 ms / iteration): compiled out by default
+    // use_tma 1: one bulk copy per tile row (tiles interior in x); 2: one tensor-map copy per plane tile (tiles interior in x and y,
+    // one staged operand, staged plane a multiple of 128 bytes)
+    constexpr bool TENSOR_OK = !ADD && !REGADD && (NA * sizeof(double)) % 128 == 0;
+    const bool interior_t = TENSOR_OK && use_tma == 2 && x0 - RP >= 0 && x0 + TXW + RP <= nx && y0 - R >= 0 && y0 + ZM_TY + R <= ny;
+    const bool interior = interior_t || (use_tma == 1 && x0 - RP >= 0 && x0 + TXW + RP <= nx && (nx % 2) == 0);
 #else
-    constexpr bool interior = false;
+    constexpr bool interior = false, interior_t = false;
     (void)use_tma;
 #endif
     if (interior) {
@@ -398,7 +458,7 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, 128 / TXW) conv3d_z
         __syncthreads();
     }
     int row_off = 0;  // TMA path: source offset of this lane's tile row inside a plane
-    if (interior && tid < AH) {
+    if (interior && !interior_t && tid < AH) {
         int gy = y0 - R + tid;
         gy = gy < 0 ? 0 : (gy > ny - 1 ? ny - 1 : gy);
         row_off = gy * nx + (x0 - RP);
@@ -422,6 +482,15 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, 128 / TXW) conv3d_z
     auto stage = [&](int z, int buf) {
         const int zc = z < 0 ? 0 : (z > nz - 1 ? nz - 1 : z);
         const size_t zo = (size_t)zc * plane;
+#ifdef B200REG_ENABLE_ZM_TMA
+        if (interior_t) {
+            if (tid == 0) {
+                mbar_arrive_expect_tx(&full_bar[buf], (unsigned)(AH * AW * sizeof(double)));
+                tma_tensor3d_g2s(Aa + buf * NA, &tmap, x0 - RP, y0 - R, comp * nz + zc, &full_bar[buf]);
+            }
+            return;
+        }
+#endif
         if (interior) {
             if (tid == 0) mbar_arrive_expect_tx(&full_bar[buf], (unsigned)((ADD ? 2 : 1) * AH * AW * sizeof(double)));
             __syncwarp();
@@ -710,27 +779,35 @@ inline int launch_zm2_tx(b200reg_ctx* ctx, const double* a, const double* b, dou
     constexpr int NB = (ZM_TY + 2 * R) * TXW;
     constexpr int NT = Zm2Threads<R, TXW>::value;
     g.x = (nx + TXW - 1) / TXW;
+    int tma_mode = 0;
+#ifdef B200REG_ENABLE_ZM_TMA
+    CUtensorMap tm;
+    memset(&tm, 0, sizeof(tm));
+    tma_mode = ctx->zm_tma;
+    // the tensor map describes operand a: (nx, ny, components * nz) float64, box = one staged plane tile
+    if (tma_mode == 2 && !zm_make_tensor_map(a, nx, ny, nz * (int)(g.z / nchunks), TXW + 2 * RP, ZM_TY + 2 * R, &tm)) tma_mode = 0;
+#endif
     if (b && addout) {
-        constexpr size_t smem = (size_t)(2 * NA + NB) * sizeof(double);
+        constexpr size_t smem = (size_t)(2 * NA + NB) * sizeof(double) + ZM_SMEM_PAD;
         B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, 3, TXW>, smem));
-        conv3d_zm2_kernel<R, RZ, 3, TXW><<<g, NT, smem, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, 0);
+        conv3d_zm2_kernel<R, RZ, 3, TXW><<<g, NT, smem, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, tma_mode == 2 ? 2 : 0 ZM_TMAP_ARG(tm));
         return B200REG_OK;
     }
 #ifdef B200REG_AB_VARIANTS
     if (b && ctx->zm_regadd) {
         constexpr size_t smem = (size_t)(2 * NA + NB) * sizeof(double);
         B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, 2, TXW>, smem));
-        conv3d_zm2_kernel<R, RZ, 2, TXW><<<g, NT, smem, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, 0);
+        conv3d_zm2_kernel<R, RZ, 2, TXW><<<g, NT, smem, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, 0 ZM_TMAP_ARG(tm));
     } else
 #endif
     if (b) {
         constexpr size_t smem = (size_t)(4 * NA + NB) * sizeof(double);
         B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, 1, TXW>, smem));
-        conv3d_zm2_kernel<R, RZ, 1, TXW><<<g, NT, smem, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, ctx->zm_tma ? 1 : 0);
+        conv3d_zm2_kernel<R, RZ, 1, TXW><<<g, NT, smem, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, tma_mode == 1 ? 1 : 0 ZM_TMAP_ARG(tm));
     } else {
-        constexpr size_t smem = (size_t)(2 * NA + NB) * sizeof(double);
+        constexpr size_t smem = (size_t)(2 * NA + NB) * sizeof(double) + ZM_SMEM_PAD;
         B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, 0, TXW>, smem));
-        conv3d_zm2_kernel<R, RZ, 0, TXW><<<g, NT, smem, ctx->stream>>>(a, nullptr, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, ctx->zm_tma ? 1 : 0);
+        conv3d_zm2_kernel<R, RZ, 0, TXW><<<g, NT, smem, ctx->stream>>>(a, nullptr, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, tma_mode ZM_TMAP_ARG(tm));
     }
     return B200REG_OK;
 }
