@@ -1,0 +1,222 @@
+"""TEST INFRASTRUCTURE: a stand-in for ``platipy_b200.engine.Engine`` whose methods are answered by the oracle (and, for the
+windowed correlation, by the kernel source under the host emulation).  It exists for one purpose: the build container has no GPU,
+so host-side glue written there (argument order, composition order, dtypes, representation handling in comparison.py, the
+patch-correlation vote, the metric / optimiser plumbing of linear_registration ...) would otherwise not execute even once before
+the GPU tests run it on a B200.  ``tests/test_session3_glue_on_fake_engine.py`` runs the bodies of the newest GPU tests against this
+stand-in.  It proves nothing about the kernels (those are checked under tests/emu and on the GPU) and nothing in the package can
+reach it: it is installed by monkeypatching ``Engine.get`` inside a test.
+
+"Device" images are ``DeviceImage`` handles around CPU torch tensors; ``stream`` is None, which makes ``torch.cuda.stream(...)`` a
+no-op context."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from oracle import itk_oracle as orc
+from oracle import platipy_ref as ref
+from platipy_b200 import sitk_compat as sk
+from platipy_b200.engine import _DT, DeviceImage
+from platipy_b200.sitk_compat import Image
+
+
+def _arr(d):
+    """numpy view of a scalar device image, or the AoS [z, y, x, 3] copy of a vector one."""
+    a = d.tensor.numpy()
+    if a.dtype != d.np_dtype:
+        a = a.view(d.np_dtype)
+    return np.moveaxis(a, 0, -1) if d.is_vector else a
+
+
+def _img(d):
+    return Image(np.ascontiguousarray(_arr(d)), d.GetSpacing(), d.GetOrigin(), d.GetDirection(), d.is_vector)
+
+
+class _Grid:
+    def __init__(self, src):
+        self.size, self.spacing, self.origin, self.direction = src.GetSize(), src.GetSpacing(), src.GetOrigin(), src.GetDirection()
+
+
+class FakeEngine:
+    stream = None
+    device = torch.device("cpu")
+
+    def __init__(self, emu=None):
+        self.emu = emu
+        self.calls = {}
+
+    def _note(self, name):
+        self.calls[name] = self.calls.get(name, 0) + 1
+
+    # -- plumbing -------------------------------------------------------------------------------------------------------
+    def _wrap(self, arr, like, is_vector=False):
+        arr = np.ascontiguousarray(arr)
+        if is_vector:
+            arr = np.ascontiguousarray(np.moveaxis(arr, -1, 0))
+        return DeviceImage(torch.from_numpy(arr.copy()), arr.dtype, like.GetSpacing(), like.GetOrigin(), like.GetDirection(), is_vector)
+
+    def empty(self, shape, np_dtype):
+        return torch.zeros(tuple(int(s) for s in shape), dtype=_DT[np.dtype(np_dtype)][1])
+
+    zeros = empty
+
+    def synchronize(self):
+        pass
+
+    wait_caller = release_to_caller = synchronize
+
+    def launch_count(self):
+        return 0
+
+    def to_device(self, image):
+        if isinstance(image, DeviceImage):
+            return image
+        image = sk.to_native(image)
+        return self._wrap(image.array, image, image.is_vector)
+
+    def to_host(self, dimg, pinned=True):
+        return _img(dimg)
+
+    # -- elementwise ----------------------------------------------------------------------------------------------------
+    def cast(self, d, np_dtype):
+        self._note("cast")
+        np_dtype = np.dtype(np_dtype)
+        if np_dtype == d.np_dtype:
+            return d
+        return self._wrap(sk.Cast(_img(d), sk.dtype_to_pixel_id(np_dtype, d.is_vector)).array, d, d.is_vector)
+
+    def minmax(self, d):
+        self._note("minmax")
+        a = _arr(d)
+        return float(a.min()), float(a.max())
+
+    def binary_threshold(self, d, lower, upper=255.0):
+        self._note("binary_threshold")
+        a = _arr(d).astype(np.float64)
+        return self._wrap(((a >= lower) & (a <= upper)).astype(np.uint8), d)
+
+    def u8_binary_op(self, a, b, op):
+        self._note("u8_binary_op")
+        fn = (np.bitwise_or, np.bitwise_and, np.add, np.bitwise_xor)[int(op)]
+        return self._wrap(fn(_arr(a), _arr(b)), a)
+
+    def mask_image(self, d, mask, outside_value=0.0):
+        self._note("mask_image")
+        a, m = _arr(d), _arr(mask) != 0
+        if d.is_vector:
+            m = m[..., None]
+        return self._wrap(np.where(m, a, a.dtype.type(outside_value)), d, d.is_vector)
+
+    def divide_scalar(self, d, divisor):
+        self._note("divide_scalar")
+        a = _arr(d)
+        return self._wrap(a / a.dtype.type(divisor), d)
+
+    def scale_shift(self, d, mul=1.0, add=0.0, take_abs=False):
+        self._note("scale_shift")
+        if d.np_dtype not in (np.dtype(np.float32), np.dtype(np.float64)) or d.is_vector:
+            raise TypeError("image arithmetic on the device is implemented for scalar Float32 / Float64 images")
+        a = _arr(d)
+        v = np.abs(a) if take_abs else a
+        return self._wrap(v * a.dtype.type(mul) + a.dtype.type(add), d)
+
+    # -- distance maps, contours, morphology ------------------------------------------------------------------------------
+    def signed_maurer_distance_map(self, mask, inside_is_positive=False, squared_distance=False, use_image_spacing=True):
+        self._note("signed_maurer_distance_map")
+        return self._wrap(orc.signed_maurer_distance_map(_arr(mask), mask.GetSpacing(), inside_is_positive, squared_distance, use_image_spacing), mask)
+
+    def label_contour(self, mask, fully_connected=False):
+        self._note("label_contour")
+        return self._wrap(orc.label_contour(_arr(mask), fully_connected), mask)
+
+    def label_contour_slicewise(self, mask):
+        self._note("label_contour_slicewise")
+        a = _arr(mask)
+        return self._wrap(np.stack([orc.label_contour(a[i:i + 1], False)[0] for i in range(a.shape[0])]), mask)
+
+    def binary_dilate(self, mask, offsets, boundary_to_foreground=False):
+        self._note("binary_dilate")
+        return self._wrap(orc.binary_morph(_arr(mask), offsets, True, boundary_to_foreground), mask)
+
+    def binary_erode(self, mask, offsets, boundary_to_foreground=True):
+        self._note("binary_erode")
+        return self._wrap(orc.binary_morph(_arr(mask), offsets, False, boundary_to_foreground), mask)
+
+    def binary_closing(self, mask, radius, offsets):
+        self._note("binary_closing")
+        r = [int(v) for v in radius]
+        offs = np.asarray(offsets).reshape(-1, 3)
+        st = np.zeros((2 * r[2] + 1, 2 * r[1] + 1, 2 * r[0] + 1), bool)
+        st[offs[:, 2] + r[2], offs[:, 1] + r[1], offs[:, 0] + r[0]] = True
+        return self._wrap(ref.binary_morphological_closing(_img(mask), r, st).array, mask)
+
+    # -- label utilities ------------------------------------------------------------------------------------------------
+    def bounding_box(self, mask):
+        self._note("bounding_box")
+        zz, yy, xx = np.nonzero(_arr(mask))
+        if zz.size == 0:
+            return [2 ** 31 - 1] * 3 + [-1] * 3
+        return [int(xx.min()), int(yy.min()), int(zz.min()), int(xx.max()), int(yy.max()), int(zz.max())]
+
+    def region_copy(self, src, src_index, dst, dst_index, region_size):
+        self._note("region_copy")
+        (sx, sy, sz), (dx, dy, dz), (nx, ny, nz) = src_index, dst_index, region_size
+        for lo, n, size in zip(tuple(src_index) + tuple(dst_index), tuple(region_size) * 2, src.GetSize() + dst.GetSize()):
+            if lo < 0 or n <= 0 or lo + n > size:
+                raise RuntimeError("requested region is (at least partially) outside the largest possible region")
+        dst.tensor[dz:dz + nz, dy:dy + ny, dx:dx + nx] = src.tensor[sz:sz + nz, sy:sy + ny, sx:sx + nx]
+        return dst
+
+    # -- resampling / smoothing -------------------------------------------------------------------------------------------
+    def resample(self, d, out_geom_src=None, transform=None, interpolator=sk.sitkLinear, default_value=0.0):
+        self._note("resample")
+        g = _Grid(out_geom_src if out_geom_src is not None else d)
+        out = ref.resample(_img(d), None, transform, interpolator, default_value, g.size, g.spacing, g.origin, g.direction)
+        return DeviceImage(torch.from_numpy(np.ascontiguousarray(out.array)), out.array.dtype, g.spacing, g.origin, g.direction, False)
+
+    def discrete_gaussian(self, d, variance, maximum_kernel_width=32, maximum_error=0.01, use_image_spacing=True):
+        self._note("discrete_gaussian")
+        var = [float(variance)] * 3 if np.isscalar(variance) else [float(v) for v in variance]
+        return self._wrap(orc.discrete_gaussian_f32(_arr(d), orc.geom_of(_img(d)), var, maximum_kernel_width, maximum_error, use_image_spacing), d)
+
+    # -- reductions behind linear_registration ----------------------------------------------------------------------------
+    def image_moments(self, d):
+        self._note("image_moments")
+        return ref.image_moments(_img(d))
+
+    @staticmethod
+    def _opt(d):
+        return _img(d) if d is not None else None
+
+    def linreg_meansq(self, fixed, moving, total_matrix, total_offset, initial_matrix, center, fixed_mask=None, moving_mask=None, stride=1):
+        self._note("linreg_meansq")
+        return ref.linreg_meansq(_img(fixed), _img(moving), total_matrix, total_offset, initial_matrix, center, self._opt(fixed_mask), self._opt(moving_mask), stride)
+
+    def linreg_correlation(self, fixed, moving, total_matrix, total_offset, initial_matrix, center, fixed_mask=None, moving_mask=None, stride=1):
+        self._note("linreg_correlation")
+        return ref.linreg_correlation(_img(fixed), _img(moving), total_matrix, total_offset, initial_matrix, center, self._opt(fixed_mask),
+                                      self._opt(moving_mask), stride)
+
+    def linreg_mattes_histogram(self, fixed, moving, total_matrix, total_offset, fixed_bins, moving_bins, n_bins=50, fixed_mask=None, moving_mask=None,
+                                stride=1):
+        self._note("linreg_mattes_histogram")
+        return ref.linreg_mattes(_img(fixed), _img(moving), total_matrix, total_offset, np.eye(3), np.zeros(3), fixed_bins, moving_bins, n_bins, None,
+                                 self._opt(fixed_mask), self._opt(moving_mask), stride)
+
+    def linreg_mattes_derivative(self, fixed, moving, total_matrix, total_offset, initial_matrix, center, fixed_bins, moving_bins, table, fixed_mask=None,
+                                 moving_mask=None, stride=1):
+        self._note("linreg_mattes_derivative")
+        return ref.linreg_mattes(_img(fixed), _img(moving), total_matrix, total_offset, initial_matrix, center, fixed_bins, moving_bins, np.asarray(table).shape[0],
+                                 table, self._opt(fixed_mask), self._opt(moving_mask), stride)[2]
+
+    # -- patch correlation: the kernel source itself, under the host emulation ------------------------------------------------
+    def patch_correlation(self, target, moving, window):
+        self._note("patch_correlation")
+        t, m = np.ascontiguousarray(_arr(target), np.float32), np.ascontiguousarray(_arr(moving), np.float32)
+        nz, ny, nx = t.shape
+        out = np.empty(t.shape, np.float64)
+        P = lambda a: a.ctypes.data_as(C.c_void_p)
+        self.emu.emu_patch_correlation(P(t), P(m), nx, ny, nz, int(window[0]), int(window[1]), int(window[2]), P(out), C.c_uint(4), C.c_uint(64))
+        return self._wrap(out, target)

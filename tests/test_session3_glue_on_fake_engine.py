@@ -1,0 +1,45 @@
+"""The bodies of the newest GPU tests (tests/test_gpu_zzz_session3.py), executed on the CPU against tests/fake_engine.py -- an
+Engine stand-in answered by the oracle.  What this checks is the HOST GLUE of the rows written after the round's last GPU minute:
+that comparison.py composes contours / distance maps / statistics the way the reference does (its golden numbers come out through
+the product's own functions), that the patch-correlation vote, the correlation / Mattes metrics, the L-BFGS-B optimiser, the moments
+initialiser, get_bone_mask and get_com pass the right things in the right order.  It says nothing about the kernels (tests/emu and
+the GPU tests do) and the stand-in is reachable only through this file's monkeypatch."""
+import importlib.util
+import os
+
+import pytest
+
+from platipy_b200.engine import Engine
+from tests.fake_engine import FakeEngine
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture()
+def fake(emu, monkeypatch):
+    eng = FakeEngine(emu)
+    monkeypatch.setattr(Engine, "get", classmethod(lambda cls, device=None: eng))
+    return eng
+
+
+@pytest.fixture(scope="module")
+def gpu_tests():
+    spec = importlib.util.spec_from_file_location("gpu_session3_tests", os.path.join(HERE, "test_gpu_zzz_session3.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("name", ["test_surface_dsc", "test_surface_metrics", "test_metrics_match_the_oracle_on_irregular_labels",
+                                  "test_patch_correlation_weight_map", "test_linear_registration_correlation_metric", "test_get_bone_mask",
+                                  "test_alignment_registration_with_moments_and_lbfgsb", "test_linear_registration_mattes_mutual_information",
+                                  "test_get_com"])
+def test_gpu_test_body_on_the_fake_engine(fake, gpu_tests, name):
+    getattr(gpu_tests, name)(fake)
+    assert fake.calls, "the test body did not reach the engine"
+
+
+def test_every_session3_gpu_test_is_covered(gpu_tests):
+    names = sorted(n for n in dir(gpu_tests) if n.startswith("test_"))
+    covered = test_gpu_test_body_on_the_fake_engine.pytestmark[0].args[1]
+    assert names == sorted(covered)
