@@ -115,6 +115,59 @@ def oracle_sample(size, fixed, moving, iters):
     return vox_it / dt / 1e6, dt, st["elapsed_iterations"], orc.num_threads()
 
 
+def run_experiments(timeout_s=120):
+    """A/B of kernel variants that are compiled out of the default library, in CHILD processes (their own CUDA contexts) after
+    every number of the JSON line has been measured: the TMA staging forms of the fused smoothing kernel (row-wise bulk copies,
+    one tensor-map copy per plane tile) against cp.async, via profiles/ab_variants.py, which also reports whether the displacement
+    field is bit-identical.  Only runs when the alternative build platipy_b200/libb200reg_tma.so is present
+    (make -C platipy_b200/csrc OUT=../libb200reg_tma.so EXTRA=-DB200REG_ENABLE_ZM_TMA); bounded by `timeout_s`; any failure is
+    recorded as text and never touches the measured values.  Informational: not part of metric / value / e2e / roofline."""
+    import subprocess
+
+    lib = "libb200reg_tma.so"
+    if not os.path.exists(os.path.join(ROOT, "platipy_b200", lib)):
+        return None
+    specs = ["default=", f"cp_async=B200REG_ZM_TMA=0,lib={lib}", f"tma_rows=B200REG_ZM_TMA=1,lib={lib}", f"tma_tensor=B200REG_ZM_TMA=2,lib={lib}"]
+    out = ""
+    try:
+        # own session: on a timeout the whole process group goes (the harness runs every configuration in a grandchild)
+        proc = subprocess.Popen([sys.executable, os.path.join(ROOT, "profiles", "ab_variants.py")] + specs, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                                text=True, start_new_session=True)
+        try:
+            out, err = proc.communicate(timeout=timeout_s)
+            note = err[-300:] if proc.returncode else None
+        except subprocess.TimeoutExpired:
+            import signal
+
+            os.killpg(proc.pid, signal.SIGKILL)
+            out, err = proc.communicate()
+            note = f"stopped after {timeout_s} s"
+    except Exception as e:  # noqa: BLE001
+        return {"error": repr(e)[:300]}
+    res = {}
+    for l in out.splitlines():  # one line per finished configuration: "<name> {json}"
+        name, _, rest = l.partition(" ")
+        if rest.startswith("{") and name in [sp.split("=")[0] for sp in specs]:
+            try:
+                res[name] = json.loads(rest)
+            except ValueError:
+                pass
+        if l.startswith("AB {"):  # the harness's closing summary also carries the configurations that failed, with the error text
+            try:
+                for k, v in json.loads(l[3:]).items():
+                    res.setdefault(k, v)
+            except ValueError:
+                pass
+    for v in res.values():  # keep the line small
+        if isinstance(v, dict) and "error" in v:
+            v["error"] = str(v["error"])[-240:]
+    exp = {"smoothing_tile_staging_ab": res, "what": "full-resolution ms per iteration and DVF identity of the fused smoothing kernel's staging variants "
+                                                      "(profiles/ab_variants.py, child processes, after the timed regions)"}
+    if note:
+        exp["note"] = note
+    return exp
+
+
 def run_reference(args):
     """--impl reference: the reference's CPU implementation of the path.  SimpleITK/ITK cannot be installed
     offline, so this arm times the oracle port (the C restatement of the ITK filters, OpenMP on all host
@@ -301,6 +354,12 @@ def run_b200(args):
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{it} full-resolution Demons iterations ({size[0]}x{size[1]}x{size[2]}) of the oracle port, {dt:.1f} s; "
                              "CPU restatement of the ITK filters, not SimpleITK"}
+        experiments = None
+        if world == 1 and not args.no_experiments and os.environ.get("B200REG_BENCH_EXPERIMENTS", "1") != "0":
+            try:
+                experiments = run_experiments()
+            except BaseException as e:  # noqa: BLE001 -- nothing here may cost the measured line
+                experiments = {"error": repr(e)[:300]}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(size, world),
                 "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(2 * nvox * 4 * world),
@@ -308,6 +367,8 @@ def run_b200(args):
                 "gpu_launches": int(total_launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
                 "levels": [{"voxels": s["voxels"], "elapsed_iterations": s["elapsed_iterations"], "gpu_ms": s["gpu_ms"], "metric": s["metric"],
                             "rms_change": s["rms_change"]} for s in stats]}
+        if experiments is not None:
+            line["experiments"] = experiments
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -322,6 +383,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, nargs=3, default=[512, 512, 256])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-experiments", action="store_true", help="skip the informational A/B of compiled-out kernel variants")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
