@@ -126,7 +126,7 @@ def run_experiments(timeout_s=120):
 
     lib = "libb200reg_tma.so"
     if not os.path.exists(os.path.join(ROOT, "platipy_b200", lib)):
-        return None
+        return None  # the alternative build is the switch for the whole informational block
     specs = ["default=", f"cp_async=B200REG_ZM_TMA=0,lib={lib}", f"tma_rows=B200REG_ZM_TMA=1,lib={lib}", f"tma_tensor=B200REG_ZM_TMA=2,lib={lib}"]
     out = ""
     try:
@@ -165,6 +165,22 @@ def run_experiments(timeout_s=120):
                                                       "(profiles/ab_variants.py, child processes, after the timed regions)"}
     if note:
         exp["note"] = note
+    # second experiment: copies of one registration overlapping the compute of its neighbours (profiles/exp_pipelined_e2e.py)
+    try:
+        proc = subprocess.Popen([sys.executable, os.path.join(ROOT, "profiles", "exp_pipelined_e2e.py")], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                                text=True, start_new_session=True)
+        try:
+            out, err = proc.communicate(timeout=90)
+            got = [l for l in out.splitlines() if l.startswith("EXP ")]
+            exp["pipelined_e2e"] = json.loads(got[-1][4:]) if got else {"error": (err or out)[-240:]}
+        except subprocess.TimeoutExpired:
+            import signal
+
+            os.killpg(proc.pid, signal.SIGKILL)
+            proc.communicate()
+            exp["pipelined_e2e"] = {"error": "stopped after 90 s"}
+    except Exception as e:  # noqa: BLE001
+        exp["pipelined_e2e"] = {"error": repr(e)[:240]}
     return exp
 
 
