@@ -165,22 +165,25 @@ def run_experiments(timeout_s=120):
                                                       "(profiles/ab_variants.py, child processes, after the timed regions)"}
     if note:
         exp["note"] = note
-    # second experiment: copies of one registration overlapping the compute of its neighbours (profiles/exp_pipelined_e2e.py)
-    try:
-        proc = subprocess.Popen([sys.executable, os.path.join(ROOT, "profiles", "exp_pipelined_e2e.py")], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
-                                text=True, start_new_session=True)
+    # further child scripts, each printing one "EXP {json}" line:
+    #   pipelined_e2e            copies of one registration overlapping the compute of its neighbours
+    #   platipy_default_staging  the headline volume with platipy's own defaults ([8, 4, 1] shrink factors, 10 iterations per level), SURVEY 8d
+    for key, script, cap in (("pipelined_e2e", "exp_pipelined_e2e.py", 90), ("platipy_default_staging", "exp_default_staging.py", 60)):
         try:
-            out, err = proc.communicate(timeout=90)
-            got = [l for l in out.splitlines() if l.startswith("EXP ")]
-            exp["pipelined_e2e"] = json.loads(got[-1][4:]) if got else {"error": (err or out)[-240:]}
-        except subprocess.TimeoutExpired:
-            import signal
+            proc = subprocess.Popen([sys.executable, os.path.join(ROOT, "profiles", script)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
+                                    start_new_session=True)
+            try:
+                out, err = proc.communicate(timeout=cap)
+                got = [l for l in out.splitlines() if l.startswith("EXP ")]
+                exp[key] = json.loads(got[-1][4:]) if got else {"error": (err or out)[-240:]}
+            except subprocess.TimeoutExpired:
+                import signal
 
-            os.killpg(proc.pid, signal.SIGKILL)
-            proc.communicate()
-            exp["pipelined_e2e"] = {"error": "stopped after 90 s"}
-    except Exception as e:  # noqa: BLE001
-        exp["pipelined_e2e"] = {"error": repr(e)[:240]}
+                os.killpg(proc.pid, signal.SIGKILL)
+                proc.communicate()
+                exp[key] = {"error": f"stopped after {cap} s"}
+        except Exception as e:  # noqa: BLE001
+            exp[key] = {"error": repr(e)[:240]}
     return exp
 
 
