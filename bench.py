@@ -115,7 +115,7 @@ def oracle_sample(size, fixed, moving, iters):
     return vox_it / dt / 1e6, dt, st["elapsed_iterations"], orc.num_threads()
 
 
-def run_experiments(timeout_s=120):
+def run_experiments(timeout_s=100):
     """A/B of kernel variants that are compiled out of the default library, in CHILD processes (their own CUDA contexts) after
     every number of the JSON line has been measured: the TMA staging forms of the fused smoothing kernel (row-wise bulk copies,
     one tensor-map copy per plane tile) against cp.async, via profiles/ab_variants.py, which also reports whether the displacement
@@ -168,7 +168,7 @@ def run_experiments(timeout_s=120):
     # further child scripts, each printing one "EXP {json}" line:
     #   pipelined_e2e            copies of one registration overlapping the compute of its neighbours
     #   platipy_default_staging  the headline volume with platipy's own defaults ([8, 4, 1] shrink factors, 10 iterations per level), SURVEY 8d
-    for key, script, cap in (("pipelined_e2e", "exp_pipelined_e2e.py", 90), ("platipy_default_staging", "exp_default_staging.py", 60)):
+    for key, script, cap in (("pipelined_e2e", "exp_pipelined_e2e.py", 60), ("platipy_default_staging", "exp_default_staging.py", 45)):
         try:
             proc = subprocess.Popen([sys.executable, os.path.join(ROOT, "profiles", script)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
                                     start_new_session=True)
