@@ -79,3 +79,33 @@ def test_reference_facing_argument_errors(built):
     assert f.GetStandardDeviations() == (2.0, 2.0, 2.0)
     p = f.params(7)
     assert p.number_of_iterations == 7 and p.max_kernel_width == 30 and p.max_error == 0.1 and p.smooth_update_field == 0
+
+
+def test_generate_random_augmentation_draws_like_the_reference(monkeypatch):
+    """generation/augment.py:86-141: one augmentation per mask, parameters drawn from the reference's ranges; the bone mask is
+    computed from the CT for the contract / expand augmentations (stubbed here: no GPU)."""
+    import random
+
+    import numpy as np
+
+    from platipy_b200 import generation as gen
+    from platipy_b200.sitk_compat import Image
+
+    sentinel = object()
+    monkeypatch.setattr(gen, "get_bone_mask", lambda image: sentinel)
+    random.seed(3)
+    masks = [Image(np.zeros((4, 4, 4), np.uint8), (1.0, 2.0, 2.5)) for _ in range(12)]
+    ct = Image(np.zeros((4, 4, 4), np.float32))
+    augs = gen.generate_random_augmentation(ct, list(masks))
+    assert len(augs) == 12 and {type(a) for a in augs} <= {gen.ShiftAugment, gen.ContractAugment, gen.ExpandAugment}
+    assert len({type(a) for a in augs}) >= 2
+    for a in augs:
+        assert isinstance(a, gen.DeformableAugment) and 3 <= a.gaussian_smooth <= 5
+        if isinstance(a, gen.ShiftAugment):
+            assert -10 <= a.vector_shift[0] <= 10 and a.vector_shift[1] == 10 and -10 <= a.vector_shift[2] <= 10  # (10, 10): the reference's range
+        else:
+            assert a.bone_mask is sentinel
+        if isinstance(a, gen.ContractAugment):  # augment.py:193: millimetres -> negative voxel counts by the mask's spacing
+            assert all(c <= 0 for c in a.contract) and all(isinstance(c, int) for c in a.contract)
+        if isinstance(a, gen.ExpandAugment):
+            assert all(0 <= v <= 10 for v in a.vector_expand)
