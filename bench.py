@@ -168,7 +168,9 @@ def run_experiments(timeout_s=100):
     # further child scripts, each printing one "EXP {json}" line:
     #   pipelined_e2e            copies of one registration overlapping the compute of its neighbours
     #   platipy_default_staging  the headline volume with platipy's own defaults ([8, 4, 1] shrink factors, 10 iterations per level), SURVEY 8d
-    for key, script, cap in (("pipelined_e2e", "exp_pipelined_e2e.py", 60), ("platipy_default_staging", "exp_default_staging.py", 45)):
+    #   session3_rows            device time at the headline size of the entry points added without GPU time in round 1's third session
+    for key, script, cap in (("pipelined_e2e", "exp_pipelined_e2e.py", 60), ("platipy_default_staging", "exp_default_staging.py", 45),
+                             ("session3_rows", "exp_session3_rows.py", 60)):
         try:
             proc = subprocess.Popen([sys.executable, os.path.join(ROOT, "profiles", script)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
                                     start_new_session=True)
