@@ -67,6 +67,7 @@ def test_call_sites_match_the_signatures_they_call():
     modules = {"lu": label_utils, "label_utils": label_utils, "linear": linear, "fusion": fusion, "cmp": comparison, "comparison": comparison,
                "generation": generation, "iar": iar}
     files = glob.glob(os.path.join(ROOT, "platipy_b200", "*.py")) + glob.glob(os.path.join(ROOT, "tests", "test_gpu_*.py")) + \
+        glob.glob(os.path.join(ROOT, "profiles", "exp_*.py")) + \
         [os.path.join(ROOT, "profiles", "bench_extras.py"), os.path.join(ROOT, "bench.py"), os.path.join(ROOT, "__graft_entry__.py")]
     problems, checked = [], 0
     for f in files:
