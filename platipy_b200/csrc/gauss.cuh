@@ -315,16 +315,24 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, u
 }
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
 {
+    // (only reachable in builds with -DB200REG_ENABLE_ZM_TMA)  A transaction count that never completes would spin for ever; after
+    // about two seconds of waiting the kernel traps instead, which turns a hang of an experimental variant into a reported error.
     const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(a), "r"(parity) : "memory");
+    const long long t0 = clock64();
+    for (;;) {
+        unsigned done;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n"
+            : "=r"(done)
+            : "r"(a), "r"(parity)
+            : "memory");
+        if (done) break;
+        if (clock64() - t0 > 4000000000LL) __trap();
+    }
 }
 // one contiguous row global -> shared; size and both addresses are multiples of 16 bytes
 __device__ __forceinline__ void tma_bulk_g2s(double* smem_dst, const double* gsrc, unsigned bytes, unsigned long long* bar)
