@@ -173,6 +173,15 @@ class FakeEngine:
     def resample(self, d, out_geom_src=None, transform=None, interpolator=sk.sitkLinear, default_value=0.0):
         self._note("resample")
         g = _Grid(out_geom_src if out_geom_src is not None else d)
+        if transform is not None:  # displacement-field transforms made on the "device" carry a DeviceImage: hand the oracle a host field
+            parts = []
+            for t in reversed(transform.flatten()):
+                if isinstance(t, sk.DisplacementFieldTransform):
+                    f = t._device_cache[1] if t._device_cache is not None else t.GetDisplacementField()
+                    parts.append(sk.DisplacementFieldTransform(_img(f) if isinstance(f, DeviceImage) else f))
+                else:
+                    parts.append(t)
+            transform = sk.CompositeTransform(parts)
         out = ref.resample(_img(d), None, transform, interpolator, default_value, g.size, g.spacing, g.origin, g.direction)
         return DeviceImage(torch.from_numpy(np.ascontiguousarray(out.array)), out.array.dtype, g.spacing, g.origin, g.direction, False)
 
@@ -210,6 +219,67 @@ class FakeEngine:
         self._note("linreg_mattes_derivative")
         return ref.linreg_mattes(_img(fixed), _img(moving), total_matrix, total_offset, initial_matrix, center, fixed_bins, moving_bins, np.asarray(table).shape[0],
                                  table, self._opt(fixed_mask), self._opt(moving_mask), stride)[2]
+
+    # -- field templates, recursive Gaussian, Demons (generation.py) -------------------------------------------------------------
+    def constant_field(self, grid, vector, mask=None):
+        self._note("constant_field")
+        x, y, z = grid.GetSize()
+        arr = np.zeros((z, y, x, 3)) + np.asarray(vector, dtype=np.float64)
+        if mask is not None:
+            arr = np.where((_arr(mask) != 0)[..., None], arr, 0.0)
+        return self._wrap(arr, grid, True)
+
+    def radial_bend_field(self, mask, reference_index, axis, scale, clip_axis=-1, clip_keep_upper=True):
+        self._note("radial_bend_field")
+        body = _arr(mask) != 0
+        zz, yy, xx = np.nonzero(np.ones_like(body))
+        idx = np.stack([xx, yy, zz], axis=1).reshape(body.shape + (3,))
+        if clip_axis >= 0:
+            c = idx[..., clip_axis]
+            body = body & ((c >= reference_index[clip_axis]) if clip_keep_upper else (c < reference_index[clip_axis]))
+        rel = (idx - np.asarray(reference_index)).astype(np.int64)
+        arr = np.where(body[..., None], np.cross(rel, np.asarray(axis, dtype=np.float64)) * float(scale), 0.0)
+        return self._wrap(arr, mask, True)
+
+    def recursive_gaussian(self, dfield, sigma):
+        self._note("recursive_gaussian")
+        out = orc.recursive_gaussian_vec3(_arr(dfield), orc.geom_of(_img(dfield)), [float(v) for v in sigma])
+        dfield.tensor.copy_(torch.from_numpy(np.ascontiguousarray(np.moveaxis(out, -1, 0))))  # the entry point works in place
+        return dfield
+
+    def multiscale_demons(self, fixed, moving, cfg, initial_field=None, initial_on_fixed_grid=False):
+        self._note("multiscale_demons")
+        n = cfg.n_levels
+        flt = ref.DemonsFilter()
+        flt.SetStandardDeviations(list(cfg.demons.std_dev))
+        flt.SetSmoothDisplacementField(bool(cfg.demons.smooth_displacement_field))
+        flt.SetSmoothUpdateField(bool(cfg.demons.smooth_update_field))
+        stats = []
+        dvf = ref.multiscale_demons(flt, _img(fixed), _img(moving), initial_displacement_field=_img(initial_field) if initial_field is not None else None,
+                                    isotropic_resample=bool(cfg.isotropic_resample), resolution_staging=list(cfg.resolution_staging[:n]),
+                                    smoothing_sigmas=list(cfg.smoothing_sigmas[:n]), iteration_staging=list(cfg.iteration_staging[:n]),
+                                    interp_order=int(cfg.interp_order), level_stats=stats)
+        for st in stats:
+            st["gpu_ms"] = 0.0
+        return self._wrap(dvf.array, fixed, True), stats
+
+    # -- fusion pieces used by iterative atlas removal -----------------------------------------------------------------------------
+    def process_probability(self, d, threshold=0.5):
+        self._note("process_probability")
+        return self._wrap(ref.process_probability_image(_img(d), threshold).array, d)
+
+    def vote_accumulate(self, label, weight, num, den, first):
+        self._note("vote_accumulate")
+        votes = self.__dict__.setdefault("_votes", {})
+        if first:
+            votes[id(num)] = []
+        votes[id(num)].append((_arr(label).copy(), _arr(weight).copy()))
+
+    def vote_finalize(self, num, den, geom_src, smooth_variance, threshold):
+        self._note("vote_finalize")
+        pairs = self._votes.pop(id(num))
+        out = orc.combine_labels_f32([l for l, _ in pairs], [w for _, w in pairs], orc.geom_of(geom_src), smooth_variance, threshold)
+        return DeviceImage(torch.from_numpy(out), np.float32, geom_src.GetSpacing(), geom_src.GetOrigin(), geom_src.GetDirection(), False)
 
     # -- patch correlation: the kernel source itself, under the host emulation ------------------------------------------------
     def patch_correlation(self, target, moving, window):

@@ -39,6 +39,26 @@ def test_gpu_test_body_on_the_fake_engine(fake, gpu_tests, name):
     assert fake.calls, "the test body did not reach the engine"
 
 
+@pytest.fixture(scope="module")
+def generation_tests():
+    spec = importlib.util.spec_from_file_location("gpu_generation_tests", os.path.join(HERE, "test_gpu_zz_generation.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("name,args", [("test_distance_map_helpers_bit_exact", ()), ("test_field_generators_bit_exact", ()),
+                                       ("test_radial_bend_bit_exact", (("z", "inf"),)), ("test_radial_bend_bit_exact", (("y", "post"),)),
+                                       ("test_radial_bend_bit_exact", (("x", "right"),)), ("test_radial_bend_bit_exact", (False,)),
+                                       ("test_generators_with_demons_in_between", ()), ("test_device_in_device_out_and_augmentation", ()),
+                                       ("test_iterative_atlas_removal", ())])
+def test_generation_and_iar_glue_on_the_fake_engine(fake, generation_tests, name, args):
+    """The same for the generators and iterative atlas removal (these did pass on a B200; here they keep the host glue covered by
+    the CPU suite)."""
+    getattr(generation_tests, name)(fake, *args)
+    assert fake.calls
+
+
 def test_every_session3_gpu_test_is_covered(gpu_tests):
     names = sorted(n for n in dir(gpu_tests) if n.startswith("test_"))
     covered = test_gpu_test_body_on_the_fake_engine.pytestmark[0].args[1]
