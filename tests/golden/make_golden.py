@@ -80,6 +80,48 @@ def main_rows():
     print("wrote rows_small.npz", int(mask.array.sum()), roi, acc[:2])
 
 
+PATCH_PARAMS = {"patch_window_mm": 12, "resampled_voxel_size_mm": 3, "correlation_function": lambda x: x + 1}
+
+
+def main_rows3(write=True):
+    """Third fixture: the rows of round 1's third session (distance map, contours, morphology, reg structure, a generated field,
+    the patch-correlation vote, correlation / Mattes sums, surface metrics) on the label and images of demons_small.npz."""
+    from oracle import comparison_ref as cref
+    from oracle import generation_ref as gref
+    from oracle import itk_oracle as orc
+
+    g = np.load(os.path.join(HERE, "demons_small.npz"))
+    spacing, origin = tuple(g["spacing"]), tuple(g["origin"])
+    F, M, L = Image(g["fixed"], spacing, origin), Image(g["moving"], spacing, origin), Image(g["label"], spacing, origin)
+    out = {}
+    out["maurer"] = orc.signed_maurer_distance_map(L.array, spacing)
+    out["contour"] = orc.label_contour(L.array, False)
+    out["dilated"] = gref.binary_dilate(L, (2, 1, 1)).array
+    out["eroded"] = gref.binary_erode(L, (2, 1, 1)).array
+    out["reg_structure"] = gref.convert_mask_to_reg_structure(L, 3).array
+    shifted, _, dvf = gref.generate_field_shift(L, (2.5, -1.9, 1.8), 2)
+    out["shift_mask"], out["shift_dvf"] = shifted.array, dvf.array
+    out["patch_weight"] = ref.compute_weight_map(F, M, "patch_correlation", PATCH_PARAMS).array
+    a = np.array([[0.99, -0.04, 0.01], [0.04, 1.01, 0.0], [0.0, 0.02, 0.98]])
+    b = np.array([1.5, -2.0, 0.7]) + np.array(origin) - a @ np.array(origin)
+    out["lin_matrix"], out["lin_offset"] = a, b
+    out["corr_sums"] = ref.linreg_correlation(F, M, a, b, np.eye(3), np.array(origin), stride=3)
+    fb = (float(F.array.max()) - float(F.array.min())) / 46, float(F.array.min()) / ((float(F.array.max()) - float(F.array.min())) / 46) - 2
+    mb = (float(M.array.max()) - float(M.array.min())) / 46, float(M.array.min()) / ((float(M.array.max()) - float(M.array.min())) / 46) - 2
+    hist, count = ref.linreg_mattes(F, M, a, b, np.eye(3), np.array(origin), fb, mb, stride=3)
+    out["mattes_bins"], out["mattes_hist"], out["mattes_count"] = np.array(fb + mb), hist, np.array(count)
+    other = Image(out["dilated"], spacing, origin)
+    sm = cref.compute_surface_metrics(L, other)
+    out["surface_metric_names"] = np.array(sorted(sm))
+    out["surface_metric_values"] = np.array([float(sm[k]) for k in sorted(sm)])
+    out["apl"] = np.array([int(v) for v in cref.compute_apl(L, other, 1.0)])
+    if write:
+        np.savez_compressed(os.path.join(HERE, "rows3_small.npz"), **out)
+        print("wrote rows3_small.npz", float(np.abs(out["maurer"]).max()), int(out["shift_mask"].sum()), out["surface_metric_values"])
+    return out
+
+
 if __name__ == "__main__":
     main()
     main_rows()
+    main_rows3()

@@ -79,3 +79,23 @@ def test_gpu_matches_row_golden(engine):
     assert lu.label_to_roi(labs["A"], [1, 1, 2.5], return_as_list=True) == [int(v) for v in R["roi"]]
     acc = engine.linreg_meansq(engine.to_device(F), engine.to_device(M), R["lin_matrix"], R["lin_offset"], np.eye(3), np.array(og), None, None, 3)
     assert acc[1] == R["lin_acc"][1] and np.allclose(acc, R["lin_acc"], rtol=1e-9, atol=1e-9 * np.abs(R["lin_acc"]).max())
+
+
+# ---- third fixture: distance maps, contours, morphology, generators, patch correlation, metric sums, surface metrics ----------------
+def test_oracle_reproduces_rows3_golden():
+    """(The GPU counterpart lives in tests/test_gpu_zzz_session3.py with the other tests of these rows.)"""
+    import importlib.util
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    now = mg.main_rows3(write=False)
+    ref3 = np.load(os.path.join(here, "golden", "rows3_small.npz"))
+    assert sorted(now) == sorted(ref3.files)
+    for k in ref3.files:
+        a, b = np.asarray(now[k]), ref3[k]
+        if a.dtype.kind in "fc" and k in ("patch_weight", "corr_sums", "mattes_hist", "surface_metric_values"):  # numpy / scipy reductions
+            assert np.allclose(a, b, rtol=1e-10, atol=1e-12), k
+        else:
+            assert np.array_equal(a, b), k

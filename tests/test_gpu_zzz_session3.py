@@ -299,3 +299,37 @@ def test_get_com(engine):
     phys = np.asarray(lab.GetOrigin()) + d @ (np.asarray(lab.GetSpacing()) * np.asarray(exp[::-1]))
     assert np.allclose(lu.get_com(lab, real_coords=True), phys, rtol=1e-12)
     assert np.allclose(lu.get_com(engine.to_device(lab), as_int=False), exp, rtol=1e-12)
+
+
+def test_gpu_matches_rows3_golden(engine):
+    """The committed fixture of these rows (tests/golden/rows3_small.npz, generated by tests/golden/make_golden.py from the oracle)."""
+    import os
+
+    from platipy_b200 import fusion, linear
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    g, r3 = np.load(os.path.join(here, "golden", "demons_small.npz")), np.load(os.path.join(here, "golden", "rows3_small.npz"))
+    sp, og = tuple(g["spacing"]), tuple(g["origin"])
+    F, M, L = Image(g["fixed"], sp, og), Image(g["moving"], sp, og), Image(g["label"], sp, og)
+    dL = engine.to_device(L)
+    assert np.array_equal(engine.to_host(engine.signed_maurer_distance_map(dL)).array, r3["maurer"])
+    assert np.array_equal(engine.to_host(engine.label_contour(dL)).array, r3["contour"])
+    assert np.array_equal(engine.to_host(engine.binary_dilate(dL, ball_offsets((2, 1, 1)))).array, r3["dilated"])
+    assert np.array_equal(engine.to_host(engine.binary_erode(dL, ball_offsets((2, 1, 1)))).array, r3["eroded"])
+    assert np.array_equal(gen.convert_mask_to_reg_structure(L, 3).array, r3["reg_structure"])
+    shifted, _, dvf = gen.generate_field_shift(L, (2.5, -1.9, 1.8), 2)
+    assert np.array_equal(shifted.array, r3["shift_mask"]) and np.array_equal(dvf.array, r3["shift_dvf"])
+    params = {"patch_window_mm": 12, "resampled_voxel_size_mm": 3, "correlation_function": lambda x: x + 1}
+    assert np.allclose(fusion.compute_weight_map(F, M, "patch_correlation", params).array, r3["patch_weight"], rtol=1e-5, atol=1e-6)
+    dF, dM = engine.to_device(F), engine.to_device(M)
+    sums = engine.linreg_correlation(dF, dM, r3["lin_matrix"], r3["lin_offset"], np.eye(3), np.array(og), None, None, 3)
+    assert sums[0] == r3["corr_sums"][0] and np.allclose(sums, r3["corr_sums"], rtol=1e-9, atol=1e-9 * np.abs(r3["corr_sums"]).max())
+    fb, mb = tuple(r3["mattes_bins"][:2]), tuple(r3["mattes_bins"][2:])
+    assert np.allclose(linear.mattes_bins(*engine.minmax(dF)), fb) and np.allclose(linear.mattes_bins(*engine.minmax(dM)), mb)
+    hist, count = engine.linreg_mattes_histogram(dF, dM, r3["lin_matrix"], r3["lin_offset"], fb, mb, 50, None, None, 3)
+    assert count == float(r3["mattes_count"]) and np.allclose(hist, r3["mattes_hist"], rtol=0, atol=count * 2.0 ** -32)
+    other = Image(r3["dilated"], sp, og)
+    sm = cmp.compute_surface_metrics(L, other)
+    assert sorted(sm) == [str(k) for k in r3["surface_metric_names"]]
+    assert np.allclose([float(sm[k]) for k in sorted(sm)], r3["surface_metric_values"], rtol=1e-10)
+    assert [int(v) for v in cmp.compute_apl(L, other, 1.0)] == [int(v) for v in r3["apl"]]

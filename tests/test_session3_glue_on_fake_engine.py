@@ -33,7 +33,7 @@ def gpu_tests():
 @pytest.mark.parametrize("name", ["test_surface_dsc", "test_surface_metrics", "test_metrics_match_the_oracle_on_irregular_labels",
                                   "test_patch_correlation_weight_map", "test_linear_registration_correlation_metric", "test_get_bone_mask",
                                   "test_alignment_registration_with_moments_and_lbfgsb", "test_linear_registration_mattes_mutual_information",
-                                  "test_get_com"])
+                                  "test_get_com", "test_gpu_matches_rows3_golden"])
 def test_gpu_test_body_on_the_fake_engine(fake, gpu_tests, name):
     getattr(gpu_tests, name)(fake)
     assert fake.calls, "the test body did not reach the engine"
