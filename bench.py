@@ -115,7 +115,7 @@ def oracle_sample(size, fixed, moving, iters):
     return vox_it / dt / 1e6, dt, st["elapsed_iterations"], orc.num_threads()
 
 
-def run_experiments(timeout_s=100):
+def run_experiments(timeout_s=100, budget_s=200):
     """A/B of kernel variants that are compiled out of the default library, in CHILD processes (their own CUDA contexts) after
     every number of the JSON line has been measured: the TMA staging forms of the fused smoothing kernel (row-wise bulk copies,
     one tensor-map copy per plane tile) against cp.async, via profiles/ab_variants.py, which also reports whether the displacement
@@ -124,6 +124,7 @@ def run_experiments(timeout_s=100):
     recorded as text and never touches the measured values.  Informational: not part of metric / value / e2e / roofline."""
     import subprocess
 
+    t_start = time.perf_counter()
     lib = "libb200reg_tma.so"
     if not os.path.exists(os.path.join(ROOT, "platipy_b200", lib)):
         return None  # the alternative build is the switch for the whole informational block
@@ -169,8 +170,14 @@ def run_experiments(timeout_s=100):
     #   pipelined_e2e            copies of one registration overlapping the compute of its neighbours
     #   platipy_default_staging  the headline volume with platipy's own defaults ([8, 4, 1] shrink factors, 10 iterations per level), SURVEY 8d
     #   session3_rows            device time at the headline size of the entry points added without GPU time in round 1's third session
-    for key, script, cap in (("pipelined_e2e", "exp_pipelined_e2e.py", 60), ("platipy_default_staging", "exp_default_staging.py", 45),
-                             ("session3_rows", "exp_session3_rows.py", 60)):
+    #   session3_gpu_tests       the GPU tests of those entry points, run without -x (every outcome is recorded)
+    # The whole block stays inside `budget_s`: a child gets what is left of it, and is skipped when that is under 15 s.
+    for key, script, cap in (("pipelined_e2e", "exp_pipelined_e2e.py", 60), ("session3_gpu_tests", "exp_session3_tests.py", 90),
+                             ("platipy_default_staging", "exp_default_staging.py", 45), ("session3_rows", "exp_session3_rows.py", 60)):
+        cap = int(min(cap, budget_s - (time.perf_counter() - t_start)))
+        if cap < 15:
+            exp[key] = {"skipped": "time budget of the informational block used up"}
+            continue
         try:
             proc = subprocess.Popen([sys.executable, os.path.join(ROOT, "profiles", script)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
                                     start_new_session=True)
