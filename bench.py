@@ -124,10 +124,20 @@ def run_experiments(timeout_s=100, budget_s=200):
     recorded as text and never touches the measured values.  Informational: not part of metric / value / e2e / roofline."""
     import subprocess
 
+    import tempfile
+
     t_start = time.perf_counter()
     lib = "libb200reg_tma.so"
     if not os.path.exists(os.path.join(ROOT, "platipy_b200", lib)):
         return None  # the alternative build is the switch for the whole informational block
+    # once per box: a scaling run repeats the N = 1 command, the informational block need not run again
+    marker = os.path.join(tempfile.gettempdir(), "b200reg_bench_experiments_done")
+    if os.path.exists(marker) and os.environ.get("B200REG_BENCH_EXPERIMENTS") != "force":
+        return {"skipped": "already ran on this box (" + marker + ")"}
+    try:
+        open(marker, "w").write(str(time.time()))
+    except OSError:
+        pass
     specs = ["default=", f"cp_async=B200REG_ZM_TMA=0,lib={lib}", f"tma_rows=B200REG_ZM_TMA=1,lib={lib}", f"tma_tensor=B200REG_ZM_TMA=2,lib={lib}"]
     out = ""
     try:
