@@ -52,6 +52,32 @@ def _back(eng, dimg, like):
 
 
 # ---------------------------------------------------------------------------------------------------------
+# the small helpers of registration/utils.py:22-51 (iteration callbacks, control-point arithmetic)
+# ---------------------------------------------------------------------------------------------------------
+def registration_command_iteration(method):
+    """Print one line per optimiser iteration of a linear registration (utils.py:22-27)."""
+    print("{0:3} = {1:10.5f}".format(method.GetOptimizerIteration(), method.GetMetricValue()))
+
+
+def stage_iteration(method):
+    """Print the number of transform parameters at a stage change (utils.py:30-34)."""
+    print(f"Number of parameters = {method.GetInitialTransform().GetNumberOfParameters()}")
+
+
+def deformable_registration_command_iteration(method):
+    """Print one line per Demons level / iteration event (utils.py:37-41); works with this module's filter object."""
+    print("{0:3} = {1:10.5f}".format(method.GetElapsedIterations(), method.GetMetric()))
+
+
+def control_point_spacing_distance_to_number(image, grid_spacing):
+    """Grid spacing in millimetres -> number of control points per axis (utils.py:44-51)."""
+    image_spacing = np.array(image.GetSpacing())
+    image_size = np.array(image.GetSize())
+    number_points = image_size * image_spacing / np.array(grid_spacing)
+    return (number_points + 0.5).astype(int)
+
+
+# ---------------------------------------------------------------------------------------------------------
 # smooth_and_resample (utils.py:195-267)
 # ---------------------------------------------------------------------------------------------------------
 def smooth_and_resample(image, isotropic_voxel_size_mm=None, shrink_factor=None, smoothing_sigma=None,

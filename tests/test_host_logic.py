@@ -109,3 +109,17 @@ def test_generate_random_augmentation_draws_like_the_reference(monkeypatch):
             assert all(c <= 0 for c in a.contract) and all(isinstance(c, int) for c in a.contract)
         if isinstance(a, gen.ExpandAugment):
             assert all(0 <= v <= 10 for v in a.vector_expand)
+
+
+def test_small_registration_helpers(capsys):
+    import numpy as np
+
+    from platipy_b200 import registration as reg
+    from platipy_b200.sitk_compat import Image
+
+    f = reg.FastSymmetricForcesDemonsRegistrationFilter()
+    f._stats = {"elapsed_iterations": 7, "metric": 12.3456789, "rms_change": 0.1}
+    reg.deformable_registration_command_iteration(f)
+    assert capsys.readouterr().out == "  7 =   12.34568\n"
+    img = Image(np.zeros((10, 20, 40), np.float32), (1.0, 2.0, 2.5))
+    assert list(reg.control_point_spacing_distance_to_number(img, (10.0, 10.0, 10.0))) == [4, 4, 3]
