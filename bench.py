@@ -18,6 +18,9 @@ roofline the full-resolution Demons iteration (the kernels between two iteration
          176 B/voxel/iteration with f64 fields, against MEASURED_PEAKS.json hbm_gbs.
 cpu_baseline / --impl reference: the CPU oracle (the restatement of the ITK filters; SimpleITK itself is
          not installable offline) timed on a bounded sample on all host cores.
+experiments  (optional, N = 1, once per box, --no-experiments to skip) informational measurements taken in child processes AFTER
+         every key above has been measured: A/B of compiled-out kernel variants, a pipelined end-to-end run, platipy's default
+         staging, the newest GPU tests without -x.  Bounded to 200 s; feeds no other key.
 """
 import argparse
 import json
