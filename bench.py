@@ -141,7 +141,8 @@ def run_experiments(timeout_s=100, budget_s=200):
         open(marker, "w").write(str(time.time()))
     except OSError:
         pass
-    specs = ["default=", f"cp_async=B200REG_ZM_TMA=0,lib={lib}", f"tma_rows=B200REG_ZM_TMA=1,lib={lib}", f"tma_tensor=B200REG_ZM_TMA=2,lib={lib}"]
+    specs = ["default=", f"cp_async=B200REG_ZM_TMA=0,lib={lib}", f"tma_rows=B200REG_ZM_TMA=1,lib={lib}", f"tma_tensor=B200REG_ZM_TMA=2,lib={lib}",
+             f"tma_tensor_l2_128=B200REG_ZM_TMA=2,B200REG_ZM_TMA_L2=2,lib={lib}"]
     out = ""
     try:
         # own session: on a timeout the whole process group goes (the harness runs every configuration in a grandchild)

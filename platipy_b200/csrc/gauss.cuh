@@ -378,8 +378,12 @@ inline bool zm_make_tensor_map(const double* base, int nx, int ny, int nz_total,
     const cuuint64_t strides[2] = { (cuuint64_t)nx * sizeof(double), (cuuint64_t)nx * ny * sizeof(double) };
     const cuuint32_t box[3] = { (cuuint32_t)box_w, (cuuint32_t)box_h, 1u };
     const cuuint32_t estr[3] = { 1u, 1u, 1u };
+    // B200REG_ZM_TMA_L2 = 0 (default) | 1 | 2 | 3: L2 promotion of the tensor-map loads (none, 64, 128, 256 bytes)
+    static const int l2 = getenv("B200REG_ZM_TMA_L2") ? atoi(getenv("B200REG_ZM_TMA_L2")) : 0;
+    const CUtensorMapL2promotion promo = l2 == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                         : (l2 == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : (l2 == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE));
     return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+               CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 __device__ __forceinline__ void tma_tensor3d_g2s(double* smem_dst, const CUtensorMap* tmap, int c0, int c1, int c2, unsigned long long* bar)
 {
