@@ -123,7 +123,7 @@ def run_experiments(timeout_s=100, budget_s=200):
     every number of the JSON line has been measured: the TMA staging forms of the fused smoothing kernel (row-wise bulk copies,
     one tensor-map copy per plane tile) against cp.async, via profiles/ab_variants.py, which also reports whether the displacement
     field is bit-identical.  Only runs when the alternative build platipy_b200/libb200reg_tma.so is present
-    (make -C platipy_b200/csrc OUT=../libb200reg_tma.so EXTRA=-DB200REG_ENABLE_ZM_TMA); bounded by `timeout_s`; any failure is
+    (make -C platipy_b200/csrc OUT=../libb200reg_tma.so EXTRA="-DB200REG_ENABLE_ZM_TMA -DB200REG_AB_VARIANTS"); bounded by `timeout_s`; any failure is
     recorded as text and never touches the measured values.  Informational: not part of metric / value / e2e / roofline."""
     import subprocess
 
@@ -141,7 +141,9 @@ def run_experiments(timeout_s=100, budget_s=200):
         open(marker, "w").write(str(time.time()))
     except OSError:
         pass
-    specs = ["default=", f"cp_async=B200REG_ZM_TMA=0,lib={lib}", f"tma_rows=B200REG_ZM_TMA=1,lib={lib}", f"tma_tensor=B200REG_ZM_TMA=2,lib={lib}",
+    # most informative first (the cap may cut the list short); the row-wise bulk copies were already measured slower in round 1
+    specs = ["default=", f"tma_tensor=B200REG_ZM_TMA=2,lib={lib}", f"tma_tensor_tx64=B200REG_ZM_TMA=2,B200REG_ZM_TX32=0,lib={lib}",
+             f"cp_async=B200REG_ZM_TMA=0,lib={lib}", f"cp_async_tx64=B200REG_ZM_TMA=0,B200REG_ZM_TX32=0,lib={lib}",
              f"tma_tensor_l2_128=B200REG_ZM_TMA=2,B200REG_ZM_TMA_L2=2,lib={lib}"]
     out = ""
     try:
