@@ -2,7 +2,7 @@
 windowed correlation, by the kernel source under the host emulation).  It exists for one purpose: the build container has no GPU,
 so host-side glue written there (argument order, composition order, dtypes, representation handling in comparison.py, the
 patch-correlation vote, the metric / optimiser plumbing of linear_registration ...) would otherwise not execute even once before
-the GPU tests run it on a B200.  ``tests/test_session3_glue_on_fake_engine.py`` runs the bodies of the newest GPU tests against this
+the GPU tests run it on a B200.  ``tests/test_host_glue_on_fake_engine.py`` runs the bodies of the newest GPU tests against this
 stand-in.  It proves nothing about the kernels (those are checked under tests/emu and on the GPU) and nothing in the package can
 reach it: it is installed by monkeypatching ``Engine.get`` inside a test.
 
@@ -173,15 +173,9 @@ class FakeEngine:
     def resample(self, d, out_geom_src=None, transform=None, interpolator=sk.sitkLinear, default_value=0.0):
         self._note("resample")
         g = _Grid(out_geom_src if out_geom_src is not None else d)
-        if transform is not None:  # displacement-field transforms made on the "device" carry a DeviceImage: hand the oracle a host field
-            parts = []
-            for t in reversed(transform.flatten()):
-                if isinstance(t, sk.DisplacementFieldTransform):
-                    f = t._device_cache[1] if t._device_cache is not None else t.GetDisplacementField()
-                    parts.append(sk.DisplacementFieldTransform(_img(f) if isinstance(f, DeviceImage) else f))
-                else:
-                    parts.append(t)
-            transform = sk.CompositeTransform(parts)
+        if d.is_vector:
+            return self.resample_vec3(d, out_geom_src if out_geom_src is not None else d, transform, default_value)
+        transform = self._host_transform(transform)  # displacement-field transforms made on the "device" carry a DeviceImage
         out = ref.resample(_img(d), None, transform, interpolator, default_value, g.size, g.spacing, g.origin, g.direction)
         return DeviceImage(torch.from_numpy(np.ascontiguousarray(out.array)), out.array.dtype, g.spacing, g.origin, g.direction, False)
 
@@ -280,6 +274,99 @@ class FakeEngine:
         pairs = self._votes.pop(id(num))
         out = orc.combine_labels_f32([l for l, _ in pairs], [w for _, w in pairs], orc.geom_of(geom_src), smooth_variance, threshold)
         return DeviceImage(torch.from_numpy(out), np.float32, geom_src.GetSpacing(), geom_src.GetOrigin(), geom_src.GetDirection(), False)
+
+    # -- the remaining entry points of the atlas pipeline (multiatlas.py, fusion.py, registration.py) -----------------------------------
+    def _host_transform(self, transform):
+        """sk transform whose displacement fields are host images (device-made transforms carry a DeviceImage)."""
+        if transform is None:
+            return None
+        parts = []
+        for t in reversed(transform.flatten()):
+            if isinstance(t, sk.DisplacementFieldTransform):
+                f = t._device_cache[1] if t._device_cache is not None else t.GetDisplacementField()
+                parts.append(sk.DisplacementFieldTransform(_img(f) if isinstance(f, DeviceImage) else f))
+            else:
+                parts.append(t)
+        return sk.CompositeTransform(parts)
+
+    def resample_batch(self, images, out_geom_src, transform, interpolators, default_values):
+        self._note("resample_batch")
+        return [self.resample(im, out_geom_src, transform, ip, dv) for im, ip, dv in zip(images, interpolators, default_values)]
+
+    def resample_vec3(self, dfield, out_geom_src, transform=None, default_value=0.0):
+        self._note("resample_vec3")
+        g = _Grid(out_geom_src)
+        out = ref.resample(_img(dfield), None, self._host_transform(transform), sk.sitkLinear, default_value, g.size, g.spacing, g.origin, g.direction)
+        return DeviceImage(torch.from_numpy(np.ascontiguousarray(np.moveaxis(out.array, -1, 0))), np.float64, g.spacing, g.origin, g.direction, True)
+
+    def transform_to_dvf(self, transform, grid):
+        self._note("transform_to_dvf")
+        arr = orc.transform_to_dvf(orc.geom_of(grid), ref._chain_of(self._host_transform(transform)))
+        return self._wrap(arr, grid, True)
+
+    def demons_execute(self, fixed, moving, params):
+        self._note("demons_execute")
+        p = orc.demons_params(list(params.std_dev), params.number_of_iterations, list(params.update_std_dev), bool(params.smooth_displacement_field),
+                              bool(params.smooth_update_field), params.max_error, params.max_kernel_width, params.max_rms_error,
+                              params.max_update_step_length, params.intensity_difference_threshold, params.denominator_threshold)
+        f, m = _img(fixed), _img(moving)
+        D, st = orc.demons_execute(f.array, orc.geom_of(f), m.array, orc.geom_of(m), p)
+        st.update(gpu_ms=0.0, voxels=fixed.GetNumberOfPixels())
+        return self._wrap(D, fixed, True), st
+
+    def weight_map(self, target, moving, vote_type, factor=1e12, sigma=2.0, epsilon=1e-5):
+        self._note("weight_map")
+        name = ("unweighted", "global", "local")[int(vote_type)]
+        params = {"factor": factor, "sigma": sigma, "epsilon": epsilon, "normalise": False}
+        return self._wrap(ref.compute_weight_map(_img(target), _img(moving), name, params).array, target)
+
+    def weight_map_block(self, target, moving, radius, factor, gain):
+        self._note("weight_map_block")
+        params = {"factor": factor, "gain": gain, "blockSize": tuple(int(v) for v in radius), "normalise": False}
+        return self._wrap(ref.compute_weight_map(_img(target), _img(moving), "block", params).array, target)
+
+    def normalise_by_max(self, weight, mask=None):
+        self._note("normalise_by_max")
+        out = ref._normalise(_arr(weight).copy(), True if mask is None else _img(mask))
+        weight.tensor.copy_(torch.from_numpy(np.ascontiguousarray(out)))
+        return weight
+
+    def pack_decision(self, label, bit, packed, first):
+        self._note("pack_decision")
+        if first:
+            packed.zero_()
+        packed += (label.tensor != 0).to(packed.dtype) << int(bit)
+
+    def unpack_decision(self, packed, bit, like):
+        self._note("unpack_decision")
+        return like.like(((packed >> int(bit)) & 1).to(torch.uint8), np.uint8, False)
+
+    def staple(self, decisions, confidence_weight=1.0, max_iterations=0xFFFFFFFF, threshold=1e-4, rescale=True):
+        self._note("staple")
+        W, p, q, it = orc.staple([_arr(d) for d in decisions], confidence_weight, max_iterations)
+        if rescale or threshold:
+            W = orc.rescale_threshold_f64(W, threshold)
+        return self._wrap(W, decisions[0]), {"p": list(p), "q": list(q), "elapsed_iterations": int(it)}
+
+    def binary_fillhole(self, d, fully_connected=False):
+        self._note("binary_fillhole")
+        return self._wrap(orc.binary_fillhole(_arr(d)), d)
+
+    def largest_component(self, d, fully_connected=False, want_info=False):
+        self._note("largest_component")
+        out, ncomp, nvox = orc.largest_component(_arr(d))
+        res = self._wrap(out, d)
+        return (res, {"n_components": ncomp, "voxels": nvox}) if want_info else res
+
+    def resolve_overlap(self, labels_ranked):
+        self._note("resolve_overlap")
+        taken = np.zeros(_arr(labels_ranked[0]).shape, bool)
+        outs = []
+        for l in labels_ranked:
+            has = _arr(l) != 0
+            outs.append(self._wrap((has & ~taken).astype(np.uint8), l))
+            taken |= has
+        return outs
 
     # -- patch correlation: the kernel source itself, under the host emulation ------------------------------------------------
     def patch_correlation(self, target, moving, window):

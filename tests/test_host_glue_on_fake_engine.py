@@ -1,5 +1,7 @@
-"""The bodies of the newest GPU tests (tests/test_gpu_zzz_session3.py), executed on the CPU against tests/fake_engine.py -- an
-Engine stand-in answered by the oracle.  What this checks is the HOST GLUE of the rows written after the round's last GPU minute:
+"""Bodies of GPU tests executed on the CPU against tests/fake_engine.py -- an Engine stand-in answered by the oracle -- so that the
+HOST GLUE of the package (everything above the C ABI: run_segmentation, the fusion and label utilities, linear_registration's
+plumbing, the generators, iterative atlas removal, the comparison metrics) is covered by the CPU suite.  It matters most for the
+rows written after the round's last GPU minute (tests/test_gpu_zzz_session3.py), which would otherwise not have executed at all:
 that comparison.py composes contours / distance maps / statistics the way the reference does (its golden numbers come out through
 the product's own functions), that the patch-correlation vote, the correlation / Mattes metrics, the L-BFGS-B optimiser, the moments
 initialiser, get_bone_mask and get_com pass the right things in the right order.  It says nothing about the kernels (tests/emu and
@@ -56,6 +58,34 @@ def test_generation_and_iar_glue_on_the_fake_engine(fake, generation_tests, name
     """The same for the generators and iterative atlas removal (these did pass on a B200; here they keep the host glue covered by
     the CPU suite)."""
     getattr(generation_tests, name)(fake, *args)
+    assert fake.calls
+
+
+def _load(name):
+    spec = importlib.util.spec_from_file_location("gpu_" + name, os.path.join(HERE, name + ".py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+@pytest.mark.parametrize("module,name,args", [
+    ("test_gpu_multiatlas", "test_run_segmentation_matches_oracle_pipeline", ("vote",)),
+    ("test_gpu_multiatlas", "test_run_segmentation_matches_oracle_pipeline", ("staple",)),
+    ("test_gpu_multiatlas", "test_run_segmentation_with_linear_prealignment", ()),
+    ("test_gpu_label_utils", "test_label_to_roi_crop_and_paste", ()),
+    ("test_gpu_label_utils", "test_correct_volume_overlap_bit_exact", ()),
+    ("test_gpu_label_utils", "test_binary_closing_matches_scipy", ()),
+    ("test_gpu_fusion", "test_weight_maps_match_oracle", ()),
+    ("test_gpu_fusion", "test_block_weight_map_and_normalise_match_oracle", ()),
+    ("test_gpu_fusion", "test_combine_labels_bit_exact", ()),
+    ("test_gpu_fusion", "test_staple_matches_oracle", ()),
+    ("test_gpu_morph", "test_process_probability_image_matches_oracle", ()),
+    ("test_gpu_linear", "test_masks_and_argument_errors", ()),
+])
+def test_atlas_pipeline_glue_on_the_fake_engine(fake, module, name, args):
+    """run_segmentation (auto-crop, linear pre-alignment, label propagation, Demons, weight maps, vote / STAPLE exchange, paste back,
+    post-processing) and the label utilities: GPU-verified flows whose host logic the CPU suite keeps covered this way."""
+    getattr(_load(module), name)(fake, *args)
     assert fake.calls
 
 
