@@ -44,6 +44,9 @@ MULTIATLAS_SETTINGS_DEFAULTS = {
 }
 
 
+MUTLIATLAS_SETTINGS_DEFAULTS = MULTIATLAS_SETTINGS_DEFAULTS  # the reference's spelling of the name (multiatlas/run.py:47)
+
+
 def shard_atlases(atlas_ids, rank, world_size):
     """Atlas ids handled by ``rank``: sorted ids, round-robin (atlas a -> rank a mod world)."""
     ids = sorted(atlas_ids)
