@@ -1102,19 +1102,24 @@ API int b200reg_linreg_mattes_histogram(b200reg_ctx* ctx, const float* d_fixed, 
     B200_TRY(mattes_setup(total_matrix, total_offset, nullptr, nullptr, n_bins, fixed_bins, moving_bins, ps, mb));
     const size_t n = nvox(*fixed_geom), nsamples = (n + (size_t)stride - 1) / (size_t)stride;
     const size_t cells = (size_t)n_bins * n_bins;
+    constexpr int REPLICAS = 32;  // histogram copies the blocks spread their atomics over (summed below)
     TempBuf hist;
-    B200_TRY(hist.alloc(ctx, sizeof(unsigned long long) * (cells + 1)));
-    B200_CUDA(cudaMemsetAsync(hist.p, 0, sizeof(unsigned long long) * (cells + 1), ctx->stream));
+    B200_TRY(hist.alloc(ctx, sizeof(unsigned long long) * (REPLICAS * cells + 1)));
+    B200_CUDA(cudaMemsetAsync(hist.p, 0, sizeof(unsigned long long) * (REPLICAS * cells + 1), ctx->stream));
     linreg_mattes_hist_kernel<<<elementwise_blocks(ctx, nsamples, 256), 256, 0, ctx->stream>>>(
-        d_fixed, d_moving, d_fixed_mask, d_moving_mask, make_corr_geom(*fixed_geom), make_corr_geom(*moving_geom), ps, mb, stride, nsamples,
-        hist.as<unsigned long long>(), hist.as<unsigned long long>() + cells);
+        d_fixed, d_moving, d_fixed_mask, d_moving_mask, make_corr_geom(*fixed_geom), make_corr_geom(*moving_geom), ps, mb, stride, nsamples, REPLICAS,
+        hist.as<unsigned long long>(), hist.as<unsigned long long>() + REPLICAS * cells);
     ctx->launches++;
     B200_CHECK_LAUNCH();
-    std::vector<unsigned long long> host(cells + 1);
-    B200_CUDA(cudaMemcpyAsync(host.data(), hist.p, sizeof(unsigned long long) * (cells + 1), cudaMemcpyDeviceToHost, ctx->stream));
+    std::vector<unsigned long long> host(REPLICAS * cells + 1);
+    B200_CUDA(cudaMemcpyAsync(host.data(), hist.p, sizeof(unsigned long long) * (REPLICAS * cells + 1), cudaMemcpyDeviceToHost, ctx->stream));
     B200_CUDA(cudaStreamSynchronize(ctx->stream));
-    for (size_t q = 0; q < cells; ++q) h_hist[q] = (double)host[q] / MATTES_FIXED_POINT;
-    *h_count = (double)host[cells];
+    for (size_t q = 0; q < cells; ++q) {
+        unsigned long long sum = 0;
+        for (int r = 0; r < REPLICAS; ++r) sum += host[(size_t)r * cells + q];
+        h_hist[q] = (double)sum / MATTES_FIXED_POINT;
+    }
+    *h_count = (double)host[REPLICAS * cells];
     return B200REG_OK;
 }
 API int b200reg_linreg_mattes_derivative(b200reg_ctx* ctx, const float* d_fixed, const b200reg_geom* fixed_geom, const float* d_moving,

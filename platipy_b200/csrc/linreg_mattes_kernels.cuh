@@ -50,14 +50,17 @@ __device__ __forceinline__ void mattes_bins(const MattesBins& mb, double fval, d
     mi = mi < lo ? lo : (mi > hi ? hi : mi);
 }
 
-// hist: [n][n] fixed-point weights (zeroed by the caller); count: number of valid samples
+// hist: [replicas][n][n] fixed-point weights (zeroed by the caller); count: number of valid samples.  Neighbouring blocks add into
+// different replicas (block index modulo `replicas`): a CT-like image puts most samples into a handful of bins, and the replicas
+// divide the contention on those addresses; the caller sums them (integers: still exactly associative).
 __global__ void __launch_bounds__(256) linreg_mattes_hist_kernel(const float* __restrict__ F, const float* __restrict__ M, const uint8_t* __restrict__ fmask,
                                                                  const uint8_t* __restrict__ mmask, const __grid_constant__ CorrGeom gf,
                                                                  const __grid_constant__ CorrGeom gm, const __grid_constant__ CorrPose ps,
-                                                                 const __grid_constant__ MattesBins mb, int stride, size_t nsamples,
+                                                                 const __grid_constant__ MattesBins mb, int stride, size_t nsamples, int replicas,
                                                                  unsigned long long* __restrict__ hist, unsigned long long* __restrict__ count)
 {
     unsigned long long local = 0;
+    hist += (size_t)(blockIdx.x % (unsigned)replicas) * mb.n * mb.n;
     for (size_t sidx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; sidx < nsamples; sidx += (size_t)gridDim.x * blockDim.x) {
         LinregPoint pt;
         if (!linreg_sample_point(F, M, fmask, mmask, gf, gm, ps, sidx * (size_t)stride, pt)) continue;

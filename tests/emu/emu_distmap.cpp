@@ -85,9 +85,10 @@ static void unpack(const int* fsize, const double* fgeo, const int* msize, const
     for (int r = 0; r < 9; ++r) { ps.A[r] = pose[r]; ps.Bt[r] = pose[12 + r]; }
     for (int r = 0; r < 3; ++r) { ps.b[r] = pose[9 + r]; ps.c[r] = pose[21 + r]; }
 }
-// bins: n, fixed (bin size, normalised minimum), moving (bin size, normalised minimum); hist: [n * n + 1] integers (weights * 2^32, count last)
+// bins: n, fixed (bin size, normalised minimum), moving (bin size, normalised minimum); hist: [replicas * n * n + 1] integers
+// (weights * 2^32 per replica, count last)
 EMU_API void emu_linreg_mattes(const float* F, const float* M, const uint8_t* fmask, const uint8_t* mmask, const int* fsize, const double* fgeo,
-                               const int* msize, const double* mgeo, const double* pose, int stride, int n_bins, const double* bins,
+                               const int* msize, const double* mgeo, const double* pose, int stride, int n_bins, const double* bins, int replicas,
                                unsigned long long* hist, const double* table, double* partials, unsigned grid, unsigned block)
 {
     CorrGeom gf, gm;
@@ -97,7 +98,9 @@ EMU_API void emu_linreg_mattes(const float* F, const float* M, const uint8_t* fm
     mb.n = n_bins; mb.fbin = bins[0]; mb.fmin = bins[1]; mb.mbin = bins[2]; mb.mmin = bins[3];
     const size_t n = (size_t)gf.nx * gf.ny * gf.nz;
     const size_t nsamples = (n + (size_t)stride - 1) / (size_t)stride;
-    if (hist) emu_launch(linreg_mattes_hist_kernel, grid, block, F, M, fmask, mmask, gf, gm, ps, mb, stride, nsamples, hist, hist + (size_t)n_bins * n_bins);
+    if (hist)
+        emu_launch(linreg_mattes_hist_kernel, grid, block, F, M, fmask, mmask, gf, gm, ps, mb, stride, nsamples, replicas, hist,
+                   hist + (size_t)replicas * n_bins * n_bins);
     if (table) emu_launch(linreg_mattes_deriv_kernel, grid, block, F, M, fmask, mmask, gf, gm, ps, mb, stride, nsamples, table, partials);
 }
 EMU_API void emu_linreg_corr(const float* F, const float* M, const uint8_t* fmask, const uint8_t* mmask, const int* fsize, const double* fgeo,

@@ -358,16 +358,18 @@ def test_emulated_mattes_kernels_match_the_numpy_restatement(emu):
     bins = np.array([fb[0], fb[1], mb[0], mb[1]])
     P = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
     for fm, mm, stride in ((None, None, 1), (fmask, mmask, 2)):
-        grid, block, nb = 3, 64, 50
-        hist_fp = np.zeros(nb * nb + 1, np.uint64)
+        grid, block, nb, replicas = 5, 64, 50, 3  # the blocks spread their atomics over `replicas` histogram copies
+        hist_fp = np.zeros(replicas * nb * nb + 1, np.uint64)
         emu.emu_linreg_mattes(P(f.array), P(mv.array), P(fm.array) if fm else None, P(mm.array) if mm else None, P(fs), P(fg), P(ms), P(mg), P(pose),
-                              stride, nb, P(bins), P(hist_fp), None, None, C.c_uint(grid), C.c_uint(block))
+                              stride, nb, P(bins), replicas, P(hist_fp), None, None, C.c_uint(grid), C.c_uint(block))
         exp_hist, exp_count = ref.linreg_mattes(f, mv, A, b, init.matrix, m.center, fb, mb, nb, None, fm, mm, stride)
-        got_hist = hist_fp[:-1].astype(np.float64).reshape(nb, nb) / 2.0 ** 32
+        per_replica = hist_fp[:-1].reshape(replicas, nb, nb)
+        assert all(per_replica[r].any() for r in range(replicas))
+        got_hist = per_replica.sum(axis=0).astype(np.float64) / 2.0 ** 32
         assert float(hist_fp[-1]) == exp_count and np.allclose(got_hist, exp_hist, rtol=0, atol=exp_count * 2.0 ** -32)
         _, table, _ = linear.mattes_value_and_table(exp_hist)
         partials = np.zeros((grid * block, 12))
         emu.emu_linreg_mattes(P(f.array), P(mv.array), P(fm.array) if fm else None, P(mm.array) if mm else None, P(fs), P(fg), P(ms), P(mg), P(pose),
-                              stride, nb, P(bins), None, P(np.ascontiguousarray(table)), P(partials), C.c_uint(grid), C.c_uint(block))
+                              stride, nb, P(bins), replicas, None, P(np.ascontiguousarray(table)), P(partials), C.c_uint(grid), C.c_uint(block))
         _, _, exp_sums = ref.linreg_mattes(f, mv, A, b, init.matrix, m.center, fb, mb, nb, table, fm, mm, stride)
         assert np.allclose(partials.sum(axis=0), exp_sums, rtol=1e-9, atol=1e-9 * np.abs(exp_sums).max())
