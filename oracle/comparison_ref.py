@@ -47,11 +47,14 @@ def label_intensity_statistics(label_arr, feature, n_bins=128):
 
 
 def hausdorff_distance(label_a, label_b):
-    """itk::HausdorffDistanceImageFilter (UseImageSpacing on): the larger of the two directed distances."""
+    """itk::HausdorffDistanceImageFilter (UseImageSpacing on): the larger of the two directed distances.  ITK's directed filter works
+    on a distance map in ITS real type (double); the Float32 restatement is therefore asked for SQUARED distances -- exact sums of
+    squares for spacings like the reference's test (1, 1, 2) -- and the root is taken in double: sqrt(6) and sqrt(150) come out as
+    the very doubles the reference's test_metrics.py lists."""
     out = []
     for la, lb in ((label_a, label_b), (label_b, label_a)):
-        d = signed_maurer(lb)
-        out.append(float(np.maximum(d[la.array != 0], 0).max()))
+        d2 = signed_maurer(lb, squared_distance=True)
+        out.append(float(np.sqrt(np.float64(np.maximum(d2[la.array != 0], 0).max()))))
     return max(out)
 
 

@@ -152,12 +152,14 @@ def _surface_statistics(eng, a, b):
 
 
 def _hausdorff(eng, a, b):
-    """itk::HausdorffDistanceImageFilter: max over the voxels of one label of max(signed distance to the other, 0), both ways."""
+    """itk::HausdorffDistanceImageFilter: max over the voxels of one label of max(signed distance to the other, 0), both ways.
+    ITK's directed filter keeps its distance map in double; the Float32 map is therefore taken SQUARED (an exact sum of squares for
+    spacings like (1, 1, 2)) and the root of the maximum is formed in double on the host."""
     out = []
     for la, lb in ((a, b), (b, a)):
-        distance = eng.signed_maurer_distance_map(lb, inside_is_positive=False, squared_distance=False, use_image_spacing=True)
+        d2 = eng.signed_maurer_distance_map(lb, inside_is_positive=False, squared_distance=True, use_image_spacing=True)
         # outside la the masked image is 0, so its maximum is max(0, max over la) -- the filter's max(d, 0)
-        out.append(max(0.0, eng.minmax(eng.mask_image(distance, la))[1]))
+        out.append(float(np.sqrt(max(0.0, eng.minmax(eng.mask_image(d2, la))[1]))))
     return max(out)
 
 

@@ -51,7 +51,8 @@ def test_golden_values_to_the_last_digit():
     label_a = cube(30, 70)
     m1, m2 = cref.compute_surface_metrics(label_a, cube(30, 71)), cref.compute_surface_metrics(label_a, cube(35, 71))
     assert m1["meanSurfaceDistance"] == 0.6649174304423457 and m2["meanSurfaceDistance"] == 3.842314521867095
-    assert m1["maximumSurfaceDistance"] == 2.4494898319244385  # sqrt(6) in float32
+    assert m1["maximumSurfaceDistance"] == 2.4494898319244385  # sqrt(6) in float32 (LabelIntensityStatistics on the Float32 map)
+    assert m1["hausdorffDistance"] == 2.449489742783178 and m2["hausdorffDistance"] == 12.24744871391589  # sqrt(6), sqrt(150) in double
     assert abs(m1["sigmaSurfaceDistance"] - 101.78549149738755) < 1e-9 and abs(m2["sigmaSurfaceDistance"] - 392.57229390698296) < 1e-9
     assert cref.compute_surface_dsc(label_a, cube(35, 72)) == 0.39725541227966404
     # the median pins the histogram rule: bin width = global maximum of |distance| / 128, the value is a bin centre
