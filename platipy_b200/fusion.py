@@ -32,6 +32,19 @@ DEFAULT_VOTE_PARAMS = {
 }
 
 
+def mutual_information(arr_a, arr_b, bins=64):
+    """Histogram-based mutual information of two flattened numpy arrays (fusion.py:26-53).  A host utility on host arrays in
+    the reference as well (no image, no ITK filter behind it): the same numpy expression."""
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        p_ab, _, _ = np.histogram2d(arr_a, arr_b, bins=bins, density=True)
+        log_p = np.log(p_ab / np.outer(p_ab.sum(axis=0), p_ab.sum(axis=1)))
+    log_p[~np.isfinite(log_p)] = 0
+    return (p_ab * log_p).sum()
+
+
 def _back(eng, dimg, like):
     if isinstance(like, DeviceImage):
         eng.release_to_caller()
