@@ -219,6 +219,22 @@ int b200reg_binary_threshold(b200reg_ctx* ctx, const void* d_in, int dtype, size
  * all-reduce of the int32 volume equals the bitwise OR, after which every rank holds all decisions. */
 int b200reg_pack_decision(b200reg_ctx* ctx, const uint8_t* d_label, int bit, int32_t* d_packed, size_t n, int first);
 int b200reg_unpack_decision(b200reg_ctx* ctx, const int32_t* d_packed, int bit, uint8_t* d_out, size_t n);
+/* Compact exchange formats of the structure-sharded fusion (multiatlas/run.py:364, fusion.py:205-292):
+ *  - STAPLE: one decision mask per structure, bit a = BinaryThreshold(label of atlas a, 0.5, 255) (fusion.py:217-220).
+ *    packed_dtype B200REG_U8 (<= 8 atlases), B200REG_U16 (<= 16) or B200REG_U32; ranks own disjoint bits, so a SUM
+ *    reduce-scatter over the structure axis is the bitwise OR.  b200reg_staple_packed runs sitk.STAPLE + RescaleIntensity +
+ *    Threshold (fusion.py:223-232) straight from the reduced mask: raters = the bits of holder_mask in ascending order
+ *    (the atlases that hold the structure), at most 16.  h_pq / h_elapsed may be NULL (the call then does not synchronise).
+ *  - unweighted vote: u8 sum of the label values; d_flag (device int32, zeroed by the caller) is raised when a label
+ *    value exceeds 1 -- the caller then falls back to the float32 accumulators of b200reg_vote_accumulate.
+ *    b200reg_vote_finalize_counts = fusion.py:263-288 with num = float(count), den = n_holders. */
+int b200reg_pack_label(b200reg_ctx* ctx, const uint8_t* d_label, int bit, void* d_packed, int packed_dtype, size_t n, int first);
+int b200reg_staple_packed(b200reg_ctx* ctx, const void* d_packed, int packed_dtype, uint32_t holder_mask, size_t n,
+                          double confidence_weight, uint32_t max_iterations, double threshold, int rescale, double* d_out,
+                          double* h_pq, int32_t* h_elapsed);
+int b200reg_count_accumulate(b200reg_ctx* ctx, const uint8_t* d_label, uint8_t* d_counts, size_t n, int first, int32_t* d_flag);
+int b200reg_vote_finalize_counts(b200reg_ctx* ctx, const uint8_t* d_counts, int n_holders, const b200reg_geom* geom,
+                                 double smooth_variance, double threshold, float* d_out);
 /* ---- N14: sitk.STAPLE + RescaleIntensity + Threshold (fusion.py:217-232) --------------------------------- */
 /* d_decisions: n_raters pointers (host array of device pointers) to u8 volumes already binarised
  * (>= 0.5).  d_out: f64.  h_pq (optional): 2*n_raters doubles (p then q).  Synchronises. */

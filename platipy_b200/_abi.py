@@ -96,6 +96,11 @@ SIGNATURES = {
     "b200reg_binary_threshold": (C.c_int, [_P, _P, C.c_int, C.c_size_t, C.c_double, C.c_double, _P]),
     "b200reg_pack_decision": (C.c_int, [_P, _P, C.c_int, _P, C.c_size_t, C.c_int]),
     "b200reg_unpack_decision": (C.c_int, [_P, _P, C.c_int, _P, C.c_size_t]),
+    "b200reg_pack_label": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_size_t, C.c_int]),
+    "b200reg_staple_packed": (C.c_int, [_P, _P, C.c_int, C.c_uint32, C.c_size_t, C.c_double, C.c_uint32, C.c_double, C.c_int, _P,
+                                        C.POINTER(C.c_double), C.POINTER(C.c_int32)]),
+    "b200reg_count_accumulate": (C.c_int, [_P, _P, _P, C.c_size_t, C.c_int, _P]),
+    "b200reg_vote_finalize_counts": (C.c_int, [_P, _P, C.c_int, C.POINTER(Geom), C.c_double, C.c_double, _P]),
     "b200reg_binary_fillhole": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.c_int, _P]),
     "b200reg_largest_component": (C.c_int, [_P, _P, C.POINTER(C.c_int32), C.c_int, _P, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "b200reg_process_probability": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_int32), C.c_double, _P, C.POINTER(C.c_int64)]),

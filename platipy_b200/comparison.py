@@ -67,7 +67,9 @@ def _pair(label_a, label_b, auto_crop):
 def _overlap_counts(eng, a, b):
     """(|A|, |B|, |A and B|, number of voxels) with A, B the non-zero voxels."""
     ba, bb = eng.binary_threshold(a, 1e-300, np.inf), eng.binary_threshold(b, 1e-300, np.inf)
-    return _count(eng, ba), _count(eng, bb), _count(eng, eng.u8_binary_op(ba, bb, _abi.OP_AND)), a.GetNumberOfPixels()
+    # numpy scalars: a zero denominator gives nan / inf with numpy's warning, as the reference's array arithmetic does, not ZeroDivisionError
+    return (np.float64(_count(eng, ba)), np.float64(_count(eng, bb)), np.float64(_count(eng, eng.u8_binary_op(ba, bb, _abi.OP_AND))),
+            np.float64(a.GetNumberOfPixels()))
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -93,7 +95,7 @@ def compute_volume_metrics(label_a, label_b):
     return {
         "DSC": (2.0 * inter) / (na + nb),
         "volumeOverlap": inter * voxel_volume,
-        "fractionOverlap": inter / float(union),
+        "fractionOverlap": inter / union,
         "truePositiveFraction": (1.0 * true_pos) / (true_pos + false_neg),
         "trueNegativeFraction": (1.0 * true_neg) / (true_neg + false_pos),
         "falsePositiveFraction": (1.0 * false_pos) / (true_neg + false_pos),

@@ -621,6 +621,121 @@ API int b200reg_unpack_decision(b200reg_ctx* ctx, const int32_t* d_packed, int b
     return B200REG_OK;
 }
 
+// ---- compact exchange formats of the sharded fusion -------------------------------------------------------------------------
+API int b200reg_pack_label(b200reg_ctx* ctx, const uint8_t* d_label, int bit, void* d_packed, int packed_dtype, size_t n, int first)
+{
+    ENTER(ctx);
+    REQUIRE(d_label && d_packed && bit >= 0, "invalid argument");
+    const int nb = ctx->sm_count * 8;
+    switch (packed_dtype) {
+    case B200REG_U8:
+        REQUIRE(bit < 8, "bit %d does not fit a UInt8 decision mask", bit);
+        pack_label_kernel<uint8_t><<<nb, 256, 0, ctx->stream>>>(d_label, bit, (uint8_t*)d_packed, n, first);
+        break;
+    case B200REG_U16: case B200REG_I16:
+        REQUIRE(bit < 16, "bit %d does not fit a 16-bit decision mask", bit);
+        pack_label_kernel<uint16_t><<<nb, 256, 0, ctx->stream>>>(d_label, bit, (uint16_t*)d_packed, n, first);
+        break;
+    case B200REG_U32: case B200REG_I32:
+        REQUIRE(bit < 31, "bit %d does not fit a 32-bit decision mask (bit 31 is kept clear for signed sums)", bit);
+        pack_label_kernel<uint32_t><<<nb, 256, 0, ctx->stream>>>(d_label, bit, (uint32_t*)d_packed, n, first);
+        break;
+    default: return set_error(B200REG_ERR_ARG, "decision masks are UInt8, UInt16 or UInt32 (got pixel type %d)", packed_dtype);
+    }
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+
+template <typename TM>
+static int staple_packed_t(b200reg_ctx* ctx, const TM* d_packed, uint32_t holder_mask, int n_raters, size_t n, double confidence_weight,
+                           uint32_t max_iterations, double threshold, int rescale, double* d_out, double* h_pq, int32_t* h_elapsed)
+{
+    const int nbins = 1 << n_raters;
+    TempBuf hist, tabw, tabo, state;
+    B200_TRY(hist.alloc(ctx, (size_t)nbins * sizeof(unsigned long long)));
+    B200_TRY(tabw.alloc(ctx, (size_t)nbins * sizeof(double)));
+    B200_TRY(tabo.alloc(ctx, (size_t)nbins * sizeof(double)));
+    B200_TRY(state.alloc(ctx, sizeof(StapleState)));
+    B200_CUDA(cudaMemsetAsync(hist.p, 0, (size_t)nbins * sizeof(unsigned long long), ctx->stream));
+    const size_t shbytes = n_raters <= 12 ? (size_t)nbins * sizeof(unsigned int) : 0;
+    const bool dense = holder_mask == (n_raters >= 32 ? 0xffffffffu : ((1u << n_raters) - 1u));  // holders are bits 0 .. n_raters-1
+    const int nb = ctx->sm_count * 8;
+    if (dense) staple_hist_mask_kernel<TM, true><<<nb, 256, shbytes, ctx->stream>>>(d_packed, holder_mask, n_raters, n, hist.as<unsigned long long>());
+    else staple_hist_mask_kernel<TM, false><<<nb, 256, shbytes, ctx->stream>>>(d_packed, holder_mask, n_raters, n, hist.as<unsigned long long>());
+    staple_em_table_kernel<<<1, 1024, 0, ctx->stream>>>(hist.as<unsigned long long>(), n_raters, confidence_weight, max_iterations, threshold, rescale,
+                                                         tabw.as<double>(), tabo.as<double>(), state.as<StapleState>());
+    if (dense) staple_write_mask_kernel<TM, true><<<nb, 256, 0, ctx->stream>>>(d_packed, holder_mask, tabo.as<double>(), d_out, n);
+    else staple_write_mask_kernel<TM, false><<<nb, 256, 0, ctx->stream>>>(d_packed, holder_mask, tabo.as<double>(), d_out, n);
+    ctx->launches += 3;
+    B200_CHECK_LAUNCH();
+    if (h_pq || h_elapsed) {
+        // the statistics are a convenience: without them the call stays asynchronous
+        StapleState* h_state = nullptr;
+        B200_CUDA(cudaMallocHost(&h_state, sizeof(StapleState)));
+        cudaError_t e = cudaMemcpyAsync(h_state, state.p, sizeof(StapleState), cudaMemcpyDeviceToHost, ctx->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+        if (e == cudaSuccess) {
+            if (h_pq)
+                for (int j = 0; j < n_raters; ++j) {
+                    h_pq[j] = h_state->p[j];
+                    h_pq[n_raters + j] = h_state->q[j];
+                }
+            if (h_elapsed) *h_elapsed = h_state->elapsed;
+        }
+        cudaFreeHost(h_state);
+        B200_CUDA(e);
+    }
+    return B200REG_OK;
+}
+
+API int b200reg_staple_packed(b200reg_ctx* ctx, const void* d_packed, int packed_dtype, uint32_t holder_mask, size_t n, double confidence_weight,
+                              uint32_t max_iterations, double threshold, int rescale, double* d_out, double* h_pq, int32_t* h_elapsed)
+{
+    ENTER(ctx);
+    REQUIRE(d_packed && d_out && n > 0, "invalid argument");
+    const int n_raters = __builtin_popcount(holder_mask);
+    REQUIRE(n_raters >= 1 && n_raters <= STAPLE_PATTERN_MAX, "number of raters %d not in [1, %d] for the packed STAPLE", n_raters, STAPLE_PATTERN_MAX);
+    switch (packed_dtype) {
+    case B200REG_U8:
+        REQUIRE(holder_mask < 256u, "holder mask does not fit a UInt8 decision mask");
+        return staple_packed_t<uint8_t>(ctx, (const uint8_t*)d_packed, holder_mask, n_raters, n, confidence_weight, max_iterations, threshold, rescale, d_out,
+                                        h_pq, h_elapsed);
+    case B200REG_U16: case B200REG_I16:
+        REQUIRE(holder_mask < 65536u, "holder mask does not fit a 16-bit decision mask");
+        return staple_packed_t<uint16_t>(ctx, (const uint16_t*)d_packed, holder_mask, n_raters, n, confidence_weight, max_iterations, threshold, rescale,
+                                         d_out, h_pq, h_elapsed);
+    case B200REG_U32: case B200REG_I32:
+        return staple_packed_t<uint32_t>(ctx, (const uint32_t*)d_packed, holder_mask, n_raters, n, confidence_weight, max_iterations, threshold, rescale,
+                                         d_out, h_pq, h_elapsed);
+    default: return set_error(B200REG_ERR_ARG, "decision masks are UInt8, UInt16 or UInt32 (got pixel type %d)", packed_dtype);
+    }
+}
+
+API int b200reg_count_accumulate(b200reg_ctx* ctx, const uint8_t* d_label, uint8_t* d_counts, size_t n, int first, int32_t* d_flag)
+{
+    ENTER(ctx);
+    REQUIRE(d_label && d_counts && d_flag, "invalid argument");
+    count_accumulate_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_label, d_counts, n, first, d_flag);
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+
+API int b200reg_vote_finalize_counts(b200reg_ctx* ctx, const uint8_t* d_counts, int n_holders, const b200reg_geom* geom, double smooth_variance,
+                                     double threshold, float* d_out)
+{
+    ENTER(ctx);
+    REQUIRE(d_counts && d_out && valid_geom(geom) && n_holders >= 0, "invalid argument");
+    const size_t n = nvox(*geom);
+    TempBuf num;
+    B200_TRY(num.alloc(ctx, n * sizeof(float)));
+    counts_to_prob_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(d_counts, (float)n_holders, num.as<float>(), n);
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    return vote_finalize(ctx, num.as<float>(), nullptr, *geom, smooth_variance, threshold, d_out);
+}
+
 API int b200reg_staple(b200reg_ctx* ctx, const uint8_t* const* d_decisions, int n_raters, size_t n, double confidence_weight,
                        uint32_t max_iterations, double threshold, int rescale, double* d_out, double* h_pq, int32_t* h_elapsed)
 {

@@ -722,4 +722,87 @@ __global__ void staple_write_kernel(const uint32_t* __restrict__ pattern, const 
     for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (size_t)gridDim.x * blockDim.x) out[v] = __ldg(out_tab + pattern[v]);
 }
 
+// ---- compact exchange formats of the sharded fusion ---------------------------------------------------
+// STAPLE: one decision mask per structure, bit a = BinaryThreshold(label of atlas a, 0.5, 255) -- u8 for up to 8 atlases,
+// u16 up to 16, u32 beyond.  Ranks own disjoint bits, so a SUM reduce-scatter of the masks is their bitwise OR.  The mask IS the
+// decision pattern the pattern-histogram EM works on: the owner of a structure goes from the reduced mask to the
+// fused probability in two passes (histogram; table look-up) without unpacking the decisions.
+template <typename TM>
+__global__ void pack_label_kernel(const uint8_t* __restrict__ label, int bit, TM* __restrict__ packed, size_t n, int first)
+{
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) {
+        const TM v = (TM)((TM)(label[q] != 0 ? 1 : 0) << bit);
+        packed[q] = first ? v : (TM)(packed[q] | v);
+    }
+}
+// software pext: the bits of `v` selected by `mask`, packed towards bit 0 in ascending order (rater j = j-th holder atlas)
+__device__ __forceinline__ uint32_t gather_bits(uint32_t v, uint32_t mask)
+{
+    uint32_t out = 0, k = 0;
+    while (mask) {
+        const uint32_t low = mask & (0u - mask);
+        if (v & low) out |= 1u << k;
+        ++k;
+        mask ^= low;
+    }
+    return out;
+}
+template <typename TM, bool DENSE>
+__global__ void __launch_bounds__(256) staple_hist_mask_kernel(const TM* __restrict__ packed, uint32_t holder_mask, int n_raters, size_t n,
+                                                                unsigned long long* __restrict__ hist)
+{
+    extern __shared__ unsigned int shist[];
+    const int nbins = 1 << n_raters;
+    const bool priv = n_raters <= 12;
+    if (priv) {
+        for (int b = threadIdx.x; b < nbins; b += blockDim.x) shist[b] = 0;
+        __syncthreads();
+    }
+    unsigned long long zero_count = 0;
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t raw = (uint32_t)packed[v];
+        const uint32_t pat = DENSE ? (raw & holder_mask) : gather_bits(raw, holder_mask);
+        if (pat == 0) ++zero_count;  // the all-background pattern dominates: counted in a register
+        else if (priv) atomicAdd(&shist[pat], 1u);
+        else atomicAdd(&hist[pat], 1ull);
+    }
+    for (int o = 16; o > 0; o >>= 1) zero_count += __shfl_down_sync(0xffffffffu, zero_count, o);
+    if ((threadIdx.x & 31) == 0 && zero_count) atomicAdd(&hist[0], zero_count);
+    if (priv) {
+        __syncthreads();
+        for (int b = threadIdx.x; b < nbins; b += blockDim.x)
+            if (shist[b]) atomicAdd(&hist[b], (unsigned long long)shist[b]);
+    }
+}
+template <typename TM, bool DENSE>
+__global__ void staple_write_mask_kernel(const TM* __restrict__ packed, uint32_t holder_mask, const double* __restrict__ out_tab,
+                                         double* __restrict__ out, size_t n)
+{
+    for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t raw = (uint32_t)packed[v];
+        out[v] = __ldg(out_tab + (DENSE ? (raw & holder_mask) : gather_bits(raw, holder_mask)));
+    }
+}
+
+// Unweighted vote (fusion.py:253-276 with every weight map == 1): num = sum_a float(L_a) is a small integer, so the float32
+// accumulation of the reference is exact and, for binary labels and up to 255 atlases, a u8 count carries the same information
+// in a quarter of the bytes (NCCL reduces 8-bit integers natively; it has no 16-bit integer type); den = number of atlases
+// holding the structure, known on the host.  A label value above 1 raises `*flag`: the caller then takes the float32 path.
+__global__ void count_accumulate_kernel(const uint8_t* __restrict__ label, uint8_t* __restrict__ counts, size_t n, int first, int* __restrict__ flag)
+{
+    bool big = false;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) {
+        const uint8_t v = label[q];
+        big |= v > 1;
+        counts[q] = first ? v : (uint8_t)(counts[q] + v);
+    }
+    if (__any_sync(0xffffffffu, big) && (threadIdx.x & 31) == 0) atomicOr(flag, 1);
+}
+__global__ void counts_to_prob_kernel(const uint8_t* __restrict__ counts, float den, float* __restrict__ out, size_t n)
+{
+    // the guarded division of vote_divide_kernel, with num = float(count) and a constant den
+    const float d = den == 0.0f ? 1.0f : den;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) out[q] = (float)counts[q] / d;
+}
+
 }  // namespace b200

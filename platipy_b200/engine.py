@@ -25,6 +25,7 @@ _DT = {
     np.dtype(np.int64): (6, torch.int64), np.dtype(np.uint64): (7, torch.int64),
     np.dtype(np.float32): (8, torch.float32), np.dtype(np.float64): (9, torch.float64),
 }
+_MASK_DT = {1: 1, 2: 3, 4: 5}  # element size of a decision mask -> b200reg dtype id (UInt8, UInt16, UInt32)
 _SIGNED_VIEW = {np.dtype(np.uint16): np.int16, np.dtype(np.uint32): np.int32, np.dtype(np.uint64): np.int64}
 
 
@@ -630,6 +631,39 @@ class Engine:
         out = self.empty(packed.shape, np.uint8)
         _abi.check(self.lib.b200reg_unpack_decision(self.ctx, C.c_void_p(packed.data_ptr()), int(bit), C.c_void_p(out.data_ptr()), packed.numel()))
         return like.like(out, np.uint8, False)
+
+    # -- compact exchange formats of the sharded fusion (multiatlas.py) -----------------------------------------
+    def pack_label(self, label, bit, packed, first):
+        """packed |= (label != 0) << bit on a UInt8 / UInt16 / UInt32 decision mask (a torch tensor of that width)."""
+        _abi.check(self.lib.b200reg_pack_label(self.ctx, label.ptr, int(bit), C.c_void_p(packed.data_ptr()), _MASK_DT[packed.element_size()],
+                                               label.tensor.numel(), int(bool(first))))
+
+    def staple_packed(self, packed, holder_mask, like, confidence_weight=1.0, max_iterations=0xFFFFFFFF, threshold=1e-4, rescale=True, want_info=False):
+        """sitk.STAPLE + RescaleIntensity + Threshold from a reduced decision mask; raters = bits of ``holder_mask``."""
+        out = self.empty(packed.shape, np.float64)
+        n = bin(int(holder_mask)).count("1")
+        pq = (C.c_double * (2 * n))()
+        elapsed = C.c_int32()
+        _abi.check(self.lib.b200reg_staple_packed(self.ctx, C.c_void_p(packed.data_ptr()), _MASK_DT[packed.element_size()], C.c_uint32(int(holder_mask)),
+                                                  packed.numel(), float(confidence_weight), C.c_uint32(max_iterations), float(threshold or 0.0),
+                                                  int(bool(rescale)), C.c_void_p(out.data_ptr()), pq if want_info else None,
+                                                  C.byref(elapsed) if want_info else None))
+        res = like.like(out, np.float64, False)
+        if want_info:
+            return res, {"p": list(pq[:n]), "q": list(pq[n:]), "elapsed_iterations": elapsed.value}
+        return res
+
+    def count_accumulate(self, label, counts, first, flag):
+        """counts (UInt8 tensor) += label values; ``flag`` (int32 tensor, one element) is raised by a label value above 1."""
+        _abi.check(self.lib.b200reg_count_accumulate(self.ctx, label.ptr, C.c_void_p(counts.data_ptr()), label.tensor.numel(), int(bool(first)),
+                                                     C.c_void_p(flag.data_ptr())))
+
+    def vote_finalize_counts(self, counts, n_holders, geom_src, smooth_variance, threshold):
+        out = self.empty(counts.shape, np.float32)
+        g = _abi.geom_of(geom_src)
+        _abi.check(self.lib.b200reg_vote_finalize_counts(self.ctx, C.c_void_p(counts.data_ptr()), int(n_holders), C.byref(g), float(smooth_variance),
+                                                         float(threshold or 0.0), C.c_void_p(out.data_ptr())))
+        return DeviceImage(out, np.float32, geom_src.GetSpacing(), geom_src.GetOrigin(), geom_src.GetDirection(), False)
 
     def staple(self, decisions, confidence_weight=1.0, max_iterations=0xFFFFFFFF, threshold=1e-4, rescale=True):
         n = len(decisions)

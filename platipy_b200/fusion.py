@@ -131,7 +131,15 @@ def accumulate_votes(eng, atlas_set, s_name, label="DIR", num=None, den=None):
         if s_name not in entry:
             continue
         lab = eng.cast(eng.to_device(entry[s_name]), np.uint8)
-        w = eng.to_device(entry["Weight Map"])
+        # fusion.py:263-272 multiplies the Float32 weight map with the label cast to Float32: both on one grid (ITK raises
+        # "Inputs do not occupy the same physical space" otherwise); a weight map of another pixel type is cast like sitk would
+        w = eng.cast(eng.to_device(entry["Weight Map"]), np.float32)
+        if w.GetSize() != lab.GetSize():
+            raise RuntimeError(f"combine_labels: weight map {w.GetSize()} and label {s_name!r} {lab.GetSize()} of atlas {case_id!r} "
+                               "do not occupy the same grid")
+        if num is not None and tuple(num.shape) != tuple(lab.tensor.shape):
+            raise RuntimeError(f"combine_labels: label {s_name!r} of atlas {case_id!r} has size {lab.GetSize()}, the votes so far "
+                               f"{tuple(num.shape)[::-1]}")
         if ref is None:
             ref = lab
         if first:
@@ -142,40 +150,48 @@ def accumulate_votes(eng, atlas_set, s_name, label="DIR", num=None, den=None):
     return num, den, ref
 
 
-def combine_labels(atlas_set, structure_name, label="DIR", threshold=1e-4, smooth_sigma=1.0, process_group=None):
-    """Combine labels using weight maps (fusion.py:239-292).  With ``process_group`` (torch.distributed) every
-    rank passes its LOCAL atlases and the vote volumes are summed with one all-reduce per structure."""
+def combine_labels(atlas_set, structure_name, label="DIR", threshold=1e-4, smooth_sigma=1.0, process_group=None, reference_image=None):
+    """Combine labels using weight maps (fusion.py:239-292).  With ``process_group`` (torch.distributed; ``True`` = the default
+    group) every rank passes its LOCAL atlases and the vote volumes are summed with one all-reduce per structure;
+    ``reference_image`` (any image on the common grid, e.g. the target) is then required on ranks that may hold no atlas with a
+    structure -- it gives the grid of their all-zero contribution.  ``multiatlas.run_segmentation`` uses the structure-sharded
+    reduce-scatter form of this exchange instead."""
     eng = Engine.get()
     out = {}
     any_like = None
     for s_name in _structure_names(structure_name):
         num, den, ref = accumulate_votes(eng, atlas_set, s_name, label)
         if process_group is not None:
-            num, den, ref = _allreduce_votes(eng, num, den, ref, atlas_set, label, process_group)
+            num, den, ref = _allreduce_votes(eng, num, den, ref, reference_image, process_group)
         if ref is None:
             raise KeyError(s_name)
         for case_id in atlas_set:
             if s_name in atlas_set[case_id][label]:
                 any_like = atlas_set[case_id][label][s_name]
                 break
+        if any_like is None:
+            any_like = reference_image
         prob = eng.vote_finalize(num, den, ref, smooth_sigma * smooth_sigma, threshold)
         out[s_name] = _back(eng, prob, any_like if any_like is not None else ref)
     return out
 
 
-def _allreduce_votes(eng, num, den, ref, atlas_set, label, process_group):
+def _allreduce_votes(eng, num, den, ref, reference_image, process_group):
     import torch
     import torch.distributed as dist
 
     if num is None:
-        # this rank holds no atlas with the structure: contribute zeros on the common grid
-        any_img = next(iter(next(iter(atlas_set.values()))[label].values()))
-        ref = eng.to_device(any_img)
+        # this rank holds no atlas with the structure: it still has to enter the collective, with zeros on the common grid
+        if reference_image is None:
+            raise ValueError("combine_labels(process_group=...): this rank holds no atlas with the structure; pass reference_image "
+                             "(an image on the common grid, e.g. the target) so that it can contribute zeros to the all-reduce")
+        ref = eng.to_device(reference_image)
         num = eng.zeros(ref.tensor.shape, np.float32)
         den = eng.zeros(ref.tensor.shape, np.float32)
+    group = process_group if process_group is not True else None
     with torch.cuda.stream(eng.stream):
-        dist.all_reduce(num, group=process_group if process_group is not True else None)
-        dist.all_reduce(den, group=process_group if process_group is not True else None)
+        dist.all_reduce(num, group=group)
+        dist.all_reduce(den, group=group)
     return num, den, ref
 
 

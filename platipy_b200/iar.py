@@ -81,7 +81,8 @@ def _z_scores(own, others, statistic):
     else:
         logger.error(" z_score must be one of: MAD, STD")
         raise ValueError("z_score must be one of: MAD, STD")
-    return np.ravel((own - centre) / spread)
+    with np.errstate(divide="ignore", invalid="ignore"):  # a zero spread gives inf / nan exactly as in the reference expression
+        return np.ravel((own - centre) / spread)
 
 
 def _q_value(z_scores):

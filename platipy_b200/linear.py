@@ -667,7 +667,7 @@ def linear_registration(fixed_image, moving_image, fixed_structure=None, moving_
 
     initial = centered_transform_initializer(fixed, moving)  # linear.py:128-130
     a_init, b_init = initial.matrix, initial.offset
-    stride = max(1, int(round(1.0 / float(sampling_rate))))   # REGULAR sampling, linear.py:150-152
+    stride = max(1, int(np.ceil(1.0 / float(sampling_rate) - 1e-12)))   # REGULAR sampling (linear.py:150-152): ITK strides by ceil(1 / percentage)
     del LAST_HISTORY[:]
 
     for level, (factor, sigma) in enumerate(zip(shrink_factors, smooth_sigmas)):

@@ -263,16 +263,42 @@ class FakeEngine:
         return self._wrap(ref.process_probability_image(_img(d), threshold).array, d)
 
     def vote_accumulate(self, label, weight, num, den, first):
+        # real float32 arithmetic on the accumulators (so that sharded runs can exchange them), as vote_accumulate_kernel does it
         self._note("vote_accumulate")
-        votes = self.__dict__.setdefault("_votes", {})
+        t = _arr(weight).astype(np.float32) * _arr(label).astype(np.float32)
+        w = _arr(weight).astype(np.float32)
         if first:
-            votes[id(num)] = []
-        votes[id(num)].append((_arr(label).copy(), _arr(weight).copy()))
+            num.copy_(torch.from_numpy(t))
+            if den is not None:
+                den.copy_(torch.from_numpy(w))
+        else:
+            num.copy_(torch.from_numpy(num.numpy() + t))
+            if den is not None:
+                den.copy_(torch.from_numpy(den.numpy() + w))
 
     def vote_finalize(self, num, den, geom_src, smooth_variance, threshold):
+        # fusion.py:264-288 from the accumulators, restating orc_combine_labels_f32's tail step for step
         self._note("vote_finalize")
-        pairs = self._votes.pop(id(num))
-        out = orc.combine_labels_f32([l for l, _ in pairs], [w for _, w in pairs], orc.geom_of(geom_src), smooth_variance, threshold)
+        comb = num.numpy().astype(np.float32)
+        if den is not None:
+            d = den.numpy().astype(np.float32).copy()
+            d[d == 0] = 1.0
+            comb = comb / d
+        sm = orc.discrete_gaussian_f32(np.ascontiguousarray(comb), orc.geom_of(geom_src), [smooth_variance] * 3, 32, 0.01, True)
+        mn, mx = np.float32(sm.min()), np.float32(sm.max())
+        if abs(np.float32(mx - mn)) > np.finfo(np.float32).eps:
+            scale = 1.0 / (float(mx) - float(mn))
+        elif float(mx) != 0.0:
+            scale = 1.0 / float(mx)
+        else:
+            scale = 0.0
+        shift = 0.0 - float(mn) * scale
+        r = (sm.astype(np.float64) * scale + shift).astype(np.float32)
+        r = np.where(r > 1, np.float32(1), r)
+        r = np.where(r < 0, np.float32(0), r)
+        if threshold:
+            r = np.where((r >= np.float32(threshold)) & (r <= 1), r, np.float32(0))
+        out = np.ascontiguousarray(r, dtype=np.float32)
         return DeviceImage(torch.from_numpy(out), np.float32, geom_src.GetSpacing(), geom_src.GetOrigin(), geom_src.GetDirection(), False)
 
     # -- the remaining entry points of the atlas pipeline (multiatlas.py, fusion.py, registration.py) -----------------------------------
@@ -340,6 +366,40 @@ class FakeEngine:
     def unpack_decision(self, packed, bit, like):
         self._note("unpack_decision")
         return like.like(((packed >> int(bit)) & 1).to(torch.uint8), np.uint8, False)
+
+    # -- compact exchange formats of the sharded fusion ---------------------------------------------------------------------------------
+    def pack_label(self, label, bit, packed, first):
+        self._note("pack_label")
+        if first:
+            packed.zero_()
+        packed |= (label.tensor != 0).to(packed.dtype) << int(bit)
+
+    def staple_packed(self, packed, holder_mask, like, confidence_weight=1.0, max_iterations=0xFFFFFFFF, threshold=1e-4, rescale=True, want_info=False):
+        self._note("staple_packed")
+        bits = [b for b in range(32) if (int(holder_mask) >> b) & 1]
+        raw = packed.numpy().astype(np.int64) & ((1 << 32) - 1 if packed.element_size() == 4 else (1 << (8 * packed.element_size())) - 1)
+        W, p, q, it = orc.staple([((raw >> b) & 1).astype(np.uint8) for b in bits], confidence_weight, max_iterations)
+        if rescale or threshold:
+            W = orc.rescale_threshold_f64(W, threshold)
+        res = self._wrap(W, like)
+        return (res, {"p": list(p), "q": list(q), "elapsed_iterations": int(it)}) if want_info else res
+
+    def count_accumulate(self, label, counts, first, flag):
+        self._note("count_accumulate")
+        if first:
+            counts.zero_()
+        counts += label.tensor
+        if bool((label.tensor > 1).any()):
+            flag |= 1
+
+    def vote_finalize_counts(self, counts, n_holders, geom_src, smooth_variance, threshold):
+        self._note("vote_finalize_counts")
+        # n_holders binary labels whose sum is the count volume, each with weight 1: the same float32 num / den as the real votes
+        c = counts.numpy()
+        labels = [(c > k).astype(np.uint8) for k in range(max(int(n_holders), 1))]
+        ones = np.ones(c.shape, np.float32)
+        out = orc.combine_labels_f32(labels, [ones] * len(labels), orc.geom_of(geom_src), smooth_variance, threshold)
+        return DeviceImage(torch.from_numpy(out), np.float32, geom_src.GetSpacing(), geom_src.GetOrigin(), geom_src.GetDirection(), False)
 
     def staple(self, decisions, confidence_weight=1.0, max_iterations=0xFFFFFFFF, threshold=1e-4, rescale=True):
         self._note("staple")

@@ -112,3 +112,52 @@ def test_staple_matches_oracle(engine):
     assert info["elapsed_iterations"] == it
     assert np.allclose(info["p"], p, rtol=1e-12) and np.allclose(info["q"], q, rtol=1e-12)
     assert np.allclose(engine.to_host(gW, pinned=False).array, W, rtol=1e-10, atol=1e-14)
+
+
+def test_compact_exchange_formats_match_the_plain_paths(engine):
+    """The structure-sharded fusion's payloads (platipy_b200/multiatlas.py): STAPLE straight from the packed decision mask equals
+    STAPLE on the decision volumes (same histogram, same table EM: bit-identical) -- dense and sparse holder masks, 8- and 16-bit
+    masks -- and equals the oracle to the reduction-order tolerance; the UInt8 vote counts give the float32 votes bit for bit."""
+    import torch
+
+    eng = engine
+    size, sp = (44, 36, 20), (1.0, 1.0, 1.5)
+    base = synth_labels(size, 1, seed=400)[0]
+    n_atlas = 11
+    labs = [eng.to_device(Image(np.roll(base, shift=(a % 3 - 1, (a * 2) % 5 - 2, a % 4 - 1), axis=(0, 1, 2)).astype(np.uint8), sp)) for a in range(n_atlas)]
+    for holders, dtype in (([0, 1, 2, 3, 4], torch.uint8), ([0, 2, 3, 7], torch.uint8), ([1, 4, 8, 9, 10], torch.int16), (list(range(11)), torch.int32)):
+        with torch.cuda.stream(eng.stream):
+            packed = torch.zeros(labs[0].tensor.shape, dtype=dtype, device=eng.device)
+        for a in holders:
+            eng.pack_label(labs[a], a, packed, False)
+        hm = sum(1 << a for a in holders)
+        got, info = eng.staple_packed(packed, hm, labs[0], threshold=1e-4, rescale=True, want_info=True)
+        plain, info_p = eng.staple([labs[a] for a in holders], threshold=1e-4, rescale=True)
+        g, p = eng.to_host(got).array, eng.to_host(plain).array
+        assert np.array_equal(g, p) and info["elapsed_iterations"] == info_p["elapsed_iterations"] and info["p"] == info_p["p"]
+        W, po, qo, it = orc.staple([eng.to_host(labs[a]).array for a in holders])
+        exp = orc.rescale_threshold_f64(W, 1e-4)
+        assert it == info["elapsed_iterations"]
+        assert np.allclose(g, exp, rtol=1e-9, atol=1e-12)
+        # without the statistics the call does not synchronise; same values
+        assert np.array_equal(eng.to_host(eng.staple_packed(packed, hm, labs[0])).array, g)
+    # unweighted vote: counts vs the float32 accumulators
+    with torch.cuda.stream(eng.stream):
+        counts = torch.zeros(labs[0].tensor.shape, dtype=torch.uint8, device=eng.device)
+        flag = torch.zeros(1, dtype=torch.int32, device=eng.device)
+    num, den = eng.empty(labs[0].tensor.shape, np.float32), eng.empty(labs[0].tensor.shape, np.float32)
+    ones = eng.weight_map(eng.cast(labs[0], np.float32), eng.cast(labs[0], np.float32), 0)
+    for k, a in enumerate(range(7)):
+        eng.count_accumulate(labs[a], counts, False, flag)
+        eng.vote_accumulate(labs[a], ones, num, den, k == 0)
+    got = eng.to_host(eng.vote_finalize_counts(counts, 7, labs[0], 1.0, 1e-4)).array
+    exp = eng.to_host(eng.vote_finalize(num, den, labs[0], 1.0, 1e-4)).array
+    assert int(flag.item()) == 0 and np.array_equal(got, exp)
+    assert np.array_equal(got, orc.combine_labels_f32([eng.to_host(labs[a]).array for a in range(7)], [np.ones(base.shape, np.float32)] * 7,
+                                                      orc.geom_of(labs[0]), 1.0, 1e-4))
+    # a label value above 1 raises the flag (the caller then takes the float32 path)
+    two = eng.to_device(Image((base * 2).astype(np.uint8), sp))
+    eng.count_accumulate(two, counts, False, flag)
+    assert int(flag.item()) == 1
+    with pytest.raises(ValueError):
+        eng.pack_label(labs[0], 9, torch.zeros(labs[0].tensor.shape, dtype=torch.uint8, device=eng.device), False)
