@@ -1,26 +1,35 @@
 #!/usr/bin/env python
 """
-bench.py -- headline benchmark of the Demons hot path (BASELINE.json configs[1]).
+bench.py -- the reference's headline metric on B200 (BASELINE.json): Demons throughput at 512x512x256 and the multi-atlas
+fusion wall-clock at 1 / 2 / 4 / 8 GPUs.
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference] [--size X Y Z]
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--size X Y Z] [--no-fusion] [--no-cpu-baseline]
 
-A "step" is one `fast_symmetric_forces_demons_registration` of a synthetic 512x512x256 float32 pair,
-3-level pyramid [4, 2, 1], 100/50/25 iterations (early stop as in the reference).  N > 1: one pair per rank
-(rank r registers atlas 100+r to the common target: independent units, weak scaling) followed by the
-path's one exchange step, the NCCL all-reduce of the propagated-label vote volume.
+Headline line (metric / value / e2e / roofline / cpu_baseline), BASELINE.json configs[1]:
+  A "step" is one `fast_symmetric_forces_demons_registration` of a synthetic 512x512x256 float32 pair, 3-level pyramid
+  [4, 2, 1], 100/50/25 iterations (early stop as in the reference).  N > 1: one pair per rank (rank r registers atlas 100+r to
+  the common target: independent units, weak scaling, no data-path collective inside the step).
+  metric   demons_voxel_iterations_per_s, unit Mvoxel*it/s: (sum over levels of voxels x elapsed iterations, summed over ranks) /
+           (max over ranks of the device time of the K timed steps / K).
+  value    inputs already resident in HBM (device-in, device-out call).
+  e2e      the same metric through the public host API: pinned host buffers in, host images out; the H2D and D2H copies are
+           inside the timed region, all K steps.
+  roofline the full-resolution Demons iteration (the kernels between two iterations of level 2), algorithmic
+           176 B/voxel/iteration with f64 fields, against MEASURED_PEAKS.json hbm_gbs.
+  cpu_baseline / --impl reference: the CPU oracle (the restatement of the ITK filters; SimpleITK itself is not installable
+           offline) on all host cores.  --impl reference times the WHOLE registration (pyramid, three levels, level glue, final
+           warp) once and reports its throughput; the remaining steps are bounded samples of full-resolution iterations.
 
-metric   demons_voxel_iterations_per_s, unit Mvoxel*it/s: (sum over levels of voxels x elapsed iterations,
-         summed over ranks) / (max over ranks of the device time of the K timed steps / K).
-value    inputs already resident in HBM (device-in, device-out call).
-e2e      the same metric through the public host API: pinned host buffers in, host images out; the H2D
-         and D2H copies are inside the timed region.
-roofline the full-resolution Demons iteration (the kernels between two iterations of level 2), algorithmic
-         176 B/voxel/iteration with f64 fields, against MEASURED_PEAKS.json hbm_gbs.
-cpu_baseline / --impl reference: the CPU oracle (the restatement of the ITK filters; SimpleITK itself is
-         not installable offline) timed on a bounded sample on all host cores.
-experiments  (optional, N = 1, once per box, --no-experiments to skip) informational measurements taken in child processes AFTER
-         every key above has been measured: A/B of compiled-out kernel variants, a pipelined end-to-end run, platipy's default
-         staging, the newest GPU tests without -x.  Bounded to 200 s; feeds no other key.
+"fusion" (same JSON line; BASELINE.json configs[3] and configs[4], strong scaling -- total work fixed as N grows):
+  `run_segmentation` (linear_registration -> Demons -> label propagation -> fusion -> process_probability_image, auto-crop and
+  paste back) over a synthetic cohort: cfg4 = 4 atlases x 5 structures at 256x256x160, unweighted vote; cfg5 = 8 atlases x
+  20 structures at 512x512x256, STAPLE.  Atlases are sharded over the N ranks, the fusion tail over structures; wall-clock is
+  the max over ranks between two barriers, inputs resident in HBM on the rank that owns them, masks on every rank at the end.
+  `stages_ms` (one extra instrumented run, every stage synchronised) separates per-atlas work, the exchange and the tail;
+  `mask_checksums` are integer checksums of the final masks -- identical at every N when the sharded run is bit-exact.
+
+"resample_cfg3" (same line; BASELINE.json configs[2]): apply_transform of one CT (linear) + 20 masks (nearest neighbour)
+  through a dense f64 DVF at 512x512x256, per call and batched, with its own HBM roofline figures.
 """
 import argparse
 import json
@@ -102,120 +111,84 @@ class ClockSampler:
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank's threads (and with them the first-touch placement of its pinned buffers) to the NUMA node its GPU hangs
+    off: eight ranks copying 1.9 GB each per step otherwise contend for one node's memory controllers.  Best effort."""
+    try:
+        import torch
+
+        pr = torch.cuda.get_device_properties(local_rank)
+        if all(hasattr(pr, k) for k in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        else:
+            uuid = str(getattr(pr, "uuid", ""))
+            out = subprocess.run(["nvidia-smi", "--query-gpu=uuid,pci.bus_id", "--format=csv,noheader"], capture_output=True, text=True, timeout=10).stdout
+            rows = [[f.strip() for f in r.split(",")] for r in out.strip().splitlines()]
+            match = [r[1] for r in rows if uuid and uuid in r[0]] or [rows[local_rank][1]]
+            bdf = match[0].lower()
+            if len(bdf.split(":")[0]) == 8:  # nvidia-smi prints an 8-digit PCI domain, sysfs uses 4
+                bdf = bdf[4:]
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus += list(range(int(a), int(b or a) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if allowed:
+            os.sched_setaffinity(0, allowed)
+            return {"numa_node": node, "cpus": len(allowed)}
+    except Exception:  # noqa: BLE001
+        return None
+    return None
+
+
 CPU_SAMPLE_ITERS = 10  # full-resolution iterations per bounded CPU sample: 10-25 s on 16-64 host cores
+
+
+def use_all_host_cores():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every core the process may run on."""
+    from oracle import itk_oracle as orc
+
+    n = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    orc.set_num_threads(n)
+    return orc.num_threads()
 
 
 def oracle_sample(size, fixed, moving, iters):
     """Bounded CPU sample: `iters` full-resolution Demons iterations of the oracle on all host cores."""
     from oracle import itk_oracle as orc
 
+    cores = use_all_host_cores()
     p = orc.demons_params((1.5, 1.5, 1.5), iters, smooth_update_field=True)
     gf = orc.geom_of(fixed)
     t0 = time.perf_counter()
     _, st = orc.demons_execute(fixed.array, gf, moving.array, gf, p)
     dt = time.perf_counter() - t0
     vox_it = fixed.GetNumberOfPixels() * st["elapsed_iterations"]
-    return vox_it / dt / 1e6, dt, st["elapsed_iterations"], orc.num_threads()
+    return vox_it / dt / 1e6, dt, st["elapsed_iterations"], cores
 
 
-def run_experiments(timeout_s=100, budget_s=200):
-    """A/B of kernel variants that are compiled out of the default library, in CHILD processes (their own CUDA contexts) after
-    every number of the JSON line has been measured: the TMA staging forms of the fused smoothing kernel (row-wise bulk copies,
-    one tensor-map copy per plane tile) against cp.async, via profiles/ab_variants.py, which also reports whether the displacement
-    field is bit-identical.  Only runs when the alternative build platipy_b200/libb200reg_tma.so is present
-    (make -C platipy_b200/csrc OUT=../libb200reg_tma.so EXTRA="-DB200REG_ENABLE_ZM_TMA -DB200REG_AB_VARIANTS"); bounded by `timeout_s`; any failure is
-    recorded as text and never touches the measured values.  Informational: not part of metric / value / e2e / roofline."""
-    import subprocess
+def oracle_whole_registration(fixed, moving):
+    """The whole `fast_symmetric_forces_demons_registration` of the headline configuration on the CPU oracle."""
+    from oracle import platipy_ref as ref
 
-    import tempfile
-
-    t_start = time.perf_counter()
-    lib = "libb200reg_tma.so"
-    if not os.path.exists(os.path.join(ROOT, "platipy_b200", lib)):
-        return None  # the alternative build is the switch for the whole informational block
-    # once per box: a scaling run repeats the N = 1 command, the informational block need not run again
-    marker = os.path.join(tempfile.gettempdir(), "b200reg_bench_experiments_done")
-    if os.path.exists(marker) and os.environ.get("B200REG_BENCH_EXPERIMENTS") != "force":
-        return {"skipped": "already ran on this box (" + marker + ")"}
-    try:
-        open(marker, "w").write(str(time.time()))
-    except OSError:
-        pass
-    # most informative first (the cap may cut the list short); the row-wise bulk copies were already measured slower in round 1
-    specs = ["default=", f"tma_tensor=B200REG_ZM_TMA=2,lib={lib}", f"tma_tensor_tx64=B200REG_ZM_TMA=2,B200REG_ZM_TX32=0,lib={lib}",
-             f"cp_async=B200REG_ZM_TMA=0,lib={lib}", f"cp_async_tx64=B200REG_ZM_TMA=0,B200REG_ZM_TX32=0,lib={lib}",
-             f"tma_tensor_l2_128=B200REG_ZM_TMA=2,B200REG_ZM_TMA_L2=2,lib={lib}"]
-    out = ""
-    try:
-        # own session: on a timeout the whole process group goes (the harness runs every configuration in a grandchild)
-        proc = subprocess.Popen([sys.executable, os.path.join(ROOT, "profiles", "ab_variants.py")] + specs, stdout=subprocess.PIPE, stderr=subprocess.PIPE,
-                                text=True, start_new_session=True)
-        try:
-            out, err = proc.communicate(timeout=timeout_s)
-            note = err[-300:] if proc.returncode else None
-        except subprocess.TimeoutExpired:
-            import signal
-
-            os.killpg(proc.pid, signal.SIGKILL)
-            out, err = proc.communicate()
-            note = f"stopped after {timeout_s} s"
-    except Exception as e:  # noqa: BLE001
-        return {"error": repr(e)[:300]}
-    res = {}
-    for l in out.splitlines():  # one line per finished configuration: "<name> {json}"
-        name, _, rest = l.partition(" ")
-        if rest.startswith("{") and name in [sp.split("=")[0] for sp in specs]:
-            try:
-                res[name] = json.loads(rest)
-            except ValueError:
-                pass
-        if l.startswith("AB {"):  # the harness's closing summary also carries the configurations that failed, with the error text
-            try:
-                for k, v in json.loads(l[3:]).items():
-                    res.setdefault(k, v)
-            except ValueError:
-                pass
-    for v in res.values():  # keep the line small
-        if isinstance(v, dict) and "error" in v:
-            v["error"] = str(v["error"])[-240:]
-    exp = {"smoothing_tile_staging_ab": res, "what": "full-resolution ms per iteration and DVF identity of the fused smoothing kernel's staging variants "
-                                                      "(profiles/ab_variants.py, child processes, after the timed regions)"}
-    if note:
-        exp["note"] = note
-    # further child scripts, each printing one "EXP {json}" line:
-    #   pipelined_e2e            copies of one registration overlapping the compute of its neighbours
-    #   platipy_default_staging  the headline volume with platipy's own defaults ([8, 4, 1] shrink factors, 10 iterations per level), SURVEY 8d
-    #   session3_rows            device time at the headline size of the entry points added without GPU time in round 1's third session
-    #   session3_gpu_tests       the GPU tests of those entry points, run without -x (every outcome is recorded)
-    # The whole block stays inside `budget_s`: a child gets what is left of it, and is skipped when that is under 15 s.
-    for key, script, cap in (("pipelined_e2e", "exp_pipelined_e2e.py", 60), ("session3_gpu_tests", "exp_session3_tests.py", 90),
-                             ("platipy_default_staging", "exp_default_staging.py", 45), ("session3_rows", "exp_session3_rows.py", 60)):
-        cap = int(min(cap, budget_s - (time.perf_counter() - t_start)))
-        if cap < 15:
-            exp[key] = {"skipped": "time budget of the informational block used up"}
-            continue
-        try:
-            proc = subprocess.Popen([sys.executable, os.path.join(ROOT, "profiles", script)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True,
-                                    start_new_session=True)
-            try:
-                out, err = proc.communicate(timeout=cap)
-                got = [l for l in out.splitlines() if l.startswith("EXP ")]
-                exp[key] = json.loads(got[-1][4:]) if got else {"error": (err or out)[-240:]}
-            except subprocess.TimeoutExpired:
-                import signal
-
-                os.killpg(proc.pid, signal.SIGKILL)
-                proc.communicate()
-                exp[key] = {"error": f"stopped after {cap} s"}
-        except Exception as e:  # noqa: BLE001
-            exp[key] = {"error": repr(e)[:240]}
-    return exp
+    cores = use_all_host_cores()
+    stats = []
+    t0 = time.perf_counter()
+    ref.fast_symmetric_forces_demons_registration(fixed, moving, resolution_staging=RES_STAGING, iteration_staging=ITER_STAGING, level_stats=stats)
+    dt = time.perf_counter() - t0
+    vox_it = float(sum(s["voxels"] * s["elapsed_iterations"] for s in stats))
+    return vox_it / dt / 1e6, dt, [s["elapsed_iterations"] for s in stats], cores
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path.  SimpleITK/ITK cannot be installed
-    offline, so this arm times the oracle port (the C restatement of the ITK filters, OpenMP on all host
-    cores); each step is a bounded sample: CPU_SAMPLE_ITERS full-resolution Demons iterations."""
+    """--impl reference: the reference's CPU implementation of the path.  SimpleITK/ITK cannot be installed offline, so this arm
+    times the oracle port (the C restatement of the ITK filters, OpenMP on all host cores).  The first timed step is the WHOLE
+    registration of the headline configuration -- pyramid, three levels with the reference's early stop, level glue, final warp --
+    and gives `value` and `ms_per_step`; warm-up steps and the remaining timed steps are bounded samples (2 full-resolution
+    iterations each) so that the run stays within a few minutes whatever K + W is; their median is reported beside it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
@@ -223,19 +196,22 @@ def run_reference(args):
 
     size = tuple(args.size)
     fixed, moving = synth_pair(size, seed=0, moving_seed=100)
-    vals = []
-    cores = None
-    # bounded: the whole --steps K --warmup W run stays within a few minutes whatever K + W is
-    iters = max(2, min(CPU_SAMPLE_ITERS, 60 // max(1, args.warmup + args.steps)))
-    for s in range(args.warmup + args.steps):
-        v, dt, it, cores = oracle_sample(size, fixed, moving, iters)
-        if s >= args.warmup:
-            vals.append((v, dt))
-    value = sum(v for v, _ in vals) / len(vals)
-    ms = 1e3 * sum(dt for _, dt in vals) / len(vals)
-    sample = f"{iters} full-resolution Demons iterations ({size[0]}x{size[1]}x{size[2]}) of the oracle port per step"
+    cores = use_all_host_cores()
+    for _ in range(args.warmup):
+        oracle_sample(size, fixed, moving, 1)
+    value, dt, elapsed, cores = oracle_whole_registration(fixed, moving)
+    samples = []
+    for _ in range(max(0, args.steps - 1)):
+        if sum(d for _, d in samples) > 90.0:
+            break
+        v, d, _, _ = oracle_sample(size, fixed, moving, 2)
+        samples.append((v, d))
+    sample = (f"whole registration once ({size[0]}x{size[1]}x{size[2]}, pyramid {RES_STAGING}, elapsed iterations {elapsed}, {dt:.1f} s on {cores} threads: "
+              f"pyramid + levels + glue + final warp) -> value; {len(samples)} further bounded samples of 2 full-resolution iterations"
+              + (f", median {statistics.median(v for v, _ in samples):.1f} {UNIT}" if samples else "")
+              + "; CPU restatement of the ITK filters, not SimpleITK")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "ms_per_step": 1e3 * dt, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(size, args.gpus),
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
@@ -245,10 +221,167 @@ def run_reference(args):
 
 def workload_config(size, n_gpus):
     return {"workload": f"single-pair Demons {size[0]}x{size[1]}x{size[2]}, 3-level pyramid {RES_STAGING}, {ITER_STAGING} iters "
-                        f"(BASELINE.json configs[1])" + ("" if n_gpus == 1 else f"; one pair per GPU x{n_gpus} + label vote all-reduce"),
+                        f"(BASELINE.json configs[1])" + ("" if n_gpus == 1 else f"; one independent pair per GPU x{n_gpus}"),
             "size": list(size), "resolution_staging": RES_STAGING, "iteration_staging": ITER_STAGING, "field_dtype": "f64",
             "cache": "inputs (2 x 268 MB) and fields (1.6 GB each) exceed the 126 MB L2; no explicit flush",
             "parallelism": "1 pair/GPU" if n_gpus > 1 else "single GPU"}
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# fusion workloads (BASELINE.json configs[3], configs[4])
+# ---------------------------------------------------------------------------------------------------------------------
+FUSION_CONFIGS = {
+    "cfg4": {"size": (256, 256, 160), "n_atlases": 4, "n_structures": 5, "fusion": "vote", "baseline_config": 3},
+    "cfg5": {"size": (512, 512, 256), "n_atlases": 8, "n_structures": 20, "fusion": "staple", "baseline_config": 4},
+}
+
+
+def fusion_settings(mode):
+    """Pipeline settings of examples/atlas_segmentation.ipynb cell 20 with Demons [4, 2, 1] x [50, 50, 25]."""
+    return {
+        "auto_crop_target_image_settings": {"expansion_mm": [20, 20, 40]},
+        "linear_registration_settings": {"reg_method": "similarity", "shrink_factors": [8, 4, 2], "smooth_sigmas": [4, 2, 0], "sampling_rate": 1,
+                                         "default_value": -1000, "number_of_iterations": 50, "metric": "mean_squares", "optimiser": "gradient_descent",
+                                         "verbose": False},
+        "deformable_registration_settings": {"isotropic_resample": False, "resolution_staging": [4, 2, 1], "iteration_staging": [50, 50, 25],
+                                             "smoothing_sigmas": [4, 2, 0], "ncores": 32, "default_value": -1000, "verbose": False},
+        "label_fusion_settings": {"vote_type": "unweighted", "vote_params": None, "optimal_threshold": {}, "fusion": mode},
+        "postprocessing_settings": {"run_postprocessing": True, "binaryfillhole_mm": 3, "structures_for_binaryfillhole": [],
+                                    "structures_for_overlap_correction": []},
+    }
+
+
+def run_fusion(name, eng, dist, rank, world, runs=2):
+    import numpy as np
+    import torch
+
+    from platipy_b200 import multiatlas
+    from platipy_b200.engine import DeviceImage
+    from platipy_b200.synth import synth_atlas_case
+
+    cfg = FUSION_CONFIGS[name]
+    size, n_atlas, n_struct = cfg["size"], cfg["n_atlases"], cfg["n_structures"]
+    spacing = (1.0, 1.0, 1.5)
+    ident = (1.0, 0.0, 0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 1.0)
+    names = [f"S{k:02d}" for k in range(n_struct)]
+    ids = [f"{a:03d}" for a in range(n_atlas)]
+
+    def dimg(t, dt):
+        return DeviceImage(t, dt, spacing, (0.0, 0.0, 0.0), ident, False)
+
+    with torch.cuda.device(eng.device):
+        ct, truth = synth_atlas_case(size, n_struct, spacing, seed=0, atlas_seed=None, as_tensors=True)
+        target = dimg(ct, np.float32)
+        mine = multiatlas.shard_atlases(ids, rank, world)
+        atlas_part = {}
+        for a in mine:
+            act, alabs = synth_atlas_case(size, n_struct, spacing, seed=0, atlas_seed=int(a), as_tensors=True)
+            entry = {"CT Image": dimg(act, np.float32)}
+            entry.update({n: dimg(l, np.uint8) for n, l in zip(names, alabs)})
+            atlas_part[a] = entry
+    torch.cuda.synchronize()
+    settings = fusion_settings(cfg["fusion"])
+
+    def barrier():
+        eng.synchronize()
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def once(timings=None):
+        return multiatlas.run_segmentation(target, atlas_part, settings, atlas_ids=ids, gather_probabilities=False, timings=timings)
+
+    masks, _ = once()  # warm-up (allocator pools, NCCL channels, shared-memory opt-ins)
+    walls = []
+    l0 = eng.launch_count()
+    for _ in range(runs):
+        barrier()
+        t0 = time.perf_counter()
+        masks, probs = once()
+        barrier()
+        walls.append(1e3 * (time.perf_counter() - t0))
+    launches = (eng.launch_count() - l0) / runs
+    stages = {}
+    barrier()
+    once(stages)
+    barrier()
+
+    def allmax(x):
+        if dist is None:
+            return float(x)
+        t = torch.tensor([x], dtype=torch.float64, device=eng.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    wall = min(allmax(w) for w in walls)
+    stage_keys = ["setup_s", "linear_s", "deformable_s", "weight_map_s", "pack_s", "exchange_s", "finalise_s", "gather_s"]
+    stages_ms = {k[:-2] + "_ms": 1e3 * allmax(stages.get(k, 0.0)) for k in stage_keys}
+    # integer checksums of the final masks (every rank holds all of them) and Dice against the cohort's ground truth
+    checks, dices = {}, []
+    with torch.cuda.stream(eng.stream):
+        idx = torch.arange(masks[names[0]].tensor.numel(), device=eng.device, dtype=torch.int64) % 1000003
+        for n, tr in zip(names, truth):
+            m = masks[n].tensor.reshape(-1).to(torch.int64)
+            checks[n] = [int(m.sum().item()), int((m * idx).sum().item())]
+            inter = int((m * tr.reshape(-1).to(torch.int64)).sum().item())
+            dices.append(2.0 * inter / max(1, checks[n][0] + int(tr.sum().item())))
+    return {"workload": f"run_segmentation {name}: {n_atlas} atlases x {n_struct} structures at {size[0]}x{size[1]}x{size[2]} (spacing 1 x 1 x 1.5 mm), "
+                        f"similarity linear_registration -> Demons [4,2,1]x[50,50,25] -> label propagation -> "
+                        f"{'STAPLE' if cfg['fusion'] == 'staple' else 'unweighted vote'} -> process_probability_image "
+                        f"(BASELINE.json configs[{cfg['baseline_config']}])",
+            "scaling": "strong", "n_gpus": world, "wall_ms": wall, "wall_ms_runs": [allmax(w) for w in walls],
+            "atlases_per_rank_max": -(-n_atlas // world), "structures_per_rank_max": -(-n_struct // world),
+            "stages_ms": stages_ms, "gpu_launches_per_run_rank0": launches,
+            "exchange_payload_bytes_per_rank": int(stages.get("exchange_bytes", 0)), "cropped_grid": stages.get("grid"), "payload": stages.get("payload"),
+            "mask_checksums": checks, "dice_vs_truth_min": min(dices), "dice_vs_truth_mean": sum(dices) / len(dices),
+            "inputs": "resident in HBM on the owning rank", "outputs": "UInt8 masks of all structures on every rank (HBM); probabilities on the owner rank"}
+
+
+def run_resample_cfg3(eng, size):
+    """BASELINE.json configs[2]: one CT (linear, default -1000) + 20 UInt8 masks (nearest neighbour, 0) through a dense f64 DVF."""
+    import torch
+
+    from platipy_b200 import registration as reg
+    from platipy_b200 import sitk_compat as sk
+    from platipy_b200.sitk_compat import Image
+    from platipy_b200.synth import smooth_random_dvf, synth_labels, synth_pair
+
+    n = size[0] * size[1] * size[2]
+    fixed, moving = synth_pair(size, seed=0, moving_seed=100)
+    labels = [eng.to_device(Image(l)) for l in synth_labels(size, 20, seed=200)]
+    dM, dF = eng.to_device(moving), eng.to_device(fixed)
+    tfm = sk.DisplacementFieldTransform(Image(smooth_random_dvf(size, seed=9, peak_mm=6.0), is_vector=True))
+    imgs = [dM] + labels
+    dvs, ips = [-1000] + [0] * 20, [sk.sitkLinear] + [sk.sitkNearestNeighbor] * 20
+
+    def timed(fn, reps=5):
+        fn()
+        fn()
+        eng.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(eng.stream)
+        for _ in range(reps):
+            fn()
+        e1.record(eng.stream)
+        eng.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    def per_call():
+        for im, dv, ip in zip(imgs, dvs, ips):
+            reg.apply_transform(im, dF, tfm, dv, ip)
+
+    ms_calls = timed(per_call)
+    ms_batch = timed(lambda: reg.apply_transform_batch(imgs, dF, tfm, dvs, ips))
+    peak, src = measured_peak_gbs()
+    b_calls, b_batch = n * (32 + 20 * 26), n * (24 + 8 + 40)  # SURVEY 8d
+    return {"workload": f"apply_transform {size[0]}x{size[1]}x{size[2]}: 1 CT (linear) + 20 UInt8 masks (nearest neighbour) through a dense f64 DVF "
+                        "(BASELINE.json configs[2])",
+            "per_call": {"ms": ms_calls, "algorithmic_bytes": b_calls, "achieved_gbs": b_calls / ms_calls / 1e6, "frac": b_calls / ms_calls / 1e6 / peak,
+                         "bytes_per_voxel": "f32 linear 32, u8 NN 26 (DVF re-read per call)"},
+            "batched": {"ms": ms_batch, "algorithmic_bytes": b_batch, "achieved_gbs": b_batch / ms_batch / 1e6, "frac": b_batch / ms_batch / 1e6 / peak,
+                        "bytes_per_voxel": "24 DVF + 8 CT + 40 masks = 72", "Gvoxel_per_s": 21 * n / (ms_batch * 1e-3) / 1e9},
+            "peak_gbs": peak, "peak_source": src}
 
 
 def run_b200(args):
@@ -261,6 +394,7 @@ def run_b200(args):
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device; platipy_b200 has no CPU fallback")
     torch.cuda.set_device(local)
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -272,16 +406,14 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from platipy_b200 import registration as reg
-    from platipy_b200 import sitk_compat as sk
     from platipy_b200.engine import Engine, pinned_image
-    from platipy_b200.synth import synth_labels, synth_pair
+    from platipy_b200.synth import synth_pair
 
     size = tuple(args.size)
     eng = Engine.get(local)
     fixed, moving = synth_pair(size, seed=0, moving_seed=100 + rank)
     fixed_p, moving_p = pinned_image(fixed), pinned_image(moving)
     dF, dM = eng.to_device(fixed_p), eng.to_device(moving_p)
-    label = eng.to_device(sk.Image(synth_labels(size, 1, seed=200)[0])) if world > 1 else None
     kw = dict(resolution_staging=RES_STAGING, iteration_staging=ITER_STAGING)
     nvox = fixed.GetNumberOfPixels()
 
@@ -296,22 +428,8 @@ def run_b200(args):
 
     def device_step():
         img, tfm, dvf = reg.fast_symmetric_forces_demons_registration(dF, dM, **kw)
-        level_stats["last"] = tfm_stats()
-        if dist is not None:
-            # the path's one exchange step: propagate a label, accumulate the vote, all-reduce, finalise
-            lab = reg.apply_transform(label, dF, tfm, 0, sk.sitkNearestNeighbor)
-            w = eng.weight_map(dF, img, 0)
-            num = eng.empty(lab.tensor.shape, np.float32)
-            den = eng.empty(lab.tensor.shape, np.float32)
-            eng.vote_accumulate(lab, w, num, den, True)
-            with torch.cuda.stream(eng.stream):
-                dist.all_reduce(num)
-                dist.all_reduce(den)
-            eng.vote_finalize(num, den, dF, 1.0, 1e-4)
+        level_stats["last"] = reg.LAST_LEVEL_STATS[:]
         return dvf
-
-    def tfm_stats():
-        return reg.LAST_LEVEL_STATS[:]
 
     def timed(fn, steps):
         barrier()
@@ -344,15 +462,14 @@ def run_b200(args):
         img, tfm, dvf = reg.fast_symmetric_forces_demons_registration(fixed_p, moving_p, **kw)
         return float(dvf.array[0, 0, 0, 0]) + float(img.array[0, 0, 0])
 
-    for _ in range(max(1, min(args.warmup, 2))):
+    for _ in range(max(1, min(args.warmup, 3))):
         e2e_step()
-    e2e_steps = max(1, min(args.steps, 3))
     barrier()
     t0 = time.perf_counter()
-    for _ in range(e2e_steps):
+    for _ in range(args.steps):
         e2e_step()
     barrier()
-    e2e_ms = 1e3 * (time.perf_counter() - t0) / e2e_steps
+    e2e_ms = 1e3 * (time.perf_counter() - t0) / args.steps
 
     def allmax(x):
         if dist is None:
@@ -374,6 +491,26 @@ def run_b200(args):
     total_launches = allsum(float(launches))
     value = total_vox_it / (ms_per_step * 1e-3) / 1e6
     e2e_value = total_vox_it / (e2e_ms * 1e-3) / 1e6
+    del dF, dM
+
+    # ---- the fusion workloads and cfg3 (their own keys; they feed nothing above) ----
+    fusion, cfg3 = None, None
+    if not args.no_fusion:
+        fusion = {}
+        for name in args.fusion_configs:
+            try:
+                torch.cuda.empty_cache()
+                fusion[name] = run_fusion(name, eng, dist, rank, world)
+            except Exception as e:  # noqa: BLE001 -- a failure here is reported, it must not cost the headline line
+                if dist is not None:
+                    raise
+                fusion[name] = {"error": repr(e)[:400]}
+    if world == 1 and not args.no_cfg3:
+        try:
+            torch.cuda.empty_cache()
+            cfg3 = run_resample_cfg3(eng, size)
+        except Exception as e:  # noqa: BLE001
+            cfg3 = {"error": repr(e)[:400]}
 
     if rank == 0:
         peak, peak_src = measured_peak_gbs()
@@ -398,21 +535,19 @@ def run_b200(args):
             cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
                    "sample": f"{it} full-resolution Demons iterations ({size[0]}x{size[1]}x{size[2]}) of the oracle port, {dt:.1f} s; "
                              "CPU restatement of the ITK filters, not SimpleITK"}
-        experiments = None
-        if world == 1 and not args.no_experiments and os.environ.get("B200REG_BENCH_EXPERIMENTS", "1") != "0":
-            try:
-                experiments = run_experiments()
-            except BaseException as e:  # noqa: BLE001 -- nothing here may cost the measured line
-                experiments = {"error": repr(e)[:300]}
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
                 "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(size, world),
-                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(2 * nvox * 4 * world),
+                "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms, "steps": args.steps, "h2d_bytes_per_step": int(2 * nvox * 4 * world),
                         "d2h_bytes_per_step": int((nvox * 24 + nvox * 4) * world)},
                 "gpu_launches": int(total_launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks,
                 "levels": [{"voxels": s["voxels"], "elapsed_iterations": s["elapsed_iterations"], "gpu_ms": s["gpu_ms"], "metric": s["metric"],
                             "rms_change": s["rms_change"]} for s in stats]}
-        if experiments is not None:
-            line["experiments"] = experiments
+        if numa is not None:
+            line["numa_binding_rank0"] = numa
+        if fusion is not None:
+            line["fusion"] = fusion
+        if cfg3 is not None:
+            line["resample_cfg3"] = cfg3
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
@@ -427,7 +562,9 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--size", type=int, nargs=3, default=[512, 512, 256])
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-experiments", action="store_true", help="skip the informational A/B of compiled-out kernel variants")
+    ap.add_argument("--no-fusion", action="store_true", help="skip the run_segmentation workloads (cfg4, cfg5)")
+    ap.add_argument("--fusion-configs", nargs="*", default=["cfg4", "cfg5"], choices=sorted(FUSION_CONFIGS))
+    ap.add_argument("--no-cfg3", action="store_true", help="skip the apply_transform workload (cfg3)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -62,7 +62,8 @@ struct b200reg_ctx {
     bool unfused_force = false;    // B200REG_UNFUSED_FORCE=1: separate warp and force kernels (W through HBM)
     bool staple_voxelwise = false; // B200REG_STAPLE_VOXELWISE=1: per-voxel EM kernels instead of the pattern-histogram EM
     bool update_ws = false;        // B200REG_UPDATE_WS=1: warp-specialised (producer/consumer) fused update kernel
-    int zm_tma = 1;                // B200REG_ZM_TMA (builds with -DB200REG_ENABLE_ZM_TMA only): 0 cp.async staging, 1 one TMA bulk copy per tile row, 2 one tensor-map copy per plane tile
+    int zm_tma = 1;                // B200REG_ZM_TMA=0: cp.async (LDGSTS) staging of the fused smoothing kernel's plane tiles instead of one tensor-map TMA copy per tile
+    int zm_tma_l2 = 2;             // B200REG_ZM_TMA_L2 = 0 | 1 | 2 | 3: L2 promotion of the tensor-map loads (none, 64, 128, 256 bytes)
     bool update_branchy = false;   // B200REG_UPDATE_BRANCHY=1: first version of the fused update kernel's force phase (per-voxel branches)
     bool zm_regadd = false;        // B200REG_ZM_REGADD=0: add + smooth stages both operands in shared memory (first version)
     bool update_split = true;      // B200REG_UPDATE_SPLIT=0: fused z-marching warp + force kernel instead of the two high-occupancy kernels
@@ -70,7 +71,6 @@ struct b200reg_ctx {
     int pf_force = 0;              // B200REG_PF_FORCE=n: force kernel prefetches W / F n steps ahead into L2
     int warp_march = 0;            // B200REG_WARP_MARCH=n: z-marching warp kernel with n planes per thread (0: one-shot kernel)
     int zm_chunks = 0;             // B200REG_ZM_CHUNKS=n: z-chunks per tile column of the fused smoothing kernel (0: automatic)
-    bool zm_split_rows = false;    // B200REG_ZM_SPLIT_ROWS=1: third-generation fused smoothing kernel (pair-split shared rows; measured equal)
     bool zm_tx32 = true;           // B200REG_ZM_TX32=0: 64-wide tiles (320 threads, 2 CTAs per SM) in the fused smoothing kernel; 32-wide: 4 CTAs per SM, -1 %
     bool zm_addout = true;         // B200REG_ZM_ADDOUT=0: D + U formed inside the displacement smoothing (staged twice) instead of at the end of the update smoothing
     bool force_zm1 = false;        // B200REG_FORCE_ZM1=1: first-generation fused smoothing kernel

@@ -303,7 +303,7 @@ template <int R, int TXW = ZM_TX>
 struct Zm2Threads {
     static constexpr int value = (ZM_TY + 2 * R) * (TXW / 4);
 };
-// ---- TMA bulk-copy staging (cp.async.bulk -> SASS UBLKCP) with mbarrier completion -----------------------------------
+// ---- TMA staging (cp.async.bulk.tensor.3d -> SASS UTMALDG) with mbarrier completion --------------------------------------
 __device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count));
@@ -313,47 +313,41 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(unsigned long long* bar, u
 {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ bool mbar_try_wait(unsigned a, unsigned parity)
+{
+    unsigned done;
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(a), "r"(parity)
+        : "memory");
+    return done != 0;
+}
 __device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity)
 {
-    // (only reachable in builds with -DB200REG_ENABLE_ZM_TMA)  A transaction count that never completes would spin for ever; after
-    // about two seconds of waiting the kernel traps instead, which turns a hang of an experimental variant into a reported error.
+    // A transaction count that never completes (a tensor map that does not match the launch) would spin for ever; after about two
+    // seconds of waiting the kernel traps instead, which turns a hang into a reported error.
     const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    if (mbar_try_wait(a, parity)) return;
     const long long t0 = clock64();
-    for (;;) {
-        unsigned done;
-        asm volatile(
-            "{\n"
-            ".reg .pred p;\n"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-            "selp.u32 %0, 1, 0, p;\n"
-            "}\n"
-            : "=r"(done)
-            : "r"(a), "r"(parity)
-            : "memory");
-        if (done) break;
+    while (!mbar_try_wait(a, parity))
         if (clock64() - t0 > 4000000000LL) __trap();
-    }
 }
-// one contiguous row global -> shared; size and both addresses are multiples of 16 bytes
-__device__ __forceinline__ void tma_bulk_g2s(double* smem_dst, const double* gsrc, unsigned bytes, unsigned long long* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                     (unsigned)__cvta_generic_to_shared(smem_dst)),
-                 "l"(gsrc), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
-                 : "memory");
-}
+// generic-proxy writes to shared memory (the border fix-up below) ordered before later async-proxy (TMA) writes to the same buffer
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-#ifdef B200REG_ENABLE_ZM_TMA
 }  // namespace b200
 #include <cuda.h>  // CUtensorMap and the cuTensorMapEncodeTiled prototype (the entry point itself comes from the runtime, no libcuda link)
 namespace b200 {
-// Tensor-map staging (B200REG_ZM_TMA=2): ONE cp.async.bulk.tensor.3d (SASS UTMALDG) per plane tile instead of one bulk copy per tile
-// row.  The field is described to the TMA unit as a 3-D tensor (x, y, component * nz + z) of float64; a tile that lies inside the
-// image in x and y is a box (AW, AH, 1) of it.  Replicated borders cannot be expressed (TMA fills out-of-range elements with
-// zeros), so border tiles keep the cp.async path; z is clamped by the coordinate.
-#define ZM_TMAP_PARAM , const __grid_constant__ CUtensorMap tmap
-#define ZM_TMAP_ARG(m) , m
-constexpr size_t ZM_SMEM_PAD = 128;  // the dynamic shared array is 128-byte aligned in this build
+// Tensor-map staging of the fused smoothing kernel: ONE cp.async.bulk.tensor.3d per plane tile.  The field is described to the TMA
+// unit as a 3-D tensor (x, y, component * nz + z) of float64; the staged tile + halo is a box (AW, AH, 1) of it whose corner may
+// lie outside the image: the TMA unit fills out-of-range elements with zeros, and the few halo cells of a BORDER tile are then
+// overwritten in shared memory with the replicated edge values (ZeroFluxNeumann), which are part of the same box.  z is clamped
+// through the coordinate.
 typedef CUresult (*zm_encode_tiled_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                        const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 inline zm_encode_tiled_fn zm_encode_tiled()
@@ -370,7 +364,7 @@ inline zm_encode_tiled_fn zm_encode_tiled()
     return fn;
 }
 // false when the geometry cannot be described (odd nx: row pitch not a multiple of 16 bytes) or the driver entry point is missing
-inline bool zm_make_tensor_map(const double* base, int nx, int ny, int nz_total, int box_w, int box_h, CUtensorMap* out)
+inline bool zm_make_tensor_map(const double* base, int nx, int ny, long nz_total, int box_w, int box_h, int l2_promotion, CUtensorMap* out)
 {
     zm_encode_tiled_fn enc = zm_encode_tiled();
     if (!enc || (nx % 2) != 0 || (reinterpret_cast<uintptr_t>(base) % 16) != 0 || box_w > 256 || box_h > 256) return false;
@@ -378,10 +372,9 @@ inline bool zm_make_tensor_map(const double* base, int nx, int ny, int nz_total,
     const cuuint64_t strides[2] = { (cuuint64_t)nx * sizeof(double), (cuuint64_t)nx * ny * sizeof(double) };
     const cuuint32_t box[3] = { (cuuint32_t)box_w, (cuuint32_t)box_h, 1u };
     const cuuint32_t estr[3] = { 1u, 1u, 1u };
-    // B200REG_ZM_TMA_L2 = 0 (default) | 1 | 2 | 3: L2 promotion of the tensor-map loads (none, 64, 128, 256 bytes)
-    static const int l2 = getenv("B200REG_ZM_TMA_L2") ? atoi(getenv("B200REG_ZM_TMA_L2")) : 0;
-    const CUtensorMapL2promotion promo = l2 == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
-                                         : (l2 == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : (l2 == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE));
+    const CUtensorMapL2promotion promo = l2_promotion == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                         : (l2_promotion == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                              : (l2_promotion == 3 ? CU_TENSOR_MAP_L2_PROMOTION_L2_256B : CU_TENSOR_MAP_L2_PROMOTION_NONE));
     return enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 3, const_cast<double*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                CU_TENSOR_MAP_SWIZZLE_NONE, promo, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
@@ -392,41 +385,46 @@ __device__ __forceinline__ void tma_tensor3d_g2s(double* smem_dst, const CUtenso
                  "l"(reinterpret_cast<unsigned long long>(tmap)), "r"(c0), "r"(c1), "r"(c2), "r"((unsigned)__cvta_generic_to_shared(bar))
                  : "memory");
 }
-#else
-#define ZM_TMAP_PARAM
-#define ZM_TMAP_ARG(m)
-constexpr size_t ZM_SMEM_PAD = 0;
-#endif
+__device__ __forceinline__ void tma_prefetch_descriptor(const CUtensorMap* tmap)
+{
+    asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<unsigned long long>(tmap)) : "memory");
+}
 
 // MODE 0: out = G(a).  MODE 1: out = G(a + b), both operands staged with cp.async and added in the x pass.
 // MODE 2: out = G(a + b), the next plane's operands are loaded into registers while the current plane is processed and
-// their sum is what gets staged: one shared buffer less, half the staging writes and x-pass reads of MODE 1.
+// their sum is what gets staged: one shared buffer less, half the staging writes and x-pass reads of MODE 1 (A/B builds only).
 // MODE 3: out = b + G(a): the second operand is added to the finished value when it is stored (one coalesced load per
 // output, no shared-memory traffic).  The Demons loop uses it to form D + G_u * U at the end of the update smoothing, so
 // that the displacement smoothing that follows is a plain MODE 0 pass instead of a MODE 1 pass.
-template <int R, int RZ, int MODE, int TXW>
+// TMA (MODE 0 / 3 only): plane tiles are staged by the TMA unit (one elected thread, one tensor-map copy per plane, completion
+// counted in bytes on an mbarrier) instead of one cp.async per element by every thread; same shared layout, same arithmetic.
+template <int R, int TXW>
+struct Zm2Layout {
+    static constexpr int RP = (R + 1) & ~1;  // x halo padded to an even count: 16-byte aligned shared rows
+    static constexpr int AW = TXW + 2 * RP, AH = ZM_TY + 2 * R, NA = AW * AH;
+    static constexpr int NAP = (NA + 15) & ~15;  // buffer stride: every staged plane starts on a 128-byte boundary (TMA destination)
+    static constexpr int NB = AH * TXW;
+};
+template <int R, int RZ, int MODE, int TXW, bool TMA>
 __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, 128 / TXW) conv3d_zm2_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out,
                                                                int nx, int ny, int nz, int zchunk, int nchunks,
-                                                               const __grid_constant__ SmallCoeffs kc, const DemonsCtrl* __restrict__ ctrl, int it, int use_tma ZM_TMAP_PARAM)
+                                                               const __grid_constant__ SmallCoeffs kc, const DemonsCtrl* __restrict__ ctrl, int it,
+                                                               const __grid_constant__ CUtensorMap tmap)
 {
     if (ctrl && it >= ctrl->halt_iter) return;
+    static_assert(!TMA || MODE == 0 || MODE == 3, "the tensor-map staging handles one staged operand");
     constexpr bool ADD = MODE == 1;     // second operand staged in shared memory
     constexpr bool REGADD = MODE == 2;  // operands summed in registers before staging
-    constexpr int RP = (R + 1) & ~1;  // x halo padded to an even count: 16-byte aligned shared rows
-    constexpr int AW = TXW + 2 * RP, AH = ZM_TY + 2 * R, NA = AW * AH;
+    using L = Zm2Layout<R, TXW>;
+    constexpr int RP = L::RP, AW = L::AW, AH = L::AH, NA = L::NA, NAP = L::NAP;
     constexpr int NR = 2 * RZ + 1;
     constexpr int NT = Zm2Threads<R, TXW>::value;
     constexpr int NYZ = 4 * TXW;  // threads that own voxels in the y / z passes
     constexpr int NLD = (NA + NT - 1) / NT;
-#ifdef B200REG_ENABLE_ZM_TMA
-    extern __shared__ __align__(128) double zm_smem128[];  // tensor-map copies need a 128-byte aligned destination
-    double* zm_smem = zm_smem128;
-#else
-    extern __shared__ __align__(16) double zm_smem[];
-#endif
-    double* Aa = zm_smem;                       // [2][NA]
-    double* Ab = zm_smem + 2 * NA;              // [2][NA] (ADD only)
-    double* B = zm_smem + (ADD ? 4 : 2) * NA;   // [AH][TX]
+    extern __shared__ __align__(128) double zm_smem[];
+    double* Aa = zm_smem;                        // [2][NAP]
+    double* Ab = zm_smem + 2 * NAP;              // [2][NAP] (ADD only)
+    double* B = zm_smem + (ADD ? 4 : 2) * NAP;   // [AH][TX]
 
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * TXW, y0 = blockIdx.y * ZM_TY;
@@ -437,43 +435,29 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, 128 / TXW) conv3d_z
     const double* __restrict__ bp = MODE != 0 ? b + (size_t)comp * vol : nullptr;
     double* __restrict__ op = out + (size_t)comp * vol;
 
+    // cp.async path: element e of a staged plane <-> clamped global offset.  TMA path: the same slots hold, for the halo cells of a
+    // border tile that lie outside the image, the shared-memory index of the replicated edge value (-1: nothing to fix).
     int goff[NLD];
+    __shared__ __align__(8) unsigned long long full_bar[2];
+    const bool border = x0 - RP < 0 || x0 + TXW + RP > nx || y0 - R < 0 || y0 + ZM_TY + R > ny;
 #pragma unroll
     for (int l = 0; l < NLD; ++l) {
         const int e = tid + l * NT;
         const int yy = e / AW, xx = e - yy * AW;
-        int gx = x0 - RP + xx, gy = y0 - R + yy;
-        gx = gx < 0 ? 0 : (gx > nx - 1 ? nx - 1 : gx);
-        gy = gy < 0 ? 0 : (gy > ny - 1 ? ny - 1 : gy);
-        goff[l] = e < NA ? gy * nx + gx : -1;
+        const int ux = x0 - RP + xx, uy = y0 - R + yy;
+        const int gx = ux < 0 ? 0 : (ux > nx - 1 ? nx - 1 : ux);
+        const int gy = uy < 0 ? 0 : (uy > ny - 1 ? ny - 1 : uy);
+        if (TMA) goff[l] = (e < NA && (gx != ux || gy != uy)) ? (gy - (y0 - R)) * AW + (gx - (x0 - RP)) : -1;
+        else goff[l] = e < NA ? gy * nx + gx : -1;
     }
-    // Interior tiles (no x clamping, 16-byte aligned rows) are staged by the TMA engine: one bulk copy per tile row
-    // (cp.async.bulk, completion counted in bytes on an mbarrier), issued by the first AH lanes of the CTA.  Rows
-    // clamp in y simply by their source address.  Border tiles keep the per-element cp.async (LDGSTS) path.
-    __shared__ __align__(8) unsigned long long full_bar[2];
-#ifdef B200REG_ENABLE_ZM_TMA  // row-wise bulk copies measured slower than the cp.async path (4.46 vs 3.96 ms / iteration): compiled out by default
-    // use_tma 1: one bulk copy per tile row (tiles interior in x); 2: one tensor-map copy per plane tile (tiles interior in x and y,
-    // one staged operand, staged plane a multiple of 128 bytes)
-    constexpr bool TENSOR_OK = !ADD && !REGADD && (NA * sizeof(double)) % 128 == 0;
-    const bool interior_t = TENSOR_OK && use_tma == 2 && x0 - RP >= 0 && x0 + TXW + RP <= nx && y0 - R >= 0 && y0 + ZM_TY + R <= ny;
-    const bool interior = interior_t || (use_tma == 1 && x0 - RP >= 0 && x0 + TXW + RP <= nx && (nx % 2) == 0);
-#else
-    constexpr bool interior = false, interior_t = false;
-    (void)use_tma;
-#endif
-    if (interior) {
+    if (TMA) {
         if (tid == 0) {
+            tma_prefetch_descriptor(&tmap);
             mbar_init(&full_bar[0], 1);
             mbar_init(&full_bar[1], 1);
             mbar_fence_init();
         }
         __syncthreads();
-    }
-    int row_off = 0;  // TMA path: source offset of this lane's tile row inside a plane
-    if (interior && !interior_t && tid < AH) {
-        int gy = y0 - R + tid;
-        gy = gy < 0 ? 0 : (gy > ny - 1 ? ny - 1 : gy);
-        row_off = gy * nx + (x0 - RP);
     }
     double pre_a[REGADD ? NLD : 1], pre_b[REGADD ? NLD : 1];  // MODE 2: operands of the next plane, in flight
     auto load_next = [&](int z) {
@@ -489,34 +473,23 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, 128 / TXW) conv3d_z
     auto store_next = [&](int buf) {
 #pragma unroll
         for (int l = 0; l < NLD; ++l)
-            if (goff[l] >= 0) Aa[buf * NA + tid + l * NT] = pre_a[l] + pre_b[l];
+            if (goff[l] >= 0) Aa[buf * NAP + tid + l * NT] = pre_a[l] + pre_b[l];
     };
     auto stage = [&](int z, int buf) {
         const int zc = z < 0 ? 0 : (z > nz - 1 ? nz - 1 : z);
-        const size_t zo = (size_t)zc * plane;
-#ifdef B200REG_ENABLE_ZM_TMA
-        if (interior_t) {
+        if (TMA) {
             if (tid == 0) {
                 mbar_arrive_expect_tx(&full_bar[buf], (unsigned)(AH * AW * sizeof(double)));
-                tma_tensor3d_g2s(Aa + buf * NA, &tmap, x0 - RP, y0 - R, comp * nz + zc, &full_bar[buf]);
+                tma_tensor3d_g2s(Aa + buf * NAP, &tmap, x0 - RP, y0 - R, comp * nz + zc, &full_bar[buf]);
             }
             return;
         }
-#endif
-        if (interior) {
-            if (tid == 0) mbar_arrive_expect_tx(&full_bar[buf], (unsigned)((ADD ? 2 : 1) * AH * AW * sizeof(double)));
-            __syncwarp();
-            if (tid < AH) {
-                tma_bulk_g2s(Aa + buf * NA + tid * AW, ap + zo + row_off, (unsigned)(AW * sizeof(double)), &full_bar[buf]);
-                if (ADD) tma_bulk_g2s(Ab + buf * NA + tid * AW, bp + zo + row_off, (unsigned)(AW * sizeof(double)), &full_bar[buf]);
-            }
-            return;
-        }
+        const size_t zo = (size_t)zc * plane;
 #pragma unroll
         for (int l = 0; l < NLD; ++l)
             if (goff[l] >= 0) {
-                cp_async8(Aa + buf * NA + tid + l * NT, ap + zo + goff[l]);
-                if (ADD) cp_async8(Ab + buf * NA + tid + l * NT, bp + zo + goff[l]);
+                cp_async8(Aa + buf * NAP + tid + l * NT, ap + zo + goff[l]);
+                if (ADD) cp_async8(Ab + buf * NAP + tid + l * NT, bp + zo + goff[l]);
             }
         cp_async_commit();
     };
@@ -552,10 +525,21 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, 128 / TXW) conv3d_z
                     __syncthreads();  // plane q (summed and stored at the end of step q - 1) is visible; B may be rewritten
                     if (q + 1 < nsteps) load_next(zbeg + q + 1);
                 } else {
-                if (interior) mbar_wait(&full_bar[buf], (unsigned)((q >> 1) & 1));
-                else cp_async_wait_all();
-                __syncthreads();
-                if (q + 1 < nsteps) stage(zbeg + q + 1, buf ^ 1);
+                    if (TMA) {
+                        mbar_wait(&full_bar[buf], (unsigned)((q >> 1) & 1));
+                        if (border) {
+                            // replicate the image edge into the zero-filled halo cells (sources are cells inside the image, targets
+                            // cells outside it: disjoint, so no barrier is needed between the reads and the writes)
+#pragma unroll
+                            for (int l = 0; l < NLD; ++l)
+                                if (goff[l] >= 0) Aa[buf * NAP + tid + l * NT] = Aa[buf * NAP + goff[l]];
+                            fence_proxy_async_smem();  // these generic-proxy stores precede the TMA overwrite of this buffer two steps on
+                        }
+                    } else {
+                        cp_async_wait_all();
+                    }
+                    __syncthreads();
+                    if (q + 1 < nsteps) stage(zbeg + q + 1, buf ^ 1);
                 }
                 // ---- x pass: per task two output pairs {2cx, 2cx+1} and {32+2cx, 32+2cx+1} of one row (rows incl. the
                 // y halo).  Lanes read consecutive 16-byte words: conflict-free 128-bit shared loads and stores.
@@ -564,13 +548,13 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, 128 / TXW) conv3d_z
 #pragma unroll
                     for (int h = 0; h < 2; ++h) {
                         const int xb = 2 * cx + h * (TXW / 2);
-                        const double2* ra = reinterpret_cast<const double2*>(Aa + buf * NA + yy * AW + xb);
+                        const double2* ra = reinterpret_cast<const double2*>(Aa + buf * NAP + yy * AW + xb);
                         double w[2 + 2 * RP];
 #pragma unroll
                         for (int v = 0; v < 1 + RP; ++v) {
                             double2 t2 = ra[v];
                             if (ADD) {
-                                const double2 u2 = reinterpret_cast<const double2*>(Ab + buf * NA + yy * AW + xb)[v];
+                                const double2 u2 = reinterpret_cast<const double2*>(Ab + buf * NAP + yy * AW + xb)[v];
                                 t2.x = t2.x + u2.x;
                                 t2.y = t2.y + u2.y;
                             }
@@ -625,223 +609,50 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, 128 / TXW) conv3d_z
     }
 }
 
-// ---- fused 3-D smoothing, third generation: even / odd pair-split shared rows ------------------------------------------
-// Same scheme, same operation order and bit-identical results as conv3d_zm2_kernel; what changes is the shared-memory
-// layout.  Every row (staged input rows and x-pass output rows alike) stores its 16-byte pairs of doubles split by
-// parity -- even pairs first, odd pairs after -- so that a thread can own FOUR consecutive x outputs: its 2 + RP input
-// pairs 2t, 2t+1, ... alternate between the two halves, and within each half the lanes of a warp read consecutive
-// 16-byte words (conflict-free LDS.128).  The x pass then needs 2 + RP 128-bit loads per 4 outputs instead of
-// 2 (1 + RP) (R = 2: 4 instead of 6; with the add fused: 8 instead of 12); stores and the y pass keep their wavefront
-// counts.  Shared-memory wavefronts per 128 outputs: 67 -> 57 (plain), 108 -> 88 (add).
-// Row geometry of a pair-split row that holds W doubles: the odd half starts at the first offset >= the even half's
-// size that is 8 doubles (mod 16), so that the 8 + 8 doubles a half-warp touches in the two halves fall on disjoint
-// banks (64-bit accesses are served per half-warp); the row stride keeps 16-byte alignment.
-template <int W>
-struct Zm3Row {
-    static constexpr int NE = (W / 2 + 1) / 2;                               // even pairs
-    static constexpr int NO = W / 2 - NE;                                    // odd pairs
-    static constexpr int OBASE = ((2 * NE + 7) / 16) * 16 + 8 >= 2 * NE ? ((2 * NE + 7) / 16) * 16 + 8 : ((2 * NE + 7) / 16) * 16 + 24;  // doubles
-    static constexpr int STRIDE = OBASE + 2 * NO;                            // doubles (even)
-};
-template <int W>
-__device__ __forceinline__ int zm3_pos(int xx)
-{
-    // position (in doubles) of x coordinate xx inside a pair-split row
-    const int p = xx >> 1;
-    return ((p & 1) ? Zm3Row<W>::OBASE + ((p >> 1) << 1) : ((p >> 1) << 1)) + (xx & 1);
-}
-template <int R, int RZ, bool ADD>
-__global__ void __launch_bounds__(Zm2Threads<R>::value, 2) conv3d_zm3_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out,
-                                                               int nx, int ny, int nz, int zchunk, int nchunks,
-                                                               const __grid_constant__ SmallCoeffs kc, const DemonsCtrl* __restrict__ ctrl, int it)
-{
-    if (ctrl && it >= ctrl->halt_iter) return;
-    constexpr int RP = (R + 1) & ~1;
-    constexpr int AW = ZM_TX + 2 * RP, AH = ZM_TY + 2 * R;
-    constexpr int AS = Zm3Row<AW>::STRIDE, BS = Zm3Row<ZM_TX>::STRIDE;   // row strides (doubles)
-    constexpr int NA = AS * AH;                    // doubles per staged plane
-    constexpr int NEL = AW * AH;                   // elements per staged plane
-    constexpr int NR = 2 * RZ + 1;
-    constexpr int NT = Zm2Threads<R>::value;
-    constexpr int NLD = (NEL + NT - 1) / NT;
-    constexpr int NPAIR = 2 + RP;                  // input pairs of one x-pass task
-    constexpr int OA2 = Zm3Row<AW>::OBASE / 2;     // odd half of a staged row, in pairs
-    constexpr int OB2 = Zm3Row<ZM_TX>::OBASE / 2;  // odd half of an x-pass output row, in pairs
-    extern __shared__ __align__(16) double zm_smem[];
-    double* Aa = zm_smem;                       // [2][NA]
-    double* Ab = zm_smem + 2 * NA;              // [2][NA] (ADD only)
-    double* B = zm_smem + (ADD ? 4 : 2) * NA;   // [AH][BS]
-
-    const int tid = threadIdx.x;
-    const int x0 = blockIdx.x * ZM_TX, y0 = blockIdx.y * ZM_TY;
-    const int comp = blockIdx.z / nchunks, chunk = blockIdx.z % nchunks;
-    const int z0 = chunk * zchunk, z1 = min(nz, z0 + zchunk);
-    const size_t plane = (size_t)nx * ny, vol = plane * nz;
-    const double* __restrict__ ap = a + (size_t)comp * vol;
-    const double* __restrict__ bp = ADD ? b + (size_t)comp * vol : nullptr;
-    double* __restrict__ op = out + (size_t)comp * vol;
-
-    int goff[NLD], spos[NLD];
-#pragma unroll
-    for (int l = 0; l < NLD; ++l) {
-        const int e = tid + l * NT;
-        const int yy = e / AW, xx = e - yy * AW;
-        int gx = x0 - RP + xx, gy = y0 - R + yy;
-        gx = gx < 0 ? 0 : (gx > nx - 1 ? nx - 1 : gx);
-        gy = gy < 0 ? 0 : (gy > ny - 1 ? ny - 1 : gy);
-        goff[l] = e < NEL ? gy * nx + gx : -1;
-        spos[l] = yy * AS + zm3_pos<AW>(xx);
-    }
-    auto stage = [&](int z, int buf) {
-        const int zc = z < 0 ? 0 : (z > nz - 1 ? nz - 1 : z);
-        const size_t zo = (size_t)zc * plane;
-#pragma unroll
-        for (int l = 0; l < NLD; ++l)
-            if (goff[l] >= 0) {
-                cp_async8(Aa + buf * NA + spos[l], ap + zo + goff[l]);
-                if (ADD) cp_async8(Ab + buf * NA + spos[l], bp + zo + goff[l]);
-            }
-        cp_async_commit();
-    };
-
-    // y/z-pass ownership: column x = tid % 64, rows 4*yb .. 4*yb+3
-    const int ox = tid & (ZM_TX - 1), yb = tid >> 6;
-    const int gx = x0 + ox;
-    const int bpos = zm3_pos<ZM_TX>(ox);
-    double ring[NR][4];
-    const int zbeg = z0 - RZ, nsteps = (z1 - z0) + 2 * RZ;
-    stage(zbeg, 0);
-    for (int q0 = 0; q0 < nsteps; q0 += NR) {
-#pragma unroll
-        for (int s = 0; s < NR; ++s) {
-            const int q = q0 + s;
-            if (q < nsteps) {
-                const int buf = q & 1;
-                cp_async_wait_all();
-                __syncthreads();
-                if (q + 1 < nsteps) stage(zbeg + q + 1, buf ^ 1);
-                // ---- x pass: task (row yy, quad cx) -> outputs 4cx .. 4cx+3 from input pairs 2cx .. 2cx+1+RP
-                {
-                    const int yy = tid >> 4, cx = tid & 15;
-                    const double2* ra = reinterpret_cast<const double2*>(Aa + buf * NA + yy * AS);
-                    const double2* rb = reinterpret_cast<const double2*>(Ab + buf * NA + yy * AS);
-                    double w[2 * NPAIR];
-#pragma unroll
-                    for (int v = 0; v < NPAIR; ++v) {
-                        // pair 2cx + v: even v -> even half at index cx + v/2, odd v -> odd half at index cx + (v-1)/2
-                        const int idx = (v & 1) ? OA2 + cx + (v >> 1) : cx + (v >> 1);
-                        double2 t2 = ra[idx];
-                        if (ADD) {
-                            const double2 u2 = rb[idx];
-                            t2.x = t2.x + u2.x;
-                            t2.y = t2.y + u2.y;
-                        }
-                        w[2 * v] = t2.x;
-                        w[2 * v + 1] = t2.y;
-                    }
-                    double o[4];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        double sum = kc.k[0][0] * w[j + (RP - R)];
-#pragma unroll
-                        for (int t = 1; t <= 2 * R; ++t) sum += kc.k[0][t] * w[j + (RP - R) + t];
-                        o[j] = sum;
-                    }
-                    double2* wb = reinterpret_cast<double2*>(B + yy * BS);
-                    wb[cx] = make_double2(o[0], o[1]);         // pair 2cx   (even half)
-                    wb[OB2 + cx] = make_double2(o[2], o[3]);   // pair 2cx+1 (odd half)
-                }
-                __syncthreads();
-                // ---- y pass: sliding window over 4 + 2R rows of this thread's column
-                if (tid < ZM_NT) {
-                    double col[4 + 2 * R];
-#pragma unroll
-                    for (int i = 0; i < 4 + 2 * R; ++i) col[i] = B[(4 * yb + i) * BS + bpos];
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        double sum = kc.k[1][0] * col[j];
-#pragma unroll
-                        for (int t = 1; t <= 2 * R; ++t) sum += kc.k[1][t] * col[j + t];
-                        ring[s][j] = sum;
-                    }
-                }
-                // ---- z pass over the ring (slot s is the newest plane; oldest is slot (s + 1) % NR)
-                if (tid < ZM_NT && q >= 2 * RZ) {
-                    const int zo = zbeg + q - RZ;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        double sum = kc.k[2][0] * ring[(s + 1) % NR][j];
-#pragma unroll
-                        for (int t = 1; t < NR; ++t) sum += kc.k[2][t] * ring[(s + 1 + t) % NR][j];
-                        const int gy = y0 + 4 * yb + j;
-                        if (gx < nx && gy < ny) op[(size_t)zo * plane + (size_t)gy * nx + gx] = sum;
-                    }
-                }
-            }
-        }
-    }
-}
-
 template <int R, int RZ, int TXW>
 inline int launch_zm2_tx(b200reg_ctx* ctx, const double* a, const double* b, double* out, int nx, int ny, int nz, dim3 g, int zchunk, int nchunks,
                          const SmallCoeffs& sc, const DemonsCtrl* ctrl, int it, bool addout)
 {
-    constexpr int RP = (R + 1) & ~1;
-    constexpr int NA = (TXW + 2 * RP) * (ZM_TY + 2 * R);
-    constexpr int NB = (ZM_TY + 2 * R) * TXW;
+    using L = Zm2Layout<R, TXW>;
     constexpr int NT = Zm2Threads<R, TXW>::value;
     g.x = (nx + TXW - 1) / TXW;
-    int tma_mode = 0;
-#ifdef B200REG_ENABLE_ZM_TMA
     CUtensorMap tm;
     memset(&tm, 0, sizeof(tm));
-    tma_mode = ctx->zm_tma;
-    // the tensor map describes operand a: (nx, ny, components * nz) float64, box = one staged plane tile
-    if (tma_mode == 2 && !zm_make_tensor_map(a, nx, ny, nz * (int)(g.z / nchunks), TXW + 2 * RP, ZM_TY + 2 * R, &tm)) tma_mode = 0;
-#endif
+    // the tensor map describes operand a: (nx, ny, components * nz) float64, box = one staged plane tile (B200REG_ZM_TMA=0: cp.async staging)
+    const bool tma = ctx->zm_tma != 0 && zm_make_tensor_map(a, nx, ny, (long)nz * (long)(g.z / nchunks), L::AW, L::AH, ctx->zm_tma_l2, &tm);
+    constexpr size_t smem1 = (size_t)(2 * L::NAP + L::NB) * sizeof(double);
+#define ZM2_GO(MODE, TMA_, A, B_)                                                                                                            \
+    do {                                                                                                                                     \
+        B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, MODE, TXW, TMA_>, smem1));                                                \
+        conv3d_zm2_kernel<R, RZ, MODE, TXW, TMA_><<<g, NT, smem1, ctx->stream>>>(A, B_, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, tm); \
+    } while (0)
     if (b && addout) {
-        constexpr size_t smem = (size_t)(2 * NA + NB) * sizeof(double) + ZM_SMEM_PAD;
-        B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, 3, TXW>, smem));
-        conv3d_zm2_kernel<R, RZ, 3, TXW><<<g, NT, smem, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, tma_mode == 2 ? 2 : 0 ZM_TMAP_ARG(tm));
+        if (tma) ZM2_GO(3, true, a, b);
+        else ZM2_GO(3, false, a, b);
         return B200REG_OK;
     }
 #ifdef B200REG_AB_VARIANTS
     if (b && ctx->zm_regadd) {
-        constexpr size_t smem = (size_t)(2 * NA + NB) * sizeof(double);
-        B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, 2, TXW>, smem));
-        conv3d_zm2_kernel<R, RZ, 2, TXW><<<g, NT, smem, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, 0 ZM_TMAP_ARG(tm));
-    } else
+        ZM2_GO(2, false, a, b);
+        return B200REG_OK;
+    }
 #endif
     if (b) {
-        constexpr size_t smem = (size_t)(4 * NA + NB) * sizeof(double);
-        B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, 1, TXW>, smem));
-        conv3d_zm2_kernel<R, RZ, 1, TXW><<<g, NT, smem, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, tma_mode == 1 ? 1 : 0 ZM_TMAP_ARG(tm));
+        constexpr size_t smem2 = (size_t)(4 * L::NAP + L::NB) * sizeof(double);
+        B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, 1, TXW, false>, smem2));
+        conv3d_zm2_kernel<R, RZ, 1, TXW, false><<<g, NT, smem2, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, tm);
     } else {
-        constexpr size_t smem = (size_t)(2 * NA + NB) * sizeof(double) + ZM_SMEM_PAD;
-        B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, 0, TXW>, smem));
-        conv3d_zm2_kernel<R, RZ, 0, TXW><<<g, NT, smem, ctx->stream>>>(a, nullptr, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, tma_mode ZM_TMAP_ARG(tm));
+        if (tma) ZM2_GO(0, true, a, nullptr);
+        else ZM2_GO(0, false, a, nullptr);
     }
+#undef ZM2_GO
     return B200REG_OK;
 }
 template <int R, int RZ>
 inline int launch_zm2_rz(b200reg_ctx* ctx, const double* a, const double* b, double* out, int nx, int ny, int nz, dim3 g, int zchunk, int nchunks,
                          const SmallCoeffs& sc, const DemonsCtrl* ctrl, int it, bool addout)
 {
-#ifdef B200REG_AB_VARIANTS  // measured alternatives (profiles/r01_summary.md), compiled with make EXTRA=-DB200REG_AB_VARIANTS
-    constexpr int RP = (R + 1) & ~1;
-    if (ctx->zm_split_rows && !addout) {
-        constexpr int NA3 = Zm3Row<ZM_TX + 2 * RP>::STRIDE * (ZM_TY + 2 * R), NB3 = Zm3Row<ZM_TX>::STRIDE * (ZM_TY + 2 * R);
-        if (b) {
-            constexpr size_t smem = (size_t)(4 * NA3 + NB3) * sizeof(double);
-            B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm3_kernel<R, RZ, true>, smem));
-            conv3d_zm3_kernel<R, RZ, true><<<g, Zm2Threads<R>::value, smem, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it);
-        } else {
-            constexpr size_t smem = (size_t)(2 * NA3 + NB3) * sizeof(double);
-            B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm3_kernel<R, RZ, false>, smem));
-            conv3d_zm3_kernel<R, RZ, false><<<g, Zm2Threads<R>::value, smem, ctx->stream>>>(a, nullptr, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it);
-        }
-        return B200REG_OK;
-    }
+#ifdef B200REG_AB_VARIANTS  // measured alternative (profiles/r01_summary.md), compiled with make EXTRA=-DB200REG_AB_VARIANTS
     if (!ctx->zm_tx32) return launch_zm2_tx<R, RZ, 64>(ctx, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it, addout);
 #endif
     return launch_zm2_tx<R, RZ, 32>(ctx, a, b, out, nx, ny, nz, g, zchunk, nchunks, sc, ctrl, it, addout);
@@ -878,7 +689,7 @@ inline int launch_conv3d_zmarch(b200reg_ctx* ctx, const double* a, const double*
         for (int t = 0; t <= 2 * kc[ax].r; ++t) sc.k[ax][t] = kc[ax].k[t];
     }
 #ifdef B200REG_AB_VARIANTS
-    const int txw = (ctx->zm_tx32 && !ctx->zm_split_rows) ? 32 : ZM_TX;
+    const int txw = ctx->zm_tx32 ? 32 : ZM_TX;
 #else
     const int txw = 32;
 #endif

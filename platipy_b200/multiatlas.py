@@ -442,6 +442,8 @@ def run_segmentation(img, atlas_set=None, settings=MUTLIATLAS_SETTINGS_DEFAULTS,
                     if s is not None and s in local[a]["DIR"]:
                         eng.vote_accumulate(eng.cast(local[a]["DIR"][s], np.uint8), local[a]["DIR"]["Weight Map"], stack[r * per + j], None, first)
                         first = False
+    if timings is not None:
+        timings.update(exchange_bytes=int(stack.numel() * stack.element_size()), grid=[int(x), int(y), int(z)], payload=payload)
     t0 = tick("pack_s", t0)
     with torch.cuda.stream(eng.stream):
         block = exchange_reduce_scatter(stack, group)
