@@ -121,6 +121,20 @@ int b200reg_synchronize(b200reg_ctx* ctx);
 /* number of kernels this context has launched since creation (bench.py's gpu_launches) */
 int64_t b200reg_launch_count(b200reg_ctx* ctx);
 
+/* Named semantic switches (process-wide).  The arithmetic this library replaces lives in ITK 5.3, which could not be re-read when
+ * it was written; every recalled behaviour of medium confidence that is cheap to state both ways is a switch
+ * whose default is the recalled behaviour.  The CPU oracle has the same switches under the same names (orc_set_semantic), and
+ * tools/validate_against_sitk.py reports the setting that matches a real SimpleITK.  Names / values:
+ *   discrete_gaussian_axis_order     0 = z, y, x    1 = x, y, z      (DiscreteGaussianImageFilter: utils.py:226, fusion.py:168,279)
+ *   recursive_gaussian_axis_order    0 = z, x, y    1 = x, y, z      (SmoothingRecursiveGaussian: deformable.py:158)
+ *   resample_linear_scanline         1 = scan-line continuous index for linear transforms, 0 = per voxel (utils.py:176-190)
+ *   dvf_transform_interpolation      0 = weighted sum of the 8 neighbours, 1 = nested lerps (DisplacementFieldTransform)
+ *   vector_resample_interpolation    0 = nested lerps, 1 = weighted sum (sitk.Resample of a vector image: deformable.py:130,137,154,185)
+ *   binary_threshold_in_pixel_type   0 = bounds compared as real numbers, 1 = bounds cast to the pixel type (fusion.py:217-220)
+ * b200reg_set_semantic returns B200REG_ERR_ARG for an unknown name; b200reg_get_semantic returns -1. */
+int b200reg_set_semantic(const char* name, int value);
+int b200reg_get_semantic(const char* name);
+
 /* ---- memory helpers (hosts without their own CUDA allocator) --------------------------------------- */
 int b200reg_malloc(b200reg_ctx* ctx, size_t bytes, void** d_ptr);
 int b200reg_free(b200reg_ctx* ctx, void* d_ptr);

@@ -36,6 +36,41 @@
 #define ORC_API __attribute__((visibility("default")))
 
 /* ------------------------------------------------------------------------------------------------ */
+/* Named semantic switches.  Every ITK behaviour this restatement could only RECALL (confidence M)   */
+/* and that is cheap to state both ways is a switch with a name: the default is the recalled behaviour, the other      */
+/* value is the plausible alternative.  libb200reg.so has the same switches under the same names                       */
+/* (b200reg_set_semantic), so a correction found against a real SimpleITK is a flag flip on both sides, not an edit    */
+/* of CUDA code.  tools/validate_against_sitk.py reports which setting of each switch matches SimpleITK.               */
+/* ------------------------------------------------------------------------------------------------ */
+typedef struct { const char* name; int value; const char* meaning; } orc_semantic;
+static orc_semantic g_semantics[] = {
+    { "discrete_gaussian_axis_order", 0, "DiscreteGaussianImageFilter pass order: 0 = z, y, x (recalled); 1 = x, y, z" },
+    { "recursive_gaussian_axis_order", 0, "SmoothingRecursiveGaussianImageFilter pass order: 0 = z, x, y (recalled); 1 = x, y, z" },
+    { "resample_linear_scanline", 1, "ResampleImageFilter with a linear transform: 1 = scan-line continuous index (recalled); 0 = per-voxel" },
+    { "dvf_transform_interpolation", 0, "interpolator inside DisplacementFieldTransform: 0 = weighted sum of 8 neighbours (recalled); 1 = nested lerps" },
+    { "vector_resample_interpolation", 0, "linear interpolation of a vector image in ResampleImageFilter: 0 = nested lerps (recalled); 1 = weighted sum" },
+    { "binary_threshold_in_pixel_type", 0, "BinaryThreshold bounds: 0 = compared as real numbers (recalled); 1 = cast to the pixel type first" },
+};
+#define ORC_N_SEMANTICS ((int)(sizeof(g_semantics) / sizeof(g_semantics[0])))
+enum { SEM_DG_ORDER = 0, SEM_RG_ORDER, SEM_SCANLINE, SEM_DVF_INTERP, SEM_VEC_INTERP, SEM_BT_PIXEL };
+#define SEM(i) (g_semantics[i].value)
+ORC_API int orc_set_semantic(const char* name, int value)
+{
+    for (int i = 0; i < ORC_N_SEMANTICS; ++i)
+        if (strcmp(g_semantics[i].name, name) == 0) { g_semantics[i].value = value; return 0; }
+    return -1;
+}
+ORC_API int orc_get_semantic(const char* name)
+{
+    for (int i = 0; i < ORC_N_SEMANTICS; ++i)
+        if (strcmp(g_semantics[i].name, name) == 0) return g_semantics[i].value;
+    return -1;
+}
+ORC_API int orc_num_semantics(void) { return ORC_N_SEMANTICS; }
+ORC_API const char* orc_semantic_name(int i) { return (i >= 0 && i < ORC_N_SEMANTICS) ? g_semantics[i].name : NULL; }
+ORC_API const char* orc_semantic_meaning(int i) { return (i >= 0 && i < ORC_N_SEMANTICS) ? g_semantics[i].meaning : NULL; }
+
+/* ------------------------------------------------------------------------------------------------ */
 /* Geometry (itk::ImageBase): index<->physical point transforms                                      */
 /* ------------------------------------------------------------------------------------------------ */
 typedef struct {
@@ -299,7 +334,8 @@ static inline void apply_chain(const tfmx* t, int nt, double* p)
             double c[3], dd[3];
             pt2cidx(&t[i].g, p, c);
             if (inside_buffer(&t[i].g, c)) {
-                interp_wsum_vec3(t[i].dvf, &t[i].g, c, dd);
+                if (SEM(SEM_DVF_INTERP)) interp_linear_vec3(t[i].dvf, &t[i].g, c, dd);
+                else interp_wsum_vec3(t[i].dvf, &t[i].g, c, dd);
                 p[0] += dd[0]; p[1] += dd[1]; p[2] += dd[2];
             }
         }
@@ -307,6 +343,7 @@ static inline void apply_chain(const tfmx* t, int nt, double* p)
 }
 static int chain_is_linear(const tfmx* t, int nt)
 {
+    if (!SEM(SEM_SCANLINE)) return 0;
     for (int i = 0; i < nt; ++i) if (t[i].kind != ORC_TFM_AFFINE) return 0;
     return 1;
 }
@@ -508,7 +545,8 @@ ORC_API int orc_resample_vec3(const double* in, const orc_geom* gin, double* out
                 size_t o = (((size_t)k * go.ny + j) * go.nx + i) * 3;
                 out_to_in_cidx(&go, &gi, t, ntf, linear, i, j, k, c);
                 if (inside_buffer(&gi, c)) {
-                    interp_linear_vec3(in, &gi, c, out + o);
+                    if (SEM(SEM_VEC_INTERP)) interp_wsum_vec3(in, &gi, c, out + o);
+                    else interp_linear_vec3(in, &gi, c, out + o);
                 } else {
                     out[o] = out[o + 1] = out[o + 2] = default_value;
                 }
@@ -673,7 +711,8 @@ ORC_API int orc_discrete_gaussian_f32(const float* in, float* out, const orc_geo
     const float* src = in;
     float* dsts[3] = { a, b, out };
     int pass = 0;
-    for (int axis = 2; axis >= 0; --axis, ++pass) {
+    for (pass = 0; pass < 3; ++pass) {
+        const int axis = SEM(SEM_DG_ORDER) ? pass : 2 - pass;
         double t = variance[axis];
         if (use_spacing) t = t / (g->spacing[axis] * g->spacing[axis]);
         int r = orc_gaussian_operator(t, max_error, max_width, kern, cap);
@@ -991,7 +1030,8 @@ ORC_API int orc_recursive_gaussian_vec3(double* field, const orc_geom* g, const 
     const int dims[3] = { nx, ny, nz };
     const size_t strides[3] = { 1, (size_t)nx, (size_t)nx * ny };
     if (nx < 4 || ny < 4 || nz < 4) return -2;
-    const int order[3] = { 2, 0, 1 };
+    const int order_zxy[3] = { 2, 0, 1 }, order_xyz[3] = { 0, 1, 2 };
+    const int* order = SEM(SEM_RG_ORDER) ? order_xyz : order_zxy;
     for (int pass = 0; pass < 3; ++pass) {
         const int axis = order[pass];
         deriche_t c;

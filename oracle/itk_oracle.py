@@ -68,6 +68,12 @@ def lib():
         _lib.orc_recursive_gaussian_vec3.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.orc_transform_to_dvf.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         _lib.orc_set_num_threads.argtypes = [C.c_int]
+        _lib.orc_set_semantic.argtypes = [C.c_char_p, C.c_int]
+        _lib.orc_get_semantic.argtypes = [C.c_char_p]
+        _lib.orc_semantic_name.restype = C.c_char_p
+        _lib.orc_semantic_name.argtypes = [C.c_int]
+        _lib.orc_semantic_meaning.restype = C.c_char_p
+        _lib.orc_semantic_meaning.argtypes = [C.c_int]
         _lib.orc_bspline3_coefficients.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
         _lib.orc_binary_fillhole.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         _lib.orc_largest_component.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -85,6 +91,41 @@ def num_threads():
 
 def set_num_threads(n):
     lib().orc_set_num_threads(int(n))
+
+
+def semantics():
+    """{name: (value, meaning)} of the named ITK-semantics switches (itk_oracle.c: g_semantics)."""
+    l = lib()
+    return {l.orc_semantic_name(i).decode(): (l.orc_get_semantic(l.orc_semantic_name(i)), l.orc_semantic_meaning(i).decode())
+            for i in range(l.orc_num_semantics())}
+
+
+def set_semantic(name, value):
+    if lib().orc_set_semantic(name.encode(), int(value)) != 0:
+        raise ValueError(f"unknown semantic switch {name!r}")
+
+
+def get_semantic(name):
+    v = lib().orc_get_semantic(name.encode())
+    if v < 0:
+        raise ValueError(f"unknown semantic switch {name!r}")
+    return v
+
+
+class semantic:
+    """``with semantic(name, value): ...`` -- flips a switch for the block and restores it."""
+
+    def __init__(self, name, value):
+        self.name, self.value = name, value
+
+    def __enter__(self):
+        self.old = get_semantic(self.name)
+        set_semantic(self.name, self.value)
+        return self
+
+    def __exit__(self, *exc):
+        set_semantic(self.name, self.old)
+        return False
 
 
 def make_geom(size, spacing, origin, direction):

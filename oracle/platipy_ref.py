@@ -335,13 +335,22 @@ def combine_labels(atlas_set, structure_name, label="DIR", threshold=1e-4, smoot
     return out
 
 
+def _binary_threshold(arr, lower, upper):
+    """BinaryThresholdImageFilter -> UInt8 {0, 1}; semantic switch binary_threshold_in_pixel_type: the bounds are cast to an
+    integer pixel type (clamped to its range, truncated) before the comparison instead of being compared as real numbers."""
+    if orc.get_semantic("binary_threshold_in_pixel_type") and arr.dtype.kind in "iu":
+        info = np.iinfo(arr.dtype)
+        lower, upper = (int(min(max(v, info.min), info.max)) for v in (lower, upper))
+    return ((arr >= lower) & (arr <= upper)).astype(np.uint8)
+
+
 def combine_labels_staple(label_list_dict, threshold=1e-4):
     # fusion.py:205-236
     names = np.unique([n for d in label_list_dict.values() for n in d.keys()])
     out = {}
     for s in names:
         imgs = [label_list_dict[i][s] for i in label_list_dict]
-        binary = [((im.array >= 0.5) & (im.array <= 255)).astype(np.uint8) for im in imgs]  # BinaryThreshold(lower=0.5, upper=255)
+        binary = [_binary_threshold(im.array, 0.5, 255) for im in imgs]  # BinaryThreshold(lower=0.5, upper=255)
         W, _, _, _ = orc.staple(binary)
         W = orc.rescale_threshold_f64(W, threshold)
         out[str(s)] = _like(W, imgs[0])

@@ -61,6 +61,8 @@ SIGNATURES = {
     "b200reg_set_stream": (C.c_int, [_P, _P]),
     "b200reg_synchronize": (C.c_int, [_P]),
     "b200reg_launch_count": (C.c_int64, [_P]),
+    "b200reg_set_semantic": (C.c_int, [C.c_char_p, C.c_int]),
+    "b200reg_get_semantic": (C.c_int, [C.c_char_p]),
     "b200reg_malloc": (C.c_int, [_P, C.c_size_t, C.POINTER(_P)]),
     "b200reg_free": (C.c_int, [_P, _P]),
     "b200reg_malloc_host": (C.c_int, [C.c_size_t, C.POINTER(_P)]),
@@ -158,6 +160,22 @@ def load():
         raise ImportError("libb200reg.so ABI version mismatch")
     _lib = lib
     return lib
+
+
+SEMANTIC_SWITCHES = ("discrete_gaussian_axis_order", "recursive_gaussian_axis_order", "resample_linear_scanline", "dvf_transform_interpolation",
+                     "vector_resample_interpolation", "binary_threshold_in_pixel_type")
+
+
+def set_semantic(name, value):
+    """Flip one of the named ITK-semantics switches of the library (process-wide; see include/b200reg.h)."""
+    check(load().b200reg_set_semantic(name.encode(), int(value)))
+
+
+def get_semantic(name):
+    v = load().b200reg_get_semantic(name.encode())
+    if v < 0:
+        raise ValueError(f"unknown semantic switch {name!r}")
+    return v
 
 
 class B200RegNotImplemented(NotImplementedError):

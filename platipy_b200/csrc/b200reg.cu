@@ -120,6 +120,20 @@ API int b200reg_synchronize(b200reg_ctx* ctx)
 }
 API int64_t b200reg_launch_count(b200reg_ctx* ctx) { return ctx ? ctx->launches : -1; }
 
+// ---- named semantic switches (process-wide; see common.cuh) ---------------------------------------------------------------------
+API int b200reg_set_semantic(const char* name, int value)
+{
+    int* slot = semantic_slot(name);
+    REQUIRE(slot != nullptr, "unknown semantic switch '%s'", name ? name : "(null)");
+    *slot = value;
+    return B200REG_OK;
+}
+API int b200reg_get_semantic(const char* name)
+{
+    const int* slot = semantic_slot(name);
+    return slot ? *slot : -1;
+}
+
 // ---- memory helpers ---------------------------------------------------------------------------------------
 API int b200reg_malloc(b200reg_ctx* ctx, size_t bytes, void** d_ptr)
 {
@@ -596,6 +610,13 @@ API int b200reg_binary_threshold(b200reg_ctx* ctx, const void* d_in, int dtype, 
     ENTER(ctx);
     REQUIRE(d_in && d_out, "invalid argument");
     const int nb = ctx->sm_count * 8;
+    if (semantics().binary_threshold_in_pixel_type && dtype != B200REG_F32 && dtype != B200REG_F64) {
+        // semantic switch: the bounds are cast to the (integer) pixel type before the comparison, clamped to its range
+        B200_DISPATCH_DTYPE(dtype, T, {
+            lower = (double)(T)Px<T>::cast_host(lower);
+            upper = (double)(T)Px<T>::cast_host(upper);
+        });
+    }
     B200_DISPATCH_DTYPE(dtype, T, { binary_threshold_kernel<T><<<nb, 256, 0, ctx->stream>>>((const T*)d_in, d_out, n, lower, upper); });
     ctx->launches++;
     B200_CHECK_LAUNCH();

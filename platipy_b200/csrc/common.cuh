@@ -49,6 +49,37 @@ inline int set_error(int code, const char* fmt, ...)
 
 }  // namespace b200
 
+// Named semantic switches (process-wide): the ITK behaviours that could only be recalled (confidence M) and are
+// cheap to state both ways.  Same names and values as the switches of the CPU checker used by tests/ (see include/b200reg.h); the defaults are
+// the recalled behaviours.  DESIGN.md section 5 lists each switch with the kernels / host loops it reaches.
+namespace b200 {
+struct Semantics {
+    int discrete_gaussian_axis_order = 0;     // 0: z, y, x   1: x, y, z                        (gauss.cuh: discrete_gaussian_f32)
+    int recursive_gaussian_axis_order = 0;    // 0: z, x, y   1: x, y, z                        (deriche.cuh: recursive_gaussian_vec3)
+    int resample_linear_scanline = 1;         // 1: scan-line continuous index for linear chains  0: per voxel   (resample.cuh: make_chain)
+    int dvf_transform_interpolation = 0;      // 0: weighted sum of 8 neighbours  1: nested lerps  (resample.cuh: apply_chain)
+    int vector_resample_interpolation = 0;    // 0: nested lerps  1: weighted sum                  (resample.cuh: resample_vec3_kernel)
+    int binary_threshold_in_pixel_type = 0;   // 0: bounds compared as real numbers  1: bounds cast to the pixel type first (fusion.cuh)
+};
+inline Semantics& semantics()
+{
+    static Semantics s;
+    return s;
+}
+inline int* semantic_slot(const char* name)
+{
+    Semantics& s = semantics();
+    struct { const char* n; int* p; } tab[] = {
+        { "discrete_gaussian_axis_order", &s.discrete_gaussian_axis_order }, { "recursive_gaussian_axis_order", &s.recursive_gaussian_axis_order },
+        { "resample_linear_scanline", &s.resample_linear_scanline }, { "dvf_transform_interpolation", &s.dvf_transform_interpolation },
+        { "vector_resample_interpolation", &s.vector_resample_interpolation }, { "binary_threshold_in_pixel_type", &s.binary_threshold_in_pixel_type },
+    };
+    for (auto& e : tab)
+        if (name && std::strcmp(e.n, name) == 0) return e.p;
+    return nullptr;
+}
+}  // namespace b200
+
 struct b200reg_ctx {
     int device = 0;
     cudaStream_t stream = nullptr;
@@ -63,7 +94,7 @@ struct b200reg_ctx {
     bool staple_voxelwise = false; // B200REG_STAPLE_VOXELWISE=1: per-voxel EM kernels instead of the pattern-histogram EM
     bool update_ws = false;        // B200REG_UPDATE_WS=1: warp-specialised (producer/consumer) fused update kernel
     int zm_tma = 1;                // B200REG_ZM_TMA=0: cp.async (LDGSTS) staging of the fused smoothing kernel's plane tiles instead of one tensor-map TMA copy per tile
-    int zm_tma_l2 = 2;             // B200REG_ZM_TMA_L2 = 0 | 1 | 2 | 3: L2 promotion of the tensor-map loads (none, 64, 128, 256 bytes)
+    int zm_tma_l2 = 3;             // B200REG_ZM_TMA_L2 = 0 | 1 | 2 | 3: L2 promotion of the tensor-map loads (none, 64, 128, 256 bytes)
     bool update_branchy = false;   // B200REG_UPDATE_BRANCHY=1: first version of the fused update kernel's force phase (per-voxel branches)
     bool zm_regadd = false;        // B200REG_ZM_REGADD=0: add + smooth stages both operands in shared memory (first version)
     bool update_split = true;      // B200REG_UPDATE_SPLIT=0: fused z-marching warp + force kernel instead of the two high-occupancy kernels

@@ -223,7 +223,8 @@ inline int recursive_gaussian_vec3(b200reg_ctx* ctx, double* field, const b200re
     TempBuf tmp;
     B200_TRY(tmp.alloc(ctx, 3 * n * sizeof(double)));
     double* bufs[2] = { field, tmp.as<double>() };
-    const int order[3] = { 2, 0, 1 };
+    const int order_zxy[3] = { 2, 0, 1 }, order_xyz[3] = { 0, 1, 2 };  // semantic switch recursive_gaussian_axis_order
+    const int* order = semantics().recursive_gaussian_axis_order ? order_xyz : order_zxy;
     const size_t strides[3] = { 1, (size_t)nx, (size_t)nx * ny };
     const int dims[3] = { nx, ny, nz };
     int cur = 0;

@@ -842,8 +842,8 @@ inline int discrete_gaussian_f32(b200reg_ctx* ctx, const float* d_in, float* d_o
     B200_TRY(t2.alloc(ctx, n * sizeof(float)));
     const float* src = d_in;
     float* dsts[3] = { t1.as<float>(), t2.as<float>(), d_out };
-    int pass = 0;
-    for (int axis = 2; axis >= 0; --axis, ++pass) {
+    for (int pass = 0; pass < 3; ++pass) {
+        const int axis = semantics().discrete_gaussian_axis_order ? pass : 2 - pass;  // z, y, x unless the switch says x, y, z
         double t = variance[axis];
         if (use_spacing) t = t / (g.spacing[axis] * g.spacing[axis]);
         KernelCoeffs kc;

@@ -16,7 +16,9 @@ struct TfmD {
 };
 struct ChainD {
     int n;
-    int linear;  // every element affine -> ITK's scan-line path
+    int linear;     // every element affine -> ITK's scan-line path (semantic switch resample_linear_scanline)
+    int dvf_lerp;   // semantic switch dvf_transform_interpolation: nested lerps instead of the weighted sum
+    int vec_wsum;   // semantic switch vector_resample_interpolation: weighted sum instead of nested lerps
     TfmD t[B200REG_MAX_TRANSFORMS];
 };
 
@@ -26,7 +28,9 @@ inline int make_chain(const b200reg_transform* chain, int n_chain, ChainD* out)
         return set_error(B200REG_ERR_ARG, "transform chain length %d not in [0, %d]", n_chain, B200REG_MAX_TRANSFORMS);
     if (n_chain > 0 && !chain) return set_error(B200REG_ERR_ARG, "null transform chain");
     out->n = n_chain;
-    out->linear = 1;
+    out->linear = semantics().resample_linear_scanline ? 1 : 0;
+    out->dvf_lerp = semantics().dvf_transform_interpolation;
+    out->vec_wsum = semantics().vector_resample_interpolation;
     for (int i = 0; i < n_chain; ++i) {
         TfmD& t = out->t[i];
         t.kind = chain[i].kind;
@@ -86,6 +90,10 @@ __device__ __forceinline__ void interp_wsum_vec3(const double* __restrict__ f, c
     }
 }
 
+// the alternative settings of the interpolation switches: out of line, so that the default paths keep their register budgets
+__device__ __noinline__ void interp_lerp_vec3_alt(const double* __restrict__ f, const GeomD& g, const double* c, double* out);
+__device__ __noinline__ void interp_wsum_vec3_alt(const double* __restrict__ f, const GeomD& g, const double* c, double* out);
+
 __device__ __forceinline__ void apply_chain(const ChainD& ch, double* p)
 {
     for (int i = 0; i < ch.n; ++i) {
@@ -107,7 +115,8 @@ __device__ __forceinline__ void apply_chain(const ChainD& ch, double* p)
             double c[3], dd[3];
             pt2cidx(t.g, p, c);
             if (inside_buffer(t.g, c)) {
-                interp_wsum_vec3(t.dvf, t.g, c, dd);
+                if (ch.dvf_lerp) interp_lerp_vec3_alt(t.dvf, t.g, c, dd);
+                else interp_wsum_vec3(t.dvf, t.g, c, dd);
                 p[0] += dd[0];
                 p[1] += dd[1];
                 p[2] += dd[2];
@@ -216,6 +225,19 @@ __device__ __forceinline__ double lin_eval_i32(const T* __restrict__ img, int nx
     const double vx11 = v011 + (v111 - v011) * w.d0;
     const double vxx1 = vx01 + (vx11 - vx01) * w.d1;
     return vxx0 + (vxx1 - vxx0) * w.d2;
+}
+
+__device__ __noinline__ void interp_lerp_vec3_alt(const double* __restrict__ f, const GeomD& g, const double* c, double* out)
+{
+    const LinW w = lin_setup(g, c);
+    const size_t plane = (size_t)g.nx * g.ny * g.nz;
+    out[0] = lin_eval<double>(f, g, w);
+    out[1] = lin_eval<double>(f + plane, g, w);
+    out[2] = lin_eval<double>(f + 2 * plane, g, w);
+}
+__device__ __noinline__ void interp_wsum_vec3_alt(const double* __restrict__ f, const GeomD& g, const double* c, double* out)
+{
+    interp_wsum_vec3(f, g, c, out);
 }
 
 // One image of a batch
@@ -461,7 +483,9 @@ __global__ void __launch_bounds__(BX* BY, 4) resample_vec3_kernel(const double* 
     const size_t o = ((size_t)k * go.ny + j) * go.nx + i;
     const size_t po = (size_t)go.nx * go.ny * go.nz, pi = (size_t)gi.nx * gi.ny * gi.nz;
     double v[3];
-    if (inside_buffer(gi, c)) {
+    if (inside_buffer(gi, c) && ch.vec_wsum) {
+        interp_wsum_vec3_alt(in, gi, c, v);
+    } else if (inside_buffer(gi, c)) {
         const LinW w = lin_setup(gi, c);
         if (SMALL) {
             v[0] = lin_eval_i32<double>(in, gi.nx, gi.nx * gi.ny, w);

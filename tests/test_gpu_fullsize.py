@@ -70,3 +70,29 @@ def test_config3_apply_transform_labels_and_image(engine, pair):
     zero = sk.DisplacementFieldTransform(Image(np.zeros(SIZE[::-1] + (3,)), is_vector=True))
     ident = reg.apply_transform(d_imgs[5], d_imgs[0], zero, 0, sk.sitkNearestNeighbor)
     assert bool((ident.tensor == d_imgs[5].tensor).all())
+
+
+def test_cfg2_whole_registration_matches_oracle(engine, pair):
+    """BASELINE.json configs[1] end to end at full size: 3-level pyramid [4, 2, 1], 100 / 50 / 25 iterations -- pyramid Gaussians
+    (sigma 4 / 2 / 1 mm), every Demons iteration with the reference's early stop, field re-gridding, composition and the recursive
+    Gaussian between levels, the final warp -- against the oracle's restatement of deformable.py:31-306 (about a minute of host
+    cores).  Asserts equal elapsed iterations per level, DVF within the north star's 1e-4 mm (in fact the same bits) and the
+    registered image within 1e-5 relative."""
+    from oracle import platipy_ref as ref
+
+    fixed, moving = pair
+    kw = dict(resolution_staging=[4, 2, 1], iteration_staging=[100, 50, 25])
+    stats = []
+    img_o, _, dvf_o = ref.fast_symmetric_forces_demons_registration(fixed, moving, level_stats=stats, **kw)
+    img, tfm, dvf = reg.fast_symmetric_forces_demons_registration(engine.to_device(fixed), engine.to_device(moving), **kw)
+    got_stats = reg.LAST_LEVEL_STATS[:]
+    assert [s["elapsed_iterations"] for s in got_stats] == [s["elapsed_iterations"] for s in stats]
+    for g, o in zip(got_stats, stats):
+        assert abs(g["metric"] - o["metric"]) <= 1e-9 * abs(o["metric"])
+    got = engine.to_host(dvf, pinned=False).array
+    err = float(np.abs(got - dvf_o.array).max())
+    print(f"cfg2 whole registration: elapsed {[s['elapsed_iterations'] for s in got_stats]}, max |DVF gpu - oracle| = {err:.3e} mm, "
+          f"identical bits: {np.array_equal(got, dvf_o.array)}")
+    assert err <= 1e-4
+    gi = engine.to_host(img, pinned=False).array
+    assert float(np.abs(gi - img_o.array).max()) <= 1e-5 * max(1.0, float(np.abs(img_o.array).max()))
