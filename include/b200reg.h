@@ -186,6 +186,11 @@ int b200reg_transform_to_dvf(b200reg_ctx* ctx, const b200reg_geom* out_geom, con
 int b200reg_demons_execute(b200reg_ctx* ctx, const float* d_fixed, const b200reg_geom* fixed_geom, const float* d_moving,
                            const b200reg_geom* moving_geom, const b200reg_demons_params* params, double* d_out_soa,
                            b200reg_demons_stats* h_stats);
+/* IterationEvent data of the most recent b200reg_demons_execute (level 0) / b200reg_multiscale_demons call on this context
+ * (deformable.py:260-264, utils.py:37-41 print GetElapsedIterations() / GetMetric() at every iteration): h_metric_rms receives
+ * (metric, RMS change) pairs, iteration 1 first, at most capacity_iterations of them.  Returns the number of iterations recorded
+ * for that level (0 for an unknown level).  Host data, no synchronisation. */
+int b200reg_demons_trace(b200reg_ctx* ctx, int level, double* h_metric_rms, int capacity_iterations);
 /* One InitializeIteration + CalculateChange (warp + ESM force), for unit parity tests: d_w (f32 warped
  * moving, FLT_MAX outside), d_u_soa (raw update); h_metric / h_rms after synchronisation. */
 int b200reg_demons_force(b200reg_ctx* ctx, const float* d_fixed, const b200reg_geom* fixed_geom, const float* d_moving,

@@ -83,6 +83,7 @@ SIGNATURES = {
     "b200reg_transform_to_dvf": (C.c_int, [_P, C.POINTER(Geom), C.POINTER(Transform), C.c_int, _P]),
     "b200reg_compose_dvf": (C.c_int, [_P, _P, _P, C.POINTER(Geom), _P]),
     "b200reg_demons_execute": (C.c_int, [_P, _P, C.POINTER(Geom), _P, C.POINTER(Geom), C.POINTER(DemonsParams), _P, C.POINTER(DemonsStats)]),
+    "b200reg_demons_trace": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.c_int]),
     "b200reg_demons_force": (C.c_int, [_P, _P, C.POINTER(Geom), _P, C.POINTER(Geom), _P, C.POINTER(DemonsParams), _P, _P,
                                        C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "b200reg_pde_smooth_field": (C.c_int, [_P, _P, C.POINTER(Geom), C.POINTER(C.c_double), C.c_double, C.c_int]),

@@ -307,12 +307,20 @@ static int check_demons_params(const b200reg_demons_params* p)
     return B200REG_OK;
 }
 
-static int read_stats(b200reg_ctx* ctx, const DemonsWorkspace& ws, const b200reg_geom& g, b200reg_demons_stats* st, float ms)
+static int read_stats(b200reg_ctx* ctx, const DemonsWorkspace& ws, const b200reg_geom& g, b200reg_demons_stats* st, float ms, int n_iters = 0,
+                      int level = -1)
 {
     DemonsCtrl h;
     B200_CUDA(cudaMemcpyAsync(ctx->h_scratch, ws.ctrl.p, sizeof(DemonsCtrl), cudaMemcpyDeviceToHost, ctx->stream));
     B200_CUDA(cudaStreamSynchronize(ctx->stream));
     memcpy(&h, ctx->h_scratch, sizeof(h));
+    if (level >= 0 && ws.trace.p) {
+        // the iteration trace (metric, RMS change per iteration, written by demons_finish_kernel): a few hundred bytes
+        if ((int)ctx->traces.size() <= level) ctx->traces.resize(level + 1);
+        const int n = h.elapsed < n_iters ? h.elapsed : n_iters;
+        ctx->traces[level].assign(2 * (size_t)(n > 0 ? n : 0), 0.0);
+        if (n > 0) B200_CUDA(cudaMemcpy(ctx->traces[level].data(), ws.trace.p, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost));
+    }
     st->elapsed_iterations = h.elapsed;
     st->voxels_lo = (int32_t)(nvox(g) & 0x7fffffff);
     st->metric = h.metric;
@@ -329,7 +337,8 @@ API int b200reg_demons_execute(b200reg_ctx* ctx, const float* d_fixed, const b20
     REQUIRE(d_fixed && d_moving && d_out_soa && valid_geom(fixed_geom) && valid_geom(moving_geom), "invalid argument");
     B200_TRY(check_demons_params(params));
     DemonsWorkspace ws;
-    B200_TRY(demons_prepare(ctx, *fixed_geom, params->number_of_iterations, &ws, false));
+    B200_TRY(demons_prepare(ctx, *fixed_geom, params->number_of_iterations, &ws, true));
+    ctx->traces.clear();
     cudaEvent_t e0, e1;
     B200_CUDA(cudaEventCreate(&e0));
     B200_CUDA(cudaEventCreate(&e1));
@@ -344,8 +353,18 @@ API int b200reg_demons_execute(b200reg_ctx* ctx, const float* d_fixed, const b20
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     B200_TRY(rc);
-    if (h_stats) B200_TRY(read_stats(ctx, ws, *fixed_geom, h_stats, ms));
+    b200reg_demons_stats local;
+    B200_TRY(read_stats(ctx, ws, *fixed_geom, h_stats ? h_stats : &local, ms, params->number_of_iterations, 0));
     return B200REG_OK;
+}
+
+API int b200reg_demons_trace(b200reg_ctx* ctx, int level, double* h_metric_rms, int capacity_iterations)
+{
+    if (!ctx || level < 0 || level >= (int)ctx->traces.size()) return 0;
+    const int n = (int)(ctx->traces[level].size() / 2);
+    const int m = n < capacity_iterations ? n : capacity_iterations;
+    if (h_metric_rms && m > 0) memcpy(h_metric_rms, ctx->traces[level].data(), sizeof(double) * 2 * (size_t)m);
+    return n;
 }
 
 API int b200reg_demons_force(b200reg_ctx* ctx, const float* d_fixed, const b200reg_geom* fixed_geom, const float* d_moving,
@@ -508,6 +527,7 @@ API int b200reg_multiscale_demons(b200reg_ctx* ctx, const float* d_fixed, const 
         B200_CUDA(cudaMemsetAsync(total.p, 0, 3 * nF * sizeof(double), ctx->stream));
     }
 
+    ctx->traces.clear();
     std::vector<cudaEvent_t> ev(2 * (size_t)L);
     for (auto& e : ev) B200_CUDA(cudaEventCreate(&e));
     std::vector<DemonsWorkspace> wss(L);
@@ -537,7 +557,7 @@ API int b200reg_multiscale_demons(b200reg_ctx* ctx, const float* d_fixed, const 
             p.number_of_iterations = cfg->iteration_staging[l];
             TempBuf iter;
             B200_TRY(iter.alloc(ctx, 3 * nl * sizeof(double)));
-            B200_TRY(demons_prepare(ctx, gl, p.number_of_iterations, &wss[l], false));
+            B200_TRY(demons_prepare(ctx, gl, p.number_of_iterations, &wss[l], true));
             B200_CUDA(cudaEventRecord(ev[2 * l], ctx->stream));
             B200_TRY(demons_enqueue(ctx, Fl[l].as<float>(), gl, mw.as<float>(), gml[l], p, iter.as<double>(), &wss[l]));
             B200_CUDA(cudaEventRecord(ev[2 * l + 1], ctx->stream));
@@ -557,7 +577,7 @@ API int b200reg_multiscale_demons(b200reg_ctx* ctx, const float* d_fixed, const 
         for (int l = 0; l < L && rc == B200REG_OK; ++l) {
             float ms = 0.f;
             if (cudaEventSynchronize(ev[2 * l + 1]) == cudaSuccess) cudaEventElapsedTime(&ms, ev[2 * l], ev[2 * l + 1]);
-            rc = read_stats(ctx, wss[l], gfl[l], &h_level_stats[l], ms);
+            rc = read_stats(ctx, wss[l], gfl[l], &h_level_stats[l], ms, cfg->iteration_staging[l], l);
         }
     }
     if (rc != B200REG_OK) cudaStreamSynchronize(ctx->stream);

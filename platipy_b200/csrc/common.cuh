@@ -89,6 +89,8 @@ struct b200reg_ctx {
     // pinned scratch for small read-backs
     double* h_scratch = nullptr;  // 64 doubles
     std::set<const void*> smem_optin;  // kernels whose dynamic shared-memory limit was raised on this device
+    // per-iteration (metric, RMS change) pairs of the most recent Demons call, one vector per level (b200reg_demons_trace)
+    std::vector<std::vector<double>> traces;
     bool force_separable = false;  // B200REG_FORCE_SEPARABLE=1: unfused smoothing passes (A/B testing)
     bool unfused_force = false;    // B200REG_UNFUSED_FORCE=1: separate warp and force kernels (W through HBM)
     bool staple_voxelwise = false; // B200REG_STAPLE_VOXELWISE=1: per-voxel EM kernels instead of the pattern-histogram EM

@@ -365,8 +365,17 @@ class Engine:
         _abi.check(self.lib.b200reg_demons_execute(self.ctx, fixed.ptr, C.byref(gf), moving.ptr, C.byref(gm), C.byref(params),
                                                    C.c_void_p(out.data_ptr()), C.byref(st)))
         stats = {"elapsed_iterations": st.elapsed_iterations, "metric": st.metric, "rms_change": st.rms_change, "gpu_ms": st.gpu_ms,
-                 "voxels": fixed.GetNumberOfPixels()}
+                 "voxels": fixed.GetNumberOfPixels(), "trace": self.demons_trace(0, st.elapsed_iterations)}
         return fixed.like(out, np.float64, True), stats
+
+    def demons_trace(self, level, n_iterations):
+        """[(metric, RMS change)] per iteration of ``level`` of the most recent Demons call: what the reference's IterationEvent
+        callbacks see through GetMetric() / GetRMSChange() (deformable.py:260-264, utils.py:37-41)."""
+        n = max(int(n_iterations), 0)
+        buf = (C.c_double * (2 * max(n, 1)))()
+        got = self.lib.b200reg_demons_trace(self.ctx, int(level), buf, n)
+        got = min(got, n)
+        return [(buf[2 * i], buf[2 * i + 1]) for i in range(got)]
 
     def demons_force(self, fixed, moving, field, params):
         x, y, z = fixed.GetSize()
@@ -389,7 +398,7 @@ class Engine:
             initial_field.ptr if initial_field is not None else None, C.byref(gi) if gi is not None else None,
             C.c_void_p(out.data_ptr()), stats))
         level_stats = [{"elapsed_iterations": s.elapsed_iterations, "metric": s.metric, "rms_change": s.rms_change, "gpu_ms": s.gpu_ms,
-                        "voxels": s.voxels_lo} for s in stats[: cfg.n_levels]]
+                        "voxels": s.voxels_lo, "trace": self.demons_trace(l, s.elapsed_iterations)} for l, s in enumerate(stats[: cfg.n_levels])]
         return fixed.like(out, np.float64, True), level_stats
 
     # -- fusion ------------------------------------------------------------------------------------------

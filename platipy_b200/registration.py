@@ -246,7 +246,9 @@ class FastSymmetricForcesDemonsRegistrationFilter:
         self._idt = float(v)
 
     def AddCommand(self, event, callback):
-        self._commands.append(callback)
+        """Callbacks registered for sitkIterationEvent (or sitkAnyEvent) run once per Demons iteration; see _fire_iteration_events."""
+        if event in (sk.sitkIterationEvent, sk.sitkAnyEvent):
+            self._commands.append(callback)
 
     def GetElapsedIterations(self):
         return self._stats["elapsed_iterations"]
@@ -278,10 +280,20 @@ class FastSymmetricForcesDemonsRegistrationFilter:
         f, m = eng.to_device(fixed_image), eng.to_device(moving_image)
         if f.np_dtype != np.float32 or m.np_dtype != np.float32:
             raise RuntimeError("FastSymmetricForcesDemonsRegistrationFilter: fixed and moving images must be sitkFloat32")
-        dvf, self._stats = eng.demons_execute(f, m, self.params())
-        for cb in self._commands:
-            cb()
+        dvf, stats = eng.demons_execute(f, m, self.params())
+        self._fire_iteration_events(stats)
         return _back(eng, dvf, fixed_image)
+
+    def _fire_iteration_events(self, stats):
+        """The reference's callbacks run at every sitkIterationEvent and read GetElapsedIterations() / GetMetric() there
+        (deformable.py:260-264, utils.py:37-41).  The whole loop runs on the device without host round trips, so the events are
+        replayed from the recorded per-iteration trace once the level has finished: same sequence of values, later in time."""
+        if self._commands:
+            for i, (metric, rms) in enumerate(stats.get("trace", [])):
+                self._stats = {"elapsed_iterations": i + 1, "metric": metric, "rms_change": rms}
+                for cb in self._commands:
+                    cb()
+        self._stats = stats
 
 
 B200DemonsFilter = FastSymmetricForcesDemonsRegistrationFilter
@@ -327,8 +339,8 @@ def multiscale_demons(registration_algorithm, fixed_image, moving_image, initial
     dvf, level_stats = eng.multiscale_demons(f, m, cfg, init, init_on_fixed_grid)
     registration_algorithm.level_stats = level_stats
     LAST_LEVEL_STATS[:] = level_stats
-    if level_stats:
-        registration_algorithm._stats = level_stats[-1]
+    for st in level_stats:  # IterationEvent callbacks, level by level (deformable.py:143-149 runs the filter once per level)
+        registration_algorithm._fire_iteration_events(st)
     return _back(eng, dvf, fixed_image)
 
 
@@ -364,12 +376,13 @@ def fast_symmetric_forces_demons_registration(fixed_image, moving_image, resolut
     if not smoothing_sigmas:
         smoothing_sigmas = [i * smoothing_sigma_factor for i in resolution_staging]
 
+    if verbose:
+        # deformable.py:260-264: one line per iteration, "{elapsed:3} = {metric:10.5f}"
+        reg.AddCommand(sk.sitkIterationEvent, lambda: deformable_registration_command_iteration(reg))
+
     dvf = multiscale_demons(reg, f, m, resolution_staging=resolution_staging, smoothing_sigmas=smoothing_sigmas,
                             iteration_staging=iteration_staging, isotropic_resample=isotropic_resample,
                             initial_displacement_field=initial_displacement_field, interp_order=interp_order)
-    if verbose:
-        for lvl, st in enumerate(reg.level_stats):
-            print("level {0}: {1:3} = {2:10.5f}".format(lvl, st["elapsed_iterations"], st["metric"]))
 
     # deformable.py:286-293: CT-like default value
     if default_value is None:

@@ -31,6 +31,8 @@ sitkVectorFloat32, sitkVectorFloat64 = 20, 21
 
 # interpolator enum (reference deformable.py:221-224)
 sitkNearestNeighbor, sitkLinear, sitkBSpline = 1, 2, 3
+# event enum of AddCommand (reference deformable.py:261: sitk.sitkIterationEvent)
+sitkAnyEvent, sitkAbortEvent, sitkDeleteEvent, sitkEndEvent, sitkIterationEvent, sitkProgressEvent, sitkStartEvent = range(7)
 
 _ID_TO_DTYPE = {
     sitkInt8: np.int8, sitkUInt8: np.uint8, sitkInt16: np.int16, sitkUInt16: np.uint16,

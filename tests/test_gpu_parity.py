@@ -354,3 +354,30 @@ def test_randomised_small_registrations(engine):
         _, _, dvf = reg.fast_symmetric_forces_demons_registration(fixed, moving, **kw)
         _, _, dvf_o = ref.fast_symmetric_forces_demons_registration(fixed, moving, **kw)
         assert np.abs(dvf.array - dvf_o.array).max() <= DVF_TOL_MM, (trial, size, sp)
+
+
+def test_iteration_events_and_trace_match_the_oracle(engine, capsys):
+    """IterationEvent callbacks (deformable.py:260-264, utils.py:37-41): GetElapsedIterations() / GetMetric() at every iteration equal
+    the oracle's per-iteration metric trace; ``verbose=True`` prints the reference's line once per iteration of every level."""
+    fixed, moving = synth_pair((40, 36, 24), seed=11, spacing=(1.0, 1.0, 1.5))
+    flt = reg.FastSymmetricForcesDemonsRegistrationFilter()
+    flt.SetStandardDeviations((1.5, 1.5, 1.0))
+    flt.SetSmoothUpdateField(True)
+    flt.SetNumberOfIterations(12)
+    seen = []
+    flt.AddCommand(sk.sitkIterationEvent, lambda: seen.append((flt.GetElapsedIterations(), flt.GetMetric(), flt.GetRMSChange())))
+    flt.AddCommand(sk.sitkStartEvent, lambda: seen.append("start event callbacks are not iteration callbacks"))
+    flt.Execute(fixed, moving)
+    _, st = orc.demons_execute(fixed.array, orc.geom_of(fixed), moving.array, orc.geom_of(moving),
+                               orc.demons_params((1.5, 1.5, 1.0), 12, smooth_update_field=True), trace=True)
+    assert [s[0] for s in seen] == list(range(1, st["elapsed_iterations"] + 1))
+    assert np.allclose([s[1] for s in seen], st["metric_trace"], rtol=1e-10, atol=0)
+    assert flt.GetElapsedIterations() == st["elapsed_iterations"] and abs(flt.GetMetric() - st["metric"]) <= 1e-10 * st["metric"]
+    assert abs(seen[-1][2] - st["rms_change"]) <= 1e-10 * max(st["rms_change"], 1e-300)
+    # verbose: one "{elapsed:3} = {metric:10.5f}" line per iteration and level
+    capsys.readouterr()
+    reg.fast_symmetric_forces_demons_registration(fixed, moving, resolution_staging=[2, 1], iteration_staging=[5, 3], verbose=True)
+    lines = [l for l in capsys.readouterr().out.splitlines() if " = " in l]
+    elapsed = [s["elapsed_iterations"] for s in reg.LAST_LEVEL_STATS]
+    assert len(lines) == sum(elapsed)
+    assert [int(l.split("=")[0]) for l in lines] == [i + 1 for n in elapsed for i in range(n)]
