@@ -166,6 +166,10 @@ class Engine:
         self.device = torch.device("cuda", device)
         with torch.cuda.device(self.device):
             self.stream = torch.cuda.Stream(device=self.device)
+            # copy streams of the pipelined host API (to_device_async / to_host_async): PCIe transfers in both directions ride
+            # beside the compute stream instead of in front of / behind it
+            self.copy_in = torch.cuda.Stream(device=self.device)
+            self.copy_out = torch.cuda.Stream(device=self.device)
         ctx = C.c_void_p()
         _abi.check(self.lib.b200reg_create(device, C.c_void_p(self.stream.cuda_stream), C.byref(ctx)))
         self.ctx = ctx
@@ -213,6 +217,48 @@ class Engine:
             dev.record_stream(self.stream)
             dev = soa
         return DeviceImage(dev, image.array.dtype, image.GetSpacing(), image.GetOrigin(), image.GetDirection(), image.is_vector)
+
+    def to_device_async(self, image):
+        """Host scalar ``Image`` (ideally in pinned memory, see ``pinned_image``) -> ``(DeviceImage, event)``, copied on the copy-in
+        stream.  Nothing waits: the consumer calls ``engine.stream.wait_event(event)`` right before the first use, so an upload
+        requested early runs beside whatever the engine stream is doing (``event`` is None when there was nothing to copy)."""
+        if isinstance(image, DeviceImage):
+            return image, None
+        image = sk.to_native(image)
+        if image.is_vector:
+            return self.to_device(image), None
+        host = _as_torch_host(image.array)
+        with torch.cuda.stream(self.copy_in):
+            dev = host.to(self.device, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_in)
+        dev.record_stream(self.stream)
+        return DeviceImage(dev, image.array.dtype, image.GetSpacing(), image.GetOrigin(), image.GetDirection(), False), ev
+
+    def to_host_async(self, dimg):
+        """``DeviceImage`` -> ``(host Image in pinned memory, event)``: the SoA -> AoS conversion of a field runs on the engine stream,
+        the PCIe copy on the copy-out stream behind it; nothing waits.  The image is valid once ``event.synchronize()`` returns."""
+        x, y, z = dimg.GetSize()
+        if dimg.is_vector:
+            aos = self.empty((z, y, x, 3), np.float64)
+            _abi.check(self.lib.b200reg_soa_to_aos(self.ctx, dimg.ptr, C.c_void_p(aos.data_ptr()), dimg.GetNumberOfPixels()))
+            src, shape = aos, (z, y, x, 3)
+        else:
+            src, shape = dimg.tensor, (z, y, x)
+        pinned = torch.empty(tuple(int(v) for v in shape), dtype=_DT[dimg.np_dtype][1], pin_memory=True)
+        host = pinned.numpy()
+        if dimg.np_dtype in _SIGNED_VIEW:
+            host = host.view(dimg.np_dtype)
+        self.copy_out.wait_stream(self.stream)
+        src.record_stream(self.copy_out)
+        with torch.cuda.stream(self.copy_out):
+            pinned.copy_(src.view(pinned.shape), non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(self.copy_out)
+        out = Image.__new__(Image)
+        out._arr = host
+        out._spacing, out._origin, out._direction, out._is_vector = dimg.spacing, dimg.origin, dimg.direction, dimg.is_vector
+        return out, ev
 
     def to_host(self, dimg, pinned=True):
         """``DeviceImage`` -> host ``Image`` (vector fields come back as AoS ``[z, y, x, 3]``).  Synchronises."""

@@ -344,21 +344,13 @@ def multiscale_demons(registration_algorithm, fixed_image, moving_image, initial
     return _back(eng, dvf, fixed_image)
 
 
-def fast_symmetric_forces_demons_registration(fixed_image, moving_image, resolution_staging=[8, 4, 1],
-                                              iteration_staging=[10, 10, 10], isotropic_resample=False,
-                                              initial_displacement_field=None, regularisation_kernel_mm=1.5,
-                                              smoothing_sigma_factor=1, smoothing_sigmas=False, default_value=None,
-                                              ncores=1, interp_order=sitkLinear, verbose=False):
-    """Deformable image propagation using Fast Symmetric-Forces Demons (deformable.py:190-306).
-
-    Returns ``(registered_image, DisplacementFieldTransform, displacement_field)``.  For ``DeviceImage``
-    inputs the three results stay on the device (the transform object then wraps the device field).
-    """
-    eng = Engine.get()
-    device_io = _is_device(fixed_image) and _is_device(moving_image)
-    f0, m0 = eng.to_device(fixed_image), eng.to_device(moving_image)
+def _register_on_device(eng, f0, m0, resolution_staging, iteration_staging, isotropic_resample, initial_displacement_field,
+                        regularisation_kernel_mm, smoothing_sigma_factor, smoothing_sigmas, default_value, ncores, interp_order, verbose,
+                        on_field_ready=None):
+    """Device part of fast_symmetric_forces_demons_registration: ``DeviceImage`` inputs -> ``(registered, transform, field)`` on the
+    device.  ``on_field_ready(dvf)`` is called as soon as the field is final, before the last warp is enqueued (the host API starts
+    the field's PCIe copy there, so that it overlaps the warp)."""
     moving_dtype = m0.np_dtype
-
     # deformable.py:238-241: cast to Float32 unless the pixel id is 6 (Int64 -- the reference's quirk)
     if f0.GetPixelID() == 6 or m0.GetPixelID() == 6:
         raise RuntimeError("FastSymmetricForcesDemonsRegistrationFilter: Int64 images are not cast by the reference "
@@ -380,15 +372,18 @@ def fast_symmetric_forces_demons_registration(fixed_image, moving_image, resolut
         # deformable.py:260-264: one line per iteration, "{elapsed:3} = {metric:10.5f}"
         reg.AddCommand(sk.sitkIterationEvent, lambda: deformable_registration_command_iteration(reg))
 
-    dvf = multiscale_demons(reg, f, m, resolution_staging=resolution_staging, smoothing_sigmas=smoothing_sigmas,
-                            iteration_staging=iteration_staging, isotropic_resample=isotropic_resample,
-                            initial_displacement_field=initial_displacement_field, interp_order=interp_order)
-
-    # deformable.py:286-293: CT-like default value
+    # deformable.py:286-293: CT-like default value of the final resample (asked for here, ahead of the long device-resident loop,
+    # because the answer costs a host synchronisation)
     if default_value is None:
         default_value = 0
         if eng.minmax(m)[0] <= -1000:
             default_value = -1000
+
+    dvf = multiscale_demons(reg, f, m, resolution_staging=resolution_staging, smoothing_sigmas=smoothing_sigmas,
+                            iteration_staging=iteration_staging, isotropic_resample=isotropic_resample,
+                            initial_displacement_field=initial_displacement_field, interp_order=interp_order)
+    if on_field_ready is not None:
+        on_field_ready(dvf)
 
     tfm = sk.DisplacementFieldTransform.__new__(sk.DisplacementFieldTransform)
     tfm._field = None
@@ -396,11 +391,111 @@ def fast_symmetric_forces_demons_registration(fixed_image, moving_image, resolut
     # deformable.py:281-304: final resample on the fixed grid, cast back to the moving image's pixel type
     reg_img = eng.resample(m, f, tfm, _check_interp(interp_order), default_value)
     reg_img = eng.cast(reg_img, moving_dtype)
+    return reg_img, tfm, dvf
 
-    if device_io:
+
+class PendingRegistration:
+    """Handle returned by ``submit_registration``: the registration has run on the device, its results are on their way to pinned
+    host memory on the copy-out stream.  ``result()`` waits for the copies and returns what the synchronous call returns."""
+
+    def __init__(self, fixed_like, moving_like, tfm, image_host, image_event, field_host, field_event, level_stats):
+        self._like = (fixed_like, moving_like)
+        self._tfm, self._image, self._field = tfm, image_host, field_host
+        self._events = (image_event, field_event)
+        self.level_stats = level_stats
+
+    def done(self):
+        return all(e.query() for e in self._events)
+
+    def result(self):
+        for e in self._events:
+            e.synchronize()
+        self._tfm._field = self._field
+        return sk.from_native(self._image, self._like[1]), self._tfm, sk.from_native(self._field, self._like[0])
+
+
+def submit_registration(fixed_image, moving_image, resolution_staging=[8, 4, 1], iteration_staging=[10, 10, 10], isotropic_resample=False,
+                        initial_displacement_field=None, regularisation_kernel_mm=1.5, smoothing_sigma_factor=1, smoothing_sigmas=False,
+                        default_value=None, ncores=1, interp_order=sitkLinear, verbose=False, _uploaded=None):
+    """``fast_symmetric_forces_demons_registration`` for host images whose results are not needed at once: the inputs go up on the
+    copy-in stream, the registration runs, and the 1.9 GB of results (VectorFloat64 field + registered image at 512 x 512 x 256) come
+    down on the copy-out stream while the caller goes on -- typically to the next ``submit_registration``, whose uploads and
+    compute then overlap these downloads (the reference's own use is a loop over atlases, multiatlas/run.py:312-347).
+    Returns a ``PendingRegistration``."""
+    eng = Engine.get()
+    (f0, f_ready), (m0, m_ready) = _uploaded if _uploaded is not None else (eng.to_device_async(fixed_image), eng.to_device_async(moving_image))
+    for ev in (f_ready, m_ready):
+        if ev is not None:
+            eng.stream.wait_event(ev)
+    started = {}
+
+    def start_field_copy(dvf):
+        started["field"] = eng.to_host_async(dvf)
+
+    reg_img, tfm, dvf = _register_on_device(eng, f0, m0, resolution_staging, iteration_staging, isotropic_resample, initial_displacement_field,
+                                            regularisation_kernel_mm, smoothing_sigma_factor, smoothing_sigmas, default_value, ncores, interp_order,
+                                            verbose, on_field_ready=start_field_copy)
+    image_host, image_event = eng.to_host_async(reg_img)
+    field_host, field_event = started["field"]
+    return PendingRegistration(fixed_image, moving_image, tfm, image_host, image_event, field_host, field_event, LAST_LEVEL_STATS[:])
+
+
+def iter_registrations(pairs, **kwargs):
+    """Registrations of a sequence of ``(fixed, moving)`` host pairs, pipelined over PCIe: while pair k is being registered the
+    inputs of pair k + 1 are uploaded and the results of pair k - 1 downloaded.  Yields ``(image, transform, field)`` per pair, in
+    order, each as soon as its copies have landed -- the same values as a loop of ``fast_symmetric_forces_demons_registration``
+    calls.  At most two results are in flight, so a long sequence needs no more pinned memory than a short one."""
+    eng = Engine.get()
+    it = iter(pairs)
+    cur_pair = next(it, None)
+    cur_up = (eng.to_device_async(cur_pair[0]), eng.to_device_async(cur_pair[1])) if cur_pair is not None else None
+    pending = None
+    while cur_pair is not None:
+        nxt_pair = next(it, None)
+        # the uploads of the next pair are queued before this pair's compute is: they run beside it
+        nxt_up = (eng.to_device_async(nxt_pair[0]), eng.to_device_async(nxt_pair[1])) if nxt_pair is not None else None
+        p = submit_registration(cur_pair[0], cur_pair[1], _uploaded=cur_up, **kwargs)
+        if pending is not None:
+            yield pending.result()
+        pending, cur_pair, cur_up = p, nxt_pair, nxt_up
+    if pending is not None:
+        yield pending.result()
+
+
+def register_batch(pairs, **kwargs):
+    """``list(iter_registrations(pairs, **kwargs))``."""
+    return list(iter_registrations(pairs, **kwargs))
+
+
+def fast_symmetric_forces_demons_registration(fixed_image, moving_image, resolution_staging=[8, 4, 1],
+                                              iteration_staging=[10, 10, 10], isotropic_resample=False,
+                                              initial_displacement_field=None, regularisation_kernel_mm=1.5,
+                                              smoothing_sigma_factor=1, smoothing_sigmas=False, default_value=None,
+                                              ncores=1, interp_order=sitkLinear, verbose=False):
+    """Deformable image propagation using Fast Symmetric-Forces Demons (deformable.py:190-306).
+
+    Returns ``(registered_image, DisplacementFieldTransform, displacement_field)``.  For ``DeviceImage``
+    inputs the three results stay on the device (the transform object then wraps the device field).  Host inputs give host
+    results; ``submit_registration`` / ``register_batch`` are the forms that overlap the PCIe copies of back-to-back calls.
+    """
+    eng = Engine.get()
+    if _is_device(fixed_image) and _is_device(moving_image):
+        f0, m0 = eng.to_device(fixed_image), eng.to_device(moving_image)
+        reg_img, tfm, dvf = _register_on_device(eng, f0, m0, resolution_staging, iteration_staging, isotropic_resample, initial_displacement_field,
+                                                regularisation_kernel_mm, smoothing_sigma_factor, smoothing_sigmas, default_value, ncores,
+                                                interp_order, verbose)
         tfm._field = dvf
         eng.release_to_caller()
         return reg_img, tfm, dvf
-    dvf_host = eng.to_host(dvf)
-    tfm._field = dvf_host
-    return sk.from_native(eng.to_host(reg_img), moving_image), tfm, sk.from_native(dvf_host, fixed_image)
+    if _is_device(fixed_image) or _is_device(moving_image) or sk.to_native(fixed_image).is_vector:
+        # mixed representations: the plain synchronous path
+        f0, m0 = eng.to_device(fixed_image), eng.to_device(moving_image)
+        reg_img, tfm, dvf = _register_on_device(eng, f0, m0, resolution_staging, iteration_staging, isotropic_resample, initial_displacement_field,
+                                                regularisation_kernel_mm, smoothing_sigma_factor, smoothing_sigmas, default_value, ncores,
+                                                interp_order, verbose)
+        dvf_host = eng.to_host(dvf)
+        tfm._field = dvf_host
+        return sk.from_native(eng.to_host(reg_img), moving_image), tfm, sk.from_native(dvf_host, fixed_image)
+    return submit_registration(fixed_image, moving_image, resolution_staging, iteration_staging, isotropic_resample, initial_displacement_field,
+                               regularisation_kernel_mm, smoothing_sigma_factor, smoothing_sigmas, default_value, ncores, interp_order,
+                               verbose).result()

@@ -79,6 +79,23 @@ class FakeEngine:
     def to_host(self, dimg, pinned=True):
         return _img(dimg)
 
+    class _Done:
+        def synchronize(self):
+            pass
+
+        def query(self):
+            return True
+
+    class _Stream:
+        def wait_event(self, ev):
+            pass
+
+    def to_device_async(self, image):
+        return self.to_device(image), None
+
+    def to_host_async(self, dimg):
+        return _img(dimg), FakeEngine._Done()
+
     # -- elementwise ----------------------------------------------------------------------------------------------------
     def cast(self, d, np_dtype):
         self._note("cast")

@@ -381,3 +381,23 @@ def test_iteration_events_and_trace_match_the_oracle(engine, capsys):
     elapsed = [s["elapsed_iterations"] for s in reg.LAST_LEVEL_STATS]
     assert len(lines) == sum(elapsed)
     assert [int(l.split("=")[0]) for l in lines] == [i + 1 for n in elapsed for i in range(n)]
+
+
+def test_pipelined_host_api_gives_the_same_results(engine):
+    """submit_registration / iter_registrations / register_batch overlap the PCIe copies of back-to-back registrations; the values are
+    those of the synchronous call, bit for bit, and the host results live in pinned memory."""
+    kw = dict(resolution_staging=[2, 1], iteration_staging=[6, 4])
+    pairs = [synth_pair((40, 36, 24), seed=20 + k, spacing=(1.0, 1.0, 1.5)) for k in range(3)]
+    pairs[1] = (Image(pairs[1][0].array.astype(np.int16), (1.0, 1.0, 1.5)), Image(pairs[1][1].array.astype(np.int16), (1.0, 1.0, 1.5)))
+    sync = [reg.fast_symmetric_forces_demons_registration(f, m, **kw) for f, m in pairs]
+    batch = reg.register_batch(pairs, **kw)
+    assert len(batch) == 3
+    for (i0, t0, d0), (i1, t1, d1) in zip(sync, batch):
+        assert np.array_equal(d0.array, d1.array) and np.array_equal(i0.array, i1.array) and i0.array.dtype == i1.array.dtype
+        assert np.array_equal(t1.GetDisplacementField().array, d1.array)
+    pend = reg.submit_registration(*pairs[0], **kw)
+    img, tfm, dvf = pend.result()
+    assert pend.done() and np.array_equal(dvf.array, sync[0][2].array) and [s["elapsed_iterations"] for s in pend.level_stats] == [6, 4]
+    # the transform that came back is usable as it is
+    assert np.array_equal(reg.apply_transform(pairs[0][1], pairs[0][0], tfm, -1000, sk.sitkLinear).array, img.array)
+    assert list(reg.iter_registrations([], **kw)) == []
