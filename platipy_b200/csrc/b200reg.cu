@@ -88,6 +88,7 @@ API int b200reg_create(int device, void* stream, b200reg_ctx** out)
     if (const char* e = getenv("B200REG_ZM_TX32")) ctx->zm_tx32 = (e[0] != '0');
     if (const char* e = getenv("B200REG_ZM_ADDOUT")) ctx->zm_addout = (e[0] != '0');
     if (const char* e = getenv("B200REG_FORCE_ZM1")) ctx->force_zm1 = (e[0] == '1');
+    if (const char* e = getenv("B200REG_PACK_LABELS")) ctx->pack_labels = (e[0] != '0');
     *out = ctx;
     return B200REG_OK;
 }

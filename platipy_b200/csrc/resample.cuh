@@ -385,11 +385,87 @@ __device__ __forceinline__ void resample_one(const BatchItem& it, const GeomD& g
     }
 }
 
+// ---- bit-packed label propagation ---------------------------------------------------------------------------------------------
+// The reference propagates S binary structures through one transform with S nearest-neighbour calls (multiatlas/run.py:338-345):
+// S gathers of one byte each per output voxel, i.e. S 32-byte sectors fetched for S useful bytes.  Here the UInt8 nearest-neighbour
+// items of a batch are first packed into ONE 32-bit word per input voxel (bit b = item b is non-zero there; a streaming pass), and
+// the resampling kernel gathers that one word per output voxel and expands it into the S outputs.  Exact for any label whose
+// non-zero voxels all carry the same value (the value is found by the packing pass: min and max over the non-zero voxels); an
+// item with several non-zero values is recognised on the device and gathered from its own image as before -- no host round trip.
+constexpr int PACK_MAX = 32;
+struct PackedD {
+    const uint32_t* words;   // [input voxels]
+    const unsigned* meta;    // [2 * n]: min over the non-zero values (0xFFFFFFFF if none), max value
+    int n;
+    const uint8_t* in[PACK_MAX];
+    uint8_t* out[PACK_MAX];
+    uint8_t dflt[PACK_MAX];  // DefaultPixelValue cast to UInt8
+};
+struct PackSrc {
+    int n;
+    const uint8_t* in[PACK_MAX];
+};
+__global__ void pack_meta_init_kernel(unsigned* meta, int n)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b < n) {
+        meta[2 * b] = 0xFFFFFFFFu;
+        meta[2 * b + 1] = 0u;
+    }
+}
+// one thread per 4 consecutive voxels (VEC) or per voxel; the per-item min / max go through a warp reduction and an atomic that
+// is skipped once the published value already covers the warp's (after the first few warps nothing is left to publish)
+template <bool VEC>
+__global__ void __launch_bounds__(256) pack_u8_bits_kernel(const __grid_constant__ PackSrc src, uint32_t* __restrict__ words, unsigned* __restrict__ meta,
+                                                            size_t nvox)
+{
+    constexpr int V = VEC ? 4 : 1;
+    const size_t q = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * V;
+    const bool live = q < nvox;
+    uint32_t w[V];
+#pragma unroll
+    for (int v = 0; v < V; ++v) w[v] = 0;
+    for (int b = 0; b < src.n; ++b) {
+        unsigned vals[V];
+        if (VEC) {
+            const uchar4 u = live ? __ldg(reinterpret_cast<const uchar4*>(src.in[b] + q)) : make_uchar4(0, 0, 0, 0);
+            vals[0] = u.x;
+            if (V > 1) {
+                vals[V > 1 ? 1 : 0] = u.y;
+                vals[V > 2 ? 2 : 0] = u.z;
+                vals[V > 3 ? 3 : 0] = u.w;
+            }
+        } else {
+            vals[0] = live ? __ldg(src.in[b] + q) : 0u;
+        }
+        unsigned mn = 0xFFFFFFFFu, mx = 0u;
+#pragma unroll
+        for (int v = 0; v < V; ++v) {
+            if (vals[v]) {
+                w[v] |= 1u << b;
+                mn = min(mn, vals[v]);
+                mx = max(mx, vals[v]);
+            }
+        }
+        mn = __reduce_min_sync(0xffffffffu, mn);
+        mx = __reduce_max_sync(0xffffffffu, mx);
+        if ((threadIdx.x & 31) == 0 && mx != 0u) {
+            if (mn < *((volatile unsigned*)(meta + 2 * b))) atomicMin(meta + 2 * b, mn);
+            if (mx > *((volatile unsigned*)(meta + 2 * b + 1))) atomicMax(meta + 2 * b + 1, mx);
+        }
+    }
+    if (live) {
+        if (VEC) *reinterpret_cast<uint4*>(words + q) = make_uint4(w[0], w[V > 1 ? 1 : 0], w[V > 2 ? 2 : 0], w[V > 3 ? 3 : 0]);
+        else words[q] = w[0];
+    }
+}
+
 // BSP: the batch contains a B-spline item (the 64-point evaluation needs far more registers than the other two
 // interpolators, so it lives in its own instantiation and the common one keeps 4 blocks per SM)
-template <bool SMALL, bool BSP>
+template <bool SMALL, bool BSP, bool PACKED = false>
 __global__ void __launch_bounds__(BX* BY, BSP ? 2 : 4) resample_batch_kernel(const __grid_constant__ BatchD batch, const __grid_constant__ GeomD gi,
-                                                                 const __grid_constant__ GeomD go, const __grid_constant__ ChainD ch)
+                                                                 const __grid_constant__ GeomD go, const __grid_constant__ ChainD ch,
+                                                                 const __grid_constant__ PackedD pk)
 {
     const int i = blockIdx.x * BX + threadIdx.x;
     const int j = blockIdx.y * BY + threadIdx.y;
@@ -414,6 +490,28 @@ __global__ void __launch_bounds__(BX* BY, BSP ? 2 : 4) resample_batch_kernel(con
         default: resample_one<double, SMALL, BSP>(it, gi, c, inside, o); break;
         }
     }
+    if (PACKED) {
+        // the packed UInt8 nearest-neighbour items: one gathered word instead of pk.n gathered bytes
+        uint32_t w = 0;
+        size_t src = 0;
+        if (inside) {
+            // NearestNeighborInterpolateImageFunction: RoundHalfIntegerUp = floor(x + 0.5), as in resample_one
+            const int i0 = (int)floor(c[0] + 0.5), i1 = (int)floor(c[1] + 0.5), i2 = (int)floor(c[2] + 0.5);
+            src = ((size_t)i2 * gi.ny + i1) * gi.nx + i0;
+            w = __ldg(pk.words + src);
+        }
+        for (int b = 0; b < pk.n; ++b) {
+            uint8_t v;
+            if (!inside) {
+                v = pk.dflt[b];
+            } else {
+                const unsigned mn = __ldg(pk.meta + 2 * b), mx = __ldg(pk.meta + 2 * b + 1);
+                if (mn >= mx) v = ((w >> b) & 1u) ? (uint8_t)mx : (uint8_t)0;  // one non-zero value (or none): the bit says it all
+                else v = __ldg(pk.in[b] + src);                                 // several non-zero values: the item's own voxel
+            }
+            pk.out[b][o] = v;
+        }
+    }
 }
 
 inline int resample_batch(b200reg_ctx* ctx, int n, const void* const* d_in, const int* dtypes, const b200reg_geom& gin,
@@ -430,17 +528,67 @@ inline int resample_batch(b200reg_ctx* ctx, int n, const void* const* d_in, cons
             return set_error(B200REG_ERR_UNSUPPORTED, "interpolator %d is not supported (nearest neighbour = 1, linear = 2, B-spline = 3)", interps[i]);
     }
     const size_t n_in = nvox(gin);
-    for (int start = 0; start < n; start += RESAMPLE_BATCH) {
+    // UInt8 nearest-neighbour items (propagated structures) travel bit-packed when there are enough of them to pay for the packing pass
+    std::vector<int> plain, packed;
+    for (int i = 0; i < n; ++i) {
+        if (dtypes[i] == B200REG_U8 && interps[i] == B200REG_INTERP_NN && d_in[i] != d_out[i] && ctx->pack_labels) packed.push_back(i);
+        else plain.push_back(i);
+    }
+    if ((int)packed.size() < 4) {
+        plain.clear();
+        packed.clear();
+        for (int i = 0; i < n; ++i) plain.push_back(i);
+    }
+    TempBuf words, meta;
+    std::vector<PackedD> groups;
+    const bool vec_ok = (n_in % 4) == 0;
+    for (size_t g0 = 0; g0 < packed.size(); g0 += PACK_MAX) {
+        PackedD pk;
+        memset(&pk, 0, sizeof(pk));
+        PackSrc src;
+        memset(&src, 0, sizeof(src));
+        pk.n = src.n = (int)std::min<size_t>(PACK_MAX, packed.size() - g0);
+        bool vec = vec_ok;
+        for (int b = 0; b < pk.n; ++b) {
+            const int i = packed[g0 + b];
+            pk.in[b] = src.in[b] = (const uint8_t*)d_in[i];
+            pk.out[b] = (uint8_t*)d_out[i];
+            pk.dflt[b] = (uint8_t)Px<uint8_t>::cast_host(defaults[i]);
+            vec = vec && (reinterpret_cast<uintptr_t>(d_in[i]) % 4) == 0;
+        }
+        if (g0 == 0) {
+            const size_t ngroups = (packed.size() + PACK_MAX - 1) / PACK_MAX;
+            B200_TRY(words.alloc(ctx, ngroups * n_in * sizeof(uint32_t)));
+            B200_TRY(meta.alloc(ctx, ngroups * 2 * PACK_MAX * sizeof(unsigned)));
+        }
+        uint32_t* wptr = words.as<uint32_t>() + (g0 / PACK_MAX) * n_in;
+        unsigned* mptr = meta.as<unsigned>() + (g0 / PACK_MAX) * 2 * PACK_MAX;
+        pack_meta_init_kernel<<<1, 64, 0, ctx->stream>>>(mptr, pk.n);
+        if (vec) pack_u8_bits_kernel<true><<<(unsigned)((n_in / 4 + 255) / 256), 256, 0, ctx->stream>>>(src, wptr, mptr, n_in);
+        else pack_u8_bits_kernel<false><<<(unsigned)((n_in + 255) / 256), 256, 0, ctx->stream>>>(src, wptr, mptr, n_in);
+        ctx->launches += 2;
+        B200_CHECK_LAUNCH();
+        pk.words = wptr;
+        pk.meta = mptr;
+        groups.push_back(pk);
+    }
+    const int n_plain = (int)plain.size();
+    PackedD no_pack;
+    memset(&no_pack, 0, sizeof(no_pack));
+    size_t next_group = 0;
+    // every launch carries up to RESAMPLE_BATCH plain items and one packed group: CT + structures share one evaluation of the transform
+    for (int start = 0; start < n_plain || next_group < groups.size(); start += RESAMPLE_BATCH) {
         BatchD b;
-        b.n = (n - start) < RESAMPLE_BATCH ? (n - start) : RESAMPLE_BATCH;
+        b.n = start < n_plain ? ((n_plain - start) < RESAMPLE_BATCH ? (n_plain - start) : RESAMPLE_BATCH) : 0;
         TempBuf coef[RESAMPLE_BATCH];
         for (int q = 0; q < b.n; ++q) {
-            b.item[q] = BatchItem{ d_in[start + q], d_out[start + q], dtypes[start + q], interps[start + q], defaults[start + q], nullptr };
-            if (interps[start + q] == B200REG_INTERP_BSPLINE) {
+            const int src_i = plain[start + q];
+            b.item[q] = BatchItem{ d_in[src_i], d_out[src_i], dtypes[src_i], interps[src_i], defaults[src_i], nullptr };
+            if (interps[src_i] == B200REG_INTERP_BSPLINE) {
                 B200_TRY(coef[q].alloc(ctx, n_in * sizeof(double)));
                 double* c = coef[q].as<double>();
                 const int nb = ctx->sm_count * 8;
-                B200_DISPATCH_DTYPE(dtypes[start + q], T, { to_f64_kernel<T><<<nb, 256, 0, ctx->stream>>>((const T*)d_in[start + q], c, n_in); });
+                B200_DISPATCH_DTYPE(dtypes[src_i], T, { to_f64_kernel<T><<<nb, 256, 0, ctx->stream>>>((const T*)d_in[src_i], c, n_in); });
                 const size_t l0 = (size_t)gi.ny * gi.nz, l1 = (size_t)gi.nx * gi.nz, l2 = (size_t)gi.nx * gi.ny;
                 bspline3_prefilter_kernel<0><<<(unsigned)((l0 + 127) / 128), 128, 0, ctx->stream>>>(c, gi.nx, gi.ny, gi.nz, bspline3_pole(gi.nx));
                 bspline3_prefilter_kernel<1><<<(unsigned)((l1 + 127) / 128), 128, 0, ctx->stream>>>(c, gi.nx, gi.ny, gi.nz, bspline3_pole(gi.ny));
@@ -453,12 +601,25 @@ inline int resample_batch(b200reg_ctx* ctx, int n, const void* const* d_in, cons
         bool bsp = false;
         for (int q = 0; q < b.n; ++q) bsp = bsp || b.item[q].interp == B200REG_INTERP_BSPLINE;
         const dim3 g3 = grid3(go.nx, go.ny, go.nz);
+        const bool with_pack = next_group < groups.size();
+        const PackedD& pk = with_pack ? groups[next_group] : no_pack;
+        if (with_pack) ++next_group;
         if (bsp) {
-            if (gi.small) resample_batch_kernel<true, true><<<g3, block3(), 0, ctx->stream>>>(b, gi, go, ch);
-            else resample_batch_kernel<false, true><<<g3, block3(), 0, ctx->stream>>>(b, gi, go, ch);
+            if (gi.small) {
+                if (with_pack) resample_batch_kernel<true, true, true><<<g3, block3(), 0, ctx->stream>>>(b, gi, go, ch, pk);
+                else resample_batch_kernel<true, true, false><<<g3, block3(), 0, ctx->stream>>>(b, gi, go, ch, pk);
+            } else {
+                if (with_pack) resample_batch_kernel<false, true, true><<<g3, block3(), 0, ctx->stream>>>(b, gi, go, ch, pk);
+                else resample_batch_kernel<false, true, false><<<g3, block3(), 0, ctx->stream>>>(b, gi, go, ch, pk);
+            }
         } else {
-            if (gi.small) resample_batch_kernel<true, false><<<g3, block3(), 0, ctx->stream>>>(b, gi, go, ch);
-            else resample_batch_kernel<false, false><<<g3, block3(), 0, ctx->stream>>>(b, gi, go, ch);
+            if (gi.small) {
+                if (with_pack) resample_batch_kernel<true, false, true><<<g3, block3(), 0, ctx->stream>>>(b, gi, go, ch, pk);
+                else resample_batch_kernel<true, false, false><<<g3, block3(), 0, ctx->stream>>>(b, gi, go, ch, pk);
+            } else {
+                if (with_pack) resample_batch_kernel<false, false, true><<<g3, block3(), 0, ctx->stream>>>(b, gi, go, ch, pk);
+                else resample_batch_kernel<false, false, false><<<g3, block3(), 0, ctx->stream>>>(b, gi, go, ch, pk);
+            }
         }
         ctx->launches++;
         B200_CHECK_LAUNCH();

@@ -401,3 +401,41 @@ def test_pipelined_host_api_gives_the_same_results(engine):
     # the transform that came back is usable as it is
     assert np.array_equal(reg.apply_transform(pairs[0][1], pairs[0][0], tfm, -1000, sk.sitkLinear).array, img.array)
     assert list(reg.iter_registrations([], **kw)) == []
+
+
+@pytest.mark.parametrize("size", [(40, 36, 24), (37, 33, 21)])
+def test_bit_packed_label_propagation_is_exact(engine, size):
+    """Batches with many UInt8 nearest-neighbour items take the bit-packed path (one gathered word per output voxel instead of one
+    byte per structure): same bits as the per-image calls and as the oracle -- for {0, 1} and {0, 255} masks, an empty mask, a
+    multi-valued label (recognised on the device, gathered from its own image), non-zero default values, more items than one word
+    holds (40 -> two groups), volumes whose size is / is not a multiple of four, and next to a linearly interpolated CT."""
+    sp = (1.0, 1.2, 1.6)
+    fixed, moving = synth_pair(size, seed=31, spacing=sp)
+    rng = np.random.default_rng(3)
+    base = synth_labels(size, 40, seed=700)
+    labels = []
+    for k, l in enumerate(base):
+        if k % 5 == 1:
+            l = (l * 255).astype(np.uint8)
+        elif k % 5 == 2:
+            l = (l * rng.integers(1, 4, size=l.shape)).astype(np.uint8)   # several non-zero values
+        elif k % 5 == 3:
+            l = np.zeros_like(l)
+        labels.append(Image(l, sp))
+    dvf = Image(smooth_random_dvf(size, seed=5, peak_mm=6.0), sp, is_vector=True)
+    tfm = sk.DisplacementFieldTransform(dvf)
+    defaults = [-1000] + [0 if k % 7 else 9 for k in range(40)]
+    interps = [sk.sitkLinear] + [sk.sitkNearestNeighbor] * 40
+    outs = reg.apply_transform_batch([moving] + labels, fixed, tfm, defaults, interps)
+    g = orc.geom_of(fixed)
+    chain = [("dvf", dvf.array, g)]
+    assert np.array_equal(outs[0].array, orc.resample_scalar(moving.array, g, g, chain, 2, -1000.0))
+    for k in range(40):
+        one = reg.apply_transform(labels[k], fixed, tfm, defaults[k + 1], sk.sitkNearestNeighbor)   # per-image path (no packing)
+        assert np.array_equal(outs[k + 1].array, one.array), k
+        assert np.array_equal(outs[k + 1].array, orc.resample_scalar(labels[k].array, g, g, chain, 1, defaults[k + 1])), k
+    # an affine chain onto another grid (points outside the input get the default value)
+    aff = sk.AffineTransform([[1, 0.02, 0], [-0.02, 1, 0], [0, 0, 1]], (3.0, -2.0, 1.0), (15.0, 15.0, 15.0))
+    outs = reg.apply_transform_batch(labels[:9], fixed, aff, [5] * 9, [sk.sitkNearestNeighbor] * 9)
+    for k in range(9):
+        assert np.array_equal(outs[k].array, ref.apply_transform(labels[k], fixed, aff, 5, sk.sitkNearestNeighbor).array), k
