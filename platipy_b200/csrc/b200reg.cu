@@ -75,12 +75,9 @@ API int b200reg_create(int device, void* stream, b200reg_ctx** out)
     if (const char* e = getenv("B200REG_FORCE_SEPARABLE")) ctx->force_separable = (e[0] == '1');
     if (const char* e = getenv("B200REG_UNFUSED_FORCE")) ctx->unfused_force = (e[0] == '1');
     if (const char* e = getenv("B200REG_STAPLE_VOXELWISE")) ctx->staple_voxelwise = (e[0] == '1');
-    if (const char* e = getenv("B200REG_UPDATE_WS")) ctx->update_ws = (e[0] == '1');
     if (const char* e = getenv("B200REG_ZM_TMA")) ctx->zm_tma = atoi(e);
     if (const char* e = getenv("B200REG_ZM_TMA_L2")) ctx->zm_tma_l2 = atoi(e);
-    if (const char* e = getenv("B200REG_UPDATE_BRANCHY")) ctx->update_branchy = (e[0] == '1');
     if (const char* e = getenv("B200REG_ZM_REGADD")) ctx->zm_regadd = (e[0] != '0');
-    if (const char* e = getenv("B200REG_UPDATE_SPLIT")) ctx->update_split = (e[0] != '0');
     if (const char* e = getenv("B200REG_PF_WARP")) ctx->pf_warp = atoi(e);
     if (const char* e = getenv("B200REG_PF_FORCE")) ctx->pf_force = atoi(e);
     if (const char* e = getenv("B200REG_WARP_MARCH")) ctx->warp_march = atoi(e);

@@ -95,12 +95,9 @@ struct b200reg_ctx {
     bool force_separable = false;  // B200REG_FORCE_SEPARABLE=1: unfused smoothing passes (A/B testing)
     bool unfused_force = false;    // B200REG_UNFUSED_FORCE=1: separate warp and force kernels (W through HBM)
     bool staple_voxelwise = false; // B200REG_STAPLE_VOXELWISE=1: per-voxel EM kernels instead of the pattern-histogram EM
-    bool update_ws = false;        // B200REG_UPDATE_WS=1: warp-specialised (producer/consumer) fused update kernel
     int zm_tma = 1;                // B200REG_ZM_TMA=0: cp.async (LDGSTS) staging of the fused smoothing kernel's plane tiles instead of one tensor-map TMA copy per tile
     int zm_tma_l2 = 3;             // B200REG_ZM_TMA_L2 = 0 | 1 | 2 | 3: L2 promotion of the tensor-map loads (none, 64, 128, 256 bytes)
-    bool update_branchy = false;   // B200REG_UPDATE_BRANCHY=1: first version of the fused update kernel's force phase (per-voxel branches)
     bool zm_regadd = false;        // B200REG_ZM_REGADD=0: add + smooth stages both operands in shared memory (first version)
-    bool update_split = true;      // B200REG_UPDATE_SPLIT=0: fused z-marching warp + force kernel instead of the two high-occupancy kernels
     int pf_warp = 0;               // B200REG_PF_WARP=n: warp kernel prefetches the field n planes ahead into L2
     int pf_force = 0;              // B200REG_PF_FORCE=n: force kernel prefetches W / F n steps ahead into L2
     int warp_march = 0;            // B200REG_WARP_MARCH=n: z-marching warp kernel with n planes per thread (0: one-shot kernel)

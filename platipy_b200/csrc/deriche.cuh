@@ -220,15 +220,18 @@ inline int recursive_gaussian_vec3(b200reg_ctx* ctx, double* field, const b200re
     if (nx < 4 || ny < 4 || nz < 4)
         return set_error(B200REG_ERR_RUNTIME, "RecursiveGaussianImageFilter: the number of pixels along a direction is less than 4");
     const size_t n = nvox(g);
-    TempBuf tmp;
-    B200_TRY(tmp.alloc(ctx, 3 * n * sizeof(double)));
-    double* bufs[2] = { field, tmp.as<double>() };
+    // field -> t1 -> t2 -> field: the third pass writes the result in place, no copy back
+    TempBuf t1, t2;
+    B200_TRY(t1.alloc(ctx, 3 * n * sizeof(double)));
+    B200_TRY(t2.alloc(ctx, 3 * n * sizeof(double)));
+    double* bufs[4] = { field, t1.as<double>(), t2.as<double>(), field };
     const int order_zxy[3] = { 2, 0, 1 }, order_xyz[3] = { 0, 1, 2 };  // semantic switch recursive_gaussian_axis_order
     const int* order = semantics().recursive_gaussian_axis_order ? order_xyz : order_zxy;
     const size_t strides[3] = { 1, (size_t)nx, (size_t)nx * ny };
     const int dims[3] = { nx, ny, nz };
-    int cur = 0;
     for (int pass = 0; pass < 3; ++pass) {
+        const double* src = bufs[pass];
+        double* dst = bufs[pass + 1];
         const int axis = order[pass];
         const DericheC c = deriche_setup(sigma[axis], g.spacing[axis]);
         // thread axes: a = the lowest remaining axis (x unless axis == 0), b = the other
@@ -237,18 +240,15 @@ inline int recursive_gaussian_vec3(b200reg_ctx* ctx, double* field, const b200re
         if (axis == 0) {
             const size_t nlines = (size_t)ny * nz * 3;  // the three component volumes are contiguous: lines are rows of nx samples
             const unsigned nblk = (unsigned)((nlines + 32 * DX_WARPS - 1) / (32 * DX_WARPS));
-            deriche_x_kernel<<<nblk, 32 * DX_WARPS, 0, ctx->stream>>>(bufs[cur], bufs[cur ^ 1], nx, ny, nlines, c);
+            deriche_x_kernel<<<nblk, 32 * DX_WARPS, 0, ctx->stream>>>(src, dst, nx, ny, nlines, c);
         } else {
             dim3 blk(128, 1, 1), grd((dims[aa] + 127) / 128, dims[ab], 3);
-            deriche_line_kernel<<<grd, blk, 0, ctx->stream>>>(bufs[cur], bufs[cur ^ 1], dims[axis], strides[axis], dims[aa], strides[aa], dims[ab],
+            deriche_line_kernel<<<grd, blk, 0, ctx->stream>>>(src, dst, dims[axis], strides[axis], dims[aa], strides[aa], dims[ab],
                                                               strides[ab], n, c);
         }
         ctx->launches++;
         B200_CHECK_LAUNCH();
-        cur ^= 1;
     }
-    // three passes: the result is in tmp
-    B200_CUDA(cudaMemcpyAsync(field, bufs[cur], 3 * n * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
     return B200REG_OK;
 }
 

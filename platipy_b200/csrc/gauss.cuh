@@ -398,15 +398,22 @@ __device__ __forceinline__ void tma_prefetch_descriptor(const CUtensorMap* tmap)
 // that the displacement smoothing that follows is a plain MODE 0 pass instead of a MODE 1 pass.
 // TMA (MODE 0 / 3 only): plane tiles are staged by the TMA unit (one elected thread, one tensor-map copy per plane, completion
 // counted in bytes on an mbarrier) instead of one cp.async per element by every thread; same shared layout, same arithmetic.
+#ifndef ZM_TMA_STAGES
+#define ZM_TMA_STAGES 4
+#endif
 template <int R, int TXW>
 struct Zm2Layout {
     static constexpr int RP = (R + 1) & ~1;  // x halo padded to an even count: 16-byte aligned shared rows
     static constexpr int AW = TXW + 2 * RP, AH = ZM_TY + 2 * R, NA = AW * AH;
     static constexpr int NAP = (NA + 15) & ~15;  // buffer stride: every staged plane starts on a 128-byte boundary (TMA destination)
     static constexpr int NB = AH * TXW;
+    // staged planes in flight: cp.async stages through registers-free but thread-issued copies, one plane ahead; the TMA unit needs no
+    // thread resources, so the tensor-map path runs ZM_TMA_STAGES - 1 planes ahead (ncu: with one plane in flight the mbarrier wait
+    // was the largest stall of the kernel -- a CTA's plane step is shorter than the DRAM latency under load)
+    static constexpr int STAGES_TMA = ZM_TMA_STAGES, STAGES_CP = 2;
 };
 template <int R, int RZ, int MODE, int TXW, bool TMA>
-__global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, 128 / TXW) conv3d_zm2_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out,
+__global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, (TMA && MODE == 0 && TXW == 32) ? 5 : 128 / TXW) conv3d_zm2_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out,
                                                                int nx, int ny, int nz, int zchunk, int nchunks,
                                                                const __grid_constant__ SmallCoeffs kc, const DemonsCtrl* __restrict__ ctrl, int it,
                                                                const __grid_constant__ CUtensorMap tmap)
@@ -421,10 +428,11 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, 128 / TXW) conv3d_z
     constexpr int NT = Zm2Threads<R, TXW>::value;
     constexpr int NYZ = 4 * TXW;  // threads that own voxels in the y / z passes
     constexpr int NLD = (NA + NT - 1) / NT;
+    constexpr int NST = TMA ? L::STAGES_TMA : L::STAGES_CP;
     extern __shared__ __align__(128) double zm_smem[];
-    double* Aa = zm_smem;                        // [2][NAP]
-    double* Ab = zm_smem + 2 * NAP;              // [2][NAP] (ADD only)
-    double* B = zm_smem + (ADD ? 4 : 2) * NAP;   // [AH][TX]
+    double* Aa = zm_smem;                              // [NST][NAP]
+    double* Ab = zm_smem + NST * NAP;                  // [NST][NAP] (ADD only)
+    double* B = zm_smem + (ADD ? 2 : 1) * NST * NAP;   // [AH][TX]
 
     const int tid = threadIdx.x;
     const int x0 = blockIdx.x * TXW, y0 = blockIdx.y * ZM_TY;
@@ -438,7 +446,7 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, 128 / TXW) conv3d_z
     // cp.async path: element e of a staged plane <-> clamped global offset.  TMA path: the same slots hold, for the halo cells of a
     // border tile that lie outside the image, the shared-memory index of the replicated edge value (-1: nothing to fix).
     int goff[NLD];
-    __shared__ __align__(8) unsigned long long full_bar[2];
+    __shared__ __align__(8) unsigned long long full_bar[NST];
     const bool border = x0 - RP < 0 || x0 + TXW + RP > nx || y0 - R < 0 || y0 + ZM_TY + R > ny;
 #pragma unroll
     for (int l = 0; l < NLD; ++l) {
@@ -453,8 +461,8 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, 128 / TXW) conv3d_z
     if (TMA) {
         if (tid == 0) {
             tma_prefetch_descriptor(&tmap);
-            mbar_init(&full_bar[0], 1);
-            mbar_init(&full_bar[1], 1);
+#pragma unroll
+            for (int b = 0; b < NST; ++b) mbar_init(&full_bar[b], 1);
             mbar_fence_init();
         }
         __syncthreads();
@@ -503,14 +511,16 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, 128 / TXW) conv3d_z
         load_next(zbeg);
         store_next(0);
     } else {
-        stage(zbeg, 0);
+#pragma unroll
+        for (int b = 0; b < NST - 1; ++b)
+            if (b < nsteps) stage(zbeg + b, b);
     }
     for (int q0 = 0; q0 < nsteps; q0 += NR) {
 #pragma unroll
         for (int s = 0; s < NR; ++s) {
             const int q = q0 + s;
             if (q < nsteps) {
-                const int buf = q & 1;
+                const int buf = q % NST;
                 // MODE 3: the operand added at the store is fetched now, a whole plane step before it is needed
                 double addv[4] = { 0.0, 0.0, 0.0, 0.0 };
                 if (MODE == 3 && tid < NYZ && q >= 2 * RZ) {
@@ -526,7 +536,7 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, 128 / TXW) conv3d_z
                     if (q + 1 < nsteps) load_next(zbeg + q + 1);
                 } else {
                     if (TMA) {
-                        mbar_wait(&full_bar[buf], (unsigned)((q >> 1) & 1));
+                        mbar_wait(&full_bar[buf], (unsigned)((q / NST) & 1));
                         if (border) {
                             // replicate the image edge into the zero-filled halo cells (sources are cells inside the image, targets
                             // cells outside it: disjoint, so no barrier is needed between the reads and the writes)
@@ -539,7 +549,8 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, 128 / TXW) conv3d_z
                         cp_async_wait_all();
                     }
                     __syncthreads();
-                    if (q + 1 < nsteps) stage(zbeg + q + 1, buf ^ 1);
+                    // the buffer refilled now was last read by the x pass of step q - 1, which every thread has left
+                    if (q + NST - 1 < nsteps) stage(zbeg + q + NST - 1, (q + NST - 1) % NST);
                 }
                 // ---- x pass: per task two output pairs {2cx, 2cx+1} and {32+2cx, 32+2cx+1} of one row (rows incl. the
                 // y halo).  Lanes read consecutive 16-byte words: conflict-free 128-bit shared loads and stores.
@@ -603,7 +614,7 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, 128 / TXW) conv3d_z
                     }
                 }
                 // MODE 2: buffer buf ^ 1 was last read by the x pass of step q - 1, two barriers ago
-                if (REGADD && q + 1 < nsteps) store_next(buf ^ 1);
+                if (REGADD && q + 1 < nsteps) store_next((q + 1) % NST);
             }
         }
     }
@@ -620,9 +631,9 @@ inline int launch_zm2_tx(b200reg_ctx* ctx, const double* a, const double* b, dou
     memset(&tm, 0, sizeof(tm));
     // the tensor map describes operand a: (nx, ny, components * nz) float64, box = one staged plane tile (B200REG_ZM_TMA=0: cp.async staging)
     const bool tma = ctx->zm_tma != 0 && zm_make_tensor_map(a, nx, ny, (long)nz * (long)(g.z / nchunks), L::AW, L::AH, ctx->zm_tma_l2, &tm);
-    constexpr size_t smem1 = (size_t)(2 * L::NAP + L::NB) * sizeof(double);
 #define ZM2_GO(MODE, TMA_, A, B_)                                                                                                            \
     do {                                                                                                                                     \
+        constexpr size_t smem1 = (size_t)((TMA_ ? L::STAGES_TMA : L::STAGES_CP) * L::NAP + L::NB) * sizeof(double);                                                \
         B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, MODE, TXW, TMA_>, smem1));                                                \
         conv3d_zm2_kernel<R, RZ, MODE, TXW, TMA_><<<g, NT, smem1, ctx->stream>>>(A, B_, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, tm); \
     } while (0)
@@ -705,7 +716,9 @@ inline int launch_conv3d_zmarch(b200reg_ctx* ctx, const double* a, const double*
         // (chunk + halo) plane steps: pick the chunk count with the least total.  Measured at 512 x 512 x 256: 3 chunks
         // (7.8 -> 8 rounds) instead of 2 (5.2 -> 6 rounds), 3.25 -> 3.20 ms / iteration; at 128 x 128 x 64 the model picks
         // 6 chunks = 288 CTAs, all resident in one round of 15 steps, instead of three rounds of 8.
-        const long slots = (long)ctx->sm_count * (txw == 32 ? 4 : 2);
+        // resident CTAs per SM: 4 at 32-wide tiles (5 for the plain tensor-map pass: 72 registers), 2 at 64-wide tiles
+        const bool tma5 = txw == 32 && !b && ctx->zm_tma != 0 && (nx % 2) == 0;
+        const long slots = (long)ctx->sm_count * (txw == 32 ? (tma5 ? 5 : 4) : 2);
         long best_cost = -1;
         int best_k = nchunks;
         for (int k = 1; k <= 32 && k <= max_chunks; ++k) {

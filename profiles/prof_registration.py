@@ -13,4 +13,4 @@ fixed, moving = synth_pair(size, seed=0, moving_seed=100)
 dF, dM = eng.to_device(fixed), eng.to_device(moving)
 img, tfm, dvf = reg.fast_symmetric_forces_demons_registration(dF, dM, resolution_staging=[4, 2, 1], iteration_staging=[100, 50, 25])
 eng.synchronize()
-print(reg.LAST_LEVEL_STATS)
+print([{k: v for k, v in s.items() if k != "trace"} for s in reg.LAST_LEVEL_STATS])
