@@ -86,6 +86,7 @@ API int b200reg_create(int device, void* stream, b200reg_ctx** out)
     if (const char* e = getenv("B200REG_ZM_ADDOUT")) ctx->zm_addout = (e[0] != '0');
     if (const char* e = getenv("B200REG_FORCE_ZM1")) ctx->force_zm1 = (e[0] == '1');
     if (const char* e = getenv("B200REG_PACK_LABELS")) ctx->pack_labels = (e[0] != '0');
+    if (const char* e = getenv("B200REG_PDL")) ctx->pdl = (e[0] != '0');
     *out = ctx;
     return B200REG_OK;
 }
@@ -96,6 +97,7 @@ API int b200reg_destroy(b200reg_ctx* ctx)
     cudaStreamSynchronize(ctx->stream);
     if (ctx->owns_stream) cudaStreamDestroy(ctx->stream);
     if (ctx->h_scratch) cudaFreeHost(ctx->h_scratch);
+    if (ctx->h_trace) cudaFreeHost(ctx->h_trace);
     delete ctx;
     return B200REG_OK;
 }
@@ -215,7 +217,7 @@ API int b200reg_minmax(b200reg_ctx* ctx, const void* d_in, int dtype, size_t n, 
     TempBuf part, mm;
     B200_TRY(mm.alloc(ctx, 2 * sizeof(double)));
     B200_DISPATCH_DTYPE(dtype, T, { B200_TRY(minmax_device<T>(ctx, (const T*)d_in, n, mm.as<double>(), &part)); });
-    B200_CUDA(cudaMemcpyAsync(ctx->h_scratch, mm.p, 2 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(small_d2h(ctx, ctx->h_scratch, mm.p, 2 * sizeof(double)));
     B200_CUDA(cudaStreamSynchronize(ctx->stream));
     if (h_min) *h_min = ctx->h_scratch[0];
     if (h_max) *h_max = ctx->h_scratch[1];
@@ -309,7 +311,7 @@ static int read_stats(b200reg_ctx* ctx, const DemonsWorkspace& ws, const b200reg
                       int level = -1)
 {
     DemonsCtrl h;
-    B200_CUDA(cudaMemcpyAsync(ctx->h_scratch, ws.ctrl.p, sizeof(DemonsCtrl), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(small_d2h(ctx, ctx->h_scratch, ws.ctrl.p, sizeof(DemonsCtrl)));
     B200_CUDA(cudaStreamSynchronize(ctx->stream));
     memcpy(&h, ctx->h_scratch, sizeof(h));
     if (level >= 0 && ws.trace.p) {
@@ -317,7 +319,17 @@ static int read_stats(b200reg_ctx* ctx, const DemonsWorkspace& ws, const b200reg
         if ((int)ctx->traces.size() <= level) ctx->traces.resize(level + 1);
         const int n = h.elapsed < n_iters ? h.elapsed : n_iters;
         ctx->traces[level].assign(2 * (size_t)(n > 0 ? n : 0), 0.0);
-        if (n > 0) B200_CUDA(cudaMemcpy(ctx->traces[level].data(), ws.trace.p, sizeof(double) * 2 * (size_t)n, cudaMemcpyDeviceToHost));
+        if (n > 0) {
+            if (ctx->h_trace_doubles < 2 * (size_t)n) {
+                if (ctx->h_trace) cudaFreeHost(ctx->h_trace);
+                ctx->h_trace = nullptr;
+                ctx->h_trace_doubles = 2 * (size_t)(n < 512 ? 512 : n);
+                B200_CUDA(cudaMallocHost(&ctx->h_trace, ctx->h_trace_doubles * sizeof(double)));
+            }
+            B200_CUDA(small_d2h(ctx, ctx->h_trace, ws.trace.p, sizeof(double) * 2 * (size_t)n));
+            B200_CUDA(cudaStreamSynchronize(ctx->stream));
+            memcpy(ctx->traces[level].data(), ctx->h_trace, sizeof(double) * 2 * (size_t)n);
+        }
     }
     st->elapsed_iterations = h.elapsed;
     st->voxels_lo = (int32_t)(nvox(g) & 0x7fffffff);
@@ -897,7 +909,7 @@ API int b200reg_largest_component(b200reg_ctx* ctx, const uint8_t* d_in, const i
     B200_TRY(largest_component(ctx, d_in, size, d_out, info.as<unsigned long long>()));
     if (h_n_components || h_voxels) {
         unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->h_scratch);
-        B200_CUDA(cudaMemcpyAsync(h, info.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        B200_CUDA(small_d2h(ctx, h, info.p, 2 * sizeof(unsigned long long)));
         B200_CUDA(cudaStreamSynchronize(ctx->stream));
         if (h_voxels) *h_voxels = (int64_t)(h[0] >> 32);
         if (h_n_components) *h_n_components = (int64_t)h[1];
@@ -931,7 +943,7 @@ API int b200reg_process_probability(b200reg_ctx* ctx, const void* d_prob, int dt
     B200_TRY(largest_component(ctx, d_out, size, d_out, info.as<unsigned long long>()));
     if (h_n_components) {
         unsigned long long* h = reinterpret_cast<unsigned long long*>(ctx->h_scratch);
-        B200_CUDA(cudaMemcpyAsync(h, info.p, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+        B200_CUDA(small_d2h(ctx, h, info.p, 2 * sizeof(unsigned long long)));
         B200_CUDA(cudaStreamSynchronize(ctx->stream));
         *h_n_components = (int64_t)h[1];
     }
@@ -972,7 +984,7 @@ API int b200reg_bounding_box(b200reg_ctx* ctx, const uint8_t* d_mask, const int3
     ctx->launches += 2;
     B200_CHECK_LAUNCH();
     int* h = reinterpret_cast<int*>(ctx->h_scratch);
-    B200_CUDA(cudaMemcpyAsync(h, bb.p, 6 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(small_d2h(ctx, h, bb.p, 6 * sizeof(int)));
     B200_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int d = 0; d < 6; ++d) h_bbox[d] = h[d];
     return B200REG_OK;
@@ -1186,7 +1198,7 @@ API int b200reg_linreg_correlation(b200reg_ctx* ctx, const float* d_fixed, const
     linreg_corr_final_kernel<<<1, 64, 0, ctx->stream>>>(part.as<double>(), nb, out.as<double>());
     ctx->launches += 2;
     B200_CHECK_LAUNCH();
-    B200_CUDA(cudaMemcpyAsync(ctx->h_scratch, out.p, sizeof(double) * LINREG_CORR_NV, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(small_d2h(ctx, ctx->h_scratch, out.p, sizeof(double) * LINREG_CORR_NV));
     B200_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int v = 0; v < LINREG_CORR_NV; ++v) h_out[v] = ctx->h_scratch[v];
     return B200REG_OK;
@@ -1213,7 +1225,7 @@ API int b200reg_image_moments(b200reg_ctx* ctx, const float* d_image, const b200
     image_moments_final_kernel<<<1, 32, 0, ctx->stream>>>(part.as<double>(), nb, out.as<double>());
     ctx->launches += 2;
     B200_CHECK_LAUNCH();
-    B200_CUDA(cudaMemcpyAsync(ctx->h_scratch, out.p, sizeof(double) * MOMENTS_NV, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(small_d2h(ctx, ctx->h_scratch, out.p, sizeof(double) * MOMENTS_NV));
     B200_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int v = 0; v < MOMENTS_NV; ++v) h_out[v] = ctx->h_scratch[v];
     return B200REG_OK;
@@ -1303,7 +1315,7 @@ API int b200reg_linreg_mattes_derivative(b200reg_ctx* ctx, const float* d_fixed,
     linreg_mattes_final_kernel<<<1, 32, 0, ctx->stream>>>(part.as<double>(), nb, out.as<double>());
     ctx->launches += 2;
     B200_CHECK_LAUNCH();
-    B200_CUDA(cudaMemcpyAsync(ctx->h_scratch, out.p, sizeof(double) * MATTES_NV, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(small_d2h(ctx, ctx->h_scratch, out.p, sizeof(double) * MATTES_NV));
     B200_CUDA(cudaStreamSynchronize(ctx->stream));  // also: h_table is caller memory
     for (int v = 0; v < MATTES_NV; ++v) h_out[v] = ctx->h_scratch[v];
     return B200REG_OK;

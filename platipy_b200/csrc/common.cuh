@@ -89,6 +89,8 @@ struct b200reg_ctx {
     int sm_count = 148;
     // pinned scratch for small read-backs
     double* h_scratch = nullptr;  // 64 doubles
+    double* h_trace = nullptr;    // pinned landing area of the Demons iteration trace (grown on demand)
+    size_t h_trace_doubles = 0;
     std::set<const void*> smem_optin;  // kernels whose dynamic shared-memory limit was raised on this device
     // per-iteration (metric, RMS change) pairs of the most recent Demons call, one vector per level (b200reg_demons_trace)
     std::vector<std::vector<double>> traces;
@@ -104,6 +106,7 @@ struct b200reg_ctx {
     int zm_chunks = 0;             // B200REG_ZM_CHUNKS=n: z-chunks per tile column of the fused smoothing kernel (0: automatic)
     bool zm_tx32 = true;           // B200REG_ZM_TX32=0: 64-wide tiles (320 threads, 2 CTAs per SM) in the fused smoothing kernel; 32-wide: 4 CTAs per SM, -1 %
     bool zm_addout = true;         // B200REG_ZM_ADDOUT=0: D + U formed inside the displacement smoothing (staged twice) instead of at the end of the update smoothing
+    bool pdl = true;               // B200REG_PDL=0: the Demons loop kernels are launched without programmatic dependent launch (A/B)
     bool pack_labels = true;       // B200REG_PACK_LABELS=0: UInt8 nearest-neighbour items of a resample batch are gathered one byte at a time (A/B)
     bool force_zm1 = false;        // B200REG_FORCE_ZM1=1: first-generation fused smoothing kernel
 };
@@ -137,6 +140,48 @@ struct TempBuf {
         return reinterpret_cast<T*>(p);
     }
 };
+
+// ---- programmatic dependent launch (PDL) ---------------------------------------------------------------------------------------
+// The Demons loop is a chain of short dependent kernels (five per iteration; at the coarse pyramid levels each runs for 10-20 us).
+// Launched with cudaLaunchAttributeProgrammaticStreamSerialization, a kernel's CTAs may become resident while the tail of its
+// predecessor is still running: every loop kernel signals `pdl_launch_dependents()` at once, runs the part of its prologue that
+// reads no data of the predecessor (index arithmetic, mbarrier / tensor-map set-up), and calls `pdl_wait()` before its first
+// dependent access -- the wait returns when the predecessor grid has completed and its writes are visible.  A kernel launched
+// without the attribute sees both as no-ops.  B200REG_PDL=0 turns the attribute off (A/B).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(b200reg_ctx* ctx, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = ctx->pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
+// ---- small read-backs ------------------------------------------------------------------------------------------------------------
+// A few bytes of statistics go back to the host after most calls (min / max, the Demons control block, metric sums).  As
+// cudaMemcpyAsync they would queue on the device-to-host copy engine BEHIND any bulk download in flight on another stream -- the
+// pipelined host API keeps a 1.6 GB field download running while the next registration starts, and a 16-byte read-back then
+// blocks the host for 30 ms.  So they are stores by one warp into pinned host memory (directly addressable under UVA) instead:
+// ordered on the compute stream, independent of the copy engines.
+__global__ void small_d2h_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, int nwords)
+{
+    for (int i = threadIdx.x; i < nwords; i += blockDim.x) dst[i] = src[i];
+    __threadfence_system();
+}
+inline cudaError_t small_d2h(b200reg_ctx* ctx, void* h_pinned_dst, const void* d_src, size_t bytes)
+{
+    small_d2h_kernel<<<1, 128, 0, ctx->stream>>>(reinterpret_cast<const uint32_t*>(d_src), reinterpret_cast<uint32_t*>(h_pinned_dst), (int)((bytes + 3) / 4));
+    return cudaGetLastError();
+}
 
 // cudaFuncAttributeMaxDynamicSharedMemorySize is a per-device attribute: opt in once per context and kernel.
 template <typename K>

@@ -177,6 +177,8 @@ __global__ void __launch_bounds__(BX* BY) demons_force_kernel(const float* __res
 __global__ void __launch_bounds__(1024) demons_finish_kernel(const double* __restrict__ partials, size_t nblocks, DemonsCtrl* ctrl,
                                                               double max_rms_error, int it, int n_iters, double* __restrict__ trace)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     if (it >= ctrl->halt_iter) return;
     double a = 0.0, b = 0.0, c = 0.0;
     for (size_t q = threadIdx.x; q < nblocks; q += 1024) {
@@ -301,7 +303,8 @@ inline int demons_calculate_change(b200reg_ctx* ctx, const float* F, const GeomD
         demons_force_kernel<<<g, b, 0, ctx->stream>>>(F, ws->W.as<float>(), ws->U.as<double>(), ws->partials.as<double>(), gf, fp, ctrl, it);
         ctx->launches += 2;
     }
-    demons_finish_kernel<<<1, 1024, 0, ctx->stream>>>(ws->partials.as<double>(), nblocks, ctrl, fp.max_rms_error, it, n_iters, ws->trace.as<double>());
+    B200_CUDA(launch_pdl(ctx, demons_finish_kernel, dim3(1), dim3(1024), 0, ws->partials.as<double>(), nblocks, ctrl, fp.max_rms_error, it, n_iters,
+                         ws->trace.as<double>()));
     ctx->launches += 1;
     B200_CHECK_LAUNCH();
     return B200REG_OK;

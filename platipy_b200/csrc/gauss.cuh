@@ -399,7 +399,7 @@ __device__ __forceinline__ void tma_prefetch_descriptor(const CUtensorMap* tmap)
 // TMA (MODE 0 / 3 only): plane tiles are staged by the TMA unit (one elected thread, one tensor-map copy per plane, completion
 // counted in bytes on an mbarrier) instead of one cp.async per element by every thread; same shared layout, same arithmetic.
 #ifndef ZM_TMA_STAGES
-#define ZM_TMA_STAGES 4
+#define ZM_TMA_STAGES 2
 #endif
 template <int R, int TXW>
 struct Zm2Layout {
@@ -408,8 +408,9 @@ struct Zm2Layout {
     static constexpr int NAP = (NA + 15) & ~15;  // buffer stride: every staged plane starts on a 128-byte boundary (TMA destination)
     static constexpr int NB = AH * TXW;
     // staged planes in flight: cp.async stages through registers-free but thread-issued copies, one plane ahead; the TMA unit needs no
-    // thread resources, so the tensor-map path runs ZM_TMA_STAGES - 1 planes ahead (ncu: with one plane in flight the mbarrier wait
-    // was the largest stall of the kernel -- a CTA's plane step is shorter than the DRAM latency under load)
+    // thread resources, so the tensor-map path can run ZM_TMA_STAGES - 1 planes ahead.  Measured (profiles/r02c_ab_tma_stages.log, full-
+    // resolution iteration): 2 staged planes 2.82 ms, 3: 2.86, 4: 2.89, 6: 2.84, cp.async 2.92 -- depth buys nothing, the wait on the
+    // mbarrier is bandwidth, not latency; the default stays at 2
     static constexpr int STAGES_TMA = ZM_TMA_STAGES, STAGES_CP = 2;
 };
 template <int R, int RZ, int MODE, int TXW, bool TMA>
@@ -418,7 +419,7 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, (TMA && MODE == 0 &
                                                                const __grid_constant__ SmallCoeffs kc, const DemonsCtrl* __restrict__ ctrl, int it,
                                                                const __grid_constant__ CUtensorMap tmap)
 {
-    if (ctrl && it >= ctrl->halt_iter) return;
+    pdl_launch_dependents();
     static_assert(!TMA || MODE == 0 || MODE == 3, "the tensor-map staging handles one staged operand");
     constexpr bool ADD = MODE == 1;     // second operand staged in shared memory
     constexpr bool REGADD = MODE == 2;  // operands summed in registers before staging
@@ -467,6 +468,9 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, (TMA && MODE == 0 &
         }
         __syncthreads();
     }
+    // everything above is index arithmetic and barrier set-up; from here on the kernel reads what its predecessor wrote
+    pdl_wait();
+    if (ctrl && it >= ctrl->halt_iter) return;
     double pre_a[REGADD ? NLD : 1], pre_b[REGADD ? NLD : 1];  // MODE 2: operands of the next plane, in flight
     auto load_next = [&](int z) {
         const int zc = z < 0 ? 0 : (z > nz - 1 ? nz - 1 : z);
@@ -635,7 +639,7 @@ inline int launch_zm2_tx(b200reg_ctx* ctx, const double* a, const double* b, dou
     do {                                                                                                                                     \
         constexpr size_t smem1 = (size_t)((TMA_ ? L::STAGES_TMA : L::STAGES_CP) * L::NAP + L::NB) * sizeof(double);                                                \
         B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, MODE, TXW, TMA_>, smem1));                                                \
-        conv3d_zm2_kernel<R, RZ, MODE, TXW, TMA_><<<g, NT, smem1, ctx->stream>>>(A, B_, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, tm); \
+        B200_CUDA(launch_pdl(ctx, conv3d_zm2_kernel<R, RZ, MODE, TXW, TMA_>, g, dim3(NT), smem1, A, B_, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, tm)); \
     } while (0)
     if (b && addout) {
         if (tma) ZM2_GO(3, true, a, b);
@@ -651,7 +655,7 @@ inline int launch_zm2_tx(b200reg_ctx* ctx, const double* a, const double* b, dou
     if (b) {
         constexpr size_t smem2 = (size_t)(4 * L::NAP + L::NB) * sizeof(double);
         B200_TRY(ensure_dynamic_smem(ctx, conv3d_zm2_kernel<R, RZ, 1, TXW, false>, smem2));
-        conv3d_zm2_kernel<R, RZ, 1, TXW, false><<<g, NT, smem2, ctx->stream>>>(a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, tm);
+        B200_CUDA(launch_pdl(ctx, conv3d_zm2_kernel<R, RZ, 1, TXW, false>, g, dim3(NT), smem2, a, b, out, nx, ny, nz, zchunk, nchunks, sc, ctrl, it, tm));
     } else {
         if (tma) ZM2_GO(0, true, a, nullptr);
         else ZM2_GO(0, false, a, nullptr);

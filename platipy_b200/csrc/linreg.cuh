@@ -115,7 +115,7 @@ inline int linreg_meansq(b200reg_ctx* ctx, const float* F, const b200reg_geom& g
     linreg_final_kernel<<<1, 32, 0, ctx->stream>>>(part.as<double>(), nb, out.as<double>());
     ctx->launches += 2;
     B200_CHECK_LAUNCH();
-    B200_CUDA(cudaMemcpyAsync(ctx->h_scratch, out.p, sizeof(double) * LINREG_NV, cudaMemcpyDeviceToHost, ctx->stream));
+    B200_CUDA(small_d2h(ctx, ctx->h_scratch, out.p, sizeof(double) * LINREG_NV));
     B200_CUDA(cudaStreamSynchronize(ctx->stream));
     for (int v = 0; v < LINREG_NV; ++v) h_out[v] = ctx->h_scratch[v];
     return B200REG_OK;
