@@ -574,3 +574,22 @@ def binary_morphological_closing(image, kernel_radius, structure):
     e = ndi.binary_erosion(d, structure=structure, border_value=0)
     e = e[r[2]:e.shape[0] - r[2], r[1]:e.shape[1] - r[1], r[0]:e.shape[2] - r[0]]
     return _like(e.astype(np.uint8), image)
+
+
+def exponentiate_field(velocity_field, number_of_iterations=None, maximum_number_of_iterations=20):
+    """Scaling and squaring as ExponentialDisplacementFieldImageFilter does it: u_0 = v / 2^N, u <- u + Resample(u, DisplacementFieldTransform(u))
+    N times; N automatic = smallest N with max|v| / 2^N <= half the smallest spacing (restates platipy_b200.registration.exponentiate_field)."""
+    v = velocity_field
+    if number_of_iterations is None:
+        max_norm = float(np.sqrt((v.array ** 2).sum(axis=-1)).max())
+        half_voxel = 0.5 * min(v.GetSpacing())
+        n = 0
+        while max_norm / (2.0 ** n) > half_voxel and n < int(maximum_number_of_iterations):
+            n += 1
+    else:
+        n = int(number_of_iterations)
+    u = _like(v.array / (2.0 ** n) if n > 0 else v.array.copy(), v, True)
+    for _ in range(n):
+        warped = resample(u, u, sk.DisplacementFieldTransform(u))
+        u = _like(u.array + warped.array, u, True)
+    return u

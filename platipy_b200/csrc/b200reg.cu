@@ -480,10 +480,12 @@ API int b200reg_multiscale_demons(b200reg_ctx* ctx, const float* d_fixed, const 
     B200_TRY(check_demons_params(&cfg->demons));
     const int L = cfg->n_levels;
     const b200reg_geom gF = *fixed_geom, gM = *moving_geom;
+    B200_NVTX("b200reg_multiscale_demons");
 
     // deformable.py:67-94: both pyramids, all levels, from the ORIGINAL images
     std::vector<b200reg_geom> gfl(L), gml(L);
     std::vector<TempBuf> Fl(L), Ml(L);
+    B200NvtxRange r_pyramid("pyramid (smooth_and_resample, all levels)");
     for (int l = 0; l < L; ++l) {
         const double res = cfg->resolution_staging[l];
         // utils.py:249-250: neither factor given -> image returned unchanged
@@ -518,6 +520,7 @@ API int b200reg_multiscale_demons(b200reg_ctx* ctx, const float* d_fixed, const 
         }
     }
 
+    r_pyramid.end();
     // deformable.py:99-130: initial field on the fixed grid (zeros, or the given field re-gridded twice)
     const size_t nF = nvox(gF);
     TempBuf total, next;
@@ -546,6 +549,10 @@ API int b200reg_multiscale_demons(b200reg_ctx* ctx, const float* d_fixed, const 
         const b200reg_geom& gl = gfl[l];
         const size_t nl = nvox(gl);
         auto step = [&]() -> int {
+            char lname[64];
+            snprintf(lname, sizeof(lname), "level %d (%d x %d x %d)", l, gl.size[0], gl.size[1], gl.size[2]);
+            B200_NVTX(lname);
+            B200NvtxRange r_regrid("regrid total + warp moving");
             // :137 dvf_total -> level grid
             B200_TRY(next.alloc(ctx, 3 * nl * sizeof(double)));
             B200_TRY(resample_vec3(ctx, total.as<double>(), g_total, next.as<double>(), gl, nullptr, 0, 0.0));
@@ -568,9 +575,13 @@ API int b200reg_multiscale_demons(b200reg_ctx* ctx, const float* d_fixed, const 
             TempBuf iter;
             B200_TRY(iter.alloc(ctx, 3 * nl * sizeof(double)));
             B200_TRY(demons_prepare(ctx, gl, p.number_of_iterations, &wss[l], true));
+            r_regrid.end();
+            B200NvtxRange r_loop("Demons iterations");
             B200_CUDA(cudaEventRecord(ev[2 * l], ctx->stream));
             B200_TRY(demons_enqueue(ctx, Fl[l].as<float>(), gl, mw.as<float>(), gml[l], p, iter.as<double>(), &wss[l]));
             B200_CUDA(cudaEventRecord(ev[2 * l + 1], ctx->stream));
+            r_loop.end();
+            B200_NVTX("compose + recursive Gaussian");
             // :154 dvf_total + Resample(dvf_iter, tfm_total)
             B200_TRY(next.alloc(ctx, 3 * nl * sizeof(double)));
             B200_TRY(resample_vec3(ctx, iter.as<double>(), gl, next.as<double>(), gl, &tfm, 1, 0.0, total.as<double>()));

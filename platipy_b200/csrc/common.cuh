@@ -14,7 +14,27 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>  // header-only NVTX 3: ranges cost nothing unless a profiler injects its library
+
 #include "../../include/b200reg.h"
+
+// NVTX range for the enclosing scope (Nsight Systems / ncu --nvtx show the pyramid, each level's Demons loop, the glue and the
+// fusion stages by name)
+struct B200NvtxRange {
+    bool open = true;
+    explicit B200NvtxRange(const char* name) { nvtxRangePushA(name); }
+    void end()
+    {
+        if (open) nvtxRangePop();
+        open = false;
+    }
+    ~B200NvtxRange() { end(); }
+    B200NvtxRange(const B200NvtxRange&) = delete;
+    B200NvtxRange& operator=(const B200NvtxRange&) = delete;
+};
+#define B200_NVTX_CAT2(a, b) a##b
+#define B200_NVTX_CAT(a, b) B200_NVTX_CAT2(a, b)
+#define B200_NVTX(name) B200NvtxRange B200_NVTX_CAT(_nvtx_range_, __LINE__)(name)
 
 namespace b200 {
 

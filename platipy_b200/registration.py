@@ -499,3 +499,41 @@ def fast_symmetric_forces_demons_registration(fixed_image, moving_image, resolut
     return submit_registration(fixed_image, moving_image, resolution_staging, iteration_staging, isotropic_resample, initial_displacement_field,
                                regularisation_kernel_mm, smoothing_sigma_factor, smoothing_sigmas, default_value, ncores, interp_order,
                                verbose).result()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# field exponentiation (scaling and squaring)
+# ---------------------------------------------------------------------------------------------------------
+def exponentiate_field(velocity_field, number_of_iterations=None, maximum_number_of_iterations=20):
+    """exp(v) of a stationary velocity field by scaling and squaring, the scheme of ITK's ExponentialDisplacementFieldImageFilter:
+    with N squarings, u_0 = v / 2^N and u_{k+1}(x) = u_k(x) + u_k(x + u_k(x)) (linear interpolation, identity outside the grid).
+    ``number_of_iterations=None`` picks N like the filter's automatic mode: the smallest N >= 0 with max|v| / 2^N <= half the
+    smallest voxel spacing, capped at ``maximum_number_of_iterations``.
+
+    The reference path itself never exponentiates: FastSymmetricForcesDemons is the additive ESM scheme and platipy only *composes*
+    level fields (deformable.py:154).  This is the optional diffeomorphic-update building block BASELINE.json's
+    north star names, built from the same composition kernel; it is not on any parity path."""
+    import torch  # plumbing: one max-norm reduction to choose N
+
+    eng = Engine.get()
+    v = eng.to_device(velocity_field)
+    if not v.is_vector:
+        raise RuntimeError("exponentiate_field expects a sitkVectorFloat64 field")
+    if number_of_iterations is None:
+        with torch.cuda.stream(eng.stream):
+            max_norm = float(torch.sqrt((v.tensor * v.tensor).sum(dim=0)).max().item())
+        half_voxel = 0.5 * min(v.GetSpacing())
+        n = 0
+        while max_norm / (2.0 ** n) > half_voxel and n < int(maximum_number_of_iterations):
+            n += 1
+    else:
+        n = int(number_of_iterations)
+    if n > 0:
+        u = eng.divide_scalar(v, 2.0 ** n)
+    else:
+        with torch.cuda.stream(eng.stream):
+            u = v.like(v.tensor.clone())
+    for _ in range(n):
+        eng.compose_dvf(u, u)  # u <- u + Resample(u, DisplacementFieldTransform(u)): one resample_vec3 with the accumulate form
+    return _back(eng, u, velocity_field)
+
