@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import ctypes as C
 import threading
+import weakref
 
 import numpy as np
 import torch
@@ -132,6 +133,33 @@ def pinned_empty(shape, dtype):
     return a
 
 
+class _PinnedPool:
+    """Pinned host buffers of the asynchronous downloads, recycled.  ``cudaHostAlloc`` of a 1.6 GB field buffer takes about a second
+    (longer when eight ranks pin memory at once), so a buffer goes back to this pool -- not to the allocator -- when the numpy array
+    that was handed to the caller, and every view of it, has been garbage collected (a ``weakref.finalize`` on the base array)."""
+
+    MAX_PER_KEY = 4
+
+    def __init__(self):
+        self.free = {}
+        self.lock = threading.Lock()
+
+    def take(self, shape, torch_dtype):
+        key = (tuple(int(v) for v in shape), torch_dtype)
+        with self.lock:
+            lst = self.free.get(key)
+            if lst:
+                return lst.pop()
+        return torch.empty(key[0], dtype=torch_dtype, pin_memory=True)
+
+    def give(self, tensor):
+        key = (tuple(tensor.shape), tensor.dtype)
+        with self.lock:
+            lst = self.free.setdefault(key, [])
+            if len(lst) < self.MAX_PER_KEY:
+                lst.append(tensor)
+
+
 def pinned_image(image):
     """Copy of ``image`` whose pixel buffer lives in pinned host memory (fast H2D)."""
     image = sk.to_native(image)
@@ -170,6 +198,7 @@ class Engine:
             # beside the compute stream instead of in front of / behind it
             self.copy_in = torch.cuda.Stream(device=self.device)
             self.copy_out = torch.cuda.Stream(device=self.device)
+        self._pinned = _PinnedPool()
         ctx = C.c_void_p()
         _abi.check(self.lib.b200reg_create(device, C.c_void_p(self.stream.cuda_stream), C.byref(ctx)))
         self.ctx = ctx
@@ -245,10 +274,10 @@ class Engine:
             src, shape = aos, (z, y, x, 3)
         else:
             src, shape = dimg.tensor, (z, y, x)
-        pinned = torch.empty(tuple(int(v) for v in shape), dtype=_DT[dimg.np_dtype][1], pin_memory=True)
-        host = pinned.numpy()
-        if dimg.np_dtype in _SIGNED_VIEW:
-            host = host.view(dimg.np_dtype)
+        pinned = self._pinned.take(shape, _DT[dimg.np_dtype][1])
+        base = pinned.numpy()  # every view the caller can make keeps this array alive; when it dies the buffer is recycled
+        weakref.finalize(base, self._pinned.give, pinned)
+        host = base.view(dimg.np_dtype) if dimg.np_dtype in _SIGNED_VIEW else base
         self.copy_out.wait_stream(self.stream)
         src.record_stream(self.copy_out)
         with torch.cuda.stream(self.copy_out):

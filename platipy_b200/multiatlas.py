@@ -150,12 +150,20 @@ def exchange_sum(tensors, group=None):
     return tensors
 
 
-def _bytes_view(t):
-    """Decision masks travel as bytes: ranks set disjoint bits, so a byte-wise SUM never carries and equals the OR whatever the
-    mask width (NCCL has no 16-bit integer type)."""
+def _lane_views(stack, out):
+    """Integer payloads travel in the widest integer type their size allows.  Decision masks: ranks set disjoint bits, so a SUM never
+    carries and equals the OR whatever the lane width (NCCL has no 16-bit integer type anyway).  Vote counts: every byte stays
+    <= 255 over all ranks (at most 255 atlases, labels in {0, 1}), so byte lanes never carry into their neighbours either -- summing
+    eight of them as one int64 gives the same bytes with an eighth of the elements.  Returns flat views of ``stack`` and ``out``
+    (``out`` is one rank's equal share of ``stack``, or ``stack`` itself) in the common lane type."""
     import torch
 
-    return t if t.dtype in (torch.uint8, torch.float32) else t.view(torch.uint8)
+    if stack.dtype == torch.float32:
+        return stack, out
+    a, b = stack.reshape(-1).view(torch.uint8), out.reshape(-1).view(torch.uint8)
+    if b.numel() % 8 == 0 and a.data_ptr() % 8 == 0 and b.data_ptr() % 8 == 0:
+        return a.view(torch.int64), b.view(torch.int64)
+    return a, b
 
 
 def exchange_reduce_scatter(stack, group=None):
@@ -171,9 +179,11 @@ def exchange_reduce_scatter(stack, group=None):
     per = stack.shape[0] // world
     if dist.get_backend(group) == "nccl":
         out = torch.empty((per,) + tuple(stack.shape[1:]), dtype=stack.dtype, device=stack.device)
-        dist.reduce_scatter_tensor(_bytes_view(out), _bytes_view(stack), op=dist.ReduceOp.SUM, group=group)
+        vin, vout = _lane_views(stack, out)
+        dist.reduce_scatter_tensor(vout, vin, op=dist.ReduceOp.SUM, group=group)
         return out
-    dist.all_reduce(_bytes_view(stack), op=dist.ReduceOp.SUM, group=group)
+    vin, _ = _lane_views(stack, stack)
+    dist.all_reduce(vin, op=dist.ReduceOp.SUM, group=group)  # gloo (CPU tests): no reduce-scatter
     return stack[rank * per:(rank + 1) * per]
 
 
