@@ -89,6 +89,9 @@ typedef struct {
     double max_update_step_length;        /* 0.5 */
     double intensity_difference_threshold; /* 0.001 */
     double denominator_threshold;          /* 1e-9 */
+    int32_t field_precision;      /* 0: Float64 fields like ITK's (parity mode, the default); 1: fast mode -- float32 fields, float32 FMA
+                                   * smoothing, NOT bit-comparable with the reference; levels it cannot run stay in parity mode */
+    int32_t reserved;
 } b200reg_demons_params;
 
 typedef struct {

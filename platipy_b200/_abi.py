@@ -37,7 +37,8 @@ class DemonsParams(C.Structure):
                 ("smooth_displacement_field", C.c_int32), ("smooth_update_field", C.c_int32),
                 ("max_error", C.c_double), ("max_kernel_width", C.c_int32), ("number_of_iterations", C.c_int32),
                 ("max_rms_error", C.c_double), ("max_update_step_length", C.c_double),
-                ("intensity_difference_threshold", C.c_double), ("denominator_threshold", C.c_double)]
+                ("intensity_difference_threshold", C.c_double), ("denominator_threshold", C.c_double),
+                ("field_precision", C.c_int32), ("reserved", C.c_int32)]
 
 
 class DemonsStats(C.Structure):

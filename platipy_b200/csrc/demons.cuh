@@ -12,6 +12,7 @@
 #pragma once
 #include "common.cuh"
 #include "gauss.cuh"
+#include "gauss_fast.cuh"
 #include "resample.cuh"
 #include "demons_split.cuh"
 
@@ -240,6 +241,7 @@ __global__ void demons_ctrl_init_kernel(DemonsCtrl* ctrl, int n_iters)
 
 struct DemonsWorkspace {
     TempBuf U, T1, T2, P1, W, partials, ctrl, trace;
+    TempBuf fP0, fP1, fU, fT1;  // fast mode: float32 fields
     size_t nblocks = 0;
 };
 
@@ -345,6 +347,63 @@ inline int make_pde_coeffs(const double sd[3], double max_error, int max_width, 
     return B200REG_OK;
 }
 
+// ---- fast mode (float32 fields, 92 algorithmic B/voxel/iteration) ------------------------------------------------------
+// Same loop, same kernels for warp / force / finish (double arithmetic per voxel, float32 storage of D and U), float32 FMA smoothing
+// (gauss_fast.cuh).  NOT a parity path -- selected explicitly (b200reg_demons_params::field_precision = 1) and reported with its
+// error against the parity path; whatever a level cannot run this way (radii, row length, size) runs in parity mode.
+__global__ void select_cast_kernel(const float* __restrict__ p0, const float* __restrict__ p1, double* __restrict__ out, size_t n,
+                                   const DemonsCtrl* __restrict__ ctrl)
+{
+    const float* __restrict__ src = (ctrl->elapsed & 1) ? p1 : p0;
+    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) out[q] = (double)src[q];
+}
+inline bool demons_fast_possible(b200reg_ctx* ctx, const b200reg_geom& gF, const b200reg_geom& gM, const b200reg_demons_params& p, KernelCoeffs kd[3],
+                                 KernelCoeffs ku[3])
+{
+    if (!p.smooth_displacement_field || !p.smooth_update_field) return false;
+    if (make_pde_coeffs(p.std_dev, p.max_error, p.max_kernel_width, kd) != B200REG_OK) return false;
+    if (make_pde_coeffs(p.update_std_dev, p.max_error, p.max_kernel_width, ku) != B200REG_OK) return false;
+    const size_t nf = nvox(gF), nm = nvox(gM);
+    (void)ctx;
+    return zmarch_fast_supported(kd, gF.size[0]) && zmarch_fast_supported(ku, gF.size[0]) && nf * 3 < (1ull << 31) && nm < (1ull << 31);
+}
+inline int demons_enqueue_fast(b200reg_ctx* ctx, const float* F, const b200reg_geom& gF, const float* M, const b200reg_geom& gM,
+                               const b200reg_demons_params& p, const KernelCoeffs kd[3], const KernelCoeffs ku[3], double* D, DemonsWorkspace* ws)
+{
+    const int nx = gF.size[0], ny = gF.size[1], nz = gF.size[2];
+    const size_t n = nvox(gF);
+    const GeomD gf = make_geomd(gF), gm = make_geomd(gM);
+    const ForceParams fp = make_force_params(gF, p);
+    const int n_iters = p.number_of_iterations;
+    B200_TRY(ws->fP0.alloc(ctx, 3 * n * sizeof(float)));
+    B200_TRY(ws->fP1.alloc(ctx, 3 * n * sizeof(float)));
+    B200_TRY(ws->fU.alloc(ctx, 3 * n * sizeof(float)));
+    B200_TRY(ws->fT1.alloc(ctx, 3 * n * sizeof(float)));
+    float* P[2] = { ws->fP0.as<float>(), ws->fP1.as<float>() };
+    float* U = ws->fU.as<float>();
+    float* T1 = ws->fT1.as<float>();
+    B200_CUDA(cudaMemsetAsync(P[0], 0, 3 * n * sizeof(float), ctx->stream));
+    DemonsCtrl* ctrl = ws->ctrl.as<DemonsCtrl>();
+    demons_ctrl_init_kernel<<<1, 1, 0, ctx->stream>>>(ctrl, n_iters);
+    ctx->launches++;
+    const bool diag = geom_is_diag(gf) && geom_is_diag(gm);
+    for (int it = 0; it < n_iters; ++it) {
+        float* cur = P[it & 1];
+        float* nxt = P[(it + 1) & 1];
+        size_t nblocks;
+        B200_TRY(launch_update_split<float>(ctx, F, gf, M, gm, cur, ws->W.as<float>(), U, ws->partials.as<double>(), fp, diag, ctrl, it, &nblocks));
+        B200_CUDA(launch_pdl(ctx, demons_finish_kernel, dim3(1), dim3(1024), 0, ws->partials.as<double>(), nblocks, ctrl, fp.max_rms_error, it, n_iters,
+                             ws->trace.as<double>()));
+        ctx->launches += 1;
+        B200_TRY(launch_conv3d_zmarch_fast(ctx, U, cur, T1, nx, ny, nz, 3, ku, ctrl, it));      // T1 = D + G_u * U
+        B200_TRY(launch_conv3d_zmarch_fast(ctx, T1, nullptr, nxt, nx, ny, nz, 3, kd, ctrl, it));  // D' = G_d * T1
+    }
+    select_cast_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(P[0], P[1], D, 3 * n, ctrl);
+    ctx->launches++;
+    B200_CHECK_LAUNCH();
+    return B200REG_OK;
+}
+
 // registration_algorithm.Execute(f_image, m_image): zero initial field, FiniteDifferenceImageFilter loop.
 // Everything is enqueued on the stream; stats are read back by the caller after synchronising.
 // Per iteration: CalculateChange (P[it%2] -> U), SmoothUpdateField (U -> T1), Add + SmoothDisplacementField
@@ -358,6 +417,7 @@ inline int demons_enqueue(b200reg_ctx* ctx, const float* F, const b200reg_geom& 
     const ForceParams fp = make_force_params(gF, p);
     const int n_iters = p.number_of_iterations;
     KernelCoeffs kd[3], ku[3];
+    if (p.field_precision == 1 && demons_fast_possible(ctx, gF, gM, p, kd, ku)) return demons_enqueue_fast(ctx, F, gF, M, gM, p, kd, ku, D, ws);
     if (p.smooth_displacement_field) B200_TRY(make_pde_coeffs(p.std_dev, p.max_error, p.max_kernel_width, kd));
     if (p.smooth_update_field) B200_TRY(make_pde_coeffs(p.update_std_dev, p.max_error, p.max_kernel_width, ku));
     B200_CUDA(cudaMemsetAsync(D, 0, 3 * n * sizeof(double), ctx->stream));

@@ -27,6 +27,10 @@ logger = logging.getLogger(__name__)
 
 sitkNearestNeighbor, sitkLinear, sitkBSpline = sk.sitkNearestNeighbor, sk.sitkLinear, sk.sitkBSpline
 
+# "parity" (Float64 fields, the reference's arithmetic) or "fast" (float32 fields inside the Demons loop); every registration entry
+# point also takes ``precision=`` for one call
+DEFAULT_PRECISION = "parity"
+
 # per-level statistics of the most recent multiscale_demons call (elapsed iterations, metric, RMS change, device ms)
 LAST_LEVEL_STATS = []
 
@@ -198,6 +202,7 @@ class FastSymmetricForcesDemonsRegistrationFilter:
         self._max_kw = 30
         self._max_err = 0.1
         self._idt = 0.001
+        self._precision = 0
         self._commands = []
         self._stats = {"elapsed_iterations": 0, "metric": 0.0, "rms_change": 0.0}
 
@@ -245,6 +250,14 @@ class FastSymmetricForcesDemonsRegistrationFilter:
     def SetIntensityDifferenceThreshold(self, v):
         self._idt = float(v)
 
+    def SetFieldPrecision(self, precision):
+        """``"parity"`` (default): Float64 fields like ITK's, results comparable bit for bit with the CPU oracle.  ``"fast"``: float32
+        fields and float32 FMA smoothing inside the Demons loop -- about half the HBM traffic per iteration, NOT a parity
+        path: expect differences of 1e-5 .. 1e-3 mm against the parity result (``bench.py`` reports the percentiles)."""
+        if precision not in ("parity", "fast"):
+            raise ValueError("precision must be 'parity' or 'fast'")
+        self._precision = 1 if precision == "fast" else 0
+
     def AddCommand(self, event, callback):
         """Callbacks registered for sitkIterationEvent (or sitkAnyEvent) run once per Demons iteration; see _fire_iteration_events."""
         if event in (sk.sitkIterationEvent, sk.sitkAnyEvent):
@@ -273,6 +286,7 @@ class FastSymmetricForcesDemonsRegistrationFilter:
         p.max_update_step_length = self._max_step
         p.intensity_difference_threshold = self._idt
         p.denominator_threshold = 1e-9
+        p.field_precision = self._precision
         return p
 
     def Execute(self, fixed_image, moving_image):
@@ -346,7 +360,7 @@ def multiscale_demons(registration_algorithm, fixed_image, moving_image, initial
 
 def _register_on_device(eng, f0, m0, resolution_staging, iteration_staging, isotropic_resample, initial_displacement_field,
                         regularisation_kernel_mm, smoothing_sigma_factor, smoothing_sigmas, default_value, ncores, interp_order, verbose,
-                        on_field_ready=None):
+                        on_field_ready=None, precision=None):
     """Device part of fast_symmetric_forces_demons_registration: ``DeviceImage`` inputs -> ``(registered, transform, field)`` on the
     device.  ``on_field_ready(dvf)`` is called as soon as the field is final, before the last warp is enqueued (the host API starts
     the field's PCIe copy there, so that it overlaps the warp)."""
@@ -362,6 +376,7 @@ def _register_on_device(eng, f0, m0, resolution_staging, iteration_staging, isot
     reg.SetNumberOfThreads(ncores)
     reg.SetSmoothUpdateField(True)
     reg.SetSmoothDisplacementField(True)
+    reg.SetFieldPrecision(precision or DEFAULT_PRECISION)
     # deformable.py:253-257: voxel-unit sigmas from the full-resolution spacing, reused at every level
     reg.SetStandardDeviations((np.array(regularisation_kernel_mm) / np.array(f.GetSpacing())).tolist())
 
@@ -416,7 +431,7 @@ class PendingRegistration:
 
 def submit_registration(fixed_image, moving_image, resolution_staging=[8, 4, 1], iteration_staging=[10, 10, 10], isotropic_resample=False,
                         initial_displacement_field=None, regularisation_kernel_mm=1.5, smoothing_sigma_factor=1, smoothing_sigmas=False,
-                        default_value=None, ncores=1, interp_order=sitkLinear, verbose=False, _uploaded=None):
+                        default_value=None, ncores=1, interp_order=sitkLinear, verbose=False, _uploaded=None, precision=None):
     """``fast_symmetric_forces_demons_registration`` for host images whose results are not needed at once: the inputs go up on the
     copy-in stream, the registration runs, and the 1.9 GB of results (VectorFloat64 field + registered image at 512 x 512 x 256) come
     down on the copy-out stream while the caller goes on -- typically to the next ``submit_registration``, whose uploads and
@@ -434,7 +449,7 @@ def submit_registration(fixed_image, moving_image, resolution_staging=[8, 4, 1],
 
     reg_img, tfm, dvf = _register_on_device(eng, f0, m0, resolution_staging, iteration_staging, isotropic_resample, initial_displacement_field,
                                             regularisation_kernel_mm, smoothing_sigma_factor, smoothing_sigmas, default_value, ncores, interp_order,
-                                            verbose, on_field_ready=start_field_copy)
+                                            verbose, on_field_ready=start_field_copy, precision=precision)
     image_host, image_event = eng.to_host_async(reg_img)
     field_host, field_event = started["field"]
     return PendingRegistration(fixed_image, moving_image, tfm, image_host, image_event, field_host, field_event, LAST_LEVEL_STATS[:])
@@ -471,8 +486,9 @@ def fast_symmetric_forces_demons_registration(fixed_image, moving_image, resolut
                                               iteration_staging=[10, 10, 10], isotropic_resample=False,
                                               initial_displacement_field=None, regularisation_kernel_mm=1.5,
                                               smoothing_sigma_factor=1, smoothing_sigmas=False, default_value=None,
-                                              ncores=1, interp_order=sitkLinear, verbose=False):
-    """Deformable image propagation using Fast Symmetric-Forces Demons (deformable.py:190-306).
+                                              ncores=1, interp_order=sitkLinear, verbose=False, precision=None):
+    """Deformable image propagation using Fast Symmetric-Forces Demons (deformable.py:190-306).  ``precision`` is this package's one
+    extra (keyword) argument: ``"parity"`` (default) or ``"fast"``, see ``FastSymmetricForcesDemonsRegistrationFilter.SetFieldPrecision``.
 
     Returns ``(registered_image, DisplacementFieldTransform, displacement_field)``.  For ``DeviceImage``
     inputs the three results stay on the device (the transform object then wraps the device field).  Host inputs give host
@@ -483,7 +499,7 @@ def fast_symmetric_forces_demons_registration(fixed_image, moving_image, resolut
         f0, m0 = eng.to_device(fixed_image), eng.to_device(moving_image)
         reg_img, tfm, dvf = _register_on_device(eng, f0, m0, resolution_staging, iteration_staging, isotropic_resample, initial_displacement_field,
                                                 regularisation_kernel_mm, smoothing_sigma_factor, smoothing_sigmas, default_value, ncores,
-                                                interp_order, verbose)
+                                                interp_order, verbose, precision=precision)
         tfm._field = dvf
         eng.release_to_caller()
         return reg_img, tfm, dvf
@@ -492,13 +508,13 @@ def fast_symmetric_forces_demons_registration(fixed_image, moving_image, resolut
         f0, m0 = eng.to_device(fixed_image), eng.to_device(moving_image)
         reg_img, tfm, dvf = _register_on_device(eng, f0, m0, resolution_staging, iteration_staging, isotropic_resample, initial_displacement_field,
                                                 regularisation_kernel_mm, smoothing_sigma_factor, smoothing_sigmas, default_value, ncores,
-                                                interp_order, verbose)
+                                                interp_order, verbose, precision=precision)
         dvf_host = eng.to_host(dvf)
         tfm._field = dvf_host
         return sk.from_native(eng.to_host(reg_img), moving_image), tfm, sk.from_native(dvf_host, fixed_image)
     return submit_registration(fixed_image, moving_image, resolution_staging, iteration_staging, isotropic_resample, initial_displacement_field,
                                regularisation_kernel_mm, smoothing_sigma_factor, smoothing_sigmas, default_value, ncores, interp_order,
-                               verbose).result()
+                               verbose, precision=precision).result()
 
 
 # ---------------------------------------------------------------------------------------------------------
