@@ -13,7 +13,9 @@ namespace b200 {
 
 template <int R, int TXW>
 struct ZmfLayout {
-    static constexpr int RP = (R + 1) & ~1;
+    // x halo padded to a multiple of FOUR floats: the TMA unit wants the box to start on a 16-byte boundary of the row (a box starting
+    // at x0 - 2 floats never completes its transaction -- found with compute-sanitizer: the mbarrier wait trapped)
+    static constexpr int RP = (R + 3) & ~3;
     static constexpr int AW = TXW + 2 * RP, AH = ZM_TY + 2 * R, NA = AW * AH;
     static constexpr int NAP = (NA + 31) & ~31;  // floats: every staged plane starts on a 128-byte boundary
     static constexpr int NB = AH * TXW;
