@@ -456,3 +456,28 @@ def test_exponentiate_field_matches_oracle(engine):
     fwd, bwd = reg.exponentiate_field(v), reg.exponentiate_field(Image(-v.array, sp, is_vector=True))
     comp = ref.resample(fwd, fwd, sk.DisplacementFieldTransform(bwd)).array + bwd.array
     assert np.abs(comp[4:-4, 4:-4, 4:-4]).max() < 0.05 * np.abs(v.array).max()
+
+
+def test_fast_mode_is_an_explicit_close_but_not_bit_equal_path(engine):
+    """precision="fast": float32 fields + float32 FMA smoothing inside the Demons loop.  Not a parity path -- it must be asked
+    for, the default stays bit-identical to the oracle, and what it returns stays close to the parity field (the thresholds of the ESM
+    force amplify float32 rounding here and there, so the bar is statistical: median and 99th percentile)."""
+    fixed, moving = synth_pair((64, 48, 40), seed=17, spacing=(1.0, 1.0, 1.5), peak_mm=3.0)
+    kw = dict(resolution_staging=[2, 1], iteration_staging=[12, 8])
+    _, _, d_par = reg.fast_symmetric_forces_demons_registration(fixed, moving, **kw)
+    st_par = [s["elapsed_iterations"] for s in reg.LAST_LEVEL_STATS]
+    _, _, d_fast = reg.fast_symmetric_forces_demons_registration(fixed, moving, precision="fast", **kw)
+    st_fast = [s["elapsed_iterations"] for s in reg.LAST_LEVEL_STATS]
+    _, _, d_par2 = reg.fast_symmetric_forces_demons_registration(fixed, moving, precision="parity", **kw)
+    assert np.array_equal(d_par.array, d_par2.array) and np.array_equal(d_par.array, ref.fast_symmetric_forces_demons_registration(fixed, moving, **kw)[2].array)
+    assert st_par == st_fast == [12, 8]
+    err = np.abs(d_fast.array - d_par.array)
+    assert err.max() > 0.0, "fast mode returned the parity bits: the switch did not act"
+    assert np.median(err) < 1e-3 and np.percentile(err, 99) < 0.1 and err.max() < 1.0, (np.median(err), np.percentile(err, 99), err.max())
+    # a row length the TMA unit cannot take in float32 (not a multiple of 4) silently stays in parity mode
+    f2, m2 = synth_pair((46, 40, 24), seed=18, spacing=(1.0, 1.0, 1.5), peak_mm=2.0)
+    a = reg.fast_symmetric_forces_demons_registration(f2, m2, precision="fast", resolution_staging=[1], iteration_staging=[4])[2]
+    b = reg.fast_symmetric_forces_demons_registration(f2, m2, resolution_staging=[1], iteration_staging=[4])[2]
+    assert np.array_equal(a.array, b.array)
+    with pytest.raises(ValueError):
+        reg.fast_symmetric_forces_demons_registration(fixed, moving, precision="sloppy", **kw)
