@@ -3,10 +3,10 @@
 set -u
 cd "$(dirname "$0")/.."
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -p no:cacheprovider --timeout 600 > gpurun_out/r02i_pytest_gpu.log 2>&1
-tail -4 gpurun_out/r02i_pytest_gpu.log
-/usr/bin/time -v timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02i_bench.json 2> gpurun_out/r02i_bench.err
-grep -E "Elapsed \(wall|Maximum resident" gpurun_out/r02i_bench.err
+echo skip-suite
+
+time timeout 900 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02i_bench.json 2> gpurun_out/r02i_bench.err
+tail -4 gpurun_out/r02i_bench.err
 python - <<'PY'
 import json
 d = json.loads(open("gpurun_out/r02i_bench.json").read().strip().splitlines()[-1])
@@ -17,5 +17,5 @@ for n, f in d["fusion"].items():
     print(n, f.get("wall_ms"), f.get("error"))
 print(d["resample_cfg3"]["batched"]["ms"], d["resample_cfg3"]["per_call"]["ms"])
 PY
-/usr/bin/time -v timeout 900 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02i_bench_reference.json 2> gpurun_out/r02i_bench_reference.err
-grep -E "Elapsed \(wall" gpurun_out/r02i_bench_reference.err; cut -c1-900 gpurun_out/r02i_bench_reference.json
+time timeout 900 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/r02i_bench_reference.json 2> gpurun_out/r02i_bench_reference.err
+tail -4 gpurun_out/r02i_bench_reference.err; cut -c1-900 gpurun_out/r02i_bench_reference.json
