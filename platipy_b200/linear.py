@@ -352,20 +352,33 @@ def centered_transform_initializer(fixed, moving):
 # ---------------------------------------------------------------------------------------------------------------------
 # optimiser pieces (itk::RegistrationParameterScalesFromPhysicalShift, itk::GradientDescentOptimizerv4)
 # ---------------------------------------------------------------------------------------------------------------------
-def _max_shift(model, p, delta, corners):
-    q = model.updated(p, delta)
-    a0, b0 = model.matrix(p), model.offset(p)
-    a1, b1 = model.matrix(q), model.offset(q)
-    d = (corners @ a1.T + b1) - (corners @ a0.T + b0)
+def _affine_of(model, p):
+    """(matrix, offset) of the model at ``p`` with one evaluation of the matrix (``model.offset`` evaluates it again)."""
+    a = model.matrix(p)
+    c = model.center
+    return a, model.translation(p) + c - a @ c
+
+
+def _max_shift(model, p, delta, corners, base=None):
+    """Largest displacement of the image corners when the parameters move from ``p`` by ``delta``; ``base`` = the corners mapped at
+    ``p`` (``corners @ A(p).T + b(p)``), passed in by callers that probe several deltas from one ``p``."""
+    if base is None:
+        a0, b0 = _affine_of(model, p)
+        base = corners @ a0.T + b0
+    a1, b1 = _affine_of(model, model.updated(p, delta))
+    d = (corners @ a1.T + b1) - base
     return float(np.sqrt((d * d).sum(axis=1)).max())
 
 
 def estimate_scales(model, p, corners):
+    a0, b0 = _affine_of(model, p)
+    base = corners @ a0.T + b0
     scales = np.zeros(model.n)
+    delta = np.zeros(model.n)
     for k in range(model.n):
-        delta = np.zeros(model.n)
         delta[k] = SMALL_PARAMETER_VARIATION
-        scales[k] = _max_shift(model, p, delta, corners) ** 2
+        scales[k] = _max_shift(model, p, delta, corners, base) ** 2
+        delta[k] = 0.0
     nz = scales[scales > np.finfo(float).eps]
     floor = nz.min() if nz.size else 1.0
     scales[scales <= np.finfo(float).eps] = floor
@@ -382,15 +395,17 @@ def estimate_step_scale(model, p, step, corners):
 
 def convergence_value(energies):
     """itk::Function::WindowConvergenceMonitoringFunction: minus the slope of a straight-line fit to the window's
-    energies, normalised by their total magnitude."""
+    energies, normalised by their total magnitude (closed-form least squares on t = 0 .. 1)."""
     e = np.asarray(energies, dtype=np.float64)
     total = np.abs(e).sum()
     if total == 0.0:
         return 0.0
-    y = e / total * len(e)
-    t = np.linspace(0.0, 1.0, len(e))
-    slope = np.polyfit(t, y, 1)[0]
-    return float(-slope)
+    n = len(e)
+    y = e / total * n
+    t = np.arange(n, dtype=np.float64) / max(n - 1, 1)
+    tc = t - t.mean()
+    slope = float((tc * (y - y.mean())).sum() / (tc * tc).sum()) if n > 1 else 0.0
+    return -slope
 
 
 def golden_section(phi, a, b, c, epsilon=0.01, max_iterations=20):
