@@ -113,6 +113,10 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, 6) conv3d_zmf_kerne
     const int gx = x0 + ox;
     float ring[NR][4];
     const int zbeg = z0 - RZ, nsteps = (z1 - z0) + 2 * RZ;
+    size_t out_off = (size_t)z0 * plane + (size_t)(y0 + 4 * yb) * nx + gx;  // running offset of this thread's outputs
+    bool okj[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) okj[j] = gx < nx && y0 + 4 * yb + j < ny;
     stage(zbeg, 0);
     for (int q0 = 0; q0 < nsteps; q0 += NR) {
 #pragma unroll
@@ -122,12 +126,9 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, 6) conv3d_zmf_kerne
                 const int buf = q & 1;
                 float addv[4] = { 0.f, 0.f, 0.f, 0.f };
                 if (MODE == 3 && tid < NYZ && q >= 2 * RZ) {
-                    const int zo = zbeg + q - RZ;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const int gy = y0 + 4 * yb + j;
-                        if (gx < nx && gy < ny) addv[j] = bp[(size_t)zo * plane + (size_t)gy * nx + gx];
-                    }
+                    for (int j = 0; j < 4; ++j)
+                        if (okj[j]) addv[j] = bp[out_off + (size_t)(j * nx)];
                 }
                 mbar_wait(&full_bar[buf], (unsigned)((q >> 1) & 1));
                 if (border) {
@@ -179,15 +180,14 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, 6) conv3d_zmf_kerne
                 }
                 // ---- z pass over the ring
                 if (tid < NYZ && q >= 2 * RZ) {
-                    const int zo = zbeg + q - RZ;
 #pragma unroll
                     for (int j = 0; j < 4; ++j) {
                         float sum = kz[0] * ring[(s + 1) % NR][j];
 #pragma unroll
                         for (int t = 1; t < NR; ++t) sum = __fmaf_rn(kz[t], ring[(s + 1 + t) % NR][j], sum);
-                        const int gy = y0 + 4 * yb + j;
-                        if (gx < nx && gy < ny) op[(size_t)zo * plane + (size_t)gy * nx + gx] = MODE == 3 ? addv[j] + sum : sum;
+                        if (okj[j]) op[out_off + (size_t)(j * nx)] = MODE == 3 ? addv[j] + sum : sum;
                     }
+                    out_off += plane;
                 }
             }
         }
