@@ -129,12 +129,13 @@ def _structure_params(size_xyz, n_structures, seed):
 
 
 def synth_atlas_case(size_xyz, n_structures, spacing=(1.0, 1.0, 1.5), seed=0, atlas_seed=None, peak_mm=6.0, n_blobs=24, noise_hu=5.0,
-                     structure_seed=200, as_tensors=False, max_shift_mm=10.0):
+                     structure_seed=200, as_tensors=False, max_shift_mm=10.0, similarity=True):
     """One member of a synthetic atlas cohort: the common anatomy of ``seed`` (the phantom of ``synth_pair``)
     and ``n_structures`` ellipsoid structures, seen through a random similarity (rotation <= 5 degrees about a random axis, scale
     0.95-1.05, shift <= ``max_shift_mm``, about the image centre, in physical space) followed by a smooth displacement (peak ``peak_mm``):
     image(x) = phantom(T(x) + u(T(x))), label_k(x) = ellipsoid_k(T(x) + u(T(x))).  ``atlas_seed=None`` gives the target itself
-    (identity transform, no displacement), whose labels are the ground truth of the fusion.  Returns ``(ct, [labels])`` as
+    (identity transform, no displacement), whose labels are the ground truth of the fusion; ``similarity=False`` leaves the
+    similarity out (atlases that are already on the target grid, i.e. the state after the linear step).  Returns ``(ct, [labels])`` as
     ``Image`` objects, or as torch tensors on the generating device with ``as_tensors`` (Float32 ``[z, y, x]`` and UInt8)."""
     nx, ny, nz = size_xyz
     dev = _dev()
@@ -158,6 +159,8 @@ def synth_atlas_case(size_xyz, n_structures, spacing=(1.0, 1.0, 1.5), seed=0, at
         R = np.eye(3) + np.sin(ang) * K + (1 - np.cos(ang)) * (K @ K)
         A = ra.uniform(0.95, 1.05) * R
         shift = ra.uniform(-1.0, 1.0, size=3) * float(max_shift_mm)
+        if not similarity:  # atlases already aligned with the target: only the smooth displacement remains
+            A, shift = np.eye(3), np.zeros(3)
         sp = np.asarray(spacing, dtype=np.float64)
         cen = 0.5 * (np.array(size_xyz) - 1) * sp
         # physical p = x * spacing; p' = A (p - c) + c + shift; back to voxel coordinates

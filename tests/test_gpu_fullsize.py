@@ -96,3 +96,38 @@ def test_cfg2_whole_registration_matches_oracle(engine, pair):
     assert err <= 1e-4
     gi = engine.to_host(img, pinned=False).array
     assert float(np.abs(gi - img_o.array).max()) <= 1e-5 * max(1.0, float(np.abs(img_o.array).max()))
+
+
+def test_cfg4_size_atlas_pipeline_matches_oracle(engine):
+    """BASELINE.json configs[3] at its size (256x256x160, spacing 1 x 1 x 1.5, 4 atlases x 5 structures, Demons [4, 2, 1] x [50, 50, 25],
+    unweighted vote): Demons -> batched (bit-packed) label propagation -> vote counts -> finalisation -> process_probability_image on the GPU
+    against the oracle pipeline run atlas by atlas on the host cores (about a minute).  The atlases are generated already aligned with
+    the target (the linear step has its own functional tests; its optimiser has no oracle).  Fused probabilities and masks: same bits."""
+    from oracle import platipy_ref as ref
+    from platipy_b200 import multiatlas
+    from platipy_b200.synth import synth_atlas_case
+
+    size, sp, n_struct = (256, 256, 160), (1.0, 1.0, 1.5), 5
+    target, _ = synth_atlas_case(size, n_struct, sp, seed=0, atlas_seed=None)
+    names = [f"S{k}" for k in range(n_struct)]
+    atlas_set = {}
+    for a in range(4):
+        ct, labs = synth_atlas_case(size, n_struct, sp, seed=0, atlas_seed=a, similarity=False)
+        atlas_set[f"{a:03d}"] = dict({"CT Image": ct}, **dict(zip(names, labs)))
+    dset = {"isotropic_resample": False, "resolution_staging": [4, 2, 1], "iteration_staging": [50, 50, 25], "smoothing_sigmas": [4, 2, 0],
+            "ncores": 32, "default_value": -1000, "verbose": False}
+    settings = {"deformable_registration_settings": dset,
+                "label_fusion_settings": {"vote_type": "unweighted", "vote_params": None, "optimal_threshold": {}, "fusion": "vote"}}
+    results, probs = multiatlas.run_segmentation(target, atlas_set, settings)
+    kw = {k: v for k, v in dset.items() if k not in ("ncores", "verbose")}
+    dirs = {}
+    for a in sorted(atlas_set):
+        _, tfm, _ = ref.fast_symmetric_forces_demons_registration(target, atlas_set[a]["CT Image"], **kw)
+        d = {n: ref.apply_transform(atlas_set[a][n], target, tfm, 0, sk.sitkNearestNeighbor) for n in names}
+        d["Weight Map"] = ref.compute_weight_map(target, target, "unweighted", None)
+        dirs[a] = {"DIR": d}
+    exp = ref.combine_labels(dirs, names)
+    for n in names:
+        assert np.array_equal(probs[n].array, exp[n].array), n
+        assert np.array_equal(results[n].array, ref.process_probability_image(exp[n], 0.5).array), n
+        assert results[n].array.sum() > 0
