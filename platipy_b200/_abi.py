@@ -12,7 +12,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.environ.get("B200REG_LIB") or os.path.join(_HERE, "libb200reg.so")  # B200REG_LIB: A/B testing of builds
+LIB_PATH = os.environ.get("PLATIPY_B200_LIB") or os.environ.get("B200REG_LIB") or os.path.join(_HERE, "libb200reg.so")  # A/B testing of builds
 
 MAX_TRANSFORMS = 4
 MAX_LEVELS = 8

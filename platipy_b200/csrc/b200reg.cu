@@ -25,6 +25,15 @@ using namespace b200;
     } while (0)
 
 namespace {
+// tuning / A-B switches: PLATIPY_B200_<NAME> (the name SURVEY.md section 5 gives the configuration knobs), or the older B200REG_<NAME>
+const char* knob(const char* name)
+{
+    char buf[96];
+    snprintf(buf, sizeof(buf), "PLATIPY_B200_%s", name);
+    if (const char* e = getenv(buf)) return e;
+    snprintf(buf, sizeof(buf), "B200REG_%s", name);
+    return getenv(buf);
+}
 struct DeviceGuard {
     int prev = -1;
     explicit DeviceGuard(int dev)
@@ -72,21 +81,21 @@ API int b200reg_create(int device, void* stream, b200reg_ctx** out)
     uint64_t thr = UINT64_MAX;
     B200_CUDA(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr));
     B200_CUDA(cudaMallocHost(&ctx->h_scratch, 64 * sizeof(double)));
-    if (const char* e = getenv("B200REG_FORCE_SEPARABLE")) ctx->force_separable = (e[0] == '1');
-    if (const char* e = getenv("B200REG_UNFUSED_FORCE")) ctx->unfused_force = (e[0] == '1');
-    if (const char* e = getenv("B200REG_STAPLE_VOXELWISE")) ctx->staple_voxelwise = (e[0] == '1');
-    if (const char* e = getenv("B200REG_ZM_TMA")) ctx->zm_tma = atoi(e);
-    if (const char* e = getenv("B200REG_ZM_TMA_L2")) ctx->zm_tma_l2 = atoi(e);
-    if (const char* e = getenv("B200REG_ZM_REGADD")) ctx->zm_regadd = (e[0] != '0');
-    if (const char* e = getenv("B200REG_PF_WARP")) ctx->pf_warp = atoi(e);
-    if (const char* e = getenv("B200REG_PF_FORCE")) ctx->pf_force = atoi(e);
-    if (const char* e = getenv("B200REG_WARP_MARCH")) ctx->warp_march = atoi(e);
-    if (const char* e = getenv("B200REG_ZM_CHUNKS")) ctx->zm_chunks = atoi(e);
-    if (const char* e = getenv("B200REG_ZM_TX32")) ctx->zm_tx32 = (e[0] != '0');
-    if (const char* e = getenv("B200REG_ZM_ADDOUT")) ctx->zm_addout = (e[0] != '0');
-    if (const char* e = getenv("B200REG_FORCE_ZM1")) ctx->force_zm1 = (e[0] == '1');
-    if (const char* e = getenv("B200REG_PACK_LABELS")) ctx->pack_labels = (e[0] != '0');
-    if (const char* e = getenv("B200REG_PDL")) ctx->pdl = (e[0] != '0');
+    if (const char* e = knob("FORCE_SEPARABLE")) ctx->force_separable = (e[0] == '1');
+    if (const char* e = knob("UNFUSED_FORCE")) ctx->unfused_force = (e[0] == '1');
+    if (const char* e = knob("STAPLE_VOXELWISE")) ctx->staple_voxelwise = (e[0] == '1');
+    if (const char* e = knob("ZM_TMA")) ctx->zm_tma = atoi(e);
+    if (const char* e = knob("ZM_TMA_L2")) ctx->zm_tma_l2 = atoi(e);
+    if (const char* e = knob("ZM_REGADD")) ctx->zm_regadd = (e[0] != '0');
+    if (const char* e = knob("PF_WARP")) ctx->pf_warp = atoi(e);
+    if (const char* e = knob("PF_FORCE")) ctx->pf_force = atoi(e);
+    if (const char* e = knob("WARP_MARCH")) ctx->warp_march = atoi(e);
+    if (const char* e = knob("ZM_CHUNKS")) ctx->zm_chunks = atoi(e);
+    if (const char* e = knob("ZM_TX32")) ctx->zm_tx32 = (e[0] != '0');
+    if (const char* e = knob("ZM_ADDOUT")) ctx->zm_addout = (e[0] != '0');
+    if (const char* e = knob("FORCE_ZM1")) ctx->force_zm1 = (e[0] == '1');
+    if (const char* e = knob("PACK_LABELS")) ctx->pack_labels = (e[0] != '0');
+    if (const char* e = knob("PDL")) ctx->pdl = (e[0] != '0');
     *out = ctx;
     return B200REG_OK;
 }
