@@ -789,6 +789,7 @@ __global__ void __launch_bounds__(256) conv_x_f32_tiled_kernel(const float* __re
     if (x >= nx) return;
     double sum = 0.0;
     const double* w = sm + threadIdx.x;
+#pragma unroll 5
     for (int t = 0; t <= 2 * r; ++t) sum += kc.k[t] * w[t];
     out[row + x] = (float)sum;
 }
@@ -814,15 +815,23 @@ __global__ void __launch_bounds__(256) conv_yz_f32_tiled_kernel(const float* __r
         sm[e * 32 + lane] = (double)in[base + (size_t)q * sa + xc];
     }
     __syncthreads();
+    // four consecutive outputs per thread over a sliding window of four staged values: per tap one shared load and one coefficient,
+    // four multiply-adds, no predicates (the earlier form tested every (value, output) pair); same ascending tap order per output
     double acc[4] = { 0.0, 0.0, 0.0, 0.0 };
     const double* col = sm + (ty * 4) * 32 + lane;
-    for (int i = 0; i < 4 + 2 * r; ++i) {
-        const double v = col[i * 32];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int t = i - j;
-            if (t >= 0 && t <= 2 * r) acc[j] += kc.k[t] * v;
-        }
+    double v0 = col[0], v1 = col[32], v2 = col[64], v3 = col[96];
+    const int last = 2 * r;
+#pragma unroll 4
+    for (int t = 0; t <= last; ++t) {
+        const double kt = kc.k[t];
+        acc[0] += kt * v0;
+        acc[1] += kt * v1;
+        acc[2] += kt * v2;
+        acc[3] += kt * v3;
+        v0 = v1;
+        v1 = v2;
+        v2 = v3;
+        if (t < last) v3 = col[(t + 4) * 32];
     }
     if (x < nx) {
 #pragma unroll
