@@ -333,11 +333,12 @@ __global__ void add_kernel(const double* __restrict__ a, const double* __restric
     if (ctrl && it >= ctrl->halt_iter) return;
     for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) out[q] = a[q] + b[q];
 }
-// The field ping-pongs between two buffers; after `elapsed` iterations it lives in buffer elapsed % 2.
-// Decided on the device: copy P1 -> P0 when the elapsed count is odd.
-__global__ void select_copy_kernel(const double* __restrict__ p1, double* __restrict__ p0, size_t n, const DemonsCtrl* __restrict__ ctrl)
+// The field ping-pongs between two buffers; starting in buffer `start` it lives in buffer (start + elapsed) % 2 after `elapsed`
+// iterations.  `start` is chosen so that a level that runs all its iterations ends in the caller's buffer P0; only an early halt
+// after an odd number of remaining iterations leaves it in P1, and then -- decided on the device -- it is copied.
+__global__ void select_copy_kernel(const double* __restrict__ p1, double* __restrict__ p0, size_t n, const DemonsCtrl* __restrict__ ctrl, int start)
 {
-    if ((ctrl->elapsed & 1) == 0) return;
+    if (((start + ctrl->elapsed) & 1) == 0) return;
     for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) p0[q] = p1[q];
 }
 
@@ -420,17 +421,18 @@ inline int demons_enqueue(b200reg_ctx* ctx, const float* F, const b200reg_geom& 
     if (p.field_precision == 1 && demons_fast_possible(ctx, gF, gM, p, kd, ku)) return demons_enqueue_fast(ctx, F, gF, M, gM, p, kd, ku, D, ws);
     if (p.smooth_displacement_field) B200_TRY(make_pde_coeffs(p.std_dev, p.max_error, p.max_kernel_width, kd));
     if (p.smooth_update_field) B200_TRY(make_pde_coeffs(p.update_std_dev, p.max_error, p.max_kernel_width, ku));
-    B200_CUDA(cudaMemsetAsync(D, 0, 3 * n * sizeof(double), ctx->stream));
+    double* P[2] = { D, ws->P1.as<double>() };
+    const int start = n_iters & 1;  // an odd number of iterations starts in P1 and ends in the caller's buffer
+    B200_CUDA(cudaMemsetAsync(P[start], 0, 3 * n * sizeof(double), ctx->stream));
     DemonsCtrl* ctrl = ws->ctrl.as<DemonsCtrl>();
     demons_ctrl_init_kernel<<<1, 1, 0, ctx->stream>>>(ctrl, n_iters);
     ctx->launches++;
     double* U = ws->U.as<double>();
     double* T1 = ws->T1.as<double>();
     double* T2 = ws->T2.as<double>();
-    double* P[2] = { D, ws->P1.as<double>() };
     for (int it = 0; it < n_iters; ++it) {
-        double* cur = P[it & 1];
-        double* nxt = P[(it + 1) & 1];
+        double* cur = P[(start + it) & 1];
+        double* nxt = P[(start + it + 1) & 1];
         B200_TRY(demons_calculate_change(ctx, F, gf, M, gm, cur, fp, ws, it, n_iters));
         const double* upd = U;
         if (p.smooth_update_field && p.smooth_displacement_field && !ctx->force_separable && ctx->zm_addout && zmarch2_supported(ctx, ku) &&
@@ -454,7 +456,7 @@ inline int demons_enqueue(b200reg_ctx* ctx, const float* F, const b200reg_geom& 
             B200_CHECK_LAUNCH();
         }
     }
-    select_copy_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(P[1], P[0], 3 * n, ctrl);
+    select_copy_kernel<<<ctx->sm_count * 8, 256, 0, ctx->stream>>>(P[1], P[0], 3 * n, ctrl, start);
     ctx->launches++;
     B200_CHECK_LAUNCH();
     return B200REG_OK;
