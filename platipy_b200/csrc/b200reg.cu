@@ -96,6 +96,7 @@ API int b200reg_create(int device, void* stream, b200reg_ctx** out)
     if (const char* e = knob("FORCE_ZM1")) ctx->force_zm1 = (e[0] == '1');
     if (const char* e = knob("PACK_LABELS")) ctx->pack_labels = (e[0] != '0');
     if (const char* e = knob("PDL")) ctx->pdl = (e[0] != '0');
+    if (const char* e = knob("IDENTITY_COPY")) ctx->identity_copy = (e[0] != '0');
     *out = ctx;
     return B200REG_OK;
 }

@@ -771,27 +771,54 @@ inline int launch_conv3d_zmarch(b200reg_ctx* ctx, const double* a, const double*
 // ---- shared-memory tiled separable pass for Float32 images (DiscreteGaussianImageFilter, any radius <= KMAX_R) ---
 // Inputs are converted to double once when staged (the per-tap f32->f64 conversion of the naive kernel saturates
 // the 16-lane XU pipe); taps are accumulated in double in ascending order, result rounded to float32.
-// AXIS 0: one block = 256 consecutive outputs of one row.
+// AXIS 0: one block = 256 consecutive outputs of each of 4 rows; 64 x 4 threads, every thread owns FOUR consecutive outputs of one row and
+// slides a four-value register window along the taps (one shared load + one coefficient + four multiply-adds per tap, as in the y / z
+// kernel below).  The staged row is stored 4-way interleaved -- element e at (e & 3) * CX_Q + (e >> 2) -- so that lanes, which are four
+// elements apart, read consecutive words (conflict-free); CX_Q = 4 (mod 16) keeps the staging stores conflict-free as well.
+constexpr int CX_Q = 100;  // >= (256 + 2 * KMAX_R) / 4, = 4 (mod 16)
 __global__ void __launch_bounds__(256) conv_x_f32_tiled_kernel(const float* __restrict__ in, float* __restrict__ out, int nx, int ny, int nz,
                                                                 const __grid_constant__ KernelCoeffs kc)
 {
-    __shared__ double sm[256 + 2 * KMAX_R];
+    __shared__ double sm[4][4 * CX_Q];
     const int r = kc.r;
-    const int x0 = blockIdx.x * 256, y = blockIdx.y, z = blockIdx.z;
-    const size_t row = ((size_t)z * ny + y) * nx;
-    for (int e = threadIdx.x; e < 256 + 2 * r; e += 256) {
+    const int tx = threadIdx.x, ty = threadIdx.y;
+    const int x0 = blockIdx.x * 256, y = blockIdx.y * 4 + ty, z = blockIdx.z;
+    const bool row_ok = y < ny;
+    const size_t row = ((size_t)z * ny + (row_ok ? y : ny - 1)) * nx;
+    double* s = sm[ty];
+    for (int e = tx; e < 256 + 2 * r; e += 64) {
         int gx = x0 - r + e;
         gx = gx < 0 ? 0 : (gx > nx - 1 ? nx - 1 : gx);
-        sm[e] = (double)in[row + gx];
+        s[(e & 3) * CX_Q + (e >> 2)] = (double)in[row + gx];
     }
     __syncthreads();
-    const int x = x0 + threadIdx.x;
-    if (x >= nx) return;
-    double sum = 0.0;
-    const double* w = sm + threadIdx.x;
-#pragma unroll 5
-    for (int t = 0; t <= 2 * r; ++t) sum += kc.k[t] * w[t];
-    out[row + x] = (float)sum;
+    const int x = x0 + 4 * tx;
+    if (!row_ok || x >= nx) return;
+    // output m of this thread uses elements 4 tx + m + t, t = 0 .. 2r, in ascending tap order
+    double acc[4] = { 0.0, 0.0, 0.0, 0.0 };
+    const double* w = s + tx;
+    double v0 = w[0], v1 = w[CX_Q], v2 = w[2 * CX_Q], v3 = w[3 * CX_Q];
+    const int last = 2 * r;
+#pragma unroll 4
+    for (int t = 0; t <= last; ++t) {
+        const double kt = kc.k[t];
+        acc[0] += kt * v0;
+        acc[1] += kt * v1;
+        acc[2] += kt * v2;
+        acc[3] += kt * v3;
+        v0 = v1;
+        v1 = v2;
+        v2 = v3;
+        if (t < last) v3 = w[((t + 4) & 3) * CX_Q + ((t + 4) >> 2)];
+    }
+    float* o = out + row + x;
+    if (x + 3 < nx && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
+        *reinterpret_cast<float4*>(o) = make_float4((float)acc[0], (float)acc[1], (float)acc[2], (float)acc[3]);
+    } else {
+#pragma unroll
+        for (int m = 0; m < 4; ++m)
+            if (x + m < nx) o[m] = (float)acc[m];
+    }
 }
 // AXIS 1 / 2: tile of 32 x-columns by 32 positions along the axis; each thread owns 4 consecutive positions and
 // slides over 4 + 2r staged values, feeding the four accumulators in ascending tap order.
@@ -844,7 +871,7 @@ __global__ void __launch_bounds__(256) conv_yz_f32_tiled_kernel(const float* __r
 inline int launch_conv_axis_f32_tiled(b200reg_ctx* ctx, int axis, const float* in, float* out, int nx, int ny, int nz, const KernelCoeffs& kc)
 {
     if (axis == 0) {
-        conv_x_f32_tiled_kernel<<<dim3((nx + 255) / 256, ny, nz), 256, 0, ctx->stream>>>(in, out, nx, ny, nz, kc);
+        conv_x_f32_tiled_kernel<<<dim3((nx + 255) / 256, (ny + 3) / 4, nz), dim3(64, 4), 0, ctx->stream>>>(in, out, nx, ny, nz, kc);
     } else if (axis == 1) {
         conv_yz_f32_tiled_kernel<1><<<dim3((nx + 31) / 32, (ny + 31) / 32, nz), 256, 0, ctx->stream>>>(in, out, nx, ny, nz, kc);
     } else {

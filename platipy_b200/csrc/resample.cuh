@@ -514,6 +514,46 @@ __global__ void __launch_bounds__(BX* BY, BSP ? 2 : 4) resample_batch_kernel(con
     }
 }
 
+// ---- identity resamples that are exact copies ---------------------------------------------------------------------------------------
+// platipy re-grids onto an identical grid in several places (the full-resolution pyramid level of smooth_and_resample, utils.py:257-267
+// with shrink factor 1; the final sitk.Resample(dvf_total, fixed_image), deformable.py:185, when the last level is the full grid).
+// ITK still runs the resampler there.  Its result equals the input exactly when every continuous index it computes is exactly the
+// integer index -- then nearest neighbour and linear interpolation (distance 0: v + (w - v) * 0) return the voxel itself.  That is
+// decided here by evaluating, on the host, the very arithmetic the kernel would evaluate (index -> point of the output grid,
+// point -> continuous index of the input grid, the scan-line interpolation of resample_linear_scanline) for every index along every
+// axis; only grids with identity direction cosines qualify (the axes then separate).  Finite voxel values assumed (an infinite
+// neighbour would turn v + (inf - v) * 0 into NaN in the generic path).
+inline bool identity_resample_is_exact(const b200reg_geom& gin, const b200reg_geom& gout)
+{
+    for (int a = 0; a < 3; ++a)
+        if (gin.size[a] != gout.size[a]) return false;
+    const GeomD gi = make_geomd(gin), go = make_geomd(gout);
+    for (int q = 0; q < 9; ++q) {
+        const double want = (q % 4 == 0) ? 1.0 : 0.0;
+        if (gi.direction[q] != want || go.direction[q] != want) return false;
+    }
+    const int n[3] = { go.nx, go.ny, go.nz };
+    const bool scanline = semantics().resample_linear_scanline != 0;
+    for (int a = 0; a < 3; ++a) {
+        // one axis of idx2pt / pt2cidx with the zero off-diagonal terms dropped (they add exact zeros)
+        auto f = [&](double t) {
+            const double p = go.i2p[a * 4] * t + go.origin[a];
+            return gi.p2i[a * 4] * (p - gi.origin[a]);
+        };
+        if (a == 0 && scanline) {
+            const double cs = f(0.0), ce = f((double)n[0]);
+            for (int i = 0; i < n[0]; ++i) {
+                const double alpha = (double)i / (double)n[0];
+                if (cs + alpha * (ce - cs) != (double)i) return false;
+            }
+        } else {
+            for (int i = 0; i < n[a]; ++i)
+                if (f((double)i) != (double)i) return false;
+        }
+    }
+    return true;
+}
+
 inline int resample_batch(b200reg_ctx* ctx, int n, const void* const* d_in, const int* dtypes, const b200reg_geom& gin,
                           void* const* d_out, const b200reg_geom& gout, const b200reg_transform* chain, int n_chain,
                           const int* interps, const double* defaults)
@@ -528,6 +568,16 @@ inline int resample_batch(b200reg_ctx* ctx, int n, const void* const* d_in, cons
             return set_error(B200REG_ERR_UNSUPPORTED, "interpolator %d is not supported (nearest neighbour = 1, linear = 2, B-spline = 3)", interps[i]);
     }
     const size_t n_in = nvox(gin);
+    if (n_chain == 0 && ctx->identity_copy) {
+        bool plain = true;
+        for (int i = 0; i < n; ++i) plain = plain && (interps[i] == B200REG_INTERP_NN || interps[i] == B200REG_INTERP_LINEAR);
+        if (plain && identity_resample_is_exact(gin, gout)) {
+            for (int i = 0; i < n; ++i)
+                if (d_in[i] != d_out[i])
+                    B200_CUDA(cudaMemcpyAsync(d_out[i], d_in[i], n_in * dtype_size(dtypes[i]), cudaMemcpyDeviceToDevice, ctx->stream));
+            return B200REG_OK;
+        }
+    }
     // UInt8 nearest-neighbour items (propagated structures) travel bit-packed when there are enough of them to pay for the packing pass
     std::vector<int> plain, packed;
     for (int i = 0; i < n; ++i) {
@@ -674,6 +724,10 @@ __global__ void __launch_bounds__(BX* BY, 4) resample_vec3_kernel(const double* 
 inline int resample_vec3(b200reg_ctx* ctx, const double* d_in, const b200reg_geom& gin, double* d_out, const b200reg_geom& gout,
                          const b200reg_transform* chain, int n_chain, double default_value, const double* d_acc = nullptr)
 {
+    if (n_chain == 0 && !d_acc && ctx->identity_copy && identity_resample_is_exact(gin, gout)) {
+        if (d_in != d_out) B200_CUDA(cudaMemcpyAsync(d_out, d_in, 3 * nvox(gin) * sizeof(double), cudaMemcpyDeviceToDevice, ctx->stream));
+        return B200REG_OK;
+    }
     ChainD ch;
     B200_TRY(make_chain(chain, n_chain, &ch));
     const GeomD gi = make_geomd(gin), go = make_geomd(gout);
