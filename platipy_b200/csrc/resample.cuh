@@ -7,12 +7,17 @@
 
 namespace b200 {
 
+#ifndef RS_MINB
+#define RS_MINB 4  // resident 256-thread blocks per SM the resampling kernels are compiled for (64 registers)
+#endif
+
 struct TfmD {
     int kind;
     double matrix[9];
     double offset[3];
     const double* dvf;  // SoA planes
     GeomD g;
+    int on_grid;        // first element only: the field lives on the OUTPUT grid and every index maps to itself exactly -> read per index
 };
 struct ChainD {
     int n;
@@ -37,6 +42,7 @@ inline int make_chain(const b200reg_transform* chain, int n_chain, ChainD* out)
         for (int k = 0; k < 9; ++k) t.matrix[k] = chain[i].matrix[k];
         for (int k = 0; k < 3; ++k) t.offset[k] = chain[i].offset[k];
         t.dvf = chain[i].d_dvf;
+        t.on_grid = 0;
         if (t.kind == B200REG_TFM_DVF) {
             if (!t.dvf || !valid_geom(&chain[i].dvf_geom)) return set_error(B200REG_ERR_ARG, "invalid displacement-field transform");
             t.g = make_geomd(chain[i].dvf_geom);
@@ -46,6 +52,56 @@ inline int make_chain(const b200reg_transform* chain, int n_chain, ChainD* out)
         }
     }
     return B200REG_OK;
+}
+
+// ---- identity resamples that are exact copies ---------------------------------------------------------------------------------------
+// platipy re-grids onto an identical grid in several places (the full-resolution pyramid level of smooth_and_resample, utils.py:257-267
+// with shrink factor 1; the final sitk.Resample(dvf_total, fixed_image), deformable.py:185, when the last level is the full grid).
+// ITK still runs the resampler there.  Its result equals the input exactly when every continuous index it computes is exactly the
+// integer index -- then nearest neighbour and linear interpolation (distance 0: v + (w - v) * 0) return the voxel itself.  That is
+// decided here by evaluating, on the host, the very arithmetic the kernel would evaluate (index -> point of the output grid,
+// point -> continuous index of the input grid, the scan-line interpolation of resample_linear_scanline) for every index along every
+// axis; only grids with identity direction cosines qualify (the axes then separate).  Finite voxel values assumed (an infinite
+// neighbour would turn v + (inf - v) * 0 into NaN in the generic path).
+inline bool identity_resample_is_exact(const b200reg_geom& gin, const b200reg_geom& gout, bool allow_scanline = true)
+{
+    for (int a = 0; a < 3; ++a)
+        if (gin.size[a] != gout.size[a]) return false;
+    const GeomD gi = make_geomd(gin), go = make_geomd(gout);
+    for (int q = 0; q < 9; ++q) {
+        const double want = (q % 4 == 0) ? 1.0 : 0.0;
+        if (gi.direction[q] != want || go.direction[q] != want) return false;
+    }
+    const int n[3] = { go.nx, go.ny, go.nz };
+    const bool scanline = allow_scanline && semantics().resample_linear_scanline != 0;
+    for (int a = 0; a < 3; ++a) {
+        // one axis of idx2pt / pt2cidx with the zero off-diagonal terms dropped (they add exact zeros)
+        auto f = [&](double t) {
+            const double p = go.i2p[a * 4] * t + go.origin[a];
+            return gi.p2i[a * 4] * (p - gi.origin[a]);
+        };
+        if (a == 0 && scanline) {
+            const double cs = f(0.0), ce = f((double)n[0]);
+            for (int i = 0; i < n[0]; ++i) {
+                const double alpha = (double)i / (double)n[0];
+                if (cs + alpha * (ce - cs) != (double)i) return false;
+            }
+        } else {
+            for (int i = 0; i < n[a]; ++i)
+                if (f((double)i) != (double)i) return false;
+        }
+    }
+    return true;
+}
+
+// A displacement field that lives on the OUTPUT grid of a resample (the usual case: the transform of a registration applied on the
+// fixed grid, deformable.py:281-301, multiatlas/run.py:331-345) is read by ITK through the generic path: output index -> point ->
+// continuous index of the field -> interpolation.  When the host proves that every such continuous index is exactly the integer
+// index (identity_resample_is_exact, per-voxel form), the interpolation returns the node value itself (weight 1 on one neighbour)
+// and the kernel reads the field per index instead.
+inline void chain_mark_on_grid(b200reg_ctx* ctx, ChainD* ch, const b200reg_transform* chain, int n_chain, const b200reg_geom& gout)
+{
+    if (ctx->identity_copy && n_chain >= 1 && chain[0].kind == B200REG_TFM_DVF && identity_resample_is_exact(chain[0].dvf_geom, gout, false)) ch->t[0].on_grid = 1;
 }
 
 // VectorLinearInterpolateImageFunction (inside DisplacementFieldTransform): weighted sum over the 8
@@ -94,9 +150,9 @@ __device__ __forceinline__ void interp_wsum_vec3(const double* __restrict__ f, c
 __device__ __noinline__ void interp_lerp_vec3_alt(const double* __restrict__ f, const GeomD& g, const double* c, double* out);
 __device__ __noinline__ void interp_wsum_vec3_alt(const double* __restrict__ f, const GeomD& g, const double* c, double* out);
 
-__device__ __forceinline__ void apply_chain(const ChainD& ch, double* p)
+__device__ __forceinline__ void apply_chain(const ChainD& ch, double* p, int first = 0)
 {
-    for (int i = 0; i < ch.n; ++i) {
+    for (int i = first; i < ch.n; ++i) {
         const TfmD& t = ch.t[i];
         if (t.kind == B200REG_TFM_AFFINE) {
             double q[3];
@@ -133,7 +189,17 @@ __device__ __forceinline__ void out_to_in_cidx(const GeomD& go, const GeomD& gi,
     double p[3];
     if (!ch.linear) {
         idx2pt(go, (double)i, (double)j, (double)k, p);
-        apply_chain(ch, p);
+        int first = 0;
+        if (ch.n > 0 && ch.t[0].on_grid) {
+            // the field on the output grid, read per index (see chain_mark_on_grid)
+            const size_t n = (size_t)go.nx * go.ny * go.nz, o = ((size_t)k * go.ny + j) * go.nx + i;
+            const double* __restrict__ f = ch.t[0].dvf;
+            p[0] += __ldg(f + o);
+            p[1] += __ldg(f + n + o);
+            p[2] += __ldg(f + 2 * n + o);
+            first = 1;
+        }
+        apply_chain(ch, p, first);
         pt2cidx(gi, p, c);
     } else {
         double cs[3], ce[3];
@@ -463,7 +529,7 @@ __global__ void __launch_bounds__(256) pack_u8_bits_kernel(const __grid_constant
 // BSP: the batch contains a B-spline item (the 64-point evaluation needs far more registers than the other two
 // interpolators, so it lives in its own instantiation and the common one keeps 4 blocks per SM)
 template <bool SMALL, bool BSP, bool PACKED = false>
-__global__ void __launch_bounds__(BX* BY, BSP ? 2 : 4) resample_batch_kernel(const __grid_constant__ BatchD batch, const __grid_constant__ GeomD gi,
+__global__ void __launch_bounds__(BX* BY, BSP ? 2 : RS_MINB) resample_batch_kernel(const __grid_constant__ BatchD batch, const __grid_constant__ GeomD gi,
                                                                  const __grid_constant__ GeomD go, const __grid_constant__ ChainD ch,
                                                                  const __grid_constant__ PackedD pk)
 {
@@ -514,52 +580,13 @@ __global__ void __launch_bounds__(BX* BY, BSP ? 2 : 4) resample_batch_kernel(con
     }
 }
 
-// ---- identity resamples that are exact copies ---------------------------------------------------------------------------------------
-// platipy re-grids onto an identical grid in several places (the full-resolution pyramid level of smooth_and_resample, utils.py:257-267
-// with shrink factor 1; the final sitk.Resample(dvf_total, fixed_image), deformable.py:185, when the last level is the full grid).
-// ITK still runs the resampler there.  Its result equals the input exactly when every continuous index it computes is exactly the
-// integer index -- then nearest neighbour and linear interpolation (distance 0: v + (w - v) * 0) return the voxel itself.  That is
-// decided here by evaluating, on the host, the very arithmetic the kernel would evaluate (index -> point of the output grid,
-// point -> continuous index of the input grid, the scan-line interpolation of resample_linear_scanline) for every index along every
-// axis; only grids with identity direction cosines qualify (the axes then separate).  Finite voxel values assumed (an infinite
-// neighbour would turn v + (inf - v) * 0 into NaN in the generic path).
-inline bool identity_resample_is_exact(const b200reg_geom& gin, const b200reg_geom& gout)
-{
-    for (int a = 0; a < 3; ++a)
-        if (gin.size[a] != gout.size[a]) return false;
-    const GeomD gi = make_geomd(gin), go = make_geomd(gout);
-    for (int q = 0; q < 9; ++q) {
-        const double want = (q % 4 == 0) ? 1.0 : 0.0;
-        if (gi.direction[q] != want || go.direction[q] != want) return false;
-    }
-    const int n[3] = { go.nx, go.ny, go.nz };
-    const bool scanline = semantics().resample_linear_scanline != 0;
-    for (int a = 0; a < 3; ++a) {
-        // one axis of idx2pt / pt2cidx with the zero off-diagonal terms dropped (they add exact zeros)
-        auto f = [&](double t) {
-            const double p = go.i2p[a * 4] * t + go.origin[a];
-            return gi.p2i[a * 4] * (p - gi.origin[a]);
-        };
-        if (a == 0 && scanline) {
-            const double cs = f(0.0), ce = f((double)n[0]);
-            for (int i = 0; i < n[0]; ++i) {
-                const double alpha = (double)i / (double)n[0];
-                if (cs + alpha * (ce - cs) != (double)i) return false;
-            }
-        } else {
-            for (int i = 0; i < n[a]; ++i)
-                if (f((double)i) != (double)i) return false;
-        }
-    }
-    return true;
-}
-
 inline int resample_batch(b200reg_ctx* ctx, int n, const void* const* d_in, const int* dtypes, const b200reg_geom& gin,
                           void* const* d_out, const b200reg_geom& gout, const b200reg_transform* chain, int n_chain,
                           const int* interps, const double* defaults)
 {
     ChainD ch;
     B200_TRY(make_chain(chain, n_chain, &ch));
+    chain_mark_on_grid(ctx, &ch, chain, n_chain, gout);
     const GeomD gi = make_geomd(gin), go = make_geomd(gout);
     for (int i = 0; i < n; ++i) {
         if (!d_in[i] || !d_out[i]) return set_error(B200REG_ERR_ARG, "null image pointer in resample batch");
@@ -681,7 +708,7 @@ inline int resample_batch(b200reg_ctx* ctx, int n, const void* const* d_in, cons
 // LinearInterpolateImageFunction on a VectorImage: the same nested-lerp form, per component.
 // ACCUM: out = acc + value (dvf_total + Resample(dvf_iter, tfm_total), deformable.py:154).
 template <bool ACCUM, bool SMALL>
-__global__ void __launch_bounds__(BX* BY, 4) resample_vec3_kernel(const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ acc,
+__global__ void __launch_bounds__(BX* BY, RS_MINB) resample_vec3_kernel(const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ acc,
                                                                 const __grid_constant__ GeomD gi, const __grid_constant__ GeomD go,
                                                                 const __grid_constant__ ChainD ch, double default_value)
 {
@@ -730,6 +757,7 @@ inline int resample_vec3(b200reg_ctx* ctx, const double* d_in, const b200reg_geo
     }
     ChainD ch;
     B200_TRY(make_chain(chain, n_chain, &ch));
+    chain_mark_on_grid(ctx, &ch, chain, n_chain, gout);
     const GeomD gi = make_geomd(gin), go = make_geomd(gout);
     const dim3 g = grid3(go.nx, go.ny, go.nz), b = block3();
     if (d_acc) {
