@@ -158,6 +158,12 @@ int b200reg_minmax(b200reg_ctx* ctx, const void* d_in, int dtype, size_t n, doub
 /* ---- N1: itk::DiscreteGaussianImageFilter (utils.py:226; fusion.py:168,279) ------------------------- */
 int b200reg_discrete_gaussian_f32(b200reg_ctx* ctx, const float* d_in, float* d_out, const b200reg_geom* geom,
                                   const double variance[3], int max_kernel_width, double max_error, int use_image_spacing);
+/* smooth_and_resample (utils.py:195-267) as one call for a Float32 image: DiscreteGaussian(variance, maximumKernelWidth, useImageSpacing)
+ * (utils.py:216-226) then Resample onto out_geom with an identity transform and default pixel value 0 (utils.py:257-267).  With
+ * allow_restricted = 1 a level that shrinks enough for it to pay, read through a linear interpolator, is blurred only at the planes /
+ * rows / columns the resampler reads; 2 takes that form whenever it is possible, 0 never (all three give the same bits). */
+int b200reg_smooth_and_resample_f32(b200reg_ctx* ctx, const float* d_in, const b200reg_geom* in_geom, const double variance[3],
+                                    int max_kernel_width, const b200reg_geom* out_geom, int interp, float* d_out, int allow_restricted);
 /* GaussianOperator coefficients (host-side; used by tests): returns radius, fills kernel[0..2r] */
 int b200reg_gaussian_operator(double variance, double max_error, int max_kernel_width, double* h_kernel, int capacity);
 

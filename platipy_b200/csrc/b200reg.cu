@@ -15,6 +15,7 @@
 #include "moments_kernels.cuh"
 #include "gauss.cuh"
 #include "resample.cuh"
+#include "pyramid.cuh"
 
 using namespace b200;
 
@@ -97,6 +98,8 @@ API int b200reg_create(int device, void* stream, b200reg_ctx** out)
     if (const char* e = knob("PACK_LABELS")) ctx->pack_labels = (e[0] != '0');
     if (const char* e = knob("PDL")) ctx->pdl = (e[0] != '0');
     if (const char* e = knob("IDENTITY_COPY")) ctx->identity_copy = (e[0] != '0');
+    if (const char* e = knob("PYRAMID_RESTRICT")) ctx->pyramid_restrict = (e[0] != '0');
+    if (const char* e = knob("PYRAMID_RESTRICT_COST")) ctx->pyramid_restrict_cost = atof(e);
     *out = ctx;
     return B200REG_OK;
 }
@@ -467,6 +470,12 @@ static int smooth_and_resample_f32(b200reg_ctx* ctx, const float* d_in, const b2
         const double var[3] = { sigma * sigma, sigma * sigma, sigma * sigma };
         double mw = 0.0;
         for (int a = 0; a < 3; ++a) mw = fmax(mw, 8 * var[a] * gin.spacing[a]);
+        if (interp == B200REG_INTERP_LINEAR) {
+            // a shrinking level: blur only what the level's interpolation reads (pyramid.cuh; bit-identical)
+            bool used = false;
+            B200_TRY(smooth_and_shrink_f32(ctx, d_in, gin, var, (int)mw, 0.01, gout, d_out, &used));
+            if (used) return B200REG_OK;
+        }
         B200_TRY(sm.alloc(ctx, n * sizeof(float)));
         B200_TRY(discrete_gaussian_f32(ctx, d_in, sm.as<float>(), gin, var, (int)mw, 0.01, 1));
         src = sm.as<float>();
@@ -476,6 +485,32 @@ static int smooth_and_resample_f32(b200reg_ctx* ctx, const float* d_in, const b2
     const int dt = B200REG_F32;
     const double dv = 0.0;
     return resample_batch(ctx, 1, ins, &dt, gin, outs, gout, nullptr, 0, &interp, &dv);
+}
+
+// a3 as one call: sitk.DiscreteGaussian (utils.py:216-226) followed by sitk.Resample onto the new grid (utils.py:257-267) for a Float32 image.
+// allow_restricted 1: a level that shrinks enough to pay (linear interpolator) blurs only what the resampler reads (pyramid.cuh); 2: whenever
+// the restricted form is possible; 0: never (the forms are bit-identical; the switch exists for tests and A/B timing).
+API int b200reg_smooth_and_resample_f32(b200reg_ctx* ctx, const float* d_in, const b200reg_geom* in_geom, const double variance[3], int max_kernel_width,
+                                        const b200reg_geom* out_geom, int interp, float* d_out, int allow_restricted)
+{
+    ENTER(ctx);
+    REQUIRE(d_in && d_out && variance && valid_geom(in_geom) && valid_geom(out_geom), "invalid argument");
+    REQUIRE(interp == B200REG_INTERP_NN || interp == B200REG_INTERP_LINEAR || interp == B200REG_INTERP_BSPLINE,
+            "interpolator %d is not supported (nearest neighbour = 1, linear = 2, B-spline = 3)", interp);
+    for (int a = 0; a < 3; ++a) REQUIRE(variance[a] >= 0.0, "variance must not be negative");
+    if (allow_restricted && interp == B200REG_INTERP_LINEAR) {
+        bool used = false;
+        B200_TRY(smooth_and_shrink_f32(ctx, d_in, *in_geom, variance, max_kernel_width, 0.01, *out_geom, d_out, &used, allow_restricted == 2));
+        if (used) return B200REG_OK;
+    }
+    TempBuf sm;
+    B200_TRY(sm.alloc(ctx, nvox(*in_geom) * sizeof(float)));
+    B200_TRY(discrete_gaussian_f32(ctx, d_in, sm.as<float>(), *in_geom, variance, max_kernel_width, 0.01, 1));
+    const void* ins[1] = { sm.p };
+    void* outs[1] = { d_out };
+    const int dt = B200REG_F32;
+    const double dv = 0.0;
+    return resample_batch(ctx, 1, ins, &dt, *in_geom, outs, *out_geom, nullptr, 0, &interp, &dv);
 }
 
 API int b200reg_multiscale_demons(b200reg_ctx* ctx, const float* d_fixed, const b200reg_geom* fixed_geom, const float* d_moving,

@@ -126,6 +126,8 @@ struct b200reg_ctx {
     int zm_chunks = 0;             // B200REG_ZM_CHUNKS=n: z-chunks per tile column of the fused smoothing kernel (0: automatic)
     bool zm_tx32 = true;           // B200REG_ZM_TX32=0: 64-wide tiles (320 threads, 2 CTAs per SM) in the fused smoothing kernel; 32-wide: 4 CTAs per SM, -1 %
     bool zm_addout = true;         // B200REG_ZM_ADDOUT=0: D + U formed inside the displacement smoothing (staged twice) instead of at the end of the update smoothing
+    double pyramid_restrict_cost = 0.6;  // B200REG_PYRAMID_RESTRICT_COST: largest restricted-work estimate (in full passes) that takes pyramid.cuh
+    bool pyramid_restrict = true;  // B200REG_PYRAMID_RESTRICT=0: shrinking pyramid levels blur the whole image before resampling it (pyramid.cuh) (A/B)
     bool identity_copy = true;     // B200REG_IDENTITY_COPY=0: identity re-grids onto an identical grid always run the resampling kernel (A/B)
     bool pdl = true;               // B200REG_PDL=0: the Demons loop kernels are launched without programmatic dependent launch (A/B)
     bool pack_labels = true;       // B200REG_PACK_LABELS=0: UInt8 nearest-neighbour items of a resample batch are gathered one byte at a time (A/B)

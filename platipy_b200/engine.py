@@ -362,6 +362,19 @@ class Engine:
                                                           int(maximum_kernel_width), float(maximum_error), int(bool(use_image_spacing))))
         return dimg.like(out)
 
+    def smooth_and_resample(self, dimg, variance, maximum_kernel_width, out_geom_src, interpolator=sk.sitkLinear, allow_restricted=True):
+        """DiscreteGaussian + Resample onto ``out_geom_src`` of a Float32 image as one library call (utils.py:216-267).  ``allow_restricted``:
+        True / 1 = blur only what the resampler reads when the level shrinks enough to pay, 2 = whenever possible, False / 0 = never."""
+        if dimg.np_dtype != np.float32 or dimg.is_vector:
+            raise NotImplementedError("smooth_and_resample as one call is implemented for Float32 scalar images")
+        var = (C.c_double * 3)(*([float(variance)] * 3 if np.isscalar(variance) else [float(v) for v in variance]))
+        gin, gout = dimg.geom, _abi.geom_of(out_geom_src)
+        x, y, z = out_geom_src.GetSize()
+        out = self.empty((z, y, x), np.float32)
+        _abi.check(self.lib.b200reg_smooth_and_resample_f32(self.ctx, dimg.ptr, C.byref(gin), var, int(maximum_kernel_width), C.byref(gout),
+                                                            int(interpolator), C.c_void_p(out.data_ptr()), int(allow_restricted)))
+        return DeviceImage(out, np.float32, out_geom_src.GetSpacing(), out_geom_src.GetOrigin(), out_geom_src.GetDirection(), False)
+
     def resample_batch(self, images, out_geom_src, transform, interpolators, default_values):
         """N images on one grid through one transform chain onto the grid of ``out_geom_src`` (anything
         with GetSize/GetSpacing/GetOrigin/GetDirection)."""

@@ -88,13 +88,18 @@ def smooth_and_resample(image, isotropic_voxel_size_mm=None, shrink_factor=None,
                         interpolator=sitkLinear):
     eng = Engine.get()
     d = eng.to_device(image)
+    pending_blur = None
     if smoothing_sigma:
         if hasattr(smoothing_sigma, "__iter__"):
             variance = [s * s for s in smoothing_sigma]
         else:
             variance = (smoothing_sigma ** 2,) * 3
         max_width = int(max(8 * v * sp for sp, v in zip(d.GetSpacing(), variance)))
-        d = eng.discrete_gaussian(d, variance, max_width)
+        if d.np_dtype == np.float32 and not d.is_vector and (isotropic_voxel_size_mm or shrink_factor):
+            # blur + resample go to the library as one call: a shrinking level is blurred only where the resampler reads it (bit-identical)
+            pending_blur = (variance, max_width)
+        else:
+            d = eng.discrete_gaussian(d, variance, max_width)
 
     size_o, spacing_o = d.GetSize(), d.GetSpacing()
     if shrink_factor and isotropic_voxel_size_mm:
@@ -124,7 +129,10 @@ def smooth_and_resample(image, isotropic_voxel_size_mm=None, shrink_factor=None,
         def GetDirection(self):
             return d.GetDirection()
 
-    out = eng.resample(d, _Grid(), None, _check_interp(interpolator), 0.0)
+    if pending_blur is not None:
+        out = eng.smooth_and_resample(d, pending_blur[0], pending_blur[1], _Grid(), _check_interp(interpolator))
+    else:
+        out = eng.resample(d, _Grid(), None, _check_interp(interpolator), 0.0)
     return _back(eng, out, image)
 
 

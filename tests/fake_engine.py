@@ -201,6 +201,10 @@ class FakeEngine:
         var = [float(variance)] * 3 if np.isscalar(variance) else [float(v) for v in variance]
         return self._wrap(orc.discrete_gaussian_f32(_arr(d), orc.geom_of(_img(d)), var, maximum_kernel_width, maximum_error, use_image_spacing), d)
 
+    def smooth_and_resample(self, d, variance, maximum_kernel_width, out_geom_src, interpolator=sk.sitkLinear, allow_restricted=True):
+        self._note("smooth_and_resample")
+        return self.resample(self.discrete_gaussian(d, variance, maximum_kernel_width), out_geom_src, None, interpolator, 0.0)
+
     # -- reductions behind linear_registration ----------------------------------------------------------------------------
     def image_moments(self, d):
         self._note("image_moments")

@@ -290,6 +290,46 @@ def test_smooth_and_resample_parity_and_errors(engine):
         reg.smooth_and_resample(fixed, shrink_factor=64)  # a level collapsing to one voxel: utils.py:252-255 divides by zero
 
 
+@pytest.mark.parametrize("size,spacing,kw", [
+    ((96, 80, 48), (1.0, 1.0, 1.0), dict(shrink_factor=4, smoothing_sigma=2.0)),
+    ((97, 83, 41), (0.9, 1.1, 2.5), dict(shrink_factor=8, smoothing_sigma=4.0)),
+    ((64, 64, 40), (0.98, 0.98, 3.0), dict(isotropic_voxel_size_mm=6, smoothing_sigma=3.0)),      # z hardly shrinks: that axis stays (almost) full
+    ((75, 50, 33), (1.0, 1.0, 1.0), dict(shrink_factor=3, smoothing_sigma=1.5)),                 # odd factor: continuous indices on / near integers
+    ((80, 72, 36), (1.2, 1.2, 1.2), dict(shrink_factor=[4, 4, 2], smoothing_sigma=[2.4, 2.4, 1.2])),
+    ((130, 24, 20), (1.0, 1.0, 1.0), dict(shrink_factor=[16, 2, 2], smoothing_sigma=[6.0, 1.0, 1.0])),  # radius near the supported maximum
+])
+def test_restricted_pyramid_level_is_bit_identical(engine, size, spacing, kw):
+    """A shrinking smooth_and_resample blurs only the planes / rows / columns the level's linear interpolation reads (pyramid.cuh): equal, bit
+    for bit, to blur-everything-then-resample (the generic path, forced through allow_restricted=0) and to the oracle's restatement of
+    utils.py:195-267 -- with both settings of the two semantic switches the restricted path depends on."""
+    from platipy_b200 import _abi
+
+    img, _ = synth_pair(size, seed=sum(size), spacing=spacing, origin=(-12.5, 7.25, 100.0))
+    exp = ref.smooth_and_resample(img, **kw)
+    out = reg.smooth_and_resample(img, **kw)
+    assert out.GetSize() == exp.GetSize()
+    assert np.array_equal(out.array, exp.array)
+    # the generic path on the same grid
+    d = engine.to_device(img)
+    sig = kw["smoothing_sigma"]
+    var = [s * s for s in sig] if hasattr(sig, "__iter__") else [sig * sig] * 3
+    mw = int(max(8 * v * sp for sp, v in zip(spacing, var)))
+    generic = host(engine, engine.smooth_and_resample(d, var, mw, exp, sk.sitkLinear, allow_restricted=0)).array
+    assert np.array_equal(generic, exp.array)
+    forced = host(engine, engine.smooth_and_resample(d, var, mw, exp, sk.sitkLinear, allow_restricted=2)).array  # also below the pay-off threshold
+    assert np.array_equal(forced, exp.array)
+    for name in ("discrete_gaussian_axis_order", "resample_linear_scanline"):
+        flipped = 1 - _abi.get_semantic(name)
+        _abi.set_semantic(name, flipped)
+        try:
+            with orc.semantic(name, flipped):
+                exp2 = ref.smooth_and_resample(img, **kw).array
+            got2 = host(engine, engine.smooth_and_resample(d, var, mw, exp, sk.sitkLinear, allow_restricted=2)).array
+        finally:
+            _abi.set_semantic(name, 1 - flipped)
+        assert np.array_equal(got2, exp2), name
+
+
 def test_reference_acceptance_sphere_phantom_dice_gpu(engine):
     """The reference's only acceptance criterion for this path (test_cardiac.py:35-71,142), on the GPU."""
     from platipy_b200.synth import insert_sphere
