@@ -98,6 +98,7 @@ API int b200reg_create(int device, void* stream, b200reg_ctx** out)
     if (const char* e = knob("PACK_LABELS")) ctx->pack_labels = (e[0] != '0');
     if (const char* e = knob("PDL")) ctx->pdl = (e[0] != '0');
     if (const char* e = knob("IDENTITY_COPY")) ctx->identity_copy = (e[0] != '0');
+    if (const char* e = knob("WARP_RESAMPLE")) ctx->warp_resample = (e[0] != '0');
     if (const char* e = knob("PYRAMID_RESTRICT")) ctx->pyramid_restrict = (e[0] != '0');
     if (const char* e = knob("PYRAMID_RESTRICT_COST")) ctx->pyramid_restrict_cost = atof(e);
     *out = ctx;
@@ -254,6 +255,18 @@ API int b200reg_gaussian_operator(double variance, double max_error, int max_ker
 }
 
 // ---- N2/N5/N9 ---------------------------------------------------------------------------------------------------
+// one Float32 image, linear interpolation, one displacement field on the output grid: the Demons loop's warp kernel (demons_split.cuh)
+static int resample_batch_routed(b200reg_ctx* ctx, int n, const void* const* d_in, const int* dtypes, const b200reg_geom& gin, void* const* d_out,
+                                 const b200reg_geom& gout, const b200reg_transform* chain, int n_chain, const int* interps, const double* default_values)
+{
+    if (n == 1 && dtypes[0] == B200REG_F32 && d_in[0] && d_out[0] && d_in[0] != d_out[0]) {
+        bool used = false;
+        B200_TRY(resample_f32_on_grid_dvf(ctx, static_cast<const float*>(d_in[0]), gin, static_cast<float*>(d_out[0]), gout, chain, n_chain, interps[0],
+                                          default_values[0], &used));
+        if (used) return B200REG_OK;
+    }
+    return resample_batch(ctx, n, d_in, dtypes, gin, d_out, gout, chain, n_chain, interps, default_values);
+}
 API int b200reg_resample_batch(b200reg_ctx* ctx, int n, const void* const* d_in, const int* dtypes, const b200reg_geom* in_geom,
                                void* const* d_out, const b200reg_geom* out_geom, const b200reg_transform* chain, int n_chain,
                                const int* interps, const double* default_values)
@@ -262,7 +275,7 @@ API int b200reg_resample_batch(b200reg_ctx* ctx, int n, const void* const* d_in,
     REQUIRE(n > 0 && n <= B200REG_MAX_BATCH, "batch size %d not in [1, %d]", n, B200REG_MAX_BATCH);
     REQUIRE(d_in && d_out && dtypes && interps && default_values, "null argument");
     REQUIRE(valid_geom(in_geom) && valid_geom(out_geom), "invalid geometry");
-    return resample_batch(ctx, n, d_in, dtypes, *in_geom, d_out, *out_geom, chain, n_chain, interps, default_values);
+    return resample_batch_routed(ctx, n, d_in, dtypes, *in_geom, d_out, *out_geom, chain, n_chain, interps, default_values);
 }
 API int b200reg_resample(b200reg_ctx* ctx, const void* d_in, int dtype, const b200reg_geom* in_geom, void* d_out, const b200reg_geom* out_geom,
                          const b200reg_transform* chain, int n_chain, int interp, double default_value)
@@ -612,7 +625,7 @@ API int b200reg_multiscale_demons(b200reg_ctx* ctx, const float* d_fixed, const 
                 void* outs[1] = { mw.p };
                 const int dt = B200REG_F32, ip = cfg->interp_order;
                 const double dv = 0.0;
-                B200_TRY(resample_batch(ctx, 1, ins, &dt, gml[l], outs, gml[l], &tfm, 1, &ip, &dv));
+                B200_TRY(resample_batch_routed(ctx, 1, ins, &dt, gml[l], outs, gml[l], &tfm, 1, &ip, &dv));
             }
             // :143-149 Demons from a zero field
             b200reg_demons_params p = cfg->demons;

@@ -128,6 +128,7 @@ struct b200reg_ctx {
     bool zm_addout = true;         // B200REG_ZM_ADDOUT=0: D + U formed inside the displacement smoothing (staged twice) instead of at the end of the update smoothing
     double pyramid_restrict_cost = 0.6;  // B200REG_PYRAMID_RESTRICT_COST: largest restricted-work estimate (in full passes) that takes pyramid.cuh
     bool pyramid_restrict = true;  // B200REG_PYRAMID_RESTRICT=0: shrinking pyramid levels blur the whole image before resampling it (pyramid.cuh) (A/B)
+    bool warp_resample = true;     // B200REG_WARP_RESAMPLE=0: a Float32 image resampled through a field on the output grid takes the generic batch kernel (A/B)
     bool identity_copy = true;     // B200REG_IDENTITY_COPY=0: identity re-grids onto an identical grid always run the resampling kernel (A/B)
     bool pdl = true;               // B200REG_PDL=0: the Demons loop kernels are launched without programmatic dependent launch (A/B)
     bool pack_labels = true;       // B200REG_PACK_LABELS=0: UInt8 nearest-neighbour items of a resample batch are gathered one byte at a time (A/B)
@@ -274,6 +275,12 @@ inline GeomD make_geomd(const b200reg_geom& s)
     return g;
 }
 inline size_t nvox(const b200reg_geom& g) { return (size_t)g.size[0] * g.size[1] * g.size[2]; }
+// identity direction cosines: index -> point and point -> index separate per axis (the zero terms add exact zeros)
+inline bool geom_is_diag(const GeomD& g)
+{
+    const double* d = g.direction;
+    return d[0] == 1.0 && d[4] == 1.0 && d[8] == 1.0 && d[1] == 0.0 && d[2] == 0.0 && d[3] == 0.0 && d[5] == 0.0 && d[6] == 0.0 && d[7] == 0.0;
+}
 inline bool valid_geom(const b200reg_geom* g)
 {
     if (!g) return false;

@@ -225,12 +225,6 @@ __global__ void __launch_bounds__(1024) demons_finish_kernel(const double* __res
 // profiles/r01_summary.md and profiles/r01_s2_ab_split_vs_fused.log -- and were removed from the product headers; git history has
 // them.)
 
-inline bool geom_is_diag(const GeomD& g)
-{
-    const double* d = g.direction;
-    return d[0] == 1.0 && d[4] == 1.0 && d[8] == 1.0 && d[1] == 0.0 && d[2] == 0.0 && d[3] == 0.0 && d[5] == 0.0 && d[6] == 0.0 && d[7] == 0.0;
-}
-
 __global__ void demons_ctrl_init_kernel(DemonsCtrl* ctrl, int n_iters)
 {
     ctrl->halt_iter = n_iters <= 0 ? 0 : 0x7fffffff;

@@ -83,6 +83,29 @@ def test_resample_batch_equals_single_calls(engine):
         reg.apply_transform(moving, fixed, tfm, 0, 4)  # sitkGaussian: not one of the interpolators the path implements
 
 
+@pytest.mark.parametrize("moving_direction", [IDENT, "rotated"])
+def test_float32_resample_through_field_on_output_grid(engine, moving_direction):
+    """One Float32 image, linear interpolation, one displacement field that lives on the output grid (deformable.py:139-140, :281-301): this
+    call takes the Demons loop's warp kernel (demons_split.cuh: resample_f32_on_grid_dvf).  Same bits as the oracle's generic resampler,
+    including points pushed outside the moving buffer (default value) and an oriented moving image (the kernel's general-geometry form)."""
+    fixed, moving = synth_pair((45, 38, 27), seed=61, spacing=(1.1, 0.9, 2.0), origin=(4.0, -3.0, 12.0))
+    direction = rot_direction(0.04, -0.06) if moving_direction == "rotated" else IDENT
+    moving = Image(moving.array[:25, :30, :41].copy(), (1.0, 1.2, 1.9), (5.0, -1.0, 13.0), direction)  # its own grid, smaller than the fixed one
+    dvf = Image(smooth_random_dvf((45, 38, 27), seed=62, peak_mm=14.0), fixed.GetSpacing(), fixed.GetOrigin(), IDENT, True)
+    tfm = sk.DisplacementFieldTransform(dvf)
+    for dv in (-1000, 0, 3.5e38, 1e39):  # the last one is beyond Float32: clamped like ITK's CastPixelWithBoundsChecking
+        got = reg.apply_transform(moving, fixed, tfm, dv, sk.sitkLinear)
+        exp = ref.apply_transform(moving, fixed, tfm, dv, sk.sitkLinear)
+        assert got.array.dtype == np.float32
+        assert np.array_equal(got.array, exp.array), dv
+        assert (got.array == np.float32(min(dv, float(np.finfo(np.float32).max)))).any()  # some points do leave the moving buffer
+    # on the moving image's own grid (the level-start warp: output grid = input grid = field grid)
+    dvf_m = Image(smooth_random_dvf((41, 30, 25), seed=63, peak_mm=6.0), moving.GetSpacing(), moving.GetOrigin(), IDENT, True)
+    if moving_direction == IDENT:
+        t2 = sk.DisplacementFieldTransform(dvf_m)
+        assert np.array_equal(reg.apply_transform(moving, moving, t2, 0, sk.sitkLinear).array, ref.apply_transform(moving, moving, t2, 0, sk.sitkLinear).array)
+
+
 def test_bspline_interpolation_bit_exact(engine):
     """sitk.sitkBSpline (order 3; deformable.py:221-224, utils.py:148-192): coefficient decomposition + 64-point
     evaluation are the same IEEE operations as the oracle's restatement of itk::BSplineInterpolateImageFunction."""
