@@ -34,7 +34,16 @@ template <typename T>
 __global__ void __launch_bounds__(256) minmax_partial_kernel(const T* __restrict__ in, size_t n, double* __restrict__ partial)
 {
     double mn = DBL_MAX, mx = -DBL_MAX;
-    for (size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x; q < n; q += (size_t)gridDim.x * blockDim.x) {
+    // four independent loads per step (one load per step left the kernel waiting on memory: 1.3 TB/s at 268 MB); min / max are
+    // order-independent, so the result is the same
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    size_t q = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; q + 3 * stride < n; q += 4 * stride) {
+        const double v0 = (double)in[q], v1 = (double)in[q + stride], v2 = (double)in[q + 2 * stride], v3 = (double)in[q + 3 * stride];
+        mn = fmin(fmin(mn, v0), fmin(v1, fmin(v2, v3)));
+        mx = fmax(fmax(mx, v0), fmax(v1, fmax(v2, v3)));
+    }
+    for (; q < n; q += stride) {
         const double v = (double)in[q];
         mn = fmin(mn, v);
         mx = fmax(mx, v);
@@ -78,7 +87,7 @@ __global__ void minmax_final_kernel(const double* __restrict__ partial, int nb, 
 template <typename T>
 inline int minmax_device(b200reg_ctx* ctx, const T* d_in, size_t n, double* d_out, TempBuf* partial)
 {
-    const int nb = ctx->sm_count * 4;
+    const int nb = ctx->sm_count * 8;
     B200_TRY(partial->alloc(ctx, sizeof(double) * 2 * (size_t)nb));
     minmax_partial_kernel<T><<<nb, 256, 0, ctx->stream>>>(d_in, n, partial->as<double>());
     minmax_final_kernel<<<1, 32, 0, ctx->stream>>>(partial->as<double>(), nb, d_out);

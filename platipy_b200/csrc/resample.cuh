@@ -215,6 +215,43 @@ __device__ __forceinline__ void out_to_in_cidx(const GeomD& go, const GeomD& gi,
     }
 }
 
+// The same for a whole (BX, BY) thread block.  In the scan-line form everything but alpha is a property of the ROW (j, k) and alpha = i / nx
+// a property of the COLUMN, yet out_to_in_cidx evaluates both row ends (2 x (index -> point -> chain -> continuous index), ~90 FP64
+// instructions) and the division for every voxel -- ncu of the field re-gridding kernel: FP64 pipe 56 %, issue slots 69 %, the kernel is
+// bound by this arithmetic, not by its 1.6 GB of stores.  Here two threads of each row evaluate the row ends, the first row of threads
+// the BX divisions, and the block shares them through shared memory: the same operations on the same operands, once.
+// Every thread of the block must call this (it synchronises), also those outside the image.
+__device__ __forceinline__ void out_to_in_cidx_block(const GeomD& go, const GeomD& gi, const ChainD& ch, int i, int j, int k, double* c)
+{
+#ifdef RS_NO_BLOCK_SCANLINE  // A/B build: every voxel evaluates its own row ends
+    out_to_in_cidx(go, gi, ch, i, j, k, c);
+    return;
+#endif
+    if (!ch.linear) {  // uniform over the grid
+        out_to_in_cidx(go, gi, ch, i, j, k, c);
+        return;
+    }
+    __shared__ double s_end[BY][2][3];
+    __shared__ double s_alpha[BX];
+    if (threadIdx.x < 2) {
+        double p[3], e[3];
+        idx2pt(go, threadIdx.x == 0 ? 0.0 : (double)go.nx, (double)j, (double)k, p);
+        apply_chain(ch, p);
+        pt2cidx(gi, p, e);
+        s_end[threadIdx.y][threadIdx.x][0] = e[0];
+        s_end[threadIdx.y][threadIdx.x][1] = e[1];
+        s_end[threadIdx.y][threadIdx.x][2] = e[2];
+    }
+    if (threadIdx.y == 0) s_alpha[threadIdx.x] = (double)i / (double)go.nx;
+    __syncthreads();
+    const double alpha = s_alpha[threadIdx.x];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const double cs = s_end[threadIdx.y][0][r], ce = s_end[threadIdx.y][1][r];
+        c[r] = cs + alpha * (ce - cs);
+    }
+}
+
 // LinearInterpolateImageFunction::EvaluateOptimized(Dispatch<3>): nested lerps x, y, z as
 // a + (b - a) * d in double.  Base index clamped up to 0 with non-positive distances treated as 0,
 // upper neighbours clamped to the last index: bit-identical to ITK's branchy form.
@@ -536,9 +573,9 @@ __global__ void __launch_bounds__(BX* BY, BSP ? 2 : RS_MINB) resample_batch_kern
     const int i = blockIdx.x * BX + threadIdx.x;
     const int j = blockIdx.y * BY + threadIdx.y;
     const int k = blockIdx.z;
-    if (i >= go.nx || j >= go.ny) return;
     double c[3];
-    out_to_in_cidx(go, gi, ch, i, j, k, c);
+    out_to_in_cidx_block(go, gi, ch, i, j, k, c);
+    if (i >= go.nx || j >= go.ny) return;
     const bool inside = inside_buffer(gi, c);
     const size_t o = ((size_t)k * go.ny + j) * go.nx + i;
     for (int b = 0; b < batch.n; ++b) {
@@ -715,9 +752,9 @@ __global__ void __launch_bounds__(BX* BY, RS_MINB) resample_vec3_kernel(const do
     const int i = blockIdx.x * BX + threadIdx.x;
     const int j = blockIdx.y * BY + threadIdx.y;
     const int k = blockIdx.z;
-    if (i >= go.nx || j >= go.ny) return;
     double c[3];
-    out_to_in_cidx(go, gi, ch, i, j, k, c);
+    out_to_in_cidx_block(go, gi, ch, i, j, k, c);
+    if (i >= go.nx || j >= go.ny) return;
     const size_t o = ((size_t)k * go.ny + j) * go.nx + i;
     const size_t po = (size_t)go.nx * go.ny * go.nz, pi = (size_t)gi.nx * gi.ny * gi.nz;
     double v[3];
