@@ -1,5 +1,5 @@
 """Small end-to-end run of the hot path for compute-sanitizer (memcheck / racecheck / synccheck): a 3-level Demons registration at 64x56x40
-(TMA-staged smoothing, PDL launches, device-resident halt), batched label propagation (bit-packed path), weighted vote, packed STAPLE,
+(TMA-staged smoothing, PDL launches, device-resident halt), a restricted pyramid level, batched label propagation (bit-packed path), weighted vote, packed STAPLE,
 process_probability_image (union-find CCL, fill-hole) and a short linear registration with the Mattes metric (histogram atomics)."""
 import os
 import sys
@@ -19,6 +19,10 @@ eng = Engine.get(0)
 size, sp = (64, 56, 40), (1.0, 1.0, 1.5)
 fixed, moving = synth_pair(size, seed=1, spacing=sp, peak_mm=3.0)
 img, tfm, dvf = reg.fast_symmetric_forces_demons_registration(fixed, moving, resolution_staging=[4, 2, 1], iteration_staging=[6, 4, 3])
+# a level that shrinks by 8: blurred only where the level reads it (pyramid.cuh); the registered image and the level-start warp take the
+# Demons warp kernel (resample_f32_on_grid_dvf)
+reg.fast_symmetric_forces_demons_registration(fixed, moving, resolution_staging=[8, 2], iteration_staging=[3, 2])
+reg.smooth_and_resample(fixed, shrink_factor=[8, 4, 3], smoothing_sigma=[4.0, 2.0, 1.5])
 labels = [Image(l, sp) for l in synth_labels(size, 8, seed=300)]
 outs = reg.apply_transform_batch([moving] + labels, fixed, tfm, [-1000] + [0] * 8, [sk.sitkLinear] + [sk.sitkNearestNeighbor] * 8)
 atlas = {str(a): {"DIR": {"S": Image(np.roll(labels[0].array, a - 1, axis=2), sp), "Weight Map": fusion.compute_weight_map(fixed, moving, "local", fusion.DEFAULT_VOTE_PARAMS)}}
