@@ -98,6 +98,7 @@ API int b200reg_create(int device, void* stream, b200reg_ctx** out)
     if (const char* e = knob("PACK_LABELS")) ctx->pack_labels = (e[0] != '0');
     if (const char* e = knob("PDL")) ctx->pdl = (e[0] != '0');
     if (const char* e = knob("IDENTITY_COPY")) ctx->identity_copy = (e[0] != '0');
+    if (const char* e = knob("CONV_STATIC_RADIUS")) ctx->conv_static_radius = (e[0] != '0');
     if (const char* e = knob("WARP_RESAMPLE")) ctx->warp_resample = (e[0] != '0');
     if (const char* e = knob("PYRAMID_RESTRICT")) ctx->pyramid_restrict = (e[0] != '0');
     if (const char* e = knob("PYRAMID_RESTRICT_COST")) ctx->pyramid_restrict_cost = atof(e);

@@ -129,6 +129,7 @@ struct b200reg_ctx {
     double pyramid_restrict_cost = 0.6;  // B200REG_PYRAMID_RESTRICT_COST: largest restricted-work estimate (in full passes) that takes pyramid.cuh
     bool pyramid_restrict = true;  // B200REG_PYRAMID_RESTRICT=0: shrinking pyramid levels blur the whole image before resampling it (pyramid.cuh) (A/B)
     bool warp_resample = true;     // B200REG_WARP_RESAMPLE=0: a Float32 image resampled through a field on the output grid takes the generic batch kernel (A/B)
+    bool conv_static_radius = true;  // B200REG_CONV_STATIC_RADIUS=0: the Float32 Gaussian passes always take the run-time-radius kernels (A/B)
     bool identity_copy = true;     // B200REG_IDENTITY_COPY=0: identity re-grids onto an identical grid always run the resampling kernel (A/B)
     bool pdl = true;               // B200REG_PDL=0: the Demons loop kernels are launched without programmatic dependent launch (A/B)
     bool pack_labels = true;       // B200REG_PACK_LABELS=0: UInt8 nearest-neighbour items of a resample batch are gathered one byte at a time (A/B)

@@ -776,11 +776,15 @@ inline int launch_conv3d_zmarch(b200reg_ctx* ctx, const double* a, const double*
 // kernel below).  The staged row is stored 4-way interleaved -- element e at (e & 3) * CX_Q + (e >> 2) -- so that lanes, which are four
 // elements apart, read consecutive words (conflict-free); CX_Q = 4 (mod 16) keeps the staging stores conflict-free as well.
 constexpr int CX_Q = 100;  // >= (256 + 2 * KMAX_R) / 4, = 4 (mod 16)
+// RT > 0: the radius as a compile-time constant (the host dispatches the radii pyramids actually use): the tap loop unrolls completely --
+// no loop counter, no remainder loop, no register shuffling of the window.  ncu of the run-time-radius form at 512 x 512 x 256, radius 3:
+// issue slots 74-89 % busy with only 22-29 % of them FP64 -- ~98 instructions per output of which 14 are the multiply-adds.
+template <int RT>
 __global__ void __launch_bounds__(256) conv_x_f32_tiled_kernel(const float* __restrict__ in, float* __restrict__ out, int nx, int ny, int nz,
                                                                 const __grid_constant__ KernelCoeffs kc)
 {
     __shared__ double sm[4][4 * CX_Q];
-    const int r = kc.r;
+    const int r = RT > 0 ? RT : kc.r;
     const int tx = threadIdx.x, ty = threadIdx.y;
     const int x0 = blockIdx.x * 256, y = blockIdx.y * 4 + ty, z = blockIdx.z;
     const bool row_ok = y < ny;
@@ -799,17 +803,32 @@ __global__ void __launch_bounds__(256) conv_x_f32_tiled_kernel(const float* __re
     const double* w = s + tx;
     double v0 = w[0], v1 = w[CX_Q], v2 = w[2 * CX_Q], v3 = w[3 * CX_Q];
     const int last = 2 * r;
+    if (RT > 0) {
+#pragma unroll
+        for (int t = 0; t <= 2 * RT; ++t) {
+            const double kt = kc.k[t];
+            acc[0] += kt * v0;
+            acc[1] += kt * v1;
+            acc[2] += kt * v2;
+            acc[3] += kt * v3;
+            v0 = v1;
+            v1 = v2;
+            v2 = v3;
+            if (t < 2 * RT) v3 = w[((t + 4) & 3) * CX_Q + ((t + 4) >> 2)];
+        }
+    } else {
 #pragma unroll 4
-    for (int t = 0; t <= last; ++t) {
-        const double kt = kc.k[t];
-        acc[0] += kt * v0;
-        acc[1] += kt * v1;
-        acc[2] += kt * v2;
-        acc[3] += kt * v3;
-        v0 = v1;
-        v1 = v2;
-        v2 = v3;
-        if (t < last) v3 = w[((t + 4) & 3) * CX_Q + ((t + 4) >> 2)];
+        for (int t = 0; t <= last; ++t) {
+            const double kt = kc.k[t];
+            acc[0] += kt * v0;
+            acc[1] += kt * v1;
+            acc[2] += kt * v2;
+            acc[3] += kt * v3;
+            v0 = v1;
+            v1 = v2;
+            v2 = v3;
+            if (t < last) v3 = w[((t + 4) & 3) * CX_Q + ((t + 4) >> 2)];
+        }
     }
     float* o = out + row + x;
     if (x + 3 < nx && ((reinterpret_cast<uintptr_t>(o) & 15) == 0)) {
@@ -822,12 +841,12 @@ __global__ void __launch_bounds__(256) conv_x_f32_tiled_kernel(const float* __re
 }
 // AXIS 1 / 2: tile of 32 x-columns by 32 positions along the axis; each thread owns 4 consecutive positions and
 // slides over 4 + 2r staged values, feeding the four accumulators in ascending tap order.
-template <int AXIS>
+template <int AXIS, int RT>
 __global__ void __launch_bounds__(256) conv_yz_f32_tiled_kernel(const float* __restrict__ in, float* __restrict__ out, int nx, int ny, int nz,
                                                                  const __grid_constant__ KernelCoeffs kc)
 {
-    __shared__ double sm[(32 + 2 * KMAX_R) * 32];
-    const int r = kc.r;
+    __shared__ double sm[(32 + 2 * (RT > 0 ? RT : KMAX_R)) * 32];
+    const int r = RT > 0 ? RT : kc.r;
     const int n = AXIS == 1 ? ny : nz;
     const size_t sa = AXIS == 1 ? (size_t)nx : (size_t)nx * ny;
     const int lane = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -848,17 +867,32 @@ __global__ void __launch_bounds__(256) conv_yz_f32_tiled_kernel(const float* __r
     const double* col = sm + (ty * 4) * 32 + lane;
     double v0 = col[0], v1 = col[32], v2 = col[64], v3 = col[96];
     const int last = 2 * r;
+    if (RT > 0) {
+#pragma unroll
+        for (int t = 0; t <= 2 * RT; ++t) {
+            const double kt = kc.k[t];
+            acc[0] += kt * v0;
+            acc[1] += kt * v1;
+            acc[2] += kt * v2;
+            acc[3] += kt * v3;
+            v0 = v1;
+            v1 = v2;
+            v2 = v3;
+            if (t < 2 * RT) v3 = col[(t + 4) * 32];
+        }
+    } else {
 #pragma unroll 4
-    for (int t = 0; t <= last; ++t) {
-        const double kt = kc.k[t];
-        acc[0] += kt * v0;
-        acc[1] += kt * v1;
-        acc[2] += kt * v2;
-        acc[3] += kt * v3;
-        v0 = v1;
-        v1 = v2;
-        v2 = v3;
-        if (t < last) v3 = col[(t + 4) * 32];
+        for (int t = 0; t <= last; ++t) {
+            const double kt = kc.k[t];
+            acc[0] += kt * v0;
+            acc[1] += kt * v1;
+            acc[2] += kt * v2;
+            acc[3] += kt * v3;
+            v0 = v1;
+            v1 = v2;
+            v2 = v3;
+            if (t < last) v3 = col[(t + 4) * 32];
+        }
     }
     if (x < nx) {
 #pragma unroll
@@ -868,14 +902,32 @@ __global__ void __launch_bounds__(256) conv_yz_f32_tiled_kernel(const float* __r
         }
     }
 }
-inline int launch_conv_axis_f32_tiled(b200reg_ctx* ctx, int axis, const float* in, float* out, int nx, int ny, int nz, const KernelCoeffs& kc)
+template <int RT>
+inline void launch_conv_axis_f32_tiled_r(b200reg_ctx* ctx, int axis, const float* in, float* out, int nx, int ny, int nz, const KernelCoeffs& kc)
 {
     if (axis == 0) {
-        conv_x_f32_tiled_kernel<<<dim3((nx + 255) / 256, (ny + 3) / 4, nz), dim3(64, 4), 0, ctx->stream>>>(in, out, nx, ny, nz, kc);
+        conv_x_f32_tiled_kernel<RT><<<dim3((nx + 255) / 256, (ny + 3) / 4, nz), dim3(64, 4), 0, ctx->stream>>>(in, out, nx, ny, nz, kc);
     } else if (axis == 1) {
-        conv_yz_f32_tiled_kernel<1><<<dim3((nx + 31) / 32, (ny + 31) / 32, nz), 256, 0, ctx->stream>>>(in, out, nx, ny, nz, kc);
+        conv_yz_f32_tiled_kernel<1, RT><<<dim3((nx + 31) / 32, (ny + 31) / 32, nz), 256, 0, ctx->stream>>>(in, out, nx, ny, nz, kc);
     } else {
-        conv_yz_f32_tiled_kernel<2><<<dim3((nx + 31) / 32, (nz + 31) / 32, ny), 256, 0, ctx->stream>>>(in, out, nx, ny, nz, kc);
+        conv_yz_f32_tiled_kernel<2, RT><<<dim3((nx + 31) / 32, (nz + 31) / 32, ny), 256, 0, ctx->stream>>>(in, out, nx, ny, nz, kc);
+    }
+}
+inline int launch_conv_axis_f32_tiled(b200reg_ctx* ctx, int axis, const float* in, float* out, int nx, int ny, int nz, const KernelCoeffs& kc)
+{
+    // compile-time radii for what the pyramids and the fusion blur use (sigma 0.5 ... 4 voxels); any other radius takes the run-time form
+    switch (ctx->conv_static_radius ? kc.r : 0) {
+    case 1: launch_conv_axis_f32_tiled_r<1>(ctx, axis, in, out, nx, ny, nz, kc); break;
+    case 2: launch_conv_axis_f32_tiled_r<2>(ctx, axis, in, out, nx, ny, nz, kc); break;
+    case 3: launch_conv_axis_f32_tiled_r<3>(ctx, axis, in, out, nx, ny, nz, kc); break;
+    case 4: launch_conv_axis_f32_tiled_r<4>(ctx, axis, in, out, nx, ny, nz, kc); break;
+    case 5: launch_conv_axis_f32_tiled_r<5>(ctx, axis, in, out, nx, ny, nz, kc); break;
+    case 6: launch_conv_axis_f32_tiled_r<6>(ctx, axis, in, out, nx, ny, nz, kc); break;
+    case 7: launch_conv_axis_f32_tiled_r<7>(ctx, axis, in, out, nx, ny, nz, kc); break;
+    case 8: launch_conv_axis_f32_tiled_r<8>(ctx, axis, in, out, nx, ny, nz, kc); break;
+    case 10: launch_conv_axis_f32_tiled_r<10>(ctx, axis, in, out, nx, ny, nz, kc); break;
+    case 12: launch_conv_axis_f32_tiled_r<12>(ctx, axis, in, out, nx, ny, nz, kc); break;
+    default: launch_conv_axis_f32_tiled_r<0>(ctx, axis, in, out, nx, ny, nz, kc); break;
     }
     ctx->launches++;
     B200_CHECK_LAUNCH();
