@@ -855,10 +855,14 @@ __global__ void __launch_bounds__(256) conv_yz_f32_tiled_kernel(const float* __r
     const int other = blockIdx.z;               // z for AXIS 1, y for AXIS 2
     const size_t base = AXIS == 1 ? (size_t)other * nx * ny : (size_t)other * nx;
     const int xc = x < nx ? x : nx - 1;
+    // element offsets inside the volume fit 32 bits (the host sends larger volumes to the generic kernel): one base pointer, then a
+    // 32-bit multiply and one wide add per element instead of a 64-bit multiply chain
+    const float* __restrict__ pin = in + base + xc;
+    const unsigned sa32 = (unsigned)sa;
     for (int e = ty; e < 32 + 2 * r; e += 8) {
         int q = a0 - r + e;
         q = q < 0 ? 0 : (q > n - 1 ? n - 1 : q);
-        sm[e * 32 + lane] = (double)in[base + (size_t)q * sa + xc];
+        sm[e * 32 + lane] = (double)pin[(unsigned)q * sa32];
     }
     __syncthreads();
     // four consecutive outputs per thread over a sliding window of four staged values: per tap one shared load and one coefficient,
@@ -895,10 +899,11 @@ __global__ void __launch_bounds__(256) conv_yz_f32_tiled_kernel(const float* __r
         }
     }
     if (x < nx) {
+        float* __restrict__ pout = out + base + x;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
             const int q = a0 + ty * 4 + j;
-            if (q < n) out[base + (size_t)q * sa + x] = (float)acc[j];
+            if (q < n) pout[(unsigned)q * sa32] = (float)acc[j];
         }
     }
 }
@@ -952,7 +957,7 @@ inline int discrete_gaussian_f32(b200reg_ctx* ctx, const float* d_in, float* d_o
         if (use_spacing) t = t / (g.spacing[axis] * g.spacing[axis]);
         KernelCoeffs kc;
         B200_TRY(make_coeffs(gaussian_operator(t, max_error, max_width), &kc));
-        if (nz <= 65535 && ny <= 65535) B200_TRY(launch_conv_axis_f32_tiled(ctx, axis, src, dsts[pass], nx, ny, nz, kc));
+        if (nz <= 65535 && ny <= 65535 && n < (1ull << 32)) B200_TRY(launch_conv_axis_f32_tiled(ctx, axis, src, dsts[pass], nx, ny, nz, kc));
         else B200_TRY((launch_conv_axis<float, false>(ctx, axis, src, nullptr, dsts[pass], nx, ny, nz, 1, kc, nullptr, 0)));
         src = dsts[pass];
     }
