@@ -96,3 +96,19 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in text and "from oracle" not in text and "itk_oracle" not in text, f
+
+
+def test_integration_md_stub_structs_match_the_header():
+    """The ctypes stub INTEGRATION.md shows a platipy maintainer (section 3) declares the same structure layouts as include/b200reg.h
+    (through platipy_b200._abi, which test_struct_layout_matches_the_c_compiler pins against gcc)."""
+    from platipy_b200 import _abi
+
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = re.search(r"```python\nimport ctypes as C, numpy as np\n(.*?)\nlib = C\.CDLL", text, re.S).group(1)
+    ns = {"C": C}
+    exec(block, ns)
+    assert C.sizeof(ns["Geom"]) == C.sizeof(_abi.Geom)
+    assert C.sizeof(ns["DemonsParams"]) == C.sizeof(_abi.DemonsParams)
+    assert C.sizeof(ns["DemonsStats"]) == C.sizeof(_abi.DemonsStats)
+    for name, _ in _abi.DemonsParams._fields_:
+        assert getattr(ns["DemonsParams"], name).offset == getattr(_abi.DemonsParams, name).offset, name
