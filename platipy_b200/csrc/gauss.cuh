@@ -413,8 +413,11 @@ struct Zm2Layout {
     // mbarrier is bandwidth, not latency; the default stays at 2
     static constexpr int STAGES_TMA = ZM_TMA_STAGES, STAGES_CP = 2;
 };
+#ifndef ZM_MODE0_CTAS
+#define ZM_MODE0_CTAS 5  // resident CTAs per SM the plain tensor-map pass is compiled for (72 registers)
+#endif
 template <int R, int RZ, int MODE, int TXW, bool TMA>
-__global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, (TMA && MODE == 0 && TXW == 32) ? 5 : 128 / TXW) conv3d_zm2_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out,
+__global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, (TMA && MODE == 0 && TXW == 32) ? ZM_MODE0_CTAS : 128 / TXW) conv3d_zm2_kernel(const double* __restrict__ a, const double* __restrict__ b, double* __restrict__ out,
                                                                int nx, int ny, int nz, int zchunk, int nchunks,
                                                                const __grid_constant__ SmallCoeffs kc, const DemonsCtrl* __restrict__ ctrl, int it,
                                                                const __grid_constant__ CUtensorMap tmap)
@@ -442,7 +445,6 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, (TMA && MODE == 0 &
     const size_t plane = (size_t)nx * ny, vol = plane * nz;
     const double* __restrict__ ap = a + (size_t)comp * vol;
     const double* __restrict__ bp = MODE != 0 ? b + (size_t)comp * vol : nullptr;
-    double* __restrict__ op = out + (size_t)comp * vol;
 
     // cp.async path: element e of a staged plane <-> clamped global offset.  TMA path: the same slots hold, for the halo cells of a
     // border tile that lie outside the image, the shared-memory index of the replicated edge value (-1: nothing to fix).
@@ -513,7 +515,11 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, (TMA && MODE == 0 &
     const int zbeg = z0 - RZ, nsteps = (z1 - z0) + 2 * RZ;
     // offsets of this thread's four outputs inside a component volume: a running plane offset (one 64-bit add per step) plus the row
     // offsets, instead of forming z * plane + y * nx + x with wide multiplies for every store (ncu: a quarter of the loop's instructions)
-    size_t out_off = (size_t)z0 * plane + (size_t)(y0 + 4 * yb) * nx + gx;
+    // (kept as running POINTERS: with the offset relative to the component volume the compiler re-formed component * volume -- a chain of
+    // wide multiplies -- in front of every store, a dozen integer instructions per output; SASS of the round-2 build)
+    const size_t out_off0 = (size_t)comp * vol + (size_t)z0 * plane + (size_t)(y0 + 4 * yb) * nx + gx;
+    double* __restrict__ oq = out + out_off0;
+    const double* __restrict__ bq = MODE == 3 ? b + out_off0 : nullptr;
     bool okj[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) okj[j] = gx < nx && y0 + 4 * yb + j < ny;
@@ -536,7 +542,7 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, (TMA && MODE == 0 &
                 if (MODE == 3 && tid < NYZ && q >= 2 * RZ) {
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
-                        if (okj[j]) addv[j] = bp[out_off + (size_t)(j * nx)];
+                        if (okj[j]) addv[j] = bq[j * nx];
                 }
                 if (REGADD) {
                     __syncthreads();  // plane q (summed and stored at the end of step q - 1) is visible; B may be rewritten
@@ -612,9 +618,10 @@ __global__ void __launch_bounds__(Zm2Threads<R, TXW>::value, (TMA && MODE == 0 &
                         double sum = kc.k[2][0] * ring[(s + 1) % NR][j];
 #pragma unroll
                         for (int t = 1; t < NR; ++t) sum += kc.k[2][t] * ring[(s + 1 + t) % NR][j];
-                        if (okj[j]) op[out_off + (size_t)(j * nx)] = MODE == 3 ? addv[j] + sum : sum;
+                        if (okj[j]) oq[j * nx] = MODE == 3 ? addv[j] + sum : sum;
                     }
-                    out_off += plane;
+                    oq += plane;
+                    if (MODE == 3) bq += plane;
                 }
                 // MODE 2: buffer buf ^ 1 was last read by the x pass of step q - 1, two barriers ago
                 if (REGADD && q + 1 < nsteps) store_next((q + 1) % NST);
@@ -721,7 +728,7 @@ inline int launch_conv3d_zmarch(b200reg_ctx* ctx, const double* a, const double*
         // 6 chunks = 288 CTAs, all resident in one round of 15 steps, instead of three rounds of 8.
         // resident CTAs per SM: 4 at 32-wide tiles (5 for the plain tensor-map pass: 72 registers), 2 at 64-wide tiles
         const bool tma5 = txw == 32 && !b && ctx->zm_tma != 0 && (nx % 2) == 0;
-        const long slots = (long)ctx->sm_count * (txw == 32 ? (tma5 ? 5 : 4) : 2);
+        const long slots = (long)ctx->sm_count * (txw == 32 ? (tma5 ? ZM_MODE0_CTAS : 4) : 2);
         long best_cost = -1;
         int best_k = nchunks;
         for (int k = 1; k <= 32 && k <= max_chunks; ++k) {
