@@ -266,6 +266,12 @@ static int resample_batch_routed(b200reg_ctx* ctx, int n, const void* const* d_i
                                           default_values[0], &used));
         if (used) return B200REG_OK;
     }
+    if (n == 1 && d_in[0] && d_out[0] && d_in[0] != d_out[0] && interps[0] == B200REG_INTERP_NN) {
+        // one label, nearest neighbour, field on the output grid (the per-structure calls of multiatlas/run.py:338-345)
+        bool used = false;
+        B200_TRY(resample_nn_on_grid_dvf(ctx, d_in[0], dtypes[0], gin, d_out[0], gout, chain, n_chain, interps[0], default_values[0], &used));
+        if (used) return B200REG_OK;
+    }
     return resample_batch(ctx, n, d_in, dtypes, gin, d_out, gout, chain, n_chain, interps, default_values);
 }
 API int b200reg_resample_batch(b200reg_ctx* ctx, int n, const void* const* d_in, const int* dtypes, const b200reg_geom* in_geom,

@@ -99,6 +99,19 @@ def test_float32_resample_through_field_on_output_grid(engine, moving_direction)
         assert got.array.dtype == np.float32
         assert np.array_equal(got.array, exp.array), dv
         assert (got.array == np.float32(min(dv, float(np.finfo(np.float32).max)))).any()  # some points do leave the moving buffer
+    # one label at a time, nearest neighbour (the per-structure calls of multiatlas/run.py:338-345): resample_nn_on_grid_dvf, raw-bit transport
+    rng = np.random.default_rng(64)
+    for dtype, dv in ((np.uint8, 0), (np.uint8, 300), (np.int8, -7), (np.int16, -1000), (np.uint16, 70000), (np.int32, -5), (np.uint32, 7), (np.float32, -1e39)):
+        if np.issubdtype(dtype, np.integer):
+            info = np.iinfo(dtype)
+            arr = rng.integers(max(info.min, -30000), min(info.max, 30000), size=moving.array.shape).astype(dtype)
+        else:
+            arr = (rng.normal(size=moving.array.shape) * 500).astype(dtype)
+        lab = Image(arr, moving.GetSpacing(), moving.GetOrigin(), moving.GetDirection())
+        got = reg.apply_transform(lab, fixed, tfm, dv, sk.sitkNearestNeighbor)
+        exp = ref.apply_transform(lab, fixed, tfm, dv, sk.sitkNearestNeighbor)
+        assert got.array.dtype == dtype
+        assert np.array_equal(got.array, exp.array), (dtype, dv)
     # on the moving image's own grid (the level-start warp: output grid = input grid = field grid)
     dvf_m = Image(smooth_random_dvf((41, 30, 25), seed=63, peak_mm=6.0), moving.GetSpacing(), moving.GetOrigin(), IDENT, True)
     if moving_direction == IDENT:
