@@ -25,6 +25,8 @@ reg.fast_symmetric_forces_demons_registration(fixed, moving, resolution_staging=
 reg.smooth_and_resample(fixed, shrink_factor=[8, 4, 3], smoothing_sigma=[4.0, 2.0, 1.5])
 labels = [Image(l, sp) for l in synth_labels(size, 8, seed=300)]
 outs = reg.apply_transform_batch([moving] + labels, fixed, tfm, [-1000] + [0] * 8, [sk.sitkLinear] + [sk.sitkNearestNeighbor] * 8)
+one = reg.apply_transform(labels[0], fixed, tfm, 0, sk.sitkNearestNeighbor)  # single label: resample_nn_on_grid_dvf
+assert np.array_equal(one.array, outs[1].array)
 atlas = {str(a): {"DIR": {"S": Image(np.roll(labels[0].array, a - 1, axis=2), sp), "Weight Map": fusion.compute_weight_map(fixed, moving, "local", fusion.DEFAULT_VOTE_PARAMS)}}
          for a in range(3)}
 prob = fusion.combine_labels(atlas, "S")["S"]
