@@ -81,6 +81,8 @@ def _load(name):
     ("test_gpu_fusion", "test_staple_matches_oracle", ()),
     ("test_gpu_morph", "test_process_probability_image_matches_oracle", ()),
     ("test_gpu_linear", "test_masks_and_argument_errors", ()),
+    ("test_gpu_parity", "test_smooth_and_resample_parity_and_errors", ()),                                  # blur + resample as one engine call
+    ("test_gpu_parity", "test_float32_resample_through_field_on_output_grid", ((1, 0, 0, 0, 1, 0, 0, 0, 1),)),  # apply_transform, one image per call
 ])
 def test_atlas_pipeline_glue_on_the_fake_engine(fake, module, name, args):
     """run_segmentation (auto-crop, linear pre-alignment, label propagation, Demons, weight maps, vote / STAPLE exchange, paste back,
