@@ -30,6 +30,9 @@ Headline line (metric / value / e2e / roofline / cpu_baseline), BASELINE.json co
 
 "resample_cfg3" (same line; BASELINE.json configs[2]): apply_transform of one CT (linear) + 20 masks (nearest neighbour)
   through a dense f64 DVF at 512x512x256, per call and batched, with its own HBM roofline figures.
+
+"platipy_default_staging" (same line, N = 1): the headline pair registered with the reference's default arguments ([8, 4, 1] x 10
+  iterations); "fast_mode": precision="fast" beside parity mode with the error percentiles of the fast field (not a parity path).
 """
 import argparse
 import json
