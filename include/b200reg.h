@@ -167,6 +167,13 @@ int b200reg_smooth_and_resample_f32(b200reg_ctx* ctx, const float* d_in, const b
 /* GaussianOperator coefficients (host-side; used by tests): returns radius, fills kernel[0..2r] */
 int b200reg_gaussian_operator(double variance, double max_error, int max_kernel_width, double* h_kernel, int capacity);
 
+/* Host-only diagnostic (no context, no device work): 1 when sitk.Resample from in_geom onto out_geom through an identity transform
+ * provably reads voxel i for output voxel i -- every continuous index the resampler would compute (index -> point of the output grid ->
+ * continuous index of the input grid; with allow_scanline != 0 in the scan-line form of linear transforms when that semantic switch is
+ * on) equals the integer index exactly.  The library then copies instead of interpolating (utils.py:257-267 with shrink factor 1,
+ * deformable.py:185) and reads a displacement field that lives on the output grid per index (allow_scanline = 0).  0 is always safe. */
+int b200reg_identity_resample_is_exact(const b200reg_geom* in_geom, const b200reg_geom* out_geom, int allow_scanline);
+
 /* ---- N2/N5/N9: itk::ResampleImageFilter, scalar (utils.py:176-190,257-267; deformable.py:140,281-301) */
 int b200reg_resample(b200reg_ctx* ctx, const void* d_in, int dtype, const b200reg_geom* in_geom, void* d_out,
                      const b200reg_geom* out_geom, const b200reg_transform* chain, int n_chain, int interp,

@@ -76,6 +76,7 @@ SIGNATURES = {
     "b200reg_cast": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_size_t]),
     "b200reg_minmax": (C.c_int, [_P, _P, C.c_int, C.c_size_t, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "b200reg_discrete_gaussian_f32": (C.c_int, [_P, _P, _P, C.POINTER(Geom), C.POINTER(C.c_double), C.c_int, C.c_double, C.c_int]),
+    "b200reg_identity_resample_is_exact": (C.c_int, [C.POINTER(Geom), C.POINTER(Geom), C.c_int]),
     "b200reg_smooth_and_resample_f32": (C.c_int, [_P, _P, C.POINTER(Geom), C.POINTER(C.c_double), C.c_int, C.POINTER(Geom), C.c_int, _P, C.c_int]),
     "b200reg_gaussian_operator": (C.c_int, [C.c_double, C.c_double, C.c_int, C.POINTER(C.c_double), C.c_int]),
     "b200reg_resample": (C.c_int, [_P, _P, C.c_int, C.POINTER(Geom), _P, C.POINTER(Geom), C.POINTER(Transform), C.c_int, C.c_int, C.c_double]),

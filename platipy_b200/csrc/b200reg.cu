@@ -255,6 +255,13 @@ API int b200reg_gaussian_operator(double variance, double max_error, int max_ker
     return ((int)k.size() - 1) / 2;
 }
 
+// Host-only diagnostic of the proof behind the copy / per-index shortcuts (resample.cuh: identity_resample_is_exact); no context, no device.
+API int b200reg_identity_resample_is_exact(const b200reg_geom* in_geom, const b200reg_geom* out_geom, int allow_scanline)
+{
+    if (!valid_geom(in_geom) || !valid_geom(out_geom)) return 0;
+    return identity_resample_is_exact(*in_geom, *out_geom, allow_scanline != 0) ? 1 : 0;
+}
+
 // ---- N2/N5/N9 ---------------------------------------------------------------------------------------------------
 // one Float32 image, linear interpolation, one displacement field on the output grid: the Demons loop's warp kernel (demons_split.cuh)
 static int resample_batch_routed(b200reg_ctx* ctx, int n, const void* const* d_in, const int* dtypes, const b200reg_geom& gin, void* const* d_out,
